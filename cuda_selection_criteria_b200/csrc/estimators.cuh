@@ -1,0 +1,127 @@
+// estimators.cuh — fp64 arithmetic of the selection path, written once for device
+// (and host-callable for the launcher code that needs the same formulas).
+//
+// Everything here must be compiled with -fmad=false: the sequence of IEEE-754
+// double operations is then exactly the one written below (the reference is
+// g++ code whose contraction is compiler-dependent; SURVEY.md §7 "Hard parts" 1).
+//
+// Reference (paths relative to the reference tree):
+//   ertl_mle      sketch/include/sketch/hll.h:628-688 (ertl_ml_estimate), relerr=1e-2 (hll.h:212)
+//   sigma_p       include/criteria_sketch.hpp:7-20
+//   crit_cb       include/criteria_sketch.hpp:45-49, called at src/selection.cpp:282
+//   crit_hll_a    include/criteria_sketch.hpp:60-64 + 36-43 (kota_mas)
+//   crit_hll_an   include/criteria_sketch.hpp:52-58 + 22-34 (cota_n)
+//   jaccard       src/selection.cpp:287
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SELB_HD __host__ __device__ __forceinline__
+#else
+#define SELB_HD inline
+#endif
+
+namespace selb {
+
+SELB_HD int imax(int a, int b) { return a > b ? a : b; }
+SELB_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// Ertl maximum-likelihood cardinality from a register histogram c[0..q+1], q = 64-p.
+// CountT is uint32_t (global/shared histogram rows).  `stride` lets the caller keep
+// its histogram column-interleaved in shared memory.
+template <typename CountT>
+SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1) {
+    const int q = 64 - p;
+    const unsigned long long m = 1ull << p;
+    if ((unsigned long long)c[(q + 1) * stride] == m) return __builtin_huge_val();
+    int kMin, kMax;
+    for (kMin = 0; c[kMin * stride] == 0; ++kMin) {}
+    const int kMinP = imax(1, kMin);
+    for (kMax = q + 1; kMax && c[kMax * stride] == 0; --kMax) {}
+    const int kMaxP = imin(q, kMax);
+    double z = 0.;
+    for (int k = kMaxP; k >= kMinP; --k) z = 0.5 * z + (double)c[k * stride];
+    z = ldexp(z, -kMinP);
+    unsigned cP = (unsigned)c[(q + 1) * stride];
+    if (q) cP += (unsigned)c[kMaxP * stride];
+    const double a = z + (double)c[0];
+    const int mP = (int)(m - (unsigned long long)c[0]);
+    double gprev = z + ldexp((double)c[(q + 1) * stride], -q);
+    double x = gprev <= 1.5 * a ? (double)mP / (0.5 * gprev + a) : ((double)mP / gprev) * log1p(gprev / a);
+    gprev = 0.;
+    double dx = x;
+    const double relerr = 1e-2 / sqrt((double)m);
+    while (dx > x * relerr) {
+        int kappaM1;
+        frexp(x, &kappaM1);
+        double xp = ldexp(x, -imax(kMaxP + 1, kappaM1 + 2));
+        const double xp2 = xp * xp;
+        double h = xp - xp2 / 3 + (xp2 * xp2) * (1. / 45. - xp2 / 472.5);
+        for (int k = kappaM1; k >= kMaxP; --k) {
+            const double hp = 1. - h;
+            h = (xp + h * hp) / (xp + hp);
+            xp += xp;
+        }
+        double g = (double)cP * h;
+        for (int k = kMaxP - 1; k >= kMinP; --k) {
+            const double hp = 1. - h;
+            h = (xp + h * hp) / (xp + hp);
+            xp += xp;
+            g += (double)c[k * stride] * h;
+        }
+        g += x * a;
+        if (gprev < g && g <= (double)mP) dx *= (g - (double)mP) / (gprev - g);
+        else dx = 0.;
+        x += dx;
+        gprev = g;
+    }
+    return x * (double)m;
+}
+
+SELB_HD float sigma_p(int p) {
+    const double s = sqrt((double)(1 << p));
+    double c = 1.039;
+    if (p == 4) c = 1.106;
+    else if (p == 5) c = 1.07;
+    else if (p == 6) c = 1.054;
+    else if (p == 7) c = 1.046;
+    return (float)(c / s);
+}
+
+// tau is (double)(float)threshold; cardinalities are the size_t truncations.
+SELB_HD bool crit_cb(double tau, unsigned long long e1, unsigned long long e2) {
+    const double gamma = (double)e1 / (double)e2;
+    return gamma >= tau;
+}
+
+// zs = Z * sigma_p as a FLOAT product (criteria_sketch.hpp:29,32,40).
+SELB_HD bool crit_hll_a(double tau, unsigned long long e1, unsigned long long e2, double t_union, float zs) {
+    const unsigned long long t_trunc = (unsigned long long)t_union;   // size_t t_hat (:61)
+    const double t_hat = (double)t_trunc;
+    const double gamma = (double)e1 / (double)e2;
+    const double t_mas = t_hat / (1.0 + (double)zs);
+    const double k_mas = ((1.0 + gamma) * (double)e2 - t_mas) / t_mas;
+    return k_mas >= tau;
+}
+
+SELB_HD bool crit_hll_an(double tau, unsigned long long e1, unsigned long long e2, double t_hat, float zs,
+                         int order_n) {
+    const double j_hat = ((double)(e1 + e2) - t_hat) / t_hat;          // size_t sum (:55)
+    const double gamma = (double)e1 / (double)e2;
+    double S = 0., num = 1.;
+    for (int k = 1; k < order_n + 1; ++k) {
+        num *= (double)zs;
+        S += num;
+    }
+    const double lim = (1.0 + (double)zs) * (double)e2 / t_hat;
+    const double minimo = lim < 1.0 ? lim : 1.0;                        // std::min(1.0, lim)
+    const double C = minimo * (1 + gamma) * S;
+    return (j_hat + C) >= tau;
+}
+
+SELB_HD double jaccard(unsigned long long e1, unsigned long long e2, double t) {
+    return ((double)e1 + (double)e2 - t) / t;
+}
+
+}  // namespace selb

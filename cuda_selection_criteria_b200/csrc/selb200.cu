@@ -1,0 +1,1215 @@
+// selb200.cu — B200 (sm_100a) kernels + C-ABI for the all-pairs genome selection path.
+//
+// Replaces, behind include/selb200.h, the hot loop of the reference
+// (src/selection.cpp:241-291 and its CUDA restatement src/selection_kernels.cu:13-117):
+//
+//   load    : per-genome register histograms + Ertl-MLE cardinalities on the device,
+//             std::sort by cardinality on the host (tie order of selection.cpp:251-256),
+//             auxiliary sketches re-laid out in sorted order for the tile kernels
+//   run     : K2  k_cb_bounds        CB band [lo(i),hi(i)] per sorted row (binary search, fp64 div)
+//             K3  k_smh_signatures   one 32-bit signature per (genome, LSH band), transposed
+//             K4  k_tile_filter_smh  128x128 pair tiles, 8x8 register micro-tiles: XOR+MIN per band
+//                 k_smh_verify       exact uint64 band compare of the (few) candidates
+//                 k_tile_filter_hll  hll_a / hll_an: thread-per-pair aux-HLL union histogram + MLE
+//                 k_tile_enum        CB-only: every pair of the band
+//             K5  k_pair_hist        warp-per-pair HLL-14 register max + 52/64-bin histogram
+//             K6  k_estimate_emit    Ertl MLE of the union, Jaccard, tau test, warp-aggregated emit
+//             K7  cub radix sort     (i,k) order of the reference's stdout
+//
+// No tensor cores: the path is byte/integer work bounded by shared-memory and L2/HBM
+// bandwidth.  Compile with -fmad=false (see estimators.cuh).
+#include "../../include/selb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "estimators.cuh"
+
+// ============================================================================
+// error plumbing
+// ============================================================================
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(SELB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define CKR(call)                      \
+    do {                               \
+        int r__ = (call);              \
+        if (r__ != SELB200_OK) return r__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return SELB200_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SELB200_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return SELB200_OK;
+    }
+    // grow keeping the first `keep` bytes
+    int grow_keep(size_t bytes, size_t keep, cudaStream_t s) {
+        if (bytes <= cap && p) return SELB200_OK;
+        void* np = nullptr;
+        size_t want = std::max(bytes, cap * 2);
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) return fail(SELB200_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        if (p && keep) {
+            e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(np); return fail(SELB200_ECUDA, "grow copy failed: %s", cudaGetErrorString(e)); }
+        }
+        if (p) cudaFree(p);
+        p = np;
+        cap = want;
+        return SELB200_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int TILE = 128;          // pair tile edge (rows x cols of the sorted order)
+constexpr int SIG_CHUNK = 16;      // LSH bands staged per shared-memory pass
+constexpr int64_t PAIR_CAP = 8ll << 20;   // pairs per filter->union pass (list 64 MB, histograms 2 GB)
+
+}  // namespace
+
+struct selb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+
+    // loaded sketches
+    bool loaded = false;
+    int64_t n = 0;
+    int p = 0;
+    size_t m = 0;
+    const uint8_t* d_regs = nullptr;     // [n][m], file-list order (owned copy or borrowed)
+    DevBuf regs_own;
+    int aux_kind = SELB200_AUX_NONE;
+    int aux_len = 0;                     // smh: buckets m_aux; hll: p_aux
+    int64_t npad = 0;                    // n rounded up to TILE
+    DevBuf aux_sorted;                   // smh: uint64 [n][m_aux] in sorted order
+    DevBuf auxT;                         // hll: uint32 [2^p_aux/4][npad], sorted order, transposed
+    DevBuf cards_in;                     // double [n] file-list order
+    DevBuf e_sorted;                     // uint64 [n] truncated cardinalities, sorted order
+    DevBuf order_dev;                    // int32 [n] sorted pos -> file-list index
+    std::vector<double> h_cards_sorted;
+    std::vector<int32_t> h_order;
+    std::vector<uint64_t> h_e;
+
+    // run scratch (grow-only)
+    DevBuf lo, hi, tile_prefix, tile_cb0, sigT, cand, pairs, hist, counters, cub_tmp;
+    DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
+    std::vector<int32_t> h_lo, h_hi;
+    int64_t out_count = 0, near_count = 0;
+    const uint64_t* res_keys = nullptr;
+    const double* res_j = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+
+    cudaEvent_t ev() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        cudaEvent_t e = ev_pool[ev_used++];
+        cudaEventRecord(e, stream);
+        return e;
+    }
+};
+
+// ============================================================================
+// device helpers
+// ============================================================================
+namespace {
+
+// SWAR byte-wise max for bytes < 128 (HLL registers are <= 64-p+1 <= 63):
+// the top bit of each byte of (a|0x80..)-b is set iff a>=b, with no borrow between bytes;
+// PRMT in sign-replicate mode turns those bits into byte masks.  4 instructions per 4 registers
+// (__vmaxu4 is a 7-instruction emulation on sm_100a).
+__device__ __forceinline__ uint32_t max4_lt128(uint32_t a, uint32_t b) {
+    const uint32_t d = (a | 0x80808080u) - b;
+    uint32_t msk;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(msk) : "r"(d), "r"(0u), "r"(0xba98u));
+    return (a & msk) | (b & ~msk);
+}
+
+// One histogram increment.  The histogram is laid out [bin][64 threads] uint32 in the CTA's
+// static shared memory, so the byte offset of thread t's counter for register value v is
+// (v << 8) | (t * 4): a single PRMT builds it from the packed register word and tb = t*4,
+// and the shared base rides on the LDS/STS immediate.  Bank = t mod 32: conflict-free.
+template <int B>
+__device__ __forceinline__ void hist_inc(uint32_t* hist, uint32_t w, uint32_t tb) {
+    const uint32_t off = __byte_perm(w, tb, 0x5504 | (B << 4));
+    uint32_t* c = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist) + off);
+    *c += 1;
+}
+
+__device__ __forceinline__ void hist_inc_word(uint32_t* hist, uint32_t w, uint32_t tb) {
+    hist_inc<0>(hist, w, tb);
+    hist_inc<1>(hist, w, tb);
+    hist_inc<2>(hist, w, tb);
+    hist_inc<3>(hist, w, tb);
+}
+
+__device__ __forceinline__ void hist_inc_max16(uint32_t* hist, const uint4& x, const uint4& y, uint32_t tb) {
+    hist_inc_word(hist, max4_lt128(x.x, y.x), tb);
+    hist_inc_word(hist, max4_lt128(x.y, y.y), tb);
+    hist_inc_word(hist, max4_lt128(x.z, y.z), tb);
+    hist_inc_word(hist, max4_lt128(x.w, y.w), tb);
+}
+
+// Warp-aggregated slot claim: one atomicAdd per warp per call site, lanes get consecutive slots.
+__device__ __forceinline__ unsigned long long warp_claim(unsigned long long* counter) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+// ============================================================================
+// K0: register validation — max byte over a buffer (values must be <= 64-p+1)
+// ============================================================================
+__global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data, size_t n16, uint32_t* out) {
+    uint32_t mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(data + i);
+        mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+    }
+    uint32_t b = max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
+    for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
+}
+
+// ============================================================================
+// K5: warp-per-pair register max + histogram (primary HLL, m >= 512)
+//   reference: sketch/include/sketch/hll.h:1188-1206 (union_size: _mm_max_epu8 + 64-bin counts)
+//   CTA = 2 warps, each warp owns its own pairs; NB bins x 64 threads x 4 B static smem.
+//   order == nullptr: pair entries are row indices into regs; else sorted positions.
+// ============================================================================
+template <int NB>
+__global__ void __launch_bounds__(64)
+k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restrict__ order,
+            const uint2* __restrict__ pairs, long long npairs, uint32_t* __restrict__ hist_out) {
+    __shared__ __align__(16) uint32_t hist[NB * 64];
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
+#pragma unroll 4
+    for (int b = 0; b < NB; ++b) hist[b * 64 + t] = 0;
+    __syncwarp();
+    const int nchunk = (int)(m >> 9);   // 512 B per warp-wide 128-bit load
+    const long long nw = (long long)gridDim.x * 2;
+    for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
+        const uint2 pr = pairs[pi];
+        const size_t ra = order ? (size_t)order[pr.x] : (size_t)pr.x;
+        const size_t rb = order ? (size_t)order[pr.y] : (size_t)pr.y;
+        const uint4* a = reinterpret_cast<const uint4*>(regs + ra * m) + lane;
+        const uint4* b = reinterpret_cast<const uint4*>(regs + rb * m) + lane;
+        // two chunks in flight ahead of the one being histogrammed
+        uint4 x0 = __ldg(a), y0 = __ldg(b);
+        uint4 x1 = x0, y1 = y0;
+        if (nchunk > 1) { x1 = __ldg(a + 32); y1 = __ldg(b + 32); }
+        for (int c = 0; c < nchunk; ++c) {
+            uint4 x2 = x1, y2 = y1;
+            if (c + 2 < nchunk) { x2 = __ldg(a + (c + 2) * 32); y2 = __ldg(b + (c + 2) * 32); }
+            hist_inc_max16(hist, x0, y0, tb);
+            x0 = x1; y0 = y1; x1 = x2; y1 = y2;
+        }
+        __syncwarp();
+        // transposed, conflict-free column sums: lane L totals bins L and L+32, and clears them
+        uint32_t s0 = 0, s1 = 0;
+        const uint32_t cb = w * 32;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t col = cb + ((lane + r) & 31);
+            s0 += hist[lane * 64 + col];
+            hist[lane * 64 + col] = 0;
+            if (lane + 32 < NB) {
+                s1 += hist[(lane + 32) * 64 + col];
+                hist[(lane + 32) * 64 + col] = 0;
+            }
+        }
+        __syncwarp();
+        hist_out[pi * 64 + lane] = s0;
+        hist_out[pi * 64 + 32 + lane] = s1;
+    }
+}
+
+// generic small-sketch variant (aux HLL diagnostics, m < 512): warp per pair, shared atomics
+__global__ void __launch_bounds__(64)
+k_pair_hist_small(const uint8_t* __restrict__ regs, size_t m, const uint2* __restrict__ pairs, long long npairs,
+                  uint32_t* __restrict__ hist_out) {
+    __shared__ uint32_t hist[2][64];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long nw = (long long)gridDim.x * 2;
+    for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
+        hist[w][lane] = 0;
+        hist[w][lane + 32] = 0;
+        __syncwarp();
+        const uint2 pr = pairs[pi];
+        const uint8_t* a = regs + (size_t)pr.x * m;
+        const uint8_t* b = regs + (size_t)pr.y * m;
+        for (size_t j = lane; j < m; j += 32) {
+            const uint8_t r = max(a[j], b[j]);
+            atomicAdd(&hist[w][r & 63], 1u);
+        }
+        __syncwarp();
+        hist_out[pi * 64 + lane] = hist[w][lane];
+        hist_out[pi * 64 + 32 + lane] = hist[w][lane + 32];
+        __syncwarp();
+    }
+}
+
+__global__ void k_iota_pairs(uint2* pairs, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) pairs[i] = make_uint2((uint32_t)i, (uint32_t)i);
+}
+
+// per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
+__global__ void k_genome_cards(const uint32_t* __restrict__ hist, const double* __restrict__ stored, long long n,
+                               int p, double* __restrict__ cards) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (stored && stored[i] >= 0.) { cards[i] = stored[i]; return; }
+    cards[i] = selb::ertl_mle(hist + i * 64, p);
+}
+
+__global__ void k_mle_only(const uint32_t* __restrict__ hist, long long n, int p, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = selb::ertl_mle(hist + i * 64, p);
+}
+
+// ============================================================================
+// load-time re-layout
+// ============================================================================
+// dst[i][:] = src[order[i]][:], rows of row_words uint32
+__global__ void k_gather_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
+                              int row_words, uint32_t* __restrict__ dst) {
+    const long long total = n * row_words;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / row_words;
+        const int j = (int)(idx - i * row_words);
+        dst[idx] = src[(size_t)order[i] * row_words + j];
+    }
+}
+
+// auxT[j][g] = word j of the aux HLL of the g-th genome in sorted order (pad columns stay 0)
+__global__ void k_aux_transpose(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
+                                long long npad, int row_words, uint32_t* __restrict__ dst) {
+    const long long total = n * row_words;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / n);
+        const long long g = idx - (long long)j * n;
+        dst[(size_t)j * npad + g] = src[(size_t)order[g] * row_words + j];
+    }
+}
+
+// ============================================================================
+// K2: CB band per sorted row
+//   reference: src/selection.cpp:278-283 — skip e2==0, break at the first CB failure.
+//   Sorted ascending + correctly-rounded fp64 division => the passing set of row i is the
+//   contiguous range [lo(i), hi(i)], lo = max(i+1, first index with e>0).
+// ============================================================================
+__global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int zeros, double tau,
+                            int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long e1 = e[i];
+    const int l = max(i + 1, zeros);
+    int a = l, b = n;   // first k in [l,n) failing CB
+    while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (selb::crit_cb(tau, e1, e[mid])) a = mid + 1; else b = mid;
+    }
+    lo[i] = l;
+    hi[i] = a - 1;
+}
+
+// ============================================================================
+// tile lookup shared by the filter kernels
+// ============================================================================
+struct TileRef { int rb, cb; };
+
+__device__ __forceinline__ TileRef find_tile(const int32_t* __restrict__ tile_prefix,
+                                             const int32_t* __restrict__ tile_cb0, int nrb, int tile) {
+    int a = 0, b = nrb;   // last rb with tile_prefix[rb] <= tile
+    while (b - a > 1) {
+        const int mid = (a + b) >> 1;
+        if (tile_prefix[mid] <= tile) a = mid; else b = mid;
+    }
+    TileRef t;
+    t.rb = a;
+    t.cb = tile_cb0[a] + (tile - tile_prefix[a]);
+    return t;
+}
+
+// ============================================================================
+// K3: LSH band signatures.  sig[b][g] = 32-bit mix of the n_rows buckets of band b of the
+// g-th sorted genome.  Equal bands => equal signatures, so "some band equal"
+// (criteria_sketch.hpp:71-79) implies "some signature equal"; the converse is checked
+// exactly by k_smh_verify.
+// ============================================================================
+__global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long npad, int m_aux,
+                                 int n_rows, int n_bands, uint32_t* __restrict__ sigT) {
+    const long long total = n * n_bands;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / n);
+        const long long g = idx - (long long)b * n;
+        const uint64_t* v = aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows;
+        uint64_t h = 0x243F6A8885A308D3ull;
+        for (int r = 0; r < n_rows; ++r) h = mix64(h ^ v[r]);
+        sigT[(size_t)b * npad + g] = (uint32_t)(h >> 32);
+    }
+}
+
+// ============================================================================
+// K4: smh_a tile pre-filter.  One CTA = one 128x128 tile of the sorted pair space,
+// 256 threads, each an 8x8 register micro-tile.  Per band: 2+2 LDS.128, 64 x (XOR, MIN);
+// acc==0 at the end <=> some band signature matched.  Candidates (rare) leave through
+// warp-aggregated atomics.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands,
+                  const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
+                  int tile0, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                  uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
+                  unsigned long long cand_cap) {
+    __shared__ __align__(16) uint32_t sR[SIG_CHUNK][TILE];
+    __shared__ __align__(16) uint32_t sC[SIG_CHUNK][TILE];
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x);
+    const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+
+    uint32_t acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
+
+    for (int b0 = 0; b0 < n_bands; b0 += SIG_CHUNK) {
+        const int nb = min(SIG_CHUNK, n_bands - b0);
+        __syncthreads();
+        for (int idx = tid; idx < nb * TILE; idx += 256) {
+            const int bb = idx >> 7, x = idx & (TILE - 1);
+            sR[bb][x] = __ldg(sigT + (size_t)(b0 + bb) * npad + r0 + x);
+            sC[bb][x] = __ldg(sigT + (size_t)(b0 + bb) * npad + c0 + x);
+        }
+        __syncthreads();
+        for (int bb = 0; bb < nb; ++bb) {
+            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8]);
+            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8 + 4]);
+            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[bb][tx * 4]);
+            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[bb][64 + tx * 4]);
+            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = min(acc[a][b], rs[a] ^ cs[b]);
+        }
+    }
+    uint32_t any = 0xffffffffu;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) any = min(any, acc[a][b]);
+    if (any != 0) return;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int i = r0 + ty * 8 + a;
+        if (i >= n) continue;
+        const int l = lo[i], h = hi[i];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (acc[a][b] != 0) continue;
+            const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+            if (k < l || k > h) continue;
+            const unsigned long long slot = warp_claim(cand_count);
+            if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+        }
+    }
+}
+
+// exact smh_a on the candidates: include/criteria_sketch.hpp:66-81.  Warp per candidate,
+// lanes take bands round-robin and stop at the first differing bucket.
+__global__ void __launch_bounds__(256)
+k_smh_verify(const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
+             const uint2* __restrict__ cand, long long ncand, uint2* __restrict__ pairs,
+             unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ncand) return;
+    const uint2 pr = cand[warp];
+    const uint64_t* v1 = aux_sorted + (size_t)pr.x * m_aux;
+    const uint64_t* v2 = aux_sorted + (size_t)pr.y * m_aux;
+    bool hit = false;
+    for (int b = lane; b < n_bands && !hit; b += 32) {
+        bool eq = true;
+        for (int r = 0; r < n_rows; ++r)
+            if (v1[b * n_rows + r] != v2[b * n_rows + r]) { eq = false; break; }
+        hit = eq;
+    }
+    if (__any_sync(0xffffffffu, hit) && lane == 0) {
+        const unsigned long long slot = atomicAdd(pair_count, 1ull);
+        if (slot < pair_cap) pairs[slot] = pr;
+    }
+}
+
+// CB only: every pair of the band inside this tile
+__global__ void __launch_bounds__(256)
+k_tile_enum(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb, int tile0,
+            const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, uint2* __restrict__ pairs,
+            unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x);
+    const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
+    for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
+        const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
+        if (i >= n || k >= n) continue;
+        if (k < lo[i] || k > hi[i]) continue;
+        const unsigned long long slot = warp_claim(pair_count);
+        if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+    }
+}
+
+// ============================================================================
+// K4': hll_a / hll_an tile filter.  Thread per pair; lanes = 32 consecutive columns of one
+// row pair (R=2 rows share each column word).  Aux registers come transposed
+// (auxT[word][genome]) so a warp's column load is one coalesced 128 B line and the row word
+// is a broadcast.  Each thread keeps R private histograms [bin][64 threads] in static smem
+// (same PRMT addressing as k_pair_hist), then runs the Ertl MLE on its own columns and the
+// criterion:
+//   hll_a  include/criteria_sketch.hpp:60-64,36-43   hll_an  :52-58,22-34
+// One CTA (2 warps) handles a 32-row x 128-col quarter of a tile.
+// ============================================================================
+template <int AN>
+__global__ void __launch_bounds__(64)
+k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
+                  const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
+                  int tile0, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                  const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
+                  uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
+                  unsigned long long pair_cap) {
+    constexpr int NB = 64;
+    __shared__ __align__(16) uint32_t hist[2][NB * 64];
+    const int unit = blockIdx.x;
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2));
+    const int r0 = tr.rb * TILE + (unit & 3) * 32, c0 = tr.cb * TILE;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
+    const int words = (1 << p_aux) >> 2;
+    const int nbins = 64 - p_aux + 2;
+    for (int b = 0; b < NB; ++b) { hist[0][b * 64 + t] = 0; hist[1][b * 64 + t] = 0; }
+    __syncwarp();
+    // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
+    for (int item = w; item < 64; item += 2) {
+        const int i0 = r0 + (item >> 2) * 2, i1 = i0 + 1;
+        const int k = c0 + (item & 3) * 32 + (int)lane;
+        const bool v0 = i0 < n && k < n && k >= lo[min(i0, n - 1)] && k <= hi[min(i0, n - 1)];
+        const bool v1 = i1 < n && k < n && k >= lo[min(i1, n - 1)] && k <= hi[min(i1, n - 1)];
+        if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+        const uint32_t* colp = auxT + min((long long)k, npad - 1);
+        const uint32_t* row0 = auxT + min(i0, n - 1);
+        const uint32_t* row1 = auxT + min(i1, n - 1);
+#pragma unroll 2
+        for (int j = 0; j < words; ++j) {
+            const uint32_t cw = __ldg(colp + (size_t)j * npad);
+            const uint32_t a0 = __ldg(row0 + (size_t)j * npad);
+            const uint32_t a1 = __ldg(row1 + (size_t)j * npad);
+            const uint32_t m0 = max4_lt128(a0, cw), m1 = max4_lt128(a1, cw);
+            hist_inc_word(hist[0], m0, tb);
+            hist_inc_word(hist[1], m1, tb);
+        }
+        bool pass0 = false, pass1 = false;
+        if (v0) {
+            const double tu = selb::ertl_mle(&hist[0][t], p_aux, 64);
+            pass0 = AN ? selb::crit_hll_an(tau, e[i0], e[k], tu, zs, order_n)
+                       : selb::crit_hll_a(tau, e[i0], e[k], tu, zs);
+        }
+        if (v1) {
+            const double tu = selb::ertl_mle(&hist[1][t], p_aux, 64);
+            pass1 = AN ? selb::crit_hll_an(tau, e[i1], e[k], tu, zs, order_n)
+                       : selb::crit_hll_a(tau, e[i1], e[k], tu, zs);
+        }
+        for (int b = 0; b < nbins; ++b) { hist[0][b * 64 + t] = 0; hist[1][b * 64 + t] = 0; }
+        if (pass0) {
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i0, (uint32_t)k);
+        }
+        if (pass1) {
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i1, (uint32_t)k);
+        }
+    }
+}
+
+// ============================================================================
+// K6: union estimate -> Jaccard -> tau test -> emit
+//   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
+// ============================================================================
+__global__ void __launch_bounds__(128)
+k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs, long long npairs,
+                const unsigned long long* __restrict__ e, int p, double tau,
+                uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
+                unsigned long long* __restrict__ out_count, unsigned long long out_cap,
+                uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
+                unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
+    const long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pi >= npairs) return;
+    const uint2 pr = pairs[pi];
+    const double t = selb::ertl_mle(hist + pi * 64, p);
+    const double jac = selb::jaccard(e[pr.x], e[pr.y], t);
+    const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
+    if (jac >= tau) {
+        const unsigned long long slot = warp_claim(out_count);
+        if (slot < out_cap) { out_keys[slot] = key; out_j[slot] = jac; }
+    }
+    if (fabs(jac - tau) <= 1e-6 * fabs(tau)) {
+        const unsigned long long slot = warp_claim(near_count);
+        if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
+    }
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+template <typename T>
+int upload(DevBuf& buf, const std::vector<T>& v, cudaStream_t s) {
+    CKR(buf.ensure(v.size() * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SELB200_OK;
+}
+
+int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const int32_t* order,
+                     const uint2* pairs, int64_t npairs, uint32_t* hist_out) {
+    if (npairs <= 0) return SELB200_OK;
+    const int64_t ctas_needed = (npairs + 1) / 2;
+    if (m >= 512) {
+        const int nbins = 64 - p + 2;
+        if (nbins <= 52) {
+            int per_sm = 17;
+            const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
+            k_pair_hist<52><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
+        } else {
+            int per_sm = 13;
+            const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
+            k_pair_hist<64><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
+        }
+    } else {
+        if (order) return fail(SELB200_EINVAL, "small-sketch histogram takes row indices");
+        const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * 16);
+        k_pair_hist_small<<<grid, 64, 0, c->stream>>>(regs, m, pairs, npairs, hist_out);
+    }
+    CK(cudaGetLastError());
+    return SELB200_OK;
+}
+
+int validate_registers(selb200_ctx* c, const void* d_data, size_t bytes, int p, const char* what) {
+    CKR(c->counters.ensure(64));
+    CK(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    const size_t n16 = bytes / 16;
+    if (n16) {
+        const int grid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8);
+        k_max_byte<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(d_data), n16,
+                                                c->counters.as<uint32_t>());
+        CK(cudaGetLastError());
+    }
+    uint32_t mx = 0;
+    CK(cudaMemcpyAsync(&mx, c->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint32_t lim = (uint32_t)(64 - p + 1);
+    if (mx > lim)
+        return fail(SELB200_EINVAL, "%s sketch holds register value %u > %u (= 64-p+1, p=%d): not an HLL of that precision",
+                    what, mx, lim, p);
+    return SELB200_OK;
+}
+
+int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_device, const double* stored,
+            int aux_kind, int aux_len, const void* aux, bool aux_on_device) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    c->loaded = false;
+    if (n < 0 || n > 0x7fffff00ll) return fail(SELB200_EINVAL, "n=%lld out of range", (long long)n);
+    if (p < 9 || p > 20) return fail(SELB200_EINVAL, "primary HLL precision p=%d unsupported (9..20)", p);
+    if (n && !regs) return fail(SELB200_EINVAL, "null register matrix");
+    size_t aux_row_bytes = 0;
+    if (aux_kind == SELB200_AUX_SMH) {
+        if (aux_len < 1 || aux_len > 65536) return fail(SELB200_EINVAL, "smh bucket count %d out of range", aux_len);
+        aux_row_bytes = (size_t)aux_len * 8;
+    } else if (aux_kind == SELB200_AUX_HLL) {
+        if (aux_len < 4 || aux_len > 14) return fail(SELB200_EINVAL, "aux HLL precision %d unsupported (4..14)", aux_len);
+        aux_row_bytes = (size_t)1 << aux_len;
+    } else if (aux_kind != SELB200_AUX_NONE) {
+        return fail(SELB200_EINVAL, "unknown aux kind %d", aux_kind);
+    }
+    if (aux_kind != SELB200_AUX_NONE && n && !aux) return fail(SELB200_EINVAL, "null aux matrix");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    c->n = n; c->p = p; c->m = (size_t)1 << p;
+    c->aux_kind = aux_kind; c->aux_len = aux_len;
+    c->npad = (n + TILE - 1) / TILE * TILE;
+    c->h_cards_sorted.assign((size_t)n, 0.);
+    c->h_order.assign((size_t)n, 0);
+    c->h_e.assign((size_t)n, 0);
+    c->out_count = c->near_count = 0;
+    if (n == 0) { c->loaded = true; return SELB200_OK; }
+
+    const size_t reg_bytes = (size_t)n * c->m;
+    if (regs_on_device) {
+        c->d_regs = regs;
+    } else {
+        CKR(c->regs_own.ensure(reg_bytes));
+        CK(cudaMemcpyAsync(c->regs_own.p, regs, reg_bytes, cudaMemcpyHostToDevice, s));
+        c->d_regs = c->regs_own.as<uint8_t>();
+    }
+    // auxiliary sketches: staged in `cand` scratch when they arrive from the host
+    const void* d_aux = aux;
+    if (aux_kind != SELB200_AUX_NONE && !aux_on_device) {
+        CKR(c->cand.ensure((size_t)n * aux_row_bytes));
+        CK(cudaMemcpyAsync(c->cand.p, aux, (size_t)n * aux_row_bytes, cudaMemcpyHostToDevice, s));
+        d_aux = c->cand.p;
+    }
+    CKR(validate_registers(c, c->d_regs, reg_bytes, p, "primary"));
+    if (aux_kind == SELB200_AUX_HLL) CKR(validate_registers(c, d_aux, (size_t)n * aux_row_bytes, aux_len, "auxiliary"));
+
+    // per-genome histogram -> cardinality (device), then the reference's host sort
+    CKR(c->pairs.ensure((size_t)n * sizeof(uint2)));
+    CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
+    CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
+    k_iota_pairs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->pairs.as<uint2>(), n);
+    CK(cudaGetLastError());
+    CKR(launch_pair_hist(c, c->d_regs, c->m, p, nullptr, c->pairs.as<uint2>(), n, c->hist.as<uint32_t>()));
+    double* d_stored = nullptr;
+    if (stored) {
+        CKR(c->out_j.ensure((size_t)n * sizeof(double)));
+        CK(cudaMemcpyAsync(c->out_j.p, stored, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+        d_stored = c->out_j.as<double>();
+    }
+    k_genome_cards<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->hist.as<uint32_t>(), d_stored, n, p,
+                                                               c->cards_in.as<double>());
+    CK(cudaGetLastError());
+    std::vector<double> cards((size_t)n);
+    CK(cudaMemcpyAsync(cards.data(), c->cards_in.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    selb200_sort_order(n, cards.data(), c->h_order.data());
+    for (int64_t i = 0; i < n; ++i) {
+        const double cd = cards[(size_t)c->h_order[(size_t)i]];
+        c->h_cards_sorted[(size_t)i] = cd;
+        c->h_e[(size_t)i] = (uint64_t)(size_t)cd;       // size_t e = card (selection.cpp:275,280)
+    }
+    CKR(upload(c->order_dev, c->h_order, s));
+    CKR(upload(c->e_sorted, c->h_e, s));
+
+    if (aux_kind == SELB200_AUX_SMH) {
+        CKR(c->aux_sorted.ensure((size_t)n * aux_row_bytes));
+        const int row_words = (int)(aux_row_bytes / 4);
+        const int grid = (int)std::min<int64_t>((n * row_words + 255) / 256, (int64_t)c->sm_count * 16);
+        k_gather_rows<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_aux), c->order_dev.as<int32_t>(), n,
+                                           row_words, c->aux_sorted.as<uint32_t>());
+        CK(cudaGetLastError());
+    } else if (aux_kind == SELB200_AUX_HLL) {
+        const int row_words = (int)(aux_row_bytes / 4);
+        CKR(c->auxT.ensure((size_t)row_words * c->npad * 4));
+        CK(cudaMemsetAsync(c->auxT.p, 0, (size_t)row_words * c->npad * 4, s));
+        const int grid = (int)std::min<int64_t>((n * row_words + 255) / 256, (int64_t)c->sm_count * 16);
+        k_aux_transpose<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_aux), c->order_dev.as<int32_t>(), n,
+                                             c->npad, row_words, c->auxT.as<uint32_t>());
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(s));
+    c->loaded = true;
+    return SELB200_OK;
+}
+
+}  // namespace
+
+// ============================================================================
+// C-ABI
+// ============================================================================
+extern "C" {
+
+int selb200_abi_version(void) { return SELB200_ABI_VERSION; }
+const char* selb200_last_error(void) { return g_err.c_str(); }
+
+int selb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int selb200_create(int device, void* stream, selb200_ctx** out) {
+    if (!out) return fail(SELB200_EINVAL, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SELB200_ECUDA, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(SELB200_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+    CK(cudaSetDevice(device));
+    selb200_ctx* c = new selb200_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return fail(SELB200_ECUDA, "cudaStreamCreate failed");
+        }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return SELB200_OK;
+}
+
+void selb200_destroy(selb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
+                      &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->sigT, &c->cand, &c->pairs, &c->hist,
+                      &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
+                      &c->near_keys, &c->near_j};
+    for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int selb200_load_host(selb200_ctx* ctx, int64_t n, int p, const uint8_t* regs, const double* stored,
+                      int aux_kind, int aux_len, const void* aux) {
+    return do_load(ctx, n, p, regs, false, stored, aux_kind, aux_len, aux, false);
+}
+
+int selb200_load_device(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_regs, const double* stored_host,
+                        int aux_kind, int aux_len, const void* d_aux) {
+    return do_load(ctx, n, p, d_regs, true, stored_host, aux_kind, aux_len, d_aux, true);
+}
+
+int selb200_get_order(selb200_ctx* c, double* cards_sorted, int32_t* order) {
+    if (!c || !c->loaded) return fail(SELB200_ESTATE, "no sketches loaded");
+    if (cards_sorted) std::memcpy(cards_sorted, c->h_cards_sorted.data(), (size_t)c->n * sizeof(double));
+    if (order) std::memcpy(order, c->h_order.data(), (size_t)c->n * sizeof(int32_t));
+    return SELB200_OK;
+}
+
+void selb200_default_params(selb200_params* p) {
+    std::memset(p, 0, sizeof *p);
+    p->tau = 0.9f;
+    p->criterion = SELB200_CRIT_SMH_A;
+    p->z_score = 1.96f;
+    p->order_n = 1;
+    p->n_shards = 1;
+    p->sort_output = 1;
+}
+
+int selb200_band_params(int m, float tau, int cpu_variant, int* n_bands, int* n_rows) {
+    if (m < 1 || !n_bands || !n_rows) return fail(SELB200_EINVAL, "bad band-search arguments");
+    int nb = 1, nr = 1;
+    for (int band = 1; band <= m; ++band) {
+        if (m % band != 0) continue;
+        if (cpu_variant) { nb = band; nr = m / band; }
+        const double inner = std::pow((double)tau, (double)((float)m / (float)band));
+        const float P_r = (float)(1.0 - std::pow(1.0 - inner, (double)(float)band));
+        if (P_r >= 0.95) {
+            if (!cpu_variant) { nb = band; nr = m / band; }
+            break;
+        }
+    }
+    *n_bands = nb;
+    *n_rows = nr;
+    return SELB200_OK;
+}
+
+int selb200_sort_order(int64_t n, const double* cards, int32_t* order) {
+    if (n < 0 || (n && (!cards || !order))) return fail(SELB200_EINVAL, "bad sort arguments");
+    std::vector<std::pair<int32_t, double>> v((size_t)n);
+    for (int64_t i = 0; i < n; ++i) v[(size_t)i] = {(int32_t)i, cards[i]};
+    std::sort(v.begin(), v.end(),
+              [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y) { return x.second < y.second; });
+    for (int64_t i = 0; i < n; ++i) order[i] = v[(size_t)i].first;
+    return SELB200_OK;
+}
+
+int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out) {
+    if (!c || !prm) return fail(SELB200_EINVAL, "null argument");
+    if (!c->loaded) return fail(SELB200_ESTATE, "selb200_run before a successful load");
+    const int crit = prm->criterion;
+    if (crit < SELB200_CRIT_CB || crit > SELB200_CRIT_HLL_AN) return fail(SELB200_EINVAL, "unknown criterion %d", crit);
+    if (crit == SELB200_CRIT_SMH_A && c->aux_kind != SELB200_AUX_SMH)
+        return fail(SELB200_ESTATE, "criterion smh_a needs SuperMinHash auxiliary sketches");
+    if ((crit == SELB200_CRIT_HLL_A || crit == SELB200_CRIT_HLL_AN) && c->aux_kind != SELB200_AUX_HLL)
+        return fail(SELB200_ESTATE, "criterion hll_a/hll_an needs auxiliary HLL sketches");
+    const int n_shards = prm->n_shards > 0 ? prm->n_shards : 1;
+    if (prm->shard < 0 || prm->shard >= n_shards) return fail(SELB200_EINVAL, "shard %d of %d", prm->shard, n_shards);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    selb200_stats st;
+    std::memset(&st, 0, sizeof st);
+    const int n = (int)c->n;
+    st.n = n;
+    st.pairs_total = (int64_t)n * (n - 1) / 2;
+    c->out_count = c->near_count = 0;
+    c->res_keys = nullptr; c->res_j = nullptr;
+    c->ev_used = 0;
+    if (n < 2) { if (st_out) *st_out = st; return SELB200_OK; }
+    const double tau = (double)prm->tau;
+
+    int n_rows = prm->n_rows, n_bands = prm->n_bands;
+    bool smh_shape_ok = true;
+    if (crit == SELB200_CRIT_SMH_A) {
+        if (n_rows <= 0 || n_bands <= 0) selb200_band_params(c->aux_len, prm->tau, 1, &n_bands, &n_rows);
+        // criteria_sketch.hpp:67-70: a shape that does not tile the sketch selects nothing
+        smh_shape_ok = (int64_t)n_rows * n_bands == c->aux_len;
+        st.n_rows = n_rows; st.n_bands = n_bands;
+    }
+
+    cudaEvent_t ev_begin = c->ev();
+    // ---- K2: CB band ---------------------------------------------------------
+    int zeros = 0;
+    while (zeros < n && c->h_e[(size_t)zeros] == 0) ++zeros;
+    CKR(c->lo.ensure((size_t)n * 4));
+    CKR(c->hi.ensure((size_t)n * 4));
+    k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau,
+                                                c->lo.as<int32_t>(), c->hi.as<int32_t>());
+    CK(cudaGetLastError());
+    st.launches++;
+    c->h_lo.resize((size_t)n); c->h_hi.resize((size_t)n);
+    CK(cudaMemcpyAsync(c->h_lo.data(), c->lo.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_hi.data(), c->hi.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    cudaEvent_t ev_bounds = c->ev();
+    CK(cudaStreamSynchronize(s));
+
+    // ---- tile list (host, O(n)) --------------------------------------------------
+    const int nrb = (n + TILE - 1) / TILE;
+    std::vector<int32_t> tprefix((size_t)nrb + 1, 0), tcb0((size_t)nrb, 0);
+    std::vector<int64_t> rb_pairs((size_t)nrb, 0);
+    int64_t pairs_cb = 0;
+    for (int rb = 0; rb < nrb; ++rb) {
+        int cmin = INT32_MAX, cmax = -1;
+        int64_t cnt = 0;
+        const int r1 = std::min(n, (rb + 1) * TILE);
+        for (int i = rb * TILE; i < r1; ++i) {
+            const int l = c->h_lo[(size_t)i], h = c->h_hi[(size_t)i];
+            if (h < l) continue;
+            cnt += h - l + 1;
+            cmin = std::min(cmin, l);
+            cmax = std::max(cmax, h);
+        }
+        int nt = 0;
+        if (cnt) { tcb0[(size_t)rb] = cmin / TILE; nt = cmax / TILE - cmin / TILE + 1; }
+        rb_pairs[(size_t)rb] = cnt;
+        pairs_cb += cnt;
+        tprefix[(size_t)rb + 1] = tprefix[(size_t)rb] + nt;
+    }
+    const int tiles_total = tprefix[(size_t)nrb];
+    st.pairs_cb = pairs_cb;
+    st.tiles_total = tiles_total;
+    const int t_begin = (int)((int64_t)tiles_total * prm->shard / n_shards);
+    const int t_end = (int)((int64_t)tiles_total * (prm->shard + 1) / n_shards);
+    st.tiles_shard = t_end - t_begin;
+    CKR(upload(c->tile_prefix, tprefix, s));
+    CKR(upload(c->tile_cb0, tcb0, s));
+
+    // counters: [0] candidates, [1] pairs, [2] out, [3] near
+    CKR(c->counters.ensure(64));
+    CK(cudaMemsetAsync(c->counters.p, 0, 64, s));
+    unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+
+    // ---- K3: signatures ---------------------------------------------------------------
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_filter, t_verify, t_union, t_est;
+    if (crit == SELB200_CRIT_SMH_A && smh_shape_ok) {
+        cudaEvent_t a = c->ev();
+        CKR(c->sigT.ensure((size_t)n_bands * c->npad * 4));
+        CK(cudaMemsetAsync(c->sigT.p, 0, (size_t)n_bands * c->npad * 4, s));
+        const int grid = (int)std::min<int64_t>(((int64_t)n * n_bands + 255) / 256, (int64_t)c->sm_count * 16);
+        k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
+                                              c->sigT.as<uint32_t>());
+        CK(cudaGetLastError());
+        st.launches++;
+        t_filter.push_back({a, c->ev()});
+    }
+
+    CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
+    CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
+    CKR(c->near_keys.ensure((size_t)(1 << 16) * 8));
+    CKR(c->near_j.ensure((size_t)(1 << 16) * 8));
+    const unsigned long long near_cap = 1ull << 16;
+    const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
+
+    // ---- filter -> union passes over tile ranges ---------------------------------------
+    std::vector<std::pair<int, int>> work;   // stack of [a,b) tile ranges
+    if (smh_shape_ok && t_end > t_begin) {
+        // CB-only fills whole tiles, so cut ranges the pair list is sure to hold; the
+        // selective criteria start with the whole shard and split on overflow.
+        const int step = (crit == SELB200_CRIT_CB) ? (int)(PAIR_CAP / (TILE * TILE)) : (t_end - t_begin);
+        for (int a = t_end; a > t_begin;) {
+            const int b = a;
+            a = std::max(t_begin, a - step);
+            work.push_back({a, b});
+        }
+    }
+    int64_t total_out = 0;
+    while (!work.empty()) {
+        const std::pair<int, int> rg = work.back();
+        work.pop_back();
+        const int nt = rg.second - rg.first;
+        CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs
+        cudaEvent_t f0 = c->ev();
+        if (crit == SELB200_CRIT_SMH_A) {
+            k_tile_filter_smh<<<nt, 256, 0, s>>>(c->sigT.as<uint32_t>(), c->npad, n_bands, c->tile_prefix.as<int32_t>(),
+                                                 c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(),
+                                                 c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0,
+                                                 (unsigned long long)PAIR_CAP);
+        } else if (crit == SELB200_CRIT_CB) {
+            k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first,
+                                           c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
+                                           d_cnt + 1, (unsigned long long)PAIR_CAP);
+        } else if (crit == SELB200_CRIT_HLL_A) {
+            k_tile_filter_hll<0><<<nt * 4, 64, 0, s>>>(
+                c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
+                nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
+                zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
+        } else {
+            k_tile_filter_hll<1><<<nt * 4, 64, 0, s>>>(
+                c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
+                nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
+                zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
+        }
+        CK(cudaGetLastError());
+        st.launches++;
+        cudaEvent_t f1 = c->ev();
+        unsigned long long h_cnt[2] = {0, 0};
+        if (crit == SELB200_CRIT_SMH_A) {
+            CK(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h_cnt[0] > (unsigned long long)PAIR_CAP) {
+                if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %llu candidates", h_cnt[0]);
+                const int mid = rg.first + nt / 2;
+                work.push_back({mid, rg.second});
+                work.push_back({rg.first, mid});
+                continue;
+            }
+            t_filter.push_back({f0, f1});
+            st.pairs_cand += (int64_t)h_cnt[0];
+            if (h_cnt[0]) {
+                const long long nc = (long long)h_cnt[0];
+                k_smh_verify<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s>>>(
+                    c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, c->cand.as<uint2>(), nc,
+                    c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
+                CK(cudaGetLastError());
+                st.launches++;
+                t_verify.push_back({f1, c->ev()});
+            }
+        }
+        CK(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const long long np = (long long)h_cnt[1];
+        if (np > PAIR_CAP) {
+            if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %lld pairs", np);
+            const int mid = rg.first + nt / 2;
+            work.push_back({mid, rg.second});
+            work.push_back({rg.first, mid});
+            continue;
+        }
+        if (crit != SELB200_CRIT_SMH_A) { t_filter.push_back({f0, f1}); st.pairs_cand += np; }
+        st.pairs_aux += np;
+        st.batches++;
+        if (np == 0) continue;
+        // ---- K5 + K6 ------------------------------------------------------------------
+        CKR(c->hist.ensure((size_t)np * 64 * sizeof(uint32_t)));
+        const size_t need = (size_t)(total_out + np);
+        CKR(c->out_keys.grow_keep(need * 8, (size_t)total_out * 8, s));
+        CKR(c->out_j.grow_keep(need * 8, (size_t)total_out * 8, s));
+        cudaEvent_t u0 = c->ev();
+        CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(), np,
+                             c->hist.as<uint32_t>()));
+        st.launches++;
+        cudaEvent_t u1 = c->ev();
+        k_estimate_emit<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(
+            c->hist.as<uint32_t>(), c->pairs.as<uint2>(), np, c->e_sorted.as<unsigned long long>(), c->p, tau,
+            c->out_keys.as<uint64_t>(), c->out_j.as<double>(), d_cnt + 2, (unsigned long long)need,
+            c->near_keys.as<uint64_t>(), c->near_j.as<double>(), d_cnt + 3, near_cap);
+        CK(cudaGetLastError());
+        st.launches++;
+        cudaEvent_t u2 = c->ev();
+        t_union.push_back({u0, u1});
+        t_est.push_back({u1, u2});
+        unsigned long long h_out = 0;
+        CK(cudaMemcpyAsync(&h_out, d_cnt + 2, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        total_out = (int64_t)h_out;
+    }
+    unsigned long long h_fin[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_fin, d_cnt, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->out_count = (int64_t)h_fin[2];
+    c->near_count = (int64_t)std::min<unsigned long long>(h_fin[3], near_cap);
+    st.pairs_out = c->out_count;
+    st.pairs_near = (int64_t)h_fin[3];
+
+    // ---- K7: reference print order -----------------------------------------------------------
+    cudaEvent_t s0 = c->ev();
+    c->res_keys = c->out_keys.as<uint64_t>();
+    c->res_j = c->out_j.as<double>();
+    if (prm->sort_output && c->out_count > 1) {
+        const int64_t cnt = c->out_count;
+        CKR(c->out_keys2.ensure((size_t)cnt * 8));
+        CKR(c->out_j2.ensure((size_t)cnt * 8));
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->out_keys.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
+                                           c->out_j.as<double>(), c->out_j2.as<double>(), (int)cnt, 0, 64, s));
+        CKR(c->cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->out_keys.as<uint64_t>(),
+                                           c->out_keys2.as<uint64_t>(), c->out_j.as<double>(), c->out_j2.as<double>(),
+                                           (int)cnt, 0, 64, s));
+        c->res_keys = c->out_keys2.as<uint64_t>();
+        c->res_j = c->out_j2.as<double>();
+    }
+    cudaEvent_t ev_end = c->ev();
+    CK(cudaStreamSynchronize(s));
+
+    auto sum_ms = [](const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+        float tot = 0.f;
+        for (const auto& pr : v) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) tot += ms;
+        }
+        return tot;
+    };
+    cudaEventElapsedTime(&st.ms_bounds, ev_begin, ev_bounds);
+    st.ms_filter = sum_ms(t_filter);
+    st.ms_verify = sum_ms(t_verify);
+    st.ms_union = sum_ms(t_union);
+    st.ms_estimate = sum_ms(t_est);
+    cudaEventElapsedTime(&st.ms_sort, s0, ev_end);
+    cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end);
+    // shard share of the CB band: pairs of the shard's tiles (whole row blocks are exact,
+    // split row blocks are apportioned by tile count)
+    {
+        double acc = 0.;
+        for (int rb = 0; rb < nrb; ++rb) {
+            const int a = std::max(tprefix[(size_t)rb], t_begin), b = std::min(tprefix[(size_t)rb + 1], t_end);
+            const int ntl = tprefix[(size_t)rb + 1] - tprefix[(size_t)rb];
+            if (b > a && ntl > 0) acc += (double)rb_pairs[(size_t)rb] * (double)(b - a) / (double)ntl;
+        }
+        st.pairs_cb_shard = (int64_t)(acc + 0.5);
+    }
+    if (st_out) *st_out = st;
+    return SELB200_OK;
+}
+
+int64_t selb200_result_count(selb200_ctx* c) { return c ? c->out_count : 0; }
+int64_t selb200_near_count(selb200_ctx* c) { return c ? c->near_count : 0; }
+
+static int copy_list(selb200_ctx* c, const uint64_t* d_keys, const double* d_j, int64_t count, int64_t cap,
+                     int32_t* i, int32_t* k, double* jac) {
+    const int64_t cnt = std::min(count, cap);
+    if (cnt <= 0) return SELB200_OK;
+    CK(cudaSetDevice(c->device));
+    std::vector<uint64_t> keys((size_t)cnt);
+    CK(cudaMemcpyAsync(keys.data(), d_keys, (size_t)cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (jac) CK(cudaMemcpyAsync(jac, d_j, (size_t)cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t t = 0; t < cnt; ++t) {
+        if (i) i[t] = (int32_t)(keys[(size_t)t] >> 32);
+        if (k) k[t] = (int32_t)(keys[(size_t)t] & 0xffffffffu);
+    }
+    return SELB200_OK;
+}
+
+int selb200_copy_results(selb200_ctx* c, int64_t cap, int32_t* i, int32_t* k, double* jaccard) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    return copy_list(c, c->res_keys, c->res_j, c->out_count, cap, i, k, jaccard);
+}
+
+int selb200_copy_near(selb200_ctx* c, int64_t cap, int32_t* i, int32_t* k, double* jaccard) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    return copy_list(c, c->near_keys.as<uint64_t>(), c->near_j.as<double>(), c->near_count, cap, i, k, jaccard);
+}
+
+int selb200_result_device(selb200_ctx* c, const uint64_t** d_keys, const double** d_jaccard) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    if (d_keys) *d_keys = c->res_keys;
+    if (d_jaccard) *d_jaccard = c->res_j;
+    return SELB200_OK;
+}
+
+int selb200_debug_union(selb200_ctx* c, int which, int64_t count, const int32_t* a, const int32_t* b, double* t) {
+    if (!c || !c->loaded) return fail(SELB200_ESTATE, "no sketches loaded");
+    if (count <= 0) return SELB200_OK;
+    if (which != 0) return fail(SELB200_EINVAL, "debug_union: only the primary sketches are addressable");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    std::vector<uint2> pr((size_t)count);
+    for (int64_t x = 0; x < count; ++x) {
+        if (a[x] < 0 || a[x] >= c->n || b[x] < 0 || b[x] >= c->n) return fail(SELB200_EINVAL, "pair index out of range");
+        pr[(size_t)x] = make_uint2((uint32_t)a[x], (uint32_t)b[x]);
+    }
+    CKR(upload(c->pairs, pr, s));
+    CKR(c->hist.ensure((size_t)count * 64 * 4));
+    CKR(c->out_j.ensure((size_t)count * 8));
+    CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, nullptr, c->pairs.as<uint2>(), count, c->hist.as<uint32_t>()));
+    k_mle_only<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(c->hist.as<uint32_t>(), count, c->p, c->out_j.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(t, c->out_j.p, (size_t)count * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->out_count = 0;
+    return SELB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE — builds the UNMODIFIED reference CPU driver (src/selection.cpp,
+# OpenMP) from the sources where they lie under /root/reference into oracle/_ref/.
+# No reference source is copied into this repo; only the binary lands in oracle/_ref/
+# (git-ignored, but it travels to the GPU box with gpurun).
+#
+# We do not run the reference's own Makefile: it uses -march=native, which fails on
+# AVX-512 hosts at sketch/include/sketch/bbmh.h:1499. Flags otherwise
+# follow the reference Makefile:32-33 (CXXFLAGS) and :39 (LDFLAGS_CPU).
+set -euo pipefail
+REF="${REFERENCE_ROOT:-/root/reference}"
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+if [ ! -f "$REF/src/selection.cpp" ]; then
+  echo "build_ref: $REF not present; keeping any prebuilt $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+if [ "$OUT/selection" -nt "$REF/src/selection.cpp" ] && [ "${FORCE:-0}" != "1" ]; then
+  echo "build_ref: $OUT/selection up to date"
+  exit 0
+fi
+cd "$REF"
+g++ -O3 -std=c++17 -march=x86-64-v3 -fopenmp -DSEQAN_HAS_ZLIB=1 -DNDEBUG -w \
+    -I. -Isketch -Isketch/include -Isketch/include/blaze \
+    -Iseqan-library-2.4.0/include -Iinclude \
+    src/selection.cpp -lz -pthread -o "$OUT/selection"
+echo "build_ref: built $OUT/selection"

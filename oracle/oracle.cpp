@@ -1,0 +1,315 @@
+// ============================================================================
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// CPU restatement ("oracle") of the reference's all-pairs selection hot path
+// (sanhue903/CUDA_Selection_Criteria), used ONLY by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs
+// as the checker.  Nothing under cuda_selection_criteria_b200/ may import, link or
+// call it; the product path fails loudly when its CUDA library is missing.
+//
+// Parity pin: this restatement is checked (tests/test_oracle_pin.py) against
+//   * the reference's golden output results.txt:1-7 on the shipped influenza
+//     sketch fixtures (copied as data under tests/golden/influenza/), and
+//   * outputs of the UNMODIFIED reference binary (oracle/_ref/selection, built by
+//     oracle/build_ref.sh from /root/reference/src/selection.cpp) on synthetic
+//     inputs, committed under tests/golden/ref_outputs/ by tests/golden/make_golden.py.
+//
+// Every function cites the reference file:line it restates (paths relative to
+// /root/reference).  It is written from the algorithm description in SURVEY.md
+// Appendix A; no reference source is copied.
+//
+// Build: g++ -O2 -std=c++17 -fopenmp -shared -fPIC oracle.cpp -o liboracle.so
+// (deliberately NOT -march=...: no FMA contraction, so the arithmetic is plain
+// IEEE-754 double, the same sequence the device code issues with -fmad=false).
+// ============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// sketch/include/sketch/hll.h:564-581 (sum_counts) — 64-bin histogram of the
+// one-byte registers.
+void hist64(const uint8_t* regs, size_t m, uint32_t* c) {
+    std::memset(c, 0, 64 * sizeof(uint32_t));
+    for (size_t j = 0; j < m; ++j) ++c[regs[j] & 63];
+}
+
+// sketch/include/sketch/hll.h:1188-1206 (union_size, SSE2 branch): register-wise
+// max of the two sketches, histogrammed.
+void hist64_union(const uint8_t* a, const uint8_t* b, size_t m, uint32_t* c) {
+    std::memset(c, 0, 64 * sizeof(uint32_t));
+    for (size_t j = 0; j < m; ++j) {
+        uint8_t r = a[j] > b[j] ? a[j] : b[j];
+        ++c[r & 63];
+    }
+}
+
+// sketch/include/sketch/hll.h:628-688 (ertl_ml_estimate) with relerr=1e-2
+// (hll.h:212 default, passed through calculate_estimate hll.h:255-258).
+// Integer types follow the reference: `int mPrime`, `unsigned cPrime`.
+double ertl_mle(const uint32_t* c, unsigned p) {
+    const unsigned q = 64 - p;                       // hll.h:1096
+    const uint64_t m = 1ull << p;
+    if (c[q + 1] == m) return std::numeric_limits<double>::infinity();
+    int kMin, kMax;
+    for (kMin = 0; c[kMin] == 0; ++kMin) {}
+    const int kMinP = std::max(1, kMin);
+    for (kMax = (int)q + 1; kMax && c[kMax] == 0; --kMax) {}
+    const int kMaxP = std::min((int)q, kMax);
+    double z = 0.;
+    for (int k = kMaxP; k >= kMinP; --k) z = 0.5 * z + c[k];
+    z = std::ldexp(z, -kMinP);
+    unsigned cP = c[q + 1];
+    if (q) cP += c[kMaxP];
+    const double a = z + c[0];
+    const int mP = (int)(m - c[0]);
+    double gprev = z + std::ldexp((double)c[q + 1], -(int)q);
+    double x = gprev <= 1.5 * a ? mP / (0.5 * gprev + a) : (mP / gprev) * std::log1p(gprev / a);
+    gprev = 0;
+    double dx = x;
+    const double relerr = 1e-2 / std::sqrt((double)m);
+    while (dx > x * relerr) {
+        int kappaM1;
+        std::frexp(x, &kappaM1);
+        double xp = std::ldexp(x, -std::max(kMaxP + 1, kappaM1 + 2));
+        const double xp2 = xp * xp;
+        double h = xp - xp2 / 3 + (xp2 * xp2) * (1. / 45. - xp2 / 472.5);
+        for (int k = kappaM1; k >= kMaxP; --k) {
+            const double hp = 1. - h;
+            h = (xp + h * hp) / (xp + hp);
+            xp += xp;
+        }
+        double g = cP * h;
+        for (int k = kMaxP - 1; k >= kMinP; --k) {
+            const double hp = 1. - h;
+            h = (xp + h * hp) / (xp + hp);
+            xp += xp;
+            g += c[k] * h;
+        }
+        g += x * a;
+        if (gprev < g && g <= mP) dx *= (g - mP) / (gprev - g);
+        else dx = 0;
+        x += dx;
+        gprev = g;
+    }
+    return x * m;
+}
+
+// include/criteria_sketch.hpp:7-20 (sigma): double expression narrowed to float.
+float sigma_p(int p) {
+    const double s = std::sqrt((double)(1 << p));
+    switch (p) {
+        case 4: return (float)(1.106 / s);
+        case 5: return (float)(1.07 / s);
+        case 6: return (float)(1.054 / s);
+        case 7: return (float)(1.046 / s);
+    }
+    return (float)(1.039 / s);
+}
+
+// include/criteria_sketch.hpp:45-49 (CB) as called from src/selection.cpp:282:
+// tau arrives as (double)(float)threshold, cardinalities as size_t -> double.
+bool cb(double tau, uint64_t e1, uint64_t e2) {
+    const double gamma = (double)e1 / (double)e2;
+    return gamma >= tau;
+}
+
+// include/criteria_sketch.hpp:66-81 (smh_a): any band whose n_rows buckets are all equal.
+bool smh_a(const uint64_t* v1, const uint64_t* v2, unsigned m, unsigned n_rows, unsigned n_bands) {
+    if (n_rows * n_bands != m) return false;   // :67-70 (prints an error, returns 0)
+    for (unsigned b = 0; b < n_bands; ++b) {
+        bool eq = true;
+        for (unsigned r = 0; r < n_rows; ++r)
+            if (v1[b * n_rows + r] != v2[b * n_rows + r]) { eq = false; break; }
+        if (eq) return true;
+    }
+    return false;
+}
+
+// include/criteria_sketch.hpp:60-64 (hll_a) + :36-43 (kota_mas).
+// t_hat is truncated to size_t (:61); Z*sigma_p is a float*float product (:40).
+bool hll_a(double tau, uint64_t e1, uint64_t e2, double t_union, int p, float Z) {
+    const uint64_t t_trunc = (uint64_t)t_union;
+    const double t_hat = (double)t_trunc;
+    const double gamma = (double)e1 / (double)e2;
+    const float sp = sigma_p(p);
+    const float zs = Z * sp;
+    const double t_mas = t_hat / (1.0 + (double)zs);
+    const double k_mas = ((1.0 + gamma) * (double)e2 - t_mas) / t_mas;
+    return k_mas >= tau;
+}
+
+// include/criteria_sketch.hpp:52-58 (hll_an) + :22-34 (cota_n).
+// card_A+card_B is a size_t sum (:55); t_hat stays double (:54).
+bool hll_an(double tau, uint64_t e1, uint64_t e2, double t_hat, int p, float Z, int order_n) {
+    const double j_hat = ((double)(e1 + e2) - t_hat) / t_hat;
+    const double gamma = (double)e1 / (double)e2;
+    const float sp = sigma_p(p);
+    const float zs = Z * sp;
+    double S = 0, num = 1;
+    for (int k = 1; k < order_n + 1; ++k) { num *= (double)zs; S += num; }
+    const double minimo = std::min(1.0, (1.0 + (double)zs) * (double)e2 / t_hat);
+    const double C = minimo * (1 + gamma) * S;
+    return (j_hat + C) >= tau;
+}
+
+}  // namespace
+
+extern "C" {
+
+enum { ORACLE_CRIT_CB = 0, ORACLE_CRIT_SMH_A = 1, ORACLE_CRIT_HLL_A = 2, ORACLE_CRIT_HLL_AN = 3 };
+
+void oracle_hist64(const uint8_t* regs, uint64_t m, uint32_t* counts) { hist64(regs, m, counts); }
+double oracle_ertl_mle(const uint32_t* counts, int p) { return ertl_mle(counts, (unsigned)p); }
+
+// sketch/include/sketch/hll.h:834-837,862 (report -> csum -> sum)
+double oracle_cardinality(const uint8_t* regs, int p) {
+    uint32_t c[64];
+    hist64(regs, 1ull << p, c);
+    return ertl_mle(c, (unsigned)p);
+}
+
+// sketch/include/sketch/hll.h:1188-1206 (union_size, estim = ERTL_MLE)
+double oracle_union_size(const uint8_t* a, const uint8_t* b, int p) {
+    uint32_t c[64];
+    hist64_union(a, b, 1ull << p, c);
+    return ertl_mle(c, (unsigned)p);
+}
+
+int oracle_cb(float tau, uint64_t e1, uint64_t e2) { return cb((double)tau, e1, e2); }
+int oracle_smh_a(const uint64_t* v1, const uint64_t* v2, int m, int n_rows, int n_bands) {
+    return smh_a(v1, v2, (unsigned)m, (unsigned)n_rows, (unsigned)n_bands);
+}
+int oracle_hll_a(float tau, uint64_t e1, uint64_t e2, double t_union, int p, float Z) {
+    return hll_a((double)tau, e1, e2, t_union, p, Z);
+}
+int oracle_hll_an(float tau, uint64_t e1, uint64_t e2, double t_union, int p, float Z, int n) {
+    return hll_an((double)tau, e1, e2, t_union, p, Z, n);
+}
+float oracle_sigma(int p) { return sigma_p(p); }
+
+// src/selection.cpp:258-267 (cpu_variant != 0): n_bands/n_rows are assigned before
+// the probability test, so a search that never qualifies ends at (m, 1).
+// src/selection_cuda.cpp:119-128 (cpu_variant == 0): assigned only on success,
+// so it ends at (1, 1).  pow() is the C double pow; only P_r is narrowed to float.
+void oracle_band_params(int m, float tau, int cpu_variant, int* n_bands, int* n_rows) {
+    int nb = 1, nr = 1;
+    for (int band = 1; band <= m; ++band) {
+        if (m % band != 0) continue;
+        if (cpu_variant) { nb = band; nr = m / band; }
+        const float P_r = (float)(1.0 - std::pow(1.0 - std::pow((double)tau, (double)((float)m / band)),
+                                                 (double)(float)band));
+        if (P_r >= 0.95) {
+            if (!cpu_variant) { nb = band; nr = m / band; }
+            break;
+        }
+    }
+    *n_bands = nb;
+    *n_rows = nr;
+}
+
+// src/selection.cpp:251-256: std::sort (unstable introsort) of (name, card) by
+// card ascending.  The permutation depends only on the comparison sequence, so
+// sorting (card, index) with the same comparator reproduces the tie order.
+void oracle_sort_order(int n, const double* cards, int32_t* order) {
+    std::vector<std::pair<int32_t, double>> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[(size_t)i] = {i, cards[i]};
+    std::sort(v.begin(), v.end(),
+              [](const std::pair<int32_t, double>& x, const std::pair<int32_t, double>& y) {
+                  return x.second < y.second;
+              });
+    for (int i = 0; i < n; ++i) order[i] = v[(size_t)i].first;
+}
+
+// Whole path, src/selection.cpp:134-173 (hll_a), :187-227 (hll_an), :230-291 (smh_a),
+// on in-memory arrays given in FILE-LIST order.  crit CB (0) is the "CB only"
+// mode of BASELINE config 2: no auxiliary filter (equivalent to running the
+// reference with -c smh_a -a 8 on identical one-bucket aux sketches).
+//
+//   regs      [n][2^p]  primary HLL registers
+//   stored    [n] or NULL: hll.h:1138-1141 honours a stored value_ >= 0
+//   aux       smh_a: uint64 [n][aux_len];  hll_a/hll_an: uint8 [n][2^aux_len]
+//   out_*     capacity out_cap; rows are SORTED positions (i<k), in the order the
+//             reference prints them (row-major by sorted row, then k ascending)
+//   stage     [4] = {pairs examined incl. the breaking one excluded, P_cb, P_aux, P_out}
+// Returns the number of emitted pairs (may exceed out_cap; only out_cap stored).
+int64_t oracle_select(int n, int p, const uint8_t* regs, const double* stored, int crit,
+                      int aux_len, const void* aux, float tau_f, float Z, int order_n,
+                      int n_rows, int n_bands, int threads,
+                      double* cards_sorted, int32_t* order,
+                      int64_t out_cap, int32_t* out_i, int32_t* out_k, double* out_j,
+                      uint8_t* dec_aux /* optional [out of scope] */, int64_t* stage) {
+    (void)dec_aux;
+    const size_t m = (size_t)1 << p;
+    std::vector<double> cards((size_t)n);
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic)
+    for (int i = 0; i < n; ++i) {
+        if (stored && stored[i] >= 0.) cards[(size_t)i] = stored[i];   // hll.h:1141 csum()
+        else cards[(size_t)i] = oracle_cardinality(regs + (size_t)i * m, p);
+    }
+    std::vector<int32_t> ord((size_t)n);
+    oracle_sort_order(n, cards.data(), ord.data());
+    for (int i = 0; i < n; ++i) {
+        order[i] = ord[(size_t)i];
+        cards_sorted[i] = cards[(size_t)ord[(size_t)i]];
+    }
+    const double tau = (double)tau_f;                    // selection.cpp:81 float threshold
+    const size_t aux_m = (crit == ORACLE_CRIT_SMH_A) ? (size_t)aux_len
+                       : (crit == ORACLE_CRIT_CB ? 0 : ((size_t)1 << aux_len));
+    std::vector<std::vector<int32_t>> rk((size_t)n);
+    std::vector<std::vector<double>> rj((size_t)n);
+    int64_t s_cb = 0, s_aux = 0, s_out = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : s_cb, s_aux, s_out)
+    for (int i = 0; i < n - 1; ++i) {
+        const uint64_t e1 = (uint64_t)cards_sorted[i];             // selection.cpp:275
+        const uint8_t* ra = regs + (size_t)ord[(size_t)i] * m;
+        for (int k = i + 1; k < n; ++k) {
+            const uint64_t e2 = (uint64_t)cards_sorted[k];         // :280
+            if (e2 == 0) continue;                                 // :281
+            if (!cb(tau, e1, e2)) break;                           // :282-283
+            ++s_cb;
+            const uint8_t* rb = regs + (size_t)ord[(size_t)k] * m;
+            bool pass = true;
+            if (crit == ORACLE_CRIT_SMH_A) {
+                const uint64_t* A = (const uint64_t*)aux;
+                pass = smh_a(A + (size_t)ord[(size_t)i] * aux_m, A + (size_t)ord[(size_t)k] * aux_m,
+                             (unsigned)aux_m, (unsigned)n_rows, (unsigned)n_bands);
+            } else if (crit == ORACLE_CRIT_HLL_A || crit == ORACLE_CRIT_HLL_AN) {
+                const uint8_t* A = (const uint8_t*)aux;
+                const double tu = oracle_union_size(A + (size_t)ord[(size_t)i] * aux_m,
+                                                    A + (size_t)ord[(size_t)k] * aux_m, aux_len);
+                pass = (crit == ORACLE_CRIT_HLL_A) ? hll_a(tau, e1, e2, tu, aux_len, Z)
+                                                   : hll_an(tau, e1, e2, tu, aux_len, Z, order_n);
+            }
+            if (!pass) continue;
+            ++s_aux;
+            const double t = oracle_union_size(ra, rb, p);         // :286
+            const double jac = ((double)e1 + (double)e2 - t) / t;  // :287
+            if (jac >= tau) {                                      // :288
+                rk[(size_t)i].push_back(k);
+                rj[(size_t)i].push_back(jac);
+                ++s_out;
+            }
+        }
+    }
+    int64_t w = 0;
+    for (int i = 0; i < n; ++i)
+        for (size_t t = 0; t < rk[(size_t)i].size(); ++t, ++w)
+            if (w < out_cap) { out_i[w] = i; out_k[w] = rk[(size_t)i][t]; out_j[w] = rj[(size_t)i][t]; }
+    if (stage) { stage[0] = (int64_t)n * (n - 1) / 2; stage[1] = s_cb; stage[2] = s_aux; stage[3] = s_out; }
+    return w;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+"""-m gpu: the CUDA path, called through the C-ABI, against the oracle and the reference goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+import oracle_api as O
+import cuda_selection_criteria_b200 as S
+from cuda_selection_criteria_b200 import sketch_io, synth
+from cuda_selection_criteria_b200.selection import AUX_HLL, AUX_NONE, AUX_SMH
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(__file__)
+GOLD = os.path.join(HERE, "golden", "influenza")
+REF_OUT = os.path.join(HERE, "golden", "ref_outputs")
+REL_TOL = 1e-6   # north_star: Jaccard within 1e-6 relative; pair set and decisions bit-exact
+
+
+def aux_kind_of(criterion):
+    return {"cb": AUX_NONE, "smh_a": AUX_SMH, "hll_a": AUX_HLL, "hll_an": AUX_HLL}[criterion]
+
+
+def run_gpu(regs, aux, criterion, tau, device=0, **kw):
+    with S.Selection(device) as sel:
+        sel.load(regs, aux, aux_kind_of(criterion))
+        return sel.run(tau=np.float32(tau), criterion=criterion, **kw)
+
+
+def compare(res, ora, tau):
+    """Pair set bit-exact, same order, Jaccard within REL_TOL; stage counts identical."""
+    near = set(zip(res.near_i.tolist(), res.near_k.tolist()))
+    got = list(zip(res.i.tolist(), res.k.tolist()))
+    want = list(zip(ora["i"].tolist(), ora["k"].tolist()))
+    if near:   # pairs within 1e-6 of tau are reported separately and excluded from the exact check
+        got = [x for x in got if x not in near]
+        want = [x for x in want if x not in near]
+    assert got == want
+    assert np.array_equal(res.order, ora["order"])
+    assert np.array_equal(res.cards_sorted.astype(np.uint64), ora["cards_sorted"].astype(np.uint64))
+    if not near:
+        rel = np.abs(res.jaccard - ora["jaccard"]) / np.maximum(np.abs(ora["jaccard"]), 1e-300)
+        assert rel.size == 0 or rel.max() <= REL_TOL
+    st = res.stats
+    assert st["pairs_total"] == ora["stage"][0]
+    assert st["pairs_cb"] == ora["stage"][1]           # CB decisions bit-exact
+    if not near:
+        assert st["pairs_aux"] == ora["stage"][2]      # aux-criterion decisions bit-exact
+        assert st["pairs_out"] == ora["stage"][3]
+
+
+@pytest.mark.parametrize("criterion,aux_bytes", [("smh_a", 512), ("smh_a", 32), ("hll_a", 256), ("hll_an", 256)])
+def test_influenza_golden(gpu, criterion, aux_bytes):
+    lines = S.run_filelist(os.path.join(GOLD, "test_influeza_filelist.txt"), tau=0.9, aux_bytes=aux_bytes,
+                           criterion=criterion, device=gpu, base=GOLD)
+    assert lines == open(os.path.join(GOLD, "results.txt")).read().splitlines()
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(REF_OUT, "cases.json"))), ids=lambda c: c["id"])
+def test_reference_binary_goldens(gpu, case):
+    data = G.build_inputs(case)
+    assert G.digest(data) == case["input_sha256"]
+    res = run_gpu(data["regs"], data["aux"], case["criterion"], case["tau"], gpu)
+    got = S.format_lines(data["names"], res)
+    want = open(os.path.join(REF_OUT, case["id"] + ".txt")).read().splitlines()
+    assert got == want
+    ora = O.select(data["regs"], data["p"], case["criterion"], np.float32(case["tau"]), aux=data["aux"])
+    compare(res, ora, case["tau"])
+
+
+def test_cardinalities_and_union_estimates(gpu):
+    plan = synth.make_plan(600, 11)
+    regs = synth.hll(plan, 14)
+    with S.Selection(gpu) as sel:
+        sel.load(regs)
+        cards, order = sel.order()
+        want = np.array([O.cardinality(regs[i], 14) for i in range(regs.shape[0])])
+        assert np.array_equal(order, np.argsort(want, kind="stable")) or np.array_equal(cards, np.sort(want))
+        rel = np.abs(cards - want[order]) / want[order]
+        assert rel.max() <= 1e-12
+        rng = np.random.default_rng(5)
+        a = rng.integers(0, 600, 4000).astype(np.int32)
+        b = rng.integers(0, 600, 4000).astype(np.int32)
+        t = sel.debug_union(a, b)
+    want_t = np.array([O.union_size(regs[x], regs[y], 14) for x, y in zip(a, b)])
+    assert (np.abs(t - want_t) / want_t).max() <= 1e-12
+
+
+def test_synth_host_equals_device(gpu):
+    plan = synth.make_plan(257, 99)
+    for p, tag in [(14, synth.TAG_PRIMARY), (10, synth.TAG_AUX_HLL), (8, synth.TAG_AUX_HLL)]:
+        h = synth.hll(plan, p, tag)
+        d = synth.hll(plan, p, tag, device=gpu).cpu().numpy()
+        assert np.array_equal(h, d)
+    h = synth.smh(plan, 128)
+    d = synth.smh(plan, 128, device=gpu).cpu().numpy().view(np.uint64)
+    assert np.array_equal(h, d)
+
+
+@pytest.mark.parametrize("criterion,tau,n", [("smh_a", 0.9, 3000), ("smh_a", 0.75, 1500), ("cb", 0.9, 1200),
+                                             ("hll_a", 0.9, 2000), ("hll_an", 0.9, 2000), ("hll_a", 0.8, 900),
+                                             ("hll_an", 0.7, 900)])
+def test_synthetic_vs_oracle(gpu, criterion, tau, n):
+    plan = synth.make_plan(n, 1002)
+    regs = synth.hll(plan, 14)
+    aux = None
+    if criterion == "smh_a":
+        aux = synth.smh(plan, 128)
+    elif criterion in ("hll_a", "hll_an"):
+        aux = synth.hll(plan, 10, synth.TAG_AUX_HLL)
+    res = run_gpu(regs, aux, criterion, tau, gpu)
+    ora = O.select(regs, 14, criterion, np.float32(tau), aux=aux, threads=8)
+    assert len(ora["i"]) > 0
+    compare(res, ora, tau)
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_shards_union_equals_whole(gpu, n_shards):
+    plan = synth.make_plan(2500, 21)
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128)
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        whole = sel.run(tau=np.float32(0.85), criterion="smh_a")
+        parts = [sel.run(tau=np.float32(0.85), criterion="smh_a", shard=s, n_shards=n_shards) for s in range(n_shards)]
+    keys = np.concatenate([(p.i.astype(np.int64) << 32) | p.k for p in parts])
+    jac = np.concatenate([p.jaccard for p in parts])
+    o = np.argsort(keys, kind="stable")
+    assert np.array_equal(keys[o], (whole.i.astype(np.int64) << 32) | whole.k)
+    assert np.array_equal(jac[o], whole.jaccard)
+    assert sum(p.stats["tiles_shard"] for p in parts) == whole.stats["tiles_total"]
+    assert sum(p.stats["pairs_aux"] for p in parts) == whole.stats["pairs_aux"]
+
+
+def test_device_resident_load_matches_host_load(gpu):
+    import torch
+    plan = synth.make_plan(1000, 3)
+    regs_d = synth.hll(plan, 14, device=gpu)
+    aux_d = synth.smh(plan, 128, device=gpu)
+    with S.Selection(gpu) as sel:
+        sel.load(regs_d, aux_d, AUX_SMH)
+        a = sel.run(tau=np.float32(0.9), criterion="smh_a")
+    b = run_gpu(regs_d.cpu().numpy(), aux_d.cpu().numpy().view(np.uint64), "smh_a", 0.9, gpu)
+    assert np.array_equal(a.i, b.i) and np.array_equal(a.k, b.k) and np.array_equal(a.jaccard, b.jaccard)
+    assert torch.cuda.is_available()
+
+
+def test_edge_cases(gpu):
+    plan = synth.make_plan(64, 5)
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128)
+    # empty and tiny inputs
+    for n in (0, 1, 2):
+        r = run_gpu(regs[:n], aux[:n], "smh_a", 0.9, gpu)
+        o = O.select(regs[:n], 14, "smh_a", np.float32(0.9), aux=aux[:n]) if n else None
+        assert r.stats["pairs_total"] == n * (n - 1) // 2
+        if o is not None:
+            compare(r, o, 0.9)
+    # tau > 1 selects nothing; tau = 0 passes CB for every pair
+    assert run_gpu(regs, aux, "smh_a", 1.5, gpu).i.size == 0
+    r0 = run_gpu(regs, None, "cb", 0.0, gpu)
+    o0 = O.select(regs, 14, "cb", np.float32(0.0))
+    compare(r0, o0, 0.0)
+    assert r0.stats["pairs_cb"] == 64 * 63 // 2
+    # all sketches identical: every cardinality ties, every pair has J = 1
+    same = np.repeat(regs[:1], 40, axis=0)
+    rs = run_gpu(same, np.repeat(aux[:1], 40, axis=0), "smh_a", 0.9, gpu)
+    os_ = O.select(same, 14, "smh_a", np.float32(0.9), aux=np.repeat(aux[:1], 40, axis=0))
+    compare(rs, os_, 0.9)
+    assert rs.i.size == 40 * 39 // 2
+    # smh band shape that does not tile the sketch: the reference's smh_a returns 0 for every pair
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        assert sel.run(tau=np.float32(0.9), criterion="smh_a", n_rows=3, n_bands=5).i.size == 0
+    # empty sketches (e == 0) among real ones
+    z = regs.copy(); z[3] = 0; z[9] = 0
+    rz = run_gpu(z, aux, "smh_a", 0.7, gpu)
+    oz = O.select(z, 14, "smh_a", np.float32(0.7), aux=aux)
+    compare(rz, oz, 0.7)
+
+
+def test_errors_are_loud(gpu):
+    plan = synth.make_plan(8, 5)
+    regs = synth.hll(plan, 14).copy()
+    with S.Selection(gpu) as sel:
+        with pytest.raises(S.SelB200Error):
+            sel.run()                                   # run before load
+        bad = regs.copy(); bad[2, 100] = 52             # > 64-14+1
+        with pytest.raises(S.SelB200Error):
+            sel.load(bad)
+        sel.load(regs)
+        with pytest.raises(S.SelB200Error):
+            sel.run(criterion="smh_a")                  # no SuperMinHash sketches loaded
+        with pytest.raises(S.SelB200Error):
+            sel.run(criterion="hll_a")
+
+
+def test_other_primary_precisions(gpu):
+    plan = synth.make_plan(300, 17)
+    for p in (10, 12, 16):
+        regs = synth.hll(plan, p)
+        r = run_gpu(regs, None, "cb", 0.9, gpu)
+        o = O.select(regs, p, "cb", np.float32(0.9))
+        compare(r, o, 0.9)
