@@ -176,29 +176,58 @@ __device__ __forceinline__ uint32_t max4_lt128(uint32_t a, uint32_t b) {
     return (a & msk) | (b & ~msk);
 }
 
-// One histogram increment.  The histogram is laid out [bin][64 threads] uint32 in the CTA's
-// static shared memory, so the byte offset of thread t's counter for register value v is
-// (v << 8) | (t * 4): a single PRMT builds it from the packed register word and tb = t*4,
-// and the shared base rides on the LDS/STS immediate.  Bank = t mod 32: conflict-free.
+// Histogram addressing.  Counters are laid out [bin][64 threads] uint32 in the CTA's static
+// shared memory, so the counter of thread t for register value v lives at shared address
+//   base + (v << 8) + t*4 .
+// `base` is 256-aligned and small, so adding (base >> 8) to every byte of the packed
+// register word (no carries: v <= 63) lets ONE PRMT build the complete address from the word
+// and tb = t*4 — no per-byte add, and the bank is t mod 32: conflict-free.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t hist_bias(const void* hist) {
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(hist);
+    if ((sbase & 0xffu) || sbase > 0x8000u) __trap();   // must fit: (63 + bias) < 256 and address < 64 KiB
+    return (sbase >> 8) * 0x01010101u;
+}
 template <int B>
-__device__ __forceinline__ void hist_inc(uint32_t* hist, uint32_t w, uint32_t tb) {
-    const uint32_t off = __byte_perm(w, tb, 0x5504 | (B << 4));
-    uint32_t* c = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist) + off);
-    *c += 1;
+__device__ __forceinline__ uint32_t hist_addr(uint32_t wb, uint32_t tb) {
+    return __byte_perm(wb, tb, 0x5504 | (B << 4));
 }
 
-__device__ __forceinline__ void hist_inc_word(uint32_t* hist, uint32_t w, uint32_t tb) {
-    hist_inc<0>(hist, w, tb);
-    hist_inc<1>(hist, w, tb);
-    hist_inc<2>(hist, w, tb);
-    hist_inc<3>(hist, w, tb);
+// Two register values per step into ONE histogram: both counters are loaded before either is
+// stored (two LDS in flight instead of a serial LDS->ADD->STS chain); if both hit the same
+// counter the second store carries the first increment (select), and stores stay in order.
+template <int B0, int B1>
+__device__ __forceinline__ void hist_inc2(uint32_t wb, uint32_t tb) {
+    const uint32_t o0 = hist_addr<B0>(wb, tb), o1 = hist_addr<B1>(wb, tb);
+    const uint32_t c0 = lds_u32(o0) + 1;
+    uint32_t c1 = lds_u32(o1);
+    c1 = (o1 == o0) ? c0 : c1;
+    sts_u32(o0, c0);
+    sts_u32(o1, c1 + 1);
 }
 
-__device__ __forceinline__ void hist_inc_max16(uint32_t* hist, const uint4& x, const uint4& y, uint32_t tb) {
-    hist_inc_word(hist, max4_lt128(x.x, y.x), tb);
-    hist_inc_word(hist, max4_lt128(x.y, y.y), tb);
-    hist_inc_word(hist, max4_lt128(x.z, y.z), tb);
-    hist_inc_word(hist, max4_lt128(x.w, y.w), tb);
+__device__ __forceinline__ void hist_inc_max16(const uint4& x, const uint4& y, uint32_t bias, uint32_t tb) {
+    uint32_t w;
+    w = max4_lt128(x.x, y.x) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
+    w = max4_lt128(x.y, y.y) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
+    w = max4_lt128(x.z, y.z) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
+    w = max4_lt128(x.w, y.w) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
+}
+
+// One register value into each of TWO different histograms (never alias): both loads first.
+template <int B>
+__device__ __forceinline__ void hist_inc_dual(uint32_t wb0, uint32_t wb1, uint32_t tb) {
+    const uint32_t o0 = hist_addr<B>(wb0, tb), o1 = hist_addr<B>(wb1, tb);
+    const uint32_t c0 = lds_u32(o0), c1 = lds_u32(o1);
+    sts_u32(o0, c0 + 1);
+    sts_u32(o1, c1 + 1);
 }
 
 // Warp-aggregated slot claim: one atomicAdd per warp per call site, lanes get consecutive slots.
@@ -243,12 +272,14 @@ template <int NB>
 __global__ void __launch_bounds__(64)
 k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restrict__ order,
             const uint2* __restrict__ pairs, long long npairs, uint32_t* __restrict__ hist_out) {
-    __shared__ __align__(16) uint32_t hist[NB * 64];
+    __shared__ __align__(1024) uint32_t hist[NB * 64];
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
+    const uint32_t bias = hist_bias(hist);
 #pragma unroll 4
     for (int b = 0; b < NB; ++b) hist[b * 64 + t] = 0;
     __syncwarp();
     const int nchunk = (int)(m >> 9);   // 512 B per warp-wide 128-bit load
+    const int ngroups = nchunk >> 2;    // software pipeline works on groups of 4 chunks
     const long long nw = (long long)gridDim.x * 2;
     for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
         const uint2 pr = pairs[pi];
@@ -256,16 +287,20 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restric
         const size_t rb = order ? (size_t)order[pr.y] : (size_t)pr.y;
         const uint4* a = reinterpret_cast<const uint4*>(regs + ra * m) + lane;
         const uint4* b = reinterpret_cast<const uint4*>(regs + rb * m) + lane;
-        // two chunks in flight ahead of the one being histogrammed
-        uint4 x0 = __ldg(a), y0 = __ldg(b);
-        uint4 x1 = x0, y1 = y0;
-        if (nchunk > 1) { x1 = __ldg(a + 32); y1 = __ldg(b + 32); }
-        for (int c = 0; c < nchunk; ++c) {
-            uint4 x2 = x1, y2 = y1;
-            if (c + 2 < nchunk) { x2 = __ldg(a + (c + 2) * 32); y2 = __ldg(b + (c + 2) * 32); }
-            hist_inc_max16(hist, x0, y0, tb);
-            x0 = x1; y0 = y1; x1 = x2; y1 = y2;
+        if (ngroups) {
+            // two chunks being histogrammed while the next two are in flight (no register rotation)
+            uint4 ax0 = __ldg(a), ay0 = __ldg(b), ax1 = __ldg(a + 32), ay1 = __ldg(b + 32);
+            for (int g = 0; g < ngroups; ++g) {
+                const uint4 bx0 = __ldg(a + 64), by0 = __ldg(b + 64), bx1 = __ldg(a + 96), by1 = __ldg(b + 96);
+                hist_inc_max16(ax0, ay0, bias, tb);
+                hist_inc_max16(ax1, ay1, bias, tb);
+                a += 128; b += 128;
+                if (g + 1 < ngroups) { ax0 = __ldg(a); ay0 = __ldg(b); ax1 = __ldg(a + 32); ay1 = __ldg(b + 32); }
+                hist_inc_max16(bx0, by0, bias, tb);
+                hist_inc_max16(bx1, by1, bias, tb);
+            }
         }
+        for (int c = ngroups * 4; c < nchunk; ++c, a += 32, b += 32) hist_inc_max16(__ldg(a), __ldg(b), bias, tb);
         __syncwarp();
         // transposed, conflict-free column sums: lane L totals bins L and L+32, and clears them
         uint32_t s0 = 0, s1 = 0;
@@ -544,13 +579,14 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                   unsigned long long pair_cap) {
     constexpr int NB = 64;
-    __shared__ __align__(16) uint32_t hist[2][NB * 64];
+    __shared__ __align__(1024) uint32_t hist[2][NB * 64];
     const int unit = blockIdx.x;
     const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2));
     const int r0 = tr.rb * TILE + (unit & 3) * 32, c0 = tr.cb * TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const int words = (1 << p_aux) >> 2;
     const int nbins = 64 - p_aux + 2;
+    const uint32_t bias0 = hist_bias(hist[0]), bias1 = hist_bias(hist[1]);
     for (int b = 0; b < NB; ++b) { hist[0][b * 64 + t] = 0; hist[1][b * 64 + t] = 0; }
     __syncwarp();
     // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
@@ -568,9 +604,11 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
             const uint32_t cw = __ldg(colp + (size_t)j * npad);
             const uint32_t a0 = __ldg(row0 + (size_t)j * npad);
             const uint32_t a1 = __ldg(row1 + (size_t)j * npad);
-            const uint32_t m0 = max4_lt128(a0, cw), m1 = max4_lt128(a1, cw);
-            hist_inc_word(hist[0], m0, tb);
-            hist_inc_word(hist[1], m1, tb);
+            const uint32_t m0 = max4_lt128(a0, cw) + bias0, m1 = max4_lt128(a1, cw) + bias1;
+            hist_inc_dual<0>(m0, m1, tb);
+            hist_inc_dual<1>(m0, m1, tb);
+            hist_inc_dual<2>(m0, m1, tb);
+            hist_inc_dual<3>(m0, m1, tb);
         }
         bool pass0 = false, pass1 = false;
         if (v0) {
@@ -632,6 +670,18 @@ int upload(DevBuf& buf, const std::vector<T>& v, cudaStream_t s) {
     return SELB200_OK;
 }
 
+// resident CTAs per SM with the maximum shared-memory carve-out (queried once per kernel)
+template <typename K>
+int resident_ctas(K kernel, int threads) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 8;
+    }
+    return per_sm;
+}
+
 int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const int32_t* order,
                      const uint2* pairs, int64_t npairs, uint32_t* hist_out) {
     if (npairs <= 0) return SELB200_OK;
@@ -639,11 +689,11 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
     if (m >= 512) {
         const int nbins = 64 - p + 2;
         if (nbins <= 52) {
-            int per_sm = 17;
+            static const int per_sm = resident_ctas(k_pair_hist<52>, 64);
             const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
             k_pair_hist<52><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
         } else {
-            int per_sm = 13;
+            static const int per_sm = resident_ctas(k_pair_hist<64>, 64);
             const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
             k_pair_hist<64><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
         }
