@@ -281,6 +281,7 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restric
     const int nchunk = (int)(m >> 9);   // 512 B per warp-wide 128-bit load
     const int ngroups = nchunk >> 2;    // software pipeline works on groups of 4 chunks
     const long long nw = (long long)gridDim.x * 2;
+    uint32_t prev0 = 0, prev1 = 0;
     for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
         const uint2 pr = pairs[pi];
         const size_t ra = order ? (size_t)order[pr.x] : (size_t)pr.x;
@@ -302,22 +303,22 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restric
         }
         for (int c = ngroups * 4; c < nchunk; ++c, a += 32, b += 32) hist_inc_max16(__ldg(a), __ldg(b), bias, tb);
         __syncwarp();
-        // transposed, conflict-free column sums: lane L totals bins L and L+32, and clears them
+        // transposed, conflict-free column sums: lane L totals bins L and L+32.  Counters are
+        // never cleared: they run cumulatively (mod 2^32) and the pair's histogram is the
+        // difference to the previous totals, which saves the 64 clearing stores per pair.
         uint32_t s0 = 0, s1 = 0;
         const uint32_t cb = w * 32;
 #pragma unroll 8
         for (int r = 0; r < 32; ++r) {
             const uint32_t col = cb + ((lane + r) & 31);
             s0 += hist[lane * 64 + col];
-            hist[lane * 64 + col] = 0;
-            if (lane + 32 < NB) {
-                s1 += hist[(lane + 32) * 64 + col];
-                hist[(lane + 32) * 64 + col] = 0;
-            }
+            if (lane + 32 < NB) s1 += hist[(lane + 32) * 64 + col];
         }
         __syncwarp();
-        hist_out[pi * 64 + lane] = s0;
-        hist_out[pi * 64 + 32 + lane] = s1;
+        hist_out[pi * 64 + lane] = s0 - prev0;
+        hist_out[pi * 64 + 32 + lane] = s1 - prev1;
+        prev0 = s0;
+        prev1 = s1;
     }
 }
 
@@ -1103,7 +1104,6 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                     c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
                 CK(cudaGetLastError());
                 st.launches++;
-                t_verify.push_back({f1, c->ev()});
             }
         }
         CK(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
@@ -1120,18 +1120,34 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         st.pairs_aux += np;
         st.batches++;
         if (np == 0) continue;
+        // ---- locality: the selective filters emit in atomic-arrival order; ordering the list by
+        // column index keeps the rows a wave of warps touches inside L2 (k_tile_enum already
+        // emits tile by tile) ----------------------------------------------------------------
+        const uint2* d_pairs = c->pairs.as<uint2>();
+        if (crit != SELB200_CRIT_CB && np > 1) {
+            int nbits = 1;
+            while ((1ll << nbits) < (long long)n) ++nbits;
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, c->pairs.as<uint64_t>(), c->cand.as<uint64_t>(),
+                                              (int)np, 32, 32 + nbits, s));
+            CKR(c->cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp_bytes, c->pairs.as<uint64_t>(),
+                                              c->cand.as<uint64_t>(), (int)np, 32, 32 + nbits, s));
+            d_pairs = c->cand.as<uint2>();
+        }
         // ---- K5 + K6 ------------------------------------------------------------------
         CKR(c->hist.ensure((size_t)np * 64 * sizeof(uint32_t)));
         const size_t need = (size_t)(total_out + np);
         CKR(c->out_keys.grow_keep(need * 8, (size_t)total_out * 8, s));
         CKR(c->out_j.grow_keep(need * 8, (size_t)total_out * 8, s));
         cudaEvent_t u0 = c->ev();
-        CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(), np,
+        if (d_pairs != c->pairs.as<uint2>()) t_verify.push_back({f1, u0});   // verify + locality sort
+        CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), d_pairs, np,
                              c->hist.as<uint32_t>()));
         st.launches++;
         cudaEvent_t u1 = c->ev();
         k_estimate_emit<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(
-            c->hist.as<uint32_t>(), c->pairs.as<uint2>(), np, c->e_sorted.as<unsigned long long>(), c->p, tau,
+            c->hist.as<uint32_t>(), d_pairs, np, c->e_sorted.as<unsigned long long>(), c->p, tau,
             c->out_keys.as<uint64_t>(), c->out_j.as<double>(), d_cnt + 2, (unsigned long long)need,
             c->near_keys.as<uint64_t>(), c->near_j.as<double>(), d_cnt + 3, near_cap);
         CK(cudaGetLastError());
