@@ -266,12 +266,31 @@ __global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data
 // K5: warp-per-pair register max + histogram (primary HLL, m >= 512)
 //   reference: sketch/include/sketch/hll.h:1188-1206 (union_size: _mm_max_epu8 + 64-bin counts)
 //   CTA = 2 warps, each warp owns its own pairs; NB bins x 64 threads x 4 B static smem.
-//   order == nullptr: pair entries are row indices into regs; else sorted positions.
+//   Src  : where pair (row a, row b) number pi comes from, and how many there are
+//   Epi  : what happens to the finished histogram (lane L holds bins L and L+32)
 // ============================================================================
-template <int NB>
+struct SrcPairs {            // pair list of the selection path: sorted positions, mapped through `order`
+    const uint2* pairs;
+    const int32_t* order;    // nullptr: entries are row indices already
+    long long n;
+    __device__ __forceinline__ long long count() const { return n; }
+    __device__ __forceinline__ uint2 rows(long long pi, uint2& id) const {
+        id = pairs[pi];
+        return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
+    }
+};
+
+struct EpiWriteHist {        // histogram rows for k_estimate_emit
+    uint32_t* out;
+    __device__ __forceinline__ void operator()(long long pi, uint2, uint32_t s0, uint32_t s1, uint32_t lane) const {
+        out[pi * 64 + lane] = s0;
+        out[pi * 64 + 32 + lane] = s1;
+    }
+};
+
+template <int NB, class Src, class Epi>
 __global__ void __launch_bounds__(64)
-k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restrict__ order,
-            const uint2* __restrict__ pairs, long long npairs, uint32_t* __restrict__ hist_out) {
+k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src src, Epi epi) {
     __shared__ __align__(1024) uint32_t hist[NB * 64];
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const uint32_t bias = hist_bias(hist);
@@ -281,13 +300,13 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restric
     const int nchunk = (int)(m >> 9);   // 512 B per warp-wide 128-bit load
     const int ngroups = nchunk >> 2;    // software pipeline works on groups of 4 chunks
     const long long nw = (long long)gridDim.x * 2;
+    const long long npairs = src.count();
     uint32_t prev0 = 0, prev1 = 0;
     for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
-        const uint2 pr = pairs[pi];
-        const size_t ra = order ? (size_t)order[pr.x] : (size_t)pr.x;
-        const size_t rb = order ? (size_t)order[pr.y] : (size_t)pr.y;
-        const uint4* a = reinterpret_cast<const uint4*>(regs + ra * m) + lane;
-        const uint4* b = reinterpret_cast<const uint4*>(regs + rb * m) + lane;
+        uint2 id;
+        const uint2 rw = src.rows(pi, id);
+        const uint4* a = reinterpret_cast<const uint4*>(regs + (size_t)rw.x * row_stride) + lane;
+        const uint4* b = reinterpret_cast<const uint4*>(regs + (size_t)rw.y * row_stride) + lane;
         if (ngroups) {
             // two chunks being histogrammed while the next two are in flight (no register rotation)
             uint4 ax0 = __ldg(a), ay0 = __ldg(b), ax1 = __ldg(a + 32), ay1 = __ldg(b + 32);
@@ -315,8 +334,7 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t m, const int32_t* __restric
             if (lane + 32 < NB) s1 += hist[(lane + 32) * 64 + col];
         }
         __syncwarp();
-        hist_out[pi * 64 + lane] = s0 - prev0;
-        hist_out[pi * 64 + 32 + lane] = s1 - prev1;
+        epi(pi, id, s0 - prev0, s1 - prev1, lane);
         prev0 = s0;
         prev1 = s1;
     }
@@ -683,26 +701,36 @@ int resident_ctas(K kernel, int threads) {
     return per_sm;
 }
 
+template <class Src, class Epi>
+int launch_pair_hist_t(cudaStream_t stream, int sm_count, const uint8_t* regs, size_t row_stride, size_t m, int p,
+                       int64_t max_pairs, Src src, Epi epi) {
+    if (max_pairs <= 0) return SELB200_OK;
+    const int64_t ctas_needed = (max_pairs + 1) / 2;
+    const int nbins = 64 - p + 2;
+    if (nbins <= 52) {
+        static const int per_sm = resident_ctas(k_pair_hist<52, Src, Epi>, 64);
+        const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count * per_sm);
+        k_pair_hist<52, Src, Epi><<<grid, 64, 0, stream>>>(regs, row_stride, m, src, epi);
+    } else {
+        static const int per_sm = resident_ctas(k_pair_hist<64, Src, Epi>, 64);
+        const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count * per_sm);
+        k_pair_hist<64, Src, Epi><<<grid, 64, 0, stream>>>(regs, row_stride, m, src, epi);
+    }
+    CK(cudaGetLastError());
+    return SELB200_OK;
+}
+
 int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const int32_t* order,
                      const uint2* pairs, int64_t npairs, uint32_t* hist_out) {
     if (npairs <= 0) return SELB200_OK;
-    const int64_t ctas_needed = (npairs + 1) / 2;
     if (m >= 512) {
-        const int nbins = 64 - p + 2;
-        if (nbins <= 52) {
-            static const int per_sm = resident_ctas(k_pair_hist<52>, 64);
-            const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
-            k_pair_hist<52><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
-        } else {
-            static const int per_sm = resident_ctas(k_pair_hist<64>, 64);
-            const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * per_sm);
-            k_pair_hist<64><<<grid, 64, 0, c->stream>>>(regs, m, order, pairs, npairs, hist_out);
-        }
-    } else {
-        if (order) return fail(SELB200_EINVAL, "small-sketch histogram takes row indices");
-        const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)c->sm_count * 16);
-        k_pair_hist_small<<<grid, 64, 0, c->stream>>>(regs, m, pairs, npairs, hist_out);
+        SrcPairs src{pairs, order, (long long)npairs};
+        EpiWriteHist epi{hist_out};
+        return launch_pair_hist_t(c->stream, c->sm_count, regs, m, m, p, npairs, src, epi);
     }
+    if (order) return fail(SELB200_EINVAL, "small-sketch histogram takes row indices");
+    const int grid = (int)std::min<int64_t>((npairs + 1) / 2, (int64_t)c->sm_count * 16);
+    k_pair_hist_small<<<grid, 64, 0, c->stream>>>(regs, m, pairs, npairs, hist_out);
     CK(cudaGetLastError());
     return SELB200_OK;
 }
@@ -1279,3 +1307,5 @@ int selb200_debug_union(selb200_ctx* c, int which, int64_t count, const int32_t*
 }
 
 }  // extern "C"
+
+#include "shims.inl"

@@ -1,0 +1,234 @@
+// selection_main.cpp — C++ host driver over the C-ABI (include/selb200.h).
+//
+// Drop-in for the reference CLIs (same flag letters, same defaults, same stdout lines):
+//   ./selection       -l list -t threads -a aux_bytes -h tau -c {smh_a|hll_a|hll_an|cb} [-b block]
+//       mirrors src/selection.cpp:70-303: file list (:36-63), sketches `P.hll` +
+//       `P.smh<a/8>` | `P.hll_<ctz(a)>` (:125,138-139,231,245-246), output lines
+//       `P_i P_k std::to_string(J)` in (sorted row, k) order (:288,297-300), invalid -c
+//       message on stdout and exit 0 (:292-294).
+//   ./selection_cuda  -l list -b block -a aux_bytes -h tau   (built with -DSELB_CUDA_DRIVER)
+//       mirrors src/selection_cuda.cpp:59-189: criterion fixed to smh_a (-c accepted and
+//       ignored, :68-88), band search that keeps (1,1) when nothing qualifies (:119-128),
+//       similarity printed through operator<<(float) (:184-186).
+// Extra, not in the reference: `-c cb` (CB only), `-g` prints run statistics to stderr.
+// The device work is entirely behind selb200_load_host / selb200_run; this file only parses
+// flags, gunzips sketches (zlib, OpenMP over files) and formats lines.
+#include <getopt.h>
+#include <omp.h>
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/selb200.h"
+
+namespace {
+
+// sketch/include/sketch/hll.h:1126-1143 (read): u32[4] header, u32 np, f64 value, 2^np registers
+struct HllFile {
+    uint32_t hdr[4];
+    uint32_t np;
+    double value;
+    std::vector<uint8_t> core;
+};
+
+void gz_read_exact(gzFile fp, void* dst, size_t len, const std::string& path) {
+    if (static_cast<uint64_t>(gzread(fp, dst, (unsigned)len)) != len) {
+        gzclose(fp);
+        throw std::runtime_error("Error reading from file " + path);
+    }
+}
+
+HllFile read_hll(const std::string& path) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (fp == nullptr) throw std::runtime_error(std::string("Could not open file at '") + path + "' for reading");
+    HllFile h;
+    gz_read_exact(fp, h.hdr, sizeof h.hdr, path);
+    gz_read_exact(fp, &h.np, sizeof h.np, path);
+    gz_read_exact(fp, &h.value, sizeof h.value, path);
+    if (h.np > 30) { gzclose(fp); throw std::runtime_error("Error reading from file " + path); }
+    h.core.resize((size_t)1 << h.np);
+    gz_read_exact(fp, h.core.data(), h.core.size(), path);
+    gzclose(fp);
+    return h;
+}
+
+// src/selection.cpp:12-33 (read_smh): u32 count, count x u64
+std::vector<uint64_t> read_smh(const std::string& path) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (fp == nullptr) throw std::runtime_error(std::string("Could not open file at '") + path + "' for reading");
+    uint32_t n = 0;
+    gz_read_exact(fp, &n, sizeof n, path);
+    std::vector<uint64_t> v(n);
+    if (n) gz_read_exact(fp, v.data(), (size_t)n * 8, path);
+    gzclose(fp);
+    return v;
+}
+
+// src/selection.cpp:36-63
+void load_file_list(std::vector<std::string>& files, const std::string& list_file) {
+    if (list_file.empty()) { std::cerr << "No input file provided\n"; exit(-1); }
+    std::ifstream file(list_file);
+    if (!file.is_open()) { std::cerr << "No valid input file provided\n"; exit(-1); }
+    std::string line;
+    while (getline(file, line)) {
+        line.erase(0, line.find_first_not_of(" \t\r\n"));
+        line.erase(line.find_last_not_of(" \t\r\n") + 1);
+        if (!line.empty()) files.push_back(line);
+    }
+}
+
+[[noreturn]] void die(const char* what) {
+    std::cerr << "selb200: " << what << ": " << selb200_last_error() << "\n";
+    exit(2);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+    std::string list_file, criterion;
+    unsigned threads = 8;
+    unsigned aux_bytes = 256;
+    float threshold = 0.9f;
+    float z_score = 1.96f;
+    int order_n = 1;
+    int block_size = 256;
+    bool verbose = false;
+    (void)block_size;
+#ifdef SELB_CUDA_DRIVER
+    criterion = "smh_a";
+#endif
+    int c;
+    while ((c = getopt(argc, argv, "xl:t:a:h:c:b:g")) != -1) {
+        switch (c) {
+            case 'x': std::cout << "Usage: -l -t -a -h -c\n"; return 0;
+            case 'l': list_file = optarg; break;
+            case 't': threads = (unsigned)std::stoi(optarg); break;
+            case 'a': aux_bytes = (unsigned)std::stoi(optarg); break;
+            case 'h': threshold = std::stof(optarg); break;
+#ifndef SELB_CUDA_DRIVER
+            case 'c': criterion = optarg; break;
+#else
+            case 'c': break;   // selection_cuda.cpp:68-88: in the optstring, no case
+#endif
+            case 'b': block_size = std::stoi(optarg); break;
+            case 'g': verbose = true; break;
+            default: break;
+        }
+    }
+    omp_set_num_threads((int)threads);
+    std::vector<std::string> files;
+    load_file_list(files, list_file);
+
+    int crit = -1, aux_kind = SELB200_AUX_NONE;
+    if (criterion == "smh_a") { crit = SELB200_CRIT_SMH_A; aux_kind = SELB200_AUX_SMH; }
+    else if (criterion == "hll_a") { crit = SELB200_CRIT_HLL_A; aux_kind = SELB200_AUX_HLL; }
+    else if (criterion == "hll_an") { crit = SELB200_CRIT_HLL_AN; aux_kind = SELB200_AUX_HLL; }
+    else if (criterion == "cb") { crit = SELB200_CRIT_CB; }
+    if (crit < 0) {
+        std::cout << "Option -c invalid. The accepted criteria are hll_a, hll_an and smh_a.\n";
+        return 0;
+    }
+    const size_t n = files.size();
+    const unsigned p_aux = aux_bytes ? (unsigned)__builtin_ctz(aux_bytes) : 0;   // selection.cpp:125
+    const unsigned m_aux = aux_bytes / 8;                                      // selection.cpp:231
+    const std::string aux_suffix = aux_kind == SELB200_AUX_SMH ? ".smh" + std::to_string(m_aux)
+                                 : aux_kind == SELB200_AUX_HLL ? ".hll_" + std::to_string(p_aux) : "";
+
+    // ---- load (OpenMP over files, like selection.cpp:241-249) ---------------------------------
+    int p = 14;
+    std::vector<uint8_t> regs, aux_hll;
+    std::vector<uint64_t> aux_smh;
+    std::vector<double> stored(n, -1.0);
+    std::string load_error;
+    if (n) {
+        HllFile first = read_hll(files[0] + ".hll");
+        p = (int)first.np;
+        const size_t m = (size_t)1 << p;
+        regs.resize(n * m);
+        if (aux_kind == SELB200_AUX_SMH) aux_smh.resize(n * (size_t)m_aux);
+        if (aux_kind == SELB200_AUX_HLL) aux_hll.resize(n << p_aux);
+#pragma omp parallel for schedule(dynamic)
+        for (size_t i = 0; i < n; ++i) {
+            try {
+                HllFile h = read_hll(files[i] + ".hll");
+                if ((int)h.np != p) throw std::runtime_error(files[i] + ".hll: precision differs from the first sketch");
+                if (h.hdr[1] != 2 || h.hdr[2] != 2)
+                    throw std::runtime_error(files[i] + ".hll: stored estimator is not ERTL_MLE (hll.h:825-827 default)");
+                std::memcpy(regs.data() + i * m, h.core.data(), m);
+                stored[i] = h.value;
+                if (aux_kind == SELB200_AUX_SMH) {
+                    std::vector<uint64_t> v = read_smh(files[i] + aux_suffix);
+                    if (v.size() != m_aux) throw std::runtime_error(files[i] + aux_suffix + ": unexpected bucket count");
+                    std::memcpy(aux_smh.data() + i * (size_t)m_aux, v.data(), (size_t)m_aux * 8);
+                } else if (aux_kind == SELB200_AUX_HLL) {
+                    HllFile a = read_hll(files[i] + aux_suffix);
+                    if (a.np != p_aux) throw std::runtime_error(files[i] + aux_suffix + ": unexpected precision");
+                    std::memcpy(aux_hll.data() + (i << p_aux), a.core.data(), (size_t)1 << p_aux);
+                }
+            } catch (const std::exception& e) {
+#pragma omp critical
+                if (load_error.empty()) load_error = e.what();
+            }
+        }
+        if (!load_error.empty()) throw std::runtime_error(load_error);   // uncaught, like the reference
+    }
+
+    // ---- device --------------------------------------------------------------------------------
+    selb200_ctx* ctx = nullptr;
+    if (selb200_create(0, nullptr, &ctx) != SELB200_OK) die("create");
+    const void* aux_ptr = aux_kind == SELB200_AUX_SMH ? (const void*)aux_smh.data()
+                        : aux_kind == SELB200_AUX_HLL ? (const void*)aux_hll.data() : nullptr;
+    const int aux_len = aux_kind == SELB200_AUX_SMH ? (int)m_aux : aux_kind == SELB200_AUX_HLL ? (int)p_aux : 0;
+    if (selb200_load_host(ctx, (int64_t)n, p, regs.data(), stored.data(), aux_kind, aux_len, aux_ptr) != SELB200_OK)
+        die("load");
+    selb200_params prm;
+    selb200_default_params(&prm);
+    prm.tau = threshold;
+    prm.criterion = crit;
+    prm.z_score = z_score;
+    prm.order_n = order_n;
+    if (crit == SELB200_CRIT_SMH_A) {
+#ifdef SELB_CUDA_DRIVER
+        selb200_band_params((int)m_aux, threshold, 0, &prm.n_bands, &prm.n_rows);
+#else
+        selb200_band_params((int)m_aux, threshold, 1, &prm.n_bands, &prm.n_rows);
+#endif
+    }
+    selb200_stats st;
+    if (selb200_run(ctx, &prm, &st) != SELB200_OK) die("run");
+    const int64_t cnt = selb200_result_count(ctx);
+    std::vector<int32_t> ri((size_t)cnt), rk((size_t)cnt), order(n);
+    std::vector<double> rj((size_t)cnt);
+    if (selb200_copy_results(ctx, cnt, ri.data(), rk.data(), rj.data()) != SELB200_OK) die("results");
+    if (selb200_get_order(ctx, nullptr, order.data()) != SELB200_OK) die("order");
+
+    std::string out;
+    out.reserve((size_t)cnt * 96);
+    for (int64_t t = 0; t < cnt; ++t) {
+        const std::string& a = files[(size_t)order[(size_t)ri[(size_t)t]]];
+        const std::string& b = files[(size_t)order[(size_t)rk[(size_t)t]]];
+#ifdef SELB_CUDA_DRIVER
+        char buf[64];
+        snprintf(buf, sizeof buf, "%g", (double)(float)rj[(size_t)t]);   // operator<<(float), 6 significant digits
+        out += a + " " + b + " " + buf + "\n";
+#else
+        out += a + " " + b + " " + std::to_string(rj[(size_t)t]) + "\n";
+#endif
+    }
+    std::cout << out;
+    if (verbose)
+        fprintf(stderr, "selb200: n=%lld pairs=%lld P_cb=%lld P_aux=%lld P_out=%lld near=%lld | bands x rows %dx%d | "
+                        "device ms: bounds %.3f filter %.3f verify %.3f union %.3f estimate %.3f sort %.3f total %.3f\n",
+                (long long)st.n, (long long)st.pairs_total, (long long)st.pairs_cb, (long long)st.pairs_aux,
+                (long long)st.pairs_out, (long long)st.pairs_near, st.n_bands, st.n_rows, st.ms_bounds, st.ms_filter,
+                st.ms_verify, st.ms_union, st.ms_estimate, st.ms_sort, st.ms_total);
+    selb200_destroy(ctx);
+    return 0;
+}

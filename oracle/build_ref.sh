@@ -16,6 +16,13 @@ if [ ! -f "$REF/src/selection.cpp" ]; then
   exit 0
 fi
 mkdir -p "$OUT"
+# The reference's own CUDA kernels + launchers (src/selection_kernels.cu), compiled in place for
+# sm_100a: the checker for our link-level shims and the "existing GPU kernel" speed bar.
+if [ ! "$OUT/libref_kernels.so" -nt "$REF/src/selection_kernels.cu" ] || [ "${FORCE:-0}" = "1" ]; then
+  (cd "$REF" && /usr/local/cuda/bin/nvcc -O3 --std=c++17 -gencode arch=compute_100a,code=sm_100a -ccbin g++ \
+      -DNDEBUG -I. -Iinclude -shared -Xcompiler -fPIC src/selection_kernels.cu -o "$OUT/libref_kernels.so") \
+    && echo "build_ref: built $OUT/libref_kernels.so"
+fi
 if [ "$OUT/selection" -nt "$REF/src/selection.cpp" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "build_ref: $OUT/selection up to date"
   exit 0
