@@ -27,11 +27,24 @@ namespace selb {
 SELB_HD int imax(int a, int b) { return a > b ? a : b; }
 SELB_HD int imin(int a, int b) { return a < b ? a : b; }
 
+struct NeverStop {
+    SELB_HD bool operator()(double) const { return false; }
+};
+
 // Ertl maximum-likelihood cardinality from a register histogram c[0..q+1], q = 64-p.
 // CountT is uint32_t (global/shared histogram rows).  `stride` lets the caller keep
 // its histogram column-interleaved in shared memory.
-template <typename CountT>
-SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1) {
+//
+// `stop(t_lb)` is an optional early exit.  The secant iteration never decreases x: deltaX is
+// either 0 or deltaX*(g-m')/(gprev-g) with g<=m' and gprev<g, i.e. a product of non-negative
+// factors, and x += deltaX — in IEEE arithmetic too, since every operation involved is monotone.
+// So x*m at any point is a LOWER BOUND of the value the full iteration returns.  A caller whose
+// decision is monotone non-increasing in the estimate (Jaccard >= tau, hll_a, hll_an) may
+// therefore stop as soon as the decision already fails at the bound: the outcome is identical
+// to running the reference iteration to its end.  When stop() fires, *stopped is set and the
+// bound is returned; otherwise the result is bit-for-bit the reference's sequence of operations.
+template <typename CountT, typename Stop = NeverStop>
+SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1, Stop stop = Stop(), bool* stopped = nullptr) {
     const int q = 64 - p;
     const unsigned long long m = 1ull << p;
     if ((unsigned long long)c[(q + 1) * stride] == m) return __builtin_huge_val();
@@ -53,6 +66,10 @@ SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1) {
     double dx = x;
     const double relerr = 1e-2 / sqrt((double)m);
     while (dx > x * relerr) {
+        if (stop(x * (double)m)) {
+            if (stopped) *stopped = true;
+            return x * (double)m;
+        }
         int kappaM1;
         frexp(x, &kappaM1);
         double xp = ldexp(x, -imax(kMaxP + 1, kappaM1 + 2));

@@ -589,6 +589,19 @@ k_tile_enum(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__
 //   hll_a  include/criteria_sketch.hpp:60-64,36-43   hll_an  :52-58,22-34
 // One CTA (2 warps) handles a 32-row x 128-col quarter of a tile.
 // ============================================================================
+struct StopHll {      // early exit of the MLE: the criterion already fails at the lower bound
+    double tau;
+    unsigned long long e1, e2;
+    float zs;
+    int order_n;
+    int an;
+    __device__ __forceinline__ bool crit(double t) const {
+        return an ? selb::crit_hll_an(tau, e1, e2, t, zs, order_n) : selb::crit_hll_a(tau, e1, e2, t, zs);
+    }
+    // both criteria are non-increasing in t only for Z*sigma >= 0 (the reference hard-codes Z = 1.96)
+    __device__ __forceinline__ bool operator()(double t_lb) const { return zs >= 0.f && !crit(t_lb); }
+};
+
 template <int AN>
 __global__ void __launch_bounds__(64)
 k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
@@ -597,16 +610,17 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                   unsigned long long pair_cap) {
-    constexpr int NB = 64;
-    __shared__ __align__(1024) uint32_t hist[2][NB * 64];
+    extern __shared__ __align__(1024) uint32_t hist_dyn[];   // 2 x [nbins][64 threads]
+    const int nbins = 64 - p_aux + 2;
+    uint32_t* hist0 = hist_dyn;
+    uint32_t* hist1 = hist_dyn + nbins * 64;
     const int unit = blockIdx.x;
     const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2));
     const int r0 = tr.rb * TILE + (unit & 3) * 32, c0 = tr.cb * TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const int words = (1 << p_aux) >> 2;
-    const int nbins = 64 - p_aux + 2;
-    const uint32_t bias0 = hist_bias(hist[0]), bias1 = hist_bias(hist[1]);
-    for (int b = 0; b < NB; ++b) { hist[0][b * 64 + t] = 0; hist[1][b * 64 + t] = 0; }
+    const uint32_t bias0 = hist_bias(hist0), bias1 = hist_bias(hist1);
+    for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
     __syncwarp();
     // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
     for (int item = w; item < 64; item += 2) {
@@ -631,16 +645,18 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
         }
         bool pass0 = false, pass1 = false;
         if (v0) {
-            const double tu = selb::ertl_mle(&hist[0][t], p_aux, 64);
-            pass0 = AN ? selb::crit_hll_an(tau, e[i0], e[k], tu, zs, order_n)
-                       : selb::crit_hll_a(tau, e[i0], e[k], tu, zs);
+            bool stopped = false;
+            const StopHll stop{tau, e[i0], e[k], zs, order_n, AN};
+            const double tu = selb::ertl_mle(hist0 + t, p_aux, 64, stop, &stopped);
+            pass0 = !stopped && stop.crit(tu);
         }
         if (v1) {
-            const double tu = selb::ertl_mle(&hist[1][t], p_aux, 64);
-            pass1 = AN ? selb::crit_hll_an(tau, e[i1], e[k], tu, zs, order_n)
-                       : selb::crit_hll_a(tau, e[i1], e[k], tu, zs);
+            bool stopped = false;
+            const StopHll stop{tau, e[i1], e[k], zs, order_n, AN};
+            const double tu = selb::ertl_mle(hist1 + t, p_aux, 64, stop, &stopped);
+            pass1 = !stopped && stop.crit(tu);
         }
-        for (int b = 0; b < nbins; ++b) { hist[0][b * 64 + t] = 0; hist[1][b * 64 + t] = 0; }
+        for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
         if (pass0) {
             const unsigned long long slot = warp_claim(pair_count);
             if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i0, (uint32_t)k);
@@ -666,8 +682,20 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
     const long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (pi >= npairs) return;
     const uint2 pr = pairs[pi];
-    const double t = selb::ertl_mle(hist + pi * 64, p);
-    const double jac = selb::jaccard(e[pr.x], e[pr.y], t);
+    const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+    // J is non-increasing in t: once it is below tau (and outside the near-tau window) at the
+    // MLE's lower bound the pair can neither be emitted nor listed as near
+    struct StopJ {
+        double tau, slack;
+        unsigned long long e1, e2;
+        __device__ __forceinline__ bool operator()(double t_lb) const {
+            return selb::jaccard(e1, e2, t_lb) < tau - slack;
+        }
+    };
+    bool stopped = false;
+    const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
+    if (stopped) return;
+    const double jac = selb::jaccard(e1, e2, t);
     const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
     if (jac >= tau) {
         const unsigned long long slot = warp_claim(out_count);
@@ -1069,6 +1097,16 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     CKR(c->near_j.ensure((size_t)(1 << 16) * 8));
     const unsigned long long near_cap = 1ull << 16;
     const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
+    size_t hll_smem = 0;
+    if (crit >= SELB200_CRIT_HLL_A) {
+        hll_smem = (size_t)2 * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
+        static bool carve = false;
+        if (!carve) {
+            cudaFuncSetAttribute(k_tile_filter_hll<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_tile_filter_hll<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve = true;
+        }
+    }
 
     // ---- filter -> union passes over tile ranges ---------------------------------------
     std::vector<std::pair<int, int>> work;   // stack of [a,b) tile ranges
@@ -1099,12 +1137,12 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                                            c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                            d_cnt + 1, (unsigned long long)PAIR_CAP);
         } else if (crit == SELB200_CRIT_HLL_A) {
-            k_tile_filter_hll<0><<<nt * 4, 64, 0, s>>>(
+            k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
                 c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
                 nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
                 zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
         } else {
-            k_tile_filter_hll<1><<<nt * 4, 64, 0, s>>>(
+            k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
                 c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
                 nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
                 zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
