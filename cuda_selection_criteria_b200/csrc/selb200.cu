@@ -110,6 +110,7 @@ struct DevBuf {
 constexpr int TILE = 128;          // pair tile edge (rows x cols of the sorted order)
 constexpr int SIG_CHUNK = 16;      // LSH bands staged per shared-memory pass
 constexpr int64_t PAIR_CAP = 8ll << 20;   // pairs per filter->union pass (list 64 MB, histograms 2 GB)
+constexpr int SNAP_MAX = 4096;            // tile ranges per run
 
 }  // namespace
 
@@ -143,6 +144,8 @@ struct selb200_ctx {
     DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
     std::vector<int32_t> h_lo, h_hi;
     int64_t out_count = 0, near_count = 0;
+    int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
+    unsigned long long* h_snap = nullptr;         // pinned: per-range counter snapshots
     const uint64_t* res_keys = nullptr;
     const double* res_j = nullptr;
     std::vector<cudaEvent_t> ev_pool;
@@ -272,8 +275,11 @@ __global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data
 struct SrcPairs {            // pair list of the selection path: sorted positions, mapped through `order`
     const uint2* pairs;
     const int32_t* order;    // nullptr: entries are row indices already
-    long long n;
-    __device__ __forceinline__ long long count() const { return n; }
+    long long n;             // count, or the capacity when n_dev is given
+    const unsigned long long* n_dev;   // optional: the count lives in device memory (no host sync)
+    __device__ __forceinline__ long long count() const {
+        return n_dev ? (long long)min((unsigned long long)n, *n_dev) : n;
+    }
     __device__ __forceinline__ uint2 rows(long long pi, uint2& id) const {
         id = pairs[pi];
         return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
@@ -451,33 +457,53 @@ __device__ __forceinline__ TileRef find_tile(const int32_t* __restrict__ tile_pr
 }
 
 // ============================================================================
-// K3: LSH band signatures.  sig[b][g] = 32-bit mix of the n_rows buckets of band b of the
-// g-th sorted genome.  Equal bands => equal signatures, so "some band equal"
-// (criteria_sketch.hpp:71-79) implies "some signature equal"; the converse is checked
-// exactly by k_smh_verify.
+// K3: LSH band signatures.  For the g-th sorted genome and band b, sig(b,g) = 16 bits of a mix
+// of the band's n_rows buckets.  Equal bands => equal signatures, so "some band equal"
+// (criteria_sketch.hpp:71-79) implies "some signature equal"; the converse is checked exactly
+// by k_smh_verify.  Two bands share one 32-bit word: word w holds bands 2w (low half) and 2w+1.
+//   sigR[w][g] =  sig              (row operand)
+//   sigC[w][g] = -sig per half     (column operand), so  r + c == 0 (mod 2^16)  <=>  equal
+// An odd band count leaves a pad half that can never match (row 0, column 1); pad genomes hold
+// row 0 / column 0x0101.
 // ============================================================================
+__device__ __forceinline__ uint32_t band_sig16(const uint64_t* v, int n_rows) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (int r = 0; r < n_rows; ++r) h = mix64(h ^ v[r]);
+    return (uint32_t)(h >> 48);
+}
+
 __global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long npad, int m_aux,
-                                 int n_rows, int n_bands, uint32_t* __restrict__ sigT) {
-    const long long total = n * n_bands;
+                                 int n_rows, int n_bands, uint32_t* __restrict__ sigR, uint32_t* __restrict__ sigC) {
+    const int nw = (n_bands + 1) >> 1;
+    const long long total = n * nw;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(idx / n);
-        const long long g = idx - (long long)b * n;
-        const uint64_t* v = aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows;
-        uint64_t h = 0x243F6A8885A308D3ull;
-        for (int r = 0; r < n_rows; ++r) h = mix64(h ^ v[r]);
-        sigT[(size_t)b * npad + g] = (uint32_t)(h >> 32);
+        const int w = (int)(idx / n);
+        const long long g = idx - (long long)w * n;
+        const uint64_t* v = aux_sorted + (size_t)g * m_aux;
+        const uint32_t s0 = band_sig16(v + (size_t)(2 * w) * n_rows, n_rows);
+        uint32_t r1 = 0, c1 = 1;
+        if (2 * w + 1 < n_bands) {
+            r1 = band_sig16(v + (size_t)(2 * w + 1) * n_rows, n_rows);
+            c1 = (0u - r1) & 0xffffu;
+        }
+        sigR[(size_t)w * npad + g] = s0 | (r1 << 16);
+        sigC[(size_t)w * npad + g] = ((0u - s0) & 0xffffu) | (c1 << 16);
     }
 }
 
 // ============================================================================
 // K4: smh_a tile pre-filter.  One CTA = one 128x128 tile of the sorted pair space,
-// 256 threads, each an 8x8 register micro-tile.  Per band: 2+2 LDS.128, 64 x (XOR, MIN);
-// acc==0 at the end <=> some band signature matched.  Candidates (rare) leave through
-// warp-aggregated atomics.
+// 256 threads, each an 8x8 register micro-tile.  Per signature word (two bands): 4 LDS.128 and
+// 64 x VIADDMNMX.U16x2 (acc = min(acc, r + c) per 16-bit half); a zero half at the end
+// <=> some band signature matched.  Candidates (rare) leave through warp-aggregated atomics.
 // ============================================================================
+// Accumulate: acc = min(acc, r + c) per 16-bit half in ONE instruction (VIADDMNMX.U16x2); the column
+// operand holds the negated halves, so a half reaches 0 exactly when the two signatures are equal.
+// Measured alternatives on B200 (n=100k, 4.66e8 CB pairs): XOR+MIN on 32-bit signatures 1.22 ms;
+// (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
 __global__ void __launch_bounds__(256)
-k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands,
+k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
                   const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
                   int tile0, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
@@ -494,13 +520,17 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
 
-    for (int b0 = 0; b0 < n_bands; b0 += SIG_CHUNK) {
-        const int nb = min(SIG_CHUNK, n_bands - b0);
+    for (int b0 = 0; b0 < n_words; b0 += SIG_CHUNK) {
+        const int nb = min(SIG_CHUNK, n_words - b0);
         __syncthreads();
-        for (int idx = tid; idx < nb * TILE; idx += 256) {
-            const int bb = idx >> 7, x = idx & (TILE - 1);
-            sR[bb][x] = __ldg(sigT + (size_t)(b0 + bb) * npad + r0 + x);
-            sC[bb][x] = __ldg(sigT + (size_t)(b0 + bb) * npad + c0 + x);
+        for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per load
+            const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
+            if (part < 32)
+                *reinterpret_cast<uint4*>(&sR[bb][x]) =
+                    __ldg(reinterpret_cast<const uint4*>(sigR + (size_t)(b0 + bb) * npad + r0 + x));
+            else
+                *reinterpret_cast<uint4*>(&sC[bb][x]) =
+                    __ldg(reinterpret_cast<const uint4*>(sigC + (size_t)(b0 + bb) * npad + c0 + x));
         }
         __syncthreads();
         for (int bb = 0; bb < nb; ++bb) {
@@ -513,15 +543,15 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = min(acc[a][b], rs[a] ^ cs[b]);
+                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
         }
     }
     uint32_t any = 0xffffffffu;
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) any = min(any, acc[a][b]);
-    if (any != 0) return;
+        for (int b = 0; b < 8; ++b) any = __vminu2(any, acc[a][b]);
+    if ((any & 0xffffu) != 0 && (any >> 16) != 0) return;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int i = r0 + ty * 8 + a;
@@ -529,7 +559,7 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands
         const int l = lo[i], h = hi[i];
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            if (acc[a][b] != 0) continue;
+            if ((acc[a][b] & 0xffffu) != 0 && (acc[a][b] >> 16) != 0) continue;
             const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
             if (k < l || k > h) continue;
             const unsigned long long slot = warp_claim(cand_count);
@@ -538,28 +568,40 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigT, long long npad, int n_bands
     }
 }
 
-// exact smh_a on the candidates: include/criteria_sketch.hpp:66-81.  Warp per candidate,
-// lanes take bands round-robin and stop at the first differing bucket.
+// exact smh_a on the candidates: include/criteria_sketch.hpp:66-81.  Thread per candidate.
+// A band can only be equal if its 16-bit signatures are, so the thread re-reads the (L2-resident)
+// signature words of both genomes, and compares bucket by bucket only the bands whose signatures
+// match, stopping at the first band that is really equal: ~2 x 64 B of auxiliary sketch per
+// candidate instead of 2 x 8m B.
 __global__ void __launch_bounds__(256)
-k_smh_verify(const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
-             const uint2* __restrict__ cand, long long ncand, uint2* __restrict__ pairs,
-             unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    if (warp >= ncand) return;
-    const uint2 pr = cand[warp];
-    const uint64_t* v1 = aux_sorted + (size_t)pr.x * m_aux;
-    const uint64_t* v2 = aux_sorted + (size_t)pr.y * m_aux;
-    bool hit = false;
-    for (int b = lane; b < n_bands && !hit; b += 32) {
-        bool eq = true;
-        for (int r = 0; r < n_rows; ++r)
-            if (v1[b * n_rows + r] != v2[b * n_rows + r]) { eq = false; break; }
-        hit = eq;
-    }
-    if (__any_sync(0xffffffffu, hit) && lane == 0) {
-        const unsigned long long slot = atomicAdd(pair_count, 1ull);
-        if (slot < pair_cap) pairs[slot] = pr;
+k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict__ sigR, long long npad, int m_aux,
+             int n_rows, int n_bands, const uint2* __restrict__ cand,
+             const unsigned long long* __restrict__ ncand_dev, unsigned long long cand_cap,
+             uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
+    const long long ncand = (long long)min(*ncand_dev, cand_cap);
+    const int n_words = (n_bands + 1) >> 1;
+    for (long long ci = blockIdx.x * (long long)blockDim.x + threadIdx.x; ci < ncand;
+         ci += (long long)gridDim.x * blockDim.x) {
+        const uint2 pr = cand[ci];
+        const uint64_t* v1 = aux_sorted + (size_t)pr.x * m_aux;
+        const uint64_t* v2 = aux_sorted + (size_t)pr.y * m_aux;
+        bool hit = false;
+        for (int w = 0; w < n_words && !hit; ++w) {
+            const uint32_t x = __ldg(sigR + (size_t)w * npad + pr.x) ^ __ldg(sigR + (size_t)w * npad + pr.y);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int b = 2 * w + half;
+                if (hit || b >= n_bands || ((x >> (16 * half)) & 0xffffu) != 0) continue;
+                bool eq = true;
+                for (int r = 0; r < n_rows; ++r)
+                    if (__ldg(v1 + (size_t)b * n_rows + r) != __ldg(v2 + (size_t)b * n_rows + r)) { eq = false; break; }
+                hit = eq;
+            }
+        }
+        if (hit) {
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = pr;
+        }
     }
 }
 
@@ -673,16 +715,13 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
 //   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
 // ============================================================================
 __global__ void __launch_bounds__(128)
-k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs, long long npairs,
+k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
+                const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
                 const unsigned long long* __restrict__ e, int p, double tau,
                 uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
                 unsigned long long* __restrict__ out_count, unsigned long long out_cap,
                 uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
                 unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
-    const long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (pi >= npairs) return;
-    const uint2 pr = pairs[pi];
-    const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
     // J is non-increasing in t: once it is below tau (and outside the near-tau window) at the
     // MLE's lower bound the pair can neither be emitted nor listed as near
     struct StopJ {
@@ -692,18 +731,24 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
             return selb::jaccard(e1, e2, t_lb) < tau - slack;
         }
     };
-    bool stopped = false;
-    const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
-    if (stopped) return;
-    const double jac = selb::jaccard(e1, e2, t);
-    const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
-    if (jac >= tau) {
-        const unsigned long long slot = warp_claim(out_count);
-        if (slot < out_cap) { out_keys[slot] = key; out_j[slot] = jac; }
-    }
-    if (fabs(jac - tau) <= 1e-6 * fabs(tau)) {
-        const unsigned long long slot = warp_claim(near_count);
-        if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
+    const long long npairs = (long long)min(*npairs_dev, npairs_cap);
+    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
+         pi += (long long)gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[pi];
+        const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+        bool stopped = false;
+        const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
+        if (stopped) continue;
+        const double jac = selb::jaccard(e1, e2, t);
+        const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
+        if (jac >= tau) {
+            const unsigned long long slot = warp_claim(out_count);
+            if (slot < out_cap) { out_keys[slot] = key; out_j[slot] = jac; }
+        }
+        if (fabs(jac - tau) <= 1e-6 * fabs(tau)) {
+            const unsigned long long slot = warp_claim(near_count);
+            if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
+        }
     }
 }
 
@@ -749,10 +794,11 @@ int launch_pair_hist_t(cudaStream_t stream, int sm_count, const uint8_t* regs, s
 }
 
 int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const int32_t* order,
-                     const uint2* pairs, int64_t npairs, uint32_t* hist_out) {
+                     const uint2* pairs, int64_t npairs, uint32_t* hist_out,
+                     const unsigned long long* npairs_dev = nullptr) {
     if (npairs <= 0) return SELB200_OK;
     if (m >= 512) {
-        SrcPairs src{pairs, order, (long long)npairs};
+        SrcPairs src{pairs, order, (long long)npairs, npairs_dev};
         EpiWriteHist epi{hist_out};
         return launch_pair_hist_t(c->stream, c->sm_count, regs, m, m, p, npairs, src, epi);
     }
@@ -933,6 +979,7 @@ void selb200_destroy(selb200_ctx* c) {
                       &c->near_keys, &c->near_j};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_snap) cudaFreeHost(c->h_snap);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1081,11 +1128,15 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_filter, t_verify, t_union, t_est;
     if (crit == SELB200_CRIT_SMH_A && smh_shape_ok) {
         cudaEvent_t a = c->ev();
-        CKR(c->sigT.ensure((size_t)n_bands * c->npad * 4));
-        CK(cudaMemsetAsync(c->sigT.p, 0, (size_t)n_bands * c->npad * 4, s));
-        const int grid = (int)std::min<int64_t>(((int64_t)n * n_bands + 255) / 256, (int64_t)c->sm_count * 16);
+        const int n_words = (n_bands + 1) / 2;
+        const size_t sig_bytes = (size_t)n_words * c->npad * 4;
+        CKR(c->sigT.ensure(2 * sig_bytes));
+        // pad genomes: row halves 0, column halves 1 -> never match
+        CK(cudaMemsetAsync(c->sigT.p, 0, sig_bytes, s));
+        CK(cudaMemsetAsync(c->sigT.as<uint8_t>() + sig_bytes, 0x01, sig_bytes, s));
+        const int grid = (int)std::min<int64_t>(((int64_t)n * n_words + 255) / 256, (int64_t)c->sm_count * 16);
         k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
-                                              c->sigT.as<uint32_t>());
+                                              c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
         CK(cudaGetLastError());
         st.launches++;
         t_filter.push_back({a, c->ev()});
@@ -1109,126 +1160,124 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     }
 
     // ---- filter -> union passes over tile ranges ---------------------------------------
-    std::vector<std::pair<int, int>> work;   // stack of [a,b) tile ranges
+    // Optimistic, sync-free pipeline: every kernel after the filter reads its work count from
+    // device memory (persistent grids), list capacities are fixed up front, and the counters of
+    // each range are snapshotted into pinned host memory.  One synchronisation at the end checks
+    // the snapshots; an overflow (rare: a filter far less selective than the capacities assume)
+    // grows the buffers / halves the offending range and the whole pass is redone.
+    std::vector<std::pair<int, int>> ranges;   // [a,b) tile ranges, in order
     if (smh_shape_ok && t_end > t_begin) {
-        // CB-only fills whole tiles, so cut ranges the pair list is sure to hold; the
-        // selective criteria start with the whole shard and split on overflow.
+        // CB-only fills whole tiles, so its ranges are cut to what the pair list is sure to hold
         const int step = (crit == SELB200_CRIT_CB) ? (int)(PAIR_CAP / (TILE * TILE)) : (t_end - t_begin);
-        for (int a = t_end; a > t_begin;) {
-            const int b = a;
-            a = std::max(t_begin, a - step);
-            work.push_back({a, b});
-        }
+        for (int a = t_begin; a < t_end; a += step) ranges.push_back({a, std::min(t_end, a + step)});
     }
-    int64_t total_out = 0;
-    while (!work.empty()) {
-        const std::pair<int, int> rg = work.back();
-        work.pop_back();
-        const int nt = rg.second - rg.first;
-        CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs
-        cudaEvent_t f0 = c->ev();
-        if (crit == SELB200_CRIT_SMH_A) {
-            k_tile_filter_smh<<<nt, 256, 0, s>>>(c->sigT.as<uint32_t>(), c->npad, n_bands, c->tile_prefix.as<int32_t>(),
-                                                 c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(),
-                                                 c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0,
-                                                 (unsigned long long)PAIR_CAP);
-        } else if (crit == SELB200_CRIT_CB) {
-            k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first,
-                                           c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
-                                           d_cnt + 1, (unsigned long long)PAIR_CAP);
-        } else if (crit == SELB200_CRIT_HLL_A) {
-            k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
-                c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
-                nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
-                zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
-        } else {
-            k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
-                c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
-                nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau,
-                zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
-        }
-        CK(cudaGetLastError());
-        st.launches++;
-        cudaEvent_t f1 = c->ev();
-        unsigned long long h_cnt[2] = {0, 0};
-        if (crit == SELB200_CRIT_SMH_A) {
-            CK(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            if (h_cnt[0] > (unsigned long long)PAIR_CAP) {
-                if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %llu candidates", h_cnt[0]);
-                const int mid = rg.first + nt / 2;
-                work.push_back({mid, rg.second});
-                work.push_back({rg.first, mid});
-                continue;
+    if (crit == SELB200_CRIT_CB) c->hist_cap_pairs = PAIR_CAP;
+    if (c->hist_cap_pairs < (1ll << 20)) c->hist_cap_pairs = 1ll << 20;
+    if (c->out_cap < (1ll << 21)) c->out_cap = 1ll << 21;
+    if (!c->h_snap) CK(cudaMallocHost(&c->h_snap, SNAP_MAX * 4 * sizeof(unsigned long long)));
+    unsigned long long h_fin[4] = {0, 0, 0, 0};
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 40) return fail(SELB200_ENOMEM, "candidate lists keep overflowing");
+        if ((int)ranges.size() > SNAP_MAX) return fail(SELB200_ENOMEM, "too many tile ranges (%zu)", ranges.size());
+        CKR(c->hist.ensure((size_t)c->hist_cap_pairs * 64 * sizeof(uint32_t)));
+        CKR(c->out_keys.ensure((size_t)c->out_cap * 8));
+        CKR(c->out_j.ensure((size_t)c->out_cap * 8));
+        CK(cudaMemsetAsync(d_cnt, 0, 32, s));
+        t_filter.resize(crit == SELB200_CRIT_SMH_A && smh_shape_ok ? 1 : 0);   // keep the signature pass
+        t_verify.clear(); t_union.clear(); t_est.clear();
+        const unsigned long long pair_lim = (unsigned long long)std::min<int64_t>(PAIR_CAP, c->hist_cap_pairs);
+        for (size_t ri = 0; ri < ranges.size(); ++ri) {
+            const std::pair<int, int> rg = ranges[ri];
+            const int nt = rg.second - rg.first;
+            CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs of this range
+            cudaEvent_t f0 = c->ev();
+            if (crit == SELB200_CRIT_SMH_A) {
+                const int n_words = (n_bands + 1) / 2;
+                k_tile_filter_smh<<<nt, 256, 0, s>>>(
+                    c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words,
+                    c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(),
+                    c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP);
+            } else if (crit == SELB200_CRIT_CB) {
+                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first,
+                                               c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
+                                               d_cnt + 1, (unsigned long long)PAIR_CAP);
+            } else if (crit == SELB200_CRIT_HLL_A) {
+                k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
+                    c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
+                    (unsigned long long)PAIR_CAP);
+            } else {
+                k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
+                    c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
+                    (unsigned long long)PAIR_CAP);
             }
+            CK(cudaGetLastError());
+            st.launches++;
+            cudaEvent_t f1 = c->ev();
             t_filter.push_back({f0, f1});
-            st.pairs_cand += (int64_t)h_cnt[0];
-            if (h_cnt[0]) {
-                const long long nc = (long long)h_cnt[0];
-                k_smh_verify<<<(unsigned)((nc * 32 + 255) / 256), 256, 0, s>>>(
-                    c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, c->cand.as<uint2>(), nc,
-                    c->pairs.as<uint2>(), d_cnt + 1, (unsigned long long)PAIR_CAP);
+            if (crit == SELB200_CRIT_SMH_A) {
+                k_smh_verify<<<c->sm_count * 8, 256, 0, s>>>(
+                    c->aux_sorted.as<uint64_t>(), c->sigT.as<uint32_t>(), c->npad, c->aux_len, n_rows, n_bands,
+                    c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP, c->pairs.as<uint2>(), d_cnt + 1,
+                    (unsigned long long)PAIR_CAP);
                 CK(cudaGetLastError());
                 st.launches++;
             }
+            // ---- K5 + K6 --------------------------------------------------------------
+            cudaEvent_t u0 = c->ev();
+            if (crit == SELB200_CRIT_SMH_A) t_verify.push_back({f1, u0});
+            CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
+                                 (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + 1));
+            st.launches++;
+            cudaEvent_t u1 = c->ev();
+            k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
+                c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + 1, pair_lim,
+                c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
+                d_cnt + 2, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                d_cnt + 3, near_cap);
+            CK(cudaGetLastError());
+            st.launches++;
+            cudaEvent_t u2 = c->ev();
+            t_union.push_back({u0, u1});
+            t_est.push_back({u1, u2});
+            CK(cudaMemcpyAsync(c->h_snap + ri * 4, d_cnt, 32, cudaMemcpyDeviceToHost, s));
         }
-        CK(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        const long long np = (long long)h_cnt[1];
-        if (np > PAIR_CAP) {
-            if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %lld pairs", np);
-            const int mid = rg.first + nt / 2;
-            work.push_back({mid, rg.second});
-            work.push_back({rg.first, mid});
-            continue;
+        // ---- overflow check ------------------------------------------------------------------
+        bool redo = false;
+        std::vector<std::pair<int, int>> next;
+        int64_t cand_sum = 0, pair_sum = 0;
+        for (size_t ri = 0; ri < ranges.size(); ++ri) {
+            const unsigned long long* sn = c->h_snap + ri * 4;
+            const bool too_many = sn[0] > (unsigned long long)PAIR_CAP || sn[1] > (unsigned long long)PAIR_CAP;
+            if (too_many) {
+                const int nt = ranges[ri].second - ranges[ri].first;
+                if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %llu pairs", std::max(sn[0], sn[1]));
+                const int mid = ranges[ri].first + nt / 2;
+                next.push_back({ranges[ri].first, mid});
+                next.push_back({mid, ranges[ri].second});
+                redo = true;
+                continue;
+            }
+            next.push_back(ranges[ri]);
+            if ((int64_t)sn[1] > c->hist_cap_pairs) { c->hist_cap_pairs = (int64_t)sn[1]; redo = true; }
+            cand_sum += crit == SELB200_CRIT_SMH_A ? (int64_t)sn[0] : (int64_t)sn[1];
+            pair_sum += (int64_t)sn[1];
         }
-        if (crit != SELB200_CRIT_SMH_A) { t_filter.push_back({f0, f1}); st.pairs_cand += np; }
-        st.pairs_aux += np;
-        st.batches++;
-        if (np == 0) continue;
-        // ---- locality: the selective filters emit in atomic-arrival order; ordering the list by
-        // column index keeps the rows a wave of warps touches inside L2 (k_tile_enum already
-        // emits tile by tile) ----------------------------------------------------------------
-        const uint2* d_pairs = c->pairs.as<uint2>();
-        if (crit != SELB200_CRIT_CB && np > 1) {
-            int nbits = 1;
-            while ((1ll << nbits) < (long long)n) ++nbits;
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, c->pairs.as<uint64_t>(), c->cand.as<uint64_t>(),
-                                              (int)np, 32, 32 + nbits, s));
-            CKR(c->cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tmp_bytes, c->pairs.as<uint64_t>(),
-                                              c->cand.as<uint64_t>(), (int)np, 32, 32 + nbits, s));
-            d_pairs = c->cand.as<uint2>();
+        if (!ranges.empty()) std::memcpy(h_fin, c->h_snap + (ranges.size() - 1) * 4, 32);
+        if ((int64_t)h_fin[2] > c->out_cap) { c->out_cap = (int64_t)h_fin[2] + (1 << 16); redo = true; }
+        if (!redo) {
+            st.pairs_cand = cand_sum;
+            st.pairs_aux = pair_sum;
+            st.batches = (int32_t)ranges.size();
+            break;
         }
-        // ---- K5 + K6 ------------------------------------------------------------------
-        CKR(c->hist.ensure((size_t)np * 64 * sizeof(uint32_t)));
-        const size_t need = (size_t)(total_out + np);
-        CKR(c->out_keys.grow_keep(need * 8, (size_t)total_out * 8, s));
-        CKR(c->out_j.grow_keep(need * 8, (size_t)total_out * 8, s));
-        cudaEvent_t u0 = c->ev();
-        if (d_pairs != c->pairs.as<uint2>()) t_verify.push_back({f1, u0});   // verify + locality sort
-        CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), d_pairs, np,
-                             c->hist.as<uint32_t>()));
-        st.launches++;
-        cudaEvent_t u1 = c->ev();
-        k_estimate_emit<<<(unsigned)((np + 127) / 128), 128, 0, s>>>(
-            c->hist.as<uint32_t>(), d_pairs, np, c->e_sorted.as<unsigned long long>(), c->p, tau,
-            c->out_keys.as<uint64_t>(), c->out_j.as<double>(), d_cnt + 2, (unsigned long long)need,
-            c->near_keys.as<uint64_t>(), c->near_j.as<double>(), d_cnt + 3, near_cap);
-        CK(cudaGetLastError());
-        st.launches++;
-        cudaEvent_t u2 = c->ev();
-        t_union.push_back({u0, u1});
-        t_est.push_back({u1, u2});
-        unsigned long long h_out = 0;
-        CK(cudaMemcpyAsync(&h_out, d_cnt + 2, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        total_out = (int64_t)h_out;
+        ranges.swap(next);
+        st.launches = 1 + (crit == SELB200_CRIT_SMH_A ? 1 : 0);
     }
-    unsigned long long h_fin[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_fin, d_cnt, 32, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     c->out_count = (int64_t)h_fin[2];
     c->near_count = (int64_t)std::min<unsigned long long>(h_fin[3], near_cap);
     st.pairs_out = c->out_count;
@@ -1243,12 +1292,14 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         CKR(c->out_keys2.ensure((size_t)cnt * 8));
         CKR(c->out_j2.ensure((size_t)cnt * 8));
         size_t tmp_bytes = 0;
+        int nbits = 1;
+        while ((1ll << nbits) < (long long)n) ++nbits;       // key = i<<32 | k with i,k < n
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->out_keys.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
-                                           c->out_j.as<double>(), c->out_j2.as<double>(), (int)cnt, 0, 64, s));
+                                           c->out_j.as<double>(), c->out_j2.as<double>(), (int)cnt, 0, 32 + nbits, s));
         CKR(c->cub_tmp.ensure(tmp_bytes));
         CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->out_keys.as<uint64_t>(),
                                            c->out_keys2.as<uint64_t>(), c->out_j.as<double>(), c->out_j2.as<double>(),
-                                           (int)cnt, 0, 64, s));
+                                           (int)cnt, 0, 32 + nbits, s));
         c->res_keys = c->out_keys2.as<uint64_t>();
         c->res_j = c->out_j2.as<double>();
     }

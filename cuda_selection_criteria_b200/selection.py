@@ -108,13 +108,17 @@ class Selection:
             _lib.check(self._L.selb200_load_host(self._h, n, p, r_ptr, stp, aux_kind, aux_len, a_ptr))
         self.n = n
         self.p = p
+        self._order = None
         return self
 
     def order(self):
+        if getattr(self, "_order", None) is not None:
+            return self._order
         cards = np.empty(self.n, np.float64)
         order = np.empty(self.n, np.int32)
         _lib.check(self._L.selb200_get_order(self._h, cards.ctypes.data, order.ctypes.data))
-        return cards, order
+        self._order = (cards, order)
+        return self._order
 
     # -- run ------------------------------------------------------------------------------
     def run(self, tau: float = 0.9, criterion: str | int = "smh_a", z_score: float = 1.96, order_n: int = 1,
