@@ -49,7 +49,8 @@ SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1, Stop stop = Stop
     const unsigned long long m = 1ull << p;
     if ((unsigned long long)c[(q + 1) * stride] == m) return __builtin_huge_val();
     int kMin, kMax;
-    for (kMin = 0; c[kMin * stride] == 0; ++kMin) {}
+    for (kMin = 0; kMin <= q + 1 && c[kMin * stride] == 0; ++kMin) {}
+    if (kMin > q + 1) return 0.;   // empty histogram: cannot happen for a sketch (counts sum to m); guards the scan
     const int kMinP = imax(1, kMin);
     for (kMax = q + 1; kMax && c[kMax * stride] == 0; --kMax) {}
     const int kMaxP = imin(q, kMax);

@@ -118,6 +118,8 @@ struct selb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;          // H2D staging of load_host, overlapped with the run stream
+    std::vector<cudaEvent_t> copy_events;
     int sm_count = 148;
 
     // loaded sketches
@@ -286,6 +288,17 @@ struct SrcPairs {            // pair list of the selection path: sorted position
     }
 };
 
+struct SrcSelf {             // rows g0..g0+n-1 against themselves: per-genome histograms (max(a,a) = a)
+    long long g0, n;
+    const uint32_t* max_seen;   // written by k_max_byte earlier on the stream: a register above
+    uint32_t max_ok;            // 64-p+1 would index past the histogram, so nothing is processed
+    __device__ __forceinline__ long long count() const { return *max_seen > max_ok ? 0 : n; }
+    __device__ __forceinline__ uint2 rows(long long pi, uint2& id) const {
+        id = make_uint2((uint32_t)(g0 + pi), (uint32_t)(g0 + pi));
+        return id;
+    }
+};
+
 struct EpiWriteHist {        // histogram rows for k_estimate_emit
     uint32_t* out;
     __device__ __forceinline__ void operator()(long long pi, uint2, uint32_t s0, uint32_t s1, uint32_t lane) const {
@@ -371,6 +384,21 @@ k_pair_hist_small(const uint8_t* __restrict__ regs, size_t m, const uint2* __res
     }
 }
 
+__global__ void k_iota_i32(int32_t* v, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+// sorted cardinalities -> truncated e (size_t e = card, selection.cpp:275,280) + tie detection
+__global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long n, unsigned long long* __restrict__ e,
+                              uint32_t* __restrict__ tie_flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cd = cards_sorted[i];
+    e[i] = (unsigned long long)cd;
+    if (i + 1 < n && !(cd < cards_sorted[i + 1])) *tie_flag = 1;
+}
+
 __global__ void k_iota_pairs(uint2* pairs, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) pairs[i] = make_uint2((uint32_t)i, (uint32_t)i);
@@ -378,9 +406,11 @@ __global__ void k_iota_pairs(uint2* pairs, long long n) {
 
 // per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
 __global__ void k_genome_cards(const uint32_t* __restrict__ hist, const double* __restrict__ stored, long long n,
-                               int p, double* __restrict__ cards) {
+                               int p, double* __restrict__ cards, const uint32_t* __restrict__ max_seen,
+                               uint32_t max_ok) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (*max_seen > max_ok) { cards[i] = 0.; return; }   // malformed input: the load fails after the sync
     if (stored && stored[i] >= 0.) { cards[i] = stored[i]; return; }
     cards[i] = selb::ertl_mle(hist + i * 64, p);
 }
@@ -863,46 +893,109 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_
         c->d_regs = regs;
     } else {
         CKR(c->regs_own.ensure(reg_bytes));
-        CK(cudaMemcpyAsync(c->regs_own.p, regs, reg_bytes, cudaMemcpyHostToDevice, s));
         c->d_regs = c->regs_own.as<uint8_t>();
     }
-    // auxiliary sketches: staged in `cand` scratch when they arrive from the host
-    const void* d_aux = aux;
-    if (aux_kind != SELB200_AUX_NONE && !aux_on_device) {
-        CKR(c->cand.ensure((size_t)n * aux_row_bytes));
-        CK(cudaMemcpyAsync(c->cand.p, aux, (size_t)n * aux_row_bytes, cudaMemcpyHostToDevice, s));
-        d_aux = c->cand.p;
-    }
-    CKR(validate_registers(c, c->d_regs, reg_bytes, p, "primary"));
-    if (aux_kind == SELB200_AUX_HLL) CKR(validate_registers(c, d_aux, (size_t)n * aux_row_bytes, aux_len, "auxiliary"));
-
-    // per-genome histogram -> cardinality (device), then the reference's host sort
-    CKR(c->pairs.ensure((size_t)n * sizeof(uint2)));
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
-    k_iota_pairs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->pairs.as<uint2>(), n);
-    CK(cudaGetLastError());
-    CKR(launch_pair_hist(c, c->d_regs, c->m, p, nullptr, c->pairs.as<uint2>(), n, c->hist.as<uint32_t>()));
+    CKR(c->counters.ensure(64));
+    CK(cudaMemsetAsync(c->counters.p, 0, 64, s));
     double* d_stored = nullptr;
     if (stored) {
         CKR(c->out_j.ensure((size_t)n * sizeof(double)));
         CK(cudaMemcpyAsync(c->out_j.p, stored, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
         d_stored = c->out_j.as<double>();
     }
-    k_genome_cards<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c->hist.as<uint32_t>(), d_stored, n, p,
-                                                               c->cards_in.as<double>());
-    CK(cudaGetLastError());
-    std::vector<double> cards((size_t)n);
-    CK(cudaMemcpyAsync(cards.data(), c->cards_in.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    selb200_sort_order(n, cards.data(), c->h_order.data());
-    for (int64_t i = 0; i < n; ++i) {
-        const double cd = cards[(size_t)c->h_order[(size_t)i]];
-        c->h_cards_sorted[(size_t)i] = cd;
-        c->h_e[(size_t)i] = (uint64_t)(size_t)cd;       // size_t e = card (selection.cpp:275,280)
+    // ---- chunked pipeline: the H2D copy of chunk c+1 (copy stream) overlaps validation, the
+    // per-genome histogram and the cardinality MLE of chunk c (run stream) -------------------
+    const int64_t rows_per_chunk = regs_on_device ? n : std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)c->m);
+    size_t ev_i = 0;
+    auto copy_done = [&]() -> int {          // run stream waits for what the copy stream has queued
+        if (ev_i == c->copy_events.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->copy_events.push_back(e);
+        }
+        CK(cudaEventRecord(c->copy_events[ev_i], c->copy_stream));
+        CK(cudaStreamWaitEvent(s, c->copy_events[ev_i], 0));
+        ++ev_i;
+        return SELB200_OK;
+    };
+    // auxiliary sketches first (small): staged in `cand` scratch when they arrive from the host
+    const void* d_aux = aux;
+    if (aux_kind != SELB200_AUX_NONE && !aux_on_device) {
+        CKR(c->cand.ensure((size_t)n * aux_row_bytes));
+        CK(cudaMemcpyAsync(c->cand.p, aux, (size_t)n * aux_row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        d_aux = c->cand.p;
     }
-    CKR(upload(c->order_dev, c->h_order, s));
-    CKR(upload(c->e_sorted, c->h_e, s));
+    for (int64_t g0 = 0; g0 < n; g0 += rows_per_chunk) {
+        const int64_t g1 = std::min(n, g0 + rows_per_chunk), rows = g1 - g0;
+        if (!regs_on_device) {
+            CK(cudaMemcpyAsync(c->regs_own.as<uint8_t>() + (size_t)g0 * c->m, regs + (size_t)g0 * c->m,
+                               (size_t)rows * c->m, cudaMemcpyHostToDevice, c->copy_stream));
+            CKR(copy_done());
+        }
+        const size_t n16 = (size_t)rows * c->m / 16;
+        k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
+            reinterpret_cast<const uint4*>(c->d_regs + (size_t)g0 * c->m), n16, c->counters.as<uint32_t>());
+        CK(cudaGetLastError());
+        SrcSelf src{(long long)g0, (long long)rows, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1)};
+        EpiWriteHist epi{c->hist.as<uint32_t>() + (size_t)g0 * 64};
+        CKR(launch_pair_hist_t(s, c->sm_count, c->d_regs, c->m, c->m, p, rows, src, epi));
+        k_genome_cards<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(
+            c->hist.as<uint32_t>() + (size_t)g0 * 64, d_stored ? d_stored + g0 : nullptr, rows, p,
+            c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1));
+        CK(cudaGetLastError());
+    }
+    if (aux_kind == SELB200_AUX_HLL) {
+        if (!aux_on_device && regs_on_device) CKR(copy_done());
+        const size_t n16 = (size_t)n * aux_row_bytes / 16;
+        k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
+            reinterpret_cast<const uint4*>(d_aux), n16, c->counters.as<uint32_t>() + 1);
+        CK(cudaGetLastError());
+    } else if (aux_kind == SELB200_AUX_SMH && !aux_on_device && regs_on_device) {
+        CKR(copy_done());
+    }
+    // ---- sort by cardinality.  Distinct keys have ONE sorted order, so a device radix sort then
+    // equals the reference's std::sort; any tie falls back to that exact std::sort on the host
+    // (its unstable tie order depends on the whole sequence, selection.cpp:251-256). --------------
+    CKR(c->order_dev.ensure((size_t)n * 4));
+    CKR(c->e_sorted.ensure((size_t)n * 8));
+    CKR(c->pairs.ensure((size_t)n * 4));          // iota scratch
+    CKR(c->out_keys.ensure((size_t)n * 8));       // sorted cardinalities
+    k_iota_i32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->pairs.as<int32_t>(), n);
+    CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->cards_in.as<double>(), c->out_keys.as<double>(),
+                                       c->pairs.as<int32_t>(), c->order_dev.as<int32_t>(), (int)n, 0, 64, s));
+    CKR(c->cub_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->cards_in.as<double>(), c->out_keys.as<double>(),
+                                       c->pairs.as<int32_t>(), c->order_dev.as<int32_t>(), (int)n, 0, 64, s));
+    k_sorted_prep<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->out_keys.as<double>(), n,
+                                                               c->e_sorted.as<unsigned long long>(),
+                                                               c->counters.as<uint32_t>() + 2);
+    CK(cudaGetLastError());
+    uint32_t h_flags[4] = {0, 0, 0, 0};   // max primary register, max aux register, tie flag
+    CK(cudaMemcpyAsync(h_flags, c->counters.p, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_cards_sorted.data(), c->out_keys.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c->h_order.data(), c->order_dev.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_flags[0] > (uint32_t)(64 - p + 1))
+        return fail(SELB200_EINVAL, "primary sketch holds register value %u > %u (= 64-p+1, p=%d): not an HLL of that precision",
+                    h_flags[0], (uint32_t)(64 - p + 1), p);
+    if (aux_kind == SELB200_AUX_HLL && h_flags[1] > (uint32_t)(64 - aux_len + 1))
+        return fail(SELB200_EINVAL, "auxiliary sketch holds register value %u > %u (= 64-p+1, p=%d)", h_flags[1],
+                    (uint32_t)(64 - aux_len + 1), aux_len);
+    if (h_flags[2]) {
+        std::vector<double> cards((size_t)n);
+        CK(cudaMemcpyAsync(cards.data(), c->cards_in.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        selb200_sort_order(n, cards.data(), c->h_order.data());
+        for (int64_t i = 0; i < n; ++i) c->h_cards_sorted[(size_t)i] = cards[(size_t)c->h_order[(size_t)i]];
+        CKR(upload(c->order_dev, c->h_order, s));
+    }
+    for (int64_t i = 0; i < n; ++i)
+        c->h_e[(size_t)i] = (uint64_t)(size_t)c->h_cards_sorted[(size_t)i];   // size_t e = card (selection.cpp:275,280)
+    if (h_flags[2]) CKR(upload(c->e_sorted, c->h_e, s));
 
     if (aux_kind == SELB200_AUX_SMH) {
         CKR(c->aux_sorted.ensure((size_t)n * aux_row_bytes));
@@ -965,6 +1058,10 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(SELB200_ECUDA, "cudaStreamCreate failed");
+    }
     *out = c;
     return SELB200_OK;
 }
@@ -980,6 +1077,8 @@ void selb200_destroy(selb200_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_snap) cudaFreeHost(c->h_snap);
+    for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
