@@ -211,7 +211,7 @@ def cpu_baseline(a, steps: int = 1, warmup: int = 0):
         shutil.rmtree(td, ignore_errors=True)
 
 
-def run_reference_arm(a, rank: int, world: int):
+def run_reference_arm(a, rank: int, world: int, out):
     if rank != 0:
         return
     cb = cpu_baseline(a, steps=a.steps, warmup=a.warmup)
@@ -222,19 +222,29 @@ def run_reference_arm(a, rank: int, world: int):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
+def _protect_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL's version banner, torchrun notes) write
+    there too, so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
     a = parse()
+    real_stdout = _protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
-        run_reference_arm(a, rank, world)
+        run_reference_arm(a, rank, world, real_stdout)
         return
 
     import torch
@@ -285,7 +295,8 @@ def main():
     stats_acc = []
 
     def step_resident():
-        res = sel.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False)
+        res = sel.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
+                      sort_output=(world == 1))   # with several ranks the merged list is sorted once on rank 0
         kp, jp, cnt = sel.result_device_ptrs()
         keys = sdist.device_tensor(kp, cnt, "<i8", local)
         jac = sdist.device_tensor(jp, cnt, "<f8", local)
@@ -368,7 +379,8 @@ def main():
                         aux_d.copy_(aux_h, non_blocking=True)
                 sdist.broadcast_sketches(regs_d, aux_d, src=0)
                 sel2.load(regs_d, aux_d, aux_kind)
-            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False)
+            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
+                     sort_output=(world == 1))
             kp, jp, cnt = sel2.result_device_ptrs()
             keys = sdist.device_tensor(kp, cnt, "<i8", local)
             jac = sdist.device_tensor(jp, cnt, "<f8", local)
@@ -415,7 +427,7 @@ def main():
                 "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(sum(s["launches"] for s in stats_acc)),
                 "roofline": roofline, "cpu_baseline": cb}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     sel.close()
     if world > 1:
         dist.destroy_process_group()

@@ -535,12 +535,12 @@ __global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long l
 __global__ void __launch_bounds__(256)
 k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
                   const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
-                  int tile0, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                  int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
                   unsigned long long cand_cap) {
     __shared__ __align__(16) uint32_t sR[SIG_CHUNK][TILE];
     __shared__ __align__(16) uint32_t sC[SIG_CHUNK][TILE];
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x);
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x * tile_stride);
     const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
 
@@ -638,9 +638,9 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 // CB only: every pair of the band inside this tile
 __global__ void __launch_bounds__(256)
 k_tile_enum(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb, int tile0,
-            const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, uint2* __restrict__ pairs,
+            int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, uint2* __restrict__ pairs,
             unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x);
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x * tile_stride);
     const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
     for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
         const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
@@ -678,7 +678,7 @@ template <int AN>
 __global__ void __launch_bounds__(64)
 k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
                   const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
-                  int tile0, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                  int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                   unsigned long long pair_cap) {
@@ -687,7 +687,7 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
     uint32_t* hist0 = hist_dyn;
     uint32_t* hist1 = hist_dyn + nbins * 64;
     const int unit = blockIdx.x;
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2));
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2) * tile_stride);
     const int r0 = tr.rb * TILE + (unit & 3) * 32, c0 = tr.cb * TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const int words = (1 << p_aux) >> 2;
@@ -1212,8 +1212,11 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const int tiles_total = tprefix[(size_t)nrb];
     st.pairs_cb = pairs_cb;
     st.tiles_total = tiles_total;
-    const int t_begin = (int)((int64_t)tiles_total * prm->shard / n_shards);
-    const int t_end = (int)((int64_t)tiles_total * (prm->shard + 1) / n_shards);
+    // shard s owns tiles s, s+S, s+2S, ... : dealing the row-major tile list round-robin gives every
+    // shard the same mix of band positions, hence nearly equal survivor counts (contiguous slices
+    // measured 1.6x imbalance in the union pass at 8 shards).  Ranges below index j, tile = s + j*S.
+    const int t_begin = 0;
+    const int t_end = tiles_total > prm->shard ? (tiles_total - prm->shard + n_shards - 1) / n_shards : 0;
     st.tiles_shard = t_end - t_begin;
     CKR(upload(c->tile_prefix, tprefix, s));
     CKR(upload(c->tile_cb0, tcb0, s));
@@ -1294,22 +1297,24 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int n_words = (n_bands + 1) / 2;
                 k_tile_filter_smh<<<nt, 256, 0, s>>>(
                     c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words,
-                    c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(),
-                    c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP);
+                    c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards,
+                    c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_CB) {
-                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, rg.first,
-                                               c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
+                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
+                                               prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                d_cnt + 1, (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_HLL_A) {
                 k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
                     c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
-                    c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
+                    c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
                     (unsigned long long)PAIR_CAP);
             } else {
                 k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
                     c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
-                    c->tile_cb0.as<int32_t>(), nrb, rg.first, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
+                    c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
                     (unsigned long long)PAIR_CAP);
             }
@@ -1420,14 +1425,17 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     st.ms_estimate = sum_ms(t_est);
     cudaEventElapsedTime(&st.ms_sort, s0, ev_end);
     cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end);
-    // shard share of the CB band: pairs of the shard's tiles (whole row blocks are exact,
-    // split row blocks are apportioned by tile count)
+    // shard share of the CB band: a row block's pairs are apportioned by how many of its tiles
+    // the shard owns
     {
         double acc = 0.;
         for (int rb = 0; rb < nrb; ++rb) {
-            const int a = std::max(tprefix[(size_t)rb], t_begin), b = std::min(tprefix[(size_t)rb + 1], t_end);
-            const int ntl = tprefix[(size_t)rb + 1] - tprefix[(size_t)rb];
-            if (b > a && ntl > 0) acc += (double)rb_pairs[(size_t)rb] * (double)(b - a) / (double)ntl;
+            const int a = tprefix[(size_t)rb], b = tprefix[(size_t)rb + 1];
+            if (b <= a) continue;
+            // tiles t in [a,b) with t % n_shards == shard
+            const int first = a + ((prm->shard - a % n_shards) % n_shards + n_shards) % n_shards;
+            const int mine = first < b ? (b - 1 - first) / n_shards + 1 : 0;
+            acc += (double)rb_pairs[(size_t)rb] * (double)mine / (double)(b - a);
         }
         st.pairs_cb_shard = (int64_t)(acc + 0.5);
     }

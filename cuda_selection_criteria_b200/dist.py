@@ -29,9 +29,9 @@ def device_tensor(ptr: int, n: int, typestr: str, device: int) -> torch.Tensor:
     return torch.as_tensor(_DevView(ptr, n, typestr), device=f"cuda:{device}")
 
 
-def shard_range(tiles_total: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous, balanced slice of the tile list (same arithmetic as selb200_run)."""
-    return tiles_total * rank // world, tiles_total * (rank + 1) // world
+def shard_tiles(tiles_total: int, rank: int, world: int) -> range:
+    """Tiles of one shard: the row-major tile list dealt round-robin (same rule as selb200_run)."""
+    return range(rank, tiles_total, world)
 
 
 def broadcast_sketches(regs: torch.Tensor, aux: torch.Tensor | None, src: int = 0):
@@ -44,33 +44,30 @@ def broadcast_sketches(regs: torch.Tensor, aux: torch.Tensor | None, src: int = 
 def gather_lists(keys: torch.Tensor, jac: torch.Tensor, dst: int = 0):
     """Gather per-rank (keys int64, jaccard float64) lists on `dst`, merged in (i,k) order.
 
-    Returns (keys, jaccard) on dst, (None, None) elsewhere."""
+    One all_gather of the counts (a single host sync) and one all_gather of a padded
+    [keys | jaccard-bits] payload.  Returns (keys, jaccard) on dst, (None, None) elsewhere."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    cnt = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
+    n = keys.numel()
+    cnt = torch.tensor([n], dtype=torch.int64, device=keys.device)
+    counts_t = torch.empty(world, dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(counts_t, cnt)
+    counts = counts_t.tolist()
     mx = max(counts) if counts else 0
     if mx == 0:
         return (keys[:0], jac[:0]) if rank == dst else (None, None)
-    pad_k = torch.zeros(mx, dtype=torch.int64, device=keys.device)
-    pad_j = torch.zeros(mx, dtype=torch.float64, device=keys.device)
-    pad_k[: keys.numel()] = keys
-    pad_j[: jac.numel()] = jac
-    if rank == dst:
-        bk = [torch.empty_like(pad_k) for _ in range(world)]
-        bj = [torch.empty_like(pad_j) for _ in range(world)]
-        dist.gather(pad_k, bk, dst=dst)
-        dist.gather(pad_j, bj, dst=dst)
-        allk = torch.cat([b[:c] for b, c in zip(bk, counts)])
-        allj = torch.cat([b[:c] for b, c in zip(bj, counts)])
-        # shards are contiguous tile ranges, so the concatenation is nearly sorted; a device sort
-        # restores the reference's print order exactly
-        o = torch.argsort(allk, stable=True)
-        return allk[o], allj[o]
-    dist.gather(pad_k, None, dst=dst)
-    dist.gather(pad_j, None, dst=dst)
-    return None, None
+    buf = torch.empty(2 * mx, dtype=torch.int64, device=keys.device)
+    buf[:n] = keys
+    buf[mx:mx + n] = jac.view(torch.int64)
+    out = torch.empty(world * 2 * mx, dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(out, buf)
+    if rank != dst:
+        return None, None
+    out = out.view(world, 2, mx)
+    allk = torch.cat([out[r, 0, :c] for r, c in enumerate(counts)])
+    allj = torch.cat([out[r, 1, :c] for r, c in enumerate(counts)]).view(torch.float64)
+    # a device sort of the merged list restores the reference's print order exactly
+    o = torch.argsort(allk, stable=True)
+    return allk[o], allj[o]
 
 
 def split_keys(keys: torch.Tensor):

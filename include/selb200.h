@@ -10,7 +10,7 @@
  *     union, Jaccard >= tau) and src/selection_cuda.cpp:111-180.
  *   - link level: src/selection_kernels_wrapper.hpp:11-45 (launch_kernel_smh /
  *     launch_kernel_CBsmh, C++ linkage).  Shims with those exact mangled names are
- *     exported by libselb200_shims.so (see selb200_shims.h / INTEGRATION.md).
+ *     exported by libselb200.so itself (see selb200_shims.h / INTEGRATION.md).
  *
  * Plain pointers and sizes only.  All functions return 0 on success or a negative
  * SELB200_E* code; selb200_last_error() gives the message of the last failure on the
@@ -64,7 +64,7 @@ typedef struct selb200_params {
     int32_t order_n;  /* 1 (selection.cpp:77)                                                  */
     int32_t n_rows;   /* smh_a band shape; 0,0 = derive with selb200_band_params(cpu_variant=1) */
     int32_t n_bands;
-    int32_t shard;    /* this process's shard of the tile list, 0 <= shard < n_shards          */
+    int32_t shard;    /* this process's shard: tiles shard, shard+n_shards, ... of the tile list */
     int32_t n_shards; /* 1 = whole pair space                                                  */
     int32_t sort_output; /* 1: order results by (i,k) like the reference prints them          */
     int32_t reserved[7];

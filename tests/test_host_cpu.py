@@ -134,8 +134,8 @@ sdist.broadcast_sketches(regs, aux, src=0)
 assert int(regs.sum()) == 8 * 16 and int(aux.sum()) == 8 * 4 * 7
 # shard ranges tile the list exactly
 T = 1001
-rngs = [sdist.shard_range(T, r, world) for r in range(world)]
-assert rngs[0][0] == 0 and rngs[-1][1] == T and all(rngs[i][1] == rngs[i + 1][0] for i in range(world - 1))
+tiles = sorted(t for r in range(world) for t in sdist.shard_tiles(T, r, world))
+assert tiles == list(range(T))
 # variable-length gather (unequal lengths), merged in (i,k) order
 full = np.array([(i << 32) | k for i in range(40) for k in range(i + 1, 40, 7)], dtype=np.int64)
 cut = full.size // 3
