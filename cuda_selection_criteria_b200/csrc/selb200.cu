@@ -111,6 +111,9 @@ constexpr int TILE = 128;          // pair tile edge (rows x cols of the sorted 
 constexpr int SIG_CHUNK = 16;      // LSH bands staged per shared-memory pass
 constexpr int64_t PAIR_CAP = 8ll << 20;   // pairs per filter->union pass (list 64 MB, histograms 2 GB)
 constexpr int SNAP_MAX = 4096;            // tile ranges per run
+#ifndef FILTER_CTAS_PER_SM
+#define FILTER_CTAS_PER_SM 2
+#endif
 
 }  // namespace
 
@@ -142,7 +145,7 @@ struct selb200_ctx {
     std::vector<uint64_t> h_e;
 
     // run scratch (grow-only)
-    DevBuf lo, hi, tile_prefix, tile_cb0, sigT, cand, pairs, hist, counters, cub_tmp;
+    DevBuf lo, hi, tile_prefix, tile_cb0, tile_rc, sigT, cand, pairs, hist, counters, cub_tmp;
     DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
     std::vector<int32_t> h_lo, h_hi;
     int64_t out_count = 0, near_count = 0;
@@ -486,6 +489,16 @@ __device__ __forceinline__ TileRef find_tile(const int32_t* __restrict__ tile_pr
     return t;
 }
 
+// (row block, column block) of every tile of the run, built once per run so that a filter CTA finds
+// its tile with one 8-byte load instead of a dependent binary search
+__global__ void k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
+                             int ntiles, int2* __restrict__ tile_rc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, t);
+    tile_rc[t] = make_int2(tr.rb, tr.cb);
+}
+
 // ============================================================================
 // K3: LSH band signatures.  For the g-th sorted genome and band b, sig(b,g) = 16 bits of a mix
 // of the band's n_rows buckets.  Equal bands => equal signatures, so "some band equal"
@@ -532,16 +545,16 @@ __global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long l
 // operand holds the negated halves, so a half reaches 0 exactly when the two signatures are equal.
 // Measured alternatives on B200 (n=100k, 4.66e8 CB pairs): XOR+MIN on 32-bit signatures 1.22 ms;
 // (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FILTER_CTAS_PER_SM)
 k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
-                  const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
+                  const int2* __restrict__ tile_rc,
                   int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
                   unsigned long long cand_cap) {
     __shared__ __align__(16) uint32_t sR[SIG_CHUNK][TILE];
     __shared__ __align__(16) uint32_t sC[SIG_CHUNK][TILE];
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x * tile_stride);
-    const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
+    const int2 rc = __ldg(tile_rc + tile0 + (int)blockIdx.x * tile_stride);
+    const int r0 = rc.x * TILE, c0 = rc.y * TILE;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
 
     uint32_t acc[8][8];
@@ -582,19 +595,22 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
 #pragma unroll
         for (int b = 0; b < 8; ++b) any = __vminu2(any, acc[a][b]);
     if ((any & 0xffffu) != 0 && (any >> 16) != 0) return;
+    // rare path: gather the matching (a,b) cells into a bit mask, then walk its set bits
+    unsigned long long cells = 0ull;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+            if ((acc[a][b] & 0xffffu) == 0 || (acc[a][b] >> 16) == 0) cells |= 1ull << (a * 8 + b);
+    while (cells) {
+        const int bit = __ffsll((long long)cells) - 1;
+        cells &= cells - 1;
+        const int a = bit >> 3, b = bit & 7;
         const int i = r0 + ty * 8 + a;
-        if (i >= n) continue;
-        const int l = lo[i], h = hi[i];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            if ((acc[a][b] & 0xffffu) != 0 && (acc[a][b] >> 16) != 0) continue;
-            const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
-            if (k < l || k > h) continue;
-            const unsigned long long slot = warp_claim(cand_count);
-            if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
-        }
+        const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+        if (i >= n || k < lo[i] || k > hi[i]) continue;
+        const unsigned long long slot = warp_claim(cand_count);
+        if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
     }
 }
 
@@ -637,11 +653,11 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 
 // CB only: every pair of the band inside this tile
 __global__ void __launch_bounds__(256)
-k_tile_enum(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb, int tile0,
+k_tile_enum(const int2* __restrict__ tile_rc, int tile0,
             int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, uint2* __restrict__ pairs,
             unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (int)blockIdx.x * tile_stride);
-    const int r0 = tr.rb * TILE, c0 = tr.cb * TILE;
+    const int2 rc = __ldg(tile_rc + tile0 + (int)blockIdx.x * tile_stride);
+    const int r0 = rc.x * TILE, c0 = rc.y * TILE;
     for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
         const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
         if (i >= n || k >= n) continue;
@@ -677,7 +693,7 @@ struct StopHll {      // early exit of the MLE: the criterion already fails at t
 template <int AN>
 __global__ void __launch_bounds__(64)
 k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
-                  const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
+                  const int2* __restrict__ tile_rc,
                   int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
@@ -687,8 +703,8 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
     uint32_t* hist0 = hist_dyn;
     uint32_t* hist1 = hist_dyn + nbins * 64;
     const int unit = blockIdx.x;
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, tile0 + (unit >> 2) * tile_stride);
-    const int r0 = tr.rb * TILE + (unit & 3) * 32, c0 = tr.cb * TILE;
+    const int2 rc = __ldg(tile_rc + tile0 + (unit >> 2) * tile_stride);
+    const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const int words = (1 << p_aux) >> 2;
     const uint32_t bias0 = hist_bias(hist0), bias1 = hist_bias(hist1);
@@ -1071,7 +1087,7 @@ void selb200_destroy(selb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
-                      &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->sigT, &c->cand, &c->pairs, &c->hist,
+                      &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
                       &c->near_keys, &c->near_j};
     for (DevBuf* b : bufs) b->release();
@@ -1220,6 +1236,13 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     st.tiles_shard = t_end - t_begin;
     CKR(upload(c->tile_prefix, tprefix, s));
     CKR(upload(c->tile_cb0, tcb0, s));
+    CKR(c->tile_rc.ensure((size_t)std::max(tiles_total, 1) * sizeof(int2)));
+    if (tiles_total > 0) {
+        k_tile_table<<<(tiles_total + 255) / 256, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
+                                                               nrb, tiles_total, c->tile_rc.as<int2>());
+        CK(cudaGetLastError());
+        st.launches++;
+    }
 
     // counters: [0] candidates, [1] pairs, [2] out, [3] near
     CKR(c->counters.ensure(64));
@@ -1297,23 +1320,23 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int n_words = (n_bands + 1) / 2;
                 k_tile_filter_smh<<<nt, 256, 0, s>>>(
                     c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words,
-                    c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards,
+                    c->tile_rc.as<int2>(), prm->shard + rg.first * n_shards, n_shards,
                     c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_CB) {
-                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
+                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_rc.as<int2>(),
                                                prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                d_cnt + 1, (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_HLL_A) {
                 k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
-                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
-                    c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_rc.as<int2>(),
+                    prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
                     c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
                     (unsigned long long)PAIR_CAP);
             } else {
                 k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
-                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_prefix.as<int32_t>(),
-                    c->tile_cb0.as<int32_t>(), nrb, prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_rc.as<int2>(),
+                    prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
                     c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
                     (unsigned long long)PAIR_CAP);
