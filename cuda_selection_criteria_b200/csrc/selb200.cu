@@ -3,18 +3,22 @@
 // Replaces, behind include/selb200.h, the hot loop of the reference
 // (src/selection.cpp:241-291 and its CUDA restatement src/selection_kernels.cu:13-117):
 //
-//   load    : per-genome register histograms + Ertl-MLE cardinalities on the device,
-//             std::sort by cardinality on the host (tie order of selection.cpp:251-256),
+//   load    : chunked H2D overlapped with k_max_byte (validation), k_pair_hist (per-genome histograms)
+//             and k_genome_cards (Ertl MLE); device radix sort by cardinality, with the host
+//             std::sort of selection.cpp:251-256 as the exact fallback when two cardinalities tie;
 //             auxiliary sketches re-laid out in sorted order for the tile kernels
 //   run     : K2  k_cb_bounds        CB band [lo(i),hi(i)] per sorted row (binary search, fp64 div)
-//             K3  k_smh_signatures   one 32-bit signature per (genome, LSH band), transposed
-//             K4  k_tile_filter_smh  128x128 pair tiles, 8x8 register micro-tiles: XOR+MIN per band
-//                 k_smh_verify       exact uint64 band compare of the (few) candidates
+//                 k_tile_table       (row block, column block) of every 128x128 tile of the band
+//             K3  k_smh_signatures   16-bit signature per (genome, LSH band), two bands per word, transposed
+//             K4  k_tile_filter_smh  8x8 register micro-tiles: one VIADDMNMX.U16x2 per two bands
+//                 k_smh_verify       exact uint64 compare of the signature-matching band(s)
 //                 k_tile_filter_hll  hll_a / hll_an: thread-per-pair aux-HLL union histogram + MLE
 //                 k_tile_enum        CB-only: every pair of the band
 //             K5  k_pair_hist        warp-per-pair HLL-14 register max + 52/64-bin histogram
 //             K6  k_estimate_emit    Ertl MLE of the union, Jaccard, tau test, warp-aggregated emit
 //             K7  cub radix sort     (i,k) order of the reference's stdout
+//   Everything after K4 reads its work count from device memory, so a run has two host syncs
+//   (after K2 for the tile list, and at the end).
 //
 // No tensor cores: the path is byte/integer work bounded by shared-memory and L2/HBM
 // bandwidth.  Compile with -fmad=false (see estimators.cuh).
@@ -117,6 +121,29 @@ constexpr int SNAP_MAX = 4096;            // tile ranges per run
 
 }  // namespace
 
+struct LoadState {            // one load in progress (begin -> chunks -> end)
+    bool active = false;
+    bool regs_borrowed = false;
+    bool have_stored = false;
+    size_t aux_row_bytes = 0;
+    const void* d_aux = nullptr;      // raw aux rows in file-list order (borrowed or scratch)
+    int64_t rows_per_chunk = 0;
+    int64_t rows_done = 0;
+    size_t ev_i = 0;
+    // streaming: pinned staging slots the caller decodes into
+    int64_t acq_g0 = -1, acq_rows = 0;
+    int acq_slot = -1;
+};
+
+struct StageSlot {            // pinned host staging of one chunk
+    uint8_t* regs = nullptr;
+    uint8_t* aux = nullptr;
+    double* stored = nullptr;
+    size_t regs_cap = 0, aux_cap = 0, stored_cap = 0;
+    cudaEvent_t free_ev = nullptr;    // recorded on the copy stream after the slot's H2D copies
+    bool in_flight = false;
+};
+
 struct selb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -150,6 +177,10 @@ struct selb200_ctx {
     std::vector<int32_t> h_lo, h_hi;
     int64_t out_count = 0, near_count = 0;
     int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
+    LoadState ld;
+    StageSlot slots[3];
+    int next_slot = 0;
+    bool _order_cache_valid = false;
     unsigned long long* h_snap = nullptr;         // pinned: per-range counter snapshots
     const uint64_t* res_keys = nullptr;
     const double* res_j = nullptr;
@@ -362,31 +393,6 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src s
     }
 }
 
-// generic small-sketch variant (aux HLL diagnostics, m < 512): warp per pair, shared atomics
-__global__ void __launch_bounds__(64)
-k_pair_hist_small(const uint8_t* __restrict__ regs, size_t m, const uint2* __restrict__ pairs, long long npairs,
-                  uint32_t* __restrict__ hist_out) {
-    __shared__ uint32_t hist[2][64];
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const long long nw = (long long)gridDim.x * 2;
-    for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
-        hist[w][lane] = 0;
-        hist[w][lane + 32] = 0;
-        __syncwarp();
-        const uint2 pr = pairs[pi];
-        const uint8_t* a = regs + (size_t)pr.x * m;
-        const uint8_t* b = regs + (size_t)pr.y * m;
-        for (size_t j = lane; j < m; j += 32) {
-            const uint8_t r = max(a[j], b[j]);
-            atomicAdd(&hist[w][r & 63], 1u);
-        }
-        __syncwarp();
-        hist_out[pi * 64 + lane] = hist[w][lane];
-        hist_out[pi * 64 + 32 + lane] = hist[w][lane + 32];
-        __syncwarp();
-    }
-}
-
 __global__ void k_iota_i32(int32_t* v, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) v[i] = (int32_t)i;
@@ -400,11 +406,6 @@ __global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long
     const double cd = cards_sorted[i];
     e[i] = (unsigned long long)cd;
     if (i + 1 < n && !(cd < cards_sorted[i + 1])) *tie_flag = 1;
-}
-
-__global__ void k_iota_pairs(uint2* pairs, long long n) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) pairs[i] = make_uint2((uint32_t)i, (uint32_t)i);
 }
 
 // per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
@@ -843,45 +844,24 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
                      const uint2* pairs, int64_t npairs, uint32_t* hist_out,
                      const unsigned long long* npairs_dev = nullptr) {
     if (npairs <= 0) return SELB200_OK;
-    if (m >= 512) {
-        SrcPairs src{pairs, order, (long long)npairs, npairs_dev};
-        EpiWriteHist epi{hist_out};
-        return launch_pair_hist_t(c->stream, c->sm_count, regs, m, m, p, npairs, src, epi);
-    }
-    if (order) return fail(SELB200_EINVAL, "small-sketch histogram takes row indices");
-    const int grid = (int)std::min<int64_t>((npairs + 1) / 2, (int64_t)c->sm_count * 16);
-    k_pair_hist_small<<<grid, 64, 0, c->stream>>>(regs, m, pairs, npairs, hist_out);
-    CK(cudaGetLastError());
-    return SELB200_OK;
+    if (m < 512) return fail(SELB200_EINVAL, "primary sketches below 512 registers are not supported");
+    SrcPairs src{pairs, order, (long long)npairs, npairs_dev};
+    EpiWriteHist epi{hist_out};
+    return launch_pair_hist_t(c->stream, c->sm_count, regs, m, m, p, npairs, src, epi);
 }
 
-int validate_registers(selb200_ctx* c, const void* d_data, size_t bytes, int p, const char* what) {
-    CKR(c->counters.ensure(64));
-    CK(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
-    const size_t n16 = bytes / 16;
-    if (n16) {
-        const int grid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8);
-        k_max_byte<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(d_data), n16,
-                                                c->counters.as<uint32_t>());
-        CK(cudaGetLastError());
-    }
-    uint32_t mx = 0;
-    CK(cudaMemcpyAsync(&mx, c->counters.p, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const uint32_t lim = (uint32_t)(64 - p + 1);
-    if (mx > lim)
-        return fail(SELB200_EINVAL, "%s sketch holds register value %u > %u (= 64-p+1, p=%d): not an HLL of that precision",
-                    what, mx, lim, p);
-    return SELB200_OK;
-}
-
-int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_device, const double* stored,
-            int aux_kind, int aux_len, const void* aux, bool aux_on_device) {
+// ---------------------------------------------------------------------------------------------
+// load = begin -> chunks -> end.  selb200_load_host / _device run all three over caller memory;
+// the streaming entry points (selb200_load_begin / acquire / commit / end) let the caller decode
+// sketch files straight into pinned staging slots while earlier chunks are already on the device.
+// ---------------------------------------------------------------------------------------------
+int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, const uint8_t* d_regs_borrowed,
+               const void* d_aux_borrowed) {
     if (!c) return fail(SELB200_EINVAL, "null context");
     c->loaded = false;
+    c->ld.active = false;
     if (n < 0 || n > 0x7fffff00ll) return fail(SELB200_EINVAL, "n=%lld out of range", (long long)n);
     if (p < 9 || p > 20) return fail(SELB200_EINVAL, "primary HLL precision p=%d unsupported (9..20)", p);
-    if (n && !regs) return fail(SELB200_EINVAL, "null register matrix");
     size_t aux_row_bytes = 0;
     if (aux_kind == SELB200_AUX_SMH) {
         if (aux_len < 1 || aux_len > 65536) return fail(SELB200_EINVAL, "smh bucket count %d out of range", aux_len);
@@ -892,7 +872,6 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_
     } else if (aux_kind != SELB200_AUX_NONE) {
         return fail(SELB200_EINVAL, "unknown aux kind %d", aux_kind);
     }
-    if (aux_kind != SELB200_AUX_NONE && n && !aux) return fail(SELB200_EINVAL, "null aux matrix");
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     c->n = n; c->p = p; c->m = (size_t)1 << p;
@@ -902,74 +881,110 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_
     c->h_order.assign((size_t)n, 0);
     c->h_e.assign((size_t)n, 0);
     c->out_count = c->near_count = 0;
-    if (n == 0) { c->loaded = true; return SELB200_OK; }
 
-    const size_t reg_bytes = (size_t)n * c->m;
-    if (regs_on_device) {
-        c->d_regs = regs;
+    LoadState& L = c->ld;
+    L = LoadState();
+    L.aux_row_bytes = aux_row_bytes;
+    L.regs_borrowed = d_regs_borrowed != nullptr;
+    L.rows_per_chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)c->m);
+    L.active = true;
+    if (n == 0) return SELB200_OK;
+    if (L.regs_borrowed) {
+        c->d_regs = d_regs_borrowed;
     } else {
-        CKR(c->regs_own.ensure(reg_bytes));
+        CKR(c->regs_own.ensure((size_t)n * c->m));
         c->d_regs = c->regs_own.as<uint8_t>();
+    }
+    if (aux_kind != SELB200_AUX_NONE) {
+        if (d_aux_borrowed) {
+            L.d_aux = d_aux_borrowed;
+        } else {
+            CKR(c->cand.ensure((size_t)n * aux_row_bytes));   // raw aux rows in file-list order (scratch)
+            L.d_aux = c->cand.p;
+        }
     }
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
+    CKR(c->out_j.ensure((size_t)n * sizeof(double)));        // stored value_ of each header (-1 = recompute)
     CKR(c->counters.ensure(64));
     CK(cudaMemsetAsync(c->counters.p, 0, 64, s));
-    double* d_stored = nullptr;
-    if (stored) {
-        CKR(c->out_j.ensure((size_t)n * sizeof(double)));
-        CK(cudaMemcpyAsync(c->out_j.p, stored, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
-        d_stored = c->out_j.as<double>();
+    return SELB200_OK;
+}
+
+// the run stream waits for everything queued on the copy stream so far
+int load_join_copies(selb200_ctx* c) {
+    LoadState& L = c->ld;
+    if (L.ev_i == c->copy_events.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->copy_events.push_back(e);
     }
-    // ---- chunked pipeline: the H2D copy of chunk c+1 (copy stream) overlaps validation, the
-    // per-genome histogram and the cardinality MLE of chunk c (run stream) -------------------
-    const int64_t rows_per_chunk = regs_on_device ? n : std::max<int64_t>(1, (int64_t)(64u << 20) / (int64_t)c->m);
-    size_t ev_i = 0;
-    auto copy_done = [&]() -> int {          // run stream waits for what the copy stream has queued
-        if (ev_i == c->copy_events.size()) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->copy_events.push_back(e);
-        }
-        CK(cudaEventRecord(c->copy_events[ev_i], c->copy_stream));
-        CK(cudaStreamWaitEvent(s, c->copy_events[ev_i], 0));
-        ++ev_i;
-        return SELB200_OK;
-    };
-    // auxiliary sketches first (small): staged in `cand` scratch when they arrive from the host
-    const void* d_aux = aux;
-    if (aux_kind != SELB200_AUX_NONE && !aux_on_device) {
-        CKR(c->cand.ensure((size_t)n * aux_row_bytes));
-        CK(cudaMemcpyAsync(c->cand.p, aux, (size_t)n * aux_row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-        d_aux = c->cand.p;
+    CK(cudaEventRecord(c->copy_events[L.ev_i], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->copy_events[L.ev_i], 0));
+    ++L.ev_i;
+    return SELB200_OK;
+}
+
+// rows [g0, g0+rows): optional H2D from host pointers (copy stream), then validation, per-genome
+// histogram and cardinality MLE on the run stream
+int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, const double* h_stored,
+               const void* h_aux) {
+    LoadState& L = c->ld;
+    cudaStream_t s = c->stream;
+    const int p = c->p;
+    if (rows <= 0) return SELB200_OK;
+    bool copied = false;
+    if (h_aux && c->aux_kind != SELB200_AUX_NONE) {
+        CK(cudaMemcpyAsync((uint8_t*)const_cast<void*>(L.d_aux) + (size_t)g0 * L.aux_row_bytes, h_aux,
+                           (size_t)rows * L.aux_row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        copied = true;
     }
-    for (int64_t g0 = 0; g0 < n; g0 += rows_per_chunk) {
-        const int64_t g1 = std::min(n, g0 + rows_per_chunk), rows = g1 - g0;
-        if (!regs_on_device) {
-            CK(cudaMemcpyAsync(c->regs_own.as<uint8_t>() + (size_t)g0 * c->m, regs + (size_t)g0 * c->m,
-                               (size_t)rows * c->m, cudaMemcpyHostToDevice, c->copy_stream));
-            CKR(copy_done());
-        }
-        const size_t n16 = (size_t)rows * c->m / 16;
-        k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
-            reinterpret_cast<const uint4*>(c->d_regs + (size_t)g0 * c->m), n16, c->counters.as<uint32_t>());
-        CK(cudaGetLastError());
-        SrcSelf src{(long long)g0, (long long)rows, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1)};
-        EpiWriteHist epi{c->hist.as<uint32_t>() + (size_t)g0 * 64};
-        CKR(launch_pair_hist_t(s, c->sm_count, c->d_regs, c->m, c->m, p, rows, src, epi));
-        k_genome_cards<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(
-            c->hist.as<uint32_t>() + (size_t)g0 * 64, d_stored ? d_stored + g0 : nullptr, rows, p,
-            c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1));
-        CK(cudaGetLastError());
+    if (h_stored) {
+        CK(cudaMemcpyAsync(c->out_j.as<double>() + g0, h_stored, (size_t)rows * 8, cudaMemcpyHostToDevice,
+                           c->copy_stream));
+        L.have_stored = true;
+        copied = true;
     }
+    if (h_regs) {
+        CK(cudaMemcpyAsync(c->regs_own.as<uint8_t>() + (size_t)g0 * c->m, h_regs, (size_t)rows * c->m,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        copied = true;
+    }
+    if (copied) CKR(load_join_copies(c));
+    const size_t n16 = (size_t)rows * c->m / 16;
+    k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(c->d_regs + (size_t)g0 * c->m), n16, c->counters.as<uint32_t>());
+    CK(cudaGetLastError());
+    SrcSelf src{(long long)g0, (long long)rows, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1)};
+    EpiWriteHist epi{c->hist.as<uint32_t>() + (size_t)g0 * 64};
+    CKR(launch_pair_hist_t(s, c->sm_count, c->d_regs, c->m, c->m, p, rows, src, epi));
+    k_genome_cards<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(
+        c->hist.as<uint32_t>() + (size_t)g0 * 64, h_stored ? c->out_j.as<double>() + g0 : nullptr, rows, p,
+        c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1));
+    CK(cudaGetLastError());
+    L.rows_done += rows;
+    return SELB200_OK;
+}
+
+int load_end(selb200_ctx* c) {
+    LoadState& L = c->ld;
+    if (!L.active) return fail(SELB200_ESTATE, "selb200_load_end without selb200_load_begin");
+    const int64_t n = c->n;
+    const int p = c->p, aux_kind = c->aux_kind, aux_len = c->aux_len;
+    cudaStream_t s = c->stream;
+    if (L.rows_done != n) {
+        L.active = false;
+        return fail(SELB200_ESTATE, "load ended after %lld of %lld rows", (long long)L.rows_done, (long long)n);
+    }
+    L.active = false;
+    if (n == 0) { c->loaded = true; return SELB200_OK; }
+    const void* d_aux = L.d_aux;
+    const size_t aux_row_bytes = L.aux_row_bytes;
     if (aux_kind == SELB200_AUX_HLL) {
-        if (!aux_on_device && regs_on_device) CKR(copy_done());
         const size_t n16 = (size_t)n * aux_row_bytes / 16;
         k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
             reinterpret_cast<const uint4*>(d_aux), n16, c->counters.as<uint32_t>() + 1);
         CK(cudaGetLastError());
-    } else if (aux_kind == SELB200_AUX_SMH && !aux_on_device && regs_on_device) {
-        CKR(copy_done());
     }
     // ---- sort by cardinality.  Distinct keys have ONE sorted order, so a device radix sort then
     // equals the reference's std::sort; any tie falls back to that exact std::sort on the host
@@ -1034,6 +1049,21 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool regs_on_
     return SELB200_OK;
 }
 
+int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool on_device, const double* stored,
+            int aux_kind, int aux_len, const void* aux) {
+    if (n > 0 && !regs) return fail(SELB200_EINVAL, "null register matrix");
+    if (aux_kind != SELB200_AUX_NONE && n > 0 && !aux) return fail(SELB200_EINVAL, "null aux matrix");
+    CKR(load_begin(c, n, p, aux_kind, aux_len, on_device ? regs : nullptr, on_device ? aux : nullptr));
+    LoadState& L = c->ld;
+    const int64_t step = on_device ? std::max<int64_t>(n, 1) : L.rows_per_chunk;
+    for (int64_t g0 = 0; g0 < n; g0 += step) {
+        const int64_t rows = std::min(step, n - g0);
+        CKR(load_chunk(c, g0, rows, on_device ? nullptr : regs + (size_t)g0 * c->m, stored ? stored + g0 : nullptr,
+                       (on_device || !aux) ? nullptr : (const uint8_t*)aux + (size_t)g0 * L.aux_row_bytes));
+    }
+    return load_end(c);
+}
+
 }  // namespace
 
 // ============================================================================
@@ -1094,6 +1124,12 @@ void selb200_destroy(selb200_ctx* c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    for (StageSlot& sl : c->slots) {
+        if (sl.regs) cudaFreeHost(sl.regs);
+        if (sl.aux) cudaFreeHost(sl.aux);
+        if (sl.stored) cudaFreeHost(sl.stored);
+        if (sl.free_ev) cudaEventDestroy(sl.free_ev);
+    }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1101,12 +1137,70 @@ void selb200_destroy(selb200_ctx* c) {
 
 int selb200_load_host(selb200_ctx* ctx, int64_t n, int p, const uint8_t* regs, const double* stored,
                       int aux_kind, int aux_len, const void* aux) {
-    return do_load(ctx, n, p, regs, false, stored, aux_kind, aux_len, aux, false);
+    return do_load(ctx, n, p, regs, false, stored, aux_kind, aux_len, aux);
 }
 
 int selb200_load_device(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_regs, const double* stored_host,
                         int aux_kind, int aux_len, const void* d_aux) {
-    return do_load(ctx, n, p, d_regs, true, stored_host, aux_kind, aux_len, d_aux, true);
+    return do_load(ctx, n, p, d_regs, true, stored_host, aux_kind, aux_len, d_aux);
+}
+
+int selb200_load_begin(selb200_ctx* ctx, int64_t n, int p, int aux_kind, int aux_len, int64_t* rows_per_chunk) {
+    CKR(load_begin(ctx, n, p, aux_kind, aux_len, nullptr, nullptr));
+    if (rows_per_chunk) *rows_per_chunk = ctx->ld.rows_per_chunk;
+    return SELB200_OK;
+}
+
+static int pinned_ensure(void** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap && *ptr) return SELB200_OK;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CK(cudaMallocHost(ptr, bytes ? bytes : 16));
+    *cap = bytes;
+    return SELB200_OK;
+}
+
+int selb200_load_acquire(selb200_ctx* c, int64_t g0, int64_t count, uint8_t** regs, double** stored, void** aux) {
+    if (!c || !c->ld.active) return fail(SELB200_ESTATE, "selb200_load_acquire outside begin/end");
+    LoadState& L = c->ld;
+    if (L.acq_slot >= 0) return fail(SELB200_ESTATE, "previous staging slot not committed");
+    if (g0 != L.rows_done || count < 1 || count > L.rows_per_chunk || g0 + count > c->n)
+        return fail(SELB200_EINVAL, "rows [%lld,+%lld) out of sequence (next row %lld, chunk limit %lld)",
+                    (long long)g0, (long long)count, (long long)L.rows_done, (long long)L.rows_per_chunk);
+    CK(cudaSetDevice(c->device));
+    StageSlot& sl = c->slots[c->next_slot];
+    if (!sl.free_ev) CK(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
+    if (sl.in_flight) { CK(cudaEventSynchronize(sl.free_ev)); sl.in_flight = false; }   // its last H2D finished
+    CKR(pinned_ensure((void**)&sl.regs, &sl.regs_cap, (size_t)L.rows_per_chunk * c->m));
+    CKR(pinned_ensure((void**)&sl.stored, &sl.stored_cap, (size_t)L.rows_per_chunk * 8));
+    if (L.aux_row_bytes) CKR(pinned_ensure((void**)&sl.aux, &sl.aux_cap, (size_t)L.rows_per_chunk * L.aux_row_bytes));
+    L.acq_slot = c->next_slot;
+    L.acq_g0 = g0;
+    L.acq_rows = count;
+    if (regs) *regs = sl.regs;
+    if (stored) *stored = sl.stored;
+    if (aux) *aux = L.aux_row_bytes ? (void*)sl.aux : nullptr;
+    return SELB200_OK;
+}
+
+int selb200_load_commit(selb200_ctx* c) {
+    if (!c || !c->ld.active || c->ld.acq_slot < 0) return fail(SELB200_ESTATE, "nothing acquired to commit");
+    LoadState& L = c->ld;
+    StageSlot& sl = c->slots[L.acq_slot];
+    CK(cudaSetDevice(c->device));
+    CKR(load_chunk(c, L.acq_g0, L.acq_rows, sl.regs, sl.stored, L.aux_row_bytes ? sl.aux : nullptr));
+    CK(cudaEventRecord(sl.free_ev, c->copy_stream));
+    sl.in_flight = true;
+    c->next_slot = (c->next_slot + 1) % 3;
+    L.acq_slot = -1;
+    return SELB200_OK;
+}
+
+int selb200_load_end(selb200_ctx* c) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    if (c->ld.acq_slot >= 0) return fail(SELB200_ESTATE, "a staging slot is still acquired");
+    return load_end(c);
 }
 
 int selb200_get_order(selb200_ctx* c, double* cards_sorted, int32_t* order) {

@@ -17,6 +17,7 @@
 #include <omp.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -59,16 +60,32 @@ HllFile read_hll(const std::string& path) {
     return h;
 }
 
+// same reader, registers decoded straight into `dst` (a pinned staging slot)
+void read_hll_into(const std::string& path, uint32_t expect_np, uint8_t* dst, double* value) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (fp == nullptr) throw std::runtime_error(std::string("Could not open file at '") + path + "' for reading");
+    uint32_t hdr[4], np = 0;
+    gz_read_exact(fp, hdr, sizeof hdr, path);
+    gz_read_exact(fp, &np, sizeof np, path);
+    gz_read_exact(fp, value, sizeof *value, path);
+    if (np != expect_np) { gzclose(fp); throw std::runtime_error(path + ": HLL precision differs from the expected one"); }
+    if (hdr[1] != 2 || hdr[2] != 2) {
+        gzclose(fp);
+        throw std::runtime_error(path + ": stored estimator is not ERTL_MLE (hll.h:825-827 default)");
+    }
+    gz_read_exact(fp, dst, (size_t)1 << np, path);
+    gzclose(fp);
+}
+
 // src/selection.cpp:12-33 (read_smh): u32 count, count x u64
-std::vector<uint64_t> read_smh(const std::string& path) {
+void read_smh_into(const std::string& path, uint32_t expect_m, uint64_t* dst) {
     gzFile fp = gzopen(path.c_str(), "rb");
     if (fp == nullptr) throw std::runtime_error(std::string("Could not open file at '") + path + "' for reading");
     uint32_t n = 0;
     gz_read_exact(fp, &n, sizeof n, path);
-    std::vector<uint64_t> v(n);
-    if (n) gz_read_exact(fp, v.data(), (size_t)n * 8, path);
+    if (n != expect_m) { gzclose(fp); throw std::runtime_error(path + ": unexpected bucket count"); }
+    if (n) gz_read_exact(fp, dst, (size_t)n * 8, path);
     gzclose(fp);
-    return v;
 }
 
 // src/selection.cpp:36-63
@@ -141,36 +158,37 @@ int main(int argc, char* argv[]) {
     const std::string aux_suffix = aux_kind == SELB200_AUX_SMH ? ".smh" + std::to_string(m_aux)
                                  : aux_kind == SELB200_AUX_HLL ? ".hll_" + std::to_string(p_aux) : "";
 
-    // ---- load (OpenMP over files, like selection.cpp:241-249) ---------------------------------
+    // ---- device context first: the sketches are decoded straight into its pinned staging slots ----
+    selb200_ctx* ctx = nullptr;
+    if (selb200_create(0, nullptr, &ctx) != SELB200_OK) die("create");
+
+    // ---- load (OpenMP over the files of a chunk, like selection.cpp:241-249); the device copy,
+    // validation, histogram and cardinality of chunk c run while chunk c+1 is being gunzipped ----
     int p = 14;
-    std::vector<uint8_t> regs, aux_hll;
-    std::vector<uint64_t> aux_smh;
-    std::vector<double> stored(n, -1.0);
-    std::string load_error;
-    if (n) {
-        HllFile first = read_hll(files[0] + ".hll");
-        p = (int)first.np;
-        const size_t m = (size_t)1 << p;
-        regs.resize(n * m);
-        if (aux_kind == SELB200_AUX_SMH) aux_smh.resize(n * (size_t)m_aux);
-        if (aux_kind == SELB200_AUX_HLL) aux_hll.resize(n << p_aux);
+    if (n) p = (int)read_hll(files[0] + ".hll").np;
+    const int aux_len = aux_kind == SELB200_AUX_SMH ? (int)m_aux : aux_kind == SELB200_AUX_HLL ? (int)p_aux : 0;
+    const size_t m = (size_t)1 << p;
+    const size_t aux_row = aux_kind == SELB200_AUX_SMH ? (size_t)m_aux * 8
+                         : aux_kind == SELB200_AUX_HLL ? (size_t)1 << p_aux : 0;
+    int64_t rows_per_chunk = 0;
+    if (selb200_load_begin(ctx, (int64_t)n, p, aux_kind, aux_len, &rows_per_chunk) != SELB200_OK) die("load");
+    for (int64_t g0 = 0; g0 < (int64_t)n; g0 += rows_per_chunk) {
+        const int64_t count = std::min<int64_t>(rows_per_chunk, (int64_t)n - g0);
+        uint8_t* R = nullptr;
+        double* S = nullptr;
+        void* A = nullptr;
+        if (selb200_load_acquire(ctx, g0, count, &R, &S, &A) != SELB200_OK) die("load");
+        std::string load_error;
 #pragma omp parallel for schedule(dynamic)
-        for (size_t i = 0; i < n; ++i) {
+        for (int64_t i = 0; i < count; ++i) {
             try {
-                HllFile h = read_hll(files[i] + ".hll");
-                if ((int)h.np != p) throw std::runtime_error(files[i] + ".hll: precision differs from the first sketch");
-                if (h.hdr[1] != 2 || h.hdr[2] != 2)
-                    throw std::runtime_error(files[i] + ".hll: stored estimator is not ERTL_MLE (hll.h:825-827 default)");
-                std::memcpy(regs.data() + i * m, h.core.data(), m);
-                stored[i] = h.value;
+                const std::string& f = files[(size_t)(g0 + i)];
+                read_hll_into(f + ".hll", (uint32_t)p, R + (size_t)i * m, S + i);
                 if (aux_kind == SELB200_AUX_SMH) {
-                    std::vector<uint64_t> v = read_smh(files[i] + aux_suffix);
-                    if (v.size() != m_aux) throw std::runtime_error(files[i] + aux_suffix + ": unexpected bucket count");
-                    std::memcpy(aux_smh.data() + i * (size_t)m_aux, v.data(), (size_t)m_aux * 8);
+                    read_smh_into(f + aux_suffix, m_aux, reinterpret_cast<uint64_t*>((uint8_t*)A + (size_t)i * aux_row));
                 } else if (aux_kind == SELB200_AUX_HLL) {
-                    HllFile a = read_hll(files[i] + aux_suffix);
-                    if (a.np != p_aux) throw std::runtime_error(files[i] + aux_suffix + ": unexpected precision");
-                    std::memcpy(aux_hll.data() + (i << p_aux), a.core.data(), (size_t)1 << p_aux);
+                    double unused;
+                    read_hll_into(f + aux_suffix, p_aux, (uint8_t*)A + (size_t)i * aux_row, &unused);
                 }
             } catch (const std::exception& e) {
 #pragma omp critical
@@ -178,16 +196,9 @@ int main(int argc, char* argv[]) {
             }
         }
         if (!load_error.empty()) throw std::runtime_error(load_error);   // uncaught, like the reference
+        if (selb200_load_commit(ctx) != SELB200_OK) die("load");
     }
-
-    // ---- device --------------------------------------------------------------------------------
-    selb200_ctx* ctx = nullptr;
-    if (selb200_create(0, nullptr, &ctx) != SELB200_OK) die("create");
-    const void* aux_ptr = aux_kind == SELB200_AUX_SMH ? (const void*)aux_smh.data()
-                        : aux_kind == SELB200_AUX_HLL ? (const void*)aux_hll.data() : nullptr;
-    const int aux_len = aux_kind == SELB200_AUX_SMH ? (int)m_aux : aux_kind == SELB200_AUX_HLL ? (int)p_aux : 0;
-    if (selb200_load_host(ctx, (int64_t)n, p, regs.data(), stored.data(), aux_kind, aux_len, aux_ptr) != SELB200_OK)
-        die("load");
+    if (selb200_load_end(ctx) != SELB200_OK) die("load");
     selb200_params prm;
     selb200_default_params(&prm);
     prm.tau = threshold;

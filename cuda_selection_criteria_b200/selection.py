@@ -111,6 +111,30 @@ class Selection:
         self._order = None
         return self
 
+    def load_stream(self, n: int, p: int, fill, aux_kind: int = AUX_NONE, aux_len: int = 0):
+        """Streaming load over the library's pinned staging slots.  `fill(g0, count, regs, stored, aux)`
+        is called per chunk with numpy views to fill in place: regs uint8[count][2^p], stored
+        float64[count] (header value_, < 0 = recompute), aux uint64[count][m] / uint8[count][2^p_aux] / None."""
+        rpc = C.c_int64()
+        _lib.check(self._L.selb200_load_begin(self._h, n, p, aux_kind, aux_len, C.byref(rpc)))
+        m = 1 << p
+        for g0 in range(0, n, rpc.value):
+            cnt = min(rpc.value, n - g0)
+            r, st, ax = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _lib.check(self._L.selb200_load_acquire(self._h, g0, cnt, C.byref(r), C.byref(st), C.byref(ax)))
+            regs = np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_uint8)), shape=(cnt, m))
+            stored = np.ctypeslib.as_array(C.cast(st, C.POINTER(C.c_double)), shape=(cnt,))
+            aux = None
+            if aux_kind == AUX_SMH:
+                aux = np.ctypeslib.as_array(C.cast(ax, C.POINTER(C.c_uint64)), shape=(cnt, aux_len))
+            elif aux_kind == AUX_HLL:
+                aux = np.ctypeslib.as_array(C.cast(ax, C.POINTER(C.c_uint8)), shape=(cnt, 1 << aux_len))
+            fill(g0, cnt, regs, stored, aux)
+            _lib.check(self._L.selb200_load_commit(self._h))
+        _lib.check(self._L.selb200_load_end(self._h))
+        self.n, self.p, self._order, self._keep = n, p, None, None
+        return self
+
     def order(self):
         if getattr(self, "_order", None) is not None:
             return self._order

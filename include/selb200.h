@@ -123,6 +123,22 @@ int selb200_load_host(selb200_ctx* ctx, int64_t n, int p, const uint8_t* regs, c
 int selb200_load_device(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_regs, const double* stored_host,
                         int aux_kind, int aux_len, const void* d_aux);
 
+/* Streaming load (what the C++ CLI uses): the caller decodes sketch files straight into pinned
+ * staging slots, chunk by chunk, while the device copy, validation, histogram and cardinality of
+ * earlier chunks are already running.
+ *   begin   : declares n, p and the aux kind; *rows_per_chunk = largest chunk (64 MiB of registers)
+ *   acquire : rows [g0, g0+count) must follow the previous chunk; returns host pointers to fill:
+ *             regs uint8[count][2^p], stored double[count] (value_ of each header, <0 = recompute),
+ *             aux per aux_kind (NULL pointer returned for SELB200_AUX_NONE).  Blocks only when
+ *             all three slots are still being copied.
+ *   commit  : queues the H2D copies + device work of the acquired rows (asynchronous)
+ *   end     : sort by cardinality, aux re-layout; afterwards selb200_run may be called
+ * Equivalent to one selb200_load_host call with the concatenated rows. */
+int selb200_load_begin(selb200_ctx* ctx, int64_t n, int p, int aux_kind, int aux_len, int64_t* rows_per_chunk);
+int selb200_load_acquire(selb200_ctx* ctx, int64_t g0, int64_t count, uint8_t** regs, double** stored, void** aux);
+int selb200_load_commit(selb200_ctx* ctx);
+int selb200_load_end(selb200_ctx* ctx);
+
 /* After a load: cards_sorted[i] = cardinality (double) of the i-th genome in sorted
  * order; order[i] = its index in file-list order.  Either pointer may be NULL. */
 int selb200_get_order(selb200_ctx* ctx, double* cards_sorted, int32_t* order);

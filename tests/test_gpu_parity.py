@@ -203,3 +203,40 @@ def test_other_primary_precisions(gpu):
         r = run_gpu(regs, None, "cb", 0.9, gpu)
         o = O.select(regs, p, "cb", np.float32(0.9))
         compare(r, o, 0.9)
+
+
+def test_streaming_load_equals_bulk_load(gpu):
+    """selb200_load_begin/acquire/commit/end over pinned slots == one selb200_load_host call."""
+    n = 9000          # > 2 chunks of 4096 rows
+    plan = synth.make_plan(n, 44)
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128)
+    stored = np.full(n, -1.0)
+    stored[17] = 1234567.25                      # a trusted stored cardinality (hll.h:1138-1141)
+
+    def fill(g0, cnt, r, st, ax):
+        r[:] = regs[g0:g0 + cnt]
+        st[:] = stored[g0:g0 + cnt]
+        ax[:] = aux[g0:g0 + cnt]
+
+    with S.Selection(gpu) as sel:
+        sel.load_stream(n, 14, fill, AUX_SMH, 128)
+        a = sel.run(tau=np.float32(0.9), criterion="smh_a")
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH, stored=stored)
+        b = sel.run(tau=np.float32(0.9), criterion="smh_a")
+    assert np.array_equal(a.order, b.order) and np.array_equal(a.cards_sorted, b.cards_sorted)
+    assert 1234567.25 in a.cards_sorted
+    assert np.array_equal(a.i, b.i) and np.array_equal(a.k, b.k) and np.array_equal(a.jaccard, b.jaccard)
+    ora = O.select(regs, 14, "smh_a", np.float32(0.9), aux=aux, stored=stored, threads=8)
+    compare(a, ora, 0.9)
+
+
+def test_malformed_aux_hll_is_rejected(gpu):
+    plan = synth.make_plan(40, 5)
+    regs = synth.hll(plan, 14)
+    aux = synth.hll(plan, 8, synth.TAG_AUX_HLL).copy()
+    aux[3, 7] = 64 - 8 + 2
+    with S.Selection(gpu) as sel:
+        with pytest.raises(S.SelB200Error):
+            sel.load(regs, aux, AUX_HLL)
