@@ -14,9 +14,9 @@ from .selection import (  # noqa: F401
     format_lines,
     run_filelist,
 )
-from . import sketch_io, synth  # noqa: F401
+from . import build_sketch, sketch_io, synth  # noqa: F401
 
 __all__ = [
     "Selection", "SelectionResult", "CRITERIA", "band_params", "format_lines", "run_filelist",
-    "sketch_io", "synth", "lib", "lib_path", "SelB200Error", "LibraryNotBuilt",
+    "sketch_io", "synth", "build_sketch", "lib", "lib_path", "SelB200Error", "LibraryNotBuilt",
 ]

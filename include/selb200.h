@@ -172,6 +172,19 @@ int selb200_sort_order(int64_t n, const double* cards, int32_t* order);
  * auxiliary-HLL (which=1) sketches; a,b are file-list indices (host arrays). */
 int selb200_debug_union(selb200_ctx* ctx, int which, int64_t count, const int32_t* a, const int32_t* b, double* t);
 
+/* ---- sketch builder (what `build_sketch` computes) ---------------------
+ * For genome g the sequence characters are seq[offsets[g] .. offsets[g+1]) with ONE non-ACGT byte
+ * between FASTA records (a record restarts the rolling 31-mer, src/build_sketch.cpp:61-92).
+ * Writes the primary HLL registers (uint8 [n][2^p], sketch/include/sketch/hll.h:886-894 with
+ * WangHash, hash.h:44-53) and the auxiliary sketch: SELB200_AUX_HLL -> uint8 [n][2^aux_len];
+ * SELB200_AUX_SMH -> uint64 [n][selb200_smh_size(aux_len)] SuperMinHash buckets
+ * (sketch/include/sketch/bbmh.h:639-670).  Host pointers in and out; byte-identical to the
+ * reference's sketches.  selb200_sketch_last_error() reports this family's failures. */
+int selb200_smh_size(int m_arg);   /* bucket count after SizePow2Policy rounding (policy.h:14-19) */
+int selb200_sketch_host(int device, int64_t n_genomes, const uint8_t* seq, const int64_t* offsets, int p,
+                        int aux_kind, int aux_len, uint8_t* out_hll, void* out_aux);
+const char* selb200_sketch_last_error(void);
+
 /* ---- synthetic sketches ("synth-v1", integer-exact; bench + tests) --------
  * Registers follow P(reg <= k) = T[k]/2^64 with T supplied by the caller
  * (64 thresholds per stream); a member's registers are byte-max(core, private),

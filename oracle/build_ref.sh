@@ -23,6 +23,12 @@ if [ ! "$OUT/libref_kernels.so" -nt "$REF/src/selection_kernels.cu" ] || [ "${FO
       -DNDEBUG -I. -Iinclude -shared -Xcompiler -fPIC src/selection_kernels.cu -o "$OUT/libref_kernels.so") \
     && echo "build_ref: built $OUT/libref_kernels.so"
 fi
+# The reference's sketch builder (src/build_sketch.cpp), checker for our GPU build_sketch.
+if [ ! "$OUT/build_sketch" -nt "$REF/src/build_sketch.cpp" ] || [ "${FORCE:-0}" = "1" ]; then
+  (cd "$REF" && g++ -O3 -std=c++17 -march=x86-64-v3 -fopenmp -DSEQAN_HAS_ZLIB=1 -DNDEBUG -w \
+      -I. -Isketch -Isketch/include -Isketch/include/blaze -Iseqan-library-2.4.0/include -Iinclude \
+      src/build_sketch.cpp -lz -pthread -o "$OUT/build_sketch") && echo "build_ref: built $OUT/build_sketch"
+fi
 if [ "$OUT/selection" -nt "$REF/src/selection.cpp" ] && [ "${FORCE:-0}" != "1" ]; then
   echo "build_ref: $OUT/selection up to date"
   exit 0

@@ -164,6 +164,61 @@ bool hll_an(double tau, uint64_t e1, uint64_t e2, double t_hat, int p, float Z, 
 
 }  // namespace
 
+namespace {
+// ---------------------------------------------------------------------------------------------
+// build_sketch restatement.  `seq` is the concatenation of the records'
+// sequence characters with one non-ACGT byte between records (a new record restarts the rolling
+// k-mer, src/build_sketch.cpp:61-62: kmer = 0, bases = 0 per readRecord).
+// ---------------------------------------------------------------------------------------------
+static inline int base_code(uint8_t ch) {           // build_sketch.cpp:69-81 after SeqAn's Iupac upper-casing
+    switch (ch) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+    }
+    return -1;
+}
+
+static inline uint64_t canonical_kmer(uint64_t kmer, unsigned k) {      // build_sketch.cpp:26-39
+    uint64_t r = kmer;
+    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+    r = ((r >> 8) & 0x00FF00FF00FF00FFull) | ((r & 0x00FF00FF00FF00FFull) << 8);
+    r = ((r >> 16) & 0x0000FFFF0000FFFFull) | ((r & 0x0000FFFF0000FFFFull) << 16);
+    r = (r >> 32) | (r << 32);
+    const uint64_t rev = (~r) >> (64 - 2 * k);
+    return kmer < rev ? kmer : rev;
+}
+
+static inline uint64_t wang_hash(uint64_t key) {                        // sketch/include/sketch/hash.h:44-53
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+template <typename F>
+static void for_each_kmer(const uint8_t* seq, uint64_t len, unsigned k, F f) {   // build_sketch.cpp:61-92
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    uint64_t kmer = 0;
+    unsigned bases = 0;
+    for (uint64_t i = 0; i < len; ++i) {
+        const int c = base_code(seq[i]);
+        ++bases;
+        uint64_t two = 0;
+        if (c < 0) { bases = 0; kmer = 0; } else two = (uint64_t)c;
+        kmer = ((kmer << 2) | two) & mask;
+        if (bases == k) { f(canonical_kmer(kmer, k)); --bases; }
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 enum { ORACLE_CRIT_CB = 0, ORACLE_CRIT_SMH_A = 1, ORACLE_CRIT_HLL_A = 2, ORACLE_CRIT_HLL_AN = 3 };
@@ -310,6 +365,63 @@ int64_t oracle_select(int n, int p, const uint8_t* regs, const double* stored, i
             if (w < out_cap) { out_i[w] = i; out_k[w] = rk[(size_t)i][t]; out_j[w] = rj[(size_t)i][t]; }
     if (stage) { stage[0] = (int64_t)n * (n - 1) / 2; stage[1] = s_cb; stage[2] = s_aux; stage[3] = s_out; }
     return w;
+}
+
+// hll_t::addh = add(WangHash(item)), sketch/include/sketch/hll.h:886-894
+void oracle_sketch_hll(const uint8_t* seq, uint64_t len, int p, uint8_t* regs) {
+    std::memset(regs, 0, (size_t)1 << p);
+    for_each_kmer(seq, len, 31, [&](uint64_t item) {
+        const uint64_t h = wang_hash(item);
+        const uint32_t index = (uint32_t)(h >> (64 - p));
+        const uint8_t lzt = (uint8_t)(__builtin_clzll(((h << 1) | 1) << (p - 1)) + 1);
+        if (regs[index] < lzt) regs[index] = lzt;
+    });
+}
+
+// SuperMinHash<>::addh, sketch/include/sketch/bbmh.h:639-670, RNG wy::WyHash<uint32_t,1>
+// (sketch/include/aesctr/wy.h:53-56,98-150): one 64-bit wyhash output feeds two 32-bit draws, low
+// half first.  m is rounded up to a power of two (policy.h:14-19).
+int oracle_smh_size(int m_arg) {
+    int lg = 0;
+    while ((1 << (lg + 1)) <= m_arg) ++lg;
+    if (m_arg & (m_arg - 1)) ++lg;
+    return 1 << lg;
+}
+
+void oracle_sketch_smh(const uint8_t* seq, uint64_t len, int m_arg, uint64_t* h_out) {
+    const uint32_t m = (uint32_t)oracle_smh_size(m_arg);
+    std::vector<uint32_t> p(m), q(m, 0xffffffffu);
+    std::vector<int32_t> b(m, 0);
+    std::vector<uint64_t> h(m, ~0ull);
+    b[m - 1] = (int32_t)m;
+    uint64_t a = m - 1, i_elem = 0;
+    for_each_kmer(seq, len, 31, [&](uint64_t item) {
+        uint64_t state = item ? item : 1337;         // WyRand(seed): seed ? seed : 1337 (seed_ = 0)
+        uint64_t j = 0;
+        while (j <= a) {
+            state += 0x60bee2bee120fc15ull;
+            const unsigned __int128 mul = (unsigned __int128)(state ^ 0xe7037ed1a0b428dbull) * state;
+            const uint64_t v = (uint64_t)mul ^ (uint64_t)(mul >> 64);
+            const uint32_t k = (uint32_t)v & (m - 1);
+            const uint32_t r = (uint32_t)(v >> 32);
+            if (q[j] != (uint32_t)i_elem) { q[j] = (uint32_t)i_elem; p[j] = (uint32_t)j; }
+            if (q[k] != (uint32_t)i_elem) { q[k] = (uint32_t)i_elem; p[k] = k; }
+            std::swap(p[k], p[j]);
+            const uint64_t crj = (j << 32) | r;
+            if (crj < h[p[j]]) {
+                const uint32_t jprime = std::min(m - 1, (uint32_t)(h[p[j]] >> 32));
+                h[p[j]] = crj;
+                if (j < jprime) {
+                    --b[jprime];
+                    ++b[j];
+                    while (b[a] == 0) --a;
+                }
+            }
+            ++j;
+        }
+        ++i_elem;
+    });
+    std::memcpy(h_out, h.data(), (size_t)m * 8);
 }
 
 }  // extern "C"

@@ -39,6 +39,8 @@ def lib():
                                     C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+        L.oracle_smh_size.restype = C.c_int
+        L.oracle_smh_size.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
