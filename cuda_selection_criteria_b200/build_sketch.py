@@ -16,21 +16,30 @@ from . import _lib, sketch_io
 from .selection import AUX_HLL, AUX_NONE, AUX_SMH
 
 
+_IUPAC = set(b"ACGTURYSWKMBDHVNacgturyswkmbdhvn")
+_SPACE = b" \t\n\r\v\f"
+
+
 def read_fasta_clean(path: str) -> bytes:
-    """Sequence characters of every record, records separated by one 'N' (SeqAn's readRecord joins the
-    lines of a record; a new record restarts the k-mer, src/build_sketch.cpp:53-62)."""
+    """Record sequences joined by one 'N', read with SeqAn's rules (seqan/seq_io/fasta_fastq.h:262-282):
+    skip to '>', id = rest of the line, sequence = everything up to the next '>' with whitespace dropped;
+    a character outside the IUPAC alphabet is a ParseError at which the reference stops reading the file
+    (src/build_sketch.cpp:55-58), dropping that record and every later one."""
     opener = gzip.open if path.endswith(".gz") else open
-    out = bytearray()
-    first = True
-    with opener(path, "rb") as f:
-        for line in f:
-            if line.startswith(b">"):
-                if not first:
-                    out += b"N"
-                first = False
-            elif not line.startswith(b";"):
-                out += line.strip()
-    return bytes(out)
+    try:
+        with opener(path, "rb") as f:
+            raw = f.read()
+    except FileNotFoundError:
+        return b""                                    # "ERROR: Could not open the file": the sketch stays empty
+    out = []
+    for rec in raw.split(b">")[1:]:
+        nl = rec.find(b"\n")
+        body = rec[nl + 1:] if nl >= 0 else b""
+        seq = body.translate(None, _SPACE)
+        if not set(seq) <= _IUPAC:
+            break
+        out.append(seq)
+    return b"N".join(out)
 
 
 def smh_size(m_arg: int) -> int:

@@ -101,6 +101,24 @@ def test_oracle_equals_live_reference_build_sketch(tmp_path):
         assert np.array_equal(ora_smh(clean, 128), sketch_io.read_smh(str(tmp_path / nm) + ".smh128"))
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "build_sketch")),
+                    reason="oracle/_ref/build_sketch not built (needs /root/reference)")
+def test_parse_error_rule_matches_live_reference(tmp_path):
+    """A non-IUPAC character stops the reference at that record (SeqAn ParseError -> break)."""
+    rng = np.random.default_rng(11)
+    r = [bytes(rng.choice(list(b"ACGT"), 3000).astype(np.uint8)) for _ in range(4)]
+    fasta = b">a\n" + r[0] + b"\n>b x\n" + r[1][:1500] + b"\n" + r[1][1500:] + b"\n>c\n" + r[2][:100] + b"*" + r[2][100:] + b"\n>d\n" + r[3] + b"\n"
+    with gzip.open(tmp_path / "g.fna.gz", "wb") as f:
+        f.write(fasta)
+    (tmp_path / "list.txt").write_text("g.fna.gz\n")
+    clean = B.read_fasta_clean(str(tmp_path / "g.fna.gz"))
+    assert clean == r[0] + b"N" + r[1]
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "build_sketch"), "-l", "list.txt", "-a", "512", "-c", "smh_a"],
+                   cwd=tmp_path, check=True, capture_output=True)
+    assert np.array_equal(ora_hll(clean, 14), sketch_io.read_hll(str(tmp_path / "g.fna.gz") + ".hll")[4])
+    assert np.array_equal(ora_smh(clean, 64), sketch_io.read_smh(str(tmp_path / "g.fna.gz") + ".smh64"))
+
+
 # ---------------------------------------------------------------------------------- GPU: the builder
 @pytest.mark.gpu
 def test_gpu_builder_regenerates_the_shipped_sketches(gpu, tmp_path):
@@ -143,3 +161,23 @@ def test_gpu_built_sketches_feed_the_selection(gpu, tmp_path):
     B.build_filelist(lst, aux_bytes=512, criterion="smh_a", device=gpu, base=base, out_base=str(tmp_path))
     lines = S.run_filelist(lst, tau=0.9, aux_bytes=512, criterion="smh_a", device=gpu, base=str(tmp_path))
     assert lines == open(os.path.join(base, "results.txt")).read().splitlines()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,suffix", [(["-a", "512", "-c", "smh_a"], ".smh64"), (["-a", "256", "-c", "hll_an", "-t", "3"], ".hll_8")])
+def test_cpp_build_sketch_cli_regenerates_fixtures(gpu, tmp_path, flags, suffix):
+    import shutil
+    names = []
+    for f in FASTAS:
+        shutil.copy(f, tmp_path / os.path.basename(f))
+        names.append(os.path.basename(f))
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    exe = os.path.join(ROOT, "cuda_selection_criteria_b200", "bin", "build_sketch")
+    r = subprocess.run([exe, "-l", "list.txt"] + flags, cwd=tmp_path, capture_output=True, text=True, check=True)
+    assert r.stdout == ""
+    for nm in names:
+        for sfx in (".hll", suffix):
+            assert gzip.open(tmp_path / (nm + sfx)).read() == gzip.open(os.path.join(FIX, nm) + sfx).read()
+    # invalid -c: primary sketches are still written, then the reference's message (build_sketch.cpp:290-292)
+    r = subprocess.run([exe, "-l", "list.txt", "-c", "nope"], cwd=tmp_path, capture_output=True, text=True, check=True)
+    assert r.stdout == "Option -c invalid. The accepted criteria are hll_a, hll_an and smh_a.\n"
