@@ -68,6 +68,7 @@ SYMBOLS = [
     ("selb200_smh_size", _I, [_I]),
     ("selb200_sketch_host", _I, [_I, _I64, _VP, _VP, _I, _I, _I, _VP, _VP]),
     ("selb200_sketch_last_error", C.c_char_p, []),
+    ("selb200_warmup", _I, [_I]),
     ("selb200_synth_hll", _I, [_I, _I, _I64, _I, _VP, _I64, _VP, _VP, C.c_uint64, C.c_uint32, _VP]),
     ("selb200_synth_smh", _I, [_I, _I, _I64, _I, _VP, _I64, _VP, _VP, C.c_uint64, C.c_uint32, _VP]),
 ]

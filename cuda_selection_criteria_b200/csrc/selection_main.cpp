@@ -25,6 +25,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/selb200.h"
@@ -140,6 +141,8 @@ int main(int argc, char* argv[]) {
         }
     }
     omp_set_num_threads((int)threads);
+    std::thread warm([] { selb200_warmup(0); });   // CUDA context comes up while the files are read
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
     std::vector<std::string> files;
     load_file_list(files, list_file);
 

@@ -192,6 +192,16 @@ extern "C" {
 
 const char* selb200_sketch_last_error(void) { return g_sk_err; }
 
+// Creates the CUDA context of `device` ahead of the first real call; a host driver runs it on a
+// side thread while it is still reading files.
+int selb200_warmup(int device) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) {
+        cudaGetLastError();
+        return SELB200_ECUDA;
+    }
+    return SELB200_OK;
+}
+
 int selb200_smh_size(int m_arg) {           // SizePow2Policy (sketch/include/sketch/policy.h:14-19)
     if (m_arg < 1) return 0;
     int lg = 0;

@@ -184,6 +184,8 @@ int selb200_smh_size(int m_arg);   /* bucket count after SizePow2Policy rounding
 int selb200_sketch_host(int device, int64_t n_genomes, const uint8_t* seq, const int64_t* offsets, int p,
                         int aux_kind, int aux_len, uint8_t* out_hll, void* out_aux);
 const char* selb200_sketch_last_error(void);
+/* Create the CUDA context of `device` ahead of time (call it on a side thread while reading files). */
+int selb200_warmup(int device);
 
 /* ---- synthetic sketches ("synth-v1", integer-exact; bench + tests) --------
  * Registers follow P(reg <= k) = T[k]/2^64 with T supplied by the caller
