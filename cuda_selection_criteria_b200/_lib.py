@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [
         ("tau", C.c_float), ("criterion", C.c_int32), ("z_score", C.c_float), ("order_n", C.c_int32),
         ("n_rows", C.c_int32), ("n_bands", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32),
-        ("sort_output", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("sort_output", C.c_int32), ("no_cb", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -1287,7 +1287,9 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     while (zeros < n && c->h_e[(size_t)zeros] == 0) ++zeros;
     CKR(c->lo.ensure((size_t)n * 4));
     CKR(c->hi.ensure((size_t)n * 4));
-    k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau,
+    // no_cb: every ratio passes a bound of -inf, so each row's range is (i, n-1] minus the e==0 columns
+    const double tau_cb = prm->no_cb ? -__builtin_huge_val() : tau;
+    k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau_cb,
                                                 c->lo.as<int32_t>(), c->hi.as<int32_t>());
     CK(cudaGetLastError());
     st.launches++;

@@ -147,7 +147,7 @@ class Selection:
     # -- run ------------------------------------------------------------------------------
     def run(self, tau: float = 0.9, criterion: str | int = "smh_a", z_score: float = 1.96, order_n: int = 1,
             n_rows: int = 0, n_bands: int = 0, shard: int = 0, n_shards: int = 1, sort_output: bool = True,
-            fetch: bool = True) -> SelectionResult:
+            fetch: bool = True, no_cb: bool = False) -> SelectionResult:
         prm = _lib.Params()
         self._L.selb200_default_params(C.byref(prm))
         prm.tau = tau
@@ -157,6 +157,7 @@ class Selection:
         prm.n_rows, prm.n_bands = n_rows, n_bands
         prm.shard, prm.n_shards = shard, n_shards
         prm.sort_output = int(sort_output)
+        prm.no_cb = int(no_cb)
         st = _lib.Stats()
         _lib.check(self._L.selb200_run(self._h, C.byref(prm), C.byref(st)))
         cards, order = self.order()

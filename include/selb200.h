@@ -67,7 +67,8 @@ typedef struct selb200_params {
     int32_t shard;    /* this process's shard: tiles shard, shard+n_shards, ... of the tile list */
     int32_t n_shards; /* 1 = whole pair space                                                  */
     int32_t sort_output; /* 1: order results by (i,k) like the reference prints them          */
-    int32_t reserved[7];
+    int32_t no_cb;    /* 1: skip the cardinality bound (the "smh_a" loop of experiments/src/time_smh.cpp:229-257; the e2==0 skip stays) */
+    int32_t reserved[6];
 } selb200_params;
 
 /* Per-run statistics (stage counts + per-kernel device times). */

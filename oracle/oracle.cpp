@@ -219,7 +219,11 @@ static void for_each_kmer(const uint8_t* seq, uint64_t len, unsigned k, F f) {  
 
 }  // namespace
 
+static int g_no_cb = 0;   // experiments/src/time_smh.cpp:229-257: the same loop without the CB test
+
 extern "C" {
+
+void oracle_set_no_cb(int v) { g_no_cb = v; }
 
 enum { ORACLE_CRIT_CB = 0, ORACLE_CRIT_SMH_A = 1, ORACLE_CRIT_HLL_A = 2, ORACLE_CRIT_HLL_AN = 3 };
 
@@ -333,7 +337,7 @@ int64_t oracle_select(int n, int p, const uint8_t* regs, const double* stored, i
         for (int k = i + 1; k < n; ++k) {
             const uint64_t e2 = (uint64_t)cards_sorted[k];         // :280
             if (e2 == 0) continue;                                 // :281
-            if (!cb(tau, e1, e2)) break;                           // :282-283
+            if (!g_no_cb && !cb(tau, e1, e2)) break;               // :282-283
             ++s_cb;
             const uint8_t* rb = regs + (size_t)ord[(size_t)k] * m;
             bool pass = true;

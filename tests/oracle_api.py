@@ -62,7 +62,7 @@ def union_size(a: np.ndarray, b: np.ndarray, p: int) -> float:
 
 
 def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, order_n=1, n_rows=0, n_bands=0,
-           threads=0):
+           threads=0, no_cb=False):
     """-> dict(i, k, jaccard, order, cards_sorted, stage=[P, P_cb, P_aux, P_out])."""
     regs = np.ascontiguousarray(regs, np.uint8)
     n = regs.shape[0]
@@ -79,6 +79,7 @@ def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, or
     st = np.ascontiguousarray(stored, np.float64) if stored is not None else None
     cards = np.empty(n, np.float64); order = np.empty(n, np.int32)
     stage = np.zeros(4, np.int64)
+    lib().oracle_set_no_cb(int(no_cb))
     cap = 1 << 16
     while True:
         oi = np.empty(cap, np.int32); ok = np.empty(cap, np.int32); oj = np.empty(cap, np.float64)
@@ -89,6 +90,7 @@ def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, or
         if cnt <= cap:
             break
         cap = int(cnt)
+    lib().oracle_set_no_cb(0)
     return dict(i=oi[:cnt].copy(), k=ok[:cnt].copy(), jaccard=oj[:cnt].copy(), order=order, cards_sorted=cards,
                 stage=stage.tolist(), n_rows=n_rows, n_bands=n_bands)
 

@@ -129,3 +129,15 @@ def test_shims_match_reference_launchers(gpu, sym, tau):
     assert res["ref"][0].size > 0
     assert np.array_equal(res["ref"][0], res["ours"][0])
     assert np.array_equal(res["ref"][1], res["ours"][1])
+
+
+def test_cli_time_smh_cuda(gpu):
+    """Three `list;phase;tau;seconds` lines like experiments/src/time_smh_cuda.cpp:228-230,279-299."""
+    r = subprocess.run([os.path.join(BIN, "time_smh_cuda"), "-l", "test_influeza_filelist.txt", "-h", "0.9", "-m", "64",
+                        "-b", "128"], cwd=GOLD, capture_output=True, text=True, check=True)
+    lines = r.stdout.splitlines()
+    assert [ln.split(";")[:3] for ln in lines] == [["test_influeza_filelist.txt", ph, "0.9"]
+                                                   for ph in ("build_smh", "smh_a", "CB+smh_a")]
+    assert all(float(ln.split(";")[3]) > 0 for ln in lines)
+    # SMH rebuilt from the FASTA files (M = 64) gives the 7 pairs of results.txt in both modes
+    assert "smh_a 7, CB+smh_a 7" in r.stderr

@@ -240,3 +240,17 @@ def test_malformed_aux_hll_is_rejected(gpu):
     with S.Selection(gpu) as sel:
         with pytest.raises(S.SelB200Error):
             sel.load(regs, aux, AUX_HLL)
+
+
+def test_no_cb_mode_matches_time_smh_loop(gpu):
+    """The "smh_a" loop of experiments/src/time_smh.cpp:229-257: no cardinality bound, e2 == 0 still skipped."""
+    plan = synth.make_plan(700, 31)
+    regs = synth.hll(plan, 14).copy()
+    regs[11] = 0
+    aux = synth.smh(plan, 128)
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        r = sel.run(tau=np.float32(0.8), criterion="smh_a", no_cb=True)
+    o = O.select(regs, 14, "smh_a", np.float32(0.8), aux=aux, no_cb=True)
+    compare(r, o, 0.8)
+    assert r.stats["pairs_cb"] == 700 * 699 // 2          # the empty genome sorts first, so it is never a second genome
