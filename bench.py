@@ -294,20 +294,22 @@ def main():
     tau32 = np.float32(a.tau)
     stats_acc = []
 
+    if world > 1:
+        sdist.setup_gather(sel)        # rank 0's landing zone, mapped into every rank (CUDA IPC)
+
+    def fetch_lists(s_):
+        """rank 0: D2H of the (merged) pair list — inside the metric."""
+        kp, jp, cnt = s_.result_device_ptrs()
+        hk = sdist.device_tensor(kp, cnt, "<i8", local).cpu()
+        hj = sdist.device_tensor(jp, cnt, "<f8", local).cpu()
+        return hk.numel() + 0 * hj.numel()
+
     def step_resident():
+        # with several ranks every rank's kernels store its pairs into rank 0's memory over NVLink
+        # (peer-memory gather inside selb200_run); rank 0 sorts the merged list
         res = sel.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
-                      sort_output=(world == 1))   # with several ranks the merged list is sorted once on rank 0
-        kp, jp, cnt = sel.result_device_ptrs()
-        keys = sdist.device_tensor(kp, cnt, "<i8", local)
-        jac = sdist.device_tensor(jp, cnt, "<f8", local)
-        if world > 1:
-            keys, jac = sdist.gather_lists(keys, jac, dst=0)
-        out_n = 0
-        if rank == 0:
-            hk = keys.cpu(); hj = jac.cpu()          # D2H of the pair list (inside the metric)
-            out_n = hk.numel()
-            _ = hj
-        return res.stats, out_n
+                      gather=(world > 1))
+        return res.stats, (fetch_lists(sel) if rank == 0 else 0)
 
     for _ in range(a.warmup):
         step_resident()
@@ -359,36 +361,30 @@ def main():
     # ---- e2e: host buffers through the public API ---------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        regs_h = aux_h = None
-        if rank == 0:
-            regs_h = torch.empty(regs_d.shape, dtype=regs_d.dtype, pin_memory=True)
-            regs_h.copy_(regs_d)
-            if aux_d is not None:
-                aux_h = torch.empty(aux_d.shape, dtype=aux_d.dtype, pin_memory=True)
-                aux_h.copy_(aux_d)
+        # every rank holds its slice of the file list in pinned host memory (world == 1: everything)
+        g0, rows, _per = sdist.slice_rows(a.n, rank, world)
+        regs_h = torch.empty((rows, regs_d.shape[1]), dtype=regs_d.dtype, pin_memory=True)
+        regs_h.copy_(regs_d[g0:g0 + rows])
+        aux_h = None
+        if aux_d is not None:
+            aux_h = torch.empty((rows, aux_d.shape[1]), dtype=aux_d.dtype, pin_memory=True)
+            aux_h.copy_(aux_d[g0:g0 + rows])
         torch.cuda.synchronize()
         sel2 = S.Selection(local, stream=stream)
+        sh = None
+        if world > 1:
+            sdist.setup_gather(sel2)
+            sh = sdist.ShardedSketches(a.n, regs_d.shape[1], aux_d.shape[1] if aux_d is not None else 0,
+                                       aux_d.dtype if aux_d is not None else None, dev, rank, world)
 
         def step_e2e():
             if world == 1:
                 sel2.load(regs_h, aux_h, aux_kind)                       # H2D inside
             else:
-                if rank == 0:
-                    regs_d.copy_(regs_h, non_blocking=True)
-                    if aux_d is not None:
-                        aux_d.copy_(aux_h, non_blocking=True)
-                sdist.broadcast_sketches(regs_d, aux_d, src=0)
-                sel2.load(regs_d, aux_d, aux_kind)
-            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
-                     sort_output=(world == 1))
-            kp, jp, cnt = sel2.result_device_ptrs()
-            keys = sdist.device_tensor(kp, cnt, "<i8", local)
-            jac = sdist.device_tensor(jp, cnt, "<f8", local)
-            if world > 1:
-                keys, jac = sdist.gather_lists(keys, jac, dst=0)
-            if rank == 0:
-                return keys.cpu().numel() + 0 * jac.cpu().numel()
-            return 0
+                r_all, a_all = sh.assemble(regs_h, aux_h)                # H2D of the slice + NCCL all-gather
+                sel2.load(r_all, a_all, aux_kind)
+            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1))
+            return fetch_lists(sel2) if rank == 0 else 0
 
         e2e_steps = max(1, min(a.steps, 5))
         step_e2e()
@@ -422,7 +418,8 @@ def main():
                 "vs_baseline": None, "dtype": "u8 registers / u64 buckets, f64 estimator", "data": "synthetic",
                 "config": {"workload": workload_name(a), "n": a.n, "pairs": int(pairs_total),
                            "pairs_cb": st0["pairs_cb"], "pairs_aux_rank0": st0["pairs_aux"], "pairs_out": out_n,
-                           "bands_x_rows": [st0["n_bands"], st0["n_rows"]], "parallelism": f"tile-shard x{world}",
+                           "bands_x_rows": [st0["n_bands"], st0["n_rows"]], "parallelism": (f"tile-shard x{world}" + (", peer-memory gather to rank 0; e2e: per-rank H2D slices + "
+                                                                       "NCCL all-gather" if world > 1 else "")),
                            "l2": "inputs (1.74 GB) larger than L2; no flush needed"},
                 "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(sum(s["launches"] for s in stats_acc)),

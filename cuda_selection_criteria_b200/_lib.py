@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [
         ("tau", C.c_float), ("criterion", C.c_int32), ("z_score", C.c_float), ("order_n", C.c_int32),
         ("n_rows", C.c_int32), ("n_bands", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32),
-        ("sort_output", C.c_int32), ("no_cb", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("sort_output", C.c_int32), ("no_cb", C.c_int32), ("gather", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -39,6 +39,8 @@ class Stats(C.Structure):
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
+
+GATHER_HANDLE_BYTES = 128
 
 # every symbol include/selb200.h declares: (name, restype, argtypes)
 _VP, _I, _I64 = C.c_void_p, C.c_int, C.c_int64
@@ -62,6 +64,9 @@ SYMBOLS = [
     ("selb200_near_count", _I64, [_VP]),
     ("selb200_copy_near", _I, [_VP, _I64, _VP, _VP, _VP]),
     ("selb200_result_device", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
+    ("selb200_gather_create", _I, [_VP, _I64, _VP]),
+    ("selb200_gather_attach", _I, [_VP, _I, _I, _VP]),
+    ("selb200_gather_close", None, [_VP]),
     ("selb200_band_params", _I, [_I, C.c_float, _I, C.POINTER(_I), C.POINTER(_I)]),
     ("selb200_sort_order", _I, [_I64, _VP, _VP]),
     ("selb200_debug_union", _I, [_VP, _I, _I64, _VP, _VP, _VP]),

@@ -25,6 +25,7 @@
 #include "../../include/selb200.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -35,6 +36,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "estimators.cuh"
 
@@ -186,6 +188,21 @@ struct selb200_ctx {
     const double* res_j = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    // device-built tile list
+    DevBuf tile_nt, rb_pairs;
+    int64_t tile_cap = 0;
+    std::vector<int32_t> h_tprefix;
+    std::vector<unsigned long long> h_rb_pairs;
+    // peer-memory gather (selb200_gather_*)
+    struct Gather {
+        bool attached = false, is_root = false, mapped = false;
+        int rank = 0, world = 1;
+        void* zone = nullptr;            // root: own allocation; others: cudaIpcOpenMemHandle mapping
+        int64_t cap = 0, near_cap = 0;
+        uint32_t epoch = 0;              // gather runs completed so far (all ranks advance together)
+        unsigned long long* h_merged = nullptr;   // pinned [4]
+    } g;
+    DevBuf g_push, g_merged;
 
     cudaEvent_t ev() {
         if (ev_used == ev_pool.size()) {
@@ -473,32 +490,70 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 }
 
 // ============================================================================
-// tile lookup shared by the filter kernels
+// tile list of the CB band, built on the device (no host round trip):
+//   k_rowblock_span : per 128-row block, the column-block span of its band and its pair count
+//   cub exclusive scan over the spans -> first tile index of every row block
+//   k_tile_table    : (row block, column block) of every tile, so that a filter CTA finds its
+//                     tile with one 8-byte load
+// meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
+// range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
 // ============================================================================
-struct TileRef { int rb, cb; };
+enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WORDS = 8 };
 
-__device__ __forceinline__ TileRef find_tile(const int32_t* __restrict__ tile_prefix,
-                                             const int32_t* __restrict__ tile_cb0, int nrb, int tile) {
-    int a = 0, b = nrb;   // last rb with tile_prefix[rb] <= tile
-    while (b - a > 1) {
-        const int mid = (a + b) >> 1;
-        if (tile_prefix[mid] <= tile) a = mid; else b = mid;
+__global__ void __launch_bounds__(128)
+k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
+                int32_t* __restrict__ nt, int32_t* __restrict__ cb0, unsigned long long* __restrict__ rb_pairs,
+                unsigned long long* __restrict__ meta) {
+    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (rb > nrb) return;
+    if (rb == nrb) { if (lane == 0) nt[nrb] = 0; return; }   // scan sentinel: prefix[nrb] = total
+    int cmin = INT32_MAX, cmax = -1;
+    unsigned long long cnt = 0;
+    for (int i = rb * TILE + lane; i < min(n, (rb + 1) * TILE); i += 32) {
+        const int l = lo[i], h = hi[i];
+        if (h < l) continue;
+        cnt += (unsigned long long)(h - l + 1);
+        cmin = min(cmin, l);
+        cmax = max(cmax, h);
     }
-    TileRef t;
-    t.rb = a;
-    t.cb = tile_cb0[a] + (tile - tile_prefix[a]);
-    return t;
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    if (lane == 0) {
+        nt[rb] = cnt ? cmax / TILE - cmin / TILE + 1 : 0;
+        cb0[rb] = cnt ? cmin / TILE : 0;
+        rb_pairs[rb] = cnt;
+        if (cnt) atomicAdd(meta + M_PAIRS_CB, cnt);
+    }
 }
 
-// (row block, column block) of every tile of the run, built once per run so that a filter CTA finds
-// its tile with one 8-byte load instead of a dependent binary search
-__global__ void k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ tile_cb0, int nrb,
-                             int ntiles, int2* __restrict__ tile_rc) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const TileRef tr = find_tile(tile_prefix, tile_cb0, nrb, t);
-    tile_rc[t] = make_int2(tr.rb, tr.cb);
+__global__ void __launch_bounds__(128)
+k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ cb0, int nrb, long long tile_cap,
+             int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
+    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (rb >= nrb) return;
+    const int a = tile_prefix[rb], cnt = tile_prefix[rb + 1] - a, c0 = cb0[rb];
+    for (int t = lane; t < cnt; t += 32)
+        if (a + t < tile_cap) tile_rc[a + t] = make_int2(rb, c0 + t);
+    if (rb == 0 && lane == 0) meta[M_TILES] = (unsigned long long)tile_prefix[nrb];
 }
+
+// tiles owned by one shard: tile = shard + j * n_shards for j in [0, count)
+struct TileWalk {
+    const int2* tile_rc;
+    const unsigned long long* meta;
+    long long tile_cap;
+    int shard, n_shards;
+    int j0, j1;          // this launch covers j in [j0, j1) (clipped to the shard's tile count)
+    __device__ __forceinline__ int count() const {
+        const long long total = (long long)min((unsigned long long)tile_cap, meta[M_TILES]);
+        const long long mine = total > shard ? (total - shard + n_shards - 1) / n_shards : 0;
+        return (int)min((long long)j1, mine);
+    }
+    __device__ __forceinline__ int2 tile(int j) const { return __ldg(tile_rc + shard + (long long)j * n_shards); }
+};
 
 // ============================================================================
 // K3: LSH band signatures.  For the g-th sorted genome and band b, sig(b,g) = 16 bits of a mix
@@ -548,70 +603,73 @@ __global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long l
 // (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
 __global__ void __launch_bounds__(256, FILTER_CTAS_PER_SM)
 k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
-                  const int2* __restrict__ tile_rc,
-                  int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                  TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
                   unsigned long long cand_cap) {
     __shared__ __align__(16) uint32_t sR[SIG_CHUNK][TILE];
     __shared__ __align__(16) uint32_t sC[SIG_CHUNK][TILE];
-    const int2 rc = __ldg(tile_rc + tile0 + (int)blockIdx.x * tile_stride);
-    const int r0 = rc.x * TILE, c0 = rc.y * TILE;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int jend = tw.count();
+    // persistent CTAs: the shard's tile count lives in device memory, so no host sync sizes the grid
+    for (int j = tw.j0 + (int)blockIdx.x; j < jend; j += (int)gridDim.x) {
+        const int2 rc = tw.tile(j);
+        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
 
-    uint32_t acc[8][8];
+        uint32_t acc[8][8];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
 
-    for (int b0 = 0; b0 < n_words; b0 += SIG_CHUNK) {
-        const int nb = min(SIG_CHUNK, n_words - b0);
-        __syncthreads();
-        for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per load
-            const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
-            if (part < 32)
-                *reinterpret_cast<uint4*>(&sR[bb][x]) =
-                    __ldg(reinterpret_cast<const uint4*>(sigR + (size_t)(b0 + bb) * npad + r0 + x));
-            else
-                *reinterpret_cast<uint4*>(&sC[bb][x]) =
-                    __ldg(reinterpret_cast<const uint4*>(sigC + (size_t)(b0 + bb) * npad + c0 + x));
+        for (int b0 = 0; b0 < n_words; b0 += SIG_CHUNK) {
+            const int nb = min(SIG_CHUNK, n_words - b0);
+            __syncthreads();
+            for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per load
+                const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
+                if (part < 32)
+                    *reinterpret_cast<uint4*>(&sR[bb][x]) =
+                        __ldg(reinterpret_cast<const uint4*>(sigR + (size_t)(b0 + bb) * npad + r0 + x));
+                else
+                    *reinterpret_cast<uint4*>(&sC[bb][x]) =
+                        __ldg(reinterpret_cast<const uint4*>(sigC + (size_t)(b0 + bb) * npad + c0 + x));
+            }
+            __syncthreads();
+            for (int bb = 0; bb < nb; ++bb) {
+                const uint4 ra = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8]);
+                const uint4 rb = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8 + 4]);
+                const uint4 ca = *reinterpret_cast<const uint4*>(&sC[bb][tx * 4]);
+                const uint4 cb = *reinterpret_cast<const uint4*>(&sC[bb][64 + tx * 4]);
+                const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
+            }
         }
-        __syncthreads();
-        for (int bb = 0; bb < nb; ++bb) {
-            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8]);
-            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8 + 4]);
-            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[bb][tx * 4]);
-            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[bb][64 + tx * 4]);
-            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        uint32_t any = 0xffffffffu;
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
+            for (int b = 0; b < 8; ++b) any = __vminu2(any, acc[a][b]);
+        if ((any & 0xffffu) != 0 && (any >> 16) != 0) continue;
+        // rare path: gather the matching (a,b) cells into a bit mask, then walk its set bits
+        unsigned long long cells = 0ull;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                if ((acc[a][b] & 0xffffu) == 0 || (acc[a][b] >> 16) == 0) cells |= 1ull << (a * 8 + b);
+        while (cells) {
+            const int bit = __ffsll((long long)cells) - 1;
+            cells &= cells - 1;
+            const int a = bit >> 3, b = bit & 7;
+            const int i = r0 + ty * 8 + a;
+            const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+            if (i >= n || k < lo[i] || k > hi[i]) continue;
+            const unsigned long long slot = warp_claim(cand_count);
+            if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
         }
-    }
-    uint32_t any = 0xffffffffu;
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) any = __vminu2(any, acc[a][b]);
-    if ((any & 0xffffu) != 0 && (any >> 16) != 0) return;
-    // rare path: gather the matching (a,b) cells into a bit mask, then walk its set bits
-    unsigned long long cells = 0ull;
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-            if ((acc[a][b] & 0xffffu) == 0 || (acc[a][b] >> 16) == 0) cells |= 1ull << (a * 8 + b);
-    while (cells) {
-        const int bit = __ffsll((long long)cells) - 1;
-        cells &= cells - 1;
-        const int a = bit >> 3, b = bit & 7;
-        const int i = r0 + ty * 8 + a;
-        const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
-        if (i >= n || k < lo[i] || k > hi[i]) continue;
-        const unsigned long long slot = warp_claim(cand_count);
-        if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
     }
 }
 
@@ -654,17 +712,19 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 
 // CB only: every pair of the band inside this tile
 __global__ void __launch_bounds__(256)
-k_tile_enum(const int2* __restrict__ tile_rc, int tile0,
-            int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, uint2* __restrict__ pairs,
-            unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const int2 rc = __ldg(tile_rc + tile0 + (int)blockIdx.x * tile_stride);
-    const int r0 = rc.x * TILE, c0 = rc.y * TILE;
-    for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
-        const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
-        if (i >= n || k >= n) continue;
-        if (k < lo[i] || k > hi[i]) continue;
-        const unsigned long long slot = warp_claim(pair_count);
-        if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+k_tile_enum(TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+            uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
+    const int jend = tw.count();
+    for (int j = tw.j0 + (int)blockIdx.x; j < jend; j += (int)gridDim.x) {
+        const int2 rc = tw.tile(j);
+        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
+        for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
+            const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
+            if (i >= n || k >= n) continue;
+            if (k < lo[i] || k > hi[i]) continue;
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+        }
     }
 }
 
@@ -693,9 +753,8 @@ struct StopHll {      // early exit of the MLE: the criterion already fails at t
 
 template <int AN>
 __global__ void __launch_bounds__(64)
-k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
-                  const int2* __restrict__ tile_rc,
-                  int tile0, int tile_stride, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, TileWalk tw,
+                  const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                   unsigned long long pair_cap) {
@@ -703,56 +762,59 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux,
     const int nbins = 64 - p_aux + 2;
     uint32_t* hist0 = hist_dyn;
     uint32_t* hist1 = hist_dyn + nbins * 64;
-    const int unit = blockIdx.x;
-    const int2 rc = __ldg(tile_rc + tile0 + (unit >> 2) * tile_stride);
-    const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
     const int words = (1 << p_aux) >> 2;
     const uint32_t bias0 = hist_bias(hist0), bias1 = hist_bias(hist1);
     for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
     __syncwarp();
-    // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
-    for (int item = w; item < 64; item += 2) {
-        const int i0 = r0 + (item >> 2) * 2, i1 = i0 + 1;
-        const int k = c0 + (item & 3) * 32 + (int)lane;
-        const bool v0 = i0 < n && k < n && k >= lo[min(i0, n - 1)] && k <= hi[min(i0, n - 1)];
-        const bool v1 = i1 < n && k < n && k >= lo[min(i1, n - 1)] && k <= hi[min(i1, n - 1)];
-        if (!__any_sync(0xffffffffu, v0 || v1)) continue;
-        const uint32_t* colp = auxT + min((long long)k, npad - 1);
-        const uint32_t* row0 = auxT + min(i0, n - 1);
-        const uint32_t* row1 = auxT + min(i1, n - 1);
+    const int uend = tw.count() * 4;
+    // persistent CTAs over the shard's (tile, quarter) units
+    for (int unit = tw.j0 * 4 + (int)blockIdx.x; unit < uend; unit += (int)gridDim.x) {
+        const int2 rc = tw.tile(unit >> 2);
+        const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
+        // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
+        for (int item = w; item < 64; item += 2) {
+            const int i0 = r0 + (item >> 2) * 2, i1 = i0 + 1;
+            const int k = c0 + (item & 3) * 32 + (int)lane;
+            const bool v0 = i0 < n && k < n && k >= lo[min(i0, n - 1)] && k <= hi[min(i0, n - 1)];
+            const bool v1 = i1 < n && k < n && k >= lo[min(i1, n - 1)] && k <= hi[min(i1, n - 1)];
+            if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+            const uint32_t* colp = auxT + min((long long)k, npad - 1);
+            const uint32_t* row0 = auxT + min(i0, n - 1);
+            const uint32_t* row1 = auxT + min(i1, n - 1);
 #pragma unroll 2
-        for (int j = 0; j < words; ++j) {
-            const uint32_t cw = __ldg(colp + (size_t)j * npad);
-            const uint32_t a0 = __ldg(row0 + (size_t)j * npad);
-            const uint32_t a1 = __ldg(row1 + (size_t)j * npad);
-            const uint32_t m0 = max4_lt128(a0, cw) + bias0, m1 = max4_lt128(a1, cw) + bias1;
-            hist_inc_dual<0>(m0, m1, tb);
-            hist_inc_dual<1>(m0, m1, tb);
-            hist_inc_dual<2>(m0, m1, tb);
-            hist_inc_dual<3>(m0, m1, tb);
-        }
-        bool pass0 = false, pass1 = false;
-        if (v0) {
-            bool stopped = false;
-            const StopHll stop{tau, e[i0], e[k], zs, order_n, AN};
-            const double tu = selb::ertl_mle(hist0 + t, p_aux, 64, stop, &stopped);
-            pass0 = !stopped && stop.crit(tu);
-        }
-        if (v1) {
-            bool stopped = false;
-            const StopHll stop{tau, e[i1], e[k], zs, order_n, AN};
-            const double tu = selb::ertl_mle(hist1 + t, p_aux, 64, stop, &stopped);
-            pass1 = !stopped && stop.crit(tu);
-        }
-        for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
-        if (pass0) {
-            const unsigned long long slot = warp_claim(pair_count);
-            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i0, (uint32_t)k);
-        }
-        if (pass1) {
-            const unsigned long long slot = warp_claim(pair_count);
-            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i1, (uint32_t)k);
+            for (int j = 0; j < words; ++j) {
+                const uint32_t cw = __ldg(colp + (size_t)j * npad);
+                const uint32_t a0 = __ldg(row0 + (size_t)j * npad);
+                const uint32_t a1 = __ldg(row1 + (size_t)j * npad);
+                const uint32_t m0 = max4_lt128(a0, cw) + bias0, m1 = max4_lt128(a1, cw) + bias1;
+                hist_inc_dual<0>(m0, m1, tb);
+                hist_inc_dual<1>(m0, m1, tb);
+                hist_inc_dual<2>(m0, m1, tb);
+                hist_inc_dual<3>(m0, m1, tb);
+            }
+            bool pass0 = false, pass1 = false;
+            if (v0) {
+                bool stopped = false;
+                const StopHll stop{tau, e[i0], e[k], zs, order_n, AN};
+                const double tu = selb::ertl_mle(hist0 + t, p_aux, 64, stop, &stopped);
+                pass0 = !stopped && stop.crit(tu);
+            }
+            if (v1) {
+                bool stopped = false;
+                const StopHll stop{tau, e[i1], e[k], zs, order_n, AN};
+                const double tu = selb::ertl_mle(hist1 + t, p_aux, 64, stop, &stopped);
+                pass1 = !stopped && stop.crit(tu);
+            }
+            for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
+            if (pass0) {
+                const unsigned long long slot = warp_claim(pair_count);
+                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i0, (uint32_t)k);
+            }
+            if (pass1) {
+                const unsigned long long slot = warp_claim(pair_count);
+                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i1, (uint32_t)k);
+            }
         }
     }
 }
@@ -797,6 +859,137 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
             if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
         }
     }
+}
+
+// ============================================================================
+// Peer-memory gather (multi-GPU, one process per GPU): every rank pushes its emitted (key, J)
+// list straight into the ROOT GPU's landing zone with plain stores over NVLink/NVSwitch (the zone
+// is mapped into each process with CUDA IPC).  One system-scope atomicAdd claims a contiguous
+// block per rank, a second one signals completion; the root spins on its own memory until all
+// ranks have signalled, then sorts the merged list.  No NCCL call and no host round trip between
+// the emit kernel and the merged result (SURVEY.md §8e "gather of (i,k,J) lists to GPU 0").
+//   landing zone: GatherHdr | keys[2][cap] | jac[2][cap] | near_keys[2][ncap] | near_j[2][ncap]
+//   two buffers (epoch parity) so that a fast rank may already push run e+1 while the root still
+//   merges run e; `consumed` stops it from getting two runs ahead.
+// ============================================================================
+struct GatherHdr {
+    unsigned long long count[2];        // slots claimed per parity
+    unsigned long long near_count[2];
+    unsigned int done[2];               // ranks whose push is complete, per parity
+    unsigned int consumed;              // runs the root has merged (monotone)
+    unsigned int error;                 // 1: a wait timed out
+    unsigned long long pad[26];
+};
+static_assert(sizeof(GatherHdr) == 256, "landing-zone header is 256 bytes");
+
+struct GatherPush {                     // local to each rank
+    unsigned long long base, near_base;
+    unsigned int go, blocks_done;
+};
+
+struct GatherZone {                     // pointers into the (local or IPC-mapped) landing zone
+    GatherHdr* hdr;
+    uint64_t* keys;                     // [2][cap]
+    double* jac;
+    uint64_t* near_keys;                // [2][near_cap]
+    double* near_j;
+    unsigned long long cap, near_cap;
+};
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+// one thread: (optionally) make sure the pass did not overflow, wait until the buffer of this parity
+// has been merged by the root two runs ago, claim the rank's block in the root's lists
+__global__ void k_gather_claim(GatherZone z, unsigned int epoch, unsigned long long* __restrict__ meta, int check,
+                               unsigned long long cand_cap, unsigned long long pair_lim, unsigned long long out_cap,
+                               unsigned long long tile_cap, unsigned long long near_cap_local,
+                               GatherPush* __restrict__ st) {
+    if (threadIdx.x | blockIdx.x) return;
+    st->go = 0;
+    st->blocks_done = 0;
+    if (check && (meta[M_CAND] > cand_cap || meta[M_PAIRS] > pair_lim || meta[M_OUT] > out_cap ||
+                  meta[M_TILES] > tile_cap))
+        return;                              // the host redoes the pass and pushes afterwards
+    if (epoch >= 2) {
+        const unsigned long long t0 = gtime_ns();
+        while (*(volatile unsigned int*)&z.hdr->consumed + 1u < epoch) {
+            if (gtime_ns() - t0 > GATHER_TIMEOUT_NS) { meta[M_PUSHED] = 2; return; }
+            __nanosleep(200);
+        }
+    }
+    const unsigned int b = epoch & 1u;
+    st->base = atomicAdd_system(&z.hdr->count[b], meta[M_OUT]);
+    st->near_base = atomicAdd_system(&z.hdr->near_count[b], min(meta[M_NEAR], near_cap_local));
+    st->go = 1;
+    meta[M_PUSHED] = 1;
+}
+
+// all CTAs: copy the rank's lists into its block of the root's lists; the last CTA signals
+__global__ void __launch_bounds__(256)
+k_gather_copy(GatherZone z, unsigned int epoch, const unsigned long long* __restrict__ meta,
+              unsigned long long near_cap_local, const uint64_t* __restrict__ keys, const double* __restrict__ jac,
+              const uint64_t* __restrict__ near_keys, const double* __restrict__ near_j, GatherPush* __restrict__ st) {
+    if (!st->go) return;
+    const unsigned int b = epoch & 1u;
+    const unsigned long long cnt = meta[M_OUT], ncnt = min(meta[M_NEAR], near_cap_local);
+    const unsigned long long base = st->base, nbase = st->near_base;
+    uint64_t* dk = z.keys + b * z.cap;
+    double* dj = z.jac + b * z.cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cnt;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long slot = base + i;
+        if (slot < z.cap) { dk[slot] = keys[i]; dj[slot] = jac[i]; }
+    }
+    uint64_t* nk = z.near_keys + b * z.near_cap;
+    double* nj = z.near_j + b * z.near_cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < ncnt;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long slot = nbase + i;
+        if (slot < z.near_cap) { nk[slot] = near_keys[i]; nj[slot] = near_j[i]; }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1) {
+            st->blocks_done = 0;
+            __threadfence_system();
+            atomicAdd_system(&z.hdr->done[b], 1u);
+        }
+    }
+}
+
+// root: wait for every rank's signal, then publish the merged counts where the host can read them
+__global__ void k_gather_wait(GatherZone z, unsigned int epoch, unsigned int world, const GatherPush* __restrict__ st,
+                              unsigned long long* __restrict__ merged /* [count, near_count, error] */) {
+    if (threadIdx.x | blockIdx.x) return;
+    if (!st->go) { merged[2] = 2; return; }      // the root's own pass is being redone: nothing to wait for yet
+    const unsigned int b = epoch & 1u;
+    const unsigned long long t0 = gtime_ns();
+    unsigned long long err = 0;
+    while (*(volatile unsigned int*)&z.hdr->done[b] < world) {
+        if (gtime_ns() - t0 > GATHER_TIMEOUT_NS) { err = 1; z.hdr->error = 1; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    merged[0] = *(volatile unsigned long long*)&z.hdr->count[b];
+    merged[1] = *(volatile unsigned long long*)&z.hdr->near_count[b];
+    merged[2] = err;
+}
+
+// root, after the merge of this parity has been copied out: hand the buffer back
+__global__ void k_gather_release(GatherZone z, unsigned int epoch) {
+    if (threadIdx.x | blockIdx.x) return;
+    const unsigned int b = epoch & 1u;
+    z.hdr->count[b] = 0;
+    z.hdr->near_count[b] = 0;
+    z.hdr->done[b] = 0;
+    __threadfence_system();
+    *(volatile unsigned int*)&z.hdr->consumed = epoch + 1u;
 }
 
 // ============================================================================
@@ -1119,9 +1312,10 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    selb200_gather_close(c);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     for (StageSlot& sl : c->slots) {
@@ -1281,87 +1475,56 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         st.n_rows = n_rows; st.n_bands = n_bands;
     }
 
+    const bool gather = prm->gather != 0;
+    if (gather && !c->g.attached) return fail(SELB200_ESTATE, "params.gather set without selb200_gather_attach");
+    if (gather && (prm->shard != c->g.rank || n_shards != c->g.world))
+        return fail(SELB200_EINVAL, "gather: shard %d/%d does not match the attached rank %d/%d", prm->shard, n_shards,
+                    c->g.rank, c->g.world);
+
+    // meta[]: see the M_* enum (device counters of the sync-free pipeline)
+    CKR(c->counters.ensure(M_WORDS * 8));
+    CK(cudaMemsetAsync(c->counters.p, 0, M_WORDS * 8, s));
+    unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+
     cudaEvent_t ev_begin = c->ev();
-    // ---- K2: CB band ---------------------------------------------------------
+    // ---- K2: CB band + tile list, all on the device ------------------------------------------
     int zeros = 0;
     while (zeros < n && c->h_e[(size_t)zeros] == 0) ++zeros;
+    const int nrb = (n + TILE - 1) / TILE;
     CKR(c->lo.ensure((size_t)n * 4));
     CKR(c->hi.ensure((size_t)n * 4));
+    CKR(c->tile_nt.ensure(((size_t)nrb + 1) * 4));
+    CKR(c->tile_prefix.ensure(((size_t)nrb + 1) * 4));
+    CKR(c->tile_cb0.ensure((size_t)nrb * 4));
+    CKR(c->rb_pairs.ensure((size_t)nrb * 8));
+    // a band can never hold more tiles than the block triangle; 16 Mi tiles (128 MB) to start with
+    // for inputs beyond n = 724k, grown on demand like every other list
+    const int64_t tri = (int64_t)nrb * (nrb + 1) / 2;
+    if (c->tile_cap < std::min<int64_t>(tri, 16ll << 20)) c->tile_cap = std::min<int64_t>(tri, 16ll << 20);
     // no_cb: every ratio passes a bound of -inf, so each row's range is (i, n-1] minus the e==0 columns
     const double tau_cb = prm->no_cb ? -__builtin_huge_val() : tau;
     k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau_cb,
                                                 c->lo.as<int32_t>(), c->hi.as<int32_t>());
     CK(cudaGetLastError());
-    st.launches++;
-    c->h_lo.resize((size_t)n); c->h_hi.resize((size_t)n);
-    CK(cudaMemcpyAsync(c->h_lo.data(), c->lo.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c->h_hi.data(), c->hi.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    cudaEvent_t ev_bounds = c->ev();
-    CK(cudaStreamSynchronize(s));
-
-    // ---- tile list (host, O(n)) --------------------------------------------------
-    const int nrb = (n + TILE - 1) / TILE;
-    std::vector<int32_t> tprefix((size_t)nrb + 1, 0), tcb0((size_t)nrb, 0);
-    std::vector<int64_t> rb_pairs((size_t)nrb, 0);
-    int64_t pairs_cb = 0;
-    for (int rb = 0; rb < nrb; ++rb) {
-        int cmin = INT32_MAX, cmax = -1;
-        int64_t cnt = 0;
-        const int r1 = std::min(n, (rb + 1) * TILE);
-        for (int i = rb * TILE; i < r1; ++i) {
-            const int l = c->h_lo[(size_t)i], h = c->h_hi[(size_t)i];
-            if (h < l) continue;
-            cnt += h - l + 1;
-            cmin = std::min(cmin, l);
-            cmax = std::max(cmax, h);
-        }
-        int nt = 0;
-        if (cnt) { tcb0[(size_t)rb] = cmin / TILE; nt = cmax / TILE - cmin / TILE + 1; }
-        rb_pairs[(size_t)rb] = cnt;
-        pairs_cb += cnt;
-        tprefix[(size_t)rb + 1] = tprefix[(size_t)rb] + nt;
+    k_rowblock_span<<<(nrb + 1 + 3) / 4, 128, 0, s>>>(c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, nrb,
+                                                      c->tile_nt.as<int32_t>(), c->tile_cb0.as<int32_t>(),
+                                                      c->rb_pairs.as<unsigned long long>(), d_cnt);
+    CK(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->tile_nt.as<int32_t>(), c->tile_prefix.as<int32_t>(),
+                                         nrb + 1, s));
+        CKR(c->cub_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->tile_nt.as<int32_t>(),
+                                         c->tile_prefix.as<int32_t>(), nrb + 1, s));
     }
-    const int tiles_total = tprefix[(size_t)nrb];
-    st.pairs_cb = pairs_cb;
-    st.tiles_total = tiles_total;
-    // shard s owns tiles s, s+S, s+2S, ... : dealing the row-major tile list round-robin gives every
-    // shard the same mix of band positions, hence nearly equal survivor counts (contiguous slices
-    // measured 1.6x imbalance in the union pass at 8 shards).  Ranges below index j, tile = s + j*S.
-    const int t_begin = 0;
-    const int t_end = tiles_total > prm->shard ? (tiles_total - prm->shard + n_shards - 1) / n_shards : 0;
-    st.tiles_shard = t_end - t_begin;
-    CKR(upload(c->tile_prefix, tprefix, s));
-    CKR(upload(c->tile_cb0, tcb0, s));
-    CKR(c->tile_rc.ensure((size_t)std::max(tiles_total, 1) * sizeof(int2)));
-    if (tiles_total > 0) {
-        k_tile_table<<<(tiles_total + 255) / 256, 256, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(),
-                                                               nrb, tiles_total, c->tile_rc.as<int2>());
-        CK(cudaGetLastError());
-        st.launches++;
-    }
-
-    // counters: [0] candidates, [1] pairs, [2] out, [3] near
-    CKR(c->counters.ensure(64));
-    CK(cudaMemsetAsync(c->counters.p, 0, 64, s));
-    unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+    st.launches += 3;
+    cudaEvent_t ev_bounds = nullptr;
 
     // ---- K3: signatures ---------------------------------------------------------------
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_filter, t_verify, t_union, t_est;
-    if (crit == SELB200_CRIT_SMH_A && smh_shape_ok) {
-        cudaEvent_t a = c->ev();
-        const int n_words = (n_bands + 1) / 2;
-        const size_t sig_bytes = (size_t)n_words * c->npad * 4;
-        CKR(c->sigT.ensure(2 * sig_bytes));
-        // pad genomes: row halves 0, column halves 1 -> never match
-        CK(cudaMemsetAsync(c->sigT.p, 0, sig_bytes, s));
-        CK(cudaMemsetAsync(c->sigT.as<uint8_t>() + sig_bytes, 0x01, sig_bytes, s));
-        const int grid = (int)std::min<int64_t>(((int64_t)n * n_words + 255) / 256, (int64_t)c->sm_count * 16);
-        k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
-                                              c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
-        CK(cudaGetLastError());
-        st.launches++;
-        t_filter.push_back({a, c->ev()});
-    }
+    const int n_words = (n_bands + 1) / 2;
+    const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
@@ -1370,6 +1533,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const unsigned long long near_cap = 1ull << 16;
     const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
     size_t hll_smem = 0;
+    int hll_grid = 0;
     if (crit >= SELB200_CRIT_HLL_A) {
         hll_smem = (size_t)2 * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
         static bool carve = false;
@@ -1378,63 +1542,142 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             cudaFuncSetAttribute(k_tile_filter_hll<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carve = true;
         }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+        hll_grid = c->sm_count * per_sm;
     }
+    static const int smh_grid_per_sm = [] {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_smh, 256, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = FILTER_CTAS_PER_SM;
+        }
+        return per_sm;
+    }();
 
     // ---- filter -> union passes over tile ranges ---------------------------------------
-    // Optimistic, sync-free pipeline: every kernel after the filter reads its work count from
+    // Optimistic, sync-free pipeline: the tile list, its length and every later work count live in
     // device memory (persistent grids), list capacities are fixed up front, and the counters of
-    // each range are snapshotted into pinned host memory.  One synchronisation at the end checks
+    // each range are snapshotted into pinned host memory.  ONE synchronisation at the end checks
     // the snapshots; an overflow (rare: a filter far less selective than the capacities assume)
     // grows the buffers / halves the offending range and the whole pass is redone.
-    std::vector<std::pair<int, int>> ranges;   // [a,b) tile ranges, in order
-    if (smh_shape_ok && t_end > t_begin) {
-        // CB-only fills whole tiles, so its ranges are cut to what the pair list is sure to hold
-        const int step = (crit == SELB200_CRIT_CB) ? (int)(PAIR_CAP / (TILE * TILE)) : (t_end - t_begin);
-        for (int a = t_begin; a < t_end; a += step) ranges.push_back({a, std::min(t_end, a + step)});
-    }
+    // Ranges index j: the shard's j-th tile is tile shard + j*n_shards of the row-major list — dealing
+    // tiles round-robin gives every shard the same mix of band positions (contiguous slices measured
+    // 1.6x imbalance in the union pass at 8 shards).  {0, INT32_MAX} = "all of them".
+    std::vector<std::pair<int, int>> ranges;
     if (crit == SELB200_CRIT_CB) c->hist_cap_pairs = PAIR_CAP;
     if (c->hist_cap_pairs < (1ll << 20)) c->hist_cap_pairs = 1ll << 20;
     if (c->out_cap < (1ll << 21)) c->out_cap = 1ll << 21;
-    if (!c->h_snap) CK(cudaMallocHost(&c->h_snap, SNAP_MAX * 4 * sizeof(unsigned long long)));
-    unsigned long long h_fin[4] = {0, 0, 0, 0};
+    if (!c->h_snap) CK(cudaMallocHost(&c->h_snap, (SNAP_MAX * 4 + M_WORDS) * sizeof(unsigned long long)));
+    unsigned long long* h_fin = c->h_snap + SNAP_MAX * 4;     // the final meta[] block
+    std::memset(h_fin, 0, M_WORDS * sizeof(unsigned long long));
+    c->h_tprefix.resize((size_t)nrb + 1);
+    c->h_rb_pairs.resize((size_t)nrb);
+    const int launches_fixed = st.launches;
+    GatherZone gz{};
+    if (gather) {
+        uint8_t* zb = (uint8_t*)c->g.zone;
+        gz.hdr = (GatherHdr*)zb;
+        gz.cap = (unsigned long long)c->g.cap;
+        gz.near_cap = (unsigned long long)c->g.near_cap;
+        gz.keys = (uint64_t*)(zb + sizeof(GatherHdr));
+        gz.jac = (double*)(gz.keys + 2 * gz.cap);
+        gz.near_keys = (uint64_t*)(gz.jac + 2 * gz.cap);
+        gz.near_j = (double*)(gz.near_keys + 2 * gz.near_cap);
+        CKR(c->g_push.ensure(sizeof(GatherPush)));
+        CKR(c->g_merged.ensure(32));
+    }
+    auto launch_push = [&](int check, unsigned long long pair_lim) -> int {
+        k_gather_claim<<<1, 32, 0, s>>>(gz, c->g.epoch, d_cnt, check, (unsigned long long)PAIR_CAP, pair_lim,
+                                        (unsigned long long)c->out_cap, (unsigned long long)c->tile_cap, near_cap,
+                                        c->g_push.as<GatherPush>());
+        CK(cudaGetLastError());
+        k_gather_copy<<<32, 256, 0, s>>>(gz, c->g.epoch, d_cnt, near_cap, c->out_keys.as<uint64_t>(),
+                                         c->out_j.as<double>(), c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                                         c->g_push.as<GatherPush>());
+        CK(cudaGetLastError());
+        st.launches += 2;
+        return SELB200_OK;
+    };
+    int64_t tiles_total = -1;      // host copy of meta[M_TILES] once known
+    auto shard_tiles = [&](int64_t total) -> int {
+        return total > prm->shard ? (int)((total - prm->shard + n_shards - 1) / n_shards) : 0;
+    };
+    bool pushed = false;
     for (int attempt = 0;; ++attempt) {
         if (attempt > 40) return fail(SELB200_ENOMEM, "candidate lists keep overflowing");
-        if ((int)ranges.size() > SNAP_MAX) return fail(SELB200_ENOMEM, "too many tile ranges (%zu)", ranges.size());
+        CKR(c->tile_rc.ensure((size_t)std::max<int64_t>(c->tile_cap, 1) * sizeof(int2)));
         CKR(c->hist.ensure((size_t)c->hist_cap_pairs * 64 * sizeof(uint32_t)));
         CKR(c->out_keys.ensure((size_t)c->out_cap * 8));
         CKR(c->out_j.ensure((size_t)c->out_cap * 8));
+        st.launches = launches_fixed;
+        k_tile_table<<<(nrb + 3) / 4, 128, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
+                                                   (long long)c->tile_cap, c->tile_rc.as<int2>(), d_cnt);
+        CK(cudaGetLastError());
+        st.launches++;
+        if (!ev_bounds) ev_bounds = c->ev();
+        if (ranges.empty()) {
+            if (crit == SELB200_CRIT_CB) {
+                // CB-only fills whole tiles: its ranges are cut on the host to what the pair list is sure to hold
+                CK(cudaMemcpyAsync(h_fin + M_TILES, d_cnt + M_TILES, 8, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                tiles_total = (int64_t)h_fin[M_TILES];
+                const int t_end = shard_tiles(std::min<int64_t>(tiles_total, c->tile_cap));
+                const int step = (int)(PAIR_CAP / (TILE * TILE));
+                for (int a0 = 0; a0 < t_end; a0 += step) ranges.push_back({a0, std::min(t_end, a0 + step)});
+            } else if (smh_shape_ok) {
+                ranges.push_back({0, INT32_MAX});
+            }
+        }
+        if ((int)ranges.size() > SNAP_MAX) return fail(SELB200_ENOMEM, "too many tile ranges (%zu)", ranges.size());
+        t_filter.clear(); t_verify.clear(); t_union.clear(); t_est.clear();
+        if (use_smh) {
+            cudaEvent_t a0 = c->ev();
+            const size_t sig_bytes = (size_t)n_words * c->npad * 4;
+            CKR(c->sigT.ensure(2 * sig_bytes));
+            // pad genomes: row halves 0, column halves 1 -> never match
+            CK(cudaMemsetAsync(c->sigT.p, 0, sig_bytes, s));
+            CK(cudaMemsetAsync(c->sigT.as<uint8_t>() + sig_bytes, 0x01, sig_bytes, s));
+            const int grid = (int)std::min<int64_t>(((int64_t)n * n_words + 255) / 256, (int64_t)c->sm_count * 16);
+            k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
+                                                  c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
+            CK(cudaGetLastError());
+            st.launches++;
+            t_filter.push_back({a0, c->ev()});
+        }
         CK(cudaMemsetAsync(d_cnt, 0, 32, s));
-        t_filter.resize(crit == SELB200_CRIT_SMH_A && smh_shape_ok ? 1 : 0);   // keep the signature pass
-        t_verify.clear(); t_union.clear(); t_est.clear();
+        CK(cudaMemsetAsync(d_cnt + M_PUSHED, 0, 8, s));
         const unsigned long long pair_lim = (unsigned long long)std::min<int64_t>(PAIR_CAP, c->hist_cap_pairs);
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
             const std::pair<int, int> rg = ranges[ri];
-            const int nt = rg.second - rg.first;
+            const int64_t nt = (int64_t)rg.second - rg.first;     // upper bound when the end is open
+            const TileWalk tw{c->tile_rc.as<int2>(), d_cnt, (long long)c->tile_cap, prm->shard, n_shards, rg.first, rg.second};
             CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs of this range
             cudaEvent_t f0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) {
-                const int n_words = (n_bands + 1) / 2;
-                k_tile_filter_smh<<<nt, 256, 0, s>>>(
-                    c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words,
-                    c->tile_rc.as<int2>(), prm->shard + rg.first * n_shards, n_shards,
-                    c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP);
+                const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
+                k_tile_filter_smh<<<grid, 256, 0, s>>>(
+                    c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words, tw,
+                    c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->cand.as<uint2>(), d_cnt + M_CAND,
+                    (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_CB) {
-                k_tile_enum<<<nt, 256, 0, s>>>(c->tile_rc.as<int2>(),
-                                               prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
-                                               d_cnt + 1, (unsigned long long)PAIR_CAP);
+                const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
+                k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
+                                                 d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
             } else if (crit == SELB200_CRIT_HLL_A) {
-                k_tile_filter_hll<0><<<nt * 4, 64, hll_smem, s>>>(
-                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_rc.as<int2>(),
-                    prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
-                    c->hi.as<int32_t>(), n,
-                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
+                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
+                k_tile_filter_hll<0><<<grid, 64, hll_smem, s>>>(
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
                     (unsigned long long)PAIR_CAP);
             } else {
-                k_tile_filter_hll<1><<<nt * 4, 64, hll_smem, s>>>(
-                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, c->tile_rc.as<int2>(),
-                    prm->shard + rg.first * n_shards, n_shards, c->lo.as<int32_t>(),
-                    c->hi.as<int32_t>(), n,
-                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + 1,
+                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
+                k_tile_filter_hll<1><<<grid, 64, hll_smem, s>>>(
+                    c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
+                    c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
                     (unsigned long long)PAIR_CAP);
             }
             CK(cudaGetLastError());
@@ -1444,8 +1687,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             if (crit == SELB200_CRIT_SMH_A) {
                 k_smh_verify<<<c->sm_count * 8, 256, 0, s>>>(
                     c->aux_sorted.as<uint64_t>(), c->sigT.as<uint32_t>(), c->npad, c->aux_len, n_rows, n_bands,
-                    c->cand.as<uint2>(), d_cnt + 0, (unsigned long long)PAIR_CAP, c->pairs.as<uint2>(), d_cnt + 1,
-                    (unsigned long long)PAIR_CAP);
+                    c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, c->pairs.as<uint2>(),
+                    d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
                 CK(cudaGetLastError());
                 st.launches++;
             }
@@ -1453,14 +1696,14 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             cudaEvent_t u0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) t_verify.push_back({f1, u0});
             CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
-                                 (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + 1));
+                                 (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
             st.launches++;
             cudaEvent_t u1 = c->ev();
             k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
-                c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + 1, pair_lim,
+                c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
                 c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
-                d_cnt + 2, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
-                d_cnt + 3, near_cap);
+                d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                d_cnt + M_NEAR, near_cap);
             CK(cudaGetLastError());
             st.launches++;
             cudaEvent_t u2 = c->ev();
@@ -1468,63 +1711,143 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             t_est.push_back({u1, u2});
             CK(cudaMemcpyAsync(c->h_snap + ri * 4, d_cnt, 32, cudaMemcpyDeviceToHost, s));
         }
+        // gather, optimistic form: the push is queued behind the only range and checks on the device
+        // that nothing overflowed; the root's wait follows, so its single sync also covers the peers
+        if (gather && ranges.size() <= 1) {
+            CKR(launch_push(1, pair_lim));
+            if (c->g.is_root) {
+                k_gather_wait<<<1, 32, 0, s>>>(gz, c->g.epoch, (unsigned)c->g.world, c->g_push.as<GatherPush>(),
+                                               c->g_merged.as<unsigned long long>());
+                CK(cudaGetLastError());
+                st.launches++;
+                CK(cudaMemcpyAsync(c->g.h_merged, c->g_merged.p, 24, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        CK(cudaMemcpyAsync(h_fin, d_cnt, M_WORDS * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_tprefix.data(), c->tile_prefix.p, ((size_t)nrb + 1) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c->h_rb_pairs.data(), c->rb_pairs.p, (size_t)nrb * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         // ---- overflow check ------------------------------------------------------------------
+        tiles_total = (int64_t)h_fin[M_TILES];
+        pushed = h_fin[M_PUSHED] == 1;
+        if (h_fin[M_PUSHED] == 2) return fail(SELB200_ECUDA, "gather: timed out waiting for the root to merge an earlier run");
         bool redo = false;
+        if (tiles_total > c->tile_cap) {
+            c->tile_cap = tiles_total;
+            ranges.clear();           // built again against the full list
+            redo = true;
+        }
         std::vector<std::pair<int, int>> next;
         int64_t cand_sum = 0, pair_sum = 0;
+        const int t_end = shard_tiles(tiles_total);
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
             const unsigned long long* sn = c->h_snap + ri * 4;
+            const int ra = ranges[ri].first, rb = std::min(ranges[ri].second, t_end);
             const bool too_many = sn[0] > (unsigned long long)PAIR_CAP || sn[1] > (unsigned long long)PAIR_CAP;
             if (too_many) {
-                const int nt = ranges[ri].second - ranges[ri].first;
-                if (nt == 1) return fail(SELB200_ENOMEM, "a single tile produced %llu pairs", std::max(sn[0], sn[1]));
-                const int mid = ranges[ri].first + nt / 2;
-                next.push_back({ranges[ri].first, mid});
-                next.push_back({mid, ranges[ri].second});
+                const int nt = rb - ra;
+                if (nt <= 1) return fail(SELB200_ENOMEM, "a single tile produced %llu pairs", std::max(sn[0], sn[1]));
+                const int mid = ra + nt / 2;
+                next.push_back({ra, mid});
+                next.push_back({mid, rb});
                 redo = true;
                 continue;
             }
-            next.push_back(ranges[ri]);
+            next.push_back({ra, rb});
             if ((int64_t)sn[1] > c->hist_cap_pairs) { c->hist_cap_pairs = (int64_t)sn[1]; redo = true; }
             cand_sum += crit == SELB200_CRIT_SMH_A ? (int64_t)sn[0] : (int64_t)sn[1];
             pair_sum += (int64_t)sn[1];
         }
-        if (!ranges.empty()) std::memcpy(h_fin, c->h_snap + (ranges.size() - 1) * 4, 32);
-        if ((int64_t)h_fin[2] > c->out_cap) { c->out_cap = (int64_t)h_fin[2] + (1 << 16); redo = true; }
+        if ((int64_t)h_fin[M_OUT] > c->out_cap) { c->out_cap = (int64_t)h_fin[M_OUT] + (1 << 16); redo = true; }
         if (!redo) {
             st.pairs_cand = cand_sum;
             st.pairs_aux = pair_sum;
             st.batches = (int32_t)ranges.size();
             break;
         }
-        ranges.swap(next);
-        st.launches = 1 + (crit == SELB200_CRIT_SMH_A ? 1 : 0);
+        if (pushed) return fail(SELB200_ECUDA, "internal: gather pushed a pass that overflowed");
+        if (!ranges.empty()) ranges.swap(next);
     }
-    c->out_count = (int64_t)h_fin[2];
-    c->near_count = (int64_t)std::min<unsigned long long>(h_fin[3], near_cap);
+    st.pairs_cb = (int64_t)h_fin[M_PAIRS_CB];
+    st.tiles_total = tiles_total;
+    st.tiles_shard = shard_tiles(tiles_total);
+    c->out_count = (int64_t)h_fin[M_OUT];
+    c->near_count = (int64_t)std::min<unsigned long long>(h_fin[M_NEAR], near_cap);
     st.pairs_out = c->out_count;
-    st.pairs_near = (int64_t)h_fin[3];
+    st.pairs_near = (int64_t)h_fin[M_NEAR];
+
+    // ---- gather, second half ----------------------------------------------------------------
+    const uint64_t* src_keys = c->out_keys.as<uint64_t>();
+    const double* src_j = c->out_j.as<double>();
+    if (gather) {
+        if (!pushed) {           // several ranges (or a redone pass): push now that the pass is final
+            CKR(launch_push(0, 0));
+            if (c->g.is_root) {
+                k_gather_wait<<<1, 32, 0, s>>>(gz, c->g.epoch, (unsigned)c->g.world, c->g_push.as<GatherPush>(),
+                                               c->g_merged.as<unsigned long long>());
+                CK(cudaGetLastError());
+                st.launches++;
+                CK(cudaMemcpyAsync(c->g.h_merged, c->g_merged.p, 24, cudaMemcpyDeviceToHost, s));
+            }
+            CK(cudaMemcpyAsync(h_fin + M_PUSHED, d_cnt + M_PUSHED, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (h_fin[M_PUSHED] != 1) return fail(SELB200_ECUDA, "gather: timed out waiting for the root to merge an earlier run");
+        }
+        const unsigned b = c->g.epoch & 1u;
+        if (c->g.is_root) {
+            if (c->g.h_merged[2]) return fail(SELB200_ECUDA, "gather: timed out waiting for %d ranks to push their lists", c->g.world);
+            if ((int64_t)c->g.h_merged[0] > c->g.cap)
+                return fail(SELB200_ENOMEM, "gather: %llu pairs exceed the landing zone of %lld (selb200_gather_create)",
+                            c->g.h_merged[0], (long long)c->g.cap);
+            c->out_count = (int64_t)c->g.h_merged[0];
+            c->near_count = (int64_t)std::min<unsigned long long>(c->g.h_merged[1], gz.near_cap);
+            src_keys = gz.keys + b * gz.cap;
+            src_j = gz.jac + b * gz.cap;
+            // the merged near-tau list moves to the context's own buffers (the zone is handed back below)
+            if (c->near_count) {
+                CKR(c->near_keys.ensure((size_t)gz.near_cap * 8));
+                CKR(c->near_j.ensure((size_t)gz.near_cap * 8));
+                CK(cudaMemcpyAsync(c->near_keys.p, gz.near_keys + b * gz.near_cap, (size_t)c->near_count * 8, cudaMemcpyDeviceToDevice, s));
+                CK(cudaMemcpyAsync(c->near_j.p, gz.near_j + b * gz.near_cap, (size_t)c->near_count * 8, cudaMemcpyDeviceToDevice, s));
+            }
+        } else {
+            c->out_count = 0;     // this rank's pairs now live on the root
+            c->near_count = 0;
+        }
+    }
 
     // ---- K7: reference print order -----------------------------------------------------------
     cudaEvent_t s0 = c->ev();
-    c->res_keys = c->out_keys.as<uint64_t>();
-    c->res_j = c->out_j.as<double>();
-    if (prm->sort_output && c->out_count > 1) {
+    c->res_keys = src_keys;
+    c->res_j = src_j;
+    const bool must_copy = gather && c->g.is_root;    // results leave the landing zone either way
+    if ((prm->sort_output || must_copy) && c->out_count > 0) {
         const int64_t cnt = c->out_count;
         CKR(c->out_keys2.ensure((size_t)cnt * 8));
         CKR(c->out_j2.ensure((size_t)cnt * 8));
-        size_t tmp_bytes = 0;
-        int nbits = 1;
-        while ((1ll << nbits) < (long long)n) ++nbits;       // key = i<<32 | k with i,k < n
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c->out_keys.as<uint64_t>(), c->out_keys2.as<uint64_t>(),
-                                           c->out_j.as<double>(), c->out_j2.as<double>(), (int)cnt, 0, 32 + nbits, s));
-        CKR(c->cub_tmp.ensure(tmp_bytes));
-        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, c->out_keys.as<uint64_t>(),
-                                           c->out_keys2.as<uint64_t>(), c->out_j.as<double>(), c->out_j2.as<double>(),
-                                           (int)cnt, 0, 32 + nbits, s));
+        if (prm->sort_output && cnt > 1) {
+            size_t tmp_bytes = 0;
+            int nbits = 1;
+            while ((1ll << nbits) < (long long)n) ++nbits;       // key = i<<32 | k with i,k < n
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, src_keys, c->out_keys2.as<uint64_t>(), src_j,
+                                               c->out_j2.as<double>(), (int)cnt, 0, 32 + nbits, s));
+            CKR(c->cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, src_keys, c->out_keys2.as<uint64_t>(), src_j,
+                                               c->out_j2.as<double>(), (int)cnt, 0, 32 + nbits, s));
+        } else {
+            CK(cudaMemcpyAsync(c->out_keys2.p, src_keys, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, s));
+            CK(cudaMemcpyAsync(c->out_j2.p, src_j, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, s));
+        }
         c->res_keys = c->out_keys2.as<uint64_t>();
         c->res_j = c->out_j2.as<double>();
+    }
+    if (gather) {
+        if (c->g.is_root) {
+            k_gather_release<<<1, 32, 0, s>>>(gz, c->g.epoch);
+            CK(cudaGetLastError());
+            st.launches++;
+        }
+        c->g.epoch++;
     }
     cudaEvent_t ev_end = c->ev();
     CK(cudaStreamSynchronize(s));
@@ -1549,16 +1872,99 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     {
         double acc = 0.;
         for (int rb = 0; rb < nrb; ++rb) {
-            const int a = tprefix[(size_t)rb], b = tprefix[(size_t)rb + 1];
+            const int a = c->h_tprefix[(size_t)rb], b = c->h_tprefix[(size_t)rb + 1];
             if (b <= a) continue;
             // tiles t in [a,b) with t % n_shards == shard
             const int first = a + ((prm->shard - a % n_shards) % n_shards + n_shards) % n_shards;
             const int mine = first < b ? (b - 1 - first) / n_shards + 1 : 0;
-            acc += (double)rb_pairs[(size_t)rb] * (double)mine / (double)(b - a);
+            acc += (double)c->h_rb_pairs[(size_t)rb] * (double)mine / (double)(b - a);
         }
         st.pairs_cb_shard = (int64_t)(acc + 0.5);
     }
     if (st_out) *st_out = st;
+    return SELB200_OK;
+}
+
+// ---- peer-memory gather ------------------------------------------------------------------
+namespace {
+struct GatherHandle {            // what selb200_gather_create exports (SELB200_GATHER_HANDLE_BYTES)
+    cudaIpcMemHandle_t ipc;      // 64 bytes
+    int64_t cap, near_cap;
+    int64_t pid;
+    uint64_t raw;                // the pointer itself: used when root and peer share a process
+    int32_t device, pad;
+};
+static_assert(sizeof(GatherHandle) <= SELB200_GATHER_HANDLE_BYTES, "handle blob too small");
+
+size_t gather_zone_bytes(int64_t cap, int64_t near_cap) {
+    return sizeof(GatherHdr) + (size_t)cap * 32 + (size_t)near_cap * 32;
+}
+}  // namespace
+
+void selb200_gather_close(selb200_ctx* c) {
+    if (!c || !c->g.zone) { if (c) c->g = selb200_ctx::Gather(); return; }
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->g.mapped) cudaIpcCloseMemHandle(c->g.zone);
+    else if (c->g.is_root) cudaFree(c->g.zone);
+    if (c->g.h_merged) cudaFreeHost(c->g.h_merged);
+    c->g = selb200_ctx::Gather();
+}
+
+int selb200_gather_create(selb200_ctx* c, int64_t cap_pairs, void* handle_out) {
+    if (!c || !handle_out) return fail(SELB200_EINVAL, "null argument");
+    if (cap_pairs < 1) return fail(SELB200_EINVAL, "gather capacity %lld", (long long)cap_pairs);
+    selb200_gather_close(c);
+    CK(cudaSetDevice(c->device));
+    const int64_t near_cap = 1 << 16;
+    void* zone = nullptr;
+    if (cudaMalloc(&zone, gather_zone_bytes(cap_pairs, near_cap)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SELB200_ENOMEM, "cudaMalloc of the %zu-byte landing zone failed", gather_zone_bytes(cap_pairs, near_cap));
+    }
+    CK(cudaMemset(zone, 0, sizeof(GatherHdr)));
+    GatherHandle h;
+    std::memset(&h, 0, sizeof h);
+    CK(cudaIpcGetMemHandle(&h.ipc, zone));
+    h.cap = cap_pairs; h.near_cap = near_cap; h.pid = (int64_t)getpid(); h.raw = (uint64_t)(uintptr_t)zone;
+    h.device = c->device;
+    std::memset(handle_out, 0, SELB200_GATHER_HANDLE_BYTES);
+    std::memcpy(handle_out, &h, sizeof h);
+    c->g.zone = zone; c->g.is_root = true; c->g.cap = cap_pairs; c->g.near_cap = near_cap;
+    return SELB200_OK;
+}
+
+int selb200_gather_attach(selb200_ctx* c, int rank, int world, const void* root_handle) {
+    if (!c || !root_handle) return fail(SELB200_EINVAL, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(SELB200_EINVAL, "rank %d of %d", rank, world);
+    CK(cudaSetDevice(c->device));
+    GatherHandle h;
+    std::memcpy(&h, root_handle, sizeof h);
+    if (c->g.is_root && c->g.zone) {
+        if ((uint64_t)(uintptr_t)c->g.zone != h.raw || h.pid != (int64_t)getpid())
+            return fail(SELB200_EINVAL, "gather_attach on the root needs the handle it created");
+    } else {
+        selb200_gather_close(c);
+        if (h.pid == (int64_t)getpid()) {
+            // same process (several contexts in one host program): the pointer itself is valid here
+            if (h.device != c->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(SELB200_ECUDA, "no peer access from device %d to %d: %s", c->device, h.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            c->g.zone = (void*)(uintptr_t)h.raw;
+        } else {
+            void* zone = nullptr;
+            CK(cudaIpcOpenMemHandle(&zone, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            c->g.zone = zone;
+            c->g.mapped = true;
+        }
+        c->g.cap = h.cap; c->g.near_cap = h.near_cap;
+    }
+    if (!c->g.h_merged) CK(cudaMallocHost(&c->g.h_merged, 32));
+    c->g.rank = rank; c->g.world = world; c->g.epoch = 0;
+    c->g.attached = true;
     return SELB200_OK;
 }
 

@@ -1,11 +1,14 @@
 """Multi-GPU sharding of the pair triangle: one process per GPU, torch.distributed for the plumbing.
 
 The path shards by construction (pairs are independent): every rank holds the full sorted
-sketch matrices (1.64 GB + 0.1 GB at n=100k, broadcast from rank 0 over NCCL/NVLink), runs the
-contiguous slice [T·r/R, T·(r+1)/R) of the CB-band tile list, and the variable-length pair lists
-are gathered on rank 0 (one all_gather of the counts, one padded gather of keys and Jaccards).
-There is no collective inside the compare kernels — the only exchange steps are the sketch
-broadcast in and the list gather out.  Works with backend "nccl" (CUDA tensors)
+sketch matrices (1.64 GB + 0.1 GB at n=100k; broadcast from rank 0 over NCCL/NVLink, or all-gathered
+from per-rank host slices: ShardedSketches), runs tiles r, r+R, r+2R, ... of the CB-band tile list,
+and the variable-length pair lists meet on rank 0.  The product path for that last step is the
+library's own peer-memory gather (setup_gather + Selection.run(gather=True): kernels store into
+the root GPU's memory over NVLink, no collective call); gather_lists is the NCCL/gloo
+restatement of the same exchange, kept as its checker and for CPU tests.  There is no collective
+inside the compare kernels — the only exchange steps are the sketches in and the lists out
+(SURVEY.md §8e).  Works with backend "nccl" (CUDA tensors)
 and "gloo" (CPU tensors; used by the world_size-2 CPU tests of this plumbing).
 """
 from __future__ import annotations
@@ -39,6 +42,53 @@ def broadcast_sketches(regs: torch.Tensor, aux: torch.Tensor | None, src: int = 
     dist.broadcast(regs, src=src)
     if aux is not None:
         dist.broadcast(aux, src=src)
+
+
+def slice_rows(n: int, rank: int, world: int) -> tuple[int, int, int]:
+    """(first row, row count, rows per slice) of `rank`'s contiguous slice of n genomes in file-list order."""
+    per = (n + world - 1) // world
+    g0 = min(n, rank * per)
+    return g0, min(n, g0 + per) - g0, per
+
+
+class ShardedSketches:
+    """Device-resident sketch matrices assembled from per-rank HOST slices.
+
+    Every rank owns rows [r*per, (r+1)*per) of the file list in (pinned) host memory — the natural
+    state after each rank has decoded its share of the sketch files.  `assemble` copies the slice to
+    the rank's GPU over its own PCIe link and all-gathers the slices over NCCL/NVLink (in place:
+    each rank's slice already sits at its offset of the full matrix), so the host->device leg of an
+    R-rank job runs on R links at once instead of through rank 0 (broadcast_sketches)."""
+
+    def __init__(self, n: int, m: int, aux_cols: int, aux_dtype, device, rank: int, world: int):
+        self.n, self.rank, self.world = n, rank, world
+        self.g0, self.rows, self.per = slice_rows(n, rank, world)
+        self.regs = torch.empty((self.per * world, m), dtype=torch.uint8, device=device)
+        self.aux = torch.empty((self.per * world, aux_cols), dtype=aux_dtype, device=device) if aux_cols else None
+
+    def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None):
+        lo = self.rank * self.per
+        mine = self.regs[lo:lo + self.per]
+        mine[:self.rows].copy_(regs_host, non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.regs, mine)
+        if self.aux is not None:
+            mine_a = self.aux[lo:lo + self.per]
+            mine_a[:self.rows].copy_(aux_host, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.aux, mine_a)
+        return self.regs[:self.n], (self.aux[:self.n] if self.aux is not None else None)
+
+
+def setup_gather(sel, cap_pairs: int = 1 << 22, root: int = 0):
+    """Create the root's landing zone and attach every rank's context to it (Selection.gather_*).
+    The handle travels through the process group's object broadcast (any backend)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [sel.gather_create(cap_pairs) if rank == root else None]
+    dist.broadcast_object_list(box, src=root)
+    sel.gather_attach(rank, world, box[0])
+    dist.barrier()
+    return sel
 
 
 def gather_lists(keys: torch.Tensor, jac: torch.Tensor, dst: int = 0):

@@ -144,10 +144,35 @@ class Selection:
         self._order = (cards, order)
         return self._order
 
+    # -- multi-GPU gather over peer memory ----------------------------------------------------
+    def gather_create(self, cap_pairs: int = 1 << 22) -> bytes:
+        """Root rank: allocate the landing zone for the merged pair list, return the handle to hand to
+        every rank's gather_attach (see include/selb200.h, selb200_gather_*)."""
+        buf = C.create_string_buffer(_lib.GATHER_HANDLE_BYTES)
+        _lib.check(self._L.selb200_gather_create(self._h, int(cap_pairs), buf))
+        return bytes(buf.raw)
+
+    def gather_attach(self, rank: int, world: int, handle: bytes):
+        if len(handle) != _lib.GATHER_HANDLE_BYTES:
+            raise ValueError("not a gather handle")
+        _lib.check(self._L.selb200_gather_attach(self._h, int(rank), int(world), C.c_char_p(handle)))
+        self._gather = (rank, world)
+        return self
+
+    def gather_close(self):
+        self._L.selb200_gather_close(self._h)
+        self._gather = None
+
     # -- run ------------------------------------------------------------------------------
     def run(self, tau: float = 0.9, criterion: str | int = "smh_a", z_score: float = 1.96, order_n: int = 1,
             n_rows: int = 0, n_bands: int = 0, shard: int = 0, n_shards: int = 1, sort_output: bool = True,
-            fetch: bool = True, no_cb: bool = False) -> SelectionResult:
+            fetch: bool = True, no_cb: bool = False, gather: bool = False) -> SelectionResult:
+        """gather=True (after gather_attach): shard/n_shards are the attached rank/world, every rank
+        pushes its pairs into the root GPU's memory and the root's result is the whole job's list."""
+        if gather:
+            if getattr(self, "_gather", None) is None:
+                raise RuntimeError("run(gather=True) needs gather_attach first")
+            shard, n_shards = self._gather
         prm = _lib.Params()
         self._L.selb200_default_params(C.byref(prm))
         prm.tau = tau
@@ -158,6 +183,7 @@ class Selection:
         prm.shard, prm.n_shards = shard, n_shards
         prm.sort_output = int(sort_output)
         prm.no_cb = int(no_cb)
+        prm.gather = int(gather)
         st = _lib.Stats()
         _lib.check(self._L.selb200_run(self._h, C.byref(prm), C.byref(st)))
         cards, order = self.order()

@@ -68,7 +68,9 @@ typedef struct selb200_params {
     int32_t n_shards; /* 1 = whole pair space                                                  */
     int32_t sort_output; /* 1: order results by (i,k) like the reference prints them          */
     int32_t no_cb;    /* 1: skip the cardinality bound (the "smh_a" loop of experiments/src/time_smh.cpp:229-257; the e2==0 skip stays) */
-    int32_t reserved[6];
+    int32_t gather;   /* 1: push this shard's pairs into the root GPU's landing zone (selb200_gather_*); the
+                         root's results are then the merged list of all n_shards ranks                     */
+    int32_t reserved[5];
 } selb200_params;
 
 /* Per-run statistics (stage counts + per-kernel device times). */
@@ -159,6 +161,22 @@ int64_t selb200_near_count(selb200_ctx* ctx);
 int selb200_copy_near(selb200_ctx* ctx, int64_t cap, int32_t* i, int32_t* k, double* jaccard);
 /* Device views of the same lists for NCCL gathers: keys[c] = (uint64)i<<32 | k. */
 int selb200_result_device(selb200_ctx* ctx, const uint64_t** d_keys, const double** d_jaccard);
+
+/* ---- multi-GPU: gather of the pair lists over peer memory -------------------------------------
+ * One process per GPU on one NVLink/NVSwitch node.  The ROOT rank allocates a landing
+ * zone for `cap_pairs` pairs on its GPU and exports an opaque handle (CUDA IPC inside); every rank,
+ * the root included, attaches with its (rank, world) and that handle — how the bytes travel between
+ * the processes is the caller's business (torch.distributed, MPI, a file).  A run with
+ * params.gather = 1, shard = rank, n_shards = world then ends with each rank storing its (i,k,J) list
+ * straight into the root's memory from a kernel (plain stores over NVLink, one system-scope atomicAdd
+ * to claim a block, one to signal); the root waits on the device for all `world` signals and sorts
+ * the merged list.  On the root, selb200_result_count / copy_results / copy_near then describe the
+ * WHOLE job; on the other ranks they are empty.  All ranks must issue the same sequence of gather
+ * runs.  Replaces the cudaMemcpy of `out_count` + `Result[]` of src/selection_cuda.cpp:177-180. */
+#define SELB200_GATHER_HANDLE_BYTES 128
+int selb200_gather_create(selb200_ctx* ctx, int64_t cap_pairs, void* handle_out);
+int selb200_gather_attach(selb200_ctx* ctx, int rank, int world, const void* root_handle);
+void selb200_gather_close(selb200_ctx* ctx);
 
 /* ---- host helpers (no device needed) -------------------------------------- */
 /* LSH band search.  cpu_variant=1: src/selection.cpp:258-267 (falls through to (m,1));

@@ -132,6 +132,14 @@ regs = torch.full((8, 16), rank + 1, dtype=torch.uint8)
 aux = torch.full((8, 4), rank + 7, dtype=torch.int64)
 sdist.broadcast_sketches(regs, aux, src=0)
 assert int(regs.sum()) == 8 * 16 and int(aux.sum()) == 8 * 4 * 7
+# per-rank host slices -> full matrices on every rank (all-gather in place), ragged last slice
+n = 11
+full = torch.arange(n * 16, dtype=torch.int64).reshape(n, 16)
+g0, rows, per = sdist.slice_rows(n, rank, world)
+assert sum(sdist.slice_rows(n, r, world)[1] for r in range(world)) == n
+sh = sdist.ShardedSketches(n, 16, 4, torch.int64, "cpu", rank, world)
+r_all, a_all = sh.assemble(full[g0:g0 + rows].to(torch.uint8), full[g0:g0 + rows, :4].contiguous())
+assert torch.equal(r_all, full.to(torch.uint8)) and torch.equal(a_all, full[:, :4])
 # shard ranges tile the list exactly
 T = 1001
 tiles = sorted(t for r in range(world) for t in sdist.shard_tiles(T, r, world))
