@@ -297,19 +297,13 @@ def main():
     if world > 1:
         sdist.setup_gather(sel)        # rank 0's landing zone, mapped into every rank (CUDA IPC)
 
-    def fetch_lists(s_):
-        """rank 0: D2H of the (merged) pair list — inside the metric."""
-        kp, jp, cnt = s_.result_device_ptrs()
-        hk = sdist.device_tensor(kp, cnt, "<i8", local).cpu()
-        hj = sdist.device_tensor(jp, cnt, "<f8", local).cpu()
-        return hk.numel() + 0 * hj.numel()
-
     def step_resident():
         # with several ranks every rank's kernels store its pairs into rank 0's memory over NVLink
-        # (peer-memory gather inside selb200_run); rank 0 sorts the merged list
+        # (peer-memory gather inside selb200_run); rank 0 sorts the merged list and its run ends with the
+        # D2H of that list into pinned host memory — inside the metric
         res = sel.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
-                      gather=(world > 1))
-        return res.stats, (fetch_lists(sel) if rank == 0 else 0)
+                      gather=(world > 1), host_results=(rank == 0))
+        return res.stats, (sel.result_host()[0].size if rank == 0 else 0)
 
     for _ in range(a.warmup):
         step_resident()
@@ -383,8 +377,9 @@ def main():
             else:
                 r_all, a_all = sh.assemble(regs_h, aux_h)                # H2D of the slice + NCCL all-gather
                 sel2.load(r_all, a_all, aux_kind)
-            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1))
-            return fetch_lists(sel2) if rank == 0 else 0
+            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1),
+                     host_results=(rank == 0))
+            return sel2.result_host()[0].size if rank == 0 else 0
 
         e2e_steps = max(1, min(a.steps, 5))
         step_e2e()

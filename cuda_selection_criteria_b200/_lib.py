@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [
         ("tau", C.c_float), ("criterion", C.c_int32), ("z_score", C.c_float), ("order_n", C.c_int32),
         ("n_rows", C.c_int32), ("n_bands", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32),
-        ("sort_output", C.c_int32), ("no_cb", C.c_int32), ("gather", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("sort_output", C.c_int32), ("no_cb", C.c_int32), ("gather", C.c_int32), ("host_results", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -64,6 +64,7 @@ SYMBOLS = [
     ("selb200_near_count", _I64, [_VP]),
     ("selb200_copy_near", _I, [_VP, _I64, _VP, _VP, _VP]),
     ("selb200_result_device", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
+    ("selb200_result_host", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     ("selb200_gather_create", _I, [_VP, _I64, _VP]),
     ("selb200_gather_attach", _I, [_VP, _I, _I, _VP]),
     ("selb200_gather_close", None, [_VP]),

@@ -203,6 +203,10 @@ struct selb200_ctx {
         unsigned long long* h_merged = nullptr;   // pinned [4]
     } g;
     DevBuf g_push, g_merged;
+    DevBuf row_cnt, row_off, sort_tmp;
+    void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
+    size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
+    int64_t host_count = -1;
 
     cudaEvent_t ev() {
         if (ev_used == ev_pool.size()) {
@@ -862,6 +866,45 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
 }
 
 // ============================================================================
+// K7: (i,k) print order of the reference (selection.cpp:297-300) for SPARSE outputs: bucket by row
+// (count -> scan -> scatter), then every element finds its place inside its row by counting the
+// smaller columns.  Four small launches instead of the ~9 of a 49-bit radix sort; rows hold a
+// handful of pairs (cluster mates), so the quadratic in-row step is a few loads per element.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_rowsort_count(const uint64_t* __restrict__ keys, long long cnt, int32_t* __restrict__ rowcnt) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e < cnt) atomicAdd(rowcnt + (keys[e] >> 32), 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_rowsort_scatter(const uint64_t* __restrict__ keys, const double* __restrict__ jac, long long cnt,
+                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ rowoff,
+                  uint64_t* __restrict__ tkeys, double* __restrict__ tj) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= cnt) return;
+    const uint64_t key = keys[e];
+    const uint32_t i = (uint32_t)(key >> 32);
+    const int pos = rowoff[i] + atomicSub(rowcnt + i, 1) - 1;    // counts back down to zero
+    tkeys[pos] = key;
+    tj[pos] = jac[e];
+}
+
+__global__ void __launch_bounds__(256)
+k_rowsort_rank(const uint64_t* __restrict__ tkeys, const double* __restrict__ tj, long long cnt,
+               const int32_t* __restrict__ rowoff, uint64_t* __restrict__ out_keys, double* __restrict__ out_j) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= cnt) return;
+    const uint64_t key = tkeys[e];
+    const uint32_t i = (uint32_t)(key >> 32);
+    const int a = rowoff[i], b = rowoff[i + 1];
+    int r = 0;
+    for (int t = a; t < b; ++t) r += tkeys[t] < key;      // keys are unique
+    out_keys[a + r] = key;
+    out_j[a + r] = tj[e];
+}
+
+// ============================================================================
 // Peer-memory gather (multi-GPU, one process per GPU): every rank pushes its emitted (key, J)
 // list straight into the ROOT GPU's landing zone with plain stores over NVLink/NVSwitch (the zone
 // is mapped into each process with CUDA IPC).  One system-scope atomicAdd claims a contiguous
@@ -1312,10 +1355,11 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
+    if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     for (StageSlot& sl : c->slots) {
@@ -1825,7 +1869,30 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         const int64_t cnt = c->out_count;
         CKR(c->out_keys2.ensure((size_t)cnt * 8));
         CKR(c->out_j2.ensure((size_t)cnt * 8));
-        if (prm->sort_output && cnt > 1) {
+        if (prm->sort_output && cnt > 1 && cnt <= 4ll * n) {
+            // sparse output (the selective criteria): bucket by row, rank inside the row
+            CKR(c->row_cnt.ensure(((size_t)n + 1) * 4));
+            CKR(c->row_off.ensure(((size_t)n + 1) * 4));
+            CKR(c->sort_tmp.ensure((size_t)cnt * 16));
+            uint64_t* tkeys = c->sort_tmp.as<uint64_t>();
+            double* tj = reinterpret_cast<double*>(tkeys + cnt);
+            CK(cudaMemsetAsync(c->row_cnt.p, 0, ((size_t)n + 1) * 4, s));
+            const unsigned grid = (unsigned)((cnt + 255) / 256);
+            k_rowsort_count<<<grid, 256, 0, s>>>(src_keys, cnt, c->row_cnt.as<int32_t>());
+            CK(cudaGetLastError());
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(), n + 1, s));
+            CKR(c->cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
+                                             n + 1, s));
+            k_rowsort_scatter<<<grid, 256, 0, s>>>(src_keys, src_j, cnt, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
+                                                   tkeys, tj);
+            CK(cudaGetLastError());
+            k_rowsort_rank<<<grid, 256, 0, s>>>(tkeys, tj, cnt, c->row_off.as<int32_t>(), c->out_keys2.as<uint64_t>(),
+                                                c->out_j2.as<double>());
+            CK(cudaGetLastError());
+            st.launches += 4;
+        } else if (prm->sort_output && cnt > 1) {
             size_t tmp_bytes = 0;
             int nbits = 1;
             while ((1ll << nbits) < (long long)n) ++nbits;       // key = i<<32 | k with i,k < n
@@ -1840,6 +1907,23 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         }
         c->res_keys = c->out_keys2.as<uint64_t>();
         c->res_j = c->out_j2.as<double>();
+    }
+    c->host_count = -1;
+    if (prm->host_results) {
+        // the lists also land in pinned host memory before the run's last synchronisation
+        const size_t cnt = (size_t)c->out_count;
+        if (cnt > c->h_res_cap) {
+            if (c->h_res) cudaFreeHost(c->h_res);
+            c->h_res = nullptr;
+            c->h_res_cap = 0;
+            CK(cudaMallocHost(&c->h_res, (cnt + cnt / 4 + 1024) * 16));
+            c->h_res_cap = cnt + cnt / 4 + 1024;
+        }
+        if (cnt) {
+            CK(cudaMemcpyAsync(c->h_res, c->res_keys, cnt * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync((uint8_t*)c->h_res + c->h_res_cap * 8, c->res_j, cnt * 8, cudaMemcpyDeviceToHost, s));
+        }
+        c->host_count = (int64_t)cnt;
     }
     if (gather) {
         if (c->g.is_root) {
@@ -1987,8 +2071,27 @@ static int copy_list(selb200_ctx* c, const uint64_t* d_keys, const double* d_j, 
     return SELB200_OK;
 }
 
+int selb200_result_host(selb200_ctx* c, const uint64_t** keys, const double** jaccard) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    if (c->host_count < 0) return fail(SELB200_ESTATE, "the last run did not set params.host_results");
+    if (keys) *keys = (const uint64_t*)c->h_res;
+    if (jaccard) *jaccard = (const double*)((const uint8_t*)c->h_res + c->h_res_cap * 8);
+    return SELB200_OK;
+}
+
 int selb200_copy_results(selb200_ctx* c, int64_t cap, int32_t* i, int32_t* k, double* jaccard) {
     if (!c) return fail(SELB200_EINVAL, "null context");
+    if (c->host_count >= 0) {       // already on the host (params.host_results)
+        const int64_t cnt = std::min(c->host_count, cap);
+        const uint64_t* hk = (const uint64_t*)c->h_res;
+        const double* hj = (const double*)((const uint8_t*)c->h_res + c->h_res_cap * 8);
+        for (int64_t t = 0; t < cnt; ++t) {
+            if (i) i[t] = (int32_t)(hk[t] >> 32);
+            if (k) k[t] = (int32_t)(hk[t] & 0xffffffffu);
+        }
+        if (jaccard && cnt > 0) std::memcpy(jaccard, hj, (size_t)cnt * 8);
+        return SELB200_OK;
+    }
     return copy_list(c, c->res_keys, c->res_j, c->out_count, cap, i, k, jaccard);
 }
 
@@ -2024,6 +2127,7 @@ int selb200_debug_union(selb200_ctx* c, int which, int64_t count, const int32_t*
     CK(cudaMemcpyAsync(t, c->out_j.p, (size_t)count * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     c->out_count = 0;
+    c->host_count = -1;
     return SELB200_OK;
 }
 

@@ -166,7 +166,8 @@ class Selection:
     # -- run ------------------------------------------------------------------------------
     def run(self, tau: float = 0.9, criterion: str | int = "smh_a", z_score: float = 1.96, order_n: int = 1,
             n_rows: int = 0, n_bands: int = 0, shard: int = 0, n_shards: int = 1, sort_output: bool = True,
-            fetch: bool = True, no_cb: bool = False, gather: bool = False) -> SelectionResult:
+            fetch: bool = True, no_cb: bool = False, gather: bool = False,
+            host_results: bool = False) -> SelectionResult:
         """gather=True (after gather_attach): shard/n_shards are the attached rank/world, every rank
         pushes its pairs into the root GPU's memory and the root's result is the whole job's list."""
         if gather:
@@ -184,6 +185,7 @@ class Selection:
         prm.sort_output = int(sort_output)
         prm.no_cb = int(no_cb)
         prm.gather = int(gather)
+        prm.host_results = int(fetch or host_results)
         st = _lib.Stats()
         _lib.check(self._L.selb200_run(self._h, C.byref(prm), C.byref(st)))
         cards, order = self.order()
@@ -197,6 +199,18 @@ class Selection:
         ni = np.empty(nc, np.int32); nk = np.empty(nc, np.int32); nj = np.empty(nc, np.float64)
         _lib.check(self._L.selb200_copy_near(self._h, nc, ni.ctypes.data, nk.ctypes.data, nj.ctypes.data))
         return SelectionResult(i, k, j, order, cards, st.as_dict(), ni, nk, nj)
+
+    def result_host(self):
+        """(keys uint64, jaccard float64) numpy views of the library's pinned host copy of the last run's
+        lists (run(host_results=True)); valid until the next run."""
+        keys, jac = C.c_void_p(), C.c_void_p()
+        _lib.check(self._L.selb200_result_host(self._h, C.byref(keys), C.byref(jac)))
+        cnt = self._L.selb200_result_count(self._h)
+        if cnt == 0:
+            return np.zeros(0, np.uint64), np.zeros(0, np.float64)
+        k = np.ctypeslib.as_array(C.cast(keys, C.POINTER(C.c_uint64)), shape=(cnt,))
+        j = np.ctypeslib.as_array(C.cast(jac, C.POINTER(C.c_double)), shape=(cnt,))
+        return k, j
 
     def result_device_ptrs(self):
         keys, jac = C.c_void_p(), C.c_void_p()

@@ -70,7 +70,9 @@ typedef struct selb200_params {
     int32_t no_cb;    /* 1: skip the cardinality bound (the "smh_a" loop of experiments/src/time_smh.cpp:229-257; the e2==0 skip stays) */
     int32_t gather;   /* 1: push this shard's pairs into the root GPU's landing zone (selb200_gather_*); the
                          root's results are then the merged list of all n_shards ranks                     */
-    int32_t reserved[5];
+    int32_t host_results; /* 1: the result lists are also copied to pinned host memory inside the run
+                             (selb200_result_host; copy_results then needs no further device copy)     */
+    int32_t reserved[4];
 } selb200_params;
 
 /* Per-run statistics (stage counts + per-kernel device times). */
@@ -161,6 +163,8 @@ int64_t selb200_near_count(selb200_ctx* ctx);
 int selb200_copy_near(selb200_ctx* ctx, int64_t cap, int32_t* i, int32_t* k, double* jaccard);
 /* Device views of the same lists for NCCL gathers: keys[c] = (uint64)i<<32 | k. */
 int selb200_result_device(selb200_ctx* ctx, const uint64_t** d_keys, const double** d_jaccard);
+/* Pinned host views of the same lists, valid after a run with params.host_results = 1. */
+int selb200_result_host(selb200_ctx* ctx, const uint64_t** keys, const double** jaccard);
 
 /* ---- multi-GPU: gather of the pair lists over peer memory -------------------------------------
  * One process per GPU on one NVLink/NVSwitch node.  The ROOT rank allocates a landing

@@ -254,3 +254,27 @@ def test_no_cb_mode_matches_time_smh_loop(gpu):
     o = O.select(regs, 14, "smh_a", np.float32(0.8), aux=aux, no_cb=True)
     compare(r, o, 0.8)
     assert r.stats["pairs_cb"] == 700 * 699 // 2          # the empty genome sorts first, so it is never a second genome
+
+
+def test_host_results_and_both_sort_paths(gpu):
+    """params.host_results: the lists are already in pinned host memory when the run returns; sparse outputs
+    take the row-bucket sort, dense ones (more than 4 pairs per genome) the radix sort — same order."""
+    plan = synth.make_plan(1500, 77)
+    regs, aux = synth.hll(plan, 14), synth.smh(plan, 128)
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        for crit, tau in (("smh_a", 0.9), ("cb", 0.5), ("smh_a", 0.3)):
+            res = sel.run(tau=np.float32(tau), criterion=crit)
+            keys, jac = sel.result_host()
+            assert np.array_equal(keys, (res.i.astype(np.uint64) << np.uint64(32)) | res.k.astype(np.uint64))
+            assert np.array_equal(jac, res.jaccard)
+            assert np.all(np.diff(keys.astype(np.int64)) > 0)          # strictly (i,k)-ordered
+            ora = O.select(regs, 14, crit, np.float32(tau), aux=aux if crit != "cb" else None, threads=8)
+            compare(res, ora, tau)
+        dense = sel.run(tau=np.float32(0.5), criterion="cb")
+        assert dense.i.size > 4 * 1500
+        raw = sel.run(tau=np.float32(0.9), criterion="smh_a", sort_output=False)
+        srt = sel.run(tau=np.float32(0.9), criterion="smh_a")
+        k_raw = (raw.i.astype(np.int64) << 32) | raw.k
+        o = np.argsort(k_raw, kind="stable")
+        assert np.array_equal(k_raw[o], (srt.i.astype(np.int64) << 32) | srt.k) and np.array_equal(raw.jaccard[o], srt.jaccard)
