@@ -204,6 +204,8 @@ struct selb200_ctx {
     } g;
     DevBuf g_push, g_merged;
     DevBuf row_cnt, row_off, sort_tmp;
+    DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
+    int chunk_regs = 0;
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
@@ -341,6 +343,7 @@ struct SrcPairs {            // pair list of the selection path: sorted position
         id = pairs[pi];
         return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
     }
+    __device__ __forceinline__ long long slot(long long pi) const { return pi; }   // histogram row of pair pi
 };
 
 struct SrcSelf {             // rows g0..g0+n-1 against themselves: per-genome histograms (max(a,a) = a)
@@ -352,6 +355,7 @@ struct SrcSelf {             // rows g0..g0+n-1 against themselves: per-genome h
         id = make_uint2((uint32_t)(g0 + pi), (uint32_t)(g0 + pi));
         return id;
     }
+    __device__ __forceinline__ long long slot(long long pi) const { return pi; }
 };
 
 struct EpiWriteHist {        // histogram rows for k_estimate_emit
@@ -408,11 +412,340 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src s
             if (lane + 32 < NB) s1 += hist[(lane + 32) * 64 + col];
         }
         __syncwarp();
-        epi(pi, id, s0 - prev0, s1 - prev1, lane);
+        epi(src.slot(pi), id, s0 - prev0, s1 - prev1, lane);
         prev0 = s0;
         prev1 = s1;
     }
 }
+
+// ============================================================================
+// K5 (bit-plane form): the same union histogram computed on BIT PLANES of the registers.
+//
+// The byte kernel above is bound by shared-memory read-modify-writes (measured ~9 registers per clock
+// per SM: two wavefronts per 32 registers, tools/ubench/int_pipes.cu).  HLL registers are 6-bit numbers,
+// so a genome can also be stored as 6 planes of 2^p bits (12 KiB instead of 16 KiB at p=14), and one
+// 32-bit logic instruction then handles 32 registers at once:
+//   max(a,b)   : borrow chain of a-b over the planes (1 LOP3 per plane) -> mask "a<b", then one select
+//                per plane                                                            12 LOP3 / 32 regs
+//   decode     : 8 masks of the low 3 bits + 4 masks of the high 3 bits (the pair's values lie in a
+//                window of 32 consecutive values starting at a multiple of 8)         12 LOP3
+//   count      : per value, mask = high & low, accumulated with carry-save adders over 4 words
+//                (2 CSA = 4 LOP3, 2 POPC, 1 IADD3 per value and 4 words)              ~2 LOP3 / value / word
+// i.e. ~2.3-2.8 ALU-pipe operations per register instead of two shared-memory wavefronts per 32.
+// POPC issues at 16 lanes/clk/SM on B200 (LOP3: 63), hence the carry-save adders.
+// The planes are staged into shared memory by cp.async.bulk (TMA) copies completing on mbarriers;
+// one warp per CTA, ~9 CTAs per SM.
+// Pairs whose value range does not fit a 32-value window (never seen on real sketches) go to a
+// "wide" list and through the byte kernel.
+// layout: genome g at planes + g * 6 * m/8 bytes; chunk c (2048 registers, or m if smaller) holds its
+//         6 planes back to back: [chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r
+// ============================================================================
+constexpr int PL_CHUNK_REGS = 2048;
+
+__global__ void __launch_bounds__(256)
+k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, int chunk_regs,
+                    uint32_t* __restrict__ planes) {
+    const int lane = threadIdx.x & 31;
+    const long long nblk = rows * (long long)(m >> 9);          // 512-register blocks
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int blk_per_genome = (int)(m >> 9), blk_per_chunk = chunk_regs >> 9;
+    const size_t chunk_words = (size_t)6 * (chunk_regs >> 5);
+    for (long long blk = warp0; blk < nblk; blk += nwarps) {
+        const long long g = blk / blk_per_genome;
+        const int bg = (int)(blk - g * blk_per_genome);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(regs + (size_t)g * m + (size_t)bg * 512) + lane);
+        const int chunk = bg / blk_per_chunk, bc = bg - chunk * blk_per_chunk;
+        uint32_t* dst = planes + (size_t)g * 6 * (m >> 5) + (size_t)chunk * chunk_words + (size_t)bc * 16;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            // bit b of the lane's 16 registers -> 16-bit mask (multiply gathers the 4 byte-bits of a word)
+            const uint32_t nx = ((((v.x >> b) & 0x01010101u) * 0x10204080u) >> 28);
+            const uint32_t ny = ((((v.y >> b) & 0x01010101u) * 0x10204080u) >> 28);
+            const uint32_t nz = ((((v.z >> b) & 0x01010101u) * 0x10204080u) >> 28);
+            const uint32_t nw = ((((v.w >> b) & 0x01010101u) * 0x10204080u) >> 28);
+            const uint32_t h = nx | (ny << 4) | (nz << 8) | (nw << 12);
+            const uint32_t lo = __shfl_sync(0xffffffffu, h, 2 * (lane & 15));
+            const uint32_t hi = __shfl_sync(0xffffffffu, h, 2 * (lane & 15) + 1);
+            if (lane < 16) dst[(size_t)b * (chunk_regs >> 5) + lane] = lo | (hi << 16);
+        }
+    }
+}
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(phase)
+        : "memory");
+}
+
+// One chunk (<= 2048 registers: 64 words per plane) against the running carry-save state.  Lane q holds
+// two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so
+// that eight independent dependency chains are in flight (LOP3 latency 4 at one issue per 2 clocks).
+template <int G0>
+__device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq,
+                                            int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
+    // nq = uint2 (2 x 32 registers) per plane; plane b of genome X at sX + b*nq
+#pragma unroll 1
+    for (int q = lane; q < nq; q += 32) {
+        uint32_t M[2][6];
+        {
+            uint2 a[6], b[6];
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) { a[pl] = sA[pl * nq + q]; b[pl] = sB[pl * nq + q]; }
+            uint32_t lt0 = 0u, lt1 = 0u;
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) {       // borrow of a - b, plane by plane: ends as the mask a < b
+                lt0 = lop3<0x8E>(a[pl].x, b[pl].x, lt0);
+                lt1 = lop3<0x8E>(a[pl].y, b[pl].y, lt1);
+            }
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) {       // max = a < b ? b : a
+                M[0][pl] = lop3<0xCA>(lt0, b[pl].x, a[pl].x);
+                M[1][pl] = lop3<0xCA>(lt1, b[pl].y, a[pl].y);
+            }
+        }
+        uint32_t L[2][8];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            L[w][0] = lop3<0x01>(M[w][2], M[w][1], M[w][0]);
+            L[w][1] = lop3<0x02>(M[w][2], M[w][1], M[w][0]);
+            L[w][2] = lop3<0x04>(M[w][2], M[w][1], M[w][0]);
+            L[w][3] = lop3<0x08>(M[w][2], M[w][1], M[w][0]);
+            L[w][4] = lop3<0x10>(M[w][2], M[w][1], M[w][0]);
+            L[w][5] = lop3<0x20>(M[w][2], M[w][1], M[w][0]);
+            L[w][6] = lop3<0x40>(M[w][2], M[w][1], M[w][0]);
+            L[w][7] = lop3<0x80>(M[w][2], M[w][1], M[w][0]);
+        }
+#define SELB_PLANE_GROUP(T)                                                                               \
+        if (gmask & (1u << T)) {                                                                          \
+            const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
+            const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
+            uint32_t m0[8], m1[8], kk[8];                                                                 \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);                 \
+        }
+        SELB_PLANE_GROUP(0)
+        SELB_PLANE_GROUP(1)
+        SELB_PLANE_GROUP(2)
+        SELB_PLANE_GROUP(3)
+#undef SELB_PLANE_GROUP
+    }
+}
+
+// pair list -> histogram rows, bit-plane form.  grange[g] = min | max<<8 of genome g's registers.
+// One warp per CTA.  Work comes in batches of 32 consecutive pairs claimed from a device counter (dynamic
+// balance, no tail): each lane fetches the descriptor of one pair of the batch (rows through `order`, value
+// window from grange), so the dependent global loads are paid once per 32 pairs and the warp then reads
+// descriptors with shuffles.  The pairs' planes flow chunk by chunk (2048 registers = 2 x 1.5 KiB) through a
+// ring of PL_STAGES shared-memory stages: lane 0 keeps PL_STAGES-1 bulk copies (TMA) in flight ahead of
+// the chunk being counted, across pair and batch boundaries.
+constexpr int PL_STAGES = 4;
+#ifndef PL_MIN_CTAS
+#define PL_MIN_CTAS 16
+#endif
+
+template <class Epi>
+__global__ void __launch_bounds__(32, PL_MIN_CTAS)
+k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
+                   SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
+                   unsigned long long* __restrict__ batch_counter) {
+    extern __shared__ __align__(128) uint8_t pl_smem[];
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int nchunks = (int)(m / (size_t)chunk_regs);
+    const uint32_t chunk_bytes = (uint32_t)(6 * (chunk_regs >> 3));
+    const int nq = chunk_regs >> 6;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(pl_smem);
+    const uint32_t bar0 = smem0 + PL_STAGES * 2 * chunk_bytes;
+    if (lane == 0)
+        for (int st = 0; st < PL_STAGES; ++st) mbar_init(bar0 + 8 * st, 1);
+    __syncwarp();
+    const size_t genome_bytes = (size_t)6 * (m >> 3);
+    const long long npairs = src.count();
+
+    // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
+    uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
+    uint32_t mask0 = 0, mask1 = 0;          // lanes of the set holding a pair to do (warp-uniform)
+    long long base0 = 0, base1 = 0;         // first pair index of the batch
+    bool end0 = false, end1 = false;        // the batch starts past the end of the list: nothing follows
+    int filled = -1;
+
+    auto fill = [&](int k) {
+        long long bidx = 0;
+        if (lane == 0) bidx = (long long)atomicAdd(batch_counter, 1ull);
+        bidx = __shfl_sync(FULL, bidx, 0);
+        const long long pi = bidx * 32 + lane;
+        bool ok = pi < npairs;
+        uint2 id = make_uint2(0u, 0u), rw = id;
+        uint32_t gm = 0;
+        if (ok) {
+            rw = src.rows(pi, id);
+            const uint32_t ra = grange[rw.x], rb = grange[rw.y];
+            const int lo = max((int)(ra & 0xff), (int)(rb & 0xff)), hi = max((int)(ra >> 8), (int)(rb >> 8));
+            const int g0 = min(lo >> 3, 4);
+            if ((hi >> 3) > g0 + 3) {        // value range wider than the window: the byte kernel does this pair
+                wide_list[atomicAdd(wide_count, 1ull)] = (uint32_t)pi;
+                ok = false;
+            } else {
+                uint32_t gmask = 0;
+                for (int t = 0; t < 4; ++t)
+                    if ((g0 + t) >= (lo >> 3) && (g0 + t) <= (hi >> 3)) gmask |= 1u << t;
+                gm = (uint32_t)g0 | (gmask << 8);
+            }
+        }
+        const uint32_t msk = __ballot_sync(FULL, ok);
+        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; mask1 = msk; base1 = bidx * 32; end1 = bidx * 32 >= npairs; }
+        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; mask0 = msk; base0 = bidx * 32; end0 = bidx * 32 >= npairs; }
+        filled = k;
+    };
+
+    struct Cur {               // position in the warp's sequence of (pair, chunk) items; warp-uniform
+        int k;                 // batch number
+        uint32_t mask;         // pairs of the batch not started yet
+        bool valid, done;
+        int ch;
+        uint32_t rx, ry, ix, iy, gm;
+        long long pi;
+    };
+    auto next_pair = [&](Cur& c, bool is_cons) {
+        c.valid = false;
+        for (;;) {
+            if (c.mask) {
+                const int j = __ffs((int)c.mask) - 1;
+                c.mask &= c.mask - 1;
+                const bool odd = c.k & 1;
+                c.rx = __shfl_sync(FULL, odd ? d_rx1 : d_rx0, j);
+                c.ry = __shfl_sync(FULL, odd ? d_ry1 : d_ry0, j);
+                c.ix = __shfl_sync(FULL, odd ? d_ix1 : d_ix0, j);
+                c.iy = __shfl_sync(FULL, odd ? d_iy1 : d_iy0, j);
+                c.gm = __shfl_sync(FULL, odd ? d_gm1 : d_gm0, j);
+                c.pi = (odd ? base1 : base0) + j;
+                c.ch = 0;
+                c.valid = true;
+                return;
+            }
+            if ((c.k & 1) ? end1 : end0) { c.done = true; return; }
+            if (c.k + 1 > filled) return;                 // producer only: the next batch is not there yet
+            ++c.k;
+            c.mask = (c.k & 1) ? mask1 : mask0;
+            // the consumer has left batch k-1: its set is free for batch k+1
+            if (is_cons && !(((filled & 1) ? end1 : end0))) fill(c.k + 1);
+        }
+    };
+    auto issue = [&](const Cur& c, uint32_t n_issued) {      // lane 0: two bulk copies into the next stage
+        const uint32_t st = n_issued % PL_STAGES;
+        const uint32_t dst = smem0 + st * 2 * chunk_bytes, bar = bar0 + 8 * st;
+        const uint8_t* ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes + (size_t)c.ch * chunk_bytes;
+        const uint8_t* gb = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.ry * genome_bytes + (size_t)c.ch * chunk_bytes;
+        mbar_expect_tx(bar, 2 * chunk_bytes);
+        tma_bulk_g2s(dst, ga, chunk_bytes, bar);
+        tma_bulk_g2s(dst + chunk_bytes, gb, chunk_bytes, bar);
+    };
+
+    fill(0);
+    if (!end0) fill(1);
+    Cur cons;
+    cons.k = 0; cons.mask = mask0; cons.valid = false; cons.done = false; cons.ch = 0;
+    cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.pi = 0;
+    Cur prod = cons;
+    next_pair(cons, true);
+    next_pair(prod, false);
+    uint32_t n_issued = 0, n_done = 0;
+    for (int k = 0; k < PL_STAGES - 1 && prod.valid; ++k) {
+        if (lane == 0) issue(prod, n_issued);
+        ++n_issued;
+        if (++prod.ch >= nchunks) next_pair(prod, false);
+    }
+    uint32_t S[32], C2[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
+    while (cons.valid) {
+        __syncwarp();                          // every lane has finished reading the stage about to be refilled
+        if (!prod.valid && !prod.done) next_pair(prod, false);
+        if (prod.valid) {
+            if (lane == 0) issue(prod, n_issued);
+            ++n_issued;
+            if (++prod.ch >= nchunks) next_pair(prod, false);
+        }
+        if (n_done == n_issued) __trap();      // cannot happen: the consumer never overtakes the producer
+        const uint32_t st = n_done % PL_STAGES;
+        mbar_wait(bar0 + 8 * st, (n_done / PL_STAGES) & 1u);
+        ++n_done;
+        const uint2* pa = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes);
+        const uint2* pb = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes + chunk_bytes);
+        const int g0 = (int)(cons.gm & 0xffu);
+        const uint32_t gmask = cons.gm >> 8;
+        switch (g0) {
+            case 0: plane_chunk<0>(pa, pb, nq, lane, gmask, S, C2); break;
+            case 1: plane_chunk<1>(pa, pb, nq, lane, gmask, S, C2); break;
+            case 2: plane_chunk<2>(pa, pb, nq, lane, gmask, S, C2); break;
+            case 3: plane_chunk<3>(pa, pb, nq, lane, gmask, S, C2); break;
+            default: plane_chunk<4>(pa, pb, nq, lane, gmask, S, C2); break;
+        }
+        if (cons.ch == nchunks - 1) {
+            // per-lane totals, then a transposing butterfly: lane L ends with the warp total of value 8*g0 + L
+            uint32_t x[32];
+#pragma unroll
+            for (int v = 0; v < 32; ++v) { x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]); S[v] = 0; C2[v] = 0; }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                    const uint32_t send = upper ? x[i] : x[i + o];
+                    const uint32_t keep = upper ? x[i + o] : x[i];
+                    x[i] = keep + __shfl_xor_sync(FULL, send, o);
+                }
+            }
+            const uint32_t tot = __shfl_sync(FULL, x[0], (lane - 8 * g0) & 31);
+            const bool first = lane >= 8 * g0;     // bin `lane` lies inside the window; else bin lane+32 does
+            epi(src.slot(cons.pi), make_uint2(cons.ix, cons.iy), first ? tot : 0u, first ? 0u : tot, (uint32_t)lane);
+        }
+        if (++cons.ch >= nchunks) next_pair(cons, true);
+    }
+}
+
+// the wide list as a pair source for the byte kernel (histogram row = the pair's own slot)
+struct SrcWide {
+    const uint2* pairs;
+    const int32_t* order;
+    const uint32_t* wide_list;
+    const unsigned long long* n_dev;
+    __device__ __forceinline__ long long count() const { return (long long)*n_dev; }
+    __device__ __forceinline__ uint2 rows(long long wi, uint2& id) const {
+        id = pairs[wide_list[wi]];
+        return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
+    }
+    __device__ __forceinline__ long long slot(long long wi) const { return (long long)wide_list[wi]; }
+};
 
 __global__ void k_iota_i32(int32_t* v, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -432,10 +765,16 @@ __global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long
 // per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
 __global__ void k_genome_cards(const uint32_t* __restrict__ hist, const double* __restrict__ stored, long long n,
                                int p, double* __restrict__ cards, const uint32_t* __restrict__ max_seen,
-                               uint32_t max_ok) {
+                               uint32_t max_ok, uint16_t* __restrict__ grange) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (*max_seen > max_ok) { cards[i] = 0.; return; }   // malformed input: the load fails after the sync
+    if (*max_seen > max_ok) { cards[i] = 0.; grange[i] = 0; return; }   // malformed input: the load fails after the sync
+    {   // smallest and largest register value of the genome (window choice of the bit-plane union kernel)
+        int vmin = 63, vmax = 0;
+        for (int b = 0; b < 64; ++b)
+            if (hist[i * 64 + b]) { vmin = min(vmin, b); vmax = max(vmax, b); }
+        grange[i] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
+    }
     if (stored && stored[i] >= 0.) { cards[i] = stored[i]; return; }
     cards[i] = selb::ertl_mle(hist + i * 64, p);
 }
@@ -502,7 +841,7 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 // meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
 // range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
 // ============================================================================
-enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WORDS = 8 };
+enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_WORDS = 16 };
 
 __global__ void __launch_bounds__(128)
 k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
@@ -1086,6 +1425,46 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
     return launch_pair_hist_t(c->stream, c->sm_count, regs, m, m, p, npairs, src, epi);
 }
 
+// bit-plane union pass over the run's pair list (+ the byte kernel on whatever landed in the wide list)
+int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pairs, uint32_t* hist_out,
+                            const unsigned long long* npairs_dev, unsigned long long* wide_count, int* launches) {
+    if (max_pairs <= 0) return SELB200_OK;
+    cudaStream_t s = c->stream;
+    CKR(c->wide_list.ensure((size_t)max_pairs * 4));
+    SrcPairs src{pairs, c->order_dev.as<int32_t>(), (long long)max_pairs, npairs_dev};
+    EpiWriteHist epi{hist_out};
+    const size_t smem = (size_t)PL_STAGES * 2 * 6 * (c->chunk_regs >> 3) + 8 * PL_STAGES;
+    static int per_sm = 0;
+    static size_t per_sm_smem = 0;
+    if (!per_sm || per_sm_smem != smem) {
+        cudaFuncSetAttribute(k_pair_hist_planes<EpiWriteHist>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_hist_planes<EpiWriteHist>, 32, smem) != cudaSuccess ||
+            per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 4;
+        }
+        per_sm_smem = smem;
+    }
+    CK(cudaMemsetAsync(wide_count, 0, 16, s));          // wide count + batch counter (adjacent words of meta[])
+    const int grid = (int)std::min<int64_t>((max_pairs + 31) / 32, (int64_t)c->sm_count * per_sm);
+    k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
+                                                           c->grange.as<uint16_t>(), src, epi,
+                                                           c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+    CK(cudaGetLastError());
+    // pairs whose value range exceeds the 32-value window: byte kernel, small persistent grid
+    SrcWide wsrc{pairs, c->order_dev.as<int32_t>(), c->wide_list.as<uint32_t>(), wide_count};
+    if (c->m >= 512) {
+        const int nbins = 64 - c->p + 2;
+        const int wgrid = (int)std::min<int64_t>((max_pairs + 1) / 2, (int64_t)c->sm_count * 2);
+        if (nbins <= 52) k_pair_hist<52, SrcWide, EpiWriteHist><<<wgrid, 64, 0, s>>>(c->d_regs, c->m, c->m, wsrc, epi);
+        else k_pair_hist<64, SrcWide, EpiWriteHist><<<wgrid, 64, 0, s>>>(c->d_regs, c->m, c->m, wsrc, epi);
+        CK(cudaGetLastError());
+    }
+    if (launches) *launches += 2;
+    return SELB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // load = begin -> chunks -> end.  selb200_load_host / _device run all three over caller memory;
 // the streaming entry points (selb200_load_begin / acquire / commit / end) let the caller decode
@@ -1139,6 +1518,9 @@ int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, cons
             L.d_aux = c->cand.p;
         }
     }
+    c->chunk_regs = (int)std::min<size_t>(c->m, (size_t)PL_CHUNK_REGS);
+    CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
+    CKR(c->grange.ensure((size_t)n * sizeof(uint16_t)));
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
     CKR(c->out_j.ensure((size_t)n * sizeof(double)));        // stored value_ of each header (-1 = recompute)
@@ -1196,8 +1578,16 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
     CKR(launch_pair_hist_t(s, c->sm_count, c->d_regs, c->m, c->m, p, rows, src, epi));
     k_genome_cards<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(
         c->hist.as<uint32_t>() + (size_t)g0 * 64, h_stored ? c->out_j.as<double>() + g0 : nullptr, rows, p,
-        c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1));
+        c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1),
+        c->grange.as<uint16_t>() + g0);
     CK(cudaGetLastError());
+    {   // bit-plane copy of the chunk for the union kernel
+        const long long nblk = rows * (long long)(c->m >> 9);
+        const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
+        k_planes_from_bytes<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
+                                                 c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5));
+        CK(cudaGetLastError());
+    }
     L.rows_done += rows;
     return SELB200_OK;
 }
@@ -1355,7 +1745,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1519,6 +1909,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         st.n_rows = n_rows; st.n_bands = n_bands;
     }
 
+    // SELB200_UNION=bytes selects the shared-memory byte kernel for the union pass (A/B measurements)
+    static const bool union_bytes = [] { const char* e = getenv("SELB200_UNION"); return e && !strcmp(e, "bytes"); }();
     const bool gather = prm->gather != 0;
     if (gather && !c->g.attached) return fail(SELB200_ESTATE, "params.gather set without selb200_gather_attach");
     if (gather && (prm->shard != c->g.rank || n_shards != c->g.world))
@@ -1739,9 +2131,14 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             // ---- K5 + K6 --------------------------------------------------------------
             cudaEvent_t u0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) t_verify.push_back({f1, u0});
-            CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
-                                 (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
-            st.launches++;
+            if (union_bytes) {
+                CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
+                                     (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
+                st.launches++;
+            } else {
+                CKR(launch_pair_hist_planes(c, c->pairs.as<uint2>(), (int64_t)pair_lim, c->hist.as<uint32_t>(),
+                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches));
+            }
             cudaEvent_t u1 = c->ev();
             k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
                 c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,

@@ -53,6 +53,7 @@ struct SrcShim {             // survivors -> caller's int2 pair list (row indice
         id = make_uint2((uint32_t)pr.x, (uint32_t)pr.y);
         return id;
     }
+    __device__ __forceinline__ long long slot(long long pi) const { return pi; }
 };
 
 struct EpiFlajolet {         // criteria_sketch_cuda.cuh:30-65 + selection_kernels.cu:41-59
