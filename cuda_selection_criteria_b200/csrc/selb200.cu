@@ -507,28 +507,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 // One chunk (<= 2048 registers: 64 words per plane) against the running carry-save state.  Lane q holds
 // two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so
 // that eight independent dependency chains are in flight (LOP3 latency 4 at one issue per 2 clocks).
-template <int G0>
-__device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq,
+template <int G0, int NQ>   // NQ > 0: uint2 per plane known at compile time (full 2048-register chunks)
+__device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
                                             int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
-    // nq = uint2 (2 x 32 registers) per plane; plane b of genome X at sX + b*nq
+    const int nq = NQ > 0 ? NQ : nq_rt;
+    // nq = uint2 (2 x 32 registers) per plane; plane b of genome X at sX + b*nq.
+    // Window 0 holds values below 32 only: plane 5 is all zero there and is neither copied nor read.
+    constexpr int NP = (G0 == 0) ? 5 : 6;
 #pragma unroll 1
     for (int q = lane; q < nq; q += 32) {
         uint32_t M[2][6];
         {
-            uint2 a[6], b[6];
+            uint2 a[NP], b[NP];
 #pragma unroll
-            for (int pl = 0; pl < 6; ++pl) { a[pl] = sA[pl * nq + q]; b[pl] = sB[pl * nq + q]; }
+            for (int pl = 0; pl < NP; ++pl) { a[pl] = sA[pl * nq + q]; b[pl] = sB[pl * nq + q]; }
             uint32_t lt0 = 0u, lt1 = 0u;
 #pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {       // borrow of a - b, plane by plane: ends as the mask a < b
+            for (int pl = 0; pl < NP; ++pl) {      // borrow of a - b, plane by plane: ends as the mask a < b
                 lt0 = lop3<0x8E>(a[pl].x, b[pl].x, lt0);
                 lt1 = lop3<0x8E>(a[pl].y, b[pl].y, lt1);
             }
 #pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {       // max = a < b ? b : a
+            for (int pl = 0; pl < NP; ++pl) {      // max = a < b ? b : a
                 M[0][pl] = lop3<0xCA>(lt0, b[pl].x, a[pl].x);
                 M[1][pl] = lop3<0xCA>(lt1, b[pl].y, a[pl].y);
             }
+            if (NP == 5) { M[0][5] = 0u; M[1][5] = 0u; }
         }
         uint32_t L[2][8];
 #pragma unroll
@@ -542,20 +546,24 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
             L[w][6] = lop3<0x40>(M[w][2], M[w][1], M[w][0]);
             L[w][7] = lop3<0x80>(M[w][2], M[w][1], M[w][0]);
         }
-#define SELB_PLANE_GROUP(T)                                                                               \
+        // SPARSE: the top group of a window holds a handful of registers per genome, so most warp-wide
+        // steps see none of them and skip the group's 40 instructions after one vote
+#define SELB_PLANE_GROUP(T, SPARSE)                                                                       \
         if (gmask & (1u << T)) {                                                                          \
             const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
             const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
-            uint32_t m0[8], m1[8], kk[8];                                                                 \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);                 \
+            if (!SPARSE || __any_sync(0xffffffffu, (H0 | H1) != 0u)) {                                    \
+                uint32_t m0[8], m1[8], kk[8];                                                             \
+                _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
+                _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
+                _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
+                _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);             \
+            }                                                                                             \
         }
-        SELB_PLANE_GROUP(0)
-        SELB_PLANE_GROUP(1)
-        SELB_PLANE_GROUP(2)
-        SELB_PLANE_GROUP(3)
+        SELB_PLANE_GROUP(0, false)
+        SELB_PLANE_GROUP(1, false)
+        SELB_PLANE_GROUP(2, false)
+        SELB_PLANE_GROUP(3, false)
 #undef SELB_PLANE_GROUP
     }
 }
@@ -665,9 +673,11 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         const uint32_t dst = smem0 + st * 2 * chunk_bytes, bar = bar0 + 8 * st;
         const uint8_t* ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes + (size_t)c.ch * chunk_bytes;
         const uint8_t* gb = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.ry * genome_bytes + (size_t)c.ch * chunk_bytes;
-        mbar_expect_tx(bar, 2 * chunk_bytes);
-        tma_bulk_g2s(dst, ga, chunk_bytes, bar);
-        tma_bulk_g2s(dst + chunk_bytes, gb, chunk_bytes, bar);
+        // window 0 (values < 32): plane 5 is zero and stays behind — 5/6 of the bytes
+        const uint32_t nbytes = (c.gm & 0xffu) == 0u ? chunk_bytes / 6u * 5u : chunk_bytes;
+        mbar_expect_tx(bar, 2 * nbytes);
+        tma_bulk_g2s(dst, ga, nbytes, bar);
+        tma_bulk_g2s(dst + chunk_bytes, gb, nbytes, bar);
     };
 
     fill(0);
@@ -703,12 +713,22 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         const uint2* pb = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes + chunk_bytes);
         const int g0 = (int)(cons.gm & 0xffu);
         const uint32_t gmask = cons.gm >> 8;
-        switch (g0) {
-            case 0: plane_chunk<0>(pa, pb, nq, lane, gmask, S, C2); break;
-            case 1: plane_chunk<1>(pa, pb, nq, lane, gmask, S, C2); break;
-            case 2: plane_chunk<2>(pa, pb, nq, lane, gmask, S, C2); break;
-            case 3: plane_chunk<3>(pa, pb, nq, lane, gmask, S, C2); break;
-            default: plane_chunk<4>(pa, pb, nq, lane, gmask, S, C2); break;
+        if (nq == 32) {
+            switch (g0) {
+                case 0: plane_chunk<0, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 1: plane_chunk<1, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 2: plane_chunk<2, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 3: plane_chunk<3, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+                default: plane_chunk<4, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+            }
+        } else {
+            switch (g0) {
+                case 0: plane_chunk<0, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 1: plane_chunk<1, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 2: plane_chunk<2, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 3: plane_chunk<3, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                default: plane_chunk<4, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+            }
         }
         if (cons.ch == nchunks - 1) {
             // per-lane totals, then a transposing butterfly: lane L ends with the warp total of value 8*g0 + L
