@@ -964,65 +964,114 @@ __global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long l
 // operand holds the negated halves, so a half reaches 0 exactly when the two signatures are equal.
 // Measured alternatives on B200 (n=100k, 4.66e8 CB pairs): XOR+MIN on 32-bit signatures 1.22 ms;
 // (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256, FILTER_CTAS_PER_SM)
 k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
                   TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
                   unsigned long long cand_cap) {
-    __shared__ __align__(16) uint32_t sR[SIG_CHUNK][TILE];
-    __shared__ __align__(16) uint32_t sC[SIG_CHUNK][TILE];
+    // two buffers: the signature words of the next (tile, chunk) item stream in with cp.async while the
+    // current one is being compared — a tile's 8 KiB arrive in about the time its 512 instructions per
+    // thread take, so without the overlap the ALU pipe idles half the time
+    __shared__ __align__(16) uint32_t sR[2][SIG_CHUNK][TILE];
+    __shared__ __align__(16) uint32_t sC[2][SIG_CHUNK][TILE];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int jend = tw.count();
+    const int nchunk = (n_words + SIG_CHUNK - 1) / SIG_CHUNK;
     // persistent CTAs: the shard's tile count lives in device memory, so no host sync sizes the grid
-    for (int j = tw.j0 + (int)blockIdx.x; j < jend; j += (int)gridDim.x) {
-        const int2 rc = tw.tile(j);
+    const int j_first = tw.j0 + (int)blockIdx.x;
+    if (j_first >= jend) return;
+    const int my_tiles = (jend - 1 - j_first) / (int)gridDim.x + 1;
+    const int n_items = my_tiles * nchunk;                 // items = (tile, chunk of SIG_CHUNK words), no divisions below
+
+    auto tile_at = [&](int t) -> int2 { return t < my_tiles ? tw.tile(j_first + t * (int)gridDim.x) : make_int2(0, 0); };
+    auto stage = [&](int ch, int2 rc, int buf) {           // queue the loads of one item
+        const int b0 = ch * SIG_CHUNK;
+        const int nb = min(SIG_CHUNK, n_words - b0);
         const int r0 = rc.x * TILE, c0 = rc.y * TILE;
-
-        uint32_t acc[8][8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
-
-        for (int b0 = 0; b0 < n_words; b0 += SIG_CHUNK) {
-            const int nb = min(SIG_CHUNK, n_words - b0);
-            __syncthreads();
-            for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per load
-                const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
-                if (part < 32)
-                    *reinterpret_cast<uint4*>(&sR[bb][x]) =
-                        __ldg(reinterpret_cast<const uint4*>(sigR + (size_t)(b0 + bb) * npad + r0 + x));
-                else
-                    *reinterpret_cast<uint4*>(&sC[bb][x]) =
-                        __ldg(reinterpret_cast<const uint4*>(sigC + (size_t)(b0 + bb) * npad + c0 + x));
-            }
-            __syncthreads();
-            for (int bb = 0; bb < nb; ++bb) {
-                const uint4 ra = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8]);
-                const uint4 rb = *reinterpret_cast<const uint4*>(&sR[bb][ty * 8 + 4]);
-                const uint4 ca = *reinterpret_cast<const uint4*>(&sC[bb][tx * 4]);
-                const uint4 cb = *reinterpret_cast<const uint4*>(&sC[bb][64 + tx * 4]);
-                const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-                const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
-            }
+        for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per copy
+            const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
+            if (part < 32) cp_async16(&sR[buf][bb][x], sigR + (size_t)(b0 + bb) * npad + r0 + x);
+            else cp_async16(&sC[buf][bb][x], sigC + (size_t)(b0 + bb) * npad + c0 + x);
         }
-        uint32_t any = 0xffffffffu;
+        cp_async_commit();
+    };
+    // zero 16-bit half somewhere in x
+    auto has_zero_half = [](uint32_t x) { return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u; };
+
+    uint32_t acc[8][8];
+    // (t, ch) = item being compared; its successor is being copied.  Tile coordinates are fetched two
+    // tiles ahead so that the copy never waits on the table lookup.
+    int t = 0, ch = 0;
+    int2 rc_t = tile_at(0), rc_t1 = tile_at(1), rc_t2 = tile_at(2);
+    stage(0, rc_t, 0);
+    for (int item = 0; item < n_items; ++item) {
+        const int buf = item & 1;
+        if (item + 1 < n_items) {
+            const bool same_tile = ch + 1 < nchunk;
+            stage(same_tile ? ch + 1 : 0, same_tile ? rc_t : rc_t1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (ch == 0) {
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) any = __vminu2(any, acc[a][b]);
-        if ((any & 0xffffu) != 0 && (any >> 16) != 0) continue;
-        // rare path: gather the matching (a,b) cells into a bit mask, then walk its set bits
-        unsigned long long cells = 0ull;
+                for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
+        }
+        const int nb = min(SIG_CHUNK, n_words - ch * SIG_CHUNK);
+        for (int bb = 0; bb < nb; ++bb) {
+            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8]);
+            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8 + 4]);
+            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[buf][bb][tx * 4]);
+            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[buf][bb][64 + tx * 4]);
+            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b)
-                if ((acc[a][b] & 0xffffu) == 0 || (acc[a][b] >> 16) == 0) cells |= 1ull << (a * 8 + b);
+                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
+        }
+        __syncthreads();                                  // the buffer is free for the item after next
+        if (++ch < nchunk) continue;
+        const int2 rc = rc_t;                               // the tile just finished
+        ch = 0;
+        ++t;
+        rc_t = rc_t1;
+        rc_t1 = rc_t2;
+        rc_t2 = tile_at(t + 2);
+        // per-row minima first: a 16-bit signature collides by chance once per ~64 thread-tiles, so four
+        // warps in ten come here with ONE row to look at, not 64 cells
+        uint32_t rowmin[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const uint32_t m0 = __vimin3_u16x2(acc[a][0], acc[a][1], acc[a][2]);
+            const uint32_t m1 = __vimin3_u16x2(acc[a][3], acc[a][4], acc[a][5]);
+            rowmin[a] = __vimin3_u16x2(m0, m1, __vminu2(acc[a][6], acc[a][7]));
+        }
+        const uint32_t any = __vimin3_u16x2(__vimin3_u16x2(rowmin[0], rowmin[1], rowmin[2]),
+                                            __vimin3_u16x2(rowmin[3], rowmin[4], rowmin[5]),
+                                            __vminu2(rowmin[6], rowmin[7]));
+        if (!has_zero_half(any)) continue;
+        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
+        unsigned long long cells = 0ull;                    // bit a*8+b: cell (a,b) has a matching band signature
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            if (!has_zero_half(rowmin[a])) continue;
+            uint32_t rowbits = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) rowbits |= has_zero_half(acc[a][b]) ? (1u << b) : 0u;
+            cells |= (unsigned long long)rowbits << (a * 8);
+        }
         while (cells) {
             const int bit = __ffsll((long long)cells) - 1;
             cells &= cells - 1;
