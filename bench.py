@@ -335,8 +335,9 @@ def main():
 
     st0 = stats_acc[-1]
     peak, peak_src = measured_peak()
-    k_union = {"name": "k_pair_hist", "ms": mean("ms_union"), "bytes": ALG_BYTES["union"] * st0["pairs_aux"],
-               "unit_def": "32768 B per aux-passing pair x pairs_aux"}
+    union_kernel = "k_pair_hist" if os.environ.get("SELB200_UNION") == "bytes" else "k_pair_hist_planes"
+    k_union = {"name": union_kernel, "ms": mean("ms_union"), "bytes": ALG_BYTES["union"] * st0["pairs_aux"],
+               "unit_def": "32768 B (2 x 2^14 one-byte registers, SURVEY.md 8d) per aux-passing pair x pairs_aux"}
     per_pair_filter = {"smh_a": ALG_BYTES["smh_a"], "cb": ALG_BYTES["cb"],
                        "hll_a": 2 * a.aux_bytes, "hll_an": 2 * a.aux_bytes}[a.criterion]
     k_filter = {"name": {"smh_a": "k_tile_filter_smh", "cb": "k_tile_enum", "hll_a": "k_tile_filter_hll",
@@ -348,6 +349,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(dom["name"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"], "bytes_def": dom["unit_def"],
+                "note": ("frac > 1 is possible: the union kernel reads 6-bit planes (24 KiB per pair, 20 KiB when all values "
+                         "are below 32) and L2 serves repeated rows; its binding limit is the integer ALU pipe "
+                         "(profiles/r01_ncu_summary.md)"),
                 "kernels_ms": {"bounds": mean("ms_bounds"), "filter": mean("ms_filter"), "verify": mean("ms_verify"),
                                "union": mean("ms_union"), "estimate": mean("ms_estimate"), "sort": mean("ms_sort"),
                                "run_total": mean("ms_total")}}
