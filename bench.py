@@ -287,7 +287,13 @@ def main():
         sdist.broadcast_sketches(regs_d, aux_d, src=0)
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for everything: torch copies and NCCL collectives issued under it and the
+    # library's kernels (which run on the stream handed to the context) are then ordered on the device
+    # (the legacy default stream has handle 0, which the C-ABI reads as "use a stream of your own")
+    main_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(main_stream)
+    stream = main_stream.cuda_stream
+    assert stream != 0
     sel = S.Selection(local, stream=stream)
     sel.load(regs_d, aux_d, aux_kind)
 
@@ -375,19 +381,31 @@ def main():
             sh = sdist.ShardedSketches(a.n, regs_d.shape[1], aux_d.shape[1] if aux_d is not None else 0,
                                        aux_d.dtype if aux_d is not None else None, dev, rank, world)
 
+        phase = {"h2d_gather_load": 0.0, "run_gather_fetch": 0.0}
+
         def step_e2e():
+            t_a = time.perf_counter()
             if world == 1:
                 sel2.load(regs_h, aux_h, aux_kind)                       # H2D inside
             else:
-                r_all, a_all = sh.assemble(regs_h, aux_h)                # H2D of the slice + NCCL all-gather
-                sel2.load(r_all, a_all, aux_kind)
+                # H2D of the slice piece by piece; each piece is all-gathered over NVLink and digested
+                # (validation, histograms, cardinalities, bit planes) while the next one is on the PCIe bus
+                sel2.load_device_begin(sh.regs, sh.aux, aux_kind)
+                sh.assemble(regs_h, aux_h, on_piece=sel2.load_device_rows)
+                sel2.load_end()
+            t_b = time.perf_counter()              # load returns after its last device sync
             sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1),
                      host_results=(rank == 0))
-            return sel2.result_host()[0].size if rank == 0 else 0
+            out = sel2.result_host()[0].size if rank == 0 else 0
+            phase["h2d_gather_load"] += t_b - t_a
+            phase["run_gather_fetch"] += time.perf_counter() - t_b
+            return out
 
         e2e_steps = max(1, min(a.steps, 5))
         step_e2e()
         barrier()
+        for k_ in phase:
+            phase[k_] = 0.0
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -404,7 +422,8 @@ def main():
         h2d = int(regs_d.numel() * regs_d.element_size() + (aux_d.numel() * aux_d.element_size() if aux_d is not None else 0))
         e2e = {"value": pairs_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(out_n * 16 + a.n * 8), "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "timer": "max(host wall clock, CUDA events) per step, max over ranks"}
+               "timer": "max(host wall clock, CUDA events) per step, max over ranks",
+               "rank0_phases_ms": {k: v * 1e3 / e2e_steps for k, v in phase.items()}}
         sel2.close()
 
     cb = None

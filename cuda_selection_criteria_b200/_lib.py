@@ -52,6 +52,8 @@ SYMBOLS = [
     ("selb200_destroy", None, [_VP]),
     ("selb200_load_host", _I, [_VP, _I64, _I, _VP, _VP, _I, _I, _VP]),
     ("selb200_load_device", _I, [_VP, _I64, _I, _VP, _VP, _I, _I, _VP]),
+    ("selb200_load_device_begin", _I, [_VP, _I64, _I, _VP, _I, _I, _VP]),
+    ("selb200_load_device_rows", _I, [_VP, _I64, _I64]),
     ("selb200_load_begin", _I, [_VP, _I64, _I, _I, _I, C.POINTER(_I64)]),
     ("selb200_load_acquire", _I, [_VP, _I64, _I64, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("selb200_load_commit", _I, [_VP]),

@@ -65,6 +65,17 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
+// SELB200_DEBUG_SYNC=1: synchronise after every stage of a run and name the stage that failed
+#define DBG_SYNC(c, what)                                                                               \
+    do {                                                                                                \
+        static const bool dbg__ = getenv("SELB200_DEBUG_SYNC") != nullptr;                              \
+        if (dbg__) {                                                                                    \
+            cudaError_t e__ = cudaStreamSynchronize((c)->stream);                                       \
+            if (e__ != cudaSuccess)                                                                     \
+                return fail(SELB200_ECUDA, "stage '%s' failed: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                               \
+    } while (0)
+
 #define CKR(call)                      \
     do {                               \
         int r__ = (call);              \
@@ -598,6 +609,10 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     __syncwarp();
     const size_t genome_bytes = (size_t)6 * (m >> 3);
     const long long npairs = src.count();
+    // batch size: 32 pairs when there is plenty of work, fewer (down to 4) when the list is short, so that
+    // every warp still gets several batches and the dynamic claiming can balance the tail
+    int bsz = 32;
+    while (bsz > 4 && npairs < (long long)bsz * gridDim.x * 4) bsz >>= 1;
 
     // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
     uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
@@ -610,8 +625,8 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         long long bidx = 0;
         if (lane == 0) bidx = (long long)atomicAdd(batch_counter, 1ull);
         bidx = __shfl_sync(FULL, bidx, 0);
-        const long long pi = bidx * 32 + lane;
-        bool ok = pi < npairs;
+        const long long pi = bidx * bsz + lane;
+        bool ok = lane < bsz && pi < npairs;
         uint2 id = make_uint2(0u, 0u), rw = id;
         uint32_t gm = 0;
         if (ok) {
@@ -630,8 +645,8 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             }
         }
         const uint32_t msk = __ballot_sync(FULL, ok);
-        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; mask1 = msk; base1 = bidx * 32; end1 = bidx * 32 >= npairs; }
-        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; mask0 = msk; base0 = bidx * 32; end0 = bidx * 32 >= npairs; }
+        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; mask1 = msk; base1 = bidx * bsz; end1 = bidx * bsz >= npairs; }
+        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; mask0 = msk; base0 = bidx * bsz; end0 = bidx * bsz >= npairs; }
         filled = k;
     };
 
@@ -643,9 +658,18 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         uint32_t rx, ry, ix, iy, gm;
         long long pi;
     };
+    Cur cons, prod;
     auto next_pair = [&](Cur& c, bool is_cons) {
         c.valid = false;
         for (;;) {
+            // A batch can be empty without being the end (all its pairs wide: one odd genome, many consecutive
+            // pairs).  The consumer then walks through it in one go and recycles its set, so a producer
+            // still parked on that batch number must not read the set any more: it rejoins the consumer,
+            // whose batch it has not touched yet.
+            if (!is_cons && c.k < cons.k) {
+                c.k = cons.k;
+                c.mask = (c.k & 1) ? mask1 : mask0;
+            }
             if (c.mask) {
                 const int j = __ffs((int)c.mask) - 1;
                 c.mask &= c.mask - 1;
@@ -682,10 +706,9 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
 
     fill(0);
     if (!end0) fill(1);
-    Cur cons;
     cons.k = 0; cons.mask = mask0; cons.valid = false; cons.done = false; cons.ch = 0;
     cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.pi = 0;
-    Cur prod = cons;
+    prod = cons;
     next_pair(cons, true);
     next_pair(prod, false);
     uint32_t n_issued = 0, n_done = 0;
@@ -705,7 +728,15 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             ++n_issued;
             if (++prod.ch >= nchunks) next_pair(prod, false);
         }
-        if (n_done == n_issued) __trap();      // cannot happen: the consumer never overtakes the producer
+        if (n_done == n_issued) {              // cannot happen: the consumer never overtakes the producer
+            if (lane == 0)
+                atomicExch(batch_counter + 1, 0xBA00000000000000ull | ((unsigned long long)prod.valid << 55) |
+                                                  ((unsigned long long)prod.done << 54) | ((unsigned long long)end0 << 53) |
+                                                  ((unsigned long long)end1 << 52) | ((unsigned long long)(prod.k & 0xfff) << 40) |
+                                                  ((unsigned long long)(cons.k & 0xfff) << 28) |
+                                                  ((unsigned long long)(filled & 0xfff) << 16) | (n_issued & 0xffffu));
+            return;
+        }
         const uint32_t st = n_done % PL_STAGES;
         mbar_wait(bar0 + 8 * st, (n_done / PL_STAGES) & 1u);
         ++n_done;
@@ -861,7 +892,7 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 // meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
 // range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
 // ============================================================================
-enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_WORDS = 16 };
+enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_WORDS = 16 };
 
 __global__ void __launch_bounds__(128)
 k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
@@ -1515,8 +1546,8 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         }
         per_sm_smem = smem;
     }
-    CK(cudaMemsetAsync(wide_count, 0, 16, s));          // wide count + batch counter (adjacent words of meta[])
-    const int grid = (int)std::min<int64_t>((max_pairs + 31) / 32, (int64_t)c->sm_count * per_sm);
+    CK(cudaMemsetAsync(wide_count, 0, 24, s));          // wide count, batch counter, kernel error word (adjacent words of meta[])
+    const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
     k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
                                                            c->grange.as<uint16_t>(), src, epi,
                                                            c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
@@ -1842,6 +1873,21 @@ int selb200_load_device(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_reg
     return do_load(ctx, n, p, d_regs, true, stored_host, aux_kind, aux_len, d_aux);
 }
 
+// device-resident matrices that become complete piece by piece (in the order of the context's stream)
+int selb200_load_device_begin(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_regs, int aux_kind, int aux_len,
+                              const void* d_aux) {
+    if (n > 0 && !d_regs) return fail(SELB200_EINVAL, "null register matrix");
+    if (aux_kind != SELB200_AUX_NONE && n > 0 && !d_aux) return fail(SELB200_EINVAL, "null aux matrix");
+    return load_begin(ctx, n, p, aux_kind, aux_len, d_regs, d_aux);
+}
+
+int selb200_load_device_rows(selb200_ctx* c, int64_t g0, int64_t count) {
+    if (!c || !c->ld.active || !c->ld.regs_borrowed) return fail(SELB200_ESTATE, "selb200_load_device_rows outside load_device_begin/load_end");
+    if (g0 < 0 || count < 0 || g0 + count > c->n) return fail(SELB200_EINVAL, "rows [%lld,+%lld) outside the matrix", (long long)g0, (long long)count);
+    CK(cudaSetDevice(c->device));
+    return load_chunk(c, g0, count, nullptr, nullptr, nullptr);
+}
+
 int selb200_load_begin(selb200_ctx* ctx, int64_t n, int p, int aux_kind, int aux_len, int64_t* rows_per_chunk) {
     CKR(load_begin(ctx, n, p, aux_kind, aux_len, nullptr, nullptr));
     if (rows_per_chunk) *rows_per_chunk = ctx->ld.rows_per_chunk;
@@ -2024,6 +2070,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                                          c->tile_prefix.as<int32_t>(), nrb + 1, s));
     }
     st.launches += 3;
+    DBG_SYNC(c, "cb bounds + row-block spans + scan");
     cudaEvent_t ev_bounds = nullptr;
 
     // ---- K3: signatures ---------------------------------------------------------------
@@ -2123,6 +2170,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                                                    (long long)c->tile_cap, c->tile_rc.as<int2>(), d_cnt);
         CK(cudaGetLastError());
         st.launches++;
+        DBG_SYNC(c, "tile table");
         if (!ev_bounds) ev_bounds = c->ev();
         if (ranges.empty()) {
             if (crit == SELB200_CRIT_CB) {
@@ -2151,6 +2199,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                                                   c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
             CK(cudaGetLastError());
             st.launches++;
+            DBG_SYNC(c, "smh signatures");
             t_filter.push_back({a0, c->ev()});
         }
         CK(cudaMemsetAsync(d_cnt, 0, 32, s));
@@ -2187,6 +2236,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             }
             CK(cudaGetLastError());
             st.launches++;
+            DBG_SYNC(c, "tile filter");
             cudaEvent_t f1 = c->ev();
             t_filter.push_back({f0, f1});
             if (crit == SELB200_CRIT_SMH_A) {
@@ -2197,6 +2247,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 CK(cudaGetLastError());
                 st.launches++;
             }
+            DBG_SYNC(c, "smh verify");
             // ---- K5 + K6 --------------------------------------------------------------
             cudaEvent_t u0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) t_verify.push_back({f1, u0});
@@ -2208,6 +2259,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 CKR(launch_pair_hist_planes(c, c->pairs.as<uint2>(), (int64_t)pair_lim, c->hist.as<uint32_t>(),
                                             d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches));
             }
+            DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
             k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
                 c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
@@ -2216,6 +2268,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 d_cnt + M_NEAR, near_cap);
             CK(cudaGetLastError());
             st.launches++;
+            DBG_SYNC(c, "estimate + emit");
             cudaEvent_t u2 = c->ev();
             t_union.push_back({u0, u1});
             t_est.push_back({u1, u2});
@@ -2239,6 +2292,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         CK(cudaStreamSynchronize(s));
         // ---- overflow check ------------------------------------------------------------------
         tiles_total = (int64_t)h_fin[M_TILES];
+        if (h_fin[M_KERR]) return fail(SELB200_ECUDA, "internal: union kernel pipeline error %llx", h_fin[M_KERR]);
         pushed = h_fin[M_PUSHED] == 1;
         if (h_fin[M_PUSHED] == 2) return fail(SELB200_ECUDA, "gather: timed out waiting for the root to merge an earlier run");
         bool redo = false;

@@ -56,28 +56,72 @@ class ShardedSketches:
 
     Every rank owns rows [r*per, (r+1)*per) of the file list in (pinned) host memory — the natural
     state after each rank has decoded its share of the sketch files.  `assemble` copies the slice to
-    the rank's GPU over its own PCIe link and all-gathers the slices over NCCL/NVLink (in place:
-    each rank's slice already sits at its offset of the full matrix), so the host->device leg of an
-    R-rank job runs on R links at once instead of through rank 0 (broadcast_sketches)."""
+    the rank's GPU over its own PCIe link and all-gathers the slices over NCCL/NVLink, so the
+    host->device leg of an R-rank job runs on R links at once instead of through rank 0
+    (broadcast_sketches).  The slice travels in `chunks` pieces: piece c+1 is still on the PCIe bus
+    (side stream) while piece c is being all-gathered, in place — the device matrix is laid out
+    piece-major, [piece][rank][rows], so that each all-gather writes one contiguous block.
+    Device row (c*R + r)*rpc + j therefore holds file `row_to_file[row]` = r*per + c*rpc + j; rows past
+    a rank's share are all-zero sketches (cardinality 0: they sort first and pair with nothing)."""
 
-    def __init__(self, n: int, m: int, aux_cols: int, aux_dtype, device, rank: int, world: int):
+    def __init__(self, n: int, m: int, aux_cols: int, aux_dtype, device, rank: int, world: int, chunks: int = 4):
         self.n, self.rank, self.world = n, rank, world
         self.g0, self.rows, self.per = slice_rows(n, rank, world)
-        self.regs = torch.empty((self.per * world, m), dtype=torch.uint8, device=device)
-        self.aux = torch.empty((self.per * world, aux_cols), dtype=aux_dtype, device=device) if aux_cols else None
+        self.chunks = max(1, min(chunks, self.per))
+        self.rpc = (self.per + self.chunks - 1) // self.chunks          # rows per piece
+        self.n_dev = self.chunks * world * self.rpc
+        self.regs = torch.zeros((self.n_dev, m), dtype=torch.uint8, device=device)
+        self.aux = torch.zeros((self.n_dev, aux_cols), dtype=aux_dtype, device=device) if aux_cols else None
+        c, r, j = np.meshgrid(np.arange(self.chunks), np.arange(world), np.arange(self.rpc), indexing="ij")
+        local = c * self.rpc + j                                         # row inside the rank's slice
+        f = r * self.per + local
+        ok = (local < self.per) & (f < n)
+        self.row_to_file = np.where(ok, f, -1).reshape(-1).astype(np.int64)
+        self._copy_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
 
-    def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None):
-        lo = self.rank * self.per
-        mine = self.regs[lo:lo + self.per]
-        mine[:self.rows].copy_(regs_host, non_blocking=True)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.regs, mine)
-        if self.aux is not None:
-            mine_a = self.aux[lo:lo + self.per]
-            mine_a[:self.rows].copy_(aux_host, non_blocking=True)
+    def _piece(self, t: torch.Tensor, c: int):
+        lo = c * self.world * self.rpc
+        return t[lo:lo + self.world * self.rpc], t[lo + self.rank * self.rpc:lo + (self.rank + 1) * self.rpc]
+
+    def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None, on_piece=None):
+        """on_piece(row0, rows): called after the all-gather of each piece has been queued on the current
+        stream (e.g. Selection.load_device_rows, so that the piece is digested while the next one travels)."""
+        cuda = self._copy_stream is not None
+        events = []
+        if cuda:
+            self._copy_stream.wait_stream(torch.cuda.current_stream())   # earlier readers of the matrices are done
+        for c in range(self.chunks):
+            h0, h1 = min(self.rows, c * self.rpc), min(self.rows, (c + 1) * self.rpc)
+            ctx = torch.cuda.stream(self._copy_stream) if cuda else _Null()
+            with ctx:
+                if h1 > h0:
+                    self._piece(self.regs, c)[1][:h1 - h0].copy_(regs_host[h0:h1], non_blocking=True)
+                    if self.aux is not None:
+                        self._piece(self.aux, c)[1][:h1 - h0].copy_(aux_host[h0:h1], non_blocking=True)
+                if cuda:
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    events.append(ev)
+        for c in range(self.chunks):
+            if cuda:
+                torch.cuda.current_stream().wait_event(events[c])
             if self.world > 1:
-                dist.all_gather_into_tensor(self.aux, mine_a)
-        return self.regs[:self.n], (self.aux[:self.n] if self.aux is not None else None)
+                whole, mine = self._piece(self.regs, c)
+                dist.all_gather_into_tensor(whole, mine)
+                if self.aux is not None:
+                    whole, mine = self._piece(self.aux, c)
+                    dist.all_gather_into_tensor(whole, mine)
+            if on_piece is not None:
+                on_piece(c * self.world * self.rpc, self.world * self.rpc)
+        return self.regs, self.aux
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def setup_gather(sel, cap_pairs: int = 1 << 22, root: int = 0):

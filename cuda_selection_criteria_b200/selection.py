@@ -46,7 +46,12 @@ def _is_cuda_tensor(x) -> bool:
 
 
 class Selection:
-    """One selection context on one GPU (one per process per device)."""
+    """One selection context on one GPU (one per process per device).
+
+    `stream`: a cudaStream_t handle (e.g. ``torch.cuda.Stream().cuda_stream``) the library's kernels run
+    on, so that torch copies / NCCL collectives issued on the same stream are ordered with them.  None or
+    0 (the handle of the legacy default stream) = a non-blocking stream owned by the context: device
+    tensors handed to load() must then be complete (synchronise first)."""
 
     def __init__(self, device: int = 0, stream: int | None = None):
         self._L = _lib.lib()
@@ -108,6 +113,32 @@ class Selection:
             _lib.check(self._L.selb200_load_host(self._h, n, p, r_ptr, stp, aux_kind, aux_len, a_ptr))
         self.n = n
         self.p = p
+        self._order = None
+        return self
+
+    def load_device_begin(self, regs, aux=None, aux_kind: int = AUX_NONE, aux_len: int = 0):
+        """Piecewise load of device matrices that are still being filled (CUDA torch tensors, borrowed):
+        follow with load_device_rows(g0, count) for every piece — issued on the context's stream behind the
+        copy / collective that completes those rows — and load_end()."""
+        n, m = int(regs.shape[0]), int(regs.shape[1])
+        p = m.bit_length() - 1
+        if (1 << p) != m or not regs.is_contiguous() or (aux is not None and not aux.is_contiguous()):
+            raise ValueError("register rows must be a power of two wide and the tensors contiguous")
+        if aux_kind == AUX_SMH and aux is not None and not aux_len:
+            aux_len = int(aux.shape[1])
+        if aux_kind == AUX_HLL and aux is not None and not aux_len:
+            aux_len = int(aux.shape[1]).bit_length() - 1
+        self._keep = (regs, aux)
+        _lib.check(self._L.selb200_load_device_begin(self._h, n, p, regs.data_ptr(), aux_kind, aux_len,
+                                                     aux.data_ptr() if aux is not None else None))
+        self.n, self.p, self._order = n, p, None
+        return self
+
+    def load_device_rows(self, g0: int, count: int):
+        _lib.check(self._L.selb200_load_device_rows(self._h, int(g0), int(count)))
+
+    def load_end(self):
+        _lib.check(self._L.selb200_load_end(self._h))
         self._order = None
         return self
 

@@ -144,6 +144,16 @@ int selb200_load_acquire(selb200_ctx* ctx, int64_t g0, int64_t count, uint8_t** 
 int selb200_load_commit(selb200_ctx* ctx);
 int selb200_load_end(selb200_ctx* ctx);
 
+/* Device matrices that become complete piece by piece — e.g. while the other ranks' slices are still
+ * arriving over NVLink.  begin BORROWS the (full-size) device matrices like selb200_load_device; every
+ * selb200_load_device_rows call declares rows [g0, g0+count) complete IN THE ORDER OF THE CONTEXT'S STREAM
+ * (enqueue it behind the copy / collective that fills them, on that stream) and queues their validation,
+ * histograms, cardinalities and bit planes without synchronising; each row must be declared exactly once;
+ * selb200_load_end (above) then sorts.  Stored header cardinalities are not supported on this route. */
+int selb200_load_device_begin(selb200_ctx* ctx, int64_t n, int p, const uint8_t* d_regs, int aux_kind, int aux_len,
+                              const void* d_aux);
+int selb200_load_device_rows(selb200_ctx* ctx, int64_t g0, int64_t count);
+
 /* After a load: cards_sorted[i] = cardinality (double) of the i-th genome in sorted
  * order; order[i] = its index in file-list order.  Either pointer may be NULL. */
 int selb200_get_order(selb200_ctx* ctx, double* cards_sorted, int32_t* order);

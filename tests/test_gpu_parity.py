@@ -278,3 +278,48 @@ def test_host_results_and_both_sort_paths(gpu):
         k_raw = (raw.i.astype(np.int64) << 32) | raw.k
         o = np.argsort(k_raw, kind="stable")
         assert np.array_equal(k_raw[o], (srt.i.astype(np.int64) << 32) | srt.k) and np.array_equal(raw.jaccard[o], srt.jaccard)
+
+
+def test_piecewise_device_load_equals_bulk_load(gpu):
+    """selb200_load_device_begin / _rows / load_end: pieces declared in any order give the bulk result."""
+    plan = synth.make_plan(1300, 9)
+    regs_d = synth.hll(plan, 14, device=gpu)
+    aux_d = synth.smh(plan, 128, device=gpu)
+    import torch
+    torch.cuda.synchronize()
+    with S.Selection(gpu) as sel:
+        sel.load(regs_d, aux_d, AUX_SMH)
+        bulk = sel.run(tau=np.float32(0.85), criterion="smh_a")
+        sel.load_device_begin(regs_d, aux_d, AUX_SMH)
+        for g0, cnt in ((900, 400), (0, 333), (333, 567)):
+            sel.load_device_rows(g0, cnt)
+        sel.load_end()
+        piece = sel.run(tau=np.float32(0.85), criterion="smh_a")
+        assert np.array_equal(bulk.i, piece.i) and np.array_equal(bulk.k, piece.k)
+        assert np.array_equal(bulk.jaccard, piece.jaccard) and np.array_equal(bulk.order, piece.order)
+        # a row left undeclared is an error, not a silent zero
+        sel.load_device_begin(regs_d, aux_d, AUX_SMH)
+        sel.load_device_rows(0, 1000)
+        with pytest.raises(S.SelB200Error):
+            sel.load_end()
+
+
+def test_wide_value_range_pairs_take_the_byte_kernel(gpu):
+    """Genomes with a register far above the rest (value window wider than 32) make every pair they are in
+    'wide': those pairs leave the bit-plane union kernel for the byte kernel, whole batches of them in a
+    row.  Results stay the oracle's, run after run (the batch bookkeeping once lost its place here)."""
+    plan = synth.make_plan(1500, 31)
+    regs = synth.hll(plan, 14).copy()
+    aux = synth.smh(plan, 128)
+    sizes = np.bincount(plan.cluster)
+    big = np.argsort(sizes)[-6:]                      # members of the six largest clusters
+    odd = np.concatenate([np.flatnonzero(plan.cluster == c)[:3] for c in big])
+    regs[odd, 7] = 45                                 # legal for p=14 (<= 51), far above everything else
+    ora = O.select(regs, 14, "smh_a", np.float32(0.8), aux=aux, threads=8)
+    assert len(ora["i"]) > 0
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        for _ in range(12):
+            compare(sel.run(tau=np.float32(0.8), criterion="smh_a"), ora, 0.8)
+    res = run_gpu(regs, None, "cb", 0.97, gpu)        # dense list: long runs of wide pairs
+    compare(res, O.select(regs, 14, "cb", np.float32(0.97), threads=8), 0.97)

@@ -137,9 +137,15 @@ n = 11
 full = torch.arange(n * 16, dtype=torch.int64).reshape(n, 16)
 g0, rows, per = sdist.slice_rows(n, rank, world)
 assert sum(sdist.slice_rows(n, r, world)[1] for r in range(world)) == n
-sh = sdist.ShardedSketches(n, 16, 4, torch.int64, "cpu", rank, world)
-r_all, a_all = sh.assemble(full[g0:g0 + rows].to(torch.uint8), full[g0:g0 + rows, :4].contiguous())
-assert torch.equal(r_all, full.to(torch.uint8)) and torch.equal(a_all, full[:, :4])
+for chunks in (1, 2, 4):
+    sh = sdist.ShardedSketches(n, 16, 4, torch.int64, "cpu", rank, world, chunks=chunks)
+    r_all, a_all = sh.assemble(full[g0:g0 + rows].to(torch.uint8), full[g0:g0 + rows, :4].contiguous())
+    f = sh.row_to_file
+    assert sorted(f[f >= 0].tolist()) == list(range(n))            # every file lands in exactly one row
+    real = torch.from_numpy(f >= 0)
+    src = torch.from_numpy(np.where(f >= 0, f, 0))
+    assert torch.equal(r_all[real], full.to(torch.uint8)[src][real]) and torch.equal(a_all[real], full[:, :4][src][real])
+    assert int(r_all[~real].sum()) == 0                            # padding rows are empty sketches
 # shard ranges tile the list exactly
 T = 1001
 tiles = sorted(t for r in range(world) for t in sdist.shard_tiles(T, r, world))
