@@ -892,7 +892,7 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 // meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
 // range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
 // ============================================================================
-enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_WORDS = 16 };
+enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_UNIT = 10, M_WORDS = 16 };
 
 __global__ void __launch_bounds__(128)
 k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
@@ -1200,8 +1200,9 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
                   const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
-                  unsigned long long pair_cap) {
+                  unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
     extern __shared__ __align__(1024) uint32_t hist_dyn[];   // 2 x [nbins][64 threads]
+    __shared__ int s_unit;
     const int nbins = 64 - p_aux + 2;
     uint32_t* hist0 = hist_dyn;
     uint32_t* hist1 = hist_dyn + nbins * 64;
@@ -1211,8 +1212,14 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
     for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
     __syncwarp();
     const int uend = tw.count() * 4;
-    // persistent CTAs over the shard's (tile, quarter) units
-    for (int unit = tw.j0 * 4 + (int)blockIdx.x; unit < uend; unit += (int)gridDim.x) {
+    // persistent CTAs claim (tile, quarter) units from a device counter: units on the edge of the band hold
+    // few pairs, full ones 4096, so a static deal leaves a long tail
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_unit = tw.j0 * 4 + (int)atomicAdd(unit_counter, 1ull);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= uend) break;
         const int2 rc = tw.tile(unit >> 2);
         const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
         // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
@@ -2210,6 +2217,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             const int64_t nt = (int64_t)rg.second - rg.first;     // upper bound when the end is open
             const TileWalk tw{c->tile_rc.as<int2>(), d_cnt, (long long)c->tile_cap, prm->shard, n_shards, rg.first, rg.second};
             CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs of this range
+            if (crit >= SELB200_CRIT_HLL_A) CK(cudaMemsetAsync(d_cnt + M_UNIT, 0, 8, s));
             cudaEvent_t f0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) {
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
@@ -2226,13 +2234,13 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 k_tile_filter_hll<0><<<grid, 64, hll_smem, s>>>(
                     c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
-                    (unsigned long long)PAIR_CAP);
+                    (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
             } else {
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 k_tile_filter_hll<1><<<grid, 64, hll_smem, s>>>(
                     c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n,
                     c->e_sorted.as<unsigned long long>(), tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
-                    (unsigned long long)PAIR_CAP);
+                    (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
             }
             CK(cudaGetLastError());
             st.launches++;
