@@ -85,7 +85,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # SELB200_LIB: another build of the same library (kernel-variant A/B measurements)
+    return os.environ.get("SELB200_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 def lib() -> C.CDLL:

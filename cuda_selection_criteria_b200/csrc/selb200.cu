@@ -657,6 +657,8 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         int ch;
         uint32_t rx, ry, ix, iy, gm;
         long long pi;
+        const uint8_t* ga;     // planes of the two genomes (producer side)
+        const uint8_t* gb;
     };
     Cur cons, prod;
     auto next_pair = [&](Cur& c, bool is_cons) {
@@ -680,6 +682,10 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
                 c.iy = __shfl_sync(FULL, odd ? d_iy1 : d_iy0, j);
                 c.gm = __shfl_sync(FULL, odd ? d_gm1 : d_gm0, j);
                 c.pi = (odd ? base1 : base0) + j;
+                if (!is_cons) {
+                    c.ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes;
+                    c.gb = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.ry * genome_bytes;
+                }
                 c.ch = 0;
                 c.valid = true;
                 return;
@@ -695,8 +701,8 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     auto issue = [&](const Cur& c, uint32_t n_issued) {      // lane 0: two bulk copies into the next stage
         const uint32_t st = n_issued % PL_STAGES;
         const uint32_t dst = smem0 + st * 2 * chunk_bytes, bar = bar0 + 8 * st;
-        const uint8_t* ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes + (size_t)c.ch * chunk_bytes;
-        const uint8_t* gb = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.ry * genome_bytes + (size_t)c.ch * chunk_bytes;
+        const uint8_t* ga = c.ga + (uint32_t)c.ch * chunk_bytes;
+        const uint8_t* gb = c.gb + (uint32_t)c.ch * chunk_bytes;
         // window 0 (values < 32): plane 5 is zero and stays behind — 5/6 of the bytes
         const uint32_t nbytes = (c.gm & 0xffu) == 0u ? chunk_bytes / 6u * 5u : chunk_bytes;
         mbar_expect_tx(bar, 2 * nbytes);
@@ -708,6 +714,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     if (!end0) fill(1);
     cons.k = 0; cons.mask = mask0; cons.valid = false; cons.done = false; cons.ch = 0;
     cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.pi = 0;
+    cons.ga = cons.gb = nullptr;
     prod = cons;
     next_pair(cons, true);
     next_pair(prod, false);
