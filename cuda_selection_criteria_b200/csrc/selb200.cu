@@ -215,6 +215,7 @@ struct selb200_ctx {
     } g;
     DevBuf g_push, g_merged;
     DevBuf row_cnt, row_off, sort_tmp;
+    DevBuf auxP, agrange;                // bit planes / register ranges of the auxiliary HLLs (sorted order)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
     int chunk_regs = 0;
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
@@ -1277,6 +1278,218 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 }
 
 // ============================================================================
+// K4'' : hll_a / hll_an tile filter on BIT PLANES of the auxiliary sketches (p_aux >= 6).
+// Same tile walk, same thread-per-pair shape (lane = column, row word = broadcast), same MLE + criterion
+// as k_tile_filter_hll; the union histogram of a pair is built with the logic of k_pair_hist_planes
+// (LOP3 borrow-chain max, 3+3-bit decode, carry-save counting) instead of 2^p_aux shared-memory
+// read-modify-writes, and written once into the thread's shared-memory column for the estimator.
+//   auxP[(plane*nw + w)*npad + g] : word w (32 registers) of a plane of the g-th sorted genome
+//   agrange[g]                    : min | max<<8 of that genome's auxiliary registers
+// The 32 pairs of a warp step share one 32-value window (their genomes sit within the CB band of each
+// other, so their register ranges coincide); a step whose pairs do not fit one window takes the byte
+// path of k_tile_filter_hll for its pairs.
+// ============================================================================
+#ifndef HLLP_MIN_CTAS
+#define HLLP_MIN_CTAS 8
+#endif
+
+__global__ void __launch_bounds__(256)
+k_aux_planes(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, long long npad,
+             int p_aux, uint32_t* __restrict__ auxP) {
+    const int nw = (1 << p_aux) >> 5;
+    const long long total = n * nw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx / n);
+        const long long g = idx - (long long)w * n;
+        const uint4* src = reinterpret_cast<const uint4*>(aux + ((size_t)order[g] << p_aux) + (size_t)w * 32);
+        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+        const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m |= ((((wd[q] >> b) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
+            auxP[((size_t)b * nw + w) * npad + g] = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_aux_range(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, int p_aux,
+            uint16_t* __restrict__ agrange) {
+    // one warp per genome: smallest / largest register value
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= n) return;
+    const uint8_t* row = aux + ((size_t)order[g] << p_aux);
+    int vmin = 255, vmax = 0;
+    for (int j = lane; j < (1 << p_aux); j += 32) { const int v = row[j]; vmin = min(vmin, v); vmax = max(vmax, v); }
+    for (int o = 16; o; o >>= 1) {
+        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) agrange[g] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
+}
+
+// all word pairs of one (row, 32 columns) step for window G0: S / C2 end as the per-value carry-save state
+template <int G0>
+__device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
+                                                long long npad, int nw, uint32_t gmask, uint32_t (&x)[32]) {
+    uint32_t S[32], C2[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
+#pragma unroll 1
+    for (int w = 0; w < nw; w += 2) {
+        uint32_t M[2][6];
+        {
+            uint32_t a[2][6], b[2][6];
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) {
+                const size_t o0 = ((size_t)pl * nw + w) * (size_t)npad, o1 = o0 + (size_t)npad;
+                a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
+                b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
+            }
+            uint32_t lt0 = 0u, lt1 = 0u;
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) {
+                lt0 = lop3<0x8E>(a[0][pl], b[0][pl], lt0);
+                lt1 = lop3<0x8E>(a[1][pl], b[1][pl], lt1);
+            }
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) {
+                M[0][pl] = lop3<0xCA>(lt0, b[0][pl], a[0][pl]);
+                M[1][pl] = lop3<0xCA>(lt1, b[1][pl], a[1][pl]);
+            }
+        }
+        uint32_t L[2][8];
+#pragma unroll
+        for (int ws = 0; ws < 2; ++ws) {
+            L[ws][0] = lop3<0x01>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][1] = lop3<0x02>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][2] = lop3<0x04>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][3] = lop3<0x08>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][4] = lop3<0x10>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][5] = lop3<0x20>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][6] = lop3<0x40>(M[ws][2], M[ws][1], M[ws][0]);
+            L[ws][7] = lop3<0x80>(M[ws][2], M[ws][1], M[ws][0]);
+        }
+#define SELB_AUX_GROUP(T)                                                                                 \
+        if (gmask & (1u << T)) {                                                                          \
+            const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
+            const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
+            uint32_t m0[8], m1[8], kk[8];                                                                 \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);                 \
+        }
+        SELB_AUX_GROUP(0)
+        SELB_AUX_GROUP(1)
+        SELB_AUX_GROUP(2)
+        SELB_AUX_GROUP(3)
+#undef SELB_AUX_GROUP
+    }
+#pragma unroll
+    for (int v = 0; v < 32; ++v) x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]);
+}
+
+template <int G0>
+__device__ __forceinline__ void aux_plane_hist(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
+                                               long long npad, int nw, uint32_t gmask, uint32_t* __restrict__ hcol,
+                                               int nbins) {
+    uint32_t x[32];
+    aux_plane_pairs<G0>(rowp, colp, npad, nw, gmask, x);
+    // the thread's histogram column: zeros outside the window, the counts inside
+    for (int b = 0; b < 8 * G0; ++b) hcol[b * 64] = 0u;
+#pragma unroll
+    for (int v = 0; v < 32; ++v)
+        if (8 * G0 + v < nbins) hcol[(8 * G0 + v) * 64] = x[v];
+    for (int b = 8 * G0 + 32; b < nbins; ++b) hcol[b * 64] = 0u;
+}
+
+template <int AN>
+__global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
+k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __restrict__ agrange,
+                         const uint32_t* __restrict__ auxT, long long npad, int p_aux, TileWalk tw,
+                         const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                         const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
+                         uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
+                         unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
+    extern __shared__ __align__(1024) uint32_t hist_dyn[];   // [nbins][64 threads]
+    __shared__ int s_unit;
+    const int nbins = 64 - p_aux + 2;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
+    const int nw = (1 << p_aux) >> 5;
+    const int words = (1 << p_aux) >> 2;
+    uint32_t* hcol = hist_dyn + t;
+    const uint32_t bias0 = hist_bias(hist_dyn);
+    const int uend = tw.count() * 4;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_unit = tw.j0 * 4 + (int)atomicAdd(unit_counter, 1ull);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= uend) break;
+        const int2 rc = tw.tile(unit >> 2);
+        const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
+        // 32 rows x 4 column groups = 128 steps, split over the 2 warps
+        for (int item = (int)w; item < 128; item += 2) {
+            const int i = r0 + (item >> 2);
+            const int k = c0 + (item & 3) * 32 + (int)lane;
+            if (i >= n) continue;
+            const bool v = k < n && k >= lo[i] && k <= hi[i];
+            if (!__any_sync(0xffffffffu, v)) continue;
+            const int kc = (int)min((long long)k, npad - 1);
+            // common value window of the step's pairs
+            const uint32_t ra = agrange[i], rb = agrange[min(kc, n - 1)];
+            int vlo = v ? max((int)(ra & 0xff), (int)(rb & 0xff)) : 255;
+            int vhi = v ? max((int)(ra >> 8), (int)(rb >> 8)) : 0;
+            for (int o = 16; o; o >>= 1) {
+                vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, o));
+                vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
+            }
+            const int g0 = min(vlo >> 3, 4);
+            if ((vhi >> 3) <= g0 + 3) {
+                uint32_t gmask = 0;
+                for (int tt = 0; tt < 4; ++tt)
+                    if ((g0 + tt) >= (vlo >> 3) && (g0 + tt) <= (vhi >> 3)) gmask |= 1u << tt;
+                const uint32_t* rowp = auxP + i;
+                const uint32_t* colp = auxP + kc;
+                switch (g0) {
+                    case 0: aux_plane_hist<0>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 1: aux_plane_hist<1>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 2: aux_plane_hist<2>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 3: aux_plane_hist<3>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    default: aux_plane_hist<4>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                }
+            } else {
+                // register ranges too far apart for one window: byte path (shared-memory counters)
+                for (int b = 0; b < nbins; ++b) hcol[b * 64] = 0u;
+                const uint32_t* colp = auxT + kc;
+                const uint32_t* row0 = auxT + i;
+                for (int j = 0; j < words; ++j) {
+                    const uint32_t m0 = max4_lt128(__ldg(row0 + (size_t)j * npad), __ldg(colp + (size_t)j * npad)) + bias0;
+                    hist_inc2<0, 1>(m0, tb);
+                    hist_inc2<2, 3>(m0, tb);
+                }
+            }
+            bool pass = false;
+            if (v) {
+                bool stopped = false;
+                const StopHll stop{tau, e[i], e[k], zs, order_n, AN};
+                const double tu = selb::ertl_mle(hcol, p_aux, 64, stop, &stopped);
+                pass = !stopped && stop.crit(tu);
+            }
+            if (pass) {
+                const unsigned long long slot = warp_claim(pair_count);
+                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+            }
+        }
+    }
+}
+
+// ============================================================================
 // K6: union estimate -> Jaccard -> tau test -> emit
 //   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
 // ============================================================================
@@ -1783,6 +1996,21 @@ int load_end(selb200_ctx* c) {
         k_aux_transpose<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_aux), c->order_dev.as<int32_t>(), n,
                                              c->npad, row_words, c->auxT.as<uint32_t>());
         CK(cudaGetLastError());
+        if (aux_len >= 6) {       // bit planes for k_tile_filter_hll_planes (two 32-register words per step)
+            const int nw = (1 << aux_len) >> 5;
+            CKR(c->auxP.ensure((size_t)6 * nw * c->npad * 4));
+            CKR(c->agrange.ensure((size_t)c->npad * sizeof(uint16_t)));
+            CK(cudaMemsetAsync(c->auxP.p, 0, (size_t)6 * nw * c->npad * 4, s));
+            CK(cudaMemsetAsync(c->agrange.p, 0, (size_t)c->npad * sizeof(uint16_t), s));
+            const int g2 = (int)std::min<int64_t>((n * nw + 255) / 256, (int64_t)c->sm_count * 16);
+            k_aux_planes<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n, c->npad,
+                                            aux_len, c->auxP.as<uint32_t>());
+            CK(cudaGetLastError());
+            k_aux_range<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux),
+                                                                         c->order_dev.as<int32_t>(), n, aux_len,
+                                                                         c->agrange.as<uint16_t>());
+            CK(cudaGetLastError());
+        }
     }
     CK(cudaStreamSynchronize(s));
     c->loaded = true;
@@ -1859,7 +2087,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -2100,16 +2328,25 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
     size_t hll_smem = 0;
     int hll_grid = 0;
+    // SELB200_HLLFILTER=bytes keeps the shared-memory-counter filter (A/B measurements); sketches below 64
+    // registers have no bit planes
+    static const bool hll_bytes_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "bytes"); }();
+    const bool hll_planes = crit >= SELB200_CRIT_HLL_A && c->aux_len >= 6 && !hll_bytes_env;
     if (crit >= SELB200_CRIT_HLL_A) {
-        hll_smem = (size_t)2 * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
+        hll_smem = (size_t)(hll_planes ? 1 : 2) * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
         static bool carve = false;
         if (!carve) {
             cudaFuncSetAttribute(k_tile_filter_hll<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_tile_filter_hll<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_tile_filter_hll_planes<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_tile_filter_hll_planes<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carve = true;
         }
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem) != cudaSuccess || per_sm < 1) {
+        const cudaError_t oe = hll_planes
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<0>, 64, hll_smem)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem);
+        if (oe != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 4;
         }
@@ -2236,6 +2473,18 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
                 k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                  d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
+            } else if (hll_planes) {
+                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
+                if (crit == SELB200_CRIT_HLL_A)
+                    k_tile_filter_hll_planes<0><<<grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
+                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
+                else
+                    k_tile_filter_hll_planes<1><<<grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
+                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
             } else if (crit == SELB200_CRIT_HLL_A) {
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 k_tile_filter_hll<0><<<grid, 64, hll_smem, s>>>(
