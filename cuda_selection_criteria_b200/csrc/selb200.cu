@@ -449,10 +449,16 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src s
 // one warp per CTA, ~9 CTAs per SM.
 // Pairs whose value range does not fit a 32-value window (never seen on real sketches) go to a
 // "wide" list and through the byte kernel.
-// layout: genome g at planes + g * 6 * m/8 bytes; chunk c (2048 registers, or m if smaller) holds its
+// layout: genome g at planes + g * 6 * m/8 bytes; chunk c (PL_CHUNK_REGS registers, or m if smaller) holds its
 //         6 planes back to back: [chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r
 // ============================================================================
-constexpr int PL_CHUNK_REGS = 2048;
+// chunk / ring geometry, measured at n=100k (511 521 pairs): 2048 regs x 4 stages x 16 CTAs/SM 1.94 ms,
+// 4096 x 3 x 12: 2.02 ms, 8192 x 2 x 9: 1.87 ms (fewer, longer steps: less pipeline control per register)
+#ifndef PL_CHUNK_REGS_V
+#define PL_CHUNK_REGS_V 8192
+#endif
+constexpr int PL_CHUNK_REGS = PL_CHUNK_REGS_V;
+constexpr int PL_NQ = PL_CHUNK_REGS / 64;   // uint2 per plane of a full chunk
 
 __global__ void __launch_bounds__(256)
 k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, int chunk_regs,
@@ -516,7 +522,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         : "memory");
 }
 
-// One chunk (<= 2048 registers: 64 words per plane) against the running carry-save state.  Lane q holds
+// One chunk (<= PL_CHUNK_REGS registers) against the running carry-save state.  Per step, lane q holds
 // two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so
 // that eight independent dependency chains are in flight (LOP3 latency 4 at one issue per 2 clocks).
 template <int G0, int NQ>   // NQ > 0: uint2 per plane known at compile time (full 2048-register chunks)
@@ -584,12 +590,15 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
 // One warp per CTA.  Work comes in batches of 32 consecutive pairs claimed from a device counter (dynamic
 // balance, no tail): each lane fetches the descriptor of one pair of the batch (rows through `order`, value
 // window from grange), so the dependent global loads are paid once per 32 pairs and the warp then reads
-// descriptors with shuffles.  The pairs' planes flow chunk by chunk (2048 registers = 2 x 1.5 KiB) through a
+// descriptors with shuffles.  The pairs' planes flow chunk by chunk (8192 registers = 2 x 6 KiB) through a
 // ring of PL_STAGES shared-memory stages: lane 0 keeps PL_STAGES-1 bulk copies (TMA) in flight ahead of
 // the chunk being counted, across pair and batch boundaries.
-constexpr int PL_STAGES = 4;
+#ifndef PL_STAGES_V
+#define PL_STAGES_V 2
+#endif
+constexpr int PL_STAGES = PL_STAGES_V;
 #ifndef PL_MIN_CTAS
-#define PL_MIN_CTAS 16
+#define PL_MIN_CTAS 9
 #endif
 
 template <class Epi>
@@ -752,13 +761,13 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         const uint2* pb = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes + chunk_bytes);
         const int g0 = (int)(cons.gm & 0xffu);
         const uint32_t gmask = cons.gm >> 8;
-        if (nq == 32) {
+        if (nq == PL_NQ) {
             switch (g0) {
-                case 0: plane_chunk<0, 32>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 1: plane_chunk<1, 32>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 2: plane_chunk<2, 32>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 3: plane_chunk<3, 32>(pa, pb, nq, lane, gmask, S, C2); break;
-                default: plane_chunk<4, 32>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 0: plane_chunk<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 1: plane_chunk<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 2: plane_chunk<2, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                case 3: plane_chunk<3, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                default: plane_chunk<4, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
             }
         } else {
             switch (g0) {
