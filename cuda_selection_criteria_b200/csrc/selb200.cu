@@ -982,23 +982,32 @@ __device__ __forceinline__ uint32_t band_sig16(const uint64_t* v, int n_rows) {
     return (uint32_t)(h >> 48);
 }
 
-__global__ void k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long npad, int m_aux,
-                                 int n_rows, int n_bands, uint32_t* __restrict__ sigR, uint32_t* __restrict__ sigC) {
+__global__ void __launch_bounds__(256)
+k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long npad, int m_aux,
+                 int n_rows, int n_bands, uint32_t* __restrict__ sigR, uint32_t* __restrict__ sigC) {
+    // thread = (genome, band), band fastest: a warp reads consecutive bands of one genome, i.e. one contiguous
+    // run of its sketch; lane pairs then pack two bands into a word
     const int nw = (n_bands + 1) >> 1;
-    const long long total = n * nw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(idx / n);
-        const long long g = idx - (long long)w * n;
-        const uint64_t* v = aux_sorted + (size_t)g * m_aux;
-        const uint32_t s0 = band_sig16(v + (size_t)(2 * w) * n_rows, n_rows);
-        uint32_t r1 = 0, c1 = 1;
-        if (2 * w + 1 < n_bands) {
-            r1 = band_sig16(v + (size_t)(2 * w + 1) * n_rows, n_rows);
-            c1 = (0u - r1) & 0xffffu;
+    const int nb2 = nw * 2;                                    // bands rounded up to even (pad band never matches)
+    const long long total = n * nb2;
+    const long long stride = (long long)gridDim.x * blockDim.x;          // even: lane pairs stay together
+    for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 - (threadIdx.x & 31) < total;
+         idx0 += stride) {
+        const bool live = idx0 < total;
+        const long long g = live ? idx0 / nb2 : 0;
+        const int b = live ? (int)(idx0 - g * nb2) : 0;
+        uint32_t sig = 0;
+        const bool real = live && b < n_bands;
+        if (real) sig = band_sig16(aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows, n_rows);
+        const uint32_t other = __shfl_down_sync(0xffffffffu, sig, 1);
+        const bool other_real = __shfl_down_sync(0xffffffffu, (int)real, 1) != 0;
+        if (live && !(b & 1)) {
+            const uint32_t r1 = other_real ? other : 0u;
+            const uint32_t c1 = other_real ? ((0u - other) & 0xffffu) : 1u;   // pad half: row 0, column 1
+            const int w = b >> 1;
+            sigR[(size_t)w * npad + g] = sig | (r1 << 16);
+            sigC[(size_t)w * npad + g] = ((0u - sig) & 0xffffu) | (c1 << 16);
         }
-        sigR[(size_t)w * npad + g] = s0 | (r1 << 16);
-        sigC[(size_t)w * npad + g] = ((0u - s0) & 0xffffu) | (c1 << 16);
     }
 }
 
