@@ -1,0 +1,55 @@
+"""-m gpu: the bit-plane kernels against the byte kernels they replaced, at sizes the CPU oracle would take
+minutes for.  Both forms compute the same integer histograms, so pair lists, Jaccard bits and stage counts
+must be identical (SELB200_UNION=bytes / SELB200_HLLFILTER=bytes select the byte forms at library load)."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import hashlib, json, os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import cuda_selection_criteria_b200 as S
+from cuda_selection_criteria_b200 import synth
+from cuda_selection_criteria_b200.selection import AUX_HLL, AUX_SMH
+out = {}
+plan = synth.make_plan(20000, 1002)
+regs = synth.hll(plan, 14, device=0)
+for crit, aux, kind, tau in (("smh_a", synth.smh(plan, 128, device=0), AUX_SMH, 0.9),
+                             ("smh_a", synth.smh(plan, 128, device=0), AUX_SMH, 0.75),
+                             ("hll_a", synth.hll(plan, 10, synth.TAG_AUX_HLL, device=0), AUX_HLL, 0.9),
+                             ("hll_an", synth.hll(plan, 8, synth.TAG_AUX_HLL, device=0), AUX_HLL, 0.85)):
+    with S.Selection(0) as sel:
+        sel.load(regs, aux, kind)
+        r = sel.run(tau=np.float32(tau), criterion=crit)
+    h = hashlib.sha256(r.i.tobytes() + r.k.tobytes() + r.jaccard.tobytes()).hexdigest()
+    out[f"{crit}@{tau}"] = [h, int(r.i.size), int(r.stats["pairs_cb"]), int(r.stats["pairs_aux"]), int(r.stats["pairs_near"])]
+print("RESULT " + json.dumps(out))
+"""
+
+
+def _run(env_extra, tmp_path):
+    script = tmp_path / "ab.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ)
+    env.pop("SELB200_UNION", None)
+    env.pop("SELB200_HLLFILTER", None)
+    env.update(env_extra)
+    r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [x for x in r.stdout.splitlines() if x.startswith("RESULT ")][-1]
+    return json.loads(line[7:])
+
+
+def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
+    planes = _run({}, tmp_path)
+    by = _run({"SELB200_UNION": "bytes", "SELB200_HLLFILTER": "bytes"}, tmp_path)
+    assert planes == by
+    assert all(v[1] > 1000 for v in planes.values())          # thousands of emitted pairs in every case
