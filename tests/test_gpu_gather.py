@@ -118,3 +118,31 @@ def test_gather_two_processes_cuda_ipc(gpu, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_gather_after_multi_range_pass(gpu):
+    """CB-only with more than 8 Mi band pairs per rank: the pass runs as several tile ranges, so the push into
+    the root's landing zone is queued after the pass is known to be final (not the optimistic form)."""
+    plan = synth.make_plan(9000, 5)
+    regs = synth.hll(plan, 14, device=gpu)
+    import torch
+    torch.cuda.synchronize()
+    tau = np.float32(0.5)
+    ctxs = [S.Selection(gpu) for _ in range(2)]
+    try:
+        for c in ctxs:
+            c.load(regs)
+        whole = ctxs[0].run(tau=tau, criterion="cb")
+        assert whole.stats["batches"] >= 2 and whole.stats["pairs_aux"] > (8 << 20)
+        handle = ctxs[0].gather_create(1 << 21)
+        for r, c in enumerate(ctxs):
+            c.gather_attach(r, 2, handle)
+        for _ in range(2):
+            part = ctxs[1].run(tau=tau, criterion="cb", gather=True)
+            root = ctxs[0].run(tau=tau, criterion="cb", gather=True)
+            assert part.stats["batches"] >= 2 or root.stats["batches"] >= 2
+            assert np.array_equal(root.i, whole.i) and np.array_equal(root.k, whole.k)
+            assert np.array_equal(root.jaccard, whole.jaccard)
+    finally:
+        for c in ctxs:
+            c.close()
