@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=100_000, help="genomes (default: config C4)")
+    ap.add_argument("--n", "--genomes", dest="n", type=int, default=100_000,
+                    help="genomes (default: config C4); use --genomes under torchrun, whose own parser claims --n")
     ap.add_argument("--criterion", default="smh_a", choices=["cb", "smh_a", "hll_a", "hll_an"])
     ap.add_argument("--tau", type=float, default=0.9)
     ap.add_argument("--aux-bytes", type=int, default=1024)
