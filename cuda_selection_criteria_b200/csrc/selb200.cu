@@ -3,25 +3,29 @@
 // Replaces, behind include/selb200.h, the hot loop of the reference
 // (src/selection.cpp:241-291 and its CUDA restatement src/selection_kernels.cu:13-117):
 //
-//   load    : chunked H2D overlapped with k_max_byte (validation), k_pair_hist (per-genome histograms)
-//             and k_genome_cards (Ertl MLE); device radix sort by cardinality, with the host
-//             std::sort of selection.cpp:251-256 as the exact fallback when two cardinalities tie;
-//             auxiliary sketches re-laid out in sorted order for the tile kernels
+//   load    : chunked H2D overlapped with k_max_byte (validation), k_pair_hist (per-genome histograms),
+//             k_genome_cards (Ertl MLE) and k_planes_from_bytes (bit planes of the registers); device
+//             radix sort by cardinality, with the host std::sort of selection.cpp:251-256 as the exact
+//             fallback when two cardinalities tie; auxiliary sketches re-laid out in sorted order
+//             (k_gather_rows / k_aux_transpose / k_aux_planes)
 //   run     : K2  k_cb_bounds        CB band [lo(i),hi(i)] per sorted row (binary search, fp64 div)
-//                 k_tile_table       (row block, column block) of every 128x128 tile of the band
+//                 k_rowblock_span + scan + k_tile_table   the band's 128x128 tile list, built on the device
 //             K3  k_smh_signatures   16-bit signature per (genome, LSH band), two bands per word, transposed
-//             K4  k_tile_filter_smh  8x8 register micro-tiles: one VIADDMNMX.U16x2 per two bands
+//             K4  k_tile_filter_smh  8x8 register micro-tiles: one VIADDMNMX.U16x2 per two bands, cp.async ring
 //                 k_smh_verify       exact uint64 compare of the signature-matching band(s)
-//                 k_tile_filter_hll  hll_a / hll_an: thread-per-pair aux-HLL union histogram + MLE
+//                 k_tile_filter_hll_planes  hll_a / hll_an: thread-per-pair aux-HLL union histogram on bit
+//                                    planes + MLE (k_tile_filter_hll: the byte form, p_aux < 6)
 //                 k_tile_enum        CB-only: every pair of the band
-//             K5  k_pair_hist        warp-per-pair HLL-14 register max + 52/64-bin histogram
+//             K5  k_pair_hist_planes warp-per-pair HLL-14 register max + histogram on bit planes (LOP3 carry-
+//                                    save logic, TMA staging); k_pair_hist: the byte form (load, wide pairs)
 //             K6  k_estimate_emit    Ertl MLE of the union, Jaccard, tau test, warp-aggregated emit
-//             K7  cub radix sort     (i,k) order of the reference's stdout
-//   Everything after K4 reads its work count from device memory, so a run has two host syncs
-//   (after K2 for the tile list, and at the end).
+//                 k_gather_*         multi-GPU: the list goes straight into the root GPU's memory (peer stores)
+//             K7  k_rowsort_*        (i,k) order of the reference's stdout (bucket by row; radix sort if dense)
+//   Every kernel after K2 reads its work count from device memory, so a run has one host sync before
+//   the sort and one at the end.
 //
-// No tensor cores: the path is byte/integer work bounded by shared-memory and L2/HBM
-// bandwidth.  Compile with -fmad=false (see estimators.cuh).
+// No tensor cores: the path is byte/integer work bounded by the integer ALU pipe, shared-memory
+// wavefronts and L2/HBM bandwidth.  Compile with -fmad=false (see estimators.cuh).
 #include "../../include/selb200.h"
 
 #include <cuda_runtime.h>
@@ -99,23 +103,6 @@ struct DevBuf {
         cap = want;
         return SELB200_OK;
     }
-    // grow keeping the first `keep` bytes
-    int grow_keep(size_t bytes, size_t keep, cudaStream_t s) {
-        if (bytes <= cap && p) return SELB200_OK;
-        void* np = nullptr;
-        size_t want = std::max(bytes, cap * 2);
-        cudaError_t e = cudaMalloc(&np, want);
-        if (e != cudaSuccess) return fail(SELB200_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-        if (p && keep) {
-            e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) { cudaFree(np); return fail(SELB200_ECUDA, "grow copy failed: %s", cudaGetErrorString(e)); }
-        }
-        if (p) cudaFree(p);
-        p = np;
-        cap = want;
-        return SELB200_OK;
-    }
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
@@ -187,7 +174,6 @@ struct selb200_ctx {
     // run scratch (grow-only)
     DevBuf lo, hi, tile_prefix, tile_cb0, tile_rc, sigT, cand, pairs, hist, counters, cub_tmp;
     DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
-    std::vector<int32_t> h_lo, h_hi;
     int64_t out_count = 0, near_count = 0;
     int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
     LoadState ld;
