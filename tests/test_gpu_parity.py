@@ -323,3 +323,19 @@ def test_wide_value_range_pairs_take_the_byte_kernel(gpu):
             compare(sel.run(tau=np.float32(0.8), criterion="smh_a"), ora, 0.8)
     res = run_gpu(regs, None, "cb", 0.97, gpu)        # dense list: long runs of wide pairs
     compare(res, O.select(regs, 14, "cb", np.float32(0.97), threads=8), 0.97)
+
+
+@pytest.mark.parametrize("criterion", ["hll_a", "hll_an"])
+@pytest.mark.parametrize("p_aux", [4, 5, 6, 7, 9, 12])
+def test_auxiliary_hll_precisions(gpu, criterion, p_aux):
+    """Every auxiliary precision the reference's sigma table distinguishes (criteria_sketch.hpp:7-20: p = 4..7
+    have their own constants) plus a large one; p_aux < 6 takes the byte filter, the rest the bit-plane
+    filter with 2, 4, 16 and 128 words per plane."""
+    plan = synth.make_plan(700, 100 + p_aux)
+    regs = synth.hll(plan, 14)
+    aux = synth.hll(plan, p_aux, synth.TAG_AUX_HLL)
+    tau = 0.8
+    res = run_gpu(regs, aux, criterion, tau, gpu)
+    ora = O.select(regs, 14, criterion, np.float32(tau), aux=aux, threads=8)
+    assert ora["stage"][2] > 0
+    compare(res, ora, tau)
