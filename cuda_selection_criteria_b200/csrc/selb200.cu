@@ -112,7 +112,7 @@ struct DevBuf {
 };
 
 constexpr int TILE = 128;          // pair tile edge (rows x cols of the sorted order)
-constexpr int SIG_CHUNK = 16;      // LSH bands staged per shared-memory pass
+constexpr int SIG_CHUNK = 8;       // signature words (2 LSH bands each) staged per shared-memory item
 constexpr int64_t PAIR_CAP = 8ll << 20;   // pairs per filter->union pass (list 64 MB, histograms 2 GB)
 constexpr int SNAP_MAX = 4096;            // tile ranges per run
 #ifndef FILTER_CTAS_PER_SM
@@ -1020,11 +1020,13 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
                   TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                   uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
                   unsigned long long cand_cap) {
-    // two buffers: the signature words of the next (tile, chunk) item stream in with cp.async while the
-    // current one is being compared — a tile's 8 KiB arrive in about the time its 512 instructions per
-    // thread take, so without the overlap the ALU pipe idles half the time
-    __shared__ __align__(16) uint32_t sR[2][SIG_CHUNK][TILE];
-    __shared__ __align__(16) uint32_t sC[2][SIG_CHUNK][TILE];
+    // three buffers: the signature words of the next two (tile, chunk) items stream in with cp.async while
+    // the current one is being compared — a tile's 8 KiB arrive in about the time its 512 instructions per
+    // thread take, so without the overlap the ALU pipe idles half the time; with three buffers ONE barrier
+    // per item both publishes the item's copies and frees the buffer of the item before it
+    constexpr int NBUF = 3;
+    __shared__ __align__(16) uint32_t sR[NBUF][SIG_CHUNK][TILE];
+    __shared__ __align__(16) uint32_t sC[NBUF][SIG_CHUNK][TILE];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int jend = tw.count();
     const int nchunk = (n_words + SIG_CHUNK - 1) / SIG_CHUNK;
@@ -1050,29 +1052,46 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
     auto has_zero_half = [](uint32_t x) { return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u; };
 
     uint32_t acc[8][8];
-    // (t, ch) = item being compared; its successor is being copied.  Tile coordinates are fetched two
-    // tiles ahead so that the copy never waits on the table lookup.
-    int t = 0, ch = 0;
-    int2 rc_t = tile_at(0), rc_t1 = tile_at(1), rc_t2 = tile_at(2);
-    stage(0, rc_t, 0);
-    for (int item = 0; item < n_items; ++item) {
-        const int buf = item & 1;
-        if (item + 1 < n_items) {
-            const bool same_tile = ch + 1 < nchunk;
-            stage(same_tile ? ch + 1 : 0, same_tile ? rc_t : rc_t1, buf ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    // (t, ch) = item being compared; (ts, chs) = the next item to copy, two items ahead.  The coordinates of the
+    // copy cursor's tile and of the tile after it are fetched ahead of use (rc_s, rc_sn).
+    int t = 0, ch = 0, buf = 0;
+    int ts = 0, chs = 0, bufs = 0;
+    int2 rc_s = tile_at(0), rc_sn = tile_at(1);
+    __shared__ int2 s_rc[4];                               // coordinates of the tiles in flight, by tile number & 3
+    auto stage_next = [&]() {
+        if (chs == 0 && tid == 0) s_rc[ts & 3] = rc_s;
+        stage(chs, rc_s, bufs);
+        bufs = bufs + 1 == NBUF ? 0 : bufs + 1;
+        if (++chs == nchunk) {
+            chs = 0;
+            ++ts;
+            rc_s = rc_sn;
+            rc_sn = tile_at(ts + 1);
         }
+    };
+    int staged = 0;
+    for (; staged < 2 && staged < n_items; ++staged) stage_next();
+    for (int item = 0; item < n_items; ++item) {
+        if (item + 1 < staged) cp_async_wait<1>();          // everything but the newest group has landed
+        else cp_async_wait<0>();
         __syncthreads();
-        if (ch == 0) {
+        if (staged < n_items) { stage_next(); ++staged; }   // into the buffer item-1 was compared from
+        const int nb = min(SIG_CHUNK, n_words - ch * SIG_CHUNK);
+        int bb = 0;
+        if (ch == 0) {                                      // first word of a tile: no accumulator to read
+            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[buf][0][ty * 8]);
+            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[buf][0][ty * 8 + 4]);
+            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[buf][0][tx * 4]);
+            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[buf][0][64 + tx * 4]);
+            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = 0xffffffffu;
+                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], 0xffffffffu);
+            bb = 1;
         }
-        const int nb = min(SIG_CHUNK, n_words - ch * SIG_CHUNK);
-        for (int bb = 0; bb < nb; ++bb) {
+        for (; bb < nb; ++bb) {
             const uint4 ra = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8]);
             const uint4 rb = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8 + 4]);
             const uint4 ca = *reinterpret_cast<const uint4*>(&sC[buf][bb][tx * 4]);
@@ -1084,14 +1103,11 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
 #pragma unroll
                 for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
         }
-        __syncthreads();                                  // the buffer is free for the item after next
+        buf = buf + 1 == NBUF ? 0 : buf + 1;
         if (++ch < nchunk) continue;
-        const int2 rc = rc_t;                               // the tile just finished
+        const int t_done = t;
         ch = 0;
         ++t;
-        rc_t = rc_t1;
-        rc_t1 = rc_t2;
-        rc_t2 = tile_at(t + 2);
         // per-row minima first: a 16-bit signature collides by chance once per ~64 thread-tiles, so four
         // warps in ten come here with ONE row to look at, not 64 cells
         uint32_t rowmin[8];
@@ -1105,6 +1121,7 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
                                             __vimin3_u16x2(rowmin[3], rowmin[4], rowmin[5]),
                                             __vminu2(rowmin[6], rowmin[7]));
         if (!has_zero_half(any)) continue;
+        const int2 rc = s_rc[t_done & 3];                   // written when the tile was queued, barriers ago
         const int r0 = rc.x * TILE, c0 = rc.y * TILE;
         unsigned long long cells = 0ull;                    // bit a*8+b: cell (a,b) has a matching band signature
 #pragma unroll
