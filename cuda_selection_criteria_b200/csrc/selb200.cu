@@ -975,7 +975,7 @@ k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long
     // run of its sketch; lane pairs then pack two bands into a word
     const int nw = (n_bands + 1) >> 1;
     const int nb2 = nw * 2;                                    // bands rounded up to even (pad band never matches)
-    const long long total = n * nb2;
+    const long long total = npad * nb2;                        // pad genomes included: row halves 0, column halves 0x0101
     const long long stride = (long long)gridDim.x * blockDim.x;          // even: lane pairs stay together
     for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 - (threadIdx.x & 31) < total;
          idx0 += stride) {
@@ -983,11 +983,15 @@ k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long
         const long long g = live ? idx0 / nb2 : 0;
         const int b = live ? (int)(idx0 - g * nb2) : 0;
         uint32_t sig = 0;
-        const bool real = live && b < n_bands;
+        const bool real = live && b < n_bands && g < n;
         if (real) sig = band_sig16(aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows, n_rows);
         const uint32_t other = __shfl_down_sync(0xffffffffu, sig, 1);
         const bool other_real = __shfl_down_sync(0xffffffffu, (int)real, 1) != 0;
-        if (live && !(b & 1)) {
+        if (live && !(b & 1) && g >= n) {                      // pad genome: never matches anything
+            const int w = b >> 1;
+            sigR[(size_t)w * npad + g] = 0u;
+            sigC[(size_t)w * npad + g] = 0x01010101u;
+        } else if (live && !(b & 1)) {
             const uint32_t r1 = other_real ? other : 0u;
             const uint32_t c1 = other_real ? ((0u - other) & 0xffffu) : 1u;   // pad half: row 0, column 1
             const int w = b >> 1;
@@ -1775,7 +1779,8 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
 
 // bit-plane union pass over the run's pair list (+ the byte kernel on whatever landed in the wide list)
 int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pairs, uint32_t* hist_out,
-                            const unsigned long long* npairs_dev, unsigned long long* wide_count, int* launches) {
+                            const unsigned long long* npairs_dev, unsigned long long* wide_count, int* launches,
+                            bool counters_are_zero) {
     if (max_pairs <= 0) return SELB200_OK;
     cudaStream_t s = c->stream;
     CKR(c->wide_list.ensure((size_t)max_pairs * 4));
@@ -1794,7 +1799,8 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         }
         per_sm_smem = smem;
     }
-    CK(cudaMemsetAsync(wide_count, 0, 24, s));          // wide count, batch counter, kernel error word (adjacent words of meta[])
+    // wide count, batch counter, kernel error word (adjacent words of meta[])
+    if (!counters_are_zero) CK(cudaMemsetAsync(wide_count, 0, 24, s));
     const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
     k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
                                                            c->grange.as<uint16_t>(), src, epi,
@@ -2463,10 +2469,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             cudaEvent_t a0 = c->ev();
             const size_t sig_bytes = (size_t)n_words * c->npad * 4;
             CKR(c->sigT.ensure(2 * sig_bytes));
-            // pad genomes: row halves 0, column halves 1 -> never match
-            CK(cudaMemsetAsync(c->sigT.p, 0, sig_bytes, s));
-            CK(cudaMemsetAsync(c->sigT.as<uint8_t>() + sig_bytes, 0x01, sig_bytes, s));
-            const int grid = (int)std::min<int64_t>(((int64_t)n * n_words + 255) / 256, (int64_t)c->sm_count * 16);
+            const int grid = (int)std::min<int64_t>(((int64_t)c->npad * n_words * 2 + 255) / 256, (int64_t)c->sm_count * 16);
             k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
                                                   c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
             CK(cudaGetLastError());
@@ -2474,15 +2477,19 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             DBG_SYNC(c, "smh signatures");
             t_filter.push_back({a0, c->ev()});
         }
-        CK(cudaMemsetAsync(d_cnt, 0, 32, s));
-        CK(cudaMemsetAsync(d_cnt + M_PUSHED, 0, 8, s));
+        if (attempt > 0) {          // the memset at the top of the run covers the first attempt
+            CK(cudaMemsetAsync(d_cnt, 0, 32, s));
+            CK(cudaMemsetAsync(d_cnt + M_PUSHED, 0, 8, s));
+        }
         const unsigned long long pair_lim = (unsigned long long)std::min<int64_t>(PAIR_CAP, c->hist_cap_pairs);
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
             const std::pair<int, int> rg = ranges[ri];
             const int64_t nt = (int64_t)rg.second - rg.first;     // upper bound when the end is open
             const TileWalk tw{c->tile_rc.as<int2>(), d_cnt, (long long)c->tile_cap, prm->shard, n_shards, rg.first, rg.second};
-            CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs of this range
-            if (crit >= SELB200_CRIT_HLL_A) CK(cudaMemsetAsync(d_cnt + M_UNIT, 0, 8, s));
+            if (attempt > 0 || ri > 0) {
+                CK(cudaMemsetAsync(d_cnt, 0, 16, s));   // candidates + pairs of this range
+                if (crit >= SELB200_CRIT_HLL_A) CK(cudaMemsetAsync(d_cnt + M_UNIT, 0, 8, s));
+            }
             cudaEvent_t f0 = c->ev();
             if (crit == SELB200_CRIT_SMH_A) {
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
@@ -2542,7 +2549,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 st.launches++;
             } else {
                 CKR(launch_pair_hist_planes(c, c->pairs.as<uint2>(), (int64_t)pair_lim, c->hist.as<uint32_t>(),
-                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches));
+                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches, attempt == 0 && ri == 0));
             }
             DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
