@@ -1,0 +1,81 @@
+// estimate_sort.inl — K6 union estimate + emit, K7 print order of sparse outputs (part of selb200.cu)
+// ============================================================================
+// K6: union estimate -> Jaccard -> tau test -> emit
+//   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
+// ============================================================================
+__global__ void __launch_bounds__(128)
+k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
+                const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
+                const unsigned long long* __restrict__ e, int p, double tau,
+                uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
+                unsigned long long* __restrict__ out_count, unsigned long long out_cap,
+                uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
+                unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
+    // J is non-increasing in t: once it is below tau (and outside the near-tau window) at the
+    // MLE's lower bound the pair can neither be emitted nor listed as near
+    struct StopJ {
+        double tau, slack;
+        unsigned long long e1, e2;
+        __device__ __forceinline__ bool operator()(double t_lb) const {
+            return selb::jaccard(e1, e2, t_lb) < tau - slack;
+        }
+    };
+    const long long npairs = (long long)min(*npairs_dev, npairs_cap);
+    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
+         pi += (long long)gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[pi];
+        const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+        bool stopped = false;
+        const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
+        if (stopped) continue;
+        const double jac = selb::jaccard(e1, e2, t);
+        const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
+        if (jac >= tau) {
+            const unsigned long long slot = warp_claim(out_count);
+            if (slot < out_cap) { out_keys[slot] = key; out_j[slot] = jac; }
+        }
+        if (fabs(jac - tau) <= 1e-6 * fabs(tau)) {
+            const unsigned long long slot = warp_claim(near_count);
+            if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
+        }
+    }
+}
+
+// ============================================================================
+// K7: (i,k) print order of the reference (selection.cpp:297-300) for SPARSE outputs: bucket by row
+// (count -> scan -> scatter), then every element finds its place inside its row by counting the
+// smaller columns.  Four small launches instead of the ~9 of a 49-bit radix sort; rows hold a
+// handful of pairs (cluster mates), so the quadratic in-row step is a few loads per element.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_rowsort_count(const uint64_t* __restrict__ keys, long long cnt, int32_t* __restrict__ rowcnt) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e < cnt) atomicAdd(rowcnt + (keys[e] >> 32), 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_rowsort_scatter(const uint64_t* __restrict__ keys, const double* __restrict__ jac, long long cnt,
+                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ rowoff,
+                  uint64_t* __restrict__ tkeys, double* __restrict__ tj) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= cnt) return;
+    const uint64_t key = keys[e];
+    const uint32_t i = (uint32_t)(key >> 32);
+    const int pos = rowoff[i] + atomicSub(rowcnt + i, 1) - 1;    // counts back down to zero
+    tkeys[pos] = key;
+    tj[pos] = jac[e];
+}
+
+__global__ void __launch_bounds__(256)
+k_rowsort_rank(const uint64_t* __restrict__ tkeys, const double* __restrict__ tj, long long cnt,
+               const int32_t* __restrict__ rowoff, uint64_t* __restrict__ out_keys, double* __restrict__ out_j) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= cnt) return;
+    const uint64_t key = tkeys[e];
+    const uint32_t i = (uint32_t)(key >> 32);
+    const int a = rowoff[i], b = rowoff[i + 1];
+    int r = 0;
+    for (int t = a; t < b; ++t) r += tkeys[t] < key;      // keys are unique
+    out_keys[a + r] = key;
+    out_j[a + r] = tj[e];
+}

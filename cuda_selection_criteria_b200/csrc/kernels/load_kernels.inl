@@ -1,0 +1,76 @@
+// load_kernels.inl — load-time kernels: validation, cardinalities, sorted re-layout (part of selb200.cu)
+// ============================================================================
+// K0: register validation — max byte over a buffer (values must be <= 64-p+1)
+// ============================================================================
+__global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data, size_t n16, uint32_t* out) {
+    uint32_t mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(data + i);
+        mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+    }
+    uint32_t b = max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
+    for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
+}
+__global__ void k_iota_i32(int32_t* v, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+// sorted cardinalities -> truncated e (size_t e = card, selection.cpp:275,280) + tie detection
+__global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long n, unsigned long long* __restrict__ e,
+                              uint32_t* __restrict__ tie_flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cd = cards_sorted[i];
+    e[i] = (unsigned long long)cd;
+    if (i + 1 < n && !(cd < cards_sorted[i + 1])) *tie_flag = 1;
+}
+
+// per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
+__global__ void k_genome_cards(const uint32_t* __restrict__ hist, const double* __restrict__ stored, long long n,
+                               int p, double* __restrict__ cards, const uint32_t* __restrict__ max_seen,
+                               uint32_t max_ok, uint16_t* __restrict__ grange) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (*max_seen > max_ok) { cards[i] = 0.; grange[i] = 0; return; }   // malformed input: the load fails after the sync
+    {   // smallest and largest register value of the genome (window choice of the bit-plane union kernel)
+        int vmin = 63, vmax = 0;
+        for (int b = 0; b < 64; ++b)
+            if (hist[i * 64 + b]) { vmin = min(vmin, b); vmax = max(vmax, b); }
+        grange[i] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
+    }
+    if (stored && stored[i] >= 0.) { cards[i] = stored[i]; return; }
+    cards[i] = selb::ertl_mle(hist + i * 64, p);
+}
+
+__global__ void k_mle_only(const uint32_t* __restrict__ hist, long long n, int p, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = selb::ertl_mle(hist + i * 64, p);
+}
+// ============================================================================
+// load-time re-layout
+// ============================================================================
+// dst[i][:] = src[order[i]][:], rows of row_words uint32
+__global__ void k_gather_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
+                              int row_words, uint32_t* __restrict__ dst) {
+    const long long total = n * row_words;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx / row_words;
+        const int j = (int)(idx - i * row_words);
+        dst[idx] = src[(size_t)order[i] * row_words + j];
+    }
+}
+
+// auxT[j][g] = word j of the aux HLL of the g-th genome in sorted order (pad columns stay 0)
+__global__ void k_aux_transpose(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
+                                long long npad, int row_words, uint32_t* __restrict__ dst) {
+    const long long total = n * row_words;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / n);
+        const long long g = idx - (long long)j * n;
+        dst[(size_t)j * npad + g] = src[(size_t)order[g] * row_words + j];
+    }
+}

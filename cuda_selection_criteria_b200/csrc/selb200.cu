@@ -221,1510 +221,19 @@ struct selb200_ctx {
 };
 
 // ============================================================================
-// device helpers
+// device code: one anonymous namespace, one translation unit; the kernels live in kernels/*.inl
 // ============================================================================
 namespace {
 
-// SWAR byte-wise max for bytes < 128 (HLL registers are <= 64-p+1 <= 63):
-// the top bit of each byte of (a|0x80..)-b is set iff a>=b, with no borrow between bytes;
-// PRMT in sign-replicate mode turns those bits into byte masks.  4 instructions per 4 registers
-// (__vmaxu4 is a 7-instruction emulation on sm_100a).
-__device__ __forceinline__ uint32_t max4_lt128(uint32_t a, uint32_t b) {
-    const uint32_t d = (a | 0x80808080u) - b;
-    uint32_t msk;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(msk) : "r"(d), "r"(0u), "r"(0xba98u));
-    return (a & msk) | (b & ~msk);
-}
-
-// Histogram addressing.  Counters are laid out [bin][64 threads] uint32 in the CTA's static
-// shared memory, so the counter of thread t for register value v lives at shared address
-//   base + (v << 8) + t*4 .
-// `base` is 256-aligned and small, so adding (base >> 8) to every byte of the packed
-// register word (no carries: v <= 63) lets ONE PRMT build the complete address from the word
-// and tb = t*4 — no per-byte add, and the bank is t mod 32: conflict-free.
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t hist_bias(const void* hist) {
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(hist);
-    if ((sbase & 0xffu) || sbase > 0x8000u) __trap();   // must fit: (63 + bias) < 256 and address < 64 KiB
-    return (sbase >> 8) * 0x01010101u;
-}
-template <int B>
-__device__ __forceinline__ uint32_t hist_addr(uint32_t wb, uint32_t tb) {
-    return __byte_perm(wb, tb, 0x5504 | (B << 4));
-}
-
-// Two register values per step into ONE histogram: both counters are loaded before either is
-// stored (two LDS in flight instead of a serial LDS->ADD->STS chain); if both hit the same
-// counter the second store carries the first increment (select), and stores stay in order.
-template <int B0, int B1>
-__device__ __forceinline__ void hist_inc2(uint32_t wb, uint32_t tb) {
-    const uint32_t o0 = hist_addr<B0>(wb, tb), o1 = hist_addr<B1>(wb, tb);
-    const uint32_t c0 = lds_u32(o0) + 1;
-    uint32_t c1 = lds_u32(o1);
-    c1 = (o1 == o0) ? c0 : c1;
-    sts_u32(o0, c0);
-    sts_u32(o1, c1 + 1);
-}
-
-__device__ __forceinline__ void hist_inc_max16(const uint4& x, const uint4& y, uint32_t bias, uint32_t tb) {
-    uint32_t w;
-    w = max4_lt128(x.x, y.x) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
-    w = max4_lt128(x.y, y.y) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
-    w = max4_lt128(x.z, y.z) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
-    w = max4_lt128(x.w, y.w) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
-}
-
-// One register value into each of TWO different histograms (never alias): both loads first.
-template <int B>
-__device__ __forceinline__ void hist_inc_dual(uint32_t wb0, uint32_t wb1, uint32_t tb) {
-    const uint32_t o0 = hist_addr<B>(wb0, tb), o1 = hist_addr<B>(wb1, tb);
-    const uint32_t c0 = lds_u32(o0), c1 = lds_u32(o1);
-    sts_u32(o0, c0 + 1);
-    sts_u32(o1, c1 + 1);
-}
-
-// Warp-aggregated slot claim: one atomicAdd per warp per call site, lanes get consecutive slots.
-__device__ __forceinline__ unsigned long long warp_claim(unsigned long long* counter) {
-    const unsigned mask = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
-}
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return x;
-}
-
-// ============================================================================
-// K0: register validation — max byte over a buffer (values must be <= 64-p+1)
-// ============================================================================
-__global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data, size_t n16, uint32_t* out) {
-    uint32_t mx = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(data + i);
-        mx = __vmaxu4(mx, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
-    }
-    uint32_t b = max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
-    for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
-    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
-}
-
-// ============================================================================
-// K5: warp-per-pair register max + histogram (primary HLL, m >= 512)
-//   reference: sketch/include/sketch/hll.h:1188-1206 (union_size: _mm_max_epu8 + 64-bin counts)
-//   CTA = 2 warps, each warp owns its own pairs; NB bins x 64 threads x 4 B static smem.
-//   Src  : where pair (row a, row b) number pi comes from, and how many there are
-//   Epi  : what happens to the finished histogram (lane L holds bins L and L+32)
-// ============================================================================
-struct SrcPairs {            // pair list of the selection path: sorted positions, mapped through `order`
-    const uint2* pairs;
-    const int32_t* order;    // nullptr: entries are row indices already
-    long long n;             // count, or the capacity when n_dev is given
-    const unsigned long long* n_dev;   // optional: the count lives in device memory (no host sync)
-    __device__ __forceinline__ long long count() const {
-        return n_dev ? (long long)min((unsigned long long)n, *n_dev) : n;
-    }
-    __device__ __forceinline__ uint2 rows(long long pi, uint2& id) const {
-        id = pairs[pi];
-        return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
-    }
-    __device__ __forceinline__ long long slot(long long pi) const { return pi; }   // histogram row of pair pi
-};
-
-struct SrcSelf {             // rows g0..g0+n-1 against themselves: per-genome histograms (max(a,a) = a)
-    long long g0, n;
-    const uint32_t* max_seen;   // written by k_max_byte earlier on the stream: a register above
-    uint32_t max_ok;            // 64-p+1 would index past the histogram, so nothing is processed
-    __device__ __forceinline__ long long count() const { return *max_seen > max_ok ? 0 : n; }
-    __device__ __forceinline__ uint2 rows(long long pi, uint2& id) const {
-        id = make_uint2((uint32_t)(g0 + pi), (uint32_t)(g0 + pi));
-        return id;
-    }
-    __device__ __forceinline__ long long slot(long long pi) const { return pi; }
-};
-
-struct EpiWriteHist {        // histogram rows for k_estimate_emit
-    uint32_t* out;
-    __device__ __forceinline__ void operator()(long long pi, uint2, uint32_t s0, uint32_t s1, uint32_t lane) const {
-        out[pi * 64 + lane] = s0;
-        out[pi * 64 + 32 + lane] = s1;
-    }
-};
-
-template <int NB, class Src, class Epi>
-__global__ void __launch_bounds__(64)
-k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src src, Epi epi) {
-    __shared__ __align__(1024) uint32_t hist[NB * 64];
-    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
-    const uint32_t bias = hist_bias(hist);
-#pragma unroll 4
-    for (int b = 0; b < NB; ++b) hist[b * 64 + t] = 0;
-    __syncwarp();
-    const int nchunk = (int)(m >> 9);   // 512 B per warp-wide 128-bit load
-    const int ngroups = nchunk >> 2;    // software pipeline works on groups of 4 chunks
-    const long long nw = (long long)gridDim.x * 2;
-    const long long npairs = src.count();
-    uint32_t prev0 = 0, prev1 = 0;
-    for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
-        uint2 id;
-        const uint2 rw = src.rows(pi, id);
-        const uint4* a = reinterpret_cast<const uint4*>(regs + (size_t)rw.x * row_stride) + lane;
-        const uint4* b = reinterpret_cast<const uint4*>(regs + (size_t)rw.y * row_stride) + lane;
-        if (ngroups) {
-            // two chunks being histogrammed while the next two are in flight (no register rotation)
-            uint4 ax0 = __ldg(a), ay0 = __ldg(b), ax1 = __ldg(a + 32), ay1 = __ldg(b + 32);
-            for (int g = 0; g < ngroups; ++g) {
-                const uint4 bx0 = __ldg(a + 64), by0 = __ldg(b + 64), bx1 = __ldg(a + 96), by1 = __ldg(b + 96);
-                hist_inc_max16(ax0, ay0, bias, tb);
-                hist_inc_max16(ax1, ay1, bias, tb);
-                a += 128; b += 128;
-                if (g + 1 < ngroups) { ax0 = __ldg(a); ay0 = __ldg(b); ax1 = __ldg(a + 32); ay1 = __ldg(b + 32); }
-                hist_inc_max16(bx0, by0, bias, tb);
-                hist_inc_max16(bx1, by1, bias, tb);
-            }
-        }
-        for (int c = ngroups * 4; c < nchunk; ++c, a += 32, b += 32) hist_inc_max16(__ldg(a), __ldg(b), bias, tb);
-        __syncwarp();
-        // transposed, conflict-free column sums: lane L totals bins L and L+32.  Counters are
-        // never cleared: they run cumulatively (mod 2^32) and the pair's histogram is the
-        // difference to the previous totals, which saves the 64 clearing stores per pair.
-        uint32_t s0 = 0, s1 = 0;
-        const uint32_t cb = w * 32;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            const uint32_t col = cb + ((lane + r) & 31);
-            s0 += hist[lane * 64 + col];
-            if (lane + 32 < NB) s1 += hist[(lane + 32) * 64 + col];
-        }
-        __syncwarp();
-        epi(src.slot(pi), id, s0 - prev0, s1 - prev1, lane);
-        prev0 = s0;
-        prev1 = s1;
-    }
-}
-
-// ============================================================================
-// K5 (bit-plane form): the same union histogram computed on BIT PLANES of the registers.
-//
-// The byte kernel above is bound by shared-memory read-modify-writes (measured ~9 registers per clock
-// per SM: two wavefronts per 32 registers, tools/ubench/int_pipes.cu).  HLL registers are 6-bit numbers,
-// so a genome can also be stored as 6 planes of 2^p bits (12 KiB instead of 16 KiB at p=14), and one
-// 32-bit logic instruction then handles 32 registers at once:
-//   max(a,b)   : borrow chain of a-b over the planes (1 LOP3 per plane) -> mask "a<b", then one select
-//                per plane                                                            12 LOP3 / 32 regs
-//   decode     : 8 masks of the low 3 bits + 4 masks of the high 3 bits (the pair's values lie in a
-//                window of 32 consecutive values starting at a multiple of 8)         12 LOP3
-//   count      : per value, mask = high & low, accumulated with carry-save adders over 4 words
-//                (2 CSA = 4 LOP3, 2 POPC, 1 IADD3 per value and 4 words)              ~2 LOP3 / value / word
-// i.e. ~2.3-2.8 ALU-pipe operations per register instead of two shared-memory wavefronts per 32.
-// POPC issues at 16 lanes/clk/SM on B200 (LOP3: 63), hence the carry-save adders.
-// The planes are staged into shared memory by cp.async.bulk (TMA) copies completing on mbarriers;
-// one warp per CTA, ~9 CTAs per SM.
-// Pairs whose value range does not fit a 32-value window (never seen on real sketches) go to a
-// "wide" list and through the byte kernel.
-// layout: genome g at planes + g * 6 * m/8 bytes; chunk c (PL_CHUNK_REGS registers, or m if smaller) holds its
-//         6 planes back to back: [chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r
-// ============================================================================
-// chunk / ring geometry, measured at n=100k (511 521 pairs): 2048 regs x 4 stages x 16 CTAs/SM 1.94 ms,
-// 4096 x 3 x 12: 2.02 ms, 8192 x 2 x 9: 1.87 ms (fewer, longer steps: less pipeline control per register)
-#ifndef PL_CHUNK_REGS_V
-#define PL_CHUNK_REGS_V 8192
-#endif
-constexpr int PL_CHUNK_REGS = PL_CHUNK_REGS_V;
-constexpr int PL_NQ = PL_CHUNK_REGS / 64;   // uint2 per plane of a full chunk
-
-__global__ void __launch_bounds__(256)
-k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, int chunk_regs,
-                    uint32_t* __restrict__ planes) {
-    const int lane = threadIdx.x & 31;
-    const long long nblk = rows * (long long)(m >> 9);          // 512-register blocks
-    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int blk_per_genome = (int)(m >> 9), blk_per_chunk = chunk_regs >> 9;
-    const size_t chunk_words = (size_t)6 * (chunk_regs >> 5);
-    for (long long blk = warp0; blk < nblk; blk += nwarps) {
-        const long long g = blk / blk_per_genome;
-        const int bg = (int)(blk - g * blk_per_genome);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(regs + (size_t)g * m + (size_t)bg * 512) + lane);
-        const int chunk = bg / blk_per_chunk, bc = bg - chunk * blk_per_chunk;
-        uint32_t* dst = planes + (size_t)g * 6 * (m >> 5) + (size_t)chunk * chunk_words + (size_t)bc * 16;
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            // bit b of the lane's 16 registers -> 16-bit mask (multiply gathers the 4 byte-bits of a word)
-            const uint32_t nx = ((((v.x >> b) & 0x01010101u) * 0x10204080u) >> 28);
-            const uint32_t ny = ((((v.y >> b) & 0x01010101u) * 0x10204080u) >> 28);
-            const uint32_t nz = ((((v.z >> b) & 0x01010101u) * 0x10204080u) >> 28);
-            const uint32_t nw = ((((v.w >> b) & 0x01010101u) * 0x10204080u) >> 28);
-            const uint32_t h = nx | (ny << 4) | (nz << 8) | (nw << 12);
-            const uint32_t lo = __shfl_sync(0xffffffffu, h, 2 * (lane & 15));
-            const uint32_t hi = __shfl_sync(0xffffffffu, h, 2 * (lane & 15) + 1);
-            if (lane < 16) dst[(size_t)b * (chunk_regs >> 5) + lane] = lo | (hi << 16);
-        }
-    }
-}
-
-template <int LUT>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
-    return d;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(phase)
-        : "memory");
-}
-
-// One chunk (<= PL_CHUNK_REGS registers) against the running carry-save state.  Per step, lane q holds
-// two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so
-// that eight independent dependency chains are in flight (LOP3 latency 4 at one issue per 2 clocks).
-template <int G0, int NQ>   // NQ > 0: uint2 per plane known at compile time (full 2048-register chunks)
-__device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
-                                            int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
-    const int nq = NQ > 0 ? NQ : nq_rt;
-    // nq = uint2 (2 x 32 registers) per plane; plane b of genome X at sX + b*nq.
-    // Window 0 holds values below 32 only: plane 5 is all zero there and is neither copied nor read.
-    constexpr int NP = (G0 == 0) ? 5 : 6;
-#pragma unroll 1
-    for (int q = lane; q < nq; q += 32) {
-        uint32_t M[2][6];
-        {
-            uint2 a[NP], b[NP];
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) { a[pl] = sA[pl * nq + q]; b[pl] = sB[pl * nq + q]; }
-            uint32_t lt0 = 0u, lt1 = 0u;
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {      // borrow of a - b, plane by plane: ends as the mask a < b
-                lt0 = lop3<0x8E>(a[pl].x, b[pl].x, lt0);
-                lt1 = lop3<0x8E>(a[pl].y, b[pl].y, lt1);
-            }
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {      // max = a < b ? b : a
-                M[0][pl] = lop3<0xCA>(lt0, b[pl].x, a[pl].x);
-                M[1][pl] = lop3<0xCA>(lt1, b[pl].y, a[pl].y);
-            }
-            if (NP == 5) { M[0][5] = 0u; M[1][5] = 0u; }
-        }
-        uint32_t L[2][8];
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            L[w][0] = lop3<0x01>(M[w][2], M[w][1], M[w][0]);
-            L[w][1] = lop3<0x02>(M[w][2], M[w][1], M[w][0]);
-            L[w][2] = lop3<0x04>(M[w][2], M[w][1], M[w][0]);
-            L[w][3] = lop3<0x08>(M[w][2], M[w][1], M[w][0]);
-            L[w][4] = lop3<0x10>(M[w][2], M[w][1], M[w][0]);
-            L[w][5] = lop3<0x20>(M[w][2], M[w][1], M[w][0]);
-            L[w][6] = lop3<0x40>(M[w][2], M[w][1], M[w][0]);
-            L[w][7] = lop3<0x80>(M[w][2], M[w][1], M[w][0]);
-        }
-        // SPARSE: the top group of a window holds a handful of registers per genome, so most warp-wide
-        // steps see none of them and skip the group's 40 instructions after one vote
-#define SELB_PLANE_GROUP(T, SPARSE)                                                                       \
-        if (gmask & (1u << T)) {                                                                          \
-            const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
-            const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
-            if (!SPARSE || __any_sync(0xffffffffu, (H0 | H1) != 0u)) {                                    \
-                uint32_t m0[8], m1[8], kk[8];                                                             \
-                _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
-                _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
-                _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
-                _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);             \
-            }                                                                                             \
-        }
-        SELB_PLANE_GROUP(0, false)
-        SELB_PLANE_GROUP(1, false)
-        SELB_PLANE_GROUP(2, false)
-        SELB_PLANE_GROUP(3, false)
-#undef SELB_PLANE_GROUP
-    }
-}
-
-// pair list -> histogram rows, bit-plane form.  grange[g] = min | max<<8 of genome g's registers.
-// One warp per CTA.  Work comes in batches of 32 consecutive pairs claimed from a device counter (dynamic
-// balance, no tail): each lane fetches the descriptor of one pair of the batch (rows through `order`, value
-// window from grange), so the dependent global loads are paid once per 32 pairs and the warp then reads
-// descriptors with shuffles.  The pairs' planes flow chunk by chunk (8192 registers = 2 x 6 KiB) through a
-// ring of PL_STAGES shared-memory stages: lane 0 keeps PL_STAGES-1 bulk copies (TMA) in flight ahead of
-// the chunk being counted, across pair and batch boundaries.
-#ifndef PL_STAGES_V
-#define PL_STAGES_V 2
-#endif
-constexpr int PL_STAGES = PL_STAGES_V;
-#ifndef PL_MIN_CTAS
-#define PL_MIN_CTAS 9
-#endif
-
-template <class Epi>
-__global__ void __launch_bounds__(32, PL_MIN_CTAS)
-k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
-                   SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
-                   unsigned long long* __restrict__ batch_counter) {
-    extern __shared__ __align__(128) uint8_t pl_smem[];
-    constexpr uint32_t FULL = 0xffffffffu;
-    const int lane = threadIdx.x;
-    const int nchunks = (int)(m / (size_t)chunk_regs);
-    const uint32_t chunk_bytes = (uint32_t)(6 * (chunk_regs >> 3));
-    const int nq = chunk_regs >> 6;
-    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(pl_smem);
-    const uint32_t bar0 = smem0 + PL_STAGES * 2 * chunk_bytes;
-    if (lane == 0)
-        for (int st = 0; st < PL_STAGES; ++st) mbar_init(bar0 + 8 * st, 1);
-    __syncwarp();
-    const size_t genome_bytes = (size_t)6 * (m >> 3);
-    const long long npairs = src.count();
-    // batch size: 32 pairs when there is plenty of work, fewer (down to 4) when the list is short, so that
-    // every warp still gets several batches and the dynamic claiming can balance the tail
-    int bsz = 32;
-    while (bsz > 4 && npairs < (long long)bsz * gridDim.x * 4) bsz >>= 1;
-
-    // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
-    uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
-    uint32_t mask0 = 0, mask1 = 0;          // lanes of the set holding a pair to do (warp-uniform)
-    long long base0 = 0, base1 = 0;         // first pair index of the batch
-    bool end0 = false, end1 = false;        // the batch starts past the end of the list: nothing follows
-    int filled = -1;
-
-    auto fill = [&](int k) {
-        long long bidx = 0;
-        if (lane == 0) bidx = (long long)atomicAdd(batch_counter, 1ull);
-        bidx = __shfl_sync(FULL, bidx, 0);
-        const long long pi = bidx * bsz + lane;
-        bool ok = lane < bsz && pi < npairs;
-        uint2 id = make_uint2(0u, 0u), rw = id;
-        uint32_t gm = 0;
-        if (ok) {
-            rw = src.rows(pi, id);
-            const uint32_t ra = grange[rw.x], rb = grange[rw.y];
-            const int lo = max((int)(ra & 0xff), (int)(rb & 0xff)), hi = max((int)(ra >> 8), (int)(rb >> 8));
-            const int g0 = min(lo >> 3, 4);
-            if ((hi >> 3) > g0 + 3) {        // value range wider than the window: the byte kernel does this pair
-                wide_list[atomicAdd(wide_count, 1ull)] = (uint32_t)pi;
-                ok = false;
-            } else {
-                uint32_t gmask = 0;
-                for (int t = 0; t < 4; ++t)
-                    if ((g0 + t) >= (lo >> 3) && (g0 + t) <= (hi >> 3)) gmask |= 1u << t;
-                gm = (uint32_t)g0 | (gmask << 8);
-            }
-        }
-        const uint32_t msk = __ballot_sync(FULL, ok);
-        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; mask1 = msk; base1 = bidx * bsz; end1 = bidx * bsz >= npairs; }
-        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; mask0 = msk; base0 = bidx * bsz; end0 = bidx * bsz >= npairs; }
-        filled = k;
-    };
-
-    struct Cur {               // position in the warp's sequence of (pair, chunk) items; warp-uniform
-        int k;                 // batch number
-        uint32_t mask;         // pairs of the batch not started yet
-        bool valid, done;
-        int ch;
-        uint32_t rx, ry, ix, iy, gm;
-        long long pi;
-        const uint8_t* ga;     // planes of the two genomes (producer side)
-        const uint8_t* gb;
-    };
-    Cur cons, prod;
-    auto next_pair = [&](Cur& c, bool is_cons) {
-        c.valid = false;
-        for (;;) {
-            // A batch can be empty without being the end (all its pairs wide: one odd genome, many consecutive
-            // pairs).  The consumer then walks through it in one go and recycles its set, so a producer
-            // still parked on that batch number must not read the set any more: it rejoins the consumer,
-            // whose batch it has not touched yet.
-            if (!is_cons && c.k < cons.k) {
-                c.k = cons.k;
-                c.mask = (c.k & 1) ? mask1 : mask0;
-            }
-            if (c.mask) {
-                const int j = __ffs((int)c.mask) - 1;
-                c.mask &= c.mask - 1;
-                const bool odd = c.k & 1;
-                c.rx = __shfl_sync(FULL, odd ? d_rx1 : d_rx0, j);
-                c.ry = __shfl_sync(FULL, odd ? d_ry1 : d_ry0, j);
-                c.ix = __shfl_sync(FULL, odd ? d_ix1 : d_ix0, j);
-                c.iy = __shfl_sync(FULL, odd ? d_iy1 : d_iy0, j);
-                c.gm = __shfl_sync(FULL, odd ? d_gm1 : d_gm0, j);
-                c.pi = (odd ? base1 : base0) + j;
-                if (!is_cons) {
-                    c.ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes;
-                    c.gb = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.ry * genome_bytes;
-                }
-                c.ch = 0;
-                c.valid = true;
-                return;
-            }
-            if ((c.k & 1) ? end1 : end0) { c.done = true; return; }
-            if (c.k + 1 > filled) return;                 // producer only: the next batch is not there yet
-            ++c.k;
-            c.mask = (c.k & 1) ? mask1 : mask0;
-            // the consumer has left batch k-1: its set is free for batch k+1
-            if (is_cons && !(((filled & 1) ? end1 : end0))) fill(c.k + 1);
-        }
-    };
-    auto issue = [&](const Cur& c, uint32_t n_issued) {      // lane 0: two bulk copies into the next stage
-        const uint32_t st = n_issued % PL_STAGES;
-        const uint32_t dst = smem0 + st * 2 * chunk_bytes, bar = bar0 + 8 * st;
-        const uint8_t* ga = c.ga + (uint32_t)c.ch * chunk_bytes;
-        const uint8_t* gb = c.gb + (uint32_t)c.ch * chunk_bytes;
-        // window 0 (values < 32): plane 5 is zero and stays behind — 5/6 of the bytes
-        const uint32_t nbytes = (c.gm & 0xffu) == 0u ? chunk_bytes / 6u * 5u : chunk_bytes;
-        mbar_expect_tx(bar, 2 * nbytes);
-        tma_bulk_g2s(dst, ga, nbytes, bar);
-        tma_bulk_g2s(dst + chunk_bytes, gb, nbytes, bar);
-    };
-
-    fill(0);
-    if (!end0) fill(1);
-    cons.k = 0; cons.mask = mask0; cons.valid = false; cons.done = false; cons.ch = 0;
-    cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.pi = 0;
-    cons.ga = cons.gb = nullptr;
-    prod = cons;
-    next_pair(cons, true);
-    next_pair(prod, false);
-    uint32_t n_issued = 0, n_done = 0;
-    for (int k = 0; k < PL_STAGES - 1 && prod.valid; ++k) {
-        if (lane == 0) issue(prod, n_issued);
-        ++n_issued;
-        if (++prod.ch >= nchunks) next_pair(prod, false);
-    }
-    uint32_t S[32], C2[32];
-#pragma unroll
-    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
-    while (cons.valid) {
-        __syncwarp();                          // every lane has finished reading the stage about to be refilled
-        if (!prod.valid && !prod.done) next_pair(prod, false);
-        if (prod.valid) {
-            if (lane == 0) issue(prod, n_issued);
-            ++n_issued;
-            if (++prod.ch >= nchunks) next_pair(prod, false);
-        }
-        if (n_done == n_issued) {              // cannot happen: the consumer never overtakes the producer
-            if (lane == 0)
-                atomicExch(batch_counter + 1, 0xBA00000000000000ull | ((unsigned long long)prod.valid << 55) |
-                                                  ((unsigned long long)prod.done << 54) | ((unsigned long long)end0 << 53) |
-                                                  ((unsigned long long)end1 << 52) | ((unsigned long long)(prod.k & 0xfff) << 40) |
-                                                  ((unsigned long long)(cons.k & 0xfff) << 28) |
-                                                  ((unsigned long long)(filled & 0xfff) << 16) | (n_issued & 0xffffu));
-            return;
-        }
-        const uint32_t st = n_done % PL_STAGES;
-        mbar_wait(bar0 + 8 * st, (n_done / PL_STAGES) & 1u);
-        ++n_done;
-        const uint2* pa = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes);
-        const uint2* pb = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes + chunk_bytes);
-        const int g0 = (int)(cons.gm & 0xffu);
-        const uint32_t gmask = cons.gm >> 8;
-        if (nq == PL_NQ) {
-            switch (g0) {
-                case 0: plane_chunk<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 1: plane_chunk<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 2: plane_chunk<2, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 3: plane_chunk<3, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                default: plane_chunk<4, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-            }
-        } else {
-            switch (g0) {
-                case 0: plane_chunk<0, 0>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 1: plane_chunk<1, 0>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 2: plane_chunk<2, 0>(pa, pb, nq, lane, gmask, S, C2); break;
-                case 3: plane_chunk<3, 0>(pa, pb, nq, lane, gmask, S, C2); break;
-                default: plane_chunk<4, 0>(pa, pb, nq, lane, gmask, S, C2); break;
-            }
-        }
-        if (cons.ch == nchunks - 1) {
-            // per-lane totals, then a transposing butterfly: lane L ends with the warp total of value 8*g0 + L
-            uint32_t x[32];
-#pragma unroll
-            for (int v = 0; v < 32; ++v) { x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]); S[v] = 0; C2[v] = 0; }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const bool upper = (lane & o) != 0;
-#pragma unroll
-                for (int i = 0; i < o; ++i) {
-                    const uint32_t send = upper ? x[i] : x[i + o];
-                    const uint32_t keep = upper ? x[i + o] : x[i];
-                    x[i] = keep + __shfl_xor_sync(FULL, send, o);
-                }
-            }
-            const uint32_t tot = __shfl_sync(FULL, x[0], (lane - 8 * g0) & 31);
-            const bool first = lane >= 8 * g0;     // bin `lane` lies inside the window; else bin lane+32 does
-            epi(src.slot(cons.pi), make_uint2(cons.ix, cons.iy), first ? tot : 0u, first ? 0u : tot, (uint32_t)lane);
-        }
-        if (++cons.ch >= nchunks) next_pair(cons, true);
-    }
-}
-
-// the wide list as a pair source for the byte kernel (histogram row = the pair's own slot)
-struct SrcWide {
-    const uint2* pairs;
-    const int32_t* order;
-    const uint32_t* wide_list;
-    const unsigned long long* n_dev;
-    __device__ __forceinline__ long long count() const { return (long long)*n_dev; }
-    __device__ __forceinline__ uint2 rows(long long wi, uint2& id) const {
-        id = pairs[wide_list[wi]];
-        return order ? make_uint2((uint32_t)order[id.x], (uint32_t)order[id.y]) : id;
-    }
-    __device__ __forceinline__ long long slot(long long wi) const { return (long long)wide_list[wi]; }
-};
-
-__global__ void k_iota_i32(int32_t* v, long long n) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (int32_t)i;
-}
-
-// sorted cardinalities -> truncated e (size_t e = card, selection.cpp:275,280) + tie detection
-__global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long n, unsigned long long* __restrict__ e,
-                              uint32_t* __restrict__ tie_flag) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double cd = cards_sorted[i];
-    e[i] = (unsigned long long)cd;
-    if (i + 1 < n && !(cd < cards_sorted[i + 1])) *tie_flag = 1;
-}
-
-// per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
-__global__ void k_genome_cards(const uint32_t* __restrict__ hist, const double* __restrict__ stored, long long n,
-                               int p, double* __restrict__ cards, const uint32_t* __restrict__ max_seen,
-                               uint32_t max_ok, uint16_t* __restrict__ grange) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (*max_seen > max_ok) { cards[i] = 0.; grange[i] = 0; return; }   // malformed input: the load fails after the sync
-    {   // smallest and largest register value of the genome (window choice of the bit-plane union kernel)
-        int vmin = 63, vmax = 0;
-        for (int b = 0; b < 64; ++b)
-            if (hist[i * 64 + b]) { vmin = min(vmin, b); vmax = max(vmax, b); }
-        grange[i] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
-    }
-    if (stored && stored[i] >= 0.) { cards[i] = stored[i]; return; }
-    cards[i] = selb::ertl_mle(hist + i * 64, p);
-}
-
-__global__ void k_mle_only(const uint32_t* __restrict__ hist, long long n, int p, double* __restrict__ out) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = selb::ertl_mle(hist + i * 64, p);
-}
-
-// ============================================================================
-// load-time re-layout
-// ============================================================================
-// dst[i][:] = src[order[i]][:], rows of row_words uint32
-__global__ void k_gather_rows(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
-                              int row_words, uint32_t* __restrict__ dst) {
-    const long long total = n * row_words;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long i = idx / row_words;
-        const int j = (int)(idx - i * row_words);
-        dst[idx] = src[(size_t)order[i] * row_words + j];
-    }
-}
-
-// auxT[j][g] = word j of the aux HLL of the g-th genome in sorted order (pad columns stay 0)
-__global__ void k_aux_transpose(const uint32_t* __restrict__ src, const int32_t* __restrict__ order, long long n,
-                                long long npad, int row_words, uint32_t* __restrict__ dst) {
-    const long long total = n * row_words;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(idx / n);
-        const long long g = idx - (long long)j * n;
-        dst[(size_t)j * npad + g] = src[(size_t)order[g] * row_words + j];
-    }
-}
-
-// ============================================================================
-// K2: CB band per sorted row
-//   reference: src/selection.cpp:278-283 — skip e2==0, break at the first CB failure.
-//   Sorted ascending + correctly-rounded fp64 division => the passing set of row i is the
-//   contiguous range [lo(i), hi(i)], lo = max(i+1, first index with e>0).
-// ============================================================================
-__global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int zeros, double tau,
-                            int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long e1 = e[i];
-    const int l = max(i + 1, zeros);
-    int a = l, b = n;   // first k in [l,n) failing CB
-    while (a < b) {
-        const int mid = (a + b) >> 1;
-        if (selb::crit_cb(tau, e1, e[mid])) a = mid + 1; else b = mid;
-    }
-    lo[i] = l;
-    hi[i] = a - 1;
-}
-
-// ============================================================================
-// tile list of the CB band, built on the device (no host round trip):
-//   k_rowblock_span : per 128-row block, the column-block span of its band and its pair count
-//   cub exclusive scan over the spans -> first tile index of every row block
-//   k_tile_table    : (row block, column block) of every tile, so that a filter CTA finds its
-//                     tile with one 8-byte load
-// meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
-// range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
-// ============================================================================
-enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_UNIT = 10, M_WORDS = 16 };
-
-__global__ void __launch_bounds__(128)
-k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
-                int32_t* __restrict__ nt, int32_t* __restrict__ cb0, unsigned long long* __restrict__ rb_pairs,
-                unsigned long long* __restrict__ meta) {
-    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (rb > nrb) return;
-    if (rb == nrb) { if (lane == 0) nt[nrb] = 0; return; }   // scan sentinel: prefix[nrb] = total
-    int cmin = INT32_MAX, cmax = -1;
-    unsigned long long cnt = 0;
-    for (int i = rb * TILE + lane; i < min(n, (rb + 1) * TILE); i += 32) {
-        const int l = lo[i], h = hi[i];
-        if (h < l) continue;
-        cnt += (unsigned long long)(h - l + 1);
-        cmin = min(cmin, l);
-        cmax = max(cmax, h);
-    }
-    for (int o = 16; o; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-    }
-    if (lane == 0) {
-        nt[rb] = cnt ? cmax / TILE - cmin / TILE + 1 : 0;
-        cb0[rb] = cnt ? cmin / TILE : 0;
-        rb_pairs[rb] = cnt;
-        if (cnt) atomicAdd(meta + M_PAIRS_CB, cnt);
-    }
-}
-
-__global__ void __launch_bounds__(128)
-k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ cb0, int nrb, long long tile_cap,
-             int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
-    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (rb >= nrb) return;
-    const int a = tile_prefix[rb], cnt = tile_prefix[rb + 1] - a, c0 = cb0[rb];
-    for (int t = lane; t < cnt; t += 32)
-        if (a + t < tile_cap) tile_rc[a + t] = make_int2(rb, c0 + t);
-    if (rb == 0 && lane == 0) meta[M_TILES] = (unsigned long long)tile_prefix[nrb];
-}
-
-// tiles owned by one shard: tile = shard + j * n_shards for j in [0, count)
-struct TileWalk {
-    const int2* tile_rc;
-    const unsigned long long* meta;
-    long long tile_cap;
-    int shard, n_shards;
-    int j0, j1;          // this launch covers j in [j0, j1) (clipped to the shard's tile count)
-    __device__ __forceinline__ int count() const {
-        const long long total = (long long)min((unsigned long long)tile_cap, meta[M_TILES]);
-        const long long mine = total > shard ? (total - shard + n_shards - 1) / n_shards : 0;
-        return (int)min((long long)j1, mine);
-    }
-    __device__ __forceinline__ int2 tile(int j) const { return __ldg(tile_rc + shard + (long long)j * n_shards); }
-};
-
-// ============================================================================
-// K3: LSH band signatures.  For the g-th sorted genome and band b, sig(b,g) = 16 bits of a mix
-// of the band's n_rows buckets.  Equal bands => equal signatures, so "some band equal"
-// (criteria_sketch.hpp:71-79) implies "some signature equal"; the converse is checked exactly
-// by k_smh_verify.  Two bands share one 32-bit word: word w holds bands 2w (low half) and 2w+1.
-//   sigR[w][g] =  sig              (row operand)
-//   sigC[w][g] = -sig per half     (column operand), so  r + c == 0 (mod 2^16)  <=>  equal
-// An odd band count leaves a pad half that can never match (row 0, column 1); pad genomes hold
-// row 0 / column 0x0101.
-// ============================================================================
-__device__ __forceinline__ uint32_t band_sig16(const uint64_t* v, int n_rows) {
-    uint64_t h = 0x243F6A8885A308D3ull;
-    for (int r = 0; r < n_rows; ++r) h = mix64(h ^ v[r]);
-    return (uint32_t)(h >> 48);
-}
-
-__global__ void __launch_bounds__(256)
-k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long npad, int m_aux,
-                 int n_rows, int n_bands, uint32_t* __restrict__ sigR, uint32_t* __restrict__ sigC) {
-    // thread = (genome, band), band fastest: a warp reads consecutive bands of one genome, i.e. one contiguous
-    // run of its sketch; lane pairs then pack two bands into a word
-    const int nw = (n_bands + 1) >> 1;
-    const int nb2 = nw * 2;                                    // bands rounded up to even (pad band never matches)
-    const long long total = npad * nb2;                        // pad genomes included: row halves 0, column halves 0x0101
-    const long long stride = (long long)gridDim.x * blockDim.x;          // even: lane pairs stay together
-    for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 - (threadIdx.x & 31) < total;
-         idx0 += stride) {
-        const bool live = idx0 < total;
-        const long long g = live ? idx0 / nb2 : 0;
-        const int b = live ? (int)(idx0 - g * nb2) : 0;
-        uint32_t sig = 0;
-        const bool real = live && b < n_bands && g < n;
-        if (real) sig = band_sig16(aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows, n_rows);
-        const uint32_t other = __shfl_down_sync(0xffffffffu, sig, 1);
-        const bool other_real = __shfl_down_sync(0xffffffffu, (int)real, 1) != 0;
-        if (live && !(b & 1) && g >= n) {                      // pad genome: never matches anything
-            const int w = b >> 1;
-            sigR[(size_t)w * npad + g] = 0u;
-            sigC[(size_t)w * npad + g] = 0x01010101u;
-        } else if (live && !(b & 1)) {
-            const uint32_t r1 = other_real ? other : 0u;
-            const uint32_t c1 = other_real ? ((0u - other) & 0xffffu) : 1u;   // pad half: row 0, column 1
-            const int w = b >> 1;
-            sigR[(size_t)w * npad + g] = sig | (r1 << 16);
-            sigC[(size_t)w * npad + g] = ((0u - sig) & 0xffffu) | (c1 << 16);
-        }
-    }
-}
-
-// ============================================================================
-// K4: smh_a tile pre-filter.  One CTA = one 128x128 tile of the sorted pair space,
-// 256 threads, each an 8x8 register micro-tile.  Per signature word (two bands): 4 LDS.128 and
-// 64 x VIADDMNMX.U16x2 (acc = min(acc, r + c) per 16-bit half); a zero half at the end
-// <=> some band signature matched.  Candidates (rare) leave through warp-aggregated atomics.
-// ============================================================================
-// Accumulate: acc = min(acc, r + c) per 16-bit half in ONE instruction (VIADDMNMX.U16x2); the column
-// operand holds the negated halves, so a half reaches 0 exactly when the two signatures are equal.
-// Measured alternatives on B200 (n=100k, 4.66e8 CB pairs): XOR+MIN on 32-bit signatures 1.22 ms;
-// (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__global__ void __launch_bounds__(256, FILTER_CTAS_PER_SM)
-k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,
-                  TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
-                  uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
-                  unsigned long long cand_cap) {
-    // three buffers: the signature words of the next two (tile, chunk) items stream in with cp.async while
-    // the current one is being compared — a tile's 8 KiB arrive in about the time its 512 instructions per
-    // thread take, so without the overlap the ALU pipe idles half the time; with three buffers ONE barrier
-    // per item both publishes the item's copies and frees the buffer of the item before it
-    constexpr int NBUF = 3;
-    __shared__ __align__(16) uint32_t sR[NBUF][SIG_CHUNK][TILE];
-    __shared__ __align__(16) uint32_t sC[NBUF][SIG_CHUNK][TILE];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const int jend = tw.count();
-    const int nchunk = (n_words + SIG_CHUNK - 1) / SIG_CHUNK;
-    // persistent CTAs: the shard's tile count lives in device memory, so no host sync sizes the grid
-    const int j_first = tw.j0 + (int)blockIdx.x;
-    if (j_first >= jend) return;
-    const int my_tiles = (jend - 1 - j_first) / (int)gridDim.x + 1;
-    const int n_items = my_tiles * nchunk;                 // items = (tile, chunk of SIG_CHUNK words), no divisions below
-
-    auto tile_at = [&](int t) -> int2 { return t < my_tiles ? tw.tile(j_first + t * (int)gridDim.x) : make_int2(0, 0); };
-    auto stage = [&](int ch, int2 rc, int buf) {           // queue the loads of one item
-        const int b0 = ch * SIG_CHUNK;
-        const int nb = min(SIG_CHUNK, n_words - b0);
-        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
-        for (int idx = tid; idx < nb * 64; idx += 256) {   // nb words x (128 row + 128 col) / 4 per copy
-            const int bb = idx >> 6, part = idx & 63, x = (part & 31) * 4;
-            if (part < 32) cp_async16(&sR[buf][bb][x], sigR + (size_t)(b0 + bb) * npad + r0 + x);
-            else cp_async16(&sC[buf][bb][x], sigC + (size_t)(b0 + bb) * npad + c0 + x);
-        }
-        cp_async_commit();
-    };
-    // zero 16-bit half somewhere in x
-    auto has_zero_half = [](uint32_t x) { return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u; };
-
-    uint32_t acc[8][8];
-    // (t, ch) = item being compared; (ts, chs) = the next item to copy, two items ahead.  The coordinates of the
-    // copy cursor's tile and of the tile after it are fetched ahead of use (rc_s, rc_sn).
-    int t = 0, ch = 0, buf = 0;
-    int ts = 0, chs = 0, bufs = 0;
-    int2 rc_s = tile_at(0), rc_sn = tile_at(1);
-    __shared__ int2 s_rc[4];                               // coordinates of the tiles in flight, by tile number & 3
-    auto stage_next = [&]() {
-        if (chs == 0 && tid == 0) s_rc[ts & 3] = rc_s;
-        stage(chs, rc_s, bufs);
-        bufs = bufs + 1 == NBUF ? 0 : bufs + 1;
-        if (++chs == nchunk) {
-            chs = 0;
-            ++ts;
-            rc_s = rc_sn;
-            rc_sn = tile_at(ts + 1);
-        }
-    };
-    int staged = 0;
-    for (; staged < 2 && staged < n_items; ++staged) stage_next();
-    for (int item = 0; item < n_items; ++item) {
-        if (item + 1 < staged) cp_async_wait<1>();          // everything but the newest group has landed
-        else cp_async_wait<0>();
-        __syncthreads();
-        if (staged < n_items) { stage_next(); ++staged; }   // into the buffer item-1 was compared from
-        const int nb = min(SIG_CHUNK, n_words - ch * SIG_CHUNK);
-        int bb = 0;
-        if (ch == 0) {                                      // first word of a tile: no accumulator to read
-            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[buf][0][ty * 8]);
-            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[buf][0][ty * 8 + 4]);
-            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[buf][0][tx * 4]);
-            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[buf][0][64 + tx * 4]);
-            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], 0xffffffffu);
-            bb = 1;
-        }
-        for (; bb < nb; ++bb) {
-            const uint4 ra = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8]);
-            const uint4 rb = *reinterpret_cast<const uint4*>(&sR[buf][bb][ty * 8 + 4]);
-            const uint4 ca = *reinterpret_cast<const uint4*>(&sC[buf][bb][tx * 4]);
-            const uint4 cb = *reinterpret_cast<const uint4*>(&sC[buf][bb][64 + tx * 4]);
-            const uint32_t rs[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-            const uint32_t cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = __viaddmin_u16x2(rs[a], cs[b], acc[a][b]);
-        }
-        buf = buf + 1 == NBUF ? 0 : buf + 1;
-        if (++ch < nchunk) continue;
-        const int t_done = t;
-        ch = 0;
-        ++t;
-        // per-row minima first: a 16-bit signature collides by chance once per ~64 thread-tiles, so four
-        // warps in ten come here with ONE row to look at, not 64 cells
-        uint32_t rowmin[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const uint32_t m0 = __vimin3_u16x2(acc[a][0], acc[a][1], acc[a][2]);
-            const uint32_t m1 = __vimin3_u16x2(acc[a][3], acc[a][4], acc[a][5]);
-            rowmin[a] = __vimin3_u16x2(m0, m1, __vminu2(acc[a][6], acc[a][7]));
-        }
-        const uint32_t any = __vimin3_u16x2(__vimin3_u16x2(rowmin[0], rowmin[1], rowmin[2]),
-                                            __vimin3_u16x2(rowmin[3], rowmin[4], rowmin[5]),
-                                            __vminu2(rowmin[6], rowmin[7]));
-        if (!has_zero_half(any)) continue;
-        const int2 rc = s_rc[t_done & 3];                   // written when the tile was queued, barriers ago
-        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
-        unsigned long long cells = 0ull;                    // bit a*8+b: cell (a,b) has a matching band signature
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            if (!has_zero_half(rowmin[a])) continue;
-            uint32_t rowbits = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) rowbits |= has_zero_half(acc[a][b]) ? (1u << b) : 0u;
-            cells |= (unsigned long long)rowbits << (a * 8);
-        }
-        while (cells) {
-            const int bit = __ffsll((long long)cells) - 1;
-            cells &= cells - 1;
-            const int a = bit >> 3, b = bit & 7;
-            const int i = r0 + ty * 8 + a;
-            const int k = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
-            if (i >= n || k < lo[i] || k > hi[i]) continue;
-            const unsigned long long slot = warp_claim(cand_count);
-            if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
-        }
-    }
-}
-
-// exact smh_a on the candidates: include/criteria_sketch.hpp:66-81.  Thread per candidate.
-// A band can only be equal if its 16-bit signatures are, so the thread re-reads the (L2-resident)
-// signature words of both genomes, and compares bucket by bucket only the bands whose signatures
-// match, stopping at the first band that is really equal: ~2 x 64 B of auxiliary sketch per
-// candidate instead of 2 x 8m B.
-__global__ void __launch_bounds__(256)
-k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict__ sigR, long long npad, int m_aux,
-             int n_rows, int n_bands, const uint2* __restrict__ cand,
-             const unsigned long long* __restrict__ ncand_dev, unsigned long long cand_cap,
-             uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const long long ncand = (long long)min(*ncand_dev, cand_cap);
-    const int n_words = (n_bands + 1) >> 1;
-    for (long long ci = blockIdx.x * (long long)blockDim.x + threadIdx.x; ci < ncand;
-         ci += (long long)gridDim.x * blockDim.x) {
-        const uint2 pr = cand[ci];
-        const uint64_t* v1 = aux_sorted + (size_t)pr.x * m_aux;
-        const uint64_t* v2 = aux_sorted + (size_t)pr.y * m_aux;
-        bool hit = false;
-        for (int w = 0; w < n_words && !hit; ++w) {
-            const uint32_t x = __ldg(sigR + (size_t)w * npad + pr.x) ^ __ldg(sigR + (size_t)w * npad + pr.y);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int b = 2 * w + half;
-                if (hit || b >= n_bands || ((x >> (16 * half)) & 0xffffu) != 0) continue;
-                bool eq = true;
-                for (int r = 0; r < n_rows; ++r)
-                    if (__ldg(v1 + (size_t)b * n_rows + r) != __ldg(v2 + (size_t)b * n_rows + r)) { eq = false; break; }
-                hit = eq;
-            }
-        }
-        if (hit) {
-            const unsigned long long slot = warp_claim(pair_count);
-            if (slot < pair_cap) pairs[slot] = pr;
-        }
-    }
-}
-
-// CB only: every pair of the band inside this tile
-__global__ void __launch_bounds__(256)
-k_tile_enum(TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
-            uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
-    const int jend = tw.count();
-    for (int j = tw.j0 + (int)blockIdx.x; j < jend; j += (int)gridDim.x) {
-        const int2 rc = tw.tile(j);
-        const int r0 = rc.x * TILE, c0 = rc.y * TILE;
-        for (int idx = threadIdx.x; idx < TILE * TILE; idx += 256) {
-            const int i = r0 + (idx >> 7), k = c0 + (idx & (TILE - 1));
-            if (i >= n || k >= n) continue;
-            if (k < lo[i] || k > hi[i]) continue;
-            const unsigned long long slot = warp_claim(pair_count);
-            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
-        }
-    }
-}
-
-// ============================================================================
-// K4': hll_a / hll_an tile filter.  Thread per pair; lanes = 32 consecutive columns of one
-// row pair (R=2 rows share each column word).  Aux registers come transposed
-// (auxT[word][genome]) so a warp's column load is one coalesced 128 B line and the row word
-// is a broadcast.  Each thread keeps R private histograms [bin][64 threads] in static smem
-// (same PRMT addressing as k_pair_hist), then runs the Ertl MLE on its own columns and the
-// criterion:
-//   hll_a  include/criteria_sketch.hpp:60-64,36-43   hll_an  :52-58,22-34
-// One CTA (2 warps) handles a 32-row x 128-col quarter of a tile.
-// ============================================================================
-struct StopHll {      // early exit of the MLE: the criterion already fails at the lower bound
-    double tau;
-    unsigned long long e1, e2;
-    float zs;
-    int order_n;
-    int an;
-    __device__ __forceinline__ bool crit(double t) const {
-        return an ? selb::crit_hll_an(tau, e1, e2, t, zs, order_n) : selb::crit_hll_a(tau, e1, e2, t, zs);
-    }
-    // both criteria are non-increasing in t only for Z*sigma >= 0 (the reference hard-codes Z = 1.96)
-    __device__ __forceinline__ bool operator()(double t_lb) const { return zs >= 0.f && !crit(t_lb); }
-};
-
-template <int AN>
-__global__ void __launch_bounds__(64)
-k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, TileWalk tw,
-                  const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
-                  const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
-                  uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
-                  unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
-    extern __shared__ __align__(1024) uint32_t hist_dyn[];   // 2 x [nbins][64 threads]
-    __shared__ int s_unit;
-    const int nbins = 64 - p_aux + 2;
-    uint32_t* hist0 = hist_dyn;
-    uint32_t* hist1 = hist_dyn + nbins * 64;
-    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
-    const int words = (1 << p_aux) >> 2;
-    const uint32_t bias0 = hist_bias(hist0), bias1 = hist_bias(hist1);
-    for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
-    __syncwarp();
-    const int uend = tw.count() * 4;
-    // persistent CTAs claim (tile, quarter) units from a device counter: units on the edge of the band hold
-    // few pairs, full ones 4096, so a static deal leaves a long tail
-    for (;;) {
-        __syncthreads();
-        if (t == 0) s_unit = tw.j0 * 4 + (int)atomicAdd(unit_counter, 1ull);
-        __syncthreads();
-        const int unit = s_unit;
-        if (unit >= uend) break;
-        const int2 rc = tw.tile(unit >> 2);
-        const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
-        // 16 row pairs x 4 column groups = 64 items, split over the 2 warps
-        for (int item = w; item < 64; item += 2) {
-            const int i0 = r0 + (item >> 2) * 2, i1 = i0 + 1;
-            const int k = c0 + (item & 3) * 32 + (int)lane;
-            const bool v0 = i0 < n && k < n && k >= lo[min(i0, n - 1)] && k <= hi[min(i0, n - 1)];
-            const bool v1 = i1 < n && k < n && k >= lo[min(i1, n - 1)] && k <= hi[min(i1, n - 1)];
-            if (!__any_sync(0xffffffffu, v0 || v1)) continue;
-            const uint32_t* colp = auxT + min((long long)k, npad - 1);
-            const uint32_t* row0 = auxT + min(i0, n - 1);
-            const uint32_t* row1 = auxT + min(i1, n - 1);
-#pragma unroll 2
-            for (int j = 0; j < words; ++j) {
-                const uint32_t cw = __ldg(colp + (size_t)j * npad);
-                const uint32_t a0 = __ldg(row0 + (size_t)j * npad);
-                const uint32_t a1 = __ldg(row1 + (size_t)j * npad);
-                const uint32_t m0 = max4_lt128(a0, cw) + bias0, m1 = max4_lt128(a1, cw) + bias1;
-                hist_inc_dual<0>(m0, m1, tb);
-                hist_inc_dual<1>(m0, m1, tb);
-                hist_inc_dual<2>(m0, m1, tb);
-                hist_inc_dual<3>(m0, m1, tb);
-            }
-            bool pass0 = false, pass1 = false;
-            if (v0) {
-                bool stopped = false;
-                const StopHll stop{tau, e[i0], e[k], zs, order_n, AN};
-                const double tu = selb::ertl_mle(hist0 + t, p_aux, 64, stop, &stopped);
-                pass0 = !stopped && stop.crit(tu);
-            }
-            if (v1) {
-                bool stopped = false;
-                const StopHll stop{tau, e[i1], e[k], zs, order_n, AN};
-                const double tu = selb::ertl_mle(hist1 + t, p_aux, 64, stop, &stopped);
-                pass1 = !stopped && stop.crit(tu);
-            }
-            for (int b = 0; b < nbins; ++b) { hist0[b * 64 + t] = 0; hist1[b * 64 + t] = 0; }
-            if (pass0) {
-                const unsigned long long slot = warp_claim(pair_count);
-                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i0, (uint32_t)k);
-            }
-            if (pass1) {
-                const unsigned long long slot = warp_claim(pair_count);
-                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i1, (uint32_t)k);
-            }
-        }
-    }
-}
-
-// ============================================================================
-// K4'' : hll_a / hll_an tile filter on BIT PLANES of the auxiliary sketches (p_aux >= 6).
-// Same tile walk, same thread-per-pair shape (lane = column, row word = broadcast), same MLE + criterion
-// as k_tile_filter_hll; the union histogram of a pair is built with the logic of k_pair_hist_planes
-// (LOP3 borrow-chain max, 3+3-bit decode, carry-save counting) instead of 2^p_aux shared-memory
-// read-modify-writes, and written once into the thread's shared-memory column for the estimator.
-//   auxP[(plane*nw + w)*npad + g] : word w (32 registers) of a plane of the g-th sorted genome
-//   agrange[g]                    : min | max<<8 of that genome's auxiliary registers
-// The 32 pairs of a warp step share one 32-value window (their genomes sit within the CB band of each
-// other, so their register ranges coincide); a step whose pairs do not fit one window takes the byte
-// path of k_tile_filter_hll for its pairs.
-// ============================================================================
-#ifndef HLLP_MIN_CTAS
-#define HLLP_MIN_CTAS 8
-#endif
-
-__global__ void __launch_bounds__(256)
-k_aux_planes(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, long long npad,
-             int p_aux, uint32_t* __restrict__ auxP) {
-    const int nw = (1 << p_aux) >> 5;
-    const long long total = n * nw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(idx / n);
-        const long long g = idx - (long long)w * n;
-        const uint4* src = reinterpret_cast<const uint4*>(aux + ((size_t)order[g] << p_aux) + (size_t)w * 32);
-        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-        const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) m |= ((((wd[q] >> b) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
-            auxP[((size_t)b * nw + w) * npad + g] = m;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_aux_range(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, int p_aux,
-            uint16_t* __restrict__ agrange) {
-    // one warp per genome: smallest / largest register value
-    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (g >= n) return;
-    const uint8_t* row = aux + ((size_t)order[g] << p_aux);
-    int vmin = 255, vmax = 0;
-    for (int j = lane; j < (1 << p_aux); j += 32) { const int v = row[j]; vmin = min(vmin, v); vmax = max(vmax, v); }
-    for (int o = 16; o; o >>= 1) {
-        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    }
-    if (lane == 0) agrange[g] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
-}
-
-// all word pairs of one (row, 32 columns) step for window G0: S / C2 end as the per-value carry-save state
-template <int G0>
-__device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
-                                                long long npad, int nw, uint32_t gmask, uint32_t (&x)[32]) {
-    uint32_t S[32], C2[32];
-#pragma unroll
-    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
-#pragma unroll 1
-    for (int w = 0; w < nw; w += 2) {
-        uint32_t M[2][6];
-        {
-            uint32_t a[2][6], b[2][6];
-#pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {
-                const size_t o0 = ((size_t)pl * nw + w) * (size_t)npad, o1 = o0 + (size_t)npad;
-                a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
-                b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
-            }
-            uint32_t lt0 = 0u, lt1 = 0u;
-#pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {
-                lt0 = lop3<0x8E>(a[0][pl], b[0][pl], lt0);
-                lt1 = lop3<0x8E>(a[1][pl], b[1][pl], lt1);
-            }
-#pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {
-                M[0][pl] = lop3<0xCA>(lt0, b[0][pl], a[0][pl]);
-                M[1][pl] = lop3<0xCA>(lt1, b[1][pl], a[1][pl]);
-            }
-        }
-        uint32_t L[2][8];
-#pragma unroll
-        for (int ws = 0; ws < 2; ++ws) {
-            L[ws][0] = lop3<0x01>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][1] = lop3<0x02>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][2] = lop3<0x04>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][3] = lop3<0x08>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][4] = lop3<0x10>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][5] = lop3<0x20>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][6] = lop3<0x40>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][7] = lop3<0x80>(M[ws][2], M[ws][1], M[ws][0]);
-        }
-#define SELB_AUX_GROUP(T)                                                                                 \
-        if (gmask & (1u << T)) {                                                                          \
-            const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
-            const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
-            uint32_t m0[8], m1[8], kk[8];                                                                 \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);                 \
-        }
-        SELB_AUX_GROUP(0)
-        SELB_AUX_GROUP(1)
-        SELB_AUX_GROUP(2)
-        SELB_AUX_GROUP(3)
-#undef SELB_AUX_GROUP
-    }
-#pragma unroll
-    for (int v = 0; v < 32; ++v) x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]);
-}
-
-template <int G0>
-__device__ __forceinline__ void aux_plane_hist(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
-                                               long long npad, int nw, uint32_t gmask, uint32_t* __restrict__ hcol,
-                                               int nbins) {
-    uint32_t x[32];
-    aux_plane_pairs<G0>(rowp, colp, npad, nw, gmask, x);
-    // the thread's histogram column: zeros outside the window, the counts inside
-    for (int b = 0; b < 8 * G0; ++b) hcol[b * 64] = 0u;
-#pragma unroll
-    for (int v = 0; v < 32; ++v)
-        if (8 * G0 + v < nbins) hcol[(8 * G0 + v) * 64] = x[v];
-    for (int b = 8 * G0 + 32; b < nbins; ++b) hcol[b * 64] = 0u;
-}
-
-template <int AN>
-__global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
-k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __restrict__ agrange,
-                         const uint32_t* __restrict__ auxT, long long npad, int p_aux, TileWalk tw,
-                         const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
-                         const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
-                         uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
-                         unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
-    extern __shared__ __align__(1024) uint32_t hist_dyn[];   // [nbins][64 threads]
-    __shared__ int s_unit;
-    const int nbins = 64 - p_aux + 2;
-    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
-    const int nw = (1 << p_aux) >> 5;
-    const int words = (1 << p_aux) >> 2;
-    uint32_t* hcol = hist_dyn + t;
-    const uint32_t bias0 = hist_bias(hist_dyn);
-    const int uend = tw.count() * 4;
-    for (;;) {
-        __syncthreads();
-        if (t == 0) s_unit = tw.j0 * 4 + (int)atomicAdd(unit_counter, 1ull);
-        __syncthreads();
-        const int unit = s_unit;
-        if (unit >= uend) break;
-        const int2 rc = tw.tile(unit >> 2);
-        const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
-        // 32 rows x 4 column groups = 128 steps, split over the 2 warps
-        for (int item = (int)w; item < 128; item += 2) {
-            const int i = r0 + (item >> 2);
-            const int k = c0 + (item & 3) * 32 + (int)lane;
-            if (i >= n) continue;
-            const bool v = k < n && k >= lo[i] && k <= hi[i];
-            if (!__any_sync(0xffffffffu, v)) continue;
-            const int kc = (int)min((long long)k, npad - 1);
-            // common value window of the step's pairs
-            const uint32_t ra = agrange[i], rb = agrange[min(kc, n - 1)];
-            int vlo = v ? max((int)(ra & 0xff), (int)(rb & 0xff)) : 255;
-            int vhi = v ? max((int)(ra >> 8), (int)(rb >> 8)) : 0;
-            for (int o = 16; o; o >>= 1) {
-                vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, o));
-                vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
-            }
-            const int g0 = min(vlo >> 3, 4);
-            if ((vhi >> 3) <= g0 + 3) {
-                uint32_t gmask = 0;
-                for (int tt = 0; tt < 4; ++tt)
-                    if ((g0 + tt) >= (vlo >> 3) && (g0 + tt) <= (vhi >> 3)) gmask |= 1u << tt;
-                const uint32_t* rowp = auxP + i;
-                const uint32_t* colp = auxP + kc;
-                switch (g0) {
-                    case 0: aux_plane_hist<0>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 1: aux_plane_hist<1>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 2: aux_plane_hist<2>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 3: aux_plane_hist<3>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    default: aux_plane_hist<4>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                }
-            } else {
-                // register ranges too far apart for one window: byte path (shared-memory counters)
-                for (int b = 0; b < nbins; ++b) hcol[b * 64] = 0u;
-                const uint32_t* colp = auxT + kc;
-                const uint32_t* row0 = auxT + i;
-                for (int j = 0; j < words; ++j) {
-                    const uint32_t m0 = max4_lt128(__ldg(row0 + (size_t)j * npad), __ldg(colp + (size_t)j * npad)) + bias0;
-                    hist_inc2<0, 1>(m0, tb);
-                    hist_inc2<2, 3>(m0, tb);
-                }
-            }
-            bool pass = false;
-            if (v) {
-                bool stopped = false;
-                const StopHll stop{tau, e[i], e[k], zs, order_n, AN};
-                const double tu = selb::ertl_mle(hcol, p_aux, 64, stop, &stopped);
-                pass = !stopped && stop.crit(tu);
-            }
-            if (pass) {
-                const unsigned long long slot = warp_claim(pair_count);
-                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
-            }
-        }
-    }
-}
-
-// ============================================================================
-// K6: union estimate -> Jaccard -> tau test -> emit
-//   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
-// ============================================================================
-__global__ void __launch_bounds__(128)
-k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
-                const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
-                const unsigned long long* __restrict__ e, int p, double tau,
-                uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
-                unsigned long long* __restrict__ out_count, unsigned long long out_cap,
-                uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
-                unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
-    // J is non-increasing in t: once it is below tau (and outside the near-tau window) at the
-    // MLE's lower bound the pair can neither be emitted nor listed as near
-    struct StopJ {
-        double tau, slack;
-        unsigned long long e1, e2;
-        __device__ __forceinline__ bool operator()(double t_lb) const {
-            return selb::jaccard(e1, e2, t_lb) < tau - slack;
-        }
-    };
-    const long long npairs = (long long)min(*npairs_dev, npairs_cap);
-    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
-         pi += (long long)gridDim.x * blockDim.x) {
-        const uint2 pr = pairs[pi];
-        const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
-        bool stopped = false;
-        const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
-        if (stopped) continue;
-        const double jac = selb::jaccard(e1, e2, t);
-        const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;
-        if (jac >= tau) {
-            const unsigned long long slot = warp_claim(out_count);
-            if (slot < out_cap) { out_keys[slot] = key; out_j[slot] = jac; }
-        }
-        if (fabs(jac - tau) <= 1e-6 * fabs(tau)) {
-            const unsigned long long slot = warp_claim(near_count);
-            if (slot < near_cap) { near_keys[slot] = key; near_j[slot] = jac; }
-        }
-    }
-}
-
-// ============================================================================
-// K7: (i,k) print order of the reference (selection.cpp:297-300) for SPARSE outputs: bucket by row
-// (count -> scan -> scatter), then every element finds its place inside its row by counting the
-// smaller columns.  Four small launches instead of the ~9 of a 49-bit radix sort; rows hold a
-// handful of pairs (cluster mates), so the quadratic in-row step is a few loads per element.
-// ============================================================================
-__global__ void __launch_bounds__(256)
-k_rowsort_count(const uint64_t* __restrict__ keys, long long cnt, int32_t* __restrict__ rowcnt) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e < cnt) atomicAdd(rowcnt + (keys[e] >> 32), 1);
-}
-
-__global__ void __launch_bounds__(256)
-k_rowsort_scatter(const uint64_t* __restrict__ keys, const double* __restrict__ jac, long long cnt,
-                  int32_t* __restrict__ rowcnt, const int32_t* __restrict__ rowoff,
-                  uint64_t* __restrict__ tkeys, double* __restrict__ tj) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= cnt) return;
-    const uint64_t key = keys[e];
-    const uint32_t i = (uint32_t)(key >> 32);
-    const int pos = rowoff[i] + atomicSub(rowcnt + i, 1) - 1;    // counts back down to zero
-    tkeys[pos] = key;
-    tj[pos] = jac[e];
-}
-
-__global__ void __launch_bounds__(256)
-k_rowsort_rank(const uint64_t* __restrict__ tkeys, const double* __restrict__ tj, long long cnt,
-               const int32_t* __restrict__ rowoff, uint64_t* __restrict__ out_keys, double* __restrict__ out_j) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= cnt) return;
-    const uint64_t key = tkeys[e];
-    const uint32_t i = (uint32_t)(key >> 32);
-    const int a = rowoff[i], b = rowoff[i + 1];
-    int r = 0;
-    for (int t = a; t < b; ++t) r += tkeys[t] < key;      // keys are unique
-    out_keys[a + r] = key;
-    out_j[a + r] = tj[e];
-}
-
-// ============================================================================
-// Peer-memory gather (multi-GPU, one process per GPU): every rank pushes its emitted (key, J)
-// list straight into the ROOT GPU's landing zone with plain stores over NVLink/NVSwitch (the zone
-// is mapped into each process with CUDA IPC).  One system-scope atomicAdd claims a contiguous
-// block per rank, a second one signals completion; the root spins on its own memory until all
-// ranks have signalled, then sorts the merged list.  No NCCL call and no host round trip between
-// the emit kernel and the merged result (SURVEY.md §8e "gather of (i,k,J) lists to GPU 0").
-//   landing zone: GatherHdr | keys[2][cap] | jac[2][cap] | near_keys[2][ncap] | near_j[2][ncap]
-//   two buffers (epoch parity) so that a fast rank may already push run e+1 while the root still
-//   merges run e; `consumed` stops it from getting two runs ahead.
-// ============================================================================
-struct GatherHdr {
-    unsigned long long count[2];        // slots claimed per parity
-    unsigned long long near_count[2];
-    unsigned int done[2];               // ranks whose push is complete, per parity
-    unsigned int consumed;              // runs the root has merged (monotone)
-    unsigned int error;                 // 1: a wait timed out
-    unsigned long long pad[26];
-};
-static_assert(sizeof(GatherHdr) == 256, "landing-zone header is 256 bytes");
-
-struct GatherPush {                     // local to each rank
-    unsigned long long base, near_base;
-    unsigned int go, blocks_done;
-};
-
-struct GatherZone {                     // pointers into the (local or IPC-mapped) landing zone
-    GatherHdr* hdr;
-    uint64_t* keys;                     // [2][cap]
-    double* jac;
-    uint64_t* near_keys;                // [2][near_cap]
-    double* near_j;
-    unsigned long long cap, near_cap;
-};
-
-__device__ __forceinline__ unsigned long long gtime_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
-
-// one thread: (optionally) make sure the pass did not overflow, wait until the buffer of this parity
-// has been merged by the root two runs ago, claim the rank's block in the root's lists
-__global__ void k_gather_claim(GatherZone z, unsigned int epoch, unsigned long long* __restrict__ meta, int check,
-                               unsigned long long cand_cap, unsigned long long pair_lim, unsigned long long out_cap,
-                               unsigned long long tile_cap, unsigned long long near_cap_local,
-                               GatherPush* __restrict__ st) {
-    if (threadIdx.x | blockIdx.x) return;
-    st->go = 0;
-    st->blocks_done = 0;
-    if (check && (meta[M_CAND] > cand_cap || meta[M_PAIRS] > pair_lim || meta[M_OUT] > out_cap ||
-                  meta[M_TILES] > tile_cap))
-        return;                              // the host redoes the pass and pushes afterwards
-    if (epoch >= 2) {
-        const unsigned long long t0 = gtime_ns();
-        while (*(volatile unsigned int*)&z.hdr->consumed + 1u < epoch) {
-            if (gtime_ns() - t0 > GATHER_TIMEOUT_NS) { meta[M_PUSHED] = 2; return; }
-            __nanosleep(200);
-        }
-    }
-    const unsigned int b = epoch & 1u;
-    st->base = atomicAdd_system(&z.hdr->count[b], meta[M_OUT]);
-    st->near_base = atomicAdd_system(&z.hdr->near_count[b], min(meta[M_NEAR], near_cap_local));
-    st->go = 1;
-    meta[M_PUSHED] = 1;
-}
-
-// all CTAs: copy the rank's lists into its block of the root's lists; the last CTA signals
-__global__ void __launch_bounds__(256)
-k_gather_copy(GatherZone z, unsigned int epoch, const unsigned long long* __restrict__ meta,
-              unsigned long long near_cap_local, const uint64_t* __restrict__ keys, const double* __restrict__ jac,
-              const uint64_t* __restrict__ near_keys, const double* __restrict__ near_j, GatherPush* __restrict__ st) {
-    if (!st->go) return;
-    const unsigned int b = epoch & 1u;
-    const unsigned long long cnt = meta[M_OUT], ncnt = min(meta[M_NEAR], near_cap_local);
-    const unsigned long long base = st->base, nbase = st->near_base;
-    uint64_t* dk = z.keys + b * z.cap;
-    double* dj = z.jac + b * z.cap;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cnt;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long slot = base + i;
-        if (slot < z.cap) { dk[slot] = keys[i]; dj[slot] = jac[i]; }
-    }
-    uint64_t* nk = z.near_keys + b * z.near_cap;
-    double* nj = z.near_j + b * z.near_cap;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < ncnt;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long slot = nbase + i;
-        if (slot < z.near_cap) { nk[slot] = near_keys[i]; nj[slot] = near_j[i]; }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1) {
-            st->blocks_done = 0;
-            __threadfence_system();
-            atomicAdd_system(&z.hdr->done[b], 1u);
-        }
-    }
-}
-
-// root: wait for every rank's signal, then publish the merged counts where the host can read them
-__global__ void k_gather_wait(GatherZone z, unsigned int epoch, unsigned int world, const GatherPush* __restrict__ st,
-                              unsigned long long* __restrict__ merged /* [count, near_count, error] */) {
-    if (threadIdx.x | blockIdx.x) return;
-    if (!st->go) { merged[2] = 2; return; }      // the root's own pass is being redone: nothing to wait for yet
-    const unsigned int b = epoch & 1u;
-    const unsigned long long t0 = gtime_ns();
-    unsigned long long err = 0;
-    while (*(volatile unsigned int*)&z.hdr->done[b] < world) {
-        if (gtime_ns() - t0 > GATHER_TIMEOUT_NS) { err = 1; z.hdr->error = 1; break; }
-        __nanosleep(100);
-    }
-    __threadfence_system();
-    merged[0] = *(volatile unsigned long long*)&z.hdr->count[b];
-    merged[1] = *(volatile unsigned long long*)&z.hdr->near_count[b];
-    merged[2] = err;
-}
-
-// root, after the merge of this parity has been copied out: hand the buffer back
-__global__ void k_gather_release(GatherZone z, unsigned int epoch) {
-    if (threadIdx.x | blockIdx.x) return;
-    const unsigned int b = epoch & 1u;
-    z.hdr->count[b] = 0;
-    z.hdr->near_count[b] = 0;
-    z.hdr->done[b] = 0;
-    __threadfence_system();
-    *(volatile unsigned int*)&z.hdr->consumed = epoch + 1u;
-}
+#include "kernels/helpers.inl"
+#include "kernels/union_bytes.inl"
+#include "kernels/union_planes.inl"
+#include "kernels/load_kernels.inl"
+#include "kernels/tiles.inl"
+#include "kernels/filter_smh.inl"
+#include "kernels/filter_hll.inl"
+#include "kernels/estimate_sort.inl"
+#include "kernels/gather.inl"
 
 // ============================================================================
 // host side
