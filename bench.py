@@ -353,9 +353,22 @@ def main():
                 "unit_def": f"{per_pair_filter} B per CB-passing pair x pairs_cb(shard)"}
     dom = k_union if k_union["ms"] >= k_filter["ms"] else k_filter
     ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    # the same launch against the integer pipe it is actually bound by: the bit-plane union kernel issues
+    # 8 steps x (20 max + 16 decode + 4 groups x 34) = 1376 LOP3 per pair and lane (profiles/r01_ncu_summary.md);
+    # the LOP3 rate of the SM was measured with tools/ubench/int_pipes.cu (profiles/r01_int_pipes_ubench.txt)
+    int_alu = None
+    if dom["name"] == "k_pair_hist_planes" and dom["ms"] > 0:
+        sm_clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        lane_ops = 1376.0 * 32.0 * st0["pairs_aux"]
+        a_int = lane_ops / (dom["ms"] * 1e-3) / sm_clk / n_sm
+        int_alu = {"bound": "int_alu", "achieved": a_int, "peak": 63.0, "unit": "LOP3 lane-ops/clk/SM",
+                   "frac": a_int / 63.0,
+                   "def": "1376 LOP3 per pair and lane x 32 lanes x pairs_aux / launch time / SM clock / SMs; peak measured"}
     roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(dom["name"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"], "bytes_def": dom["unit_def"],
+                "int_alu": int_alu,
                 "note": ("frac > 1 is possible: the union kernel reads 6-bit planes (24 KiB per pair, 20 KiB when all values "
                          "are below 32) and L2 serves repeated rows; its binding limit is the integer ALU pipe "
                          "(profiles/r01_ncu_summary.md)"),
