@@ -15,16 +15,18 @@
 // i.e. ~2.3-2.8 ALU-pipe operations per register instead of two shared-memory wavefronts per 32.
 // POPC issues at 16 lanes/clk/SM on B200 (LOP3: 63), hence the carry-save adders.
 // The planes are staged into shared memory by cp.async.bulk (TMA) copies completing on mbarriers;
-// one warp per CTA, ~9 CTAs per SM.
+// one warp per CTA, 16 CTAs per SM.
 // Pairs whose value range does not fit a 32-value window (never seen on real sketches) go to a
 // "wide" list and through the byte kernel.
 // layout: genome g at planes + g * 6 * m/8 bytes; chunk c (PL_CHUNK_REGS registers, or m if smaller) holds its
 //         6 planes back to back: [chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r
 // ============================================================================
-// chunk / ring geometry, measured at n=100k (511 521 pairs): 2048 regs x 4 stages x 16 CTAs/SM 1.94 ms,
-// 4096 x 3 x 12: 2.02 ms, 8192 x 2 x 9: 1.87 ms (fewer, longer steps: less pipeline control per register)
+// chunk / ring geometry, measured at n=100k (511 521 pairs), registers x stages x CTAs/SM:
+//   2048 x 4 x 16: 1.94 ms   4096 x 3 x 12: 2.02   8192 x 2 x 9: 1.86   8192 x 2 x 8: 1.97   8192 x 3 x 6: 2.38
+//   2048 x 2 x 16: 1.93      2048 x 3 x 16: 1.92   4096 x 2 x 16: 1.78  <- kept: 16 warps per SM and half
+//   the pipeline-control steps of the 2048-register chunks
 #ifndef PL_CHUNK_REGS_V
-#define PL_CHUNK_REGS_V 8192
+#define PL_CHUNK_REGS_V 4096
 #endif
 constexpr int PL_CHUNK_REGS = PL_CHUNK_REGS_V;
 constexpr int PL_NQ = PL_CHUNK_REGS / 64;   // uint2 per plane of a full chunk
@@ -159,7 +161,7 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
 // One warp per CTA.  Work comes in batches of 32 consecutive pairs claimed from a device counter (dynamic
 // balance, no tail): each lane fetches the descriptor of one pair of the batch (rows through `order`, value
 // window from grange), so the dependent global loads are paid once per 32 pairs and the warp then reads
-// descriptors with shuffles.  The pairs' planes flow chunk by chunk (8192 registers = 2 x 6 KiB) through a
+// descriptors with shuffles.  The pairs' planes flow chunk by chunk (4096 registers = 2 x 3 KiB) through a
 // ring of PL_STAGES shared-memory stages: lane 0 keeps PL_STAGES-1 bulk copies (TMA) in flight ahead of
 // the chunk being counted, across pair and batch boundaries.
 #ifndef PL_STAGES_V
@@ -167,7 +169,7 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
 #endif
 constexpr int PL_STAGES = PL_STAGES_V;
 #ifndef PL_MIN_CTAS
-#define PL_MIN_CTAS 9
+#define PL_MIN_CTAS 16
 #endif
 
 template <class Epi>
