@@ -204,6 +204,9 @@ struct selb200_ctx {
     DevBuf auxP, agrange;                // bit planes / register ranges of the auxiliary HLLs (sorted order)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
     int chunk_regs = 0;
+    // split form of the union pass (kernels/union_split.inl): 5 relative planes + high list per genome
+    bool union_split = false;
+    DevBuf split_rec, gmeta;
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
@@ -228,6 +231,7 @@ namespace {
 #include "kernels/helpers.inl"
 #include "kernels/union_bytes.inl"
 #include "kernels/union_planes.inl"
+#include "kernels/union_split.inl"
 #include "kernels/load_kernels.inl"
 #include "kernels/tiles.inl"
 #include "kernels/filter_smh.inl"
@@ -310,10 +314,30 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
     }
     // wide count, batch counter, kernel error word (adjacent words of meta[])
     if (!counters_are_zero) CK(cudaMemsetAsync(wide_count, 0, 24, s));
-    const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
-    k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
-                                                           c->grange.as<uint16_t>(), src, epi,
-                                                           c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+    if (c->union_split) {
+        const size_t ssmem = (size_t)PL_STAGES * 2 * split_chunk_bytes(c->chunk_regs) + 8 * PL_STAGES + 64 * sizeof(uint32_t);
+        static int s_per_sm = 0;
+        static size_t s_per_sm_smem = 0;
+        if (!s_per_sm || s_per_sm_smem != ssmem) {
+            cudaFuncSetAttribute(k_pair_hist_split<EpiWriteHist>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_per_sm, k_pair_hist_split<EpiWriteHist>, 32, ssmem) != cudaSuccess ||
+                s_per_sm < 1) {
+                cudaGetLastError();
+                s_per_sm = 4;
+            }
+            s_per_sm_smem = ssmem;
+        }
+        const int sgrid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * s_per_sm);
+        k_pair_hist_split<EpiWriteHist><<<sgrid, 32, ssmem, s>>>(c->split_rec.as<uint8_t>(), c->m, c->chunk_regs,
+                                                                c->gmeta.as<uint32_t>(), src, epi,
+                                                                c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+    } else {
+        const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
+        k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
+                                                               c->grange.as<uint16_t>(), src, epi,
+                                                               c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+    }
     CK(cudaGetLastError());
     // pairs whose value range exceeds the 32-value window: byte kernel, small persistent grid
     SrcWide wsrc{pairs, c->order_dev.as<int32_t>(), c->wide_list.as<uint32_t>(), wide_count};
@@ -382,7 +406,13 @@ int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, cons
         }
     }
     c->chunk_regs = (int)std::min<size_t>(c->m, (size_t)PL_CHUNK_REGS);
-    CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
+    if (c->union_split) {
+        const size_t items = c->m / (size_t)c->chunk_regs + 1;
+        CKR(c->split_rec.ensure((size_t)n * items * split_chunk_bytes(c->chunk_regs)));
+        CKR(c->gmeta.ensure((size_t)n * sizeof(uint32_t)));
+    } else {
+        CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
+    }
     CKR(c->grange.ensure((size_t)n * sizeof(uint16_t)));
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
@@ -444,7 +474,15 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
         c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1),
         c->grange.as<uint16_t>() + g0);
     CK(cudaGetLastError());
-    {   // bit-plane copy of the chunk for the union kernel
+    if (c->union_split) {   // relative planes + high lists of the chunk for the split union kernel
+        const size_t items = c->m / (size_t)c->chunk_regs + 1;
+        const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)c->sm_count * 8);
+        k_split_build<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
+                                           c->grange.as<uint16_t>() + g0, c->hist.as<uint32_t>() + (size_t)g0 * 64,
+                                           c->split_rec.as<uint8_t>() + (size_t)g0 * items * split_chunk_bytes(c->chunk_regs),
+                                           c->gmeta.as<uint32_t>() + g0);
+        CK(cudaGetLastError());
+    } else {   // bit-plane copy of the chunk for the union kernel
         const long long nblk = rows * (long long)(c->m >> 9);
         const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
         k_planes_from_bytes<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
@@ -608,6 +646,10 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // SELB200_UNION: planes (default) | split | bytes — form of the union pass, read per context
+        const char* e = getenv("SELB200_UNION");
+        c->union_split = e && !strcmp(e, "split");
+    }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return fail(SELB200_ECUDA, "cudaStreamCreate failed");
@@ -623,7 +665,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->split_rec, &c->gmeta};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);

@@ -1,6 +1,7 @@
-"""-m gpu: the bit-plane kernels against the byte kernels they replaced, at sizes the CPU oracle would take
-minutes for.  Both forms compute the same integer histograms, so pair lists, Jaccard bits and stage counts
-must be identical (SELB200_UNION=bytes / SELB200_HLLFILTER=bytes select the byte forms at library load)."""
+"""-m gpu: the three forms of the union pass (bit planes = default, split, bytes) and the two forms of the hll filter
+against each other, at sizes the CPU oracle would take minutes for.  All forms compute the same integer
+histograms, so pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=split|planes|bytes is
+read when a context is created, SELB200_HLLFILTER=bytes at library load)."""
 import hashlib
 import json
 import os
@@ -49,7 +50,11 @@ def _run(env_extra, tmp_path):
 
 
 def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
-    planes = _run({}, tmp_path)
+    default = _run({}, tmp_path)
+    split = _run({"SELB200_UNION": "split"}, tmp_path)
+    planes = _run({"SELB200_UNION": "planes"}, tmp_path)
     by = _run({"SELB200_UNION": "bytes", "SELB200_HLLFILTER": "bytes"}, tmp_path)
+    assert default == by
+    assert split == by
     assert planes == by
     assert all(v[1] > 1000 for v in planes.values())          # thousands of emitted pairs in every case

@@ -325,6 +325,27 @@ def test_wide_value_range_pairs_take_the_byte_kernel(gpu):
     compare(res, O.select(regs, 14, "cb", np.float32(0.97), threads=8), 0.97)
 
 
+def test_split_union_mixed_bases_and_long_lists(gpu, monkeypatch):
+    """SELB200_UNION=split (read when a context is created): the split union kernel counts the 16 values above base = 8*(min>>3) on bit planes and keeps every higher
+    register in a per-genome list.  Pairs whose genomes have different bases, or a list longer than its slot,
+    leave it for the byte kernel; lists of every length in between are merged exactly."""
+    monkeypatch.setenv("SELB200_UNION", "split")
+    plan = synth.make_plan(1200, 77)
+    regs = synth.hll(plan, 14).copy()
+    aux = synth.smh(plan, 128)
+    regs[::3] = np.maximum(regs[::3], 8)              # every third genome: smallest register 8 -> base 8
+    regs[5::50, ::8] = 30                             # 2048 high registers: longer than any list slot
+    regs[7::50, ::40] = 29                            # 410 high registers: a long list that still fits
+    regs[11::50, 100:140] = 51                        # the largest legal value, a run of neighbours
+    for crit, tau, a in (("cb", 0.93, None), ("smh_a", 0.8, aux)):
+        ora = O.select(regs, 14, crit, np.float32(tau), aux=a, threads=8)
+        assert ora["stage"][2] > 1000
+        with S.Selection(gpu) as sel:
+            sel.load(regs, a, aux_kind_of(crit))
+            for _ in range(3):
+                compare(sel.run(tau=np.float32(tau), criterion=crit), ora, tau)
+
+
 @pytest.mark.parametrize("criterion", ["hll_a", "hll_an"])
 @pytest.mark.parametrize("p_aux", [4, 5, 6, 7, 9, 12])
 def test_auxiliary_hll_precisions(gpu, criterion, p_aux):
