@@ -61,6 +61,7 @@ k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, 
     }
 }
 
+#ifndef SELB_EMUL   // tests/emul/cuda_emul.h supplies host versions of these five when the .inl runs on the CPU
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -92,6 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "}\n" ::"r"(bar), "r"(phase)
         : "memory");
 }
+#endif   // SELB_EMUL
 
 // One chunk (<= PL_CHUNK_REGS registers) against the running carry-save state.  Per step, lane q holds
 // two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so

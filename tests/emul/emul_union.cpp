@@ -1,17 +1,18 @@
-// emul_split.cpp — runs kernels/union_split.inl (k_split_build + k_pair_hist_split) on the CPU through cuda_emul.h
+// emul_union.cpp — runs the bit-plane forms of the union pass on the CPU through cuda_emul.h, from the same .inl
+// sources the GPU build compiles:
+//   kernels/union_planes.inl : k_planes_from_bytes + k_pair_hist_planes   (the default form)
+//   kernels/union_split.inl  : k_split_build + k_pair_hist_split          (SELB200_UNION=split)
 // and compares every pair's 64-bin histogram with the byte-wise definition
-//   hist[max(a[j], b[j])]++   (sketch/include/sketch/hll.h:1191-1206 of the reference).
-// Test infrastructure (tests/test_emul_split.py builds and runs it); exit code 0 = all cases identical.
+//   hist[max(a[j], b[j])]++   (sketch/include/sketch/hll.h:1191-1206 of the reference),
+// and the pairs each form hands to the byte kernel ("wide") with the rule it documents.
+// Test infrastructure (tests/test_emul_union.py builds and runs it); exit code 0 = all cases identical.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
 
+#define SELB_EMUL 1
 #include "cuda_emul.h"
-
-constexpr int PL_STAGES = 2;
-constexpr int PL_CHUNK_REGS = 4096;
-constexpr int PL_NQ = PL_CHUNK_REGS / 64;
 
 struct SrcPairs {
     const uint2* pairs;
@@ -33,6 +34,7 @@ struct EpiWriteHist {
     }
 };
 
+#include "../../cuda_selection_criteria_b200/csrc/kernels/union_planes.inl"
 #include "../../cuda_selection_criteria_b200/csrc/kernels/union_split.inl"
 
 namespace {
@@ -44,6 +46,7 @@ struct Case {
     double shared;                 // fraction of a genome's load that comes from a common core
     int clamp_hi;                  // registers are clamped to [0, clamp_hi]
     unsigned grid;
+    int outlier_every = 0;         // > 0: every such genome gets one register of value 50 (a range wider than 32)
 };
 
 int run_case(const Case& cs, uint64_t seed) {
@@ -67,6 +70,8 @@ int run_case(const Case& cs, uint64_t seed) {
             const int c = cs.shared > 0 ? (int)std::min<int>(core[j], cs.clamp_hi) : 0;
             regs[(size_t)g * m + j] = (uint8_t)std::max(c, draw(cs.load[g] * (1.0 - cs.shared)));
         }
+    if (cs.outlier_every > 0)
+        for (int g = 0; g < n; g += cs.outlier_every) regs[(size_t)g * m + 7] = 50;
     // per-genome histogram + range, as k_pair_hist(SrcSelf) / k_genome_cards leave them
     std::vector<uint32_t> ghist((size_t)n * 64, 0);
     std::vector<uint16_t> grange(n);
@@ -89,44 +94,71 @@ int run_case(const Case& cs, uint64_t seed) {
     for (int a = 0; a < n; ++a)
         for (int b = a + 1; b < n; ++b) pairs.push_back(a & 1 ? make_uint2(b, a) : make_uint2(a, b));
     const long long np = (long long)pairs.size();
-    std::vector<uint32_t> hist((size_t)np * 64, 0xDEADBEEFu), wide(np, 0);
-    unsigned long long counters[3] = {0, 0, 0};           // wide count, batch counter, error word
     unsigned long long np_dev = (unsigned long long)np;
     SrcPairs src{pairs.data(), nullptr, np, &np_dev};
-    EpiWriteHist epi{hist.data()};
-    std::memset(pl_smem, 0x5A, sizeof pl_smem);
-    emul_tma_bytes = emul_tma_expected = 0;
-    emul::launch(cs.grid, [&] {
-        k_pair_hist_split<EpiWriteHist>(rec, m, chunk_regs, gmeta.data(), src, epi, wide.data(), counters, counters + 1);
-    });
     int bad = 0;
-    if (counters[2]) { printf("  %s: kernel error word %llx\n", cs.name, counters[2]); ++bad; }
-    if (emul_tma_bytes != emul_tma_expected) { printf("  %s: expect_tx %llu != copied %llu\n", cs.name, (unsigned long long)emul_tma_expected, (unsigned long long)emul_tma_bytes); ++bad; }
-    std::vector<char> is_wide(np, 0);
-    for (unsigned long long w = 0; w < counters[0]; ++w) is_wide[wide[w]] = 1;
-    long long n_dense = 0, n_high = 0;
-    for (long long pi = 0; pi < np; ++pi) {
-        const uint32_t a = pairs[pi].x, b = pairs[pi].y;
-        const bool expect_wide = (gmeta[a] & 0xff) != (gmeta[b] & 0xff) || (gmeta[a] >> 8) == SPLIT_LEN_OVERFLOW ||
-                                 (gmeta[b] >> 8) == SPLIT_LEN_OVERFLOW;
-        if (expect_wide != (bool)is_wide[pi]) { printf("  %s: pair %lld wide=%d expected %d\n", cs.name, pi, is_wide[pi], expect_wide); ++bad; continue; }
-        if (expect_wide) continue;
-        uint32_t want[64] = {0};
-        for (size_t j = 0; j < m; ++j) want[std::max(regs[(size_t)a * m + j], regs[(size_t)b * m + j])]++;
-        ++n_dense;
-        n_high += (gmeta[a] >> 8) + (gmeta[b] >> 8);
-        if (std::memcmp(want, &hist[(size_t)pi * 64], sizeof want)) {
-            if (bad < 5) {
-                printf("  %s: pair %lld (%u,%u) base %u lens %u %u differs:", cs.name, pi, a, b, gmeta[a] & 0xff, gmeta[a] >> 8, gmeta[b] >> 8);
-                for (int v = 0; v < 64; ++v)
-                    if (want[v] != hist[(size_t)pi * 64 + v]) printf(" [%d] %u!=%u", v, hist[(size_t)pi * 64 + v], want[v]);
-                printf("\n");
+
+    // runs one form, then checks its wide set against `expect_wide` and every other pair against the definition
+    auto check = [&](const char* form, const std::function<void(EpiWriteHist, uint32_t*, unsigned long long*)>& run,
+                     const std::function<bool(uint32_t, uint32_t)>& expect_wide) {
+        std::vector<uint32_t> hist((size_t)np * 64, 0xDEADBEEFu), wide(np, 0);
+        unsigned long long counters[3] = {0, 0, 0};           // wide count, batch counter, error word
+        std::memset(pl_smem, 0x5A, sizeof pl_smem);
+        emul_tma_bytes = emul_tma_expected = 0;
+        run(EpiWriteHist{hist.data()}, wide.data(), counters);
+        int fbad = 0;
+        if (counters[2]) { printf("  %s/%s: kernel error word %llx\n", cs.name, form, counters[2]); ++fbad; }
+        if (emul_tma_bytes != emul_tma_expected) { printf("  %s/%s: expect_tx %llu != copied %llu\n", cs.name, form, (unsigned long long)emul_tma_expected, (unsigned long long)emul_tma_bytes); ++fbad; }
+        std::vector<char> is_wide(np, 0);
+        for (unsigned long long w = 0; w < counters[0]; ++w) is_wide[wide[w]] = 1;
+        long long n_done = 0;
+        for (long long pi = 0; pi < np; ++pi) {
+            const uint32_t a = pairs[pi].x, b = pairs[pi].y;
+            const bool ew = expect_wide(a, b);
+            if (ew != (bool)is_wide[pi]) { printf("  %s/%s: pair %lld wide=%d expected %d\n", cs.name, form, pi, is_wide[pi], ew); ++fbad; continue; }
+            if (ew) continue;
+            uint32_t want[64] = {0};
+            for (size_t j = 0; j < m; ++j) want[std::max(regs[(size_t)a * m + j], regs[(size_t)b * m + j])]++;
+            ++n_done;
+            if (std::memcmp(want, &hist[(size_t)pi * 64], sizeof want)) {
+                if (fbad < 5) {
+                    printf("  %s/%s: pair %lld (%u,%u) differs:", cs.name, form, pi, a, b);
+                    for (int v = 0; v < 64; ++v)
+                        if (want[v] != hist[(size_t)pi * 64 + v]) printf(" [%d] %u!=%u", v, hist[(size_t)pi * 64 + v], want[v]);
+                    printf("\n");
+                }
+                ++fbad;
             }
-            ++bad;
         }
-    }
-    printf("%-28s p=%d n=%d pairs=%lld split=%lld wide=%llu avg list=%.1f  %s\n", cs.name, cs.p, n, np, n_dense, counters[0],
-           n_dense ? (double)n_high / (2.0 * n_dense) : 0.0, bad ? "FAIL" : "ok");
+        printf("%-26s %-6s p=%d n=%d pairs=%lld counted=%lld wide=%llu  %s\n", cs.name, form, cs.p, n, np, n_done, counters[0], fbad ? "FAIL" : "ok");
+        bad += fbad;
+    };
+
+    // ---- split form ----
+    check("split",
+          [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
+              emul::launch(cs.grid, [&] {
+                  k_pair_hist_split<EpiWriteHist>(rec, m, chunk_regs, gmeta.data(), src, epi, wide, counters, counters + 1);
+              });
+          },
+          [&](uint32_t a, uint32_t b) {
+              return (gmeta[a] & 0xff) != (gmeta[b] & 0xff) || (gmeta[a] >> 8) == SPLIT_LEN_OVERFLOW ||
+                     (gmeta[b] >> 8) == SPLIT_LEN_OVERFLOW;
+          });
+
+    // ---- plane form (default) ----
+    std::vector<uint32_t> planes((size_t)n * 6 * (m >> 5), 0xA5A5A5A5u);
+    emul::launch(2, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes.data()); });
+    check("planes",
+          [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
+              emul::launch(cs.grid, [&] {
+                  k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide, counters, counters + 1);
+              });
+          },
+          [&](uint32_t a, uint32_t b) {   // the pair's values must fit 32 consecutive values starting at a multiple of 8
+              const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
+              return (hi >> 3) > std::min(lo >> 3, 4) + 3;
+          });
     free(rec);
     return bad;
 }
@@ -150,6 +182,10 @@ int main() {
         // genome 0 has another base: its 39 pairs are consecutive in the list, so whole batches are wide
         {"whole batches wide p10", 10, {9000, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 116, 117, 118,
                                         119, 120, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138}, 0.0, 55, 2},
+        // the plane kernel hands every pair of genomes 0, 3, 6, ... to the byte kernel (39 + 36 + ... consecutive pairs);
+        // for the split kernel the outlier is one more list entry
+        {"outliers p10", 10, {100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 116, 117, 118, 119,
+                              120, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138, 139}, 0.5, 54, 2, 3},
         {"many pairs few warps p10", 10, {50, 55, 60, 65, 70, 75, 80, 85, 90, 95, 100, 105, 110, 115, 120, 125, 130, 135}, 0.8, 55, 2},
     };
     uint64_t seed = 12345;
