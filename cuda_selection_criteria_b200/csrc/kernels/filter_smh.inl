@@ -58,6 +58,7 @@ k_smh_signatures(const uint64_t* __restrict__ aux_sorted, long long n, long long
 // operand holds the negated halves, so a half reaches 0 exactly when the two signatures are equal.
 // Measured alternatives on B200 (n=100k, 4.66e8 CB pairs): XOR+MIN on 32-bit signatures 1.22 ms;
 // (LOP3, IADD, LOP3) zero-half test on packed halves 1.07 ms; this form 0.86 ms.
+#ifndef SELB_EMUL   // tests/emul/cuda_emul.h supplies host versions
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -65,6 +66,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif   // SELB_EMUL
 
 __global__ void __launch_bounds__(256, FILTER_CTAS_PER_SM)
 k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict__ sigC, long long npad, int n_words,

@@ -1,5 +1,6 @@
 // helpers.inl — device helpers shared by the selection kernels (part of selb200.cu, inside its anonymous namespace)
 
+#ifndef SELB_EMUL   // byte-histogram helpers (inline PTX) and warp_claim: not used / replaced on the CPU emulator (tests/emul)
 // SWAR byte-wise max for bytes < 128 (HLL registers are <= 64-p+1 <= 63):
 // the top bit of each byte of (a|0x80..)-b is set iff a>=b, with no borrow between bytes;
 // PRMT in sign-replicate mode turns those bits into byte masks.  4 instructions per 4 registers
@@ -75,6 +76,8 @@ __device__ __forceinline__ unsigned long long warp_claim(unsigned long long* cou
     base = __shfl_sync(mask, base, leader);
     return base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
 }
+
+#endif   // SELB_EMUL
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;

@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(32, SPLIT_MIN_CTAS)
 k_pair_hist_split(const uint8_t* __restrict__ rec, size_t m, int chunk_regs, const uint32_t* __restrict__ gmeta,
                   SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
                   unsigned long long* __restrict__ batch_counter) {
+#ifndef SELB_EMUL   // the emulator's dynamic shared memory is a global array of this name
     extern __shared__ __align__(128) uint8_t pl_smem[];
+#endif
     constexpr uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     const int nchunks = (int)(m / (size_t)chunk_regs);

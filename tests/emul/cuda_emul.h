@@ -1,17 +1,23 @@
-// cuda_emul.h — just enough of the CUDA execution model to run a ONE-WARP-PER-CTA kernel of this repo on the
-// CPU, from the same .inl source the GPU build compiles (test infrastructure; used by tests/emul/*.cpp only).
+// cuda_emul.h — just enough of the CUDA execution model to run the kernels of this repo on the CPU, from the same
+// .inl sources the GPU build compiles (test infrastructure; used by tests/emul/*.cpp only).
 //
-// A warp is 32 std::threads in lock step at every warp-wide operation: a shuffle / vote is "everybody writes
-// its value, barrier, everybody reads, barrier".  That is valid for kernels that call warp-wide operations
-// only from converged code with the full mask, which the emulated kernels do.  Bulk copies (TMA) complete
-// immediately at issue, an mbarrier wait is a warp barrier (so the issuing lane's copy is visible), shared
-// memory is one global array (CTAs run one after the other).  Timing, phases and asynchrony are NOT modelled:
-// this checks arithmetic, index math and the producer/consumer walk, not the hardware protocol.
+// A CTA is blockDim.x std::threads; a warp is 32 of them in lock step at every warp-wide operation: a shuffle /
+// vote is "everybody writes its value, warp barrier, everybody reads, warp barrier"; __syncthreads is a CTA
+// barrier.  That is valid for kernels that call warp-wide operations only from converged code with the full
+// mask, which the emulated kernels do (warp_claim, which uses __activemask in divergent code, is replaced by a
+// plain atomic claim: same set of slots, another order).  Bulk copies (TMA) and cp.async complete immediately at
+// issue, an mbarrier wait is a warp barrier (so the issuing lane's copy is visible), __shared__ variables are
+// statics and the dynamic shared memory one global array (CTAs run one after the other).  Timing, phases and
+// asynchrony are NOT modelled: this checks arithmetic, index math and the control flow, not the hardware protocol.
 #pragma once
 #include <barrier>
 #include <cstdint>
 #include <cstring>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -21,72 +27,108 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__
+#define __shared__ static
 #define __align__(x)
 
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct int2 { int x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 struct dim3e { unsigned x = 1, y = 1, z = 1; };
 static thread_local dim3e threadIdx, blockIdx;
 static dim3e gridDim, blockDim;
 
 namespace emul {
-static std::barrier<>* bar = nullptr;
-static uint64_t xchg[32];
-static inline void sync() { bar->arrive_and_wait(); }
+struct Warp {
+    std::barrier<> bar;
+    uint64_t xchg[32];
+    explicit Warp(int lanes) : bar(lanes) {}
+};
+static thread_local Warp* warp = nullptr;
+static std::barrier<>* cta_bar = nullptr;
+static inline void sync() { warp->bar.arrive_and_wait(); }
 static inline uint64_t exchange(uint64_t mine, int src) {
-    xchg[threadIdx.x & 31] = mine;
+    warp->xchg[threadIdx.x & 31] = mine;
     sync();
-    const uint64_t v = xchg[src & 31];
+    const uint64_t v = warp->xchg[src & 31];
     sync();
     return v;
 }
-// run `body` as one CTA of 32 threads (one warp) for every block index of the grid
-static inline void launch(unsigned grid, const std::function<void()>& body) {
+// run `body` as CTAs of `block` threads (a multiple of 32) for every block index of the grid, one CTA at a time
+static inline void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
     gridDim.x = grid;
-    blockDim.x = 32;
+    blockDim.x = block;
     for (unsigned b = 0; b < grid; ++b) {
-        std::barrier<> br(32);
-        bar = &br;
+        std::barrier<> cb((std::ptrdiff_t)block);
+        cta_bar = &cb;
+        std::vector<std::unique_ptr<Warp>> warps;
+        for (unsigned w = 0; w < block / 32; ++w) warps.emplace_back(new Warp(32));
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < 32; ++t)
+        for (unsigned t = 0; t < block; ++t)
             th.emplace_back([&, t] {
                 threadIdx.x = t;
                 blockIdx.x = b;
+                warp = warps[t / 32].get();
                 body();
-                br.arrive_and_drop();     // a lane that returns early must not block the others
+                warp->bar.arrive_and_drop();     // a thread that returns early must not block the others
+                cb.arrive_and_drop();
             });
         for (auto& x : th) x.join();
     }
+    cta_bar = nullptr;
 }
+static inline void launch(unsigned grid, const std::function<void()>& body) { launch(grid, 32, body); }
 }  // namespace emul
 
 template <class T> static inline T __shfl_sync(uint32_t, T v, int src) { return (T)emul::exchange((uint64_t)v, src); }
-template <class T> static inline T __shfl_xor_sync(uint32_t, T v, int m) { return (T)emul::exchange((uint64_t)v, (int)(threadIdx.x ^ (unsigned)m)); }
+template <class T> static inline T __shfl_xor_sync(uint32_t, T v, int m) { return (T)emul::exchange((uint64_t)v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
 template <class T> static inline T __shfl_up_sync(uint32_t, T v, int d) {
-    const int lane = (int)threadIdx.x;
+    const int lane = (int)(threadIdx.x & 31);
     return (T)emul::exchange((uint64_t)v, lane >= d ? lane - d : lane);
 }
+template <class T> static inline T __shfl_down_sync(uint32_t, T v, int d) {
+    const int lane = (int)(threadIdx.x & 31);
+    return (T)emul::exchange((uint64_t)v, lane + d < 32 ? lane + d : lane);
+}
 static inline uint32_t __ballot_sync(uint32_t, bool p) {
-    emul::xchg[threadIdx.x] = p ? 1u : 0u;
+    emul::warp->xchg[threadIdx.x & 31] = p ? 1u : 0u;
     emul::sync();
     uint32_t m = 0;
-    for (int l = 0; l < 32; ++l) m |= (uint32_t)emul::xchg[l] << l;
+    for (int l = 0; l < 32; ++l) m |= (uint32_t)emul::warp->xchg[l] << l;
     emul::sync();
     return m;
 }
 static inline bool __any_sync(uint32_t m, bool p) { return __ballot_sync(m, p) != 0u; }
 static inline void __syncwarp() { emul::sync(); }
+static inline void __syncthreads() { emul::cta_bar->arrive_and_wait(); }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+// SIMD-in-word integer intrinsics of the smh filter (per unsigned 16-bit half)
+static inline uint32_t emul_half_op(uint32_t a, uint32_t b, uint32_t (*f)(uint32_t, uint32_t)) {
+    return (f(a & 0xffffu, b & 0xffffu) & 0xffffu) | (f(a >> 16, b >> 16) << 16);
+}
+static inline uint32_t __vminu2(uint32_t a, uint32_t b) {
+    return emul_half_op(a, b, [](uint32_t x, uint32_t y) { return x < y ? x : y; });
+}
+static inline uint32_t __vimin3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
+static inline uint32_t __viaddmin_u16x2(uint32_t a, uint32_t b, uint32_t c) {      // min(a + b, c) per half, sum mod 2^16
+    return __vminu2(emul_half_op(a, b, [](uint32_t x, uint32_t y) { return (x + y) & 0xffffu; }), c);
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> static inline T max(T a, T b) { return a < b ? b : a; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+// helpers.inl's warp_claim aggregates over __activemask(); here every thread claims its own slot
+static inline unsigned long long warp_claim(unsigned long long* counter) { return atomicAdd(counter, 1ull); }
+// cp.async: the copy is done when it is queued
+static inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
 
 // LOP3: bit i of the result = LUT[(a_i << 2) | (b_i << 1) | c_i]
 template <int LUT> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

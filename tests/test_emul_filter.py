@@ -1,0 +1,95 @@
+"""CPU-only: the CB + smh_a chain of a run (k_cb_bounds, k_rowblock_span, k_tile_table, k_smh_signatures,
+k_tile_filter_smh, k_smh_verify) compiled as host code from the .inl sources of the GPU build and run on the warp
+emulator (tests/emul/), held against the oracle decision by decision: the CB band of every row
+(src/selection.cpp:278-283, include/criteria_sketch.hpp:45-49), the number of pairs inside it, and the set of pairs
+with an equal LSH band (criteria_sketch.hpp:66-81) — the bit-exact gate of the north star, without a GPU."""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+from cuda_selection_criteria_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emulf") / "emul_filter"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "emul", "emul_filter.cpp"), "-o", str(out)], check=True)
+    return str(out)
+
+
+def oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands):
+    """Row by row as the reference loops: skip e_k == 0, stop the row at the first CB failure, then smh_a."""
+    ora = O.lib()
+    n, m = aux_sorted.shape
+    lo = np.zeros(n, np.int32)
+    hi = np.zeros(n, np.int32)
+    pairs = []
+    p_cb = 0
+    rows = [np.ascontiguousarray(aux_sorted[g]) for g in range(n)]
+    zeros = int(np.count_nonzero(e == 0))
+    for i in range(n):
+        lo[i] = max(i + 1, zeros)
+        k = lo[i]
+        while k < n and ora.oracle_cb(tau32, int(e[i]), int(e[k])):
+            p_cb += 1
+            if ora.oracle_smh_a(rows[i].ctypes.data, rows[k].ctypes.data, m, n_rows, n_bands):
+                pairs.append((i, k))
+            k += 1
+        hi[i] = k - 1
+    return lo, hi, p_cb, pairs
+
+
+def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid):
+    n, m = aux_sorted.shape
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<5i", n, m, n_rows, n_bands, int(np.count_nonzero(e == 0))))
+        f.write(struct.pack("<d", float(tau32)))          # tau = (double)(float) threshold, selection.cpp:81
+        f.write(np.ascontiguousarray(e, np.uint64).tobytes())
+        f.write(np.ascontiguousarray(aux_sorted, np.uint64).tobytes())
+    r = subprocess.run([exe, str(inp), str(outp), str(n_shards), str(grid)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(outp, "rb").read()
+    p_cb, tiles, cand, npairs = struct.unpack_from("<4q", raw, 0)
+    off = 32
+    lo = np.frombuffer(raw, np.int32, n, off); off += 4 * n
+    hi = np.frombuffer(raw, np.int32, n, off); off += 4 * n
+    pr = np.frombuffer(raw, np.uint32, 2 * npairs, off).reshape(-1, 2)
+    return lo, hi, p_cb, tiles, cand, [tuple(x) for x in pr.tolist()]
+
+
+@pytest.mark.parametrize("n,seed,tau,m_aux,n_shards,grid", [
+    (700, 41, 0.9, 128, 1, 3),        # the benchmark's shape: 16 bands x 8 rows, 8 signature words
+    (600, 42, 0.75, 128, 2, 2),       # 32 bands x 4 rows: two chunks of signature words per tile; two shards
+    (500, 43, 0.95, 64, 1, 5),        # 4 bands x 16 rows; more CTAs than some shards have tiles
+    (300, 44, 0.9, 4, 3, 1),          # 2 bands x 2 rows: one signature word; three shards, one CTA
+    (250, 45, 0.9, 1, 1, 2),          # 1 band x 1 row: the odd band count leaves a pad half that must never match
+])
+def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, n_shards, grid):
+    tau32 = np.float32(tau)
+    plan = synth.make_plan(n, seed)
+    regs = synth.hll(plan, 14)
+    smh = synth.smh(plan, m_aux)
+    cards = np.array([O.cardinality(regs[g], 14) for g in range(n)])
+    cards[::97] = 0.0                                      # a few empty sketches: e == 0 columns are skipped
+    order = np.argsort(cards, kind="stable")
+    e = cards[order].astype(np.uint64)                     # size_t e = card (selection.cpp:275,280)
+    aux_sorted = np.ascontiguousarray(smh[order])
+    n_bands, n_rows = O.band_params(m_aux, tau32)
+    assert n_bands * n_rows == m_aux
+    lo, hi, p_cb, tiles, cand, pairs = run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid)
+    olo, ohi, op_cb, opairs = oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands)
+    rows_with_band = ohi >= olo
+    assert np.array_equal(lo[rows_with_band], olo[rows_with_band]) and np.array_equal(hi[rows_with_band], ohi[rows_with_band])
+    assert np.all(hi[~rows_with_band] < lo[~rows_with_band])
+    assert p_cb == op_cb                                   # CB decisions bit-exact
+    assert pairs == opairs                                 # smh_a decisions bit-exact, nothing lost by the 16-bit pre-filter
+    assert len(opairs) > 20 and cand >= len(pairs) and tiles > 0
