@@ -29,7 +29,9 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
                   const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                   uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                   unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
+#ifndef SELB_EMUL   // the emulator's dynamic shared memory is a global array of this name
     extern __shared__ __align__(1024) uint32_t hist_dyn[];   // 2 x [nbins][64 threads]
+#endif
     __shared__ int s_unit;
     const int nbins = 64 - p_aux + 2;
     uint32_t* hist0 = hist_dyn;
@@ -236,7 +238,9 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
                          const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
                          uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
                          unsigned long long pair_cap, unsigned long long* __restrict__ unit_counter) {
+#ifndef SELB_EMUL
     extern __shared__ __align__(1024) uint32_t hist_dyn[];   // [nbins][64 threads]
+#endif
     __shared__ int s_unit;
     const int nbins = 64 - p_aux + 2;
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;

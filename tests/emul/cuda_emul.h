@@ -39,6 +39,8 @@ struct dim3e { unsigned x = 1, y = 1, z = 1; };
 static thread_local dim3e threadIdx, blockIdx;
 static dim3e gridDim, blockDim;
 
+static uint32_t* emul_hists[4] = {nullptr, nullptr, nullptr, nullptr};   // see hist_bias below
+
 namespace emul {
 struct Warp {
     std::barrier<> bar;
@@ -59,6 +61,7 @@ static inline uint64_t exchange(uint64_t mine, int src) {
 static inline void launch(unsigned grid, unsigned block, const std::function<void()>& body) {
     gridDim.x = grid;
     blockDim.x = block;
+    for (auto& h : emul_hists) h = nullptr;
     for (unsigned b = 0; b < grid; ++b) {
         std::barrier<> cb((std::ptrdiff_t)block);
         cta_bar = &cb;
@@ -125,6 +128,38 @@ static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetc
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 // helpers.inl's warp_claim aggregates over __activemask(); here every thread claims its own slot
 static inline unsigned long long warp_claim(unsigned long long* counter) { return atomicAdd(counter, 1ull); }
+// Byte-histogram helpers of helpers.inl (inline PTX there: PRMT-built shared addresses).  Same contract here:
+// hist_bias(h) names a [bin][64 threads] counter array, the bias rides in every byte of a packed register word
+// (registers are <= 63, so value + 64 * index has no carries), hist_inc* bump the counter [value][thread].
+static inline uint32_t hist_bias(const void* hist) {
+    for (uint32_t k = 0; k < 4; ++k) {
+        uint32_t* expect = nullptr;
+        if (__atomic_load_n(&emul_hists[k], __ATOMIC_SEQ_CST) == hist ||
+            __atomic_compare_exchange_n(&emul_hists[k], &expect, (uint32_t*)hist, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST) ||
+            expect == hist)
+            return (k << 6) * 0x01010101u;
+    }
+    fprintf(stderr, "hist_bias: more than 4 histograms\n");
+    abort();
+}
+static inline void emul_hist_bump(uint32_t byte, uint32_t tb) { emul_hists[byte >> 6][(byte & 63u) * 64u + tb / 4u]++; }
+template <int B0, int B1> static inline void hist_inc2(uint32_t wb, uint32_t tb) {
+    emul_hist_bump((wb >> (8 * B0)) & 0xffu, tb);
+    emul_hist_bump((wb >> (8 * B1)) & 0xffu, tb);
+}
+template <int B> static inline void hist_inc_dual(uint32_t wb0, uint32_t wb1, uint32_t tb) {
+    emul_hist_bump((wb0 >> (8 * B)) & 0xffu, tb);
+    emul_hist_bump((wb1 >> (8 * B)) & 0xffu, tb);
+}
+static inline uint32_t max4_lt128(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t x = (a >> (8 * i)) & 0xffu, y = (b >> (8 * i)) & 0xffu;
+        r |= (x > y ? x : y) << (8 * i);
+    }
+    return r;
+}
+alignas(1024) static uint32_t hist_dyn[2 * 64 * 64];     // the dynamic shared memory of the hll filters
 // cp.async: the copy is done when it is queued
 static inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
 static inline void cp_async_commit() {}

@@ -1,0 +1,101 @@
+// emul_filter_hll.cpp — runs the CB + hll_a / hll_an chain of a selection run on the CPU through cuda_emul.h, from the
+// same .inl sources the GPU build compiles:
+//   k_cb_bounds -> k_rowblock_span -> exclusive scan -> k_tile_table                 (kernels/tiles.inl)
+//   k_aux_planes, k_aux_range (load time) -> k_tile_filter_hll_planes<AN>            (kernels/filter_hll.inl)
+//   or the byte form k_tile_filter_hll<AN> over the transposed registers
+// Input (file): sorted truncated cardinalities, auxiliary HLL registers in sorted order, tau, Z*sigma, criterion.
+// Output (file): P_cb and the surviving pair list — tests/test_emul_filter.py holds them against the oracle's
+// union_size + hll_a / hll_an decision of every pair inside the CB band.  Test infrastructure.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+
+#define SELB_EMUL 1
+#include "cuda_emul.h"
+#include "../../cuda_selection_criteria_b200/csrc/estimators.cuh"
+
+constexpr int TILE = 128;          // as in csrc/selb200.cu
+
+#include "../../cuda_selection_criteria_b200/csrc/kernels/helpers.inl"
+#include "../../cuda_selection_criteria_b200/csrc/kernels/tiles.inl"
+#include "../../cuda_selection_criteria_b200/csrc/kernels/filter_hll.inl"
+
+template <class T> static void rd(FILE* f, T* p, size_t n) { if (fread(p, sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
+template <class T> static void wr(FILE* f, const T* p, size_t n) { if (fwrite(p, sizeof(T), n, f) != n) { fprintf(stderr, "short write\n"); exit(2); } }
+
+int main(int argc, char** argv) {
+    if (argc < 5) { fprintf(stderr, "usage: emul_filter_hll in.bin out.bin planes|bytes n_shards [grid]\n"); return 2; }
+    const bool planes = std::string(argv[3]) == "planes";
+    const int n_shards = atoi(argv[4]);
+    const unsigned fgrid = argc > 5 ? (unsigned)atoi(argv[5]) : 3u;
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror(argv[1]); return 2; }
+    int32_t hdr[5];
+    double tau;
+    float zs;
+    rd(f, hdr, 5);
+    rd(f, &tau, 1);
+    rd(f, &zs, 1);
+    const int n = hdr[0], p_aux = hdr[1], an = hdr[2], order_n = hdr[3], zeros = hdr[4];
+    const size_t m_aux = (size_t)1 << p_aux;
+    std::vector<unsigned long long> e((size_t)n);
+    std::vector<uint8_t> aux((size_t)n * m_aux + 32);      // k_aux_planes reads 32 bytes per word
+    rd(f, e.data(), e.size());
+    rd(f, aux.data(), (size_t)n * m_aux);
+    fclose(f);
+
+    const long long npad = ((long long)n + TILE - 1) / TILE * TILE;
+    const int nrb = (n + TILE - 1) / TILE;
+    std::vector<int32_t> lo(n), hi(n), tile_nt(nrb + 1), tile_prefix(nrb + 1), tile_cb0(nrb), order(n);
+    std::iota(order.begin(), order.end(), 0);              // the input is in sorted order already
+    std::vector<unsigned long long> rb_pairs(nrb), meta(M_WORDS, 0);
+    emul::launch((unsigned)((n + 255) / 256), 256, [&] { k_cb_bounds(e.data(), n, zeros, tau, lo.data(), hi.data()); });
+    emul::launch((unsigned)((nrb + 1 + 3) / 4), 128, [&] {
+        k_rowblock_span(lo.data(), hi.data(), n, nrb, tile_nt.data(), tile_cb0.data(), rb_pairs.data(), meta.data());
+    });
+    std::exclusive_scan(tile_nt.begin(), tile_nt.end(), tile_prefix.begin(), 0);
+    const long long tile_cap = std::max<long long>(1, (long long)nrb * (nrb + 1) / 2);
+    std::vector<int2> tile_rc((size_t)tile_cap);
+    emul::launch((unsigned)((nrb + 3) / 4), 128, [&] {
+        k_tile_table(tile_prefix.data(), tile_cb0.data(), nrb, tile_cap, tile_rc.data(), meta.data());
+    });
+    // load-time layouts: auxT[word][genome] (k_aux_transpose, restated here), bit planes and ranges by the kernels
+    const int row_words = (int)(m_aux / 4);
+    std::vector<uint32_t> auxT((size_t)row_words * npad, 0u);
+    for (int g = 0; g < n; ++g)
+        for (int j = 0; j < row_words; ++j) std::memcpy(&auxT[(size_t)j * npad + g], &aux[(size_t)g * m_aux + 4 * (size_t)j], 4);
+    const int nw = (int)(m_aux >> 5);
+    std::vector<uint32_t> auxP(planes ? (size_t)6 * nw * npad : 1, 0u);
+    std::vector<uint16_t> agrange((size_t)npad, 0);
+    if (planes) {
+        emul::launch(2, 256, [&] { k_aux_planes(aux.data(), order.data(), n, npad, p_aux, auxP.data()); });
+        emul::launch((unsigned)(((long long)n * 32 + 255) / 256), 256, [&] { k_aux_range(aux.data(), order.data(), n, p_aux, agrange.data()); });
+    }
+    const unsigned long long cap = 1ull << 22;
+    std::vector<uint2> pairs((size_t)cap), all_pairs;
+    for (int shard = 0; shard < n_shards; ++shard) {
+        meta[M_PAIRS] = meta[M_UNIT] = 0;
+        const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};
+        emul::launch(fgrid, 64, [&] {
+            if (planes) {
+                if (an) k_tile_filter_hll_planes<1>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                else k_tile_filter_hll_planes<0>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+            } else {
+                if (an) k_tile_filter_hll<1>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                else k_tile_filter_hll<0>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+            }
+        });
+        if (meta[M_PAIRS] > cap) { fprintf(stderr, "list overflow\n"); return 3; }
+        all_pairs.insert(all_pairs.end(), pairs.begin(), pairs.begin() + (long long)meta[M_PAIRS]);
+    }
+    std::sort(all_pairs.begin(), all_pairs.end(), [](uint2 a, uint2 b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    f = fopen(argv[2], "wb");
+    if (!f) { perror(argv[2]); return 2; }
+    const long long out_hdr[2] = {(long long)meta[M_PAIRS_CB], (long long)all_pairs.size()};
+    wr(f, out_hdr, 2);
+    wr(f, all_pairs.data(), all_pairs.size());
+    fclose(f);
+    printf("n=%d p_aux=%d %s %s P_cb=%llu pairs=%zu\n", n, p_aux, planes ? "planes" : "bytes", an ? "hll_an" : "hll_a", meta[M_PAIRS_CB], all_pairs.size());
+    return 0;
+}

@@ -93,3 +93,75 @@ def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_a
     assert p_cb == op_cb                                   # CB decisions bit-exact
     assert pairs == opairs                                 # smh_a decisions bit-exact, nothing lost by the 16-bit pre-filter
     assert len(opairs) > 20 and cand >= len(pairs) and tiles > 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# hll_a / hll_an: k_aux_planes + k_aux_range + k_tile_filter_hll_planes<AN> (bit-plane form) and k_tile_filter_hll<AN>
+# (byte form; the histogram helpers are the emulator's semantic versions) against the oracle's decision per pair
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def exe_hll(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emulh") / "emul_filter_hll"
+    subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                    os.path.join(ROOT, "tests", "emul", "emul_filter_hll.cpp"), "-o", str(out)], check=True)
+    return str(out)
+
+
+def oracle_hll_decisions(e, aux_sorted, p_aux, tau32, an, order_n):
+    ora = O.lib()
+    n = aux_sorted.shape[0]
+    rows = [np.ascontiguousarray(aux_sorted[g]) for g in range(n)]
+    zeros = int(np.count_nonzero(e == 0))
+    pairs, p_cb = [], 0
+    z = np.float32(1.96)
+    for i in range(n):
+        k = max(i + 1, zeros)
+        while k < n and ora.oracle_cb(tau32, int(e[i]), int(e[k])):
+            p_cb += 1
+            t = ora.oracle_union_size(rows[i].ctypes.data, rows[k].ctypes.data, p_aux)
+            ok = (ora.oracle_hll_an(tau32, int(e[i]), int(e[k]), t, p_aux, z, order_n) if an
+                  else ora.oracle_hll_a(tau32, int(e[i]), int(e[k]), t, p_aux, z))
+            if ok:
+                pairs.append((i, k))
+            k += 1
+    return p_cb, pairs
+
+
+@pytest.mark.parametrize("n,seed,tau,p_aux,criterion,form,n_shards,grid,odd", [
+    (400, 51, 0.9, 8, "hll_a", "planes", 1, 3, False),
+    (400, 52, 0.85, 8, "hll_an", "planes", 2, 2, False),
+    (300, 53, 0.9, 10, "hll_a", "planes", 1, 4, False),
+    (300, 54, 0.9, 6, "hll_an", "planes", 1, 2, True),     # outliers: steps whose pairs do not share a 32-value window
+    (300, 55, 0.9, 5, "hll_a", "bytes", 1, 2, False),       # p_aux < 6 has no bit planes: the byte form
+    (300, 56, 0.8, 8, "hll_an", "bytes", 2, 3, True),
+])
+def test_cb_and_hll_decisions_on_the_emulator(exe_hll, tmp_path, n, seed, tau, p_aux, criterion, form, n_shards, grid, odd):
+    tau32 = np.float32(tau)
+    an = criterion == "hll_an"
+    plan = synth.make_plan(n, seed)
+    regs = synth.hll(plan, 14)
+    aux = synth.hll(plan, p_aux, synth.TAG_AUX_HLL).copy()
+    if odd:
+        aux[::7, 3] = 64 - p_aux + 1                       # the largest legal register, far above the rest
+    cards = np.array([O.cardinality(regs[g], 14) for g in range(n)])
+    cards[::89] = 0.0
+    order = np.argsort(cards, kind="stable")
+    e = cards[order].astype(np.uint64)
+    aux_sorted = np.ascontiguousarray(aux[order])
+    zs = np.float32(1.96) * np.float32(O.lib().oracle_sigma(p_aux))      # float product (criteria_sketch.hpp:29,32,40)
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<5i", n, p_aux, int(an), 1, int(np.count_nonzero(e == 0))))
+        f.write(struct.pack("<d", float(tau32)))
+        f.write(struct.pack("<f", float(zs)))
+        f.write(e.tobytes())
+        f.write(aux_sorted.tobytes())
+    r = subprocess.run([exe_hll, str(inp), str(outp), form, str(n_shards), str(grid)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(outp, "rb").read()
+    p_cb, npairs = struct.unpack_from("<2q", raw, 0)
+    pairs = [tuple(x) for x in np.frombuffer(raw, np.uint32, 2 * npairs, 16).reshape(-1, 2).tolist()]
+    op_cb, opairs = oracle_hll_decisions(e, aux_sorted, p_aux, tau32, an, 1)
+    assert p_cb == op_cb
+    assert pairs == opairs                                 # hll_a / hll_an decisions bit-exact (early-exit MLE included)
+    assert 10 < len(opairs) < op_cb
