@@ -49,6 +49,8 @@ __device__ __forceinline__ void hist_inc2(uint32_t wb, uint32_t tb) {
     sts_u32(o1, c1 + 1);
 }
 
+#endif   // SELB_EMUL
+
 __device__ __forceinline__ void hist_inc_max16(const uint4& x, const uint4& y, uint32_t bias, uint32_t tb) {
     uint32_t w;
     w = max4_lt128(x.x, y.x) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
@@ -57,6 +59,7 @@ __device__ __forceinline__ void hist_inc_max16(const uint4& x, const uint4& y, u
     w = max4_lt128(x.w, y.w) + bias; hist_inc2<0, 1>(w, tb); hist_inc2<2, 3>(w, tb);
 }
 
+#ifndef SELB_EMUL
 // One register value into each of TWO different histograms (never alias): both loads first.
 template <int B>
 __device__ __forceinline__ void hist_inc_dual(uint32_t wb0, uint32_t wb1, uint32_t tb) {

@@ -125,6 +125,13 @@ template <class T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> static inline T max(T a, T b) { return a < b ? b : a; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicSub(int* p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 // helpers.inl's warp_claim aggregates over __activemask(); here every thread claims its own slot
 static inline unsigned long long warp_claim(unsigned long long* counter) { return atomicAdd(counter, 1ull); }
@@ -159,6 +166,7 @@ static inline uint32_t max4_lt128(uint32_t a, uint32_t b) {
     }
     return r;
 }
+static inline uint32_t __vmaxu4(uint32_t a, uint32_t b) { return max4_lt128(a, b); }    // bytes of any value
 alignas(1024) static uint32_t hist_dyn[2 * 64 * 64];     // the dynamic shared memory of the hll filters
 // cp.async: the copy is done when it is queued
 static inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
