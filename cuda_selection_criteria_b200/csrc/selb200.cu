@@ -39,6 +39,8 @@
 #include <utility>
 #include <vector>
 
+#include <immintrin.h>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -207,6 +209,8 @@ struct selb200_ctx {
     // split form of the union pass (kernels/union_split.inl): 5 relative planes + high list per genome
     bool union_split = false;
     DevBuf split_rec, gmeta;
+    // SELB200_H2D=planes: selb200_load_host packs every chunk to bit planes on the host before the PCIe copy
+    bool h2d_planes = false;
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
@@ -357,6 +361,113 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
 // the streaming entry points (selb200_load_begin / acquire / commit / end) let the caller decode
 // sketch files straight into pinned staging slots while earlier chunks are already on the device.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Host-side bit slicing (SELB200_H2D=planes).  HLL registers are 6-bit numbers, so a chunk can cross PCIe as
+// 6 planes (12 KiB per genome at p=14) instead of bytes (16 KiB); the layout is the device one
+// ([genome][chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r of the chunk), so the copy lands
+// in ctx->planes and k_bytes_from_planes rebuilds the byte matrix next to it.
+// 32 registers -> one word per plane: shift the wanted bit into every byte's top position, movemask.
+// *or_all collects the OR of every byte seen (a value above 63 cannot be sliced; the caller fails the load).
+// ---------------------------------------------------------------------------------------------
+__attribute__((target("avx2"))) void pack_planes_avx2(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst,
+                                                     uint32_t* or_all) {
+    const int cw = chunk_regs >> 5;
+    __m256i acc = _mm256_setzero_si256();
+    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
+        uint32_t* d = dst + ch * 6 * (size_t)cw;
+        for (int w = 0; w < cw; ++w) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + c0 + 32 * (size_t)w));
+            acc = _mm256_or_si256(acc, v);
+            d[0 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7));
+            d[1 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
+            d[2 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
+            d[3 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4));
+            d[4 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 3));
+            d[5 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 2));
+        }
+    }
+    alignas(32) uint32_t t[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(t), acc);
+    uint32_t o = 0;
+    for (int i = 0; i < 8; ++i) o |= t[i];
+    *or_all |= (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xffu;
+}
+
+// 64 registers -> two consecutive words of every plane per vpmovb2m
+__attribute__((target("avx512bw"))) void pack_planes_avx512(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst,
+                                                           uint32_t* or_all) {
+    const int cw = chunk_regs >> 5;
+    __m512i acc = _mm512_setzero_si512();
+    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
+        uint32_t* d = dst + ch * 6 * (size_t)cw;
+        for (int w = 0; w < cw; w += 2) {
+            const __m512i v = _mm512_loadu_si512(src + c0 + 32 * (size_t)w);
+            acc = _mm512_or_si512(acc, v);
+            const uint64_t k0 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 7)), k1 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 6));
+            const uint64_t k2 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 5)), k3 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 4));
+            const uint64_t k4 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 3)), k5 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 2));
+            std::memcpy(d + 0 * cw + w, &k0, 8);
+            std::memcpy(d + 1 * cw + w, &k1, 8);
+            std::memcpy(d + 2 * cw + w, &k2, 8);
+            std::memcpy(d + 3 * cw + w, &k3, 8);
+            std::memcpy(d + 4 * cw + w, &k4, 8);
+            std::memcpy(d + 5 * cw + w, &k5, 8);
+        }
+    }
+    alignas(64) uint32_t t[16];
+    _mm512_store_si512(t, acc);
+    uint32_t o = 0;
+    for (int i = 0; i < 16; ++i) o |= t[i];
+    *or_all |= (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xffu;
+}
+
+void pack_planes_scalar(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst, uint32_t* or_all) {
+    const int cw = chunk_regs >> 5;
+    uint64_t acc = 0;
+    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
+        uint32_t* d = dst + ch * 6 * (size_t)cw;
+        for (int w = 0; w < cw; ++w) {
+            uint64_t q[4];
+            std::memcpy(q, src + c0 + 32 * (size_t)w, 32);
+            acc |= q[0] | q[1] | q[2] | q[3];
+            for (int b = 0; b < 6; ++b) {
+                uint32_t word = 0;
+                for (int k = 0; k < 4; ++k)      // bit b of 8 bytes -> 8 bits (the multiply gathers them into the top byte)
+                    word |= (uint32_t)((((q[k] >> b) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56) << (8 * k);
+                d[b * cw + w] = word;
+            }
+        }
+    }
+    acc |= acc >> 32;
+    acc |= acc >> 16;
+    acc |= acc >> 8;
+    *or_all |= (uint32_t)(acc & 0xffu);
+}
+
+// rows genomes of m registers -> planes; returns the OR of all bytes
+uint32_t pack_planes_rows(const uint8_t* regs, int64_t rows, size_t m, int chunk_regs, uint32_t* out) {
+    // widest instruction set of the host; SELB200_PACK=avx2|scalar forces a narrower one (tests)
+    static const int level = [] {
+        const char* e = getenv("SELB200_PACK");
+        int lv = __builtin_cpu_supports("avx512bw") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+        if (e && !strcmp(e, "avx2")) lv = std::min(lv, 1);
+        if (e && !strcmp(e, "scalar")) lv = 0;
+        return lv;
+    }();
+    uint32_t or_all = 0;
+#pragma omp parallel for schedule(static) reduction(| : or_all)
+    for (int64_t g = 0; g < rows; ++g) {
+        uint32_t o = 0;
+        const uint8_t* src = regs + (size_t)g * m;
+        uint32_t* dst = out + (size_t)g * 6 * (m >> 5);
+        if (level == 2) pack_planes_avx512(src, m, chunk_regs, dst, &o);
+        else if (level == 1) pack_planes_avx2(src, m, chunk_regs, dst, &o);
+        else pack_planes_scalar(src, m, chunk_regs, dst, &o);
+        or_all |= o;
+    }
+    return or_all;
+}
+
 int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, const uint8_t* d_regs_borrowed,
                const void* d_aux_borrowed) {
     if (!c) return fail(SELB200_EINVAL, "null context");
@@ -422,6 +533,16 @@ int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, cons
     return SELB200_OK;
 }
 
+int pinned_ensure(void** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap && *ptr) return SELB200_OK;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CK(cudaMallocHost(ptr, bytes ? bytes : 16));
+    *cap = bytes;
+    return SELB200_OK;
+}
+
 // the run stream waits for everything queued on the copy stream so far
 int load_join_copies(selb200_ctx* c) {
     LoadState& L = c->ld;
@@ -439,7 +560,7 @@ int load_join_copies(selb200_ctx* c) {
 // rows [g0, g0+rows): optional H2D from host pointers (copy stream), then validation, per-genome
 // histogram and cardinality MLE on the run stream
 int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, const double* h_stored,
-               const void* h_aux) {
+               const void* h_aux, bool pack_planes = false) {
     LoadState& L = c->ld;
     cudaStream_t s = c->stream;
     const int p = c->p;
@@ -456,12 +577,38 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
         L.have_stored = true;
         copied = true;
     }
-    if (h_regs) {
+    const bool packed = pack_planes && h_regs && !c->union_split && c->m >= 512;
+    if (packed) {
+        // slice on the host (this thread's OpenMP team) into a pinned slot while the previous chunk's copy is
+        // still on the bus; 3 slots, a slot is reused once its copy has completed
+        StageSlot& sl = c->slots[c->next_slot];
+        if (!sl.free_ev) CK(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
+        if (sl.in_flight) { CK(cudaEventSynchronize(sl.free_ev)); sl.in_flight = false; }
+        const size_t plane_bytes = (size_t)rows * 6 * (c->m >> 3);
+        CKR(pinned_ensure((void**)&sl.regs, &sl.regs_cap, (size_t)L.rows_per_chunk * 6 * (c->m >> 3)));
+        const uint32_t or_all = pack_planes_rows(h_regs, rows, c->m, c->chunk_regs, reinterpret_cast<uint32_t*>(sl.regs));
+        if (or_all & 0xC0u)
+            return fail(SELB200_EINVAL, "primary sketch holds a register value above 63: not an HLL (rows %lld..%lld)",
+                        (long long)g0, (long long)(g0 + rows - 1));
+        CK(cudaMemcpyAsync(c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5), sl.regs, plane_bytes,
+                           cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(sl.free_ev, c->copy_stream));
+        sl.in_flight = true;
+        c->next_slot = (c->next_slot + 1) % 3;
+        copied = true;
+    } else if (h_regs) {
         CK(cudaMemcpyAsync(c->regs_own.as<uint8_t>() + (size_t)g0 * c->m, h_regs, (size_t)rows * c->m,
                            cudaMemcpyHostToDevice, c->copy_stream));
         copied = true;
     }
     if (copied) CKR(load_join_copies(c));
+    if (packed) {   // the byte matrix, rebuilt from the planes that just arrived
+        const long long nblk = rows * (long long)(c->m >> 9);
+        const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
+        k_bytes_from_planes<<<grid, 256, 0, s>>>(c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5), rows, c->m,
+                                                 c->chunk_regs, c->regs_own.as<uint8_t>() + (size_t)g0 * c->m);
+        CK(cudaGetLastError());
+    }
     const size_t n16 = (size_t)rows * c->m / 16;
     k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
         reinterpret_cast<const uint4*>(c->d_regs + (size_t)g0 * c->m), n16, c->counters.as<uint32_t>());
@@ -482,7 +629,7 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
                                            c->split_rec.as<uint8_t>() + (size_t)g0 * items * split_chunk_bytes(c->chunk_regs),
                                            c->gmeta.as<uint32_t>() + g0);
         CK(cudaGetLastError());
-    } else {   // bit-plane copy of the chunk for the union kernel
+    } else if (!packed) {   // bit-plane copy of the chunk for the union kernel
         const long long nblk = rows * (long long)(c->m >> 9);
         const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
         k_planes_from_bytes<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
@@ -601,7 +748,8 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool on_devic
     for (int64_t g0 = 0; g0 < n; g0 += step) {
         const int64_t rows = std::min(step, n - g0);
         CKR(load_chunk(c, g0, rows, on_device ? nullptr : regs + (size_t)g0 * c->m, stored ? stored + g0 : nullptr,
-                       (on_device || !aux) ? nullptr : (const uint8_t*)aux + (size_t)g0 * L.aux_row_bytes));
+                       (on_device || !aux) ? nullptr : (const uint8_t*)aux + (size_t)g0 * L.aux_row_bytes,
+                       !on_device && c->h2d_planes));
     }
     return load_end(c);
 }
@@ -649,6 +797,8 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
     {   // SELB200_UNION: planes (default) | split | bytes — form of the union pass, read per context
         const char* e = getenv("SELB200_UNION");
         c->union_split = e && !strcmp(e, "split");
+        const char* h = getenv("SELB200_H2D");      // planes: selb200_load_host slices on the host, 25 % fewer PCIe bytes
+        c->h2d_planes = h && !strcmp(h, "planes");
     }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
@@ -711,16 +861,6 @@ int selb200_load_device_rows(selb200_ctx* c, int64_t g0, int64_t count) {
 int selb200_load_begin(selb200_ctx* ctx, int64_t n, int p, int aux_kind, int aux_len, int64_t* rows_per_chunk) {
     CKR(load_begin(ctx, n, p, aux_kind, aux_len, nullptr, nullptr));
     if (rows_per_chunk) *rows_per_chunk = ctx->ld.rows_per_chunk;
-    return SELB200_OK;
-}
-
-static int pinned_ensure(void** ptr, size_t* cap, size_t bytes) {
-    if (bytes <= *cap && *ptr) return SELB200_OK;
-    if (*ptr) cudaFreeHost(*ptr);
-    *ptr = nullptr;
-    *cap = 0;
-    CK(cudaMallocHost(ptr, bytes ? bytes : 16));
-    *cap = bytes;
     return SELB200_OK;
 }
 
@@ -1467,6 +1607,14 @@ int selb200_result_device(selb200_ctx* c, const uint64_t** d_keys, const double*
     if (!c) return fail(SELB200_EINVAL, "null context");
     if (d_keys) *d_keys = c->res_keys;
     if (d_jaccard) *d_jaccard = c->res_j;
+    return SELB200_OK;
+}
+
+int selb200_debug_pack_planes(int64_t rows, int p, const uint8_t* regs, uint32_t* planes, uint32_t* or_all) {
+    if (rows < 0 || p < 9 || p > 20 || !regs || !planes) return fail(SELB200_EINVAL, "bad arguments");
+    const size_t m = (size_t)1 << p;
+    const uint32_t o = pack_planes_rows(regs, rows, m, (int)std::min<size_t>(m, (size_t)PL_CHUNK_REGS), planes);
+    if (or_all) *or_all = o;
     return SELB200_OK;
 }
 

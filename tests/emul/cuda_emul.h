@@ -35,6 +35,7 @@ struct uint4 { uint32_t x, y, z, w; };
 struct int2 { int x, y; };
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 struct dim3e { unsigned x = 1, y = 1, z = 1; };
 static thread_local dim3e threadIdx, blockIdx;
 static dim3e gridDim, blockDim;

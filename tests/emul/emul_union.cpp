@@ -6,6 +6,8 @@
 //   hist[max(a[j], b[j])]++   (sketch/include/sketch/hll.h:1191-1206 of the reference),
 // and the pairs each form hands to the byte kernel ("wide") with the rule it documents.
 // Test infrastructure (tests/test_emul_union.py builds and runs it); exit code 0 = all cases identical.
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +50,11 @@ struct Case {
     unsigned grid;
     int outlier_every = 0;         // > 0: every such genome gets one register of value 50 (a range wider than 32)
 };
+
+// selb200_debug_pack_planes of the built library (argv[1]), when given: the host-side slicing of SELB200_H2D=planes
+typedef int (*pack_fn_t)(int64_t, int, const uint8_t*, uint32_t*, uint32_t*);
+pack_fn_t g_host_pack = nullptr;
+bool g_layout_only = false;        // argv[2]: only the planes <-> bytes / host packer checks
 
 int run_case(const Case& cs, uint64_t seed) {
     const size_t m = (size_t)1 << cs.p;
@@ -135,7 +142,7 @@ int run_case(const Case& cs, uint64_t seed) {
     };
 
     // ---- split form ----
-    check("split",
+    if (!g_layout_only) check("split",
           [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
               emul::launch(cs.grid, [&] {
                   k_pair_hist_split<EpiWriteHist>(rec, m, chunk_regs, gmeta.data(), src, epi, wide, counters, counters + 1);
@@ -149,7 +156,21 @@ int run_case(const Case& cs, uint64_t seed) {
     // ---- plane form (default) ----
     std::vector<uint32_t> planes((size_t)n * 6 * (m >> 5), 0xA5A5A5A5u);
     emul::launch(2, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes.data()); });
-    check("planes",
+    {   // the planes <-> bytes pair of kernels, and the host packer against the device layout
+        std::vector<uint8_t> back((size_t)n * m, 0xEE);
+        emul::launch(2, 256, [&] { k_bytes_from_planes(planes.data(), n, m, chunk_regs, back.data()); });
+        int fbad = back != regs;
+        if (g_host_pack) {
+            std::vector<uint32_t> hp(planes.size(), 0x5A5A5A5Au);
+            uint32_t or_all = 0, or_want = 0;
+            for (uint8_t v : regs) or_want |= v;
+            if (g_host_pack(n, cs.p, regs.data(), hp.data(), &or_all) != 0 || hp != planes || or_all != or_want) ++fbad;
+        }
+        printf("%-26s %-6s p=%d n=%d bytes->planes->bytes%s  %s\n", cs.name, "layout", cs.p, n,
+               g_host_pack ? ", host packer == k_planes_from_bytes" : "", fbad ? "FAIL" : "ok");
+        bad += fbad;
+    }
+    if (!g_layout_only) check("planes",
           [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
               emul::launch(cs.grid, [&] {
                   k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide, counters, counters + 1);
@@ -165,8 +186,15 @@ int run_case(const Case& cs, uint64_t seed) {
 
 }  // namespace
 
-int main() {
+int main(int argc, char** argv) {
     int bad = 0;
+    if (argc > 1) {
+        void* h = dlopen(argv[1], RTLD_NOW);
+        if (!h) { fprintf(stderr, "dlopen %s: %s\n", argv[1], dlerror()); return 2; }
+        g_host_pack = (pack_fn_t)dlsym(h, "selb200_debug_pack_planes");
+        if (!g_host_pack) { fprintf(stderr, "selb200_debug_pack_planes not exported\n"); return 2; }
+    }
+    g_layout_only = argc > 2;
     const std::vector<Case> cases = {
         {"bacterial p14", 14, {61, 80, 122, 200, 305, 488, 480, 300}, 0.85, 51, 3},
         {"identical-ish p14", 14, {400, 400, 400, 401}, 0.98, 51, 2},

@@ -346,6 +346,30 @@ def test_split_union_mixed_bases_and_long_lists(gpu, monkeypatch):
                 compare(sel.run(tau=np.float32(tau), criterion=crit), ora, tau)
 
 
+@pytest.mark.skipif(os.environ.get("SELB200_TEST_H2D") != "1",
+                    reason="SELB200_H2D=planes (host-side bit slicing before the PCIe copy) has not run on a GPU yet: "
+                           "written in a session without GPU budget, checked on the CPU emulator only "
+                           "(tests/test_emul_union.py); set SELB200_TEST_H2D=1 to run it")
+def test_packed_upload_equals_byte_upload(gpu, monkeypatch):
+    """selb200_load_host with SELB200_H2D=planes: same cardinalities, order and results as the byte upload, several
+    64 MiB chunks (staging-slot reuse), and a register above 63 is refused on the host."""
+    plan = synth.make_plan(9000, 91)                   # 9000 x 16 KiB = 2.2 chunks
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128)
+    ref = run_gpu(regs, aux, "smh_a", 0.9, gpu)
+    monkeypatch.setenv("SELB200_H2D", "planes")
+    for _ in range(2):
+        res = run_gpu(regs, aux, "smh_a", 0.9, gpu)
+        assert np.array_equal(res.order, ref.order)
+        assert np.array_equal(res.cards_sorted.view(np.int64), ref.cards_sorted.view(np.int64))
+        assert np.array_equal(res.i, ref.i) and np.array_equal(res.k, ref.k)
+        assert np.array_equal(res.jaccard.view(np.int64), ref.jaccard.view(np.int64))
+    bad = regs.copy()
+    bad[8999, 100] = 64
+    with pytest.raises(S.SelB200Error):
+        run_gpu(bad, aux, "smh_a", 0.9, gpu)
+
+
 @pytest.mark.parametrize("criterion", ["hll_a", "hll_an"])
 @pytest.mark.parametrize("p_aux", [4, 5, 6, 7, 9, 12])
 def test_auxiliary_hll_precisions(gpu, criterion, p_aux):
