@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 
 #define SELB_EMUL 1
 #include "cuda_emul.h"
@@ -194,7 +195,31 @@ int main(int argc, char** argv) {
         g_host_pack = (pack_fn_t)dlsym(h, "selb200_debug_pack_planes");
         if (!g_host_pack) { fprintf(stderr, "selb200_debug_pack_planes not exported\n"); return 2; }
     }
-    g_layout_only = argc > 2;
+    g_layout_only = argc > 2 && std::string(argv[2]) == "layout-only";
+    if (argc > 4 && std::string(argv[2]) == "fuzz") {        // emul_union LIB fuzz SEED COUNT: random cases
+        std::mt19937_64 rng(strtoull(argv[3], nullptr, 10));
+        const int count = atoi(argv[4]);
+        auto uni = [&](double a, double b) { return std::uniform_real_distribution<double>(a, b)(rng); };
+        for (int it = 0; it < count; ++it) {
+            Case cs;
+            cs.name = "fuzz";
+            cs.p = 9 + (int)(rng() % 7);
+            const int n = 2 + (int)(rng() % 9);
+            const double centre = std::exp(uni(std::log(0.05), std::log(2e5)));
+            const double spread = uni(0.0, 3.0);
+            for (int g = 0; g < n; ++g) cs.load.push_back(rng() % 17 == 0 ? 0.0 : centre * std::exp(uni(-spread, spread)));
+            cs.shared = (rng() % 3 == 0) ? 0.0 : uni(0.1, 0.99);
+            cs.clamp_hi = 64 - cs.p + 1;
+            cs.grid = 1 + (unsigned)(rng() % 3);
+            cs.outlier_every = (rng() % 3 == 0) ? 2 + (int)(rng() % 3) : 0;
+            const int b = run_case(cs, rng());
+            if (b) printf("FUZZ FAILURE: p=%d n=%d centre=%g spread=%g shared=%g grid=%u outliers=%d\n", cs.p, n, centre, spread,
+                          cs.shared, cs.grid, cs.outlier_every);
+            bad += b;
+        }
+        printf(bad ? "FAILED (%d)\n" : "all identical\n", bad);
+        return bad ? 1 : 0;
+    }
     const std::vector<Case> cases = {
         {"bacterial p14", 14, {61, 80, 122, 200, 305, 488, 480, 300}, 0.85, 51, 3},
         {"identical-ish p14", 14, {400, 400, 400, 401}, 0.98, 51, 2},
