@@ -110,6 +110,8 @@ static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 // SIMD-in-word integer intrinsics of the smh filter (per unsigned 16-bit half)
 static inline uint32_t emul_half_op(uint32_t a, uint32_t b, uint32_t (*f)(uint32_t, uint32_t)) {
     return (f(a & 0xffffu, b & 0xffffu) & 0xffffu) | (f(a >> 16, b >> 16) << 16);
@@ -131,6 +133,11 @@ static inline int atomicSub(int* p, int v) { return __atomic_fetch_sub(p, v, __A
 static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
     uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
@@ -168,6 +175,7 @@ static inline uint32_t max4_lt128(uint32_t a, uint32_t b) {
     return r;
 }
 static inline uint32_t __vmaxu4(uint32_t a, uint32_t b) { return max4_lt128(a, b); }    // bytes of any value
+alignas(16) static uint8_t smem_raw[160 << 10];           // the dynamic shared memory of the sketch builder
 alignas(1024) static uint32_t hist_dyn[2 * 64 * 64];     // the dynamic shared memory of the hll filters
 // cp.async: the copy is done when it is queued
 static inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
