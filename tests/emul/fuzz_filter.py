@@ -1,9 +1,9 @@
 """Offline differential fuzz of the emulated filter chains (tests/emul/emul_filter*.cpp: the CB + smh_a / hll_a / hll_an
 kernels compiled as host code) against the oracle's per-pair decisions: random n, tau, sketch sizes, shards, grids,
-empty sketches, cardinality ties, outlier registers.  usage: python tools/fuzz_emul_filter.py SEED COUNT
+empty sketches, cardinality ties, outlier registers.  usage: python tests/emul/fuzz_filter.py SEED COUNT
 The union kernels have the same in tests/emul/emul_union.cpp:  emul_union LIB fuzz SEED COUNT."""
 import os, sys, struct, subprocess, tempfile, pathlib, random
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import oracle_api as O
