@@ -232,13 +232,13 @@ int main(int argc, char** argv) {
         {"p16 sixteen chunks", 16, {250, 260}, 0.9, 49, 1},
         {"empty and sparse p14", 14, {0, 0.01, 0.5, 3}, 0.0, 51, 2},
         {"saturated values p14", 14, {1e12, 2e12, 200}, 0.5, 51, 1},
-        // genome 0 has another base: its 39 pairs are consecutive in the list, so whole batches are wide
+        // genome 0 has another base: its 25 pairs come first in the list, so with batches of 16 a whole batch is wide
         {"whole batches wide p10", 10, {9000, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 116, 117, 118,
-                                        119, 120, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138}, 0.0, 55, 2},
-        // the plane kernel hands every pair of genomes 0, 3, 6, ... to the byte kernel (39 + 36 + ... consecutive pairs);
+                                        119, 120, 121, 122, 123, 124}, 0.0, 55, 3},
+        // the plane kernel hands every pair of genomes 0, 3, 6, ... to the byte kernel (25 + 22 + ... consecutive pairs);
         // for the split kernel the outlier is one more list entry
         {"outliers p10", 10, {100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 116, 117, 118, 119,
-                              120, 121, 122, 123, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138, 139}, 0.5, 54, 2, 3},
+                              120, 121, 122, 123, 124, 125}, 0.5, 54, 3, 3},
         {"many pairs few warps p10", 10, {50, 55, 60, 65, 70, 75, 80, 85, 90, 95, 100, 105, 110, 115, 120, 125, 130, 135}, 0.8, 55, 2},
     };
     uint64_t seed = 12345;
