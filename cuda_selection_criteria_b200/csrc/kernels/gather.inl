@@ -34,12 +34,14 @@ struct GatherZone {                     // pointers into the (local or IPC-mappe
     unsigned long long cap, near_cap;
 };
 
+#ifndef SELB_EMUL   // tests/emul/cuda_emul.h: host clock, and a timeout short enough to test
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 constexpr unsigned long long GATHER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+#endif
 
 // one thread: (optionally) make sure the pass did not overflow, wait until the buffer of this parity
 // has been merged by the root two runs ago, claim the rank's block in the root's lists

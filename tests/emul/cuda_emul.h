@@ -11,6 +11,7 @@
 // asynchrony are NOT modelled: this checks arithmetic, index math and the control flow, not the hardware protocol.
 #pragma once
 #include <barrier>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <climits>
@@ -140,6 +141,14 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
     while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
+static inline unsigned int atomicAdd_system(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd_system(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+static inline unsigned long long gtime_ns() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+constexpr unsigned long long GATHER_TIMEOUT_NS = 300ull * 1000 * 1000;     // 0.3 s instead of the device's 20 s
 static inline unsigned long long atomicExch(unsigned long long* p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 // helpers.inl's warp_claim aggregates over __activemask(); here every thread claims its own slot
 static inline unsigned long long warp_claim(unsigned long long* counter) { return atomicAdd(counter, 1ull); }
