@@ -189,6 +189,73 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
     }
 }
 
+// The same chunk step in SUBSET form (SELB200_UNION=subsets; written without GPU budget, CPU-checked on the warp
+// emulator, to be measured in round 2).  The one-hot form above spends, per 32 registers, 8 decode masks + per
+// 8-value group 1 selector + 8 ANDs before the 8 carry-save inputs.  Here the window is cut into eight groups of
+// FOUR values (selected by planes 5..2) and a group counts the four SUBSET masks of the two low planes
+//   c[{}] = sel,  c[{0}] = sel & M0,  c[{1}] = sel & M1,  c[{0,1}] = sel & M0 & M1        (one LOP3 each)
+// i.e. #registers of the group whose low bits CONTAIN the subset; the epilogue turns the four totals back into the
+// four bins with two subtract steps (Moebius inversion, exact in integers).  Every counted mask now costs one LOP3
+// to form and one to absorb, the decode masks are gone, and groups of four follow the pair's value range more
+// closely (a range 6..25 counts 24 bins instead of 32): per 32 registers and a range of 20 values
+// 12 (max) + 4 + 6*4 (form) + 24 (absorb) = 64 LOP3 and 12 POPC instead of 88 and 16.
+// gmask: bit t = the group of values 8*G0 + 4t .. 8*G0 + 4t + 3 lies inside the pair's range (warp-uniform).
+template <int G0, int NQ>
+__device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
+                                                    int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
+    const int nq = NQ > 0 ? NQ : nq_rt;
+    constexpr int NP = (G0 == 0) ? 5 : 6;
+#pragma unroll 1
+    for (int q = lane; q < nq; q += 32) {
+        uint32_t M[2][6];
+        {
+            uint2 a[NP], b[NP];
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) { a[pl] = sA[pl * nq + q]; b[pl] = sB[pl * nq + q]; }
+            uint32_t lt0 = 0u, lt1 = 0u;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+                lt0 = lop3<0x8E>(a[pl].x, b[pl].x, lt0);
+                lt1 = lop3<0x8E>(a[pl].y, b[pl].y, lt1);
+            }
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+                M[0][pl] = lop3<0xCA>(lt0, b[pl].x, a[pl].x);
+                M[1][pl] = lop3<0xCA>(lt1, b[pl].y, a[pl].y);
+            }
+            if (NP == 5) { M[0][5] = 0u; M[1][5] = 0u; }
+        }
+        // T8: 8-value group of the window (selector from planes 5..3), HALF: its lower / upper four values (plane 2)
+#define SELB_SUBSET_GROUP(T8, HALF)                                                                       \
+        if (gmask & (1u << (2 * T8 + HALF))) {                                                            \
+            constexpr int c0 = 4 * (2 * T8 + HALF);                                                       \
+            const uint32_t e0 = HALF ? lop3<0xC0>(H0, M[0][2], 0u) : lop3<0x30>(H0, M[0][2], 0u);         \
+            const uint32_t e1 = HALF ? lop3<0xC0>(H1, M[1][2], 0u) : lop3<0x30>(H1, M[1][2], 0u);         \
+            uint32_t m0[4], m1[4], kk[4];                                                                 \
+            m0[0] = e0; m0[1] = lop3<0xC0>(e0, M[0][0], 0u); m0[2] = lop3<0xC0>(e0, M[0][1], 0u);         \
+            m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);                                                     \
+            m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);         \
+            m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                     \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);    \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);                    \
+        }
+#define SELB_SUBSET_GROUP8(T8)                                                                            \
+        if (gmask & (3u << (2 * T8))) {                                                                   \
+            const uint32_t H0 = lop3<(1 << (G0 + T8))>(M[0][5], M[0][4], M[0][3]);                        \
+            const uint32_t H1 = lop3<(1 << (G0 + T8))>(M[1][5], M[1][4], M[1][3]);                        \
+            SELB_SUBSET_GROUP(T8, 0)                                                                      \
+            SELB_SUBSET_GROUP(T8, 1)                                                                      \
+        }
+        SELB_SUBSET_GROUP8(0)
+        SELB_SUBSET_GROUP8(1)
+        SELB_SUBSET_GROUP8(2)
+        SELB_SUBSET_GROUP8(3)
+#undef SELB_SUBSET_GROUP8
+#undef SELB_SUBSET_GROUP
+    }
+}
+
 // pair list -> histogram rows, bit-plane form.  grange[g] = min | max<<8 of genome g's registers.
 // One warp per CTA.  Work comes in batches of 32 consecutive pairs claimed from a device counter (dynamic
 // balance, no tail): each lane fetches the descriptor of one pair of the batch (rows through `order`, value
@@ -204,11 +271,20 @@ constexpr int PL_STAGES = PL_STAGES_V;
 #define PL_MIN_CTAS 16
 #endif
 
+// The counting form is a property of the epilogue type, so that the default instantiation keeps its name and its code:
+// k_pair_hist_planes<Epi> counts one-hot (plane_chunk), k_pair_hist_planes<EpiSubsets<Epi>> in subset form on groups of
+// four values (plane_chunk_subsets, SELB200_UNION=subsets).  Everything but the counting step, the granularity of the
+// range mask and two subtract steps in the epilogue is shared.
+template <class E> struct EpiSubsets : E {};
+template <class E> struct union_form { static constexpr int value = 0; };
+template <class E> struct union_form<EpiSubsets<E>> { static constexpr int value = 1; };
+
 template <class Epi>
 __global__ void __launch_bounds__(32, PL_MIN_CTAS)
 k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
                    SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
                    unsigned long long* __restrict__ batch_counter) {
+    constexpr int FORM = union_form<Epi>::value;
 #ifndef SELB_EMUL   // the emulator's dynamic shared memory is a global array of this name
     extern __shared__ __align__(128) uint8_t pl_smem[];
 #endif
@@ -254,8 +330,13 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
                 ok = false;
             } else {
                 uint32_t gmask = 0;
-                for (int t = 0; t < 4; ++t)
-                    if ((g0 + t) >= (lo >> 3) && (g0 + t) <= (hi >> 3)) gmask |= 1u << t;
+                if (FORM == 0) {
+                    for (int t = 0; t < 4; ++t)
+                        if ((g0 + t) >= (lo >> 3) && (g0 + t) <= (hi >> 3)) gmask |= 1u << t;
+                } else {                     // groups of four values: 8*g0 + 4t .. 8*g0 + 4t + 3
+                    for (int t = 0; t < 8; ++t)
+                        if ((2 * g0 + t) >= (lo >> 2) && (2 * g0 + t) <= (hi >> 2)) gmask |= 1u << t;
+                }
                 gm = (uint32_t)g0 | (gmask << 8);
             }
         }
@@ -366,7 +447,25 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         const uint2* pb = reinterpret_cast<const uint2*>(pl_smem + (size_t)st * 2 * chunk_bytes + chunk_bytes);
         const int g0 = (int)(cons.gm & 0xffu);
         const uint32_t gmask = cons.gm >> 8;
-        if (nq == PL_NQ) {
+        if (FORM == 1) {
+            if (nq == PL_NQ) {
+                switch (g0) {
+                    case 0: plane_chunk_subsets<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 1: plane_chunk_subsets<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 2: plane_chunk_subsets<2, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 3: plane_chunk_subsets<3, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                    default: plane_chunk_subsets<4, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                }
+            } else {
+                switch (g0) {
+                    case 0: plane_chunk_subsets<0, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 1: plane_chunk_subsets<1, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 2: plane_chunk_subsets<2, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 3: plane_chunk_subsets<3, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                    default: plane_chunk_subsets<4, 0>(pa, pb, nq, lane, gmask, S, C2); break;
+                }
+            }
+        } else if (nq == PL_NQ) {
             switch (g0) {
                 case 0: plane_chunk<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
                 case 1: plane_chunk<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
@@ -397,6 +496,14 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
                     const uint32_t keep = upper ? x[i + o] : x[i];
                     x[i] = keep + __shfl_xor_sync(FULL, send, o);
                 }
+            }
+            if (FORM == 1) {
+                // lane 4t + s holds #registers of group t whose two low bits contain subset s: two subtract steps
+                // (s without a bit -= s with the bit) leave the count of low bits == s, i.e. the bin 8*g0 + lane
+                const uint32_t y0 = __shfl_xor_sync(FULL, x[0], 1);
+                if (!(lane & 1)) x[0] -= y0;
+                const uint32_t y1 = __shfl_xor_sync(FULL, x[0], 2);
+                if (!(lane & 2)) x[0] -= y1;
             }
             const uint32_t tot = __shfl_sync(FULL, x[0], (lane - 8 * g0) & 31);
             const bool first = lane >= 8 * g0;     // bin `lane` lies inside the window; else bin lane+32 does

@@ -208,6 +208,8 @@ struct selb200_ctx {
     int chunk_regs = 0;
     // split form of the union pass (kernels/union_split.inl): 5 relative planes + high list per genome
     bool union_split = false;
+    // subset form of the plane kernel (k_pair_hist_planes<EpiSubsets<..>>): same planes, other counting step
+    bool union_subsets = false;
     DevBuf split_rec, gmeta;
     // SELB200_H2D=planes: selb200_load_host packs every chunk to bit planes on the host before the PCIe copy
     bool h2d_planes = false;
@@ -336,6 +338,23 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         k_pair_hist_split<EpiWriteHist><<<sgrid, 32, ssmem, s>>>(c->split_rec.as<uint8_t>(), c->m, c->chunk_regs,
                                                                 c->gmeta.as<uint32_t>(), src, epi,
                                                                 c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+    } else if (c->union_subsets) {
+        static int u_per_sm = 0;
+        static size_t u_per_sm_smem = 0;
+        if (!u_per_sm || u_per_sm_smem != smem) {
+            cudaFuncSetAttribute(k_pair_hist_planes<EpiSubsets<EpiWriteHist>>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&u_per_sm, k_pair_hist_planes<EpiSubsets<EpiWriteHist>>, 32, smem) != cudaSuccess ||
+                u_per_sm < 1) {
+                cudaGetLastError();
+                u_per_sm = 4;
+            }
+            u_per_sm_smem = smem;
+        }
+        const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * u_per_sm);
+        k_pair_hist_planes<EpiSubsets<EpiWriteHist>><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
+                                                                       c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
+                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
     } else {
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
         k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
@@ -794,9 +813,10 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    {   // SELB200_UNION: planes (default) | split | bytes — form of the union pass, read per context
+    {   // SELB200_UNION: planes (default) | subsets | split | bytes — form of the union pass, read per context
         const char* e = getenv("SELB200_UNION");
         c->union_split = e && !strcmp(e, "split");
+        c->union_subsets = e && !strcmp(e, "subsets");
         const char* h = getenv("SELB200_H2D");      // planes: selb200_load_host slices on the host, 25 % fewer PCIe bytes
         c->h2d_planes = h && !strcmp(h, "planes");
     }

@@ -44,6 +44,10 @@ static dim3e gridDim, blockDim;
 static uint32_t* emul_hists[4] = {nullptr, nullptr, nullptr, nullptr};   // see hist_bias below
 
 namespace emul {
+// instruction counts as the source writes them (per thread, added up when a thread of a launch ends): lets a harness
+// compare two forms of a kernel by LOP3 / POPC per work item without a GPU
+static thread_local uint64_t t_lop3 = 0, t_popc = 0;
+static uint64_t n_lop3 = 0, n_popc = 0;
 struct Warp {
     std::barrier<> bar;
     uint64_t xchg[32];
@@ -75,7 +79,10 @@ static inline void launch(unsigned grid, unsigned block, const std::function<voi
                 threadIdx.x = t;
                 blockIdx.x = b;
                 warp = warps[t / 32].get();
+                t_lop3 = t_popc = 0;
                 body();
+                __atomic_fetch_add(&n_lop3, t_lop3, __ATOMIC_RELAXED);
+                __atomic_fetch_add(&n_popc, t_popc, __ATOMIC_RELAXED);
                 warp->bar.arrive_and_drop();     // a thread that returns early must not block the others
                 cb.arrive_and_drop();
             });
@@ -107,7 +114,7 @@ static inline uint32_t __ballot_sync(uint32_t, bool p) {
 static inline bool __any_sync(uint32_t m, bool p) { return __ballot_sync(m, p) != 0u; }
 static inline void __syncwarp() { emul::sync(); }
 static inline void __syncthreads() { emul::cta_bar->arrive_and_wait(); }
-static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __popc(uint32_t v) { ++emul::t_popc; return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
@@ -194,6 +201,7 @@ template <int N> static inline void cp_async_wait() {}
 // LOP3: bit i of the result = LUT[(a_i << 2) | (b_i << 1) | c_i]
 template <int LUT> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d = 0;
+    ++emul::t_lop3;
     for (int i = 0; i < 32; ++i) {
         const int idx = (int)(((a >> i) & 1u) << 2 | ((b >> i) & 1u) << 1 | ((c >> i) & 1u));
         d |= (uint32_t)((LUT >> idx) & 1) << i;

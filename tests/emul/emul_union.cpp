@@ -1,6 +1,7 @@
 // emul_union.cpp — runs the bit-plane forms of the union pass on the CPU through cuda_emul.h, from the same .inl
 // sources the GPU build compiles:
 //   kernels/union_planes.inl : k_planes_from_bytes + k_pair_hist_planes   (the default form)
+//                              k_pair_hist_planes<EpiSubsets<..>>          (SELB200_UNION=subsets)
 //   kernels/union_split.inl  : k_split_build + k_pair_hist_split          (SELB200_UNION=split)
 // and compares every pair's 64-bin histogram with the byte-wise definition
 //   hist[max(a[j], b[j])]++   (sketch/include/sketch/hll.h:1191-1206 of the reference),
@@ -113,7 +114,9 @@ int run_case(const Case& cs, uint64_t seed) {
         unsigned long long counters[3] = {0, 0, 0};           // wide count, batch counter, error word
         std::memset(pl_smem, 0x5A, sizeof pl_smem);
         emul_tma_bytes = emul_tma_expected = 0;
+        emul::n_lop3 = emul::n_popc = 0;
         run(EpiWriteHist{hist.data()}, wide.data(), counters);
+        const uint64_t ops_lop3 = emul::n_lop3, ops_popc = emul::n_popc;
         int fbad = 0;
         if (counters[2]) { printf("  %s/%s: kernel error word %llx\n", cs.name, form, counters[2]); ++fbad; }
         if (emul_tma_bytes != emul_tma_expected) { printf("  %s/%s: expect_tx %llu != copied %llu\n", cs.name, form, (unsigned long long)emul_tma_expected, (unsigned long long)emul_tma_bytes); ++fbad; }
@@ -138,7 +141,12 @@ int run_case(const Case& cs, uint64_t seed) {
                 ++fbad;
             }
         }
-        printf("%-26s %-6s p=%d n=%d pairs=%lld counted=%lld wide=%llu  %s\n", cs.name, form, cs.p, n, np, n_done, counters[0], fbad ? "FAIL" : "ok");
+        // per counted pair and lane: lop3<> and __popc calls as the source writes them (the butterfly's 32 __popc
+        // included).  The one-hot form writes its 16 mask ANDs per group and step as plain `&` (LOP3 in SASS, not
+        // counted here): tests/emul/union_lop3_model.py and tools/sass_loops.py give the comparable numbers.
+        printf("%-26s %-7s p=%d n=%d pairs=%lld counted=%lld wide=%llu lop3<>/pair=%.0f popc/pair=%.0f  %s\n", cs.name, form, cs.p, n,
+               np, n_done, counters[0], n_done ? (double)ops_lop3 / 32.0 / (double)n_done : 0.0,
+               n_done ? (double)ops_popc / 32.0 / (double)n_done : 0.0, fbad ? "FAIL" : "ok");
         bad += fbad;
     };
 
@@ -178,6 +186,17 @@ int run_case(const Case& cs, uint64_t seed) {
               });
           },
           [&](uint32_t a, uint32_t b) {   // the pair's values must fit 32 consecutive values starting at a multiple of 8
+              const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
+              return (hi >> 3) > std::min(lo >> 3, 4) + 3;
+          });
+    // ---- plane form with subset counting on groups of four values (SELB200_UNION=subsets): same wide rule ----
+    if (!g_layout_only) check("subsets",
+          [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
+              emul::launch(cs.grid, [&] {
+                  k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi}, wide, counters, counters + 1);
+              });
+          },
+          [&](uint32_t a, uint32_t b) {
               const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
               return (hi >> 3) > std::min(lo >> 3, 4) + 3;
           });

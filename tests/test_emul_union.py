@@ -1,6 +1,7 @@
 """CPU-only: the bit-plane union kernels compiled as host code from the .inl sources of the GPU build and run through
 the warp emulator tests/emul/cuda_emul.h — k_planes_from_bytes + k_pair_hist_planes (the default form of the union
-pass) and k_split_build + k_pair_hist_split (SELB200_UNION=split) against the byte-wise definition of the union
+pass), the same kernel with subset counting (k_pair_hist_planes<EpiSubsets<..>>, SELB200_UNION=subsets) and
+k_split_build + k_pair_hist_split (SELB200_UNION=split) against the byte-wise definition of the union
 histogram (sketch/include/sketch/hll.h:1191-1206), for precisions 9..16, narrow and wide value ranges, equal and
 mixed bases, empty, saturated and overflowing high lists.  The emulator checks arithmetic, index math and the
 producer/consumer walk; the hardware protocol (TMA, mbarriers) is covered by the -m gpu tests.  The same run checks
@@ -22,7 +23,8 @@ def test_union_kernels_on_the_warp_emulator(tmp_path):
     r = subprocess.run([str(exe), S.lib_path()], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "all identical" in r.stdout
-    assert r.stdout.count(" ok") >= 42 and "FAIL" not in r.stdout
+    assert r.stdout.count(" ok") >= 56 and "FAIL" not in r.stdout          # 14 cases x (layout, split, planes, subsets)
+    assert r.stdout.count(" subsets ") == 14
     assert r.stdout.count("host packer == k_planes_from_bytes") == 14
     # the packer's narrower code paths (the default is the widest the host has: AVX-512BW, AVX2 or scalar)
     for level in ("avx2", "scalar"):

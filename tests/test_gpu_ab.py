@@ -1,4 +1,4 @@
-"""-m gpu: the three forms of the union pass (bit planes = default, split, bytes) and the two forms of the hll filter
+"""-m gpu: the forms of the union pass (bit planes = default, split, bytes; subsets when enabled) and the two forms of the hll filter
 against each other, at sizes the CPU oracle would take minutes for.  All forms compute the same integer
 histograms, so pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=split|planes|bytes is
 read when a context is created, SELB200_HLLFILTER=bytes at library load)."""
@@ -58,3 +58,14 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
     assert split == by
     assert planes == by
     assert all(v[1] > 1000 for v in planes.values())          # thousands of emitted pairs in every case
+
+
+@pytest.mark.skipif(os.environ.get("SELB200_TEST_SUBSETS") != "1",
+                    reason="SELB200_UNION=subsets (subset counting on groups of four values in the plane kernel) has not run "
+                           "on a GPU yet: written in a session without GPU budget, checked on the CPU warp emulator only "
+                           "(tests/test_emul_union.py, 14 cases + fuzz); set SELB200_TEST_SUBSETS=1 to run it")
+def test_subsets_union_equals_byte_kernels(gpu, tmp_path):
+    subsets = _run({"SELB200_UNION": "subsets"}, tmp_path)
+    by = _run({"SELB200_UNION": "bytes", "SELB200_HLLFILTER": "bytes"}, tmp_path)
+    assert subsets == by
+    assert all(v[1] > 1000 for v in subsets.values())
