@@ -342,8 +342,8 @@ def main():
 
     st0 = stats_acc[-1]
     peak, peak_src = measured_peak()
-    union_kernel = {"bytes": "k_pair_hist", "split": "k_pair_hist_split"}.get(os.environ.get("SELB200_UNION", ""),
-                                                                              "k_pair_hist_planes")
+    union_kernel = {"bytes": "k_pair_hist", "split": "k_pair_hist_split",
+                    "subsets": "k_pair_hist_planes<EpiSubsets>"}.get(os.environ.get("SELB200_UNION", ""), "k_pair_hist_planes")
     k_union = {"name": union_kernel, "ms": mean("ms_union"), "bytes": ALG_BYTES["union"] * st0["pairs_aux"],
                "unit_def": "32768 B (2 x 2^14 one-byte registers, SURVEY.md 8d) per aux-passing pair x pairs_aux"}
     per_pair_filter = {"smh_a": ALG_BYTES["smh_a"], "cb": ALG_BYTES["cb"],
@@ -356,10 +356,14 @@ def main():
     ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     # the same launch against the integer pipe it is actually bound by.  Essential LOP3 per pair and lane at p=14
     # (8 steps of 64 registers per lane): split kernel 8 x (2 flags + 16 max + 4 group masks + 16 decode + 2 groups x 32)
-    # = 816; bit-plane kernel 8 x (20 max + 16 decode + 4 groups x 34) = 1376.  The LOP3 rate of the SM was measured
-    # with tools/ubench/int_pipes.cu (profiles/r01_int_pipes_ubench.txt)
+    # = 816; bit-plane kernel 8 x (20 max + 16 decode + 4 groups x 34) = 1376; its subset form 8 x (20 max + 8 selectors
+    # + 8 groups of four x 16) = 1248.  These are the counts with every value group of the window active; the group masks
+    # of the C4 workload make the kernels execute about 1200 and 905 (tests/emul/union_lop3_model.py), so `frac` is an
+    # upper bound of the essential-LOP3 share.  The LOP3 rate of the SM was measured with tools/ubench/int_pipes.cu
+    # (profiles/r01_int_pipes_ubench.txt)
     int_alu = None
-    lop3_per_pair = {"k_pair_hist_split": 816.0, "k_pair_hist_planes": 1376.0}.get(dom["name"])
+    lop3_per_pair = {"k_pair_hist_split": 816.0, "k_pair_hist_planes": 1376.0,
+                     "k_pair_hist_planes<EpiSubsets>": 1248.0}.get(dom["name"])
     if lop3_per_pair and dom["ms"] > 0:
         sm_clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
@@ -367,7 +371,8 @@ def main():
         a_int = lane_ops / (dom["ms"] * 1e-3) / sm_clk / n_sm
         int_alu = {"bound": "int_alu", "achieved": a_int, "peak": 63.0, "unit": "LOP3 lane-ops/clk/SM",
                    "frac": a_int / 63.0,
-                   "def": f"{lop3_per_pair:.0f} LOP3 per pair and lane x 32 lanes x pairs_aux / launch time / SM clock / SMs; peak measured"}
+                   "def": f"{lop3_per_pair:.0f} LOP3 per pair and lane (all value groups of the window active: upper bound) "
+                          "x 32 lanes x pairs_aux / launch time / SM clock / SMs; peak measured"}
     roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(dom["name"]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"], "bytes_def": dom["unit_def"],
