@@ -155,7 +155,10 @@ k_aux_range(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, 
 }
 
 // all word pairs of one (row, 32 columns) step for window G0: S / C2 end as the per-value carry-save state
-template <int G0>
+// FORM 0: one-hot masks on groups of eight values (gmask: 4 bits); FORM 1: subset masks on groups of four values
+// (gmask: 8 bits) followed by the in-register Moebius step — the counting step of plane_chunk_subsets in
+// kernels/union_planes.inl, where the scheme is described (SELB200_HLLFILTER=subsets; CPU-checked, not yet measured)
+template <int G0, int FORM>
 __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
                                                 long long npad, int nw, uint32_t gmask, uint32_t (&x)[32]) {
     uint32_t S[32], C2[32];
@@ -183,6 +186,36 @@ __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ row
                 M[0][pl] = lop3<0xCA>(lt0, b[0][pl], a[0][pl]);
                 M[1][pl] = lop3<0xCA>(lt1, b[1][pl], a[1][pl]);
             }
+        }
+        if (FORM == 1) {
+#define SELB_AUX_SUBSET_GROUP(T8, HALF)                                                                   \
+            if (gmask & (1u << (2 * T8 + HALF))) {                                                        \
+                constexpr int c0 = 4 * (2 * T8 + HALF);                                                   \
+                const uint32_t e0 = HALF ? lop3<0xC0>(H0, M[0][2], 0u) : lop3<0x30>(H0, M[0][2], 0u);     \
+                const uint32_t e1 = HALF ? lop3<0xC0>(H1, M[1][2], 0u) : lop3<0x30>(H1, M[1][2], 0u);     \
+                uint32_t m0[4], m1[4], kk[4];                                                             \
+                m0[0] = e0; m0[1] = lop3<0xC0>(e0, M[0][0], 0u); m0[2] = lop3<0xC0>(e0, M[0][1], 0u);     \
+                m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);                                                 \
+                m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);     \
+                m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                 \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]); \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);                \
+            }
+#define SELB_AUX_SUBSET_GROUP8(T8)                                                                        \
+            if (gmask & (3u << (2 * T8))) {                                                               \
+                const uint32_t H0 = lop3<(1 << (G0 + T8))>(M[0][5], M[0][4], M[0][3]);                    \
+                const uint32_t H1 = lop3<(1 << (G0 + T8))>(M[1][5], M[1][4], M[1][3]);                    \
+                SELB_AUX_SUBSET_GROUP(T8, 0)                                                              \
+                SELB_AUX_SUBSET_GROUP(T8, 1)                                                              \
+            }
+            SELB_AUX_SUBSET_GROUP8(0)
+            SELB_AUX_SUBSET_GROUP8(1)
+            SELB_AUX_SUBSET_GROUP8(2)
+            SELB_AUX_SUBSET_GROUP8(3)
+#undef SELB_AUX_SUBSET_GROUP8
+#undef SELB_AUX_SUBSET_GROUP
+            continue;
         }
         uint32_t L[2][8];
 #pragma unroll
@@ -214,14 +247,24 @@ __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ row
     }
 #pragma unroll
     for (int v = 0; v < 32; ++v) x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]);
+    if (FORM == 1) {
+        // x[4t + s] = #registers of group t whose two low bits contain subset s -> the four bins of the group
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            x[4 * t + 0] -= x[4 * t + 1];
+            x[4 * t + 2] -= x[4 * t + 3];
+            x[4 * t + 0] -= x[4 * t + 2];
+            x[4 * t + 1] -= x[4 * t + 3];
+        }
+    }
 }
 
-template <int G0>
+template <int G0, int FORM>
 __device__ __forceinline__ void aux_plane_hist(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
                                                long long npad, int nw, uint32_t gmask, uint32_t* __restrict__ hcol,
                                                int nbins) {
     uint32_t x[32];
-    aux_plane_pairs<G0>(rowp, colp, npad, nw, gmask, x);
+    aux_plane_pairs<G0, FORM>(rowp, colp, npad, nw, gmask, x);
     // the thread's histogram column: zeros outside the window, the counts inside
     for (int b = 0; b < 8 * G0; ++b) hcol[b * 64] = 0u;
 #pragma unroll
@@ -230,6 +273,8 @@ __device__ __forceinline__ void aux_plane_hist(const uint32_t* __restrict__ rowp
     for (int b = 8 * G0 + 32; b < nbins; ++b) hcol[b * 64] = 0u;
 }
 
+// AN bit 0: 0 = hll_a, 1 = hll_an; AN bit 1: counting form (0 = one-hot, 1 = subsets).  One integer keeps the names of
+// the two GPU-validated instantiations <0> and <1> (and with them the SASS identity check of tools/sass_diff.py).
 template <int AN>
 __global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
 k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __restrict__ agrange,
@@ -275,17 +320,23 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
             }
             const int g0 = min(vlo >> 3, 4);
             if ((vhi >> 3) <= g0 + 3) {
+                constexpr int FORM = (AN >> 1) & 1;
                 uint32_t gmask = 0;
-                for (int tt = 0; tt < 4; ++tt)
-                    if ((g0 + tt) >= (vlo >> 3) && (g0 + tt) <= (vhi >> 3)) gmask |= 1u << tt;
+                if (FORM == 0) {
+                    for (int tt = 0; tt < 4; ++tt)
+                        if ((g0 + tt) >= (vlo >> 3) && (g0 + tt) <= (vhi >> 3)) gmask |= 1u << tt;
+                } else {
+                    for (int tt = 0; tt < 8; ++tt)
+                        if ((2 * g0 + tt) >= (vlo >> 2) && (2 * g0 + tt) <= (vhi >> 2)) gmask |= 1u << tt;
+                }
                 const uint32_t* rowp = auxP + i;
                 const uint32_t* colp = auxP + kc;
                 switch (g0) {
-                    case 0: aux_plane_hist<0>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 1: aux_plane_hist<1>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 2: aux_plane_hist<2>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 3: aux_plane_hist<3>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    default: aux_plane_hist<4>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 0: aux_plane_hist<0, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 1: aux_plane_hist<1, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 2: aux_plane_hist<2, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    case 3: aux_plane_hist<3, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
+                    default: aux_plane_hist<4, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
                 }
             } else {
                 // register ranges too far apart for one window: byte path (shared-memory counters)
@@ -301,7 +352,7 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
             bool pass = false;
             if (v) {
                 bool stopped = false;
-                const StopHll stop{tau, e[i], e[k], zs, order_n, AN};
+                const StopHll stop{tau, e[i], e[k], zs, order_n, AN & 1};
                 const double tu = selb::ertl_mle(hcol, p_aux, 64, stop, &stopped);
                 pass = !stopped && stop.crit(tu);
             }

@@ -1069,6 +1069,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     // SELB200_HLLFILTER=bytes keeps the shared-memory-counter filter (A/B measurements); sketches below 64
     // registers have no bit planes
     static const bool hll_bytes_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "bytes"); }();
+    // SELB200_HLLFILTER=subsets: the plane filter with subset counting on groups of four values (instantiations <2>, <3>)
+    static const bool hll_subsets_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "subsets"); }();
     const bool hll_planes = crit >= SELB200_CRIT_HLL_A && c->aux_len >= 6 && !hll_bytes_env;
     if (crit >= SELB200_CRIT_HLL_A) {
         hll_smem = (size_t)(hll_planes ? 1 : 2) * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
@@ -1078,11 +1080,14 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             cudaFuncSetAttribute(k_tile_filter_hll<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_tile_filter_hll_planes<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_tile_filter_hll_planes<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_tile_filter_hll_planes<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_tile_filter_hll_planes<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carve = true;
         }
         int per_sm = 0;
         const cudaError_t oe = hll_planes
-            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<0>, 64, hll_smem)
+            ? (hll_subsets_env ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<2>, 64, hll_smem)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<0>, 64, hll_smem))
             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem);
         if (oe != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
@@ -1212,6 +1217,18 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
                 k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                  d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
+            } else if (hll_planes && hll_subsets_env) {
+                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
+                if (crit == SELB200_CRIT_HLL_A)
+                    k_tile_filter_hll_planes<2><<<grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
+                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
+                else
+                    k_tile_filter_hll_planes<3><<<grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
+                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
             } else if (hll_planes) {
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 if (crit == SELB200_CRIT_HLL_A)

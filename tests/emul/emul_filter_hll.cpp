@@ -1,7 +1,8 @@
 // emul_filter_hll.cpp — runs the CB + hll_a / hll_an chain of a selection run on the CPU through cuda_emul.h, from the
 // same .inl sources the GPU build compiles:
 //   k_cb_bounds -> k_rowblock_span -> exclusive scan -> k_tile_table                 (kernels/tiles.inl)
-//   k_aux_planes, k_aux_range (load time) -> k_tile_filter_hll_planes<AN>            (kernels/filter_hll.inl)
+//   k_aux_planes, k_aux_range (load time) -> k_tile_filter_hll_planes<AN>            (kernels/filter_hll.inl;
+//                                            <2>, <3>: the subset counting form, SELB200_HLLFILTER=subsets)
 //   or the byte form k_tile_filter_hll<AN> over the transposed registers
 // Input (file): sorted truncated cardinalities, auxiliary HLL registers in sorted order, tau, Z*sigma, criterion.
 // Output (file): P_cb and the surviving pair list — tests/test_emul_filter.py holds them against the oracle's
@@ -10,6 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
+#include <random>
+#include <string>
+#include <type_traits>
 
 #define SELB_EMUL 1
 #include "cuda_emul.h"
@@ -24,9 +28,73 @@ constexpr int TILE = 128;          // as in csrc/selb200.cu
 template <class T> static void rd(FILE* f, T* p, size_t n) { if (fread(p, sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 template <class T> static void wr(FILE* f, const T* p, size_t n) { if (fwrite(p, sizeof(T), n, f) != n) { fprintf(stderr, "short write\n"); exit(2); } }
 
+// emul_filter_hll hist-check SEED COUNT: the per-thread histogram step of the plane filter (aux_plane_hist, both
+// counting forms, every window) against the byte-wise definition hist[max(a[j], b[j])]++ on random sketch pairs
+static int hist_check(uint64_t seed, int count) {
+    std::mt19937_64 rng(seed);
+    int bad = 0, done = 0;
+    for (int it = 0; it < count; ++it) {
+        const int p_aux = 6 + (int)(rng() % 7);                       // 6 .. 12
+        const int m = 1 << p_aux, nw = m >> 5, nbins = 64 - p_aux + 2;
+        const int g0 = (int)(rng() % 5);                              // window 8*g0 .. 8*g0 + 31
+        int vlo = 8 * g0 + (int)(rng() % 12), vhi = vlo + (int)(rng() % 24);
+        vhi = std::min(std::min(vhi, 8 * g0 + 31), nbins - 1);
+        vlo = std::min(vlo, vhi);
+        if (std::min(vlo >> 3, 4) != g0) continue;                    // the kernel derives the window from vlo
+        std::vector<uint8_t> a(m), b(m);
+        for (int j = 0; j < m; ++j) {
+            a[j] = (uint8_t)(vlo + (int)(rng() % (unsigned)(vhi - vlo + 1)));
+            b[j] = (uint8_t)(vlo + (int)(rng() % (unsigned)(vhi - vlo + 1)));
+            if (rng() % 5 == 0) b[j] = a[j];
+        }
+        a[rng() % m] = b[rng() % m] = (uint8_t)vhi;                   // the range is attained
+        a[rng() % m] = (uint8_t)vlo; b[rng() % m] = (uint8_t)vlo;
+        const long long npad = 2;                                     // two "genomes": planes[plane][word][genome]
+        std::vector<uint32_t> P((size_t)6 * nw * npad, 0u);
+        for (int g = 0; g < 2; ++g)
+            for (int j = 0; j < m; ++j)
+                for (int pl = 0; pl < 6; ++pl)
+                    if (((g ? b[j] : a[j]) >> pl) & 1) P[((size_t)pl * nw + (j >> 5)) * npad + g] |= 1u << (j & 31);
+        uint32_t want[64] = {0};
+        int rlo = 63, rhi = 0;
+        for (int j = 0; j < m; ++j) { const int v = std::max(a[j], b[j]); want[v]++; rlo = std::min(rlo, v); rhi = std::max(rhi, v); }
+        // the kernel's range: max of the minima .. max of the maxima (a superset of the union's own range)
+        const int klo = std::max((int)*std::min_element(a.begin(), a.end()), (int)*std::min_element(b.begin(), b.end()));
+        const int khi = std::max((int)*std::max_element(a.begin(), a.end()), (int)*std::max_element(b.begin(), b.end()));
+        ++done;
+        for (int form = 0; form < 2; ++form) {
+            uint32_t gmask = 0;
+            if (form == 0) { for (int t = 0; t < 4; ++t) if (g0 + t >= (klo >> 3) && g0 + t <= (khi >> 3)) gmask |= 1u << t; }
+            else { for (int t = 0; t < 8; ++t) if (2 * g0 + t >= (klo >> 2) && 2 * g0 + t <= (khi >> 2)) gmask |= 1u << t; }
+            std::vector<uint32_t> hcol((size_t)64 * 64, 0xDEADBEEFu);
+            auto run = [&](auto G0) {
+                if (form) aux_plane_hist<decltype(G0)::value, 1>(P.data(), P.data() + 1, npad, nw, gmask, hcol.data(), nbins);
+                else aux_plane_hist<decltype(G0)::value, 0>(P.data(), P.data() + 1, npad, nw, gmask, hcol.data(), nbins);
+            };
+            switch (g0) {
+                case 0: run(std::integral_constant<int, 0>{}); break;
+                case 1: run(std::integral_constant<int, 1>{}); break;
+                case 2: run(std::integral_constant<int, 2>{}); break;
+                case 3: run(std::integral_constant<int, 3>{}); break;
+                default: run(std::integral_constant<int, 4>{}); break;
+            }
+            for (int v = 0; v < nbins; ++v)
+                if (hcol[(size_t)v * 64] != want[v]) {
+                    if (bad < 10) printf("hist-check %d form %d p_aux=%d g0=%d range %d..%d: bin %d is %u, want %u\n", it, form, p_aux, g0, klo, khi, v, hcol[(size_t)v * 64], want[v]);
+                    ++bad;
+                }
+        }
+    }
+    if (bad) printf("hist-check FAILED (%d bins of %d pairs)\n", bad, done);
+    else printf("hist-check: both forms identical to the definition on %d pairs\n", done);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 5) { fprintf(stderr, "usage: emul_filter_hll in.bin out.bin planes|bytes n_shards [grid]\n"); return 2; }
-    const bool planes = std::string(argv[3]) == "planes";
+    if (argc == 4 && std::string(argv[1]) == "hist-check") return hist_check(strtoull(argv[2], nullptr, 10), atoi(argv[3]));
+    if (argc < 5) { fprintf(stderr, "usage: emul_filter_hll in.bin out.bin planes|subsets|bytes n_shards [grid]\n"); return 2; }
+    const bool subsets = std::string(argv[3]) == "subsets";      // plane filter, subset counting (SELB200_HLLFILTER=subsets)
+    const bool planes = std::string(argv[3]) == "planes" || subsets;
     const int n_shards = atoi(argv[4]);
     const unsigned fgrid = argc > 5 ? (unsigned)atoi(argv[5]) : 3u;
     FILE* f = fopen(argv[1], "rb");
@@ -78,7 +146,10 @@ int main(int argc, char** argv) {
         meta[M_PAIRS] = meta[M_UNIT] = 0;
         const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};
         emul::launch(fgrid, 64, [&] {
-            if (planes) {
+            if (subsets) {
+                if (an) k_tile_filter_hll_planes<3>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                else k_tile_filter_hll_planes<2>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+            } else if (planes) {
                 if (an) k_tile_filter_hll_planes<1>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
                 else k_tile_filter_hll_planes<0>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
             } else {
@@ -96,6 +167,6 @@ int main(int argc, char** argv) {
     wr(f, out_hdr, 2);
     wr(f, all_pairs.data(), all_pairs.size());
     fclose(f);
-    printf("n=%d p_aux=%d %s %s P_cb=%llu pairs=%zu\n", n, p_aux, planes ? "planes" : "bytes", an ? "hll_an" : "hll_a", meta[M_PAIRS_CB], all_pairs.size());
+    printf("n=%d p_aux=%d %s %s P_cb=%llu pairs=%zu\n", n, p_aux, subsets ? "subsets" : planes ? "planes" : "bytes", an ? "hll_an" : "hll_a", meta[M_PAIRS_CB], all_pairs.size());
     return 0;
 }

@@ -134,6 +134,10 @@ def oracle_hll_decisions(e, aux_sorted, p_aux, tau32, an, order_n):
     (300, 54, 0.9, 6, "hll_an", "planes", 1, 2, True),     # outliers: steps whose pairs do not share a 32-value window
     (300, 55, 0.9, 5, "hll_a", "bytes", 1, 2, False),       # p_aux < 6 has no bit planes: the byte form
     (300, 56, 0.8, 8, "hll_an", "bytes", 2, 3, True),
+    # the plane filter with subset counting on groups of four values (SELB200_HLLFILTER=subsets)
+    (400, 57, 0.9, 8, "hll_a", "subsets", 1, 3, False),
+    (300, 58, 0.85, 10, "hll_an", "subsets", 2, 2, False),
+    (300, 59, 0.9, 6, "hll_a", "subsets", 1, 2, True),
 ])
 def test_cb_and_hll_decisions_on_the_emulator(exe_hll, tmp_path, n, seed, tau, p_aux, criterion, form, n_shards, grid, odd):
     tau32 = np.float32(tau)
@@ -165,3 +169,11 @@ def test_cb_and_hll_decisions_on_the_emulator(exe_hll, tmp_path, n, seed, tau, p
     assert p_cb == op_cb
     assert pairs == opairs                                 # hll_a / hll_an decisions bit-exact (early-exit MLE included)
     assert 10 < len(opairs) < op_cb
+
+
+def test_hll_plane_histograms_both_counting_forms(exe_hll):
+    """aux_plane_hist (the per-thread histogram step of k_tile_filter_hll_planes) in its one-hot and its subset form
+    against hist[max(a[j], b[j])]++ on random sketch pairs: p_aux 6..12, every window, ranges of 1..24 values."""
+    r = subprocess.run([exe_hll, "hist-check", "20261018", "4000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "both forms identical to the definition" in r.stdout

@@ -1,7 +1,7 @@
 """-m gpu: the forms of the union pass (bit planes = default, split, bytes; subsets when enabled) and the two forms of the hll filter
 against each other, at sizes the CPU oracle would take minutes for.  All forms compute the same integer
-histograms, so pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=split|planes|bytes is
-read when a context is created, SELB200_HLLFILTER=bytes at library load)."""
+histograms, so pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=split|planes|subsets|bytes
+is read when a context is created, SELB200_HLLFILTER=bytes|subsets at library load)."""
 import hashlib
 import json
 import os
@@ -61,11 +61,12 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
 
 
 @pytest.mark.skipif(os.environ.get("SELB200_TEST_SUBSETS") != "1",
-                    reason="SELB200_UNION=subsets (subset counting on groups of four values in the plane kernel) has not run "
-                           "on a GPU yet: written in a session without GPU budget, checked on the CPU warp emulator only "
-                           "(tests/test_emul_union.py, 14 cases + fuzz); set SELB200_TEST_SUBSETS=1 to run it")
+                    reason="SELB200_UNION=subsets / SELB200_HLLFILTER=subsets (subset counting on groups of four values in "
+                           "the plane union kernel and the plane hll filter) have not run on a GPU yet: written in a session "
+                           "without GPU budget, checked on the CPU warp emulator only (tests/test_emul_union.py, "
+                           "tests/test_emul_filter.py); set SELB200_TEST_SUBSETS=1 to run it")
 def test_subsets_union_equals_byte_kernels(gpu, tmp_path):
-    subsets = _run({"SELB200_UNION": "subsets"}, tmp_path)
+    subsets = _run({"SELB200_UNION": "subsets", "SELB200_HLLFILTER": "subsets"}, tmp_path)
     by = _run({"SELB200_UNION": "bytes", "SELB200_HLLFILTER": "bytes"}, tmp_path)
     assert subsets == by
     assert all(v[1] > 1000 for v in subsets.values())

@@ -4,7 +4,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round2_first.sh 1400'      -> gpurun_out/r2a_*
 # 1. the whole -m gpu suite with the gated tests enabled (subset union form, packed upload)
 # 2. bench.py, kernel-resident part: default plane kernel, SELB200_UNION=subsets, then the full default line
-# 3. bench.py e2e: default upload against SELB200_H2D=planes
+# 3. bench.py e2e: default upload against SELB200_H2D=planes; C5 hll_a with the one-hot and the subset plane filter
 # 4. ncu launch list of the faster union form + one --set full capture of its union kernel (after 2 has exited 0)
 # 5. compute-sanitizer passes (tools/sanitize.sh) with what is left
 BUDGET=${1:-1400}
@@ -47,6 +47,19 @@ for f in ("e2e_bytes", "e2e_planes"):
     d = line(f)
     if d:
         print(f, "e2e ms/step", round(d["e2e"]["ms_per_step"], 2), d["e2e"].get("rank0_phases_ms"), "h2d bytes", d["e2e"]["h2d_bytes_per_step"])
+PY
+# C5 (n=50k, hll_a, p_aux=10): plane hll filter, one-hot against subset counting
+C5="python bench.py --steps 5 --warmup 3 --n 50000 --seed 1003 --criterion hll_a --aux-bytes 1024 --no-cpu-baseline --no-e2e"
+step bench_c5_planes 90 $C5 > $OUT/${TAG}_bench_c5_planes.json 2> /dev/null
+SELB200_HLLFILTER=subsets step bench_c5_subsets 90 $C5 > $OUT/${TAG}_bench_c5_subsets.json 2> /dev/null
+python - <<PY | tee -a $OUT/${TAG}_summary.txt
+import json
+for f in ("c5_planes", "c5_subsets"):
+    try:
+        d = json.loads(open("$OUT/${TAG}_bench_%s.json" % f).read().strip().splitlines()[-1])
+        print(f, "ms/step", round(d["ms_per_step"], 3), "filter", round(d["roofline"]["kernels_ms"]["filter"], 3), "pairs_aux", d["config"]["pairs_aux_rank0"], "pairs_out", d["config"]["pairs_out"])
+    except Exception as e:
+        print(f, "unreadable:", e)
 PY
 # ncu only for the form that won, and only if its plain run exited 0
 FORM=planes
