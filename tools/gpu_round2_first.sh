@@ -48,6 +48,22 @@ for f in ("e2e_bytes", "e2e_planes"):
     if d:
         print(f, "e2e ms/step", round(d["e2e"]["ms_per_step"], 2), d["e2e"].get("rank0_phases_ms"), "h2d bytes", d["e2e"]["h2d_bytes_per_step"])
 PY
+# geometry variants of the plane kernels, when built beforehand (make -C cuda_selection_criteria_b200/csrc variants)
+for lib in cuda_selection_criteria_b200/csrc/variants/libselb200_*.so; do
+    [ -f "$lib" ] || continue
+    tag=$(basename $lib .so); tag=${tag#libselb200_}
+    for form in planes subsets; do
+        SELB200_LIB=$PWD/$lib SELB200_UNION=$form step bench_${tag}_$form 45 $KO > $OUT/${TAG}_bench_${tag}_$form.json 2> /dev/null
+        python - <<PY | tee -a $OUT/${TAG}_summary.txt
+import json
+try:
+    d = json.loads(open("$OUT/${TAG}_bench_${tag}_$form.json").read().strip().splitlines()[-1])
+    print("$tag $form", "ms/step", round(d["ms_per_step"], 3), "union", round(d["roofline"]["kernels_ms"]["union"], 3))
+except Exception as e:
+    print("$tag $form unreadable:", e)
+PY
+    done
+done
 # C5 (n=50k, hll_a, p_aux=10): plane hll filter, one-hot against subset counting
 C5="python bench.py --steps 5 --warmup 3 --n 50000 --seed 1003 --criterion hll_a --aux-bytes 1024 --no-cpu-baseline --no-e2e"
 step bench_c5_planes 90 $C5 > $OUT/${TAG}_bench_c5_planes.json 2> /dev/null
