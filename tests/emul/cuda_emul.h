@@ -5,10 +5,13 @@
 // vote is "everybody writes its value, warp barrier, everybody reads, warp barrier"; __syncthreads is a CTA
 // barrier.  That is valid for kernels that call warp-wide operations only from converged code with the full
 // mask, which the emulated kernels do (warp_claim, which uses __activemask in divergent code, is replaced by a
-// plain atomic claim: same set of slots, another order).  Bulk copies (TMA) and cp.async complete immediately at
-// issue, an mbarrier wait is a warp barrier (so the issuing lane's copy is visible), __shared__ variables are
-// statics and the dynamic shared memory one global array (CTAs run one after the other).  Timing, phases and
-// asynchrony are NOT modelled: this checks arithmetic, index math and the control flow, not the hardware protocol.
+// plain atomic claim: same set of slots, another order).  cp.async completes at issue.  Bulk copies (TMA) on
+// mbarriers take the latest legal completion: the destination is poisoned at issue and filled at the wait, and
+// every wait is checked for its phase parity and expect_tx balance (see mbar_wait below) — single-warp CTAs, one
+// outstanding phase per barrier, which is what the union kernels use.  __shared__ variables are statics and the
+// dynamic shared memory one global array (CTAs run one after the other).  Timing and real concurrency of the copy
+// engine are NOT modelled: this checks arithmetic, index math, control flow and the ordering rules of the ring, not
+// the hardware itself.
 #pragma once
 #include <barrier>
 #include <chrono>
@@ -214,11 +217,62 @@ alignas(128) static uint8_t pl_smem[1 << 16];
 constexpr uint32_t SMEM_BASE = 0x400u;
 static inline uint32_t __cvta_generic_to_shared(const void* p) { return SMEM_BASE + (uint32_t)((const uint8_t*)p - pl_smem); }
 static uint64_t emul_tma_bytes = 0, emul_tma_expected = 0;
-static inline void mbar_init(uint32_t, uint32_t) {}
-static inline void mbar_expect_tx(uint32_t, uint32_t bytes) { emul_tma_expected += bytes; }
-static inline void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t) {
+// Bulk copies and mbarriers, modelled as the LATEST legal completion: a copy poisons its destination when it is issued
+// (the hardware may start writing at once, so nobody may still be reading that stage) and delivers the data only when
+// the barrier it completes on is waited for (nobody may read a stage before its wait).  Per barrier: the number of
+// completed phases, the bytes announced by expect_tx and the copies in flight.  A wait must name the parity of the
+// phase in flight (anything else spins forever or falls through on hardware), a phase's copies must add up to its
+// expect_tx, and a barrier takes a new phase only after the previous one was waited for.
+struct EmulBulkCopy { uint32_t dst; const void* src; uint32_t bytes; };
+struct EmulMbar {
+    uint32_t addr = 0;
+    uint64_t phases_done = 0, expected = 0;
+    bool armed = false;
+    std::vector<EmulBulkCopy> inflight;
+};
+static std::vector<EmulMbar> emul_mbars;
+[[noreturn]] static inline void emul_mbar_die(const char* what, uint32_t bar) {
+    fprintf(stderr, "mbarrier model: %s (barrier at shared offset 0x%x)\n", what, bar);
+    abort();
+}
+static inline EmulMbar& emul_mbar(uint32_t bar) {
+    for (EmulMbar& b : emul_mbars)
+        if (b.addr == bar) return b;
+    emul_mbar_die("barrier used before mbarrier.init", bar);
+}
+static inline void mbar_init(uint32_t bar, uint32_t) {
+    for (EmulMbar& b : emul_mbars)
+        if (b.addr == bar) { b = EmulMbar{}; b.addr = bar; return; }
+    emul_mbars.push_back(EmulMbar{});
+    emul_mbars.back().addr = bar;
+}
+static inline void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    EmulMbar& b = emul_mbar(bar);
+    if (b.armed) emul_mbar_die("expect_tx on a barrier whose previous phase was never waited for", bar);
+    b.armed = true;
+    b.expected = bytes;
+    emul_tma_expected += bytes;
+}
+static inline void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     if ((dst & 15u) || ((uintptr_t)src & 15u) || (bytes & 15u) || bytes == 0) { fprintf(stderr, "bulk copy: misaligned or empty (%u bytes)\n", bytes); abort(); }
-    std::memcpy(pl_smem + (dst - SMEM_BASE), src, bytes);
+    EmulMbar& b = emul_mbar(bar);
+    if (!b.armed) emul_mbar_die("bulk copy completing on a barrier without expect_tx", bar);
+    std::memset(pl_smem + (dst - SMEM_BASE), 0xEE, bytes);          // in flight: the old content is gone, the new not there
+    b.inflight.push_back(EmulBulkCopy{dst, src, bytes});
     emul_tma_bytes += bytes;
 }
-static inline void mbar_wait(uint32_t, uint32_t) { emul::sync(); }
+static inline void mbar_wait(uint32_t bar, uint32_t parity) {
+    emul::sync();                                                     // the issuing lane is past its issue
+    if ((threadIdx.x & 31) == 0) {
+        EmulMbar& b = emul_mbar(bar);
+        if (!b.armed) emul_mbar_die("wait on a barrier with no phase in flight", bar);
+        if ((parity & 1u) != (b.phases_done & 1u)) emul_mbar_die("wait names the wrong phase parity", bar);
+        uint64_t got = 0;
+        for (const EmulBulkCopy& c : b.inflight) { std::memcpy(pl_smem + (c.dst - SMEM_BASE), c.src, c.bytes); got += c.bytes; }
+        if (got != b.expected) emul_mbar_die("the phase's copies do not add up to its expect_tx", bar);
+        b.inflight.clear();
+        b.armed = false;
+        ++b.phases_done;
+    }
+    emul::sync();                                                     // the data is there for every lane
+}

@@ -8,7 +8,10 @@ producer/consumer walk; the hardware protocol (TMA, mbarriers) is covered by the
 k_bytes_from_planes (planes back to bytes) and the library's host-side slicing (selb200_debug_pack_planes, the
 SELB200_H2D=planes upload path) word for word against k_planes_from_bytes."""
 import os
+import shutil
 import subprocess
+
+import pytest
 
 import cuda_selection_criteria_b200 as S
 
@@ -32,3 +35,41 @@ def test_union_kernels_on_the_warp_emulator(tmp_path):
                            env=dict(os.environ, SELB200_PACK=level))
         assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout[-3000:]
         assert r.stdout.count("host packer == k_planes_from_bytes") == 14
+
+
+_MUTATIONS = [
+    # (name, text in kernels/union_planes.inl, replacement, what the run must show)
+    ("wrong wait parity",
+     "mbar_wait(bar0 + 8 * st, (n_done / PL_STAGES) & 1u);",
+     "mbar_wait(bar0 + 8 * st, ((n_done / PL_STAGES) + 1) & 1u);",
+     "wait names the wrong phase parity"),
+    ("ring over-issued by one stage",
+     "for (int k = 0; k < PL_STAGES - 1 && prod.valid; ++k) {",
+     "for (int k = 0; k < PL_STAGES && prod.valid; ++k) {",
+     "previous phase was never waited for"),
+    ("no __syncwarp before a stage is refilled",
+     "        __syncwarp();                          // every lane has finished reading the stage about to be refilled\n",
+     "\n",
+     "FAIL"),
+]
+
+
+@pytest.mark.parametrize("name,old,new,expect", _MUTATIONS, ids=[m[0] for m in _MUTATIONS])
+def test_mbarrier_model_catches_protocol_mutations(tmp_path, name, old, new, expect):
+    """The emulator's TMA / mbarrier model (destination poisoned at issue, data delivered at the wait, parity and
+    expect_tx checked) must reject a plane kernel whose ring protocol is broken — otherwise the CPU check of the
+    union kernels would say nothing about their staging."""
+    tree = tmp_path / "repo"
+    shutil.copytree(os.path.join(ROOT, "tests", "emul"), tree / "tests" / "emul")
+    shutil.copytree(os.path.join(ROOT, "cuda_selection_criteria_b200", "csrc", "kernels"),
+                    tree / "cuda_selection_criteria_b200" / "csrc" / "kernels")
+    src = tree / "cuda_selection_criteria_b200" / "csrc" / "kernels" / "union_planes.inl"
+    text = src.read_text()
+    assert text.count(old) == 1, name
+    src.write_text(text.replace(old, new))
+    exe = tmp_path / "emul_union_mut"
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
+                    str(tree / "tests" / "emul" / "emul_union.cpp"), "-o", str(exe), "-ldl"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0
+    assert expect in r.stdout + r.stderr, (r.stdout[-1500:], r.stderr[-500:])
