@@ -5,7 +5,7 @@
 // vote is "everybody writes its value, warp barrier, everybody reads, warp barrier"; __syncthreads is a CTA
 // barrier.  That is valid for kernels that call warp-wide operations only from converged code with the full
 // mask, which the emulated kernels do (warp_claim, which uses __activemask in divergent code, is replaced by a
-// plain atomic claim: same set of slots, another order).  cp.async completes at issue.  Bulk copies (TMA) on
+// plain atomic claim: same set of slots, another order).  cp.async (per thread) and bulk copies (TMA) on
 // mbarriers take the latest legal completion: the destination is poisoned at issue and filled at the wait, and
 // every wait is checked for its phase parity and expect_tx balance (see mbar_wait below) — single-warp CTAs, one
 // outstanding phase per barrier, which is what the union kernels use.  __shared__ variables are statics and the
@@ -46,6 +46,7 @@ static dim3e gridDim, blockDim;
 
 static uint32_t* emul_hists[4] = {nullptr, nullptr, nullptr, nullptr};   // see hist_bias below
 
+static inline void emul_thread_exit();      // a kernel must not end with cp.async copies in flight
 namespace emul {
 // instruction counts as the source writes them (per thread, added up when a thread of a launch ends): lets a harness
 // compare two forms of a kernel by LOP3 / POPC per work item without a GPU
@@ -84,6 +85,7 @@ static inline void launch(unsigned grid, unsigned block, const std::function<voi
                 warp = warps[t / 32].get();
                 t_lop3 = t_popc = 0;
                 body();
+                emul_thread_exit();
                 __atomic_fetch_add(&n_lop3, t_lop3, __ATOMIC_RELAXED);
                 __atomic_fetch_add(&n_popc, t_popc, __ATOMIC_RELAXED);
                 warp->bar.arrive_and_drop();     // a thread that returns early must not block the others
@@ -196,10 +198,29 @@ static inline uint32_t max4_lt128(uint32_t a, uint32_t b) {
 static inline uint32_t __vmaxu4(uint32_t a, uint32_t b) { return max4_lt128(a, b); }    // bytes of any value
 alignas(16) static uint8_t smem_raw[160 << 10];           // the dynamic shared memory of the sketch builder
 alignas(1024) static uint32_t hist_dyn[2 * 64 * 64];     // the dynamic shared memory of the hll filters
-// cp.async: the copy is done when it is queued
-static inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
+// cp.async, per thread as on the hardware, with the latest legal completion: the 16 destination bytes are poisoned
+// when the copy is queued and written when the thread's wait_group retires the copy's group (all but the newest N
+// groups); a reader that has not passed that wait plus the CTA barrier behind it sees the poison.
+struct EmulCpAsync { void* dst; const void* src; };
+static thread_local std::vector<std::vector<EmulCpAsync>> emul_cp_groups;     // committed groups, oldest first
+static thread_local std::vector<EmulCpAsync> emul_cp_open;                    // copies queued since the last commit
+static inline void cp_async16(void* smem_dst, const void* gsrc) {
+    std::memset(smem_dst, 0xEE, 16);
+    emul_cp_open.push_back(EmulCpAsync{smem_dst, gsrc});
+}
+static inline void cp_async_commit() {
+    emul_cp_groups.push_back(std::move(emul_cp_open));
+    emul_cp_open.clear();
+}
+static inline void emul_thread_exit() {
+    if (!emul_cp_groups.empty() || !emul_cp_open.empty()) { fprintf(stderr, "cp.async model: thread ends with copies in flight\n"); abort(); }
+}
+template <int N> static inline void cp_async_wait() {
+    while (emul_cp_groups.size() > (size_t)N) {
+        for (const EmulCpAsync& c : emul_cp_groups.front()) std::memcpy(c.dst, c.src, 16);
+        emul_cp_groups.erase(emul_cp_groups.begin());
+    }
+}
 
 // LOP3: bit i of the result = LUT[(a_i << 2) | (b_i << 1) | c_i]
 template <int LUT> static inline uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

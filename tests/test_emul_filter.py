@@ -177,3 +177,42 @@ def test_hll_plane_histograms_both_counting_forms(exe_hll):
     r = subprocess.run([exe_hll, "hist-check", "20261018", "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "both forms identical to the definition" in r.stdout
+
+
+_SMH_MUTATIONS = [
+    ("wait leaves the group being read in flight",
+     "if (item + 1 < staged) cp_async_wait<1>();", "if (item + 1 < staged) cp_async_wait<2>();"),
+    ("refill queued before the barrier of the item",
+     "        __syncthreads();\n        if (staged < n_items) { stage_next(); ++staged; }",
+     "        if (staged < n_items) { stage_next(); ++staged; }\n        __syncthreads();"),
+]
+
+
+@pytest.mark.parametrize("name,old,new", _SMH_MUTATIONS, ids=[m[0] for m in _SMH_MUTATIONS])
+def test_cp_async_model_catches_ring_mutations(tmp_path, name, old, new):
+    """The emulator's cp.async model (destination poisoned when the copy is queued, written when wait_group retires
+    its group) must reject an smh filter whose three-buffer ring is broken: the pair set then differs from the oracle's."""
+    import shutil
+    tree = tmp_path / "repo"
+    shutil.copytree(os.path.join(ROOT, "tests", "emul"), tree / "tests" / "emul")
+    shutil.copytree(os.path.join(ROOT, "cuda_selection_criteria_b200", "csrc"), tree / "cuda_selection_criteria_b200" / "csrc",
+                    ignore=shutil.ignore_patterns("*.o", "*.so", "*.log", "variants"))
+    src = tree / "cuda_selection_criteria_b200" / "csrc" / "kernels" / "filter_smh.inl"
+    text = src.read_text()
+    assert text.count(old) == 1, name
+    src.write_text(text.replace(old, new))
+    exe = tmp_path / "emul_filter_mut"
+    subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                    str(tree / "tests" / "emul" / "emul_filter.cpp"), "-o", str(exe)], check=True)
+    n, m_aux, tau32 = 700, 128, np.float32(0.9)
+    plan = synth.make_plan(n, 41)
+    regs, smh = synth.hll(plan, 14), synth.smh(plan, m_aux)
+    cards = np.array([O.cardinality(regs[g], 14) for g in range(n)])
+    order = np.argsort(cards, kind="stable")
+    e = cards[order].astype(np.uint64)
+    aux_sorted = np.ascontiguousarray(smh[order])
+    n_bands, n_rows = O.band_params(m_aux, tau32)
+    _, _, p_cb, _, _, pairs = run_emulated(str(exe), tmp_path, e, aux_sorted, tau32, n_rows, n_bands, 1, 3)
+    _, _, op_cb, opairs = oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands)
+    assert p_cb == op_cb                       # the band does not depend on the ring
+    assert pairs != opairs                     # the broken ring loses or invents pairs, and the check sees it
