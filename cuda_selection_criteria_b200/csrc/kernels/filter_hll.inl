@@ -169,11 +169,23 @@ __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ row
         uint32_t M[2][6];
         {
             uint32_t a[2][6], b[2][6];
+            if (FORM == 1) {
+                // 32-bit word offsets from the two pointers (the launcher takes this form only while the plane
+                // matrix stays below 2^32 words): one widening multiply-add per load instead of 64-bit index math
+                const uint32_t np32 = (uint32_t)npad, ps = (uint32_t)nw * np32, ow = (uint32_t)w * np32;
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) {
+                    const uint32_t o0 = (uint32_t)pl * ps + ow, o1 = o0 + np32;
+                    a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
+                    b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
+                }
+            } else {
 #pragma unroll
             for (int pl = 0; pl < 6; ++pl) {
                 const size_t o0 = ((size_t)pl * nw + w) * (size_t)npad, o1 = o0 + (size_t)npad;
                 a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
                 b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
+            }
             }
             uint32_t lt0 = 0u, lt1 = 0u;
 #pragma unroll

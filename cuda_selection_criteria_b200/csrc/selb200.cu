@@ -1217,7 +1217,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
                 k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                  d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
-            } else if (hll_planes && hll_subsets_env) {
+            } else if (hll_planes && hll_subsets_env && (uint64_t)6 * ((1u << c->aux_len) >> 5) * (uint64_t)c->npad < (1ull << 32)) {
+                // (the subset form indexes the plane matrix with 32-bit word offsets)
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 if (crit == SELB200_CRIT_HLL_A)
                     k_tile_filter_hll_planes<2><<<grid, 64, hll_smem, s>>>(
