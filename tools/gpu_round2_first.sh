@@ -25,7 +25,7 @@ step() {   # step NAME LIMIT cmd...
     return $rc
 }
 KO="python bench.py --no-cpu-baseline --no-e2e"
-SELB200_TEST_SUBSETS=1 SELB200_TEST_H2D=1 step pytest 420 python -m pytest tests -m gpu -x -q -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
+SELB200_TEST_SUBSETS=1 SELB200_TEST_H2D=1 step pytest 420 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
 step bench_planes 60 $KO > $OUT/${TAG}_bench_planes.json 2> $OUT/${TAG}_bench_planes.err
 SELB200_UNION=subsets step bench_subsets 60 $KO > $OUT/${TAG}_bench_subsets.json 2> $OUT/${TAG}_bench_subsets.err
 step bench_e2e_bytes 120 python bench.py --no-cpu-baseline > $OUT/${TAG}_bench_e2e_bytes.json 2> /dev/null
