@@ -106,6 +106,7 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 // (LOP3 borrow-chain max, 3+3-bit decode, carry-save counting) instead of 2^p_aux shared-memory
 // read-modify-writes, and written once into the thread's shared-memory column for the estimator.
 //   auxP[(plane*nw + w)*npad + g] : word w (32 registers) of a plane of the g-th sorted genome
+//                                   (subset form: the quad layout of k_aux_planes_quad in the same buffer)
 //   agrange[g]                    : min | max<<8 of that genome's auxiliary registers
 // The 32 pairs of a warp step share one 32-value window (their genomes sit within the CB band of each
 // other, so their register ranges coincide); a step whose pairs do not fit one window takes the byte
@@ -133,6 +134,34 @@ k_aux_planes(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order,
 #pragma unroll
             for (int q = 0; q < 8; ++q) m |= ((((wd[q] >> b) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
             auxP[((size_t)b * nw + w) * npad + g] = m;
+        }
+    }
+}
+
+// The same planes in QUAD layout, read by the subset form of the filter (k_tile_filter_hll_planes<2>, <3>): the twelve
+// plane words of a word PAIR (planes 0..5 of word 2wp, then of word 2wp+1) of one genome sit in three uint4,
+//   auxQ[(wp*3 + q)*npad + g]   q = 0: planes 0..3 of word 2wp   q = 1: planes 4,5 of 2wp and 0,1 of 2wp+1   q = 2: planes 2..5 of 2wp+1
+// so a filter step is three 128-bit loads per genome (coalesced over the 32 columns of a warp step) instead of twelve
+// 32-bit loads with their own index arithmetic.
+__global__ void __launch_bounds__(256)
+k_aux_planes_quad(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, long long npad,
+                  int p_aux, uint32_t* __restrict__ auxQ) {
+    const int nw = (1 << p_aux) >> 5;
+    const long long total = n * nw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx / n);
+        const long long g = idx - (long long)w * n;
+        const uint4* src = reinterpret_cast<const uint4*>(aux + ((size_t)order[g] << p_aux) + (size_t)w * 32);
+        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+        const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) m |= ((((wd[q] >> b) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
+            const int slot = (w & 1) * 6 + b;            // 0..11 inside the word pair
+            auxQ[(((size_t)(w >> 1) * 3 + (slot >> 2)) * npad + g) * 4 + (slot & 3)] = m;
         }
     }
 }
@@ -170,15 +199,17 @@ __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ row
         {
             uint32_t a[2][6], b[2][6];
             if (FORM == 1) {
-                // 32-bit word offsets from the two pointers (the launcher takes this form only while the plane
-                // matrix stays below 2^32 words): one widening multiply-add per load instead of 64-bit index math
-                const uint32_t np32 = (uint32_t)npad, ps = (uint32_t)nw * np32, ow = (uint32_t)w * np32;
-#pragma unroll
-                for (int pl = 0; pl < 6; ++pl) {
-                    const uint32_t o0 = (uint32_t)pl * ps + ow, o1 = o0 + np32;
-                    a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
-                    b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
-                }
+                // quad layout (k_aux_planes_quad): rowp / colp point at the genome's first uint4; three 128-bit loads
+                // per genome and step, 32-bit uint4 offsets (the launcher checks that the matrix stays below 2^32)
+                const uint4* rq = reinterpret_cast<const uint4*>(rowp);
+                const uint4* cq = reinterpret_cast<const uint4*>(colp);
+                const uint32_t np32 = (uint32_t)npad, o = (uint32_t)(w >> 1) * 3u * np32;
+                const uint4 r0 = __ldg(rq + o), r1 = __ldg(rq + (o + np32)), r2 = __ldg(rq + (o + 2u * np32));
+                const uint4 c0 = __ldg(cq + o), c1 = __ldg(cq + (o + np32)), c2 = __ldg(cq + (o + 2u * np32));
+                a[0][0] = r0.x; a[0][1] = r0.y; a[0][2] = r0.z; a[0][3] = r0.w; a[0][4] = r1.x; a[0][5] = r1.y;
+                a[1][0] = r1.z; a[1][1] = r1.w; a[1][2] = r2.x; a[1][3] = r2.y; a[1][4] = r2.z; a[1][5] = r2.w;
+                b[0][0] = c0.x; b[0][1] = c0.y; b[0][2] = c0.z; b[0][3] = c0.w; b[0][4] = c1.x; b[0][5] = c1.y;
+                b[1][0] = c1.z; b[1][1] = c1.w; b[1][2] = c2.x; b[1][3] = c2.y; b[1][4] = c2.z; b[1][5] = c2.w;
             } else {
 #pragma unroll
             for (int pl = 0; pl < 6; ++pl) {
@@ -341,8 +372,8 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
                     for (int tt = 0; tt < 8; ++tt)
                         if ((2 * g0 + tt) >= (vlo >> 2) && (2 * g0 + tt) <= (vhi >> 2)) gmask |= 1u << tt;
                 }
-                const uint32_t* rowp = auxP + i;
-                const uint32_t* colp = auxP + kc;
+                const uint32_t* rowp = FORM ? auxP + 4 * (size_t)i : auxP + i;      // FORM 1: quad layout, uint4 per genome
+                const uint32_t* colp = FORM ? auxP + 4 * (size_t)kc : auxP + kc;
                 switch (g0) {
                     case 0: aux_plane_hist<0, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
                     case 1: aux_plane_hist<1, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;

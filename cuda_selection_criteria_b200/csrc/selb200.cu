@@ -53,6 +53,12 @@ namespace {
 
 thread_local std::string g_err;
 
+// SELB200_HLLFILTER=subsets (read once per process): subset form of the plane hll filter and its quad plane layout
+bool hll_subsets_enabled() {
+    static const bool on = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "subsets"); }();
+    return on;
+}
+
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -204,6 +210,7 @@ struct selb200_ctx {
     DevBuf g_push, g_merged;
     DevBuf row_cnt, row_off, sort_tmp;
     DevBuf auxP, agrange;                // bit planes / register ranges of the auxiliary HLLs (sorted order)
+    bool auxp_quad = false;              // auxP holds the quad layout of k_aux_planes_quad (SELB200_HLLFILTER=subsets)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
     int chunk_regs = 0;
     // split form of the union pass (kernels/union_split.inl): 5 relative planes + high list per genome
@@ -743,8 +750,14 @@ int load_end(selb200_ctx* c) {
             CK(cudaMemsetAsync(c->auxP.p, 0, (size_t)6 * nw * c->npad * 4, s));
             CK(cudaMemsetAsync(c->agrange.p, 0, (size_t)c->npad * sizeof(uint16_t), s));
             const int g2 = (int)std::min<int64_t>((n * nw + 255) / 256, (int64_t)c->sm_count * 16);
-            k_aux_planes<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n, c->npad,
-                                            aux_len, c->auxP.as<uint32_t>());
+            // the subset form of the filter reads the quad layout with 32-bit uint4 offsets
+            c->auxp_quad = hll_subsets_enabled() && (uint64_t)6 * nw * (uint64_t)c->npad < (1ull << 32);
+            if (c->auxp_quad)
+                k_aux_planes_quad<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n,
+                                                     c->npad, aux_len, c->auxP.as<uint32_t>());
+            else
+                k_aux_planes<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n, c->npad,
+                                                aux_len, c->auxP.as<uint32_t>());
             CK(cudaGetLastError());
             k_aux_range<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux),
                                                                          c->order_dev.as<int32_t>(), n, aux_len,
@@ -1069,8 +1082,9 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     // SELB200_HLLFILTER=bytes keeps the shared-memory-counter filter (A/B measurements); sketches below 64
     // registers have no bit planes
     static const bool hll_bytes_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "bytes"); }();
-    // SELB200_HLLFILTER=subsets: the plane filter with subset counting on groups of four values (instantiations <2>, <3>)
-    static const bool hll_subsets_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "subsets"); }();
+    // SELB200_HLLFILTER=subsets: the plane filter with subset counting on groups of four values (instantiations <2>, <3>),
+    // decided at load time together with the layout of auxP
+    const bool hll_subsets_env = c->auxp_quad;
     const bool hll_planes = crit >= SELB200_CRIT_HLL_A && c->aux_len >= 6 && !hll_bytes_env;
     if (crit >= SELB200_CRIT_HLL_A) {
         hll_smem = (size_t)(hll_planes ? 1 : 2) * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
@@ -1217,8 +1231,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
                 k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                  d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
-            } else if (hll_planes && hll_subsets_env && (uint64_t)6 * ((1u << c->aux_len) >> 5) * (uint64_t)c->npad < (1ull << 32)) {
-                // (the subset form indexes the plane matrix with 32-bit word offsets)
+            } else if (hll_planes && hll_subsets_env) {
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 if (crit == SELB200_CRIT_HLL_A)
                     k_tile_filter_hll_planes<2><<<grid, 64, hll_smem, s>>>(

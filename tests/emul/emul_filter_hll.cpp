@@ -50,11 +50,15 @@ static int hist_check(uint64_t seed, int count) {
         a[rng() % m] = b[rng() % m] = (uint8_t)vhi;                   // the range is attained
         a[rng() % m] = (uint8_t)vlo; b[rng() % m] = (uint8_t)vlo;
         const long long npad = 2;                                     // two "genomes": planes[plane][word][genome]
-        std::vector<uint32_t> P((size_t)6 * nw * npad, 0u);
+        std::vector<uint32_t> P((size_t)6 * nw * npad, 0u), Q((size_t)6 * nw * npad, 0u);   // Q: quad layout (k_aux_planes_quad)
         for (int g = 0; g < 2; ++g)
             for (int j = 0; j < m; ++j)
                 for (int pl = 0; pl < 6; ++pl)
-                    if (((g ? b[j] : a[j]) >> pl) & 1) P[((size_t)pl * nw + (j >> 5)) * npad + g] |= 1u << (j & 31);
+                    if (((g ? b[j] : a[j]) >> pl) & 1) {
+                        const int w = j >> 5, slot = (w & 1) * 6 + pl;
+                        P[((size_t)pl * nw + w) * npad + g] |= 1u << (j & 31);
+                        Q[(((size_t)(w >> 1) * 3 + (slot >> 2)) * npad + g) * 4 + (slot & 3)] |= 1u << (j & 31);
+                    }
         uint32_t want[64] = {0};
         int rlo = 63, rhi = 0;
         for (int j = 0; j < m; ++j) { const int v = std::max(a[j], b[j]); want[v]++; rlo = std::min(rlo, v); rhi = std::max(rhi, v); }
@@ -68,7 +72,7 @@ static int hist_check(uint64_t seed, int count) {
             else { for (int t = 0; t < 8; ++t) if (2 * g0 + t >= (klo >> 2) && 2 * g0 + t <= (khi >> 2)) gmask |= 1u << t; }
             std::vector<uint32_t> hcol((size_t)64 * 64, 0xDEADBEEFu);
             auto run = [&](auto G0) {
-                if (form) aux_plane_hist<decltype(G0)::value, 1>(P.data(), P.data() + 1, npad, nw, gmask, hcol.data(), nbins);
+                if (form) aux_plane_hist<decltype(G0)::value, 1>(Q.data(), Q.data() + 4, npad, nw, gmask, hcol.data(), nbins);
                 else aux_plane_hist<decltype(G0)::value, 0>(P.data(), P.data() + 1, npad, nw, gmask, hcol.data(), nbins);
             };
             switch (g0) {
@@ -137,7 +141,10 @@ int main(int argc, char** argv) {
     std::vector<uint32_t> auxP(planes ? (size_t)6 * nw * npad : 1, 0u);
     std::vector<uint16_t> agrange((size_t)npad, 0);
     if (planes) {
-        emul::launch(2, 256, [&] { k_aux_planes(aux.data(), order.data(), n, npad, p_aux, auxP.data()); });
+        emul::launch(2, 256, [&] {
+            if (subsets) k_aux_planes_quad(aux.data(), order.data(), n, npad, p_aux, auxP.data());
+            else k_aux_planes(aux.data(), order.data(), n, npad, p_aux, auxP.data());
+        });
         emul::launch((unsigned)(((long long)n * 32 + 255) / 256), 256, [&] { k_aux_range(aux.data(), order.data(), n, p_aux, agrange.data()); });
     }
     const unsigned long long cap = 1ull << 22;
