@@ -743,6 +743,7 @@ int load_end(selb200_ctx* c) {
         k_aux_transpose<<<grid, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(d_aux), c->order_dev.as<int32_t>(), n,
                                              c->npad, row_words, c->auxT.as<uint32_t>());
         CK(cudaGetLastError());
+        c->auxp_quad = false;
         if (aux_len >= 6) {       // bit planes for k_tile_filter_hll_planes (two 32-register words per step)
             const int nw = (1 << aux_len) >> 5;
             CKR(c->auxP.ensure((size_t)6 * nw * c->npad * 4));
