@@ -212,7 +212,10 @@ def test_cp_async_model_catches_ring_mutations(tmp_path, name, old, new):
     e = cards[order].astype(np.uint64)
     aux_sorted = np.ascontiguousarray(smh[order])
     n_bands, n_rows = O.band_params(m_aux, tau32)
-    _, _, p_cb, _, _, pairs = run_emulated(str(exe), tmp_path, e, aux_sorted, tau32, n_rows, n_bands, 1, 3)
     _, _, op_cb, opairs = oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands)
-    assert p_cb == op_cb                       # the band does not depend on the ring
-    assert pairs != opairs                     # the broken ring loses or invents pairs, and the check sees it
+    for attempt in range(3):                   # the barrier mutation shows through thread timing: up to three runs
+        _, _, p_cb, _, _, pairs = run_emulated(str(exe), tmp_path, e, aux_sorted, tau32, n_rows, n_bands, 1, 3)
+        assert p_cb == op_cb                   # the band does not depend on the ring
+        if pairs != opairs:
+            return                             # the broken ring loses or invents pairs, and the check sees it
+    assert pairs != opairs

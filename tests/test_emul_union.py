@@ -70,6 +70,11 @@ def test_mbarrier_model_catches_protocol_mutations(tmp_path, name, old, new, exp
     exe = tmp_path / "emul_union_mut"
     subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-Wno-unknown-pragmas",
                     str(tree / "tests" / "emul" / "emul_union.cpp"), "-o", str(exe), "-ldl"], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    # the missing-barrier mutation shows through thread timing (a lane still reading when lane 0 poisons the stage):
+    # seen in every run so far, but give it three runs before calling the model blind
+    for attempt in range(3):
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 and expect in r.stdout + r.stderr:
+            return
     assert r.returncode != 0
     assert expect in r.stdout + r.stderr, (r.stdout[-1500:], r.stderr[-500:])
