@@ -261,7 +261,11 @@ int main(int argc, char** argv) {
         {"many pairs few warps p10", 10, {50, 55, 60, 65, 70, 75, 80, 85, 90, 95, 100, 105, 110, 115, 120, 125, 130, 135}, 0.8, 55, 2},
     };
     uint64_t seed = 12345;
-    for (const Case& cs : cases) bad += run_case(cs, seed++);
+    const bool first_fail = getenv("EMUL_UNION_FIRST_FAIL") != nullptr;      // mutation tests: one failing case is enough
+    for (const Case& cs : cases) {
+        bad += run_case(cs, seed++);
+        if (bad && first_fail) break;
+    }
     printf(bad ? "FAILED (%d)\n" : "all identical\n", bad);
     return bad ? 1 : 0;
 }

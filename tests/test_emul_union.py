@@ -73,7 +73,8 @@ def test_mbarrier_model_catches_protocol_mutations(tmp_path, name, old, new, exp
     # the missing-barrier mutation shows through thread timing (a lane still reading when lane 0 poisons the stage):
     # seen in every run so far, but give it three runs before calling the model blind
     for attempt in range(3):
-        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, EMUL_UNION_FIRST_FAIL="1"))
         if r.returncode != 0 and expect in r.stdout + r.stderr:
             return
     assert r.returncode != 0
