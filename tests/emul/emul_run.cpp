@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <numeric>
 
+#include <string>
+
 #define SELB_EMUL 1
 #include "cuda_emul.h"
 #include "../../cuda_selection_criteria_b200/csrc/estimators.cuh"
@@ -41,7 +43,7 @@ static void lap(const char* what) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: emul_run in.bin out.bin\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: emul_run in.bin out.bin [subsets]\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     int32_t hdr[5];
@@ -129,9 +131,14 @@ int main(int argc, char** argv) {
     {
         SrcPairs src{pairs.data(), order.data(), (long long)cap, meta.data() + M_PAIRS};
         EpiWriteHist epi{hist.data()};
+        const bool subsets = argc > 3 && std::string(argv[3]) == "subsets";     // SELB200_UNION=subsets
         emul::launch(3, 32, [&] {
-            k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide.data(), meta.data() + M_WIDE,
-                                             meta.data() + M_BATCH);
+            if (subsets)
+                k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi},
+                                                             wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH);
+            else
+                k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide.data(), meta.data() + M_WIDE,
+                                                 meta.data() + M_BATCH);
         });
         SrcWide wsrc{pairs.data(), order.data(), wide.data(), meta.data() + M_WIDE};
         emul::launch(2, 64, [&] { k_pair_hist<52, SrcWide, EpiWriteHist>(regs.data(), m, m, wsrc, epi); });

@@ -25,11 +25,12 @@ def exe(tmp_path_factory):
     return str(out)
 
 
-@pytest.mark.parametrize("n,seed,tau,m_aux,outliers", [
-    (130, 61, 0.9, 128, False),
-    (140, 62, 0.9, 64, True),          # a few registers far above the rest: wide pairs take the byte kernel
+@pytest.mark.parametrize("n,seed,tau,m_aux,outliers,union_form", [
+    (130, 61, 0.9, 128, False, "planes"),
+    (140, 62, 0.9, 64, True, "planes"),          # a few registers far above the rest: wide pairs take the byte kernel
+    (120, 63, 0.9, 128, True, "subsets"),        # the subset counting form of the plane kernel (SELB200_UNION=subsets)
 ])
-def test_whole_smh_a_run_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, outliers):
+def test_whole_smh_a_run_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, outliers, union_form):
     tau32 = np.float32(tau)
     plan = synth.make_plan(n, seed)
     regs = synth.hll(plan, 14).copy()
@@ -49,7 +50,7 @@ def test_whole_smh_a_run_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, out
         f.write(struct.pack("<d", float(tau32)))
         f.write(np.ascontiguousarray(regs, np.uint8).tobytes())
         f.write(np.ascontiguousarray(smh, np.uint64).tobytes())
-    r = subprocess.run([exe, str(inp), str(outp)], capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([exe, str(inp), str(outp), union_form], capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(outp, "rb").read()
     p_cb, cand, p_aux, p_out, near, wide, tie, _ = struct.unpack_from("<8q", raw, 0)
