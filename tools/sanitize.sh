@@ -13,7 +13,7 @@ for tool in memcheck racecheck synccheck initcheck; do
     [ "$left" -lt 30 ] && { echo "$tool: skipped (only ${left}s left)"; continue; }
     lim=$(( left < 240 ? left : 240 ))
     for form in planes subsets split; do
-        SELB200_UNION=$form timeout -k 5 $lim compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 9 \
+        SELB200_UNION=$form SELB200_HLLFILTER=$form timeout -k 5 $lim compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 9 \
             python -c "$SMOKE" > $OUT/sanitize_${tool}_${form}.log 2>&1
         echo "$tool ($form): rc=$? $(grep -c 'ERROR SUMMARY' $OUT/sanitize_${tool}_${form}.log) summary line(s): $(grep 'ERROR SUMMARY' $OUT/sanitize_${tool}_${form}.log | tail -1)"
     done
