@@ -10,19 +10,28 @@ synthetic bacterial-size genomes ("synth-v1", seed 1002), primary HLL p=14, CB +
 over that batch: CB band -> smh_a filter -> HLL-14 union -> Jaccard >= tau -> pair list, sorted,
 gathered on rank 0.  metric = [n(n-1)/2] / step time.
 
-  value : inputs already resident in HBM (sketches generated on the device; with N>1 ranks they
-          are broadcast once over NCCL before the timed region), device time by CUDA events on
-          the stream the kernels run on, max over ranks.
-  e2e   : the same through the public API with HOST buffers: pinned host -> device copy of the
-          sketch matrices, per-genome cardinalities + sort, the run, and the device -> host read
-          of the pair list, every step (N>1: rank 0 uploads, NCCL broadcast, shards, gather).
-  roofline / cpu_baseline: see DESIGN.md §measurement.
+  value   : inputs already resident in HBM (sketches generated on the device; with N>1 ranks they
+            are broadcast once over NCCL before the timed region), device time by CUDA events on
+            the stream the kernels run on, max over ranks.
+  e2e     : the same through the public API with HOST buffers: pinned host -> device copy of the
+            sketch matrices, per-genome cardinalities + sort, the run, and the device -> host read
+            of the pair list, every step (N>1: every rank uploads its slice, NCCL all-gather).
+  parity  : outside the timed region.  N=1: the pair list of the benchmark configuration is diffed
+            against the stdout of the UNMODIFIED reference binary (oracle/_ref/selection) run on the
+            same inputs written as the reference's own gz files, and against the oracle port
+            (full-precision Jaccards, stage counts, near-tau list).  N>1: the merged multi-GPU list
+            against an unsharded run on rank 0 (whose SHA-256 is the one the N=1 run verified).
+  configs : C2, C3 (tau sweep) and C5 of BASELINE.json measured in the same run (resident inputs),
+            each with stage counts, per-stage device times, its dominant kernel and (N=1) its own
+            oracle diff.
+  roofline / kernels / cpu_baseline: see DESIGN.md §7.
 
 One JSON line on stdout (rank 0).  Under torchrun it reads RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import shutil
@@ -30,7 +39,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,6 +49,9 @@ import numpy as np  # noqa: E402
 METRIC = "sketch_pair_comparisons_per_sec"
 UNIT = "pairs/s"
 ALG_BYTES = {"cb": 16, "smh_a": 2048, "union": 32768, "emit": 16}   # SURVEY.md §8d, per unit of work
+INT_PEAK = 64.0   # alu-pipe lane-ops per clock per SM: 4 SMSPs x 16 lanes (B300_MICROARCH.md "alu-pipe rt_SMSP=2");
+#                   tools/ubench/int_pipes.cu measured 63 for LOP3 / PRMT / VIADDMNMX on this pool's B200s
+REL_TOL = 1e-6    # north_star: Jaccard within 1e-6 relative; pairs within 1e-6 of tau listed separately
 
 
 def parse():
@@ -55,15 +66,44 @@ def parse():
     ap.add_argument("--tau", type=float, default=0.9)
     ap.add_argument("--aux-bytes", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=1002)
-    ap.add_argument("--cpu-sample", type=int, default=25_000, help="genomes in the bounded CPU-baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=900.0,
+                    help="--impl reference: wall-clock budget for the timed full-configuration passes")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference pass (and with it the parity block)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C5 block")
+    ap.add_argument("--no-config-parity", action="store_true", help="configs block without its oracle diffs")
+    ap.add_argument("--cfg-steps", type=int, default=5)
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"synth-v1 seed {a.seed}: n={a.n} genomes, HLL p=14, CB + {a.criterion}"
-            + (f" (aux {a.aux_bytes} B)" if a.criterion != "cb" else "") + f", tau={a.tau}")
+class Cfg:
+    """One workload: what both arms put into `config` (identical dicts) and what the generators need."""
+
+    def __init__(self, n, seed, criterion, tau, aux_bytes):
+        self.n, self.seed, self.criterion, self.tau = int(n), int(seed), criterion, float(tau)
+        self.aux_bytes = int(aux_bytes) if criterion != "cb" else 0
+
+    @property
+    def pairs(self):
+        return self.n * (self.n - 1) // 2
+
+    def name(self):
+        return (f"synth-v1 seed {self.seed}: n={self.n} genomes, HLL p=14, CB + {self.criterion}"
+                + (f" (aux {self.aux_bytes} B)" if self.criterion != "cb" else "") + f", tau={self.tau}")
+
+    def config(self):
+        return {"workload": self.name(), "n": self.n, "pairs": self.pairs, "criterion": self.criterion, "tau": self.tau,
+                "aux_bytes": self.aux_bytes, "seed": self.seed, "p": 14,
+                "l2": "inputs larger than L2 at n >= 10k (n x 16 KiB registers); no flush needed"}
+
+
+def other_configs():
+    """BASELINE.json configs[1], [2], [4]; C4 is the headline workload."""
+    out = [("C2 cb", Cfg(10_000, 1001, "cb", 0.9, 0))]
+    out += [(f"C3 smh_a tau={t:.2f}", Cfg(10_000, 1001, "smh_a", t, 1024)) for t in (0.70, 0.75, 0.80, 0.85, 0.90, 0.95)]
+    out += [("C5 hll_a p_aux=10", Cfg(50_000, 1003, "hll_a", 0.9, 1024)), ("C5 hll_an p_aux=10", Cfg(50_000, 1003, "hll_an", 0.9, 1024)),
+            ("C5 hll_a p_aux=8", Cfg(50_000, 1003, "hll_a", 0.9, 256)), ("C5 hll_an p_aux=8", Cfg(50_000, 1003, "hll_an", 0.9, 256))]
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -133,97 +173,227 @@ def ncu_traffic(kernel: str):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline: the reference's own OpenMP selection.cpp (oracle/_ref/selection), bounded sample
+# the reference's own OpenMP selection.cpp (oracle/_ref/selection) on the workload written as its gz files
 # ----------------------------------------------------------------------------------------------
-def write_sample(a, n_s: int, td: str):
-    from cuda_selection_criteria_b200 import sketch_io, synth
-    plan = synth.make_plan(a.n, a.seed).head(n_s)
+def file_names(n):
+    return [f"g{i:06d}.fna.gz" for i in range(n)]
+
+
+def host_inputs(cfg: Cfg):
+    """(regs uint8[n][2^14], aux or None) from the host generator (bit-identical to the device one, tested)."""
+    from cuda_selection_criteria_b200 import synth
+    plan = synth.make_plan(cfg.n, cfg.seed)
     regs = synth.hll(plan, 14)
-    names = [f"g{i:06d}.fna.gz" for i in range(n_s)]
-    smh = aux = None
+    aux = None
+    if cfg.criterion == "smh_a":
+        aux = synth.smh(plan, cfg.aux_bytes // 8)
+    elif cfg.criterion in ("hll_a", "hll_an"):
+        aux = synth.hll(plan, cfg.aux_bytes.bit_length() - 1, synth.TAG_AUX_HLL)
+    return regs, aux
+
+
+_W = {}
+
+
+def _write_range(rg):
+    from cuda_selection_criteria_b200 import sketch_io
+    a, b = rg
+    td, names, regs, smh, aux, pa = _W["td"], _W["names"], _W["regs"], _W["smh"], _W["aux"], _W["pa"]
+    for i in range(a, b):
+        base = os.path.join(td, names[i])
+        sketch_io.write_hll(base + ".hll", regs[i], 14, level=1)
+        if smh is not None:
+            sketch_io.write_smh(base + ".smh" + str(smh.shape[1]), smh[i], level=1)
+        if aux is not None:
+            sketch_io.write_hll(base + ".hll_" + str(pa), aux[i], pa, level=1)
+    return b - a
+
+
+def write_files(cfg: Cfg, regs, aux, td: str):
+    """The reference's on-disk layout (sketch_io) for the whole workload, written by forked workers (the parent
+    must not have touched CUDA yet: the reference leg runs before the device is initialised)."""
+    import multiprocessing as mp
+    n = cfg.n
+    smh = auxh = None
     pa = 0
-    if a.criterion == "smh_a":
-        smh = synth.smh(plan, a.aux_bytes // 8)
-    elif a.criterion in ("hll_a", "hll_an"):
-        pa = a.aux_bytes.bit_length() - 1
-        aux = synth.hll(plan, pa, synth.TAG_AUX_HLL)
+    if cfg.criterion == "smh_a":
+        smh = aux
+    elif cfg.criterion in ("hll_a", "hll_an"):
+        auxh, pa = aux, cfg.aux_bytes.bit_length() - 1
     else:
-        smh = np.full((n_s, 1), 42, np.uint64)     # CB only: constant .smh1 -> smh_a always passes
-    sketch_io.write_dataset(td, names, 14, regs, smh=smh, aux_hll=aux, aux_p=pa, threads=os.cpu_count() or 8)
+        smh = np.full((n, 1), 42, np.uint64)     # CB only: constant .smh1 -> smh_a always passes (SURVEY.md §8c)
+    _W.update(td=td, names=file_names(n), regs=regs, smh=smh, aux=auxh, pa=pa)
+    nw = os.cpu_count() or 1
+    step = max(1, (n + nw * 8 - 1) // (nw * 8))
+    with mp.get_context("fork").Pool(nw) as pool:
+        done = sum(pool.map(_write_range, [(a, min(n, a + step)) for a in range(0, n, step)]))
+    assert done == n
     with open(os.path.join(td, "list.txt"), "w") as f:
-        f.write("\n".join(names) + "\n")
-    return regs, smh if smh is not None else aux
+        f.write("\n".join(_W["names"]) + "\n")
+    _W.clear()
 
 
-def ref_flags(a):
-    crit = "smh_a" if a.criterion == "cb" else a.criterion
-    aux_bytes = 8 if a.criterion == "cb" else a.aux_bytes
-    return crit, aux_bytes
-
-
-def time_reference_once(a, td: str, cores: int):
-    """compare-phase seconds of the unmodified binary: wall(tau) - wall(-h 2.0) (load + sort only)."""
+def ref_cmd(cfg: Cfg, cores: int, tau):
     ref = os.path.join(ROOT, "oracle", "_ref", "selection")
-    crit, aux_bytes = ref_flags(a)
-    base = [ref, "-l", "list.txt", "-t", str(cores), "-a", str(aux_bytes), "-c", crit]
+    crit = "smh_a" if cfg.criterion == "cb" else cfg.criterion
+    aux_bytes = 8 if cfg.criterion == "cb" else cfg.aux_bytes
+    return [ref, "-l", "list.txt", "-t", str(cores), "-a", str(aux_bytes), "-c", crit, "-h", str(tau)]
+
+
+def ref_pass(cfg: Cfg, td: str, cores: int, tau=None):
+    """(wall seconds, stdout bytes) of one run of the unmodified binary over the whole workload."""
     t0 = time.perf_counter()
-    out = subprocess.run(base + ["-h", str(a.tau)], cwd=td, capture_output=True, check=True).stdout
-    t1 = time.perf_counter()
-    subprocess.run(base + ["-h", "2.0"], cwd=td, capture_output=True, check=True)
-    t2 = time.perf_counter()
-    return max((t1 - t0) - (t2 - t1), 1e-9), (t1 - t0), (t2 - t1), out.count(b"\n")
+    out = subprocess.run(ref_cmd(cfg, cores, cfg.tau if tau is None else tau), cwd=td, capture_output=True, check=True).stdout
+    return time.perf_counter() - t0, out
 
 
-def time_port_once(a, regs, aux, cores: int):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_api as O
-    t0 = time.perf_counter()
-    res = O.select(regs, 14, a.criterion, np.float32(a.tau), aux=aux, threads=cores)
-    # the port computes cardinalities inside; subtract nothing — report as is, it is only a fallback
-    return time.perf_counter() - t0, len(res["i"])
+class ReferenceLeg:
+    """Materialises the workload once and runs the reference on ALL of it.  compare phase = wall(-h tau) minus
+    wall(-h 2.0) (CB breaks every row at once: load + sort only), BASELINE.md §4.2."""
 
+    def __init__(self, cfg: Cfg):
+        self.cfg = cfg
+        self.cores = os.cpu_count() or 1
+        self.have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "selection"))
+        self.td = tempfile.mkdtemp(prefix="selb200_ref_")
+        self.lines = None
+        self.t_prep = self.t_load = 0.0
+        self.regs = self.aux = None
 
-def cpu_baseline(a, steps: int = 1, warmup: int = 0):
-    cores = os.cpu_count() or 1
-    n_s = min(a.cpu_sample, a.n)
-    pairs = n_s * (n_s - 1) / 2
-    td = tempfile.mkdtemp(prefix="selb200_cpu_")
-    try:
-        regs, aux = write_sample(a, n_s, td)
-        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "selection"))
-        secs = []
-        detail = {}
-        for it in range(warmup + steps):
-            if have_ref:
-                cmp_s, full_s, load_s, lines = time_reference_once(a, td, cores)
-                detail = {"wall_tau_s": round(full_s, 3), "wall_load_only_s": round(load_s, 3), "lines": lines}
-            else:
-                cmp_s, lines = time_port_once(a, regs, aux if a.criterion != "cb" else None, cores)
-                detail = {"lines": lines}
-            if it >= warmup:
-                secs.append(cmp_s)
+    def prepare(self):
+        t0 = time.perf_counter()
+        self.regs, self.aux = host_inputs(self.cfg)
+        if self.have_ref:
+            write_files(self.cfg, self.regs, self.aux, self.td)
+            self.t_prep = time.perf_counter() - t0
+            self.t_load = min(ref_pass(self.cfg, self.td, self.cores, tau=2.0)[0] for _ in range(2))
+        else:
+            self.t_prep = time.perf_counter() - t0
+
+    def one_pass(self):
+        """compare-phase seconds of one full pass; keeps the reference's stdout lines of the first one."""
+        if self.have_ref:
+            wall, out = ref_pass(self.cfg, self.td, self.cores)
+            if self.lines is None:
+                self.lines = out.decode().splitlines()
+            return max(wall - self.t_load, 1e-9), wall
+        # no reference binary on this machine (it is built where /root/reference exists): the oracle port
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+        t0 = time.perf_counter()
+        res = O.select(self.regs, 14, self.cfg.criterion, np.float32(self.cfg.tau),
+                       aux=self.aux if self.cfg.criterion != "cb" else None, threads=self.cores)
+        wall = time.perf_counter() - t0
+        if self.lines is None:
+            self.lines = O.format_lines(file_names(self.cfg.n), res)
+        return wall, wall
+
+    def drop_files(self):
+        shutil.rmtree(self.td, ignore_errors=True)
+
+    def baseline(self, secs, walls):
         t = sum(secs) / len(secs)
-        return {"value": pairs / t, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port",
-                "sample": (f"first {n_s} genomes of the workload ({int(pairs)} pairs); compare phase = "
-                           f"wall(-h {a.tau}) - wall(-h 2.0) of oracle/_ref/selection -t {cores}"
-                           if have_ref else f"first {n_s} genomes, oracle port incl. cardinalities, {cores} threads"),
-                "seconds_per_pass": t, **detail}
-    finally:
-        shutil.rmtree(td, ignore_errors=True)
+        kind = "reference" if self.have_ref else "port"
+        return {"value": self.cfg.pairs / t, "unit": UNIT, "cores": self.cores, "kind": kind,
+                "sample": (f"the whole workload ({self.cfg.pairs} pairs, all {self.cfg.n} genomes), {len(secs)} full pass(es) of "
+                           + (f"oracle/_ref/selection -t {self.cores} on the reference's own gz files; compare phase = "
+                              f"wall(-h {self.cfg.tau}) - wall(-h 2.0)" if self.have_ref else
+                              f"the oracle port (oracle/liboracle.so, {self.cores} threads, incl. cardinalities)")),
+                "seconds_per_pass": t, "passes": len(secs), "wall_tau_s": [round(w, 2) for w in walls],
+                "wall_load_only_s": round(self.t_load, 2), "prep_s": round(self.t_prep, 1),
+                "lines": len(self.lines) if self.lines is not None else None}
 
 
-def run_reference_arm(a, rank: int, world: int, out):
+def run_reference_arm(a, cfg: Cfg, rank: int, out):
+    """--impl reference: the unmodified binary on the SAME configuration (all n genomes), every step one full pass.
+    A full pass takes minutes of host-core time at n = 100k (std::map<string> lookups and by-value vector copies per
+    CB pair, src/selection.cpp:279-284), so when warmup + steps passes do not fit --ref-budget-s the arm times as many
+    full passes as fit (at least one after one warm-up pass) and says so in `steps` / `steps_requested`."""
     if rank != 0:
         return
-    cb = cpu_baseline(a, steps=a.steps, warmup=a.warmup)
+    leg = ReferenceLeg(cfg)
+    try:
+        leg.prepare()
+        t0 = time.perf_counter()
+        first_cmp, first_wall = leg.one_pass()                 # warm-up pass 1 (page cache, and the pair list)
+        per_pass = time.perf_counter() - t0
+        fit = int(max(0.0, a.ref_budget_s - per_pass) // max(per_pass, 1e-3))
+        if fit >= (a.warmup - 1) + a.steps:
+            n_warm, n_steps = a.warmup, a.steps
+        else:
+            n_warm, n_steps = 1, max(1, min(a.steps, fit))
+        for _ in range(n_warm - 1):
+            leg.one_pass()
+        secs, walls = [], []
+        for _ in range(n_steps):
+            c, w = leg.one_pass()
+            secs.append(c); walls.append(w)
+        cb = leg.baseline(secs, walls)
+    finally:
+        leg.drop_files()
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["seconds_per_pass"] * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/u64 + f64",
-            "data": "synthetic", "config": {"workload": workload_name(a), "sample": cb["sample"]},
-            "cpu_baseline": cb,
+            "steps": n_steps, "warmup": n_warm, "steps_requested": a.steps, "warmup_requested": a.warmup,
+            "ms_per_step": cb["seconds_per_pass"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 registers / u64 buckets, f64 estimator", "data": "synthetic", "config": cfg.config(),
+            "parallelism": f"host OpenMP, {cb['cores']} threads", "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if (n_warm, n_steps) != (a.warmup, a.steps):
+        line["note"] = (f"{a.warmup}+{a.steps} full passes of {per_pass:.0f} s do not fit the {a.ref_budget_s:.0f} s budget: "
+                        f"{n_warm} warm-up + {n_steps} timed full-configuration passes were run instead of a smaller sample")
     print(json.dumps(line), file=out, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# parity helpers (outside every timed region)
+# ----------------------------------------------------------------------------------------------
+def lines_sha(lines):
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()
+
+
+def diff_reference_lines(got_lines, ref_lines, tau):
+    """Pair-set diff of `name name jaccard` lines (run_comparison_experiment.sh:36-52 joins on the two names)."""
+    def keyed(ls):
+        d = {}
+        for ln in ls:
+            p = ln.rsplit(" ", 1)
+            d[p[0]] = p[1]
+        return d
+    g, r = keyed(got_lines), keyed(ref_lines)
+    common = [k for k in r if k in g]
+    max_abs = max((abs(float(g[k]) - float(r[k])) for k in common), default=0.0)
+    return {"against": "stdout of the unmodified reference binary (oracle/_ref/selection) on the same inputs, all n genomes",
+            "pairs_reference": len(r), "pairs_ours": len(g), "pairs_missing": len(r) - len(common),
+            "pairs_extra": len(g) - len(common), "lines_identical_in_order": got_lines == ref_lines,
+            "max_abs_diff_printed_jaccard": max_abs,
+            "printed_precision": "std::to_string: 6 decimals, so identical strings bound |dJ| by 1e-6 absolute; "
+                                 "the full-precision comparison is the `oracle_port` block"}
+
+
+def diff_oracle(res, ora, tau):
+    """Full-precision diff against the oracle port: pair set, stage counts, relative Jaccard error, near-tau list."""
+    got = {(int(i), int(k)): float(j) for i, k, j in zip(res.i, res.k, res.jaccard)}
+    want = {(int(i), int(k)): float(j) for i, k, j in zip(ora["i"], ora["k"], ora["jaccard"])}
+    near = sorted({(int(i), int(k)) for i, k in zip(res.near_i, res.near_k)})
+    missing = [p for p in want if p not in got and p not in near]
+    extra = [p for p in got if p not in want and p not in near]
+    common = [p for p in want if p in got]
+    rel = max((abs(got[p] - want[p]) / max(abs(want[p]), 1e-300) for p in common), default=0.0)
+    st = res.stats
+    return {"against": "oracle/liboracle.so (CPU restatement pinned to the reference's goldens), same inputs, all n genomes",
+            "pairs_oracle": len(want), "pairs_ours": len(got), "pairs_missing": len(missing), "pairs_extra": len(extra),
+            "order_identical": list(zip(res.i.tolist(), res.k.tolist())) == list(zip(ora["i"].tolist(), ora["k"].tolist())),
+            "max_rel_jaccard": rel, "rel_tol": REL_TOL, "jaccard_bits_identical": bool(
+                len(got) == len(want) and np.array_equal(res.jaccard.view(np.int64), ora["jaccard"].view(np.int64))),
+            "pairs_cb_equal": st["pairs_cb"] == ora["stage"][1], "pairs_aux_equal": st["pairs_aux"] == ora["stage"][2],
+            "pairs_out_equal": st["pairs_out"] == ora["stage"][3], "cards_truncated_equal": bool(np.array_equal(
+                res.cards_sorted.astype(np.uint64), ora["cards_sorted"].astype(np.uint64))),
+            "near_tau": [[i, k, got.get((i, k), None)] for i, k in near][:64], "near_tau_count": len(near)}
+
+
+def parity_ok(p):
+    return (p["pairs_missing"] == 0 and p["pairs_extra"] == 0 and p.get("max_rel_jaccard", 0.0) <= REL_TOL
+            and p.get("pairs_cb_equal", True) and p.get("pairs_aux_equal", True) and p.get("cards_truncated_equal", True))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -238,15 +408,95 @@ def _protect_stdout():
     return os.fdopen(saved, "w")
 
 
+def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
+    """One entry per stage of the run (this rank's launches, CUDA events inside the library): time, share of the run,
+    the roof that binds it and the achieved fraction.  Integer-pipe entries count ESSENTIAL lane-operations (the
+    instructions the algorithm needs, not the ones issued) against the alu-pipe rate of the SM; byte entries count
+    SURVEY.md §8d's algorithmic bytes against the measured HBM rate."""
+    run_ms = mean("ms_total")
+    rows = []
+
+    def add(stage, kernel, ms, bound, work, per_unit, unit_def, note=None):
+        if ms <= 0:
+            return
+        e = {"stage": stage, "kernel": kernel, "ms": ms, "share_of_run": ms / run_ms if run_ms > 0 else None, "bound": bound}
+        if bound == "int_alu":
+            ach = work * per_unit / (ms * 1e-3) / sm_clk_hz / n_sm
+            e.update(achieved=ach, peak=INT_PEAK, unit="essential alu lane-ops/clk/SM", frac=ach / INT_PEAK)
+        else:
+            ach = work * per_unit / (ms * 1e-3) / 1e9
+            e.update(achieved=ach, peak=peak_hbm, unit="GB/s (algorithmic bytes)", frac=ach / peak_hbm)
+        e["def"] = unit_def
+        if note:
+            e["note"] = note
+        rows.append(e)
+
+    p_cb, p_cand, p_aux, p_out = st["pairs_cb_shard"], st["pairs_cand"], st["pairs_aux"], st["pairs_out"]
+    add("bounds", "k_cb_bounds + k_rowblock_span + scan + k_tile_table", mean("ms_bounds"), "hbm", cfg.n, 16.0 * 20,
+        "16 B per tested pair x ~20 binary-search probes per row", "latency-bound: four small launches")
+    if cfg.criterion == "smh_a":
+        nb = st["n_bands"]
+        add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, ((nb + 1) // 2) * 32.0,
+            f"one packed min/add (VIADDMNMX.U16x2) per two LSH bands and pair: {(nb + 1) // 2} per CB pair of the shard, 32-bit lanes")
+        add("verify", "k_smh_verify", mean("ms_verify"), "hbm", p_cand, 2.0 * 8 * st["n_rows"] + 16,
+            "2 x 8 x n_rows bucket bytes + 16 B per candidate", "latency-bound: thread per candidate, dependent loads")
+    elif cfg.criterion in ("hll_a", "hll_an"):
+        regs_aux = cfg.aux_bytes
+        add("filter", "k_tile_filter_hll_planes", mean("ms_filter"), "int_alu", p_cb, hll_essential_lop3(regs_aux),
+            f"essential LOP3 per CB pair (thread per pair, so lane-op = op): {hll_essential_lop3(regs_aux):.0f} for "
+            f"{regs_aux} auxiliary registers (max 12 + subset counting of 5 four-value groups: 6 selectors + 80, per 64 registers)")
+    else:
+        add("filter", "k_tile_enum", mean("ms_filter"), "hbm", p_cb, 16.0, "16 B per CB pair (emit the band)")
+    lop3 = union_lop3_per_pair()
+    add("union", union_kernel_name(), mean("ms_union"), "int_alu", p_aux, lop3 * 32.0,
+        f"{lop3:.0f} essential LOP3 per pair and lane (all value groups of the 32-value window active: upper bound) x 32 lanes")
+    add("estimate", "k_estimate_emit", mean("ms_estimate"), "hbm", p_aux, 256.0 + 16,
+        "256 B histogram row + 16 B descriptor per aux-passing pair", "fp64-latency-bound: thread per histogram, Ertl MLE secant loop")
+    add("sort", "k_rowsort_* + D2H", mean("ms_sort"), "hbm", max(p_out, 1), 16.0 * 4, "16 B per emitted pair, four passes",
+        "latency-bound: four small launches + the copy to pinned host memory")
+    return rows
+
+
+def union_kernel_name():
+    return {"bytes": "k_pair_hist", "planes": "k_pair_hist_planes<one-hot>"}.get(os.environ.get("SELB200_UNION", ""),
+                                                                                "k_pair_hist_planes<EpiSubsets>")
+
+
+def union_lop3_per_pair():
+    # essential LOP3 per pair and lane at p=14 (8 steps of 64 registers per lane): one-hot form 8 x (20 max + 16 decode +
+    # 4 groups x 34) = 1376; subset form 8 x (20 max + 8 selectors + 8 groups of four x 16) = 1248.  With the group masks of
+    # the C4 workload the kernels execute about 1200 and 905 (tests/emul/union_lop3_model.py).
+    return {"planes": 1376.0, "bytes": 0.0}.get(os.environ.get("SELB200_UNION", ""), 1248.0)
+
+
+def hll_essential_lop3(regs_aux):
+    return (regs_aux / 64.0) * (24 + 6 + 5 * 16)
+
+
 def main():
     a = parse()
     real_stdout = _protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = Cfg(a.n, a.seed, a.criterion, a.tau, a.aux_bytes)
     if a.impl == "reference":
-        run_reference_arm(a, rank, world, real_stdout)
+        run_reference_arm(a, cfg, rank, real_stdout)
         return
+
+    # ---- reference leg first (rank 0 at N=1 only), before this process touches CUDA: the file writers fork -------
+    cb = None
+    ref_lines = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        leg = ReferenceLeg(cfg)
+        try:
+            leg.prepare()
+            c, w = leg.one_pass()
+            cb = leg.baseline([c], [w])
+            ref_lines = leg.lines
+        finally:
+            leg.drop_files()
+        del leg
 
     import torch
     import torch.distributed as dist
@@ -267,26 +517,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    aux_kind = {"cb": AUX_NONE, "smh_a": AUX_SMH, "hll_a": AUX_HLL, "hll_an": AUX_HLL}[a.criterion]
-    plan = synth.make_plan(a.n, a.seed)
-    # ---- resident inputs: generated on rank 0's device, broadcast over NCCL -----------------------
-    if rank == 0:
-        regs_d = synth.hll(plan, 14, device=local)
-        aux_d = None
-        if aux_kind == AUX_SMH:
-            aux_d = synth.smh(plan, a.aux_bytes // 8, device=local)
-        elif aux_kind == AUX_HLL:
-            aux_d = synth.hll(plan, a.aux_bytes.bit_length() - 1, synth.TAG_AUX_HLL, device=local)
-    else:
-        regs_d = torch.empty((a.n, 1 << 14), dtype=torch.uint8, device=dev)
-        aux_d = None
-        if aux_kind == AUX_SMH:
-            aux_d = torch.empty((a.n, a.aux_bytes // 8), dtype=torch.int64, device=dev)
-        elif aux_kind == AUX_HLL:
-            aux_d = torch.empty((a.n, a.aux_bytes), dtype=torch.uint8, device=dev)
-    if world > 1:
-        sdist.broadcast_sketches(regs_d, aux_d, src=0)
-    torch.cuda.synchronize()
+    def aux_kind_of(c: Cfg):
+        return {"cb": AUX_NONE, "smh_a": AUX_SMH, "hll_a": AUX_HLL, "hll_an": AUX_HLL}[c.criterion]
+
+    def resident_inputs(c: Cfg):
+        """sketches generated on rank 0's device, broadcast over NCCL"""
+        plan = synth.make_plan(c.n, c.seed)
+        kind = aux_kind_of(c)
+        if rank == 0:
+            regs_d = synth.hll(plan, 14, device=local)
+            aux_d = None
+            if kind == AUX_SMH:
+                aux_d = synth.smh(plan, c.aux_bytes // 8, device=local)
+            elif kind == AUX_HLL:
+                aux_d = synth.hll(plan, c.aux_bytes.bit_length() - 1, synth.TAG_AUX_HLL, device=local)
+        else:
+            regs_d = torch.empty((c.n, 1 << 14), dtype=torch.uint8, device=dev)
+            aux_d = None
+            if kind == AUX_SMH:
+                aux_d = torch.empty((c.n, c.aux_bytes // 8), dtype=torch.int64, device=dev)
+            elif kind == AUX_HLL:
+                aux_d = torch.empty((c.n, c.aux_bytes), dtype=torch.uint8, device=dev)
+        if world > 1:
+            sdist.broadcast_sketches(regs_d, aux_d, src=0)
+        torch.cuda.synchronize()
+        return regs_d, aux_d, kind
+
+    regs_d, aux_d, aux_kind = resident_inputs(cfg)
 
     # one explicit stream for everything: torch copies and NCCL collectives issued under it and the
     # library's kernels (which run on the stream handed to the context) are then ordered on the device
@@ -297,98 +554,111 @@ def main():
     assert stream != 0
     sel = S.Selection(local, stream=stream)
     sel.load(regs_d, aux_d, aux_kind)
-
-    tau32 = np.float32(a.tau)
-    stats_acc = []
-
     if world > 1:
         sdist.setup_gather(sel)        # rank 0's landing zone, mapped into every rank (CUDA IPC)
 
-    def step_resident():
-        # with several ranks every rank's kernels store its pairs into rank 0's memory over NVLink
-        # (peer-memory gather inside selb200_run); rank 0 sorts the merged list and its run ends with the
-        # D2H of that list into pinned host memory — inside the metric
-        res = sel.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False,
-                      gather=(world > 1), host_results=(rank == 0))
-        return res.stats, (sel.result_host()[0].size if rank == 0 else 0)
+    def timed_steps(sel_, c: Cfg, warmup, steps, sample_clocks):
+        """W warm-up + K timed steps of the resident path; (ms per step max over ranks, stats of every step, clocks)"""
+        tau32 = np.float32(c.tau)
+        acc = []
 
-    for _ in range(a.warmup):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    out_n = 0
-    for _ in range(a.steps):
-        st, out_n = step_resident()
-        stats_acc.append(st)
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1) / a.steps
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms.item())
-    pairs_total = a.n * (a.n - 1) / 2
-    value = pairs_total / (ms_step * 1e-3)
+        def step():
+            # with several ranks every rank's kernels store its pairs into rank 0's memory over NVLink
+            # (peer-memory gather inside selb200_run); rank 0 sorts the merged list and its run ends with the
+            # D2H of that list into pinned host memory — inside the metric (SURVEY §8d)
+            res = sel_.run(tau=tau32, criterion=c.criterion, shard=rank, n_shards=world, fetch=False,
+                           gather=(world > 1), host_results=(rank == 0))
+            return res.stats, (sel_.result_host()[0].size if rank == 0 else 0)
 
-    # ---- roofline of the dominant kernel (this rank's launches, CUDA events inside the library) ----
-    def mean(key):
-        return sum(s[key] for s in stats_acc) / len(stats_acc)
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        out_n = 0
+        for _ in range(steps):
+            st, out_n = step()
+            acc.append(st)
+        ev1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        t_ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item()), acc, out_n, clocks
+
+    ms_step, stats_acc, out_n, clocks = timed_steps(sel, cfg, a.warmup, a.steps, True)
+    value = cfg.pairs / (ms_step * 1e-3)
+
+    def mean_of(acc):
+        return lambda key: sum(s[key] for s in acc) / len(acc)
 
     st0 = stats_acc[-1]
     peak, peak_src = measured_peak()
-    union_kernel = {"bytes": "k_pair_hist", "split": "k_pair_hist_split",
-                    "subsets": "k_pair_hist_planes<EpiSubsets>"}.get(os.environ.get("SELB200_UNION", ""), "k_pair_hist_planes")
-    k_union = {"name": union_kernel, "ms": mean("ms_union"), "bytes": ALG_BYTES["union"] * st0["pairs_aux"],
-               "unit_def": "32768 B (2 x 2^14 one-byte registers, SURVEY.md 8d) per aux-passing pair x pairs_aux"}
-    per_pair_filter = {"smh_a": ALG_BYTES["smh_a"], "cb": ALG_BYTES["cb"],
-                       "hll_a": 2 * a.aux_bytes, "hll_an": 2 * a.aux_bytes}[a.criterion]
-    k_filter = {"name": {"smh_a": "k_tile_filter_smh", "cb": "k_tile_enum", "hll_a": "k_tile_filter_hll",
-                         "hll_an": "k_tile_filter_hll"}[a.criterion],
-                "ms": mean("ms_filter"), "bytes": per_pair_filter * st0["pairs_cb_shard"],
-                "unit_def": f"{per_pair_filter} B per CB-passing pair x pairs_cb(shard)"}
-    dom = k_union if k_union["ms"] >= k_filter["ms"] else k_filter
-    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-    # the same launch against the integer pipe it is actually bound by.  Essential LOP3 per pair and lane at p=14
-    # (8 steps of 64 registers per lane): split kernel 8 x (2 flags + 16 max + 4 group masks + 16 decode + 2 groups x 32)
-    # = 816; bit-plane kernel 8 x (20 max + 16 decode + 4 groups x 34) = 1376; its subset form 8 x (20 max + 8 selectors
-    # + 8 groups of four x 16) = 1248.  These are the counts with every value group of the window active; the group masks
-    # of the C4 workload make the kernels execute about 1200 and 905 (tests/emul/union_lop3_model.py), so `frac` is an
-    # upper bound of the essential-LOP3 share.  The LOP3 rate of the SM was measured with tools/ubench/int_pipes.cu
-    # (profiles/r01_int_pipes_ubench.txt)
-    int_alu = None
-    lop3_per_pair = {"k_pair_hist_split": 816.0, "k_pair_hist_planes": 1376.0,
-                     "k_pair_hist_planes<EpiSubsets>": 1248.0}.get(dom["name"])
-    if lop3_per_pair and dom["ms"] > 0:
-        sm_clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
-        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-        lane_ops = lop3_per_pair * 32.0 * st0["pairs_aux"]
-        a_int = lane_ops / (dom["ms"] * 1e-3) / sm_clk / n_sm
-        int_alu = {"bound": "int_alu", "achieved": a_int, "peak": 63.0, "unit": "LOP3 lane-ops/clk/SM",
-                   "frac": a_int / 63.0,
-                   "def": f"{lop3_per_pair:.0f} LOP3 per pair and lane (all value groups of the window active: upper bound) "
-                          "x 32 lanes x pairs_aux / launch time / SM clock / SMs; peak measured"}
-    roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": ncu_traffic(dom["name"]), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"], "bytes_def": dom["unit_def"],
-                "int_alu": int_alu,
-                "note": ("frac > 1 is possible: the union kernel reads 6-bit planes (24 KiB per pair, 20 KiB when all values "
-                         "are below 32) and L2 serves repeated rows; its binding limit is the integer ALU pipe "
-                         "(profiles/r01_ncu_summary.md)"),
-                "kernels_ms": {"bounds": mean("ms_bounds"), "filter": mean("ms_filter"), "verify": mean("ms_verify"),
-                               "union": mean("ms_union"), "estimate": mean("ms_estimate"), "sort": mean("ms_sort"),
-                               "run_total": mean("ms_total")}}
+    sm_clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    kernels = kernel_table(cfg, st0, mean_of(stats_acc), sm_clk, n_sm, peak)
+    dom = max(kernels, key=lambda e: e["ms"])
+    dom_alg_bytes = {"union": ALG_BYTES["union"] * st0["pairs_aux"],
+                     "filter": {"smh_a": ALG_BYTES["smh_a"], "cb": ALG_BYTES["cb"], "hll_a": 2 * cfg.aux_bytes,
+                                "hll_an": 2 * cfg.aux_bytes}[cfg.criterion] * st0["pairs_cb_shard"]}.get(dom["stage"], 0)
+    hbm_ach = dom_alg_bytes / (dom["ms"] * 1e-3) / 1e9
+    # the contract's block for the DOMINANT kernel.  Its binding roof is the integer ALU pipe (ncu: profiles/), so
+    # bound / achieved / peak / frac are stated against that pipe; the algorithmic-byte figure of SURVEY.md §8d against
+    # the measured HBM rate sits beside it under "hbm" (it can exceed 1: bit planes move 20-24 KiB per pair, not 32,
+    # and L2 serves repeated rows — see `traffic`)
+    roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]), "launch_ms": dom["ms"],
+                "def": dom["def"],
+                "peak_source": ("alu pipe: 4 SMSPs x 16 lanes per clock (B300_MICROARCH.md 'alu-pipe rt_SMSP=2'; "
+                                "tools/ubench/int_pipes.cu measured 63 on this pool)" if dom["bound"] == "int_alu" else peak_src),
+                "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": dom_alg_bytes,
+                        "note": "SURVEY.md 8d algorithmic bytes / launch time; not the binding roof when frac > 1"},
+                "kernels_ms": {k: mean_of(stats_acc)(f"ms_{k}") for k in ("bounds", "filter", "verify", "union", "estimate", "sort")}
+                | {"run_total": mean_of(stats_acc)("ms_total")}}
+
+    # ---- parity of the benchmark configuration (untimed) ---------------------------------------------
+    parity = None
+    names = file_names(cfg.n)
+    full = sel.run(tau=np.float32(cfg.tau), criterion=cfg.criterion, shard=rank, n_shards=world, gather=(world > 1),
+                   fetch=(rank == 0))
+    if rank == 0:
+        got_lines = S.format_lines(names, full)
+        parity = {"lines_sha256": lines_sha(got_lines), "pairs": len(got_lines)}
+    if world > 1:
+        # the merged multi-GPU list against an unsharded run of the same context on rank 0
+        if rank == 0:
+            solo = sel.run(tau=np.float32(cfg.tau), criterion=cfg.criterion)
+            same = (np.array_equal(solo.i, full.i) and np.array_equal(solo.k, full.k)
+                    and np.array_equal(solo.jaccard.view(np.int64), full.jaccard.view(np.int64)))
+            parity["multi_gpu"] = {"against": "unsharded run on rank 0 (the list whose SHA-256 the N=1 run checks against the reference)",
+                                   "pairs_single": int(solo.i.size), "pairs_merged": int(full.i.size),
+                                   "identical_pairs_order_and_jaccard_bits": bool(same),
+                                   "single_gpu_lines_sha256": lines_sha(S.format_lines(names, solo))}
+            parity["ok"] = bool(same)
+        barrier()
+    elif rank == 0 and ref_lines is not None:
+        parity["reference_binary" if cb["kind"] == "reference" else "oracle_lines"] = diff_reference_lines(got_lines, ref_lines, cfg.tau)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api as O
+        regs_h = regs_d.cpu().numpy()
+        aux_h = None if aux_d is None else (aux_d.cpu().numpy().view(np.uint64) if aux_kind == AUX_SMH else aux_d.cpu().numpy())
+        ora = O.select(regs_h, 14, cfg.criterion, np.float32(cfg.tau), aux=aux_h, threads=os.cpu_count() or 1)
+        parity["oracle_port"] = diff_oracle(full, ora, cfg.tau)
+        del regs_h, aux_h, ora
+        parity["ok"] = all(parity_ok(parity[k]) for k in ("reference_binary", "oracle_lines", "oracle_port") if k in parity)
+    del full
 
     # ---- e2e: host buffers through the public API ---------------------------------------------------
     e2e = None
     if not a.no_e2e:
         # every rank holds its slice of the file list in pinned host memory (world == 1: everything)
-        g0, rows, _per = sdist.slice_rows(a.n, rank, world)
+        g0, rows, _per = sdist.slice_rows(cfg.n, rank, world)
         regs_h = torch.empty((rows, regs_d.shape[1]), dtype=regs_d.dtype, pin_memory=True)
         regs_h.copy_(regs_d[g0:g0 + rows])
         aux_h = None
@@ -396,14 +666,30 @@ def main():
             aux_h = torch.empty((rows, aux_d.shape[1]), dtype=aux_d.dtype, pin_memory=True)
             aux_h.copy_(aux_d[g0:g0 + rows])
         torch.cuda.synchronize()
+        # what the link itself delivers: the same pinned buffer copied alone (best of 3), every rank at once
+        link = []
+        scratch = torch.empty_like(regs_h, device=dev)
+        for _ in range(3):
+            barrier()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            scratch.copy_(regs_h, non_blocking=True)
+            l1.record()
+            torch.cuda.synchronize()
+            link.append(regs_h.numel() / (l0.elapsed_time(l1) * 1e-3) / 1e9)
+        del scratch
+        link_gbs = torch.tensor([max(link)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(link_gbs, op=dist.ReduceOp.SUM)
         sel2 = S.Selection(local, stream=stream)
         sh = None
         if world > 1:
             sdist.setup_gather(sel2)
-            sh = sdist.ShardedSketches(a.n, regs_d.shape[1], aux_d.shape[1] if aux_d is not None else 0,
+            sh = sdist.ShardedSketches(cfg.n, regs_d.shape[1], aux_d.shape[1] if aux_d is not None else 0,
                                        aux_d.dtype if aux_d is not None else None, dev, rank, world)
 
         phase = {"h2d_gather_load": 0.0, "run_gather_fetch": 0.0}
+        tau32 = np.float32(cfg.tau)
 
         def step_e2e():
             t_a = time.perf_counter()
@@ -416,7 +702,7 @@ def main():
                 sh.assemble(regs_h, aux_h, on_piece=sel2.load_device_rows)
                 sel2.load_end()
             t_b = time.perf_counter()              # load returns after its last device sync
-            sel2.run(tau=tau32, criterion=a.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1),
+            sel2.run(tau=tau32, criterion=cfg.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1),
                      host_results=(rank == 0))
             out = sel2.result_host()[0].size if rank == 0 else 0
             phase["h2d_gather_load"] += t_b - t_a
@@ -429,43 +715,87 @@ def main():
         for k_ in phase:
             phase[k_] = 0.0
         t0 = time.perf_counter()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+        g0e, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0e.record()
         for _ in range(e2e_steps):
-            n_out = step_e2e()
-        g1.record()
+            step_e2e()
+        g1e.record()
         barrier()
         wall = (time.perf_counter() - t0) / e2e_steps
-        dev_ms = g0.elapsed_time(g1) / e2e_steps
+        dev_ms = g0e.elapsed_time(g1e) / e2e_steps
         t2 = torch.tensor([max(wall * 1e3, dev_ms)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2.item())
         h2d = int(regs_d.numel() * regs_d.element_size() + (aux_d.numel() * aux_d.element_size() if aux_d is not None else 0))
-        e2e = {"value": pairs_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(out_n * 16 + a.n * 8), "ms_per_step": e2e_ms, "steps": e2e_steps,
+        link_total = float(link_gbs.item())
+        e2e = {"value": cfg.pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(out_n * 16 + cfg.n * 8), "ms_per_step": e2e_ms, "steps": e2e_steps,
                "timer": "max(host wall clock, CUDA events) per step, max over ranks",
-               "rank0_phases_ms": {k: v * 1e3 / e2e_steps for k, v in phase.items()}}
+               "rank0_phases_ms": {k: v * 1e3 / e2e_steps for k, v in phase.items()},
+               "h2d_link": {"measured_gbs_all_ranks": link_total, "achieved_gbs": h2d / (e2e_ms * 1e-3) / 1e9,
+                            "frac": (h2d / (e2e_ms * 1e-3) / 1e9) / link_total if link_total > 0 else None,
+                            "def": "pinned host -> device copy of the same register buffer alone, best of 3, summed over "
+                                   "ranks copying at once; achieved = h2d bytes / whole e2e step"}}
         sel2.close()
+        del regs_h, aux_h
 
-    cb = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cb = cpu_baseline(a)
+    # ---- the other configurations of BASELINE.json, measured in the same run -------------------------
+    configs = None
+    if not a.no_configs:
+        sel.close()
+        del regs_d, aux_d
+        torch.cuda.empty_cache()
+        configs = {}
+        for label, c in other_configs():
+            r_d, a_d, kind = resident_inputs(c)
+            s2 = S.Selection(local, stream=stream)
+            s2.load(r_d, a_d, kind)
+            if world > 1:
+                sdist.setup_gather(s2)
+            ms_c, acc_c, out_c, _ = timed_steps(s2, c, 3, max(1, a.cfg_steps), False)
+            stc = acc_c[-1]
+            kt = kernel_table(c, stc, mean_of(acc_c), sm_clk, n_sm, peak)
+            d = max(kt, key=lambda e: e["ms"])
+            entry = {"config": c.config(), "ms_per_step": ms_c, "value": c.pairs / (ms_c * 1e-3), "unit": UNIT,
+                     "steps": max(1, a.cfg_steps), "warmup": 3,
+                     "stages": {"pairs_cb": stc["pairs_cb"], "pairs_aux_rank0": stc["pairs_aux"], "pairs_out": out_c,
+                                "bands_x_rows": [stc["n_bands"], stc["n_rows"]]},
+                     "kernels_ms": {k: mean_of(acc_c)(f"ms_{k}") for k in ("bounds", "filter", "verify", "union", "estimate", "sort")}
+                     | {"run_total": mean_of(acc_c)("ms_total")},
+                     "dominant": {k: d[k] for k in ("stage", "kernel", "ms", "bound", "achieved", "peak", "unit", "frac")}}
+            if world == 1 and rank == 0 and not a.no_config_parity and not a.no_cpu_baseline:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import oracle_api as O
+                res = s2.run(tau=np.float32(c.tau), criterion=c.criterion)
+                rh = r_d.cpu().numpy()
+                ah = None if a_d is None else (a_d.cpu().numpy().view(np.uint64) if kind == AUX_SMH else a_d.cpu().numpy())
+                ora = O.select(rh, 14, c.criterion, np.float32(c.tau), aux=ah, threads=os.cpu_count() or 1)
+                p = diff_oracle(res, ora, c.tau)
+                p["ok"] = parity_ok(p)
+                entry["parity"] = {k: p[k] for k in ("ok", "pairs_oracle", "pairs_missing", "pairs_extra", "max_rel_jaccard",
+                                                     "pairs_cb_equal", "pairs_aux_equal", "near_tau_count")}
+                del res, rh, ah, ora
+            configs[label] = entry
+            s2.close()
+            del r_d, a_d
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u8 registers / u64 buckets, f64 estimator", "data": "synthetic",
-                "config": {"workload": workload_name(a), "n": a.n, "pairs": int(pairs_total),
-                           "pairs_cb": st0["pairs_cb"], "pairs_aux_rank0": st0["pairs_aux"], "pairs_out": out_n,
-                           "bands_x_rows": [st0["n_bands"], st0["n_rows"]], "parallelism": (f"tile-shard x{world}" + (", peer-memory gather to rank 0; e2e: per-rank H2D slices + "
-                                                                       "NCCL all-gather" if world > 1 else "")),
-                           "l2": "inputs (1.74 GB) larger than L2; no flush needed"},
+                "config": cfg.config(),
+                "parallelism": (f"tile-shard x{world}" + (", peer-memory gather to rank 0; e2e: per-rank H2D slices + "
+                                                           "NCCL all-gather" if world > 1 else "")),
+                "stages": {"pairs_cb": st0["pairs_cb"], "pairs_aux_rank0": st0["pairs_aux"], "pairs_out": out_n,
+                           "bands_x_rows": [st0["n_bands"], st0["n_rows"]]},
                 "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(sum(s["launches"] for s in stats_acc)),
-                "roofline": roofline, "cpu_baseline": cb}
+                "roofline": roofline, "kernels": kernels, "parity": parity, "cpu_baseline": cb, "configs": configs}
         print(json.dumps(line), file=real_stdout, flush=True)
-    sel.close()
+    if configs is None:
+        sel.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -73,7 +73,6 @@ SYMBOLS = [
     ("selb200_band_params", _I, [_I, C.c_float, _I, C.POINTER(_I), C.POINTER(_I)]),
     ("selb200_sort_order", _I, [_I64, _VP, _VP]),
     ("selb200_debug_union", _I, [_VP, _I, _I64, _VP, _VP, _VP]),
-    ("selb200_debug_pack_planes", _I, [_I64, _I, _VP, _VP, _VP]),
     ("selb200_smh_size", _I, [_I]),
     ("selb200_sketch_host", _I, [_I, _I64, _VP, _VP, _I, _I, _I, _VP, _VP]),
     ("selb200_sketch_last_error", C.c_char_p, []),

@@ -61,36 +61,6 @@ k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, 
     }
 }
 
-// inverse of k_planes_from_bytes: used when the host uploads bit planes instead of bytes (SELB200_H2D=planes: 12 KiB
-// instead of 16 KiB per genome over PCIe); the byte matrix is rebuilt on the device for validation, per-genome
-// histograms and the byte kernels.  Same warp shape: 512 registers per step, 16 per lane.
-__global__ void __launch_bounds__(256)
-k_bytes_from_planes(const uint32_t* __restrict__ planes, long long rows, size_t m, int chunk_regs,
-                    uint8_t* __restrict__ regs) {
-    const int lane = threadIdx.x & 31;
-    const long long nblk = rows * (long long)(m >> 9);
-    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int blk_per_genome = (int)(m >> 9), blk_per_chunk = chunk_regs >> 9;
-    const size_t chunk_words = (size_t)6 * (chunk_regs >> 5);
-    for (long long blk = warp0; blk < nblk; blk += nwarps) {
-        const long long g = blk / blk_per_genome;
-        const int bg = (int)(blk - g * blk_per_genome);
-        const int chunk = bg / blk_per_chunk, bc = bg - chunk * blk_per_chunk;
-        const uint32_t* src = planes + (size_t)g * 6 * (m >> 5) + (size_t)chunk * chunk_words + (size_t)bc * 16;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            // the lane's 16 registers are one half of word lane/2 of the plane
-            const uint32_t h = (__ldg(src + (size_t)b * (chunk_regs >> 5) + (lane >> 1)) >> (16 * (lane & 1))) & 0xffffu;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)      // 4 plane bits -> bit 0 of 4 bytes (the multiply spreads them 7 apart)
-                w[k] |= ((((h >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) << b;
-        }
-        reinterpret_cast<uint4*>(regs + (size_t)g * m + (size_t)bg * 512)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
 #ifndef SELB_EMUL   // tests/emul/cuda_emul.h supplies host versions of these five when the .inl runs on the CPU
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

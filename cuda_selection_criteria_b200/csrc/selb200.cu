@@ -39,8 +39,6 @@
 #include <utility>
 #include <vector>
 
-#include <immintrin.h>
-
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -213,13 +211,9 @@ struct selb200_ctx {
     bool auxp_quad = false;              // auxP holds the quad layout of k_aux_planes_quad (SELB200_HLLFILTER=subsets)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
     int chunk_regs = 0;
-    // split form of the union pass (kernels/union_split.inl): 5 relative planes + high list per genome
-    bool union_split = false;
-    // subset form of the plane kernel (k_pair_hist_planes<EpiSubsets<..>>): same planes, other counting step
-    bool union_subsets = false;
-    DevBuf split_rec, gmeta;
-    // SELB200_H2D=planes: selb200_load_host packs every chunk to bit planes on the host before the PCIe copy
-    bool h2d_planes = false;
+    // counting step of the plane kernel: subset masks on groups of four values (k_pair_hist_planes<EpiSubsets<..>>,
+    // default) or one-hot masks on groups of eight (SELB200_UNION=planes)
+    bool union_subsets = true;
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
@@ -244,7 +238,6 @@ namespace {
 #include "kernels/helpers.inl"
 #include "kernels/union_bytes.inl"
 #include "kernels/union_planes.inl"
-#include "kernels/union_split.inl"
 #include "kernels/load_kernels.inl"
 #include "kernels/tiles.inl"
 #include "kernels/filter_smh.inl"
@@ -325,27 +318,10 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         }
         per_sm_smem = smem;
     }
-    // wide count, batch counter, kernel error word (adjacent words of meta[])
-    if (!counters_are_zero) CK(cudaMemsetAsync(wide_count, 0, 24, s));
-    if (c->union_split) {
-        const size_t ssmem = (size_t)PL_STAGES * 2 * split_chunk_bytes(c->chunk_regs) + 8 * PL_STAGES + 64 * sizeof(uint32_t);
-        static int s_per_sm = 0;
-        static size_t s_per_sm_smem = 0;
-        if (!s_per_sm || s_per_sm_smem != ssmem) {
-            cudaFuncSetAttribute(k_pair_hist_split<EpiWriteHist>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_per_sm, k_pair_hist_split<EpiWriteHist>, 32, ssmem) != cudaSuccess ||
-                s_per_sm < 1) {
-                cudaGetLastError();
-                s_per_sm = 4;
-            }
-            s_per_sm_smem = ssmem;
-        }
-        const int sgrid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * s_per_sm);
-        k_pair_hist_split<EpiWriteHist><<<sgrid, 32, ssmem, s>>>(c->split_rec.as<uint8_t>(), c->m, c->chunk_regs,
-                                                                c->gmeta.as<uint32_t>(), src, epi,
-                                                                c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
-    } else if (c->union_subsets) {
+    // wide count and batch counter (adjacent words of meta[]); the kernel error word behind them is sticky for the
+    // whole run: an error raised in an earlier range must still be there when the host reads meta[] at the end
+    if (!counters_are_zero) CK(cudaMemsetAsync(wide_count, 0, 16, s));
+    if (c->union_subsets) {
         static int u_per_sm = 0;
         static size_t u_per_sm_smem = 0;
         if (!u_per_sm || u_per_sm_smem != smem) {
@@ -387,113 +363,6 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
 // the streaming entry points (selb200_load_begin / acquire / commit / end) let the caller decode
 // sketch files straight into pinned staging slots while earlier chunks are already on the device.
 // ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
-// Host-side bit slicing (SELB200_H2D=planes).  HLL registers are 6-bit numbers, so a chunk can cross PCIe as
-// 6 planes (12 KiB per genome at p=14) instead of bytes (16 KiB); the layout is the device one
-// ([genome][chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r of the chunk), so the copy lands
-// in ctx->planes and k_bytes_from_planes rebuilds the byte matrix next to it.
-// 32 registers -> one word per plane: shift the wanted bit into every byte's top position, movemask.
-// *or_all collects the OR of every byte seen (a value above 63 cannot be sliced; the caller fails the load).
-// ---------------------------------------------------------------------------------------------
-__attribute__((target("avx2"))) void pack_planes_avx2(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst,
-                                                     uint32_t* or_all) {
-    const int cw = chunk_regs >> 5;
-    __m256i acc = _mm256_setzero_si256();
-    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
-        uint32_t* d = dst + ch * 6 * (size_t)cw;
-        for (int w = 0; w < cw; ++w) {
-            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + c0 + 32 * (size_t)w));
-            acc = _mm256_or_si256(acc, v);
-            d[0 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 7));
-            d[1 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
-            d[2 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
-            d[3 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 4));
-            d[4 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 3));
-            d[5 * cw + w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 2));
-        }
-    }
-    alignas(32) uint32_t t[8];
-    _mm256_store_si256(reinterpret_cast<__m256i*>(t), acc);
-    uint32_t o = 0;
-    for (int i = 0; i < 8; ++i) o |= t[i];
-    *or_all |= (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xffu;
-}
-
-// 64 registers -> two consecutive words of every plane per vpmovb2m
-__attribute__((target("avx512bw"))) void pack_planes_avx512(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst,
-                                                           uint32_t* or_all) {
-    const int cw = chunk_regs >> 5;
-    __m512i acc = _mm512_setzero_si512();
-    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
-        uint32_t* d = dst + ch * 6 * (size_t)cw;
-        for (int w = 0; w < cw; w += 2) {
-            const __m512i v = _mm512_loadu_si512(src + c0 + 32 * (size_t)w);
-            acc = _mm512_or_si512(acc, v);
-            const uint64_t k0 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 7)), k1 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 6));
-            const uint64_t k2 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 5)), k3 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 4));
-            const uint64_t k4 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 3)), k5 = _mm512_movepi8_mask(_mm512_slli_epi16(v, 2));
-            std::memcpy(d + 0 * cw + w, &k0, 8);
-            std::memcpy(d + 1 * cw + w, &k1, 8);
-            std::memcpy(d + 2 * cw + w, &k2, 8);
-            std::memcpy(d + 3 * cw + w, &k3, 8);
-            std::memcpy(d + 4 * cw + w, &k4, 8);
-            std::memcpy(d + 5 * cw + w, &k5, 8);
-        }
-    }
-    alignas(64) uint32_t t[16];
-    _mm512_store_si512(t, acc);
-    uint32_t o = 0;
-    for (int i = 0; i < 16; ++i) o |= t[i];
-    *or_all |= (o | (o >> 8) | (o >> 16) | (o >> 24)) & 0xffu;
-}
-
-void pack_planes_scalar(const uint8_t* src, size_t m, int chunk_regs, uint32_t* dst, uint32_t* or_all) {
-    const int cw = chunk_regs >> 5;
-    uint64_t acc = 0;
-    for (size_t c0 = 0, ch = 0; c0 < m; c0 += (size_t)chunk_regs, ++ch) {
-        uint32_t* d = dst + ch * 6 * (size_t)cw;
-        for (int w = 0; w < cw; ++w) {
-            uint64_t q[4];
-            std::memcpy(q, src + c0 + 32 * (size_t)w, 32);
-            acc |= q[0] | q[1] | q[2] | q[3];
-            for (int b = 0; b < 6; ++b) {
-                uint32_t word = 0;
-                for (int k = 0; k < 4; ++k)      // bit b of 8 bytes -> 8 bits (the multiply gathers them into the top byte)
-                    word |= (uint32_t)((((q[k] >> b) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56) << (8 * k);
-                d[b * cw + w] = word;
-            }
-        }
-    }
-    acc |= acc >> 32;
-    acc |= acc >> 16;
-    acc |= acc >> 8;
-    *or_all |= (uint32_t)(acc & 0xffu);
-}
-
-// rows genomes of m registers -> planes; returns the OR of all bytes
-uint32_t pack_planes_rows(const uint8_t* regs, int64_t rows, size_t m, int chunk_regs, uint32_t* out) {
-    // widest instruction set of the host; SELB200_PACK=avx2|scalar forces a narrower one (tests)
-    static const int level = [] {
-        const char* e = getenv("SELB200_PACK");
-        int lv = __builtin_cpu_supports("avx512bw") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
-        if (e && !strcmp(e, "avx2")) lv = std::min(lv, 1);
-        if (e && !strcmp(e, "scalar")) lv = 0;
-        return lv;
-    }();
-    uint32_t or_all = 0;
-#pragma omp parallel for schedule(static) reduction(| : or_all)
-    for (int64_t g = 0; g < rows; ++g) {
-        uint32_t o = 0;
-        const uint8_t* src = regs + (size_t)g * m;
-        uint32_t* dst = out + (size_t)g * 6 * (m >> 5);
-        if (level == 2) pack_planes_avx512(src, m, chunk_regs, dst, &o);
-        else if (level == 1) pack_planes_avx2(src, m, chunk_regs, dst, &o);
-        else pack_planes_scalar(src, m, chunk_regs, dst, &o);
-        or_all |= o;
-    }
-    return or_all;
-}
-
 int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, const uint8_t* d_regs_borrowed,
                const void* d_aux_borrowed) {
     if (!c) return fail(SELB200_EINVAL, "null context");
@@ -543,13 +412,7 @@ int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, cons
         }
     }
     c->chunk_regs = (int)std::min<size_t>(c->m, (size_t)PL_CHUNK_REGS);
-    if (c->union_split) {
-        const size_t items = c->m / (size_t)c->chunk_regs + 1;
-        CKR(c->split_rec.ensure((size_t)n * items * split_chunk_bytes(c->chunk_regs)));
-        CKR(c->gmeta.ensure((size_t)n * sizeof(uint32_t)));
-    } else {
-        CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
-    }
+    CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
     CKR(c->grange.ensure((size_t)n * sizeof(uint16_t)));
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
@@ -586,7 +449,7 @@ int load_join_copies(selb200_ctx* c) {
 // rows [g0, g0+rows): optional H2D from host pointers (copy stream), then validation, per-genome
 // histogram and cardinality MLE on the run stream
 int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, const double* h_stored,
-               const void* h_aux, bool pack_planes = false) {
+               const void* h_aux) {
     LoadState& L = c->ld;
     cudaStream_t s = c->stream;
     const int p = c->p;
@@ -603,38 +466,12 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
         L.have_stored = true;
         copied = true;
     }
-    const bool packed = pack_planes && h_regs && !c->union_split && c->m >= 512;
-    if (packed) {
-        // slice on the host (this thread's OpenMP team) into a pinned slot while the previous chunk's copy is
-        // still on the bus; 3 slots, a slot is reused once its copy has completed
-        StageSlot& sl = c->slots[c->next_slot];
-        if (!sl.free_ev) CK(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
-        if (sl.in_flight) { CK(cudaEventSynchronize(sl.free_ev)); sl.in_flight = false; }
-        const size_t plane_bytes = (size_t)rows * 6 * (c->m >> 3);
-        CKR(pinned_ensure((void**)&sl.regs, &sl.regs_cap, (size_t)L.rows_per_chunk * 6 * (c->m >> 3)));
-        const uint32_t or_all = pack_planes_rows(h_regs, rows, c->m, c->chunk_regs, reinterpret_cast<uint32_t*>(sl.regs));
-        if (or_all & 0xC0u)
-            return fail(SELB200_EINVAL, "primary sketch holds a register value above 63: not an HLL (rows %lld..%lld)",
-                        (long long)g0, (long long)(g0 + rows - 1));
-        CK(cudaMemcpyAsync(c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5), sl.regs, plane_bytes,
-                           cudaMemcpyHostToDevice, c->copy_stream));
-        CK(cudaEventRecord(sl.free_ev, c->copy_stream));
-        sl.in_flight = true;
-        c->next_slot = (c->next_slot + 1) % 3;
-        copied = true;
-    } else if (h_regs) {
+    if (h_regs) {
         CK(cudaMemcpyAsync(c->regs_own.as<uint8_t>() + (size_t)g0 * c->m, h_regs, (size_t)rows * c->m,
                            cudaMemcpyHostToDevice, c->copy_stream));
         copied = true;
     }
     if (copied) CKR(load_join_copies(c));
-    if (packed) {   // the byte matrix, rebuilt from the planes that just arrived
-        const long long nblk = rows * (long long)(c->m >> 9);
-        const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
-        k_bytes_from_planes<<<grid, 256, 0, s>>>(c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5), rows, c->m,
-                                                 c->chunk_regs, c->regs_own.as<uint8_t>() + (size_t)g0 * c->m);
-        CK(cudaGetLastError());
-    }
     const size_t n16 = (size_t)rows * c->m / 16;
     k_max_byte<<<(int)std::min<size_t>((n16 + 255) / 256, (size_t)c->sm_count * 8), 256, 0, s>>>(
         reinterpret_cast<const uint4*>(c->d_regs + (size_t)g0 * c->m), n16, c->counters.as<uint32_t>());
@@ -647,15 +484,7 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
         c->cards_in.as<double>() + g0, c->counters.as<uint32_t>(), (uint32_t)(64 - p + 1),
         c->grange.as<uint16_t>() + g0);
     CK(cudaGetLastError());
-    if (c->union_split) {   // relative planes + high lists of the chunk for the split union kernel
-        const size_t items = c->m / (size_t)c->chunk_regs + 1;
-        const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)c->sm_count * 8);
-        k_split_build<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
-                                           c->grange.as<uint16_t>() + g0, c->hist.as<uint32_t>() + (size_t)g0 * 64,
-                                           c->split_rec.as<uint8_t>() + (size_t)g0 * items * split_chunk_bytes(c->chunk_regs),
-                                           c->gmeta.as<uint32_t>() + g0);
-        CK(cudaGetLastError());
-    } else if (!packed) {   // bit-plane copy of the chunk for the union kernel
+    {   // bit-plane copy of the chunk for the union kernel
         const long long nblk = rows * (long long)(c->m >> 9);
         const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
         k_planes_from_bytes<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
@@ -781,8 +610,7 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool on_devic
     for (int64_t g0 = 0; g0 < n; g0 += step) {
         const int64_t rows = std::min(step, n - g0);
         CKR(load_chunk(c, g0, rows, on_device ? nullptr : regs + (size_t)g0 * c->m, stored ? stored + g0 : nullptr,
-                       (on_device || !aux) ? nullptr : (const uint8_t*)aux + (size_t)g0 * L.aux_row_bytes,
-                       !on_device && c->h2d_planes));
+                       (on_device || !aux) ? nullptr : (const uint8_t*)aux + (size_t)g0 * L.aux_row_bytes));
     }
     return load_end(c);
 }
@@ -827,12 +655,9 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    {   // SELB200_UNION: planes (default) | subsets | split | bytes — form of the union pass, read per context
+    {   // SELB200_UNION: subsets (default) | planes (one-hot counting) | bytes — form of the union pass, read per context
         const char* e = getenv("SELB200_UNION");
-        c->union_split = e && !strcmp(e, "split");
-        c->union_subsets = e && !strcmp(e, "subsets");
-        const char* h = getenv("SELB200_H2D");      // planes: selb200_load_host slices on the host, 25 % fewer PCIe bytes
-        c->h2d_planes = h && !strcmp(h, "planes");
+        c->union_subsets = !(e && !strcmp(e, "planes"));
     }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
@@ -849,7 +674,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->split_rec, &c->gmeta};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1659,14 +1484,6 @@ int selb200_result_device(selb200_ctx* c, const uint64_t** d_keys, const double*
     if (!c) return fail(SELB200_EINVAL, "null context");
     if (d_keys) *d_keys = c->res_keys;
     if (d_jaccard) *d_jaccard = c->res_j;
-    return SELB200_OK;
-}
-
-int selb200_debug_pack_planes(int64_t rows, int p, const uint8_t* regs, uint32_t* planes, uint32_t* or_all) {
-    if (rows < 0 || p < 9 || p > 20 || !regs || !planes) return fail(SELB200_EINVAL, "bad arguments");
-    const size_t m = (size_t)1 << p;
-    const uint32_t o = pack_planes_rows(regs, rows, m, (int)std::min<size_t>(m, (size_t)PL_CHUNK_REGS), planes);
-    if (or_all) *or_all = o;
     return SELB200_OK;
 }
 

@@ -204,10 +204,6 @@ int selb200_sort_order(int64_t n, const double* cards, int32_t* order);
  * t[c] = union_size(sketch a[c], sketch b[c]) over the loaded PRIMARY (which=0) or
  * auxiliary-HLL (which=1) sketches; a,b are file-list indices (host arrays). */
 int selb200_debug_union(selb200_ctx* ctx, int which, int64_t count, const int32_t* a, const int32_t* b, double* t);
-/* Host only (no device needed): the bit slicing selb200_load_host applies before the PCIe copy when SELB200_H2D=planes.
- * regs: rows x 2^p register bytes; planes: rows x 6 * 2^p / 32 words in the device layout
- * [genome][chunk][plane][word], bit r of word w = register 32w+r of the chunk; *or_all = OR of all register bytes. */
-int selb200_debug_pack_planes(int64_t rows, int p, const uint8_t* regs, uint32_t* planes, uint32_t* or_all);
 
 /* ---- sketch builder (what `build_sketch` computes) ---------------------
  * For genome g the sequence characters are seq[offsets[g] .. offsets[g+1]) with ONE non-ACGT byte

@@ -1,13 +1,11 @@
 // emul_union.cpp — runs the bit-plane forms of the union pass on the CPU through cuda_emul.h, from the same .inl
 // sources the GPU build compiles:
-//   kernels/union_planes.inl : k_planes_from_bytes + k_pair_hist_planes   (the default form)
-//                              k_pair_hist_planes<EpiSubsets<..>>          (SELB200_UNION=subsets)
-//   kernels/union_split.inl  : k_split_build + k_pair_hist_split          (SELB200_UNION=split)
+//   kernels/union_planes.inl : k_planes_from_bytes + k_pair_hist_planes<EpiSubsets<..>>   (the default form)
+//                              k_pair_hist_planes<EpiWriteHist>: one-hot counting       (SELB200_UNION=planes)
 // and compares every pair's 64-bin histogram with the byte-wise definition
 //   hist[max(a[j], b[j])]++   (sketch/include/sketch/hll.h:1191-1206 of the reference),
 // and the pairs each form hands to the byte kernel ("wide") with the rule it documents.
 // Test infrastructure (tests/test_emul_union.py builds and runs it); exit code 0 = all cases identical.
-#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdio>
@@ -39,7 +37,6 @@ struct EpiWriteHist {
 };
 
 #include "../../cuda_selection_criteria_b200/csrc/kernels/union_planes.inl"
-#include "../../cuda_selection_criteria_b200/csrc/kernels/union_split.inl"
 
 namespace {
 
@@ -53,17 +50,10 @@ struct Case {
     int outlier_every = 0;         // > 0: every such genome gets one register of value 50 (a range wider than 32)
 };
 
-// selb200_debug_pack_planes of the built library (argv[1]), when given: the host-side slicing of SELB200_H2D=planes
-typedef int (*pack_fn_t)(int64_t, int, const uint8_t*, uint32_t*, uint32_t*);
-pack_fn_t g_host_pack = nullptr;
-bool g_layout_only = false;        // argv[2]: only the planes <-> bytes / host packer checks
-
 int run_case(const Case& cs, uint64_t seed) {
     const size_t m = (size_t)1 << cs.p;
     const int n = (int)cs.load.size();
     const int chunk_regs = (int)std::min<size_t>(m, PL_CHUNK_REGS);
-    const int nchunks = (int)(m / chunk_regs);
-    const uint32_t cb = split_chunk_bytes(chunk_regs);
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(1e-12, 1.0);
     auto draw = [&](double load) {
@@ -91,13 +81,6 @@ int run_case(const Case& cs, uint64_t seed) {
             if (ghist[(size_t)g * 64 + b]) { vmin = std::min(vmin, b); vmax = std::max(vmax, b); }
         grange[g] = (uint16_t)(std::min(vmin, vmax) | (vmax << 8));
     }
-    const size_t rec_bytes = (size_t)(nchunks + 1) * cb;
-    uint8_t* rec = (uint8_t*)aligned_alloc(128, ((size_t)n * rec_bytes + 127) / 128 * 128);
-    std::memset(rec, 0xA5, (size_t)n * rec_bytes);       // stale bytes behind short lists must not matter
-    std::vector<uint32_t> gmeta(n, 0);
-    emul::launch(std::min<unsigned>(n, 3), [&] {
-        k_split_build(regs.data(), n, m, chunk_regs, grange.data(), ghist.data(), rec, gmeta.data());
-    });
     // all pairs
     std::vector<uint2> pairs;
     for (int a = 0; a < n; ++a)
@@ -150,36 +133,10 @@ int run_case(const Case& cs, uint64_t seed) {
         bad += fbad;
     };
 
-    // ---- split form ----
-    if (!g_layout_only) check("split",
-          [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
-              emul::launch(cs.grid, [&] {
-                  k_pair_hist_split<EpiWriteHist>(rec, m, chunk_regs, gmeta.data(), src, epi, wide, counters, counters + 1);
-              });
-          },
-          [&](uint32_t a, uint32_t b) {
-              return (gmeta[a] & 0xff) != (gmeta[b] & 0xff) || (gmeta[a] >> 8) == SPLIT_LEN_OVERFLOW ||
-                     (gmeta[b] >> 8) == SPLIT_LEN_OVERFLOW;
-          });
-
-    // ---- plane form (default) ----
+    // ---- plane form, one-hot counting (SELB200_UNION=planes) ----
     std::vector<uint32_t> planes((size_t)n * 6 * (m >> 5), 0xA5A5A5A5u);
     emul::launch(2, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes.data()); });
-    {   // the planes <-> bytes pair of kernels, and the host packer against the device layout
-        std::vector<uint8_t> back((size_t)n * m, 0xEE);
-        emul::launch(2, 256, [&] { k_bytes_from_planes(planes.data(), n, m, chunk_regs, back.data()); });
-        int fbad = back != regs;
-        if (g_host_pack) {
-            std::vector<uint32_t> hp(planes.size(), 0x5A5A5A5Au);
-            uint32_t or_all = 0, or_want = 0;
-            for (uint8_t v : regs) or_want |= v;
-            if (g_host_pack(n, cs.p, regs.data(), hp.data(), &or_all) != 0 || hp != planes || or_all != or_want) ++fbad;
-        }
-        printf("%-26s %-6s p=%d n=%d bytes->planes->bytes%s  %s\n", cs.name, "layout", cs.p, n,
-               g_host_pack ? ", host packer == k_planes_from_bytes" : "", fbad ? "FAIL" : "ok");
-        bad += fbad;
-    }
-    if (!g_layout_only) check("planes",
+    check("planes",
           [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
               emul::launch(cs.grid, [&] {
                   k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide, counters, counters + 1);
@@ -189,8 +146,8 @@ int run_case(const Case& cs, uint64_t seed) {
               const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
               return (hi >> 3) > std::min(lo >> 3, 4) + 3;
           });
-    // ---- plane form with subset counting on groups of four values (SELB200_UNION=subsets): same wide rule ----
-    if (!g_layout_only) check("subsets",
+    // ---- plane form with subset counting on groups of four values (the default): same wide rule ----
+    check("subsets",
           [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
               emul::launch(cs.grid, [&] {
                   k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi}, wide, counters, counters + 1);
@@ -200,7 +157,6 @@ int run_case(const Case& cs, uint64_t seed) {
               const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
               return (hi >> 3) > std::min(lo >> 3, 4) + 3;
           });
-    free(rec);
     return bad;
 }
 
@@ -208,13 +164,6 @@ int run_case(const Case& cs, uint64_t seed) {
 
 int main(int argc, char** argv) {
     int bad = 0;
-    if (argc > 1) {
-        void* h = dlopen(argv[1], RTLD_NOW);
-        if (!h) { fprintf(stderr, "dlopen %s: %s\n", argv[1], dlerror()); return 2; }
-        g_host_pack = (pack_fn_t)dlsym(h, "selb200_debug_pack_planes");
-        if (!g_host_pack) { fprintf(stderr, "selb200_debug_pack_planes not exported\n"); return 2; }
-    }
-    g_layout_only = argc > 2 && std::string(argv[2]) == "layout-only";
     if (argc > 4 && std::string(argv[2]) == "fuzz") {        // emul_union LIB fuzz SEED COUNT: random cases
         std::mt19937_64 rng(strtoull(argv[3], nullptr, 10));
         const int count = atoi(argv[4]);

@@ -325,17 +325,19 @@ def test_wide_value_range_pairs_take_the_byte_kernel(gpu):
     compare(res, O.select(regs, 14, "cb", np.float32(0.97), threads=8), 0.97)
 
 
-def test_split_union_mixed_bases_and_long_lists(gpu, monkeypatch):
-    """SELB200_UNION=split (read when a context is created): the split union kernel counts the 16 values above base = 8*(min>>3) on bit planes and keeps every higher
-    register in a per-genome list.  Pairs whose genomes have different bases, or a list longer than its slot,
-    leave it for the byte kernel; lists of every length in between are merged exactly."""
-    monkeypatch.setenv("SELB200_UNION", "split")
+@pytest.mark.parametrize("form", ["subsets", "planes"])
+def test_union_mixed_value_ranges(gpu, monkeypatch, form):
+    """Both counting steps of the plane union kernel (SELB200_UNION is read when a context is created; subsets is
+    the default) on genomes whose registers start at different values, hold long runs of high values and reach the
+    largest legal value: pairs whose values do not fit one 32-value window leave for the byte kernel, the rest is
+    counted on the planes, and the result must not depend on which."""
+    monkeypatch.setenv("SELB200_UNION", form)
     plan = synth.make_plan(1200, 77)
     regs = synth.hll(plan, 14).copy()
     aux = synth.smh(plan, 128)
-    regs[::3] = np.maximum(regs[::3], 8)              # every third genome: smallest register 8 -> base 8
-    regs[5::50, ::8] = 30                             # 2048 high registers: longer than any list slot
-    regs[7::50, ::40] = 29                            # 410 high registers: a long list that still fits
+    regs[::3] = np.maximum(regs[::3], 8)              # every third genome: smallest register 8 -> window base 8
+    regs[5::50, ::8] = 30                             # 2048 high registers
+    regs[7::50, ::40] = 29                            # 410 high registers
     regs[11::50, 100:140] = 51                        # the largest legal value, a run of neighbours
     for crit, tau, a in (("cb", 0.93, None), ("smh_a", 0.8, aux)):
         ora = O.select(regs, 14, crit, np.float32(tau), aux=a, threads=8)
@@ -344,30 +346,6 @@ def test_split_union_mixed_bases_and_long_lists(gpu, monkeypatch):
             sel.load(regs, a, aux_kind_of(crit))
             for _ in range(3):
                 compare(sel.run(tau=np.float32(tau), criterion=crit), ora, tau)
-
-
-@pytest.mark.skipif(os.environ.get("SELB200_TEST_H2D") != "1",
-                    reason="SELB200_H2D=planes (host-side bit slicing before the PCIe copy) has not run on a GPU yet: "
-                           "written in a session without GPU budget, checked on the CPU emulator only "
-                           "(tests/test_emul_union.py); set SELB200_TEST_H2D=1 to run it")
-def test_packed_upload_equals_byte_upload(gpu, monkeypatch):
-    """selb200_load_host with SELB200_H2D=planes: same cardinalities, order and results as the byte upload, several
-    64 MiB chunks (staging-slot reuse), and a register above 63 is refused on the host."""
-    plan = synth.make_plan(9000, 91)                   # 9000 x 16 KiB = 2.2 chunks
-    regs = synth.hll(plan, 14)
-    aux = synth.smh(plan, 128)
-    ref = run_gpu(regs, aux, "smh_a", 0.9, gpu)
-    monkeypatch.setenv("SELB200_H2D", "planes")
-    for _ in range(2):
-        res = run_gpu(regs, aux, "smh_a", 0.9, gpu)
-        assert np.array_equal(res.order, ref.order)
-        assert np.array_equal(res.cards_sorted.view(np.int64), ref.cards_sorted.view(np.int64))
-        assert np.array_equal(res.i, ref.i) and np.array_equal(res.k, ref.k)
-        assert np.array_equal(res.jaccard.view(np.int64), ref.jaccard.view(np.int64))
-    bad = regs.copy()
-    bad[8999, 100] = 64
-    with pytest.raises(S.SelB200Error):
-        run_gpu(bad, aux, "smh_a", 0.9, gpu)
 
 
 @pytest.mark.parametrize("criterion", ["hll_a", "hll_an"])
