@@ -374,7 +374,8 @@ def diff_oracle(res, ora, tau):
     """Full-precision diff against the oracle port: pair set, stage counts, relative Jaccard error, near-tau list."""
     got = {(int(i), int(k)): float(j) for i, k, j in zip(res.i, res.k, res.jaccard)}
     want = {(int(i), int(k)): float(j) for i, k, j in zip(ora["i"], ora["k"], ora["jaccard"])}
-    near = sorted({(int(i), int(k)) for i, k in zip(res.near_i, res.near_k)})
+    near_j = {(int(i), int(k)): float(j) for i, k, j in zip(res.near_i, res.near_k, res.near_jaccard)}
+    near = sorted(near_j)
     missing = [p for p in want if p not in got and p not in near]
     extra = [p for p in got if p not in want and p not in near]
     common = [p for p in want if p in got]
@@ -388,7 +389,10 @@ def diff_oracle(res, ora, tau):
             "pairs_cb_equal": st["pairs_cb"] == ora["stage"][1], "pairs_aux_equal": st["pairs_aux"] == ora["stage"][2],
             "pairs_out_equal": st["pairs_out"] == ora["stage"][3], "cards_truncated_equal": bool(np.array_equal(
                 res.cards_sorted.astype(np.uint64), ora["cards_sorted"].astype(np.uint64))),
-            "near_tau": [[i, k, got.get((i, k), None)] for i, k in near][:64], "near_tau_count": len(near)}
+            "near_tau": [[i, k, near_j[(i, k)], (i, k) in got] for i, k in near][:64], "near_tau_count": len(near),
+            "near_tau_fields": "sorted row i, sorted column k, Jaccard, emitted",
+            "near_tau_equal_oracle": near == sorted(zip(ora.get("near_i", np.zeros(0, np.int32)).tolist(),
+                                                         ora.get("near_k", np.zeros(0, np.int32)).tolist()))}
 
 
 def parity_ok(p):
@@ -436,8 +440,9 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
         "16 B per tested pair x ~20 binary-search probes per row", "latency-bound: four small launches")
     if cfg.criterion == "smh_a":
         nb = st["n_bands"]
-        add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, ((nb + 1) // 2) * 32.0,
-            f"one packed min/add (VIADDMNMX.U16x2) per two LSH bands and pair: {(nb + 1) // 2} per CB pair of the shard, 32-bit lanes")
+        add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, float((nb + 1) // 2),
+            f"one packed min/add lane-operation (VIADDMNMX.U16x2) per two LSH bands and pair: {(nb + 1) // 2} per CB pair of the shard "
+            "(a thread owns an 8x8 block of pairs, so one lane-operation serves one pair)")
         add("verify", "k_smh_verify", mean("ms_verify"), "hbm", p_cand, 2.0 * 8 * st["n_rows"] + 16,
             "2 x 8 x n_rows bucket bytes + 16 B per candidate", "latency-bound: thread per candidate, dependent loads")
     elif cfg.criterion in ("hll_a", "hll_an"):

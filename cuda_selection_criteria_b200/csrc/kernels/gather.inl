@@ -53,7 +53,7 @@ __global__ void k_gather_claim(GatherZone z, unsigned int epoch, unsigned long l
     st->go = 0;
     st->blocks_done = 0;
     if (check && (meta[M_CAND] > cand_cap || meta[M_PAIRS] > pair_lim || meta[M_OUT] > out_cap ||
-                  meta[M_TILES] > tile_cap))
+                  meta[M_TILES] > tile_cap || meta[M_NEAR] > near_cap_local))
         return;                              // the host redoes the pass and pushes afterwards
     if (epoch >= 2) {
         const unsigned long long t0 = gtime_ns();

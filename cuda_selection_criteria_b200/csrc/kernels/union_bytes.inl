@@ -6,7 +6,11 @@
 //   Src  : where pair (row a, row b) number pi comes from, and how many there are
 //   Epi  : what happens to the finished histogram (lane L holds bins L and L+32)
 // ============================================================================
+// kMask: ANDed onto every loaded register word.  The selection path validates its registers at load time (k_max_byte,
+// SrcSelf) and passes all-ones; the link-level shims histogram caller-owned, unvalidated bytes and keep six bits, so
+// that no byte can address a counter outside the 64-bin array.
 struct SrcPairs {            // pair list of the selection path: sorted positions, mapped through `order`
+    static constexpr uint32_t kMask = 0xffffffffu;
     const uint2* pairs;
     const int32_t* order;    // nullptr: entries are row indices already
     long long n;             // count, or the capacity when n_dev is given
@@ -22,6 +26,7 @@ struct SrcPairs {            // pair list of the selection path: sorted position
 };
 
 struct SrcSelf {             // rows g0..g0+n-1 against themselves: per-genome histograms (max(a,a) = a)
+    static constexpr uint32_t kMask = 0xffffffffu;
     long long g0, n;
     const uint32_t* max_seen;   // written by k_max_byte earlier on the stream: a register above
     uint32_t max_ok;            // 64-p+1 would index past the histogram, so nothing is processed
@@ -55,6 +60,11 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src s
     const long long nw = (long long)gridDim.x * 2;
     const long long npairs = src.count();
     uint32_t prev0 = 0, prev1 = 0;
+    auto ld = [](const uint4* q) {
+        uint4 v = __ldg(q);
+        if (Src::kMask != 0xffffffffu) { v.x &= Src::kMask; v.y &= Src::kMask; v.z &= Src::kMask; v.w &= Src::kMask; }
+        return v;
+    };
     for (long long pi = (long long)blockIdx.x * 2 + w; pi < npairs; pi += nw) {
         uint2 id;
         const uint2 rw = src.rows(pi, id);
@@ -62,18 +72,18 @@ k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src s
         const uint4* b = reinterpret_cast<const uint4*>(regs + (size_t)rw.y * row_stride) + lane;
         if (ngroups) {
             // two chunks being histogrammed while the next two are in flight (no register rotation)
-            uint4 ax0 = __ldg(a), ay0 = __ldg(b), ax1 = __ldg(a + 32), ay1 = __ldg(b + 32);
+            uint4 ax0 = ld(a), ay0 = ld(b), ax1 = ld(a + 32), ay1 = ld(b + 32);
             for (int g = 0; g < ngroups; ++g) {
-                const uint4 bx0 = __ldg(a + 64), by0 = __ldg(b + 64), bx1 = __ldg(a + 96), by1 = __ldg(b + 96);
+                const uint4 bx0 = ld(a + 64), by0 = ld(b + 64), bx1 = ld(a + 96), by1 = ld(b + 96);
                 hist_inc_max16(ax0, ay0, bias, tb);
                 hist_inc_max16(ax1, ay1, bias, tb);
                 a += 128; b += 128;
-                if (g + 1 < ngroups) { ax0 = __ldg(a); ay0 = __ldg(b); ax1 = __ldg(a + 32); ay1 = __ldg(b + 32); }
+                if (g + 1 < ngroups) { ax0 = ld(a); ay0 = ld(b); ax1 = ld(a + 32); ay1 = ld(b + 32); }
                 hist_inc_max16(bx0, by0, bias, tb);
                 hist_inc_max16(bx1, by1, bias, tb);
             }
         }
-        for (int c = ngroups * 4; c < nchunk; ++c, a += 32, b += 32) hist_inc_max16(__ldg(a), __ldg(b), bias, tb);
+        for (int c = ngroups * 4; c < nchunk; ++c, a += 32, b += 32) hist_inc_max16(ld(a), ld(b), bias, tb);
         __syncwarp();
         // transposed, conflict-free column sums: lane L totals bins L and L+32.  Counters are
         // never cleared: they run cumulatively (mod 2^32) and the pair's histogram is the

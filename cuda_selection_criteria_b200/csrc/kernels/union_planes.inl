@@ -485,6 +485,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
 
 // the wide list as a pair source for the byte kernel (histogram row = the pair's own slot)
 struct SrcWide {
+    static constexpr uint32_t kMask = 0xffffffffu;
     const uint2* pairs;
     const int32_t* order;
     const uint32_t* wide_list;

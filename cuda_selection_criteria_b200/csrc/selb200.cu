@@ -182,6 +182,7 @@ struct selb200_ctx {
     DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
     int64_t out_count = 0, near_count = 0;
     int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
+    int64_t near_cap = 1 << 16;                   // near-tau list: grown (and the pass redone) when a run overflows it
     LoadState ld;
     StageSlot slots[3];
     int next_slot = 0;
@@ -272,7 +273,7 @@ int launch_pair_hist_t(cudaStream_t stream, int sm_count, const uint8_t* regs, s
                        int64_t max_pairs, Src src, Epi epi) {
     if (max_pairs <= 0) return SELB200_OK;
     const int64_t ctas_needed = (max_pairs + 1) / 2;
-    const int nbins = 64 - p + 2;
+    const int nbins = Src::kMask != 0xffffffffu ? 64 : 64 - p + 2;   // masked (unvalidated) bytes can take any 6-bit value
     if (nbins <= 52) {
         static const int per_sm = resident_ctas(k_pair_hist<52, Src, Epi>, 64);
         const int grid = (int)std::min<int64_t>(ctas_needed, (int64_t)sm_count * per_sm);
@@ -899,9 +900,6 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
-    CKR(c->near_keys.ensure((size_t)(1 << 16) * 8));
-    CKR(c->near_j.ensure((size_t)(1 << 16) * 8));
-    const unsigned long long near_cap = 1ull << 16;
     const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
     size_t hll_smem = 0;
     int hll_grid = 0;
@@ -978,10 +976,10 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     }
     auto launch_push = [&](int check, unsigned long long pair_lim) -> int {
         k_gather_claim<<<1, 32, 0, s>>>(gz, c->g.epoch, d_cnt, check, (unsigned long long)PAIR_CAP, pair_lim,
-                                        (unsigned long long)c->out_cap, (unsigned long long)c->tile_cap, near_cap,
-                                        c->g_push.as<GatherPush>());
+                                        (unsigned long long)c->out_cap, (unsigned long long)c->tile_cap,
+                                        (unsigned long long)c->near_cap, c->g_push.as<GatherPush>());
         CK(cudaGetLastError());
-        k_gather_copy<<<32, 256, 0, s>>>(gz, c->g.epoch, d_cnt, near_cap, c->out_keys.as<uint64_t>(),
+        k_gather_copy<<<32, 256, 0, s>>>(gz, c->g.epoch, d_cnt, (unsigned long long)c->near_cap, c->out_keys.as<uint64_t>(),
                                          c->out_j.as<double>(), c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
                                          c->g_push.as<GatherPush>());
         CK(cudaGetLastError());
@@ -999,6 +997,9 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         CKR(c->hist.ensure((size_t)c->hist_cap_pairs * 64 * sizeof(uint32_t)));
         CKR(c->out_keys.ensure((size_t)c->out_cap * 8));
         CKR(c->out_j.ensure((size_t)c->out_cap * 8));
+        CKR(c->near_keys.ensure((size_t)c->near_cap * 8));
+        CKR(c->near_j.ensure((size_t)c->near_cap * 8));
+        const unsigned long long near_cap = (unsigned long long)c->near_cap;
         st.launches = launches_fixed;
         k_tile_table<<<(nrb + 3) / 4, 128, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
                                                    (long long)c->tile_cap, c->tile_rc.as<int2>(), d_cnt);
@@ -1183,6 +1184,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             pair_sum += (int64_t)sn[1];
         }
         if ((int64_t)h_fin[M_OUT] > c->out_cap) { c->out_cap = (int64_t)h_fin[M_OUT] + (1 << 16); redo = true; }
+        // the near-tau list is part of the result (north_star: "listed separately"): never truncated, grown like the others
+        if ((int64_t)h_fin[M_NEAR] > c->near_cap) { c->near_cap = (int64_t)h_fin[M_NEAR] + (1 << 12); redo = true; }
         if (!redo) {
             st.pairs_cand = cand_sum;
             st.pairs_aux = pair_sum;
@@ -1196,7 +1199,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     st.tiles_total = tiles_total;
     st.tiles_shard = shard_tiles(tiles_total);
     c->out_count = (int64_t)h_fin[M_OUT];
-    c->near_count = (int64_t)std::min<unsigned long long>(h_fin[M_NEAR], near_cap);
+    c->near_count = (int64_t)h_fin[M_NEAR];
     st.pairs_out = c->out_count;
     st.pairs_near = (int64_t)h_fin[M_NEAR];
 
@@ -1223,8 +1226,11 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             if ((int64_t)c->g.h_merged[0] > c->g.cap)
                 return fail(SELB200_ENOMEM, "gather: %llu pairs exceed the landing zone of %lld (selb200_gather_create)",
                             c->g.h_merged[0], (long long)c->g.cap);
+            if (c->g.h_merged[1] > gz.near_cap)
+                return fail(SELB200_ENOMEM, "gather: %llu near-tau pairs exceed the landing zone's %llu (selb200_gather_create)",
+                            c->g.h_merged[1], gz.near_cap);
             c->out_count = (int64_t)c->g.h_merged[0];
-            c->near_count = (int64_t)std::min<unsigned long long>(c->g.h_merged[1], gz.near_cap);
+            c->near_count = (int64_t)c->g.h_merged[1];
             src_keys = gz.keys + b * gz.cap;
             src_j = gz.jac + b * gz.cap;
             // the merged near-tau list moves to the context's own buffers (the zone is handed back below)

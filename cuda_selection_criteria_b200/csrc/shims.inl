@@ -44,6 +44,10 @@ __global__ void k_shim_smh_compact(const uint64_t* __restrict__ aux, const int2*
 }
 
 struct SrcShim {             // survivors -> caller's int2 pair list (row indices)
+    // caller-owned, unvalidated register bytes: six bits are kept and the histogram has all 64 bins, so no byte can
+    // address shared memory outside the counters (the reference kernel feeds any byte to ldexp; a byte above 63 is
+    // not an HLL register of any precision, and for those inputs the shim's estimate differs from the reference's)
+    static constexpr uint32_t kMask = 0x3f3f3f3fu;
     const int2* pairs;
     const uint32_t* surv;
     const unsigned long long* surv_count;
@@ -73,7 +77,9 @@ struct EpiFlajolet {         // criteria_sketch_cuda.cuh:30-65 + selection_kerne
         const double alpha = 0.7213 / (1 + 1.079 / m);
         double raw = alpha * m * m / (zeros + sum);
         if (raw < 2.5 * m && zeros) raw = m * log(double(m) / zeros);
-        else if (raw > (1ULL << 32) / 30.0) raw = -(double)(1ULL << 32) * log1p(-raw / (1ULL << 32));
+        // criteria_sketch_cuda.cuh:61-63 negates the UNSIGNED 1ULL<<32 (= 2^64 - 2^32) before the conversion to double:
+        // the "corrected" estimate comes out negative and the pair is dropped below — reproduced, not repaired
+        else if (raw > (1ULL << 32) / 30.0) raw = (double)(-(1ULL << 32)) * log1p(-raw / (1ULL << 32));
         if (raw == 0.0) return;
         if (!isfinite(raw) || raw < 0.0) return;
         double jac = (cards[id.x] + cards[id.y] - raw) / raw;

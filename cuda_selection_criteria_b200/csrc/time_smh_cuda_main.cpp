@@ -10,6 +10,14 @@
 //   smh_a     : selection without the cardinality bound (experiments/src/time_smh.cpp:229-257)
 //   CB+smh_a  : selection with it (time_smh.cpp:261-292)
 // Band shape: the drivers' search that keeps (1,1) when nothing qualifies (time_smh_cuda.cpp:231-240).
+//
+// Built twice (csrc/Makefile): bin/time_smh_cuda, and with -DSELB_TIME_SMH bin/time_smh — the flag set and line
+// format of the reference's CPU harness (experiments/src/time_smh.cpp:139 "xl:t:h:m:R:", ";m:M" / ";r:R_b:B"
+// suffixes, -R repetitions of the two compare phases, :226-292) over the same GPU path, so run_time_experiment.sh's
+// CPU leg has a binary too.  The reference prints each time AFTER the next label (TIMERSTOP has no newline,
+// include/metrictime2.hpp:14-18); here every line carries its own seconds in field 4, which is what the script's
+// awk reads.  Both builds also report, on stderr, the CUDA-event time of each compare phase
+// (`selb200: device ms: ...`): the printed wall-clock seconds bracket a synchronised run and must not be below it.
 #include <getopt.h>
 #include <omp.h>
 #include <zlib.h>
@@ -117,18 +125,25 @@ double seconds_since(std::chrono::high_resolution_clock::time_point t0) {
 
 int main(int argc, char* argv[]) {
     std::string list_file;
-    const unsigned threads = 8;           // time_smh_cuda.cpp:145
+    unsigned threads = 8;                 // time_smh_cuda.cpp:145 (fixed there; -t in time_smh.cpp:149)
     float threshold = 0.9f;
-    int mh_size = 8, block_size = 256;
+    int mh_size = 8, block_size = 256, total_rep = 1;
     (void)block_size;
     int c;
-    while ((c = getopt(argc, argv, "xl:h:m:b:")) != -1) {
+#ifdef SELB_TIME_SMH
+    const char* optstring = "xl:t:h:m:R:";      // experiments/src/time_smh.cpp:139
+#else
+    const char* optstring = "xl:h:m:b:";        // experiments/src/time_smh_cuda.cpp:154
+#endif
+    while ((c = getopt(argc, argv, optstring)) != -1) {
         switch (c) {
             case 'x': std::cout << "Usage: -l -t -h -m\n"; return 0;
             case 'l': list_file = optarg; break;
             case 'h': threshold = std::stof(optarg); break;
             case 'm': mh_size = std::stoi(optarg); break;
             case 'b': block_size = std::stoi(optarg); break;
+            case 't': threads = (unsigned)std::stoi(optarg); break;
+            case 'R': total_rep = std::stoi(optarg); break;
             default: break;
         }
     }
@@ -178,7 +193,11 @@ int main(int argc, char* argv[]) {
     if (selb200_create(0, nullptr, &ctx) != SELB200_OK) die("create", selb200_last_error());
     if (selb200_load_host(ctx, n, p, regs.data(), stored.data(), SELB200_AUX_SMH, mh_size, smh.data()) != SELB200_OK)
         die("load", selb200_last_error());
+#ifdef SELB_TIME_SMH
+    std::cout << list_file << ";build_smh;" << threshold << ";" << seconds_since(t0) << ";m:" << mh_size << std::endl;
+#else
     std::cout << list_file << ";build_smh;" << threshold << ";" << seconds_since(t0) << std::endl;
+#endif
 
     selb200_params prm;
     selb200_default_params(&prm);
@@ -186,16 +205,28 @@ int main(int argc, char* argv[]) {
     prm.criterion = SELB200_CRIT_SMH_A;
     selb200_band_params(mh_size, threshold, 0, &prm.n_bands, &prm.n_rows);
     selb200_stats st;
-    // ---- smh_a (no cardinality bound) and CB+smh_a; selb200_run returns after the device finished ----
-    prm.no_cb = 1;
-    t0 = std::chrono::high_resolution_clock::now();
-    if (selb200_run(ctx, &prm, &st) != SELB200_OK) die("run", selb200_last_error());
-    std::cout << list_file << ";smh_a;" << threshold << ";" << seconds_since(t0) << std::endl;
-    const long long out_smh = (long long)st.pairs_out;
-    prm.no_cb = 0;
-    t0 = std::chrono::high_resolution_clock::now();
-    if (selb200_run(ctx, &prm, &st) != SELB200_OK) die("run", selb200_last_error());
-    std::cout << list_file << ";CB+smh_a;" << threshold << ";" << seconds_since(t0) << std::endl;
+    long long out_smh = 0;
+    for (int rep = 0; rep < total_rep; ++rep) {
+        // ---- smh_a (no cardinality bound) and CB+smh_a; selb200_run returns after the device finished ----
+        const char* label[2] = {"smh_a", "CB+smh_a"};
+        float dev_ms[2] = {0.f, 0.f};
+        double secs[2] = {0., 0.};
+        for (int phase = 0; phase < 2; ++phase) {
+            prm.no_cb = phase == 0;
+            t0 = std::chrono::high_resolution_clock::now();
+            if (selb200_run(ctx, &prm, &st) != SELB200_OK) die("run", selb200_last_error());
+            secs[phase] = seconds_since(t0);
+            dev_ms[phase] = st.ms_total;
+            std::cout << list_file << ";" << label[phase] << ";" << threshold << ";" << secs[phase];
+#ifdef SELB_TIME_SMH
+            std::cout << ";r:" << prm.n_rows << "_b:" << prm.n_bands;
+#endif
+            std::cout << std::endl;
+            if (phase == 0) out_smh = (long long)st.pairs_out;
+        }
+        fprintf(stderr, "selb200: device ms: smh_a %.4f, CB+smh_a %.4f | wall ms: %.4f, %.4f\n", dev_ms[0], dev_ms[1],
+                secs[0] * 1e3, secs[1] * 1e3);
+    }
     fprintf(stderr, "selb200: n=%lld bands x rows %dx%d | pairs out: smh_a %lld, CB+smh_a %lld\n", (long long)n,
             prm.n_bands, prm.n_rows, out_smh, (long long)st.pairs_out);
     selb200_destroy(ctx);

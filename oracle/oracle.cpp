@@ -225,6 +225,18 @@ extern "C" {
 
 void oracle_set_no_cb(int v) { g_no_cb = v; }
 
+// Tolerance report of the parity check (BASELINE.json north_star: "pairs within 1e-6 of tau are listed separately"):
+// every EVALUATED pair (CB and the auxiliary criterion passed, union estimated) whose Jaccard lies within 1e-6*|tau| of
+// tau, emitted or not, collected by the next oracle_select in (i,k) order.  Not a reference feature: the reference
+// has one arithmetic; the list names the pairs whose tau decision a 1e-6 relative error could flip.
+static std::vector<std::pair<std::pair<int32_t, int32_t>, double>> g_near;
+static int g_want_near = 0;
+void oracle_want_near(int v) { g_want_near = v; g_near.clear(); }
+int64_t oracle_near_count(void) { return (int64_t)g_near.size(); }
+void oracle_near_copy(int32_t* i, int32_t* k, double* j) {
+    for (size_t t = 0; t < g_near.size(); ++t) { i[t] = g_near[t].first.first; k[t] = g_near[t].first.second; j[t] = g_near[t].second; }
+}
+
 enum { ORACLE_CRIT_CB = 0, ORACLE_CRIT_SMH_A = 1, ORACLE_CRIT_HLL_A = 2, ORACLE_CRIT_HLL_AN = 3 };
 
 void oracle_hist64(const uint8_t* regs, uint64_t m, uint32_t* counts) { hist64(regs, m, counts); }
@@ -356,6 +368,10 @@ int64_t oracle_select(int n, int p, const uint8_t* regs, const double* stored, i
             ++s_aux;
             const double t = oracle_union_size(ra, rb, p);         // :286
             const double jac = ((double)e1 + (double)e2 - t) / t;  // :287
+            if (g_want_near && std::fabs(jac - tau) <= 1e-6 * std::fabs(tau)) {
+#pragma omp critical(oracle_near)
+                g_near.push_back({{i, k}, jac});
+            }
             if (jac >= tau) {                                      // :288
                 rk[(size_t)i].push_back(k);
                 rj[(size_t)i].push_back(jac);
@@ -363,6 +379,7 @@ int64_t oracle_select(int n, int p, const uint8_t* regs, const double* stored, i
             }
         }
     }
+    std::sort(g_near.begin(), g_near.end());
     int64_t w = 0;
     for (int i = 0; i < n; ++i)
         for (size_t t = 0; t < rk[(size_t)i].size(); ++t, ++w)

@@ -70,7 +70,7 @@ int main() {
             std::vector<std::pair<uint64_t, double>> want, want_near;
             for (unsigned r = 0; r < world; ++r) {
                 Rank& R = ranks[r];
-                const size_t cnt = (epoch == 3 && r == 1) ? 0 : 1 + rng() % 5000, ncnt = rng() % 100;     // one empty list too
+                const size_t cnt = (epoch == 3 && r == 1) ? 0 : 1 + rng() % 5000, ncnt = rng() % 65;      // one empty list too; a near list never exceeds its capacity (the host grows it and redoes the pass)
                 R.keys.resize(cnt + 1); R.jac.resize(cnt + 1); R.near_keys.resize(ncnt + 1); R.near_j.resize(ncnt + 1);
                 for (size_t i = 0; i < cnt; ++i) { R.keys[i] = ((uint64_t)epoch << 56) | ((uint64_t)r << 48) | i; R.jac[i] = (double)(rng() % 1000) / 1000.0; want.push_back({R.keys[i], R.jac[i]}); }
                 for (size_t i = 0; i < ncnt; ++i) { R.near_keys[i] = ((uint64_t)0xEE << 56) | ((uint64_t)r << 48) | i; R.near_j[i] = 0.9; if (i < near_cap_local) want_near.push_back({R.near_keys[i], R.near_j[i]}); }
@@ -116,7 +116,11 @@ int main() {
         unsigned long long merged[3] = {7, 7, 7};
         emul::launch(1, 32, [&] { k_gather_wait(zone.z, 0, 1, &R.push, merged); });
         CHECK(R.push.go == 0 && R.meta[M_PUSHED] == 0 && zone.z.hdr->count[0] == 0 && zone.z.hdr->done[0] == 0 && merged[2] == 2, "overflowed pass was pushed");
-        R.meta[M_CAND] = 0;                                  // the redone pass pushes without the check
+        R.meta[M_CAND] = 0;
+        R.meta[M_NEAR] = near_cap_local + 1;                 // so did the near-tau list: same rule
+        push(R, zone.z, 0, 1, near_cap_local, 2);
+        CHECK(R.push.go == 0 && R.meta[M_PUSHED] == 0 && zone.z.hdr->count[0] == 0, "pass with an overflowed near list was pushed");
+        R.meta[M_NEAR] = 0;                                  // the redone pass pushes without the check
         push(R, zone.z, 0, 0, near_cap_local, 2);
         emul::launch(1, 32, [&] { k_gather_wait(zone.z, 0, 1, &R.push, merged); });
         CHECK(R.meta[M_PUSHED] == 1 && merged[0] == 5 && merged[2] == 0, "redone pass");

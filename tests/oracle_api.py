@@ -39,6 +39,8 @@ def lib():
                                     C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+        L.oracle_near_count.restype = C.c_int64
+        L.oracle_near_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_smh_size.restype = C.c_int
         L.oracle_smh_size.argtypes = [C.c_int]
         _LIB = L
@@ -63,7 +65,8 @@ def union_size(a: np.ndarray, b: np.ndarray, p: int) -> float:
 
 def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, order_n=1, n_rows=0, n_bands=0,
            threads=0, no_cb=False):
-    """-> dict(i, k, jaccard, order, cards_sorted, stage=[P, P_cb, P_aux, P_out])."""
+    """-> dict(i, k, jaccard, order, cards_sorted, stage=[P, P_cb, P_aux, P_out], near_i, near_k, near_jaccard);
+    near_* = every evaluated pair with |J - tau| <= 1e-6*|tau| (emitted or not), in (i,k) order."""
     regs = np.ascontiguousarray(regs, np.uint8)
     n = regs.shape[0]
     crit = CRIT[criterion]
@@ -82,6 +85,7 @@ def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, or
     lib().oracle_set_no_cb(int(no_cb))
     cap = 1 << 16
     while True:
+        lib().oracle_want_near(1)
         oi = np.empty(cap, np.int32); ok = np.empty(cap, np.int32); oj = np.empty(cap, np.float64)
         cnt = lib().oracle_select(n, p, regs.ctypes.data, st.ctypes.data if st is not None else None, crit, aux_len,
                                   a.ctypes.data if a is not None else None, C.c_float(tau), C.c_float(z), order_n,
@@ -91,8 +95,13 @@ def select(regs, p, criterion, tau, aux=None, aux_len=0, stored=None, z=1.96, or
             break
         cap = int(cnt)
     lib().oracle_set_no_cb(0)
+    nn = lib().oracle_near_count()
+    ni = np.empty(nn, np.int32); nk = np.empty(nn, np.int32); nj = np.empty(nn, np.float64)
+    if nn:
+        lib().oracle_near_copy(ni.ctypes.data, nk.ctypes.data, nj.ctypes.data)
+    lib().oracle_want_near(0)
     return dict(i=oi[:cnt].copy(), k=ok[:cnt].copy(), jaccard=oj[:cnt].copy(), order=order, cards_sorted=cards,
-                stage=stage.tolist(), n_rows=n_rows, n_bands=n_bands)
+                stage=stage.tolist(), n_rows=n_rows, n_bands=n_bands, near_i=ni, near_k=nk, near_jaccard=nj)
 
 
 def format_lines(names, res):

@@ -59,13 +59,13 @@ def test_line_diff_reports_missing_extra_and_printed_error():
 def test_oracle_diff_excludes_only_near_tau_pairs():
     ora = {"i": np.array([0, 0, 2], np.int32), "k": np.array([1, 3, 3], np.int32),
            "jaccard": np.array([0.95, 0.9000000001, 0.97]), "stage": [6, 5, 4, 3],
-           "cards_sorted": np.array([10.5, 11.5, 12.5, 13.5])}
+           "cards_sorted": np.array([10.5, 11.5, 12.5, 13.5]), "near_i": np.array([0], np.int32), "near_k": np.array([3], np.int32)}
     res = types.SimpleNamespace(i=np.array([0, 2], np.int32), k=np.array([1, 3], np.int32), jaccard=np.array([0.95, 0.97 * (1 + 5e-7)]),
                                 near_i=np.array([0], np.int32), near_k=np.array([3], np.int32), near_jaccard=np.array([0.8999999999]),
                                 stats={"pairs_cb": 5, "pairs_aux": 4, "pairs_out": 2}, cards_sorted=np.array([10.1, 11.9, 12.0, 13.99]))
     d = bench.diff_oracle(res, ora, 0.9)
     assert d["pairs_missing"] == 0 and d["pairs_extra"] == 0          # (0,3) sits within 1e-6 of tau: listed, not counted
-    assert d["near_tau_count"] == 1 and d["near_tau"][0][:2] == [0, 3]
+    assert d["near_tau_count"] == 1 and d["near_tau"][0][:2] == [0, 3] and d["near_tau_equal_oracle"]
     assert 4e-7 < d["max_rel_jaccard"] < 6e-7 and bench.parity_ok(d)
     res.i = np.array([0], np.int32); res.k = np.array([1], np.int32); res.jaccard = np.array([0.95])
     d = bench.diff_oracle(res, ora, 0.9)

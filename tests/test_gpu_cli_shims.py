@@ -100,8 +100,13 @@ def test_shims_match_reference_launchers(gpu, sym, tau):
     ours = C.CDLL(S.lib_path())
     n, m_aux = 500, 128
     plan = synth.make_plan(n, 77)
-    regs = synth.hll(plan, 14)
-    aux = synth.smh(plan, m_aux)
+    regs = synth.hll(plan, 14).copy()
+    aux = synth.smh(plan, m_aux).copy()
+    # four near-saturated sketches with equal auxiliary buckets: their union estimate exceeds 2^32/30, the branch where
+    # criteria_sketch_cuda.cuh:61-63 negates an unsigned constant (the estimate goes negative, the pair is dropped)
+    rng = np.random.default_rng(3)
+    regs[10:14] = rng.integers(15, 19, size=(4, 1 << 14), dtype=np.uint8)
+    aux[10:14] = aux[10]
     ora = O.select(regs, 14, "cb", np.float32(2.0))                     # cardinalities + order only
     order = ora["order"]
     dev = torch.device("cuda", gpu)
@@ -131,8 +136,22 @@ def test_shims_match_reference_launchers(gpu, sym, tau):
     assert np.array_equal(res["ref"][1], res["ours"][1])
 
 
+def _device_ms(stderr):
+    """(device ms, wall ms) of the two compare phases from the harness's `selb200: device ms: ...` lines."""
+    out = []
+    for ln in stderr.splitlines():
+        if ln.startswith("selb200: device ms:"):
+            dev, wall = ln.split("|")
+            d = [float(x.split()[-1]) for x in dev.split(":")[2].split(",")]
+            w = [float(x) for x in wall.split(":")[1].split(",")]
+            out.append((d, w))
+    return out
+
+
 def test_cli_time_smh_cuda(gpu):
-    """Three `list;phase;tau;seconds` lines like experiments/src/time_smh_cuda.cpp:228-230,279-299."""
+    """Three `list;phase;tau;seconds` lines like experiments/src/time_smh_cuda.cpp:228-230,279-299, and — unlike the
+    reference, whose timers bracket an unsynchronised launch — seconds that cover the device work: each compare
+    phase's printed time is at least the CUDA-event time of its run and at most a host overhead above it."""
     r = subprocess.run([os.path.join(BIN, "time_smh_cuda"), "-l", "test_influeza_filelist.txt", "-h", "0.9", "-m", "64",
                         "-b", "128"], cwd=GOLD, capture_output=True, text=True, check=True)
     lines = r.stdout.splitlines()
@@ -141,3 +160,73 @@ def test_cli_time_smh_cuda(gpu):
     assert all(float(ln.split(";")[3]) > 0 for ln in lines)
     # SMH rebuilt from the FASTA files (M = 64) gives the 7 pairs of results.txt in both modes
     assert "smh_a 7, CB+smh_a 7" in r.stderr
+    (dev, wall), = _device_ms(r.stderr)
+    for ph in range(2):
+        printed_ms = float(lines[1 + ph].split(";")[3]) * 1e3
+        assert dev[ph] > 0 and abs(printed_ms - wall[ph]) < 0.01 * max(printed_ms, 1e-3) + 1e-3
+        assert dev[ph] <= printed_ms <= dev[ph] + 50.0
+
+
+def test_cli_time_smh_cpu_flag_set(gpu):
+    """bin/time_smh: the flags and line suffixes of the reference's CPU harness (experiments/src/time_smh.cpp:139,
+    197,257,292: -t, -R repetitions, ';m:M', ';r:R_b:B') over the same GPU path."""
+    r = subprocess.run([os.path.join(BIN, "time_smh"), "-l", "test_influeza_filelist.txt", "-t", "4", "-h", "0.9", "-m", "64",
+                        "-R", "2"], cwd=GOLD, capture_output=True, text=True, check=True)
+    lines = r.stdout.splitlines()
+    assert [ln.split(";")[1] for ln in lines] == ["build_smh", "smh_a", "CB+smh_a", "smh_a", "CB+smh_a"]
+    assert lines[0].split(";")[4] == "m:64"
+    nb, nr = O.band_params(64, np.float32(0.9), False)
+    assert all(ln.split(";")[4] == f"r:{nr}_b:{nb}" for ln in lines[1:])
+    assert all(float(ln.split(";")[3]) > 0 for ln in lines)
+    assert len(_device_ms(r.stderr)) == 2 and "smh_a 7, CB+smh_a 7" in r.stderr
+
+
+def test_time_experiment_script(gpu, tmp_path):
+    """tools/run_time_experiment.sh (the sweep of the reference's run_time_experiment.sh:17-42) over both harnesses:
+    the CSV the reference's analysis expects, one row per (impl, phase, repetition), every time a positive number."""
+    log = tmp_path / "times.csv"
+    env = dict(os.environ, LISTA="test_influeza_filelist.txt", MH_SIZE_ARR="64", REPS="2", LOG=str(log))
+    subprocess.run(["bash", os.path.join(ROOT, "tools", "run_time_experiment.sh")], cwd=GOLD, env=env, check=True,
+                   capture_output=True, text=True)
+    rows = log.read_text().splitlines()
+    assert rows[0] == "impl,threads,mh_size,rep,criterio,tiempo"
+    body = [r.split(",") for r in rows[1:]]
+    assert sorted((b[0], b[4]) for b in body) == sorted((i, c) for i in ("cpu", "gpu") for c in ("build_smh", "smh_a", "CB+smh_a")
+                                                        for _ in range(2))
+    assert all(b[2] == "64" and float(b[5]) > 0 for b in body)
+    assert {b[1] for b in body if b[0] == "cpu"} == {"8"} and {b[1] for b in body if b[0] == "gpu"} == {"256"}
+
+
+def _write_synthetic_files(tmp_path, n, seed, m_smh):
+    plan = synth.make_plan(n, seed)
+    regs, aux = synth.hll(plan, 14), synth.smh(plan, m_smh)
+    names = [f"s{i:04d}.fna.gz" for i in range(n)]
+    for i, nm in enumerate(names):
+        sketch_io.write_hll(str(tmp_path / nm) + ".hll", regs[i], 14, level=1)
+        sketch_io.write_smh(str(tmp_path / nm) + f".smh{m_smh}", aux[i], level=1)
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    return regs, aux, names
+
+
+@pytest.mark.parametrize("tau", ["0.9", "0.75"])
+def test_comparison_experiment_script_joins_cpu_and_gpu_output(gpu, tmp_path, tau):
+    """tools/run_comparison_experiment.sh = the join / diff of the reference's run_comparison_experiment.sh:36-52
+    (key nameA_nameB, |sim_cpu - sim_gpu| with EPS 1e-6).  CPU side: the UNMODIFIED reference binary when it was
+    built (oracle/_ref/selection), else this repo's bin/selection; GPU side: bin/selection_cuda.  Every pair of the
+    CPU side must be joined, none may exist on one side only, and no similarity may differ by more than the
+    float the CUDA driver prints (src/selection_cuda.cpp:184-186: 6 significant digits)."""
+    regs, aux, names = _write_synthetic_files(tmp_path, 500, 31, 128)
+    out = tmp_path / "cmp.csv"
+    cpu = O.ref_binary() or os.path.join(BIN, "selection")
+    env = dict(os.environ, LISTA="list.txt", THRESHOLD=tau, MH_SIZE_ARR="1024", THREADS="4", CPU_BINARY=cpu, OUT=str(out))
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "run_comparison_experiment.sh")], cwd=tmp_path, env=env,
+                       check=True, capture_output=True, text=True)
+    assert "only on the CPU side: 0, only on the GPU side: 0" in r.stderr
+    rows = out.read_text().splitlines()
+    assert rows[0] == "cfg,card1,card2,sim_cpu,sim_gpu,diff"
+    ora = O.select(regs, 14, "smh_a", np.float32(float(tau)), aux=aux, threads=8)
+    assert len(rows) - 1 == len(ora["i"]) > 100
+    want = {tuple(ln.split()[:2]) for ln in O.format_lines(names, ora)}
+    assert {tuple(r_.split(",")[1:3]) for r_ in rows[1:]} == want
+    assert all(r_.split(",")[0] == "t4_b128_m1024_r1" for r_ in rows[1:])
+    assert max(float(r_.split(",")[5]) for r_ in rows[1:]) <= 1.0000001e-6

@@ -29,24 +29,31 @@ def run_gpu(regs, aux, criterion, tau, device=0, **kw):
 
 
 def compare(res, ora, tau):
-    """Pair set bit-exact, same order, Jaccard within REL_TOL; stage counts identical."""
-    near = set(zip(res.near_i.tolist(), res.near_k.tolist()))
-    got = list(zip(res.i.tolist(), res.k.tolist()))
-    want = list(zip(ora["i"].tolist(), ora["k"].tolist()))
-    if near:   # pairs within 1e-6 of tau are reported separately and excluded from the exact check
-        got = [x for x in got if x not in near]
-        want = [x for x in want if x not in near]
-    assert got == want
+    """Pair set bit-exact, same order, Jaccard within REL_TOL; stage counts identical.  Pairs within 1e-6 of tau
+    (north_star: "listed separately") must be the ORACLE's near-tau pairs; only their tau decision is exempt from
+    the exact check — every other pair, every Jaccard value and every stage count is still held to it."""
+    near = list(zip(res.near_i.tolist(), res.near_k.tolist()))
+    assert sorted(near) == list(zip(ora["near_i"].tolist(), ora["near_k"].tolist()))
+    assert len(near) == res.stats["pairs_near"]
+    near = set(near)
+    got = dict(zip(zip(res.i.tolist(), res.k.tolist()), res.jaccard.tolist()))
+    want = dict(zip(zip(ora["i"].tolist(), ora["k"].tolist()), ora["jaccard"].tolist()))
+    assert [x for x in got if x not in near] == [x for x in want if x not in near]        # dicts keep list order
     assert np.array_equal(res.order, ora["order"])
     assert np.array_equal(res.cards_sorted.astype(np.uint64), ora["cards_sorted"].astype(np.uint64))
-    if not near:
-        rel = np.abs(res.jaccard - ora["jaccard"]) / np.maximum(np.abs(ora["jaccard"]), 1e-300)
-        assert rel.size == 0 or rel.max() <= REL_TOL
+    for pr, j in got.items():
+        if pr in want:
+            assert abs(j - want[pr]) <= REL_TOL * abs(want[pr])
+    nj = dict(zip(zip(ora["near_i"].tolist(), ora["near_k"].tolist()), ora["near_jaccard"].tolist()))
+    for pr, j in zip(zip(res.near_i.tolist(), res.near_k.tolist()), res.near_jaccard.tolist()):
+        assert abs(j - nj[pr]) <= REL_TOL * abs(nj[pr])
     st = res.stats
     assert st["pairs_total"] == ora["stage"][0]
     assert st["pairs_cb"] == ora["stage"][1]           # CB decisions bit-exact
+    assert st["pairs_aux"] == ora["stage"][2]          # aux-criterion decisions bit-exact
+    flipped = sum((pr in got) != (pr in want) for pr in near)
+    assert abs(st["pairs_out"] - ora["stage"][3]) <= flipped
     if not near:
-        assert st["pairs_aux"] == ora["stage"][2]      # aux-criterion decisions bit-exact
         assert st["pairs_out"] == ora["stage"][3]
 
 
@@ -362,3 +369,90 @@ def test_auxiliary_hll_precisions(gpu, criterion, p_aux):
     ora = O.select(regs, 14, criterion, np.float32(tau), aux=aux, threads=8)
     assert ora["stage"][2] > 0
     compare(res, ora, tau)
+
+
+@pytest.mark.parametrize("criterion", ["cb", "smh_a"])
+def test_pairs_within_1e6_of_tau_are_listed_separately(gpu, criterion):
+    """tau chosen as the float nearest to the Jaccard of an actual pair puts that pair within 6e-8 (relative) of tau,
+    below it or above it depending on the rounding: once on each side, plus a tau with several near pairs.  The near
+    list must be the oracle's, an emitted near pair appears in both lists, and everything else stays exact."""
+    plan = synth.make_plan(900, 4242)
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128) if criterion == "smh_a" else None
+    base = O.select(regs, 14, criterion, np.float32(0.80), aux=aux, threads=8)
+    js = base["jaccard"][(base["jaccard"] > 0.86) & (base["jaccard"] < 0.97)]
+    assert js.size > 50
+    above = [j for j in js if float(np.float32(j)) > j][:2]        # tau just above J: evaluated, near, NOT emitted
+    below = [j for j in js if float(np.float32(j)) < j][:2]        # tau just below J: near AND emitted
+    assert above and below
+    sides = set()
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, aux_kind_of(criterion))
+        for j in above + below:
+            tau = np.float32(j)
+            ora = O.select(regs, 14, criterion, tau, aux=aux, threads=8)
+            assert ora["near_i"].size >= 1
+            res = sel.run(tau=tau, criterion=criterion)
+            compare(res, ora, tau)
+            emitted = set(zip(res.i.tolist(), res.k.tolist()))
+            for pr, jn in zip(zip(res.near_i.tolist(), res.near_k.tolist()), res.near_jaccard.tolist()):
+                assert (pr in emitted) == (jn >= float(tau))
+                sides.add(jn >= float(tau))
+    assert sides == {True, False}
+
+
+def test_near_tau_list_grows_instead_of_truncating(gpu):
+    """400 identical sketches at tau = 1: every pair has J = (2e - t)/t with e = trunc(t), i.e. 1 - 2 frac(t)/t — within
+    1e-6 of tau and below it.  79 800 near pairs exceed the list's initial 65 536 entries: the run must grow the list
+    and return all of them (it used to cut the list silently)."""
+    plan = synth.make_plan(3, 5)
+    one = synth.hll(plan, 14)[:1]
+    regs = np.repeat(one, 400, axis=0)
+    ora = O.select(regs, 14, "cb", np.float32(1.0), threads=8)
+    assert ora["near_i"].size == 400 * 399 // 2 and ora["stage"][3] == 0
+    res = run_gpu(regs, None, "cb", 1.0, gpu)
+    assert res.stats["pairs_near"] == 79800 and res.near_i.size == 79800
+    compare(res, ora, 1.0)
+
+
+# ---- BASELINE.json configs at their own size (SURVEY.md §8d C2, C3, C5's criteria at n = 10k) ----------------
+NCPU = os.cpu_count() or 8
+
+
+def test_config_c2_cb_only_10k(gpu):
+    """C2: n = 10 000, CB only, tau = 0.9 — 4.7 M pairs through the HLL-14 union, every one against the oracle."""
+    plan = synth.make_plan(10_000, 1001)
+    regs = synth.hll(plan, 14)
+    res = run_gpu(regs, None, "cb", 0.9, gpu)
+    ora = O.select(regs, 14, "cb", np.float32(0.9), threads=NCPU)
+    assert ora["stage"][1] == ora["stage"][2] > 4_000_000
+    compare(res, ora, 0.9)
+
+
+def test_config_c3_tau_sweep_10k(gpu):
+    """C3: n = 10 000, CB + smh_a (1 KiB, m = 128), all six thresholds of the sweep on one loaded context."""
+    plan = synth.make_plan(10_000, 1001)
+    regs = synth.hll(plan, 14)
+    aux = synth.smh(plan, 128)
+    with S.Selection(gpu) as sel:
+        sel.load(regs, aux, AUX_SMH)
+        for tau in (0.70, 0.75, 0.80, 0.85, 0.90, 0.95):
+            res = sel.run(tau=np.float32(tau), criterion="smh_a")
+            ora = O.select(regs, 14, "smh_a", np.float32(tau), aux=aux, threads=NCPU)
+            assert (res.stats["n_bands"], res.stats["n_rows"]) == (ora["n_bands"], ora["n_rows"])
+            assert len(ora["i"]) > 500
+            compare(res, ora, tau)
+
+
+@pytest.mark.parametrize("criterion", ["hll_a", "hll_an"])
+@pytest.mark.parametrize("p_aux", [10, 8])
+def test_config_c5_criteria_10k(gpu, criterion, p_aux):
+    """C5's criteria and auxiliary sizes (-a 1024 and -a 256) on 10 000 genomes of its seed: every CB pair's hll_a /
+    hll_an decision (P_aux) and the final list against the oracle."""
+    plan = synth.make_plan(10_000, 1003)
+    regs = synth.hll(plan, 14)
+    aux = synth.hll(plan, p_aux, synth.TAG_AUX_HLL)
+    res = run_gpu(regs, aux, criterion, 0.9, gpu)
+    ora = O.select(regs, 14, criterion, np.float32(0.9), aux=aux, threads=NCPU)
+    assert ora["stage"][1] > 4_000_000 and ora["stage"][3] > 500
+    compare(res, ora, 0.9)
