@@ -447,9 +447,24 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
             "2 x 8 x n_rows bucket bytes + 16 B per candidate", "latency-bound: thread per candidate, dependent loads")
     elif cfg.criterion in ("hll_a", "hll_an"):
         regs_aux = cfg.aux_bytes
-        add("filter", "k_tile_filter_hll_planes", mean("ms_filter"), "int_alu", p_cb, hll_essential_lop3(regs_aux),
-            f"essential LOP3 per CB pair (thread per pair, so lane-op = op): {hll_essential_lop3(regs_aux):.0f} for "
-            f"{regs_aux} auxiliary registers (max 12 + subset counting of 5 four-value groups: 6 selectors + 80, per 64 registers)")
+        mode = os.environ.get("SELB200_HLLFILTER", "")
+        if mode in ("onepass", "bytes") or regs_aux < 64:
+            add("filter", "k_tile_filter_hll_planes" if mode == "onepass" else "k_tile_filter_hll", mean("ms_filter"), "int_alu", p_cb,
+                hll_essential_lop3(regs_aux),
+                f"essential LOP3 per CB pair (thread per pair, so lane-op = op): {hll_essential_lop3(regs_aux):.0f} for "
+                f"{regs_aux} auxiliary registers (max 12 + subset counting of 5 four-value groups: 6 selectors + 80, per 64 registers)")
+        else:
+            # pass A stops a warp step once its 32 pairs are decided, so the work it needs is what it read: the library
+            # counts the executed steps (stats.filter_steps: 64 registers x 32 pairs each)
+            steps = st["filter_steps"]
+            full = p_cb / 32.0 * (regs_aux / 64.0)
+            add("filter", "k_tile_filter_hll_bound", mean("ms_filter"), "int_alu", steps * 32.0, hll_essential_lop3(64),
+                f"essential LOP3 per executed step and pair: {hll_essential_lop3(64):.0f} per 64 registers (max 2x12 + 6 selectors + "
+                f"5 four-value groups x 16); {steps} warp steps executed = {steps / max(full, 1):.3f} of the "
+                f"{full:.0f} a full read of every CB pair's sketches would take (bound decided after 1/2 or 3/4 of the registers)")
+            add("verify", "k_hll_verify", mean("ms_verify"), "int_alu", p_cand, hll_essential_lop3(regs_aux),
+                f"essential LOP3 per candidate: {hll_essential_lop3(regs_aux):.0f} (full sketch) ; then the fp64 Ertl MLE per candidate",
+                "fp64-latency-bound: thread per candidate, secant loop on a shared-memory histogram column")
     else:
         add("filter", "k_tile_enum", mean("ms_filter"), "hbm", p_cb, 16.0, "16 B per CB pair (emit the band)")
     lop3 = union_lop3_per_pair()

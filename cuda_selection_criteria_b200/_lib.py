@@ -33,11 +33,12 @@ class Stats(C.Structure):
         ("tiles_total", C.c_int64), ("tiles_shard", C.c_int64),
         ("n_bands", C.c_int32), ("n_rows", C.c_int32), ("batches", C.c_int32), ("launches", C.c_int32),
         ("ms_bounds", C.c_float), ("ms_filter", C.c_float), ("ms_verify", C.c_float), ("ms_union", C.c_float),
-        ("ms_estimate", C.c_float), ("ms_sort", C.c_float), ("ms_total", C.c_float), ("reserved", C.c_int32 * 8),
+        ("ms_estimate", C.c_float), ("ms_sort", C.c_float), ("ms_total", C.c_float), ("reserved0", C.c_int32),
+        ("filter_steps", C.c_int64), ("reserved", C.c_int32 * 5),
     ]
 
     def as_dict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 GATHER_HANDLE_BYTES = 128

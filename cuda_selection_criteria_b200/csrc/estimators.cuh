@@ -138,6 +138,34 @@ SELB_HD bool crit_hll_an(double tau, unsigned long long e1, unsigned long long e
     return (j_hat + C) >= tau;
 }
 
+// Sufficient (never necessary) fp32 test that hll_a (an = 0) / hll_an (an = 1) FAIL for a pair whose auxiliary union has
+// harmonic sum (over its non-empty registers) at most z_ub and at most c0_ub empty registers, m = 2^p_aux registers, none
+// of them at q+1.  ertl_mle starts from x0 = m'/(0.5 g + a), g = z, a = z + c[0], m' = m - c[0] (its first branch: g <= 1.5 a
+// always holds when c[q+1] = 0) and never decreases x, so t_lb = m x0 is a lower bound of the estimate; x0 decreases in z
+// and c[0], so upper bounds of those give a lower bound of x0.  Both criteria are non-increasing in the estimate
+// (Z sigma >= 0), so failing at the lower bound means failing.  Everything is biased towards "not sure": z is inflated
+// and t_lb deflated by 2e-5 (fp32 rounding of the whole chain stays below 4e-6), hll_a's size_t truncation is charged a
+// full unit, and the criterion must miss tau by 1e-4.  A pair that is not rejected here is decided exactly elsewhere.
+SELB_HD bool hll_surely_fails(int an, float tau, float zs, int order_n, float m, float e1, float e2, float z_ub, float c0_ub) {
+    const float den = 1.5f * (z_ub * 1.00002f) + c0_ub;
+    if (!(den > 0.f) || !(zs >= 0.f)) return false;
+    const float t_lb = m * (m - c0_ub) / den * 0.99998f;
+    if (!(t_lb > 2.f)) return false;
+    const float s = e1 + e2;
+    if (!an) {
+        const float t_mas = (t_lb - 1.f) / (1.f + zs);
+        return (s - t_mas) / t_mas < tau - 1e-4f;
+    }
+    float S = 0.f, num = 1.f;
+    for (int k = 1; k < order_n + 1; ++k) {
+        num *= zs;
+        S += num;
+    }
+    const float lim = (1.f + zs) * e2 / t_lb;
+    const float C = (lim < 1.f ? lim : 1.f) * (s / e2) * S * 1.00002f;
+    return (s - t_lb) / t_lb + C < tau - 1e-4f;
+}
+
 SELB_HD double jaccard(unsigned long long e1, unsigned long long e2, double t) {
     return ((double)e1 + (double)e2 - t) / t;
 }

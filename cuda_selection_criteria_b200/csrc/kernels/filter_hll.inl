@@ -100,49 +100,40 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 }
 
 // ============================================================================
-// K4'' : hll_a / hll_an tile filter on BIT PLANES of the auxiliary sketches (p_aux >= 6).
-// Same tile walk, same thread-per-pair shape (lane = column, row word = broadcast), same MLE + criterion
-// as k_tile_filter_hll; the union histogram of a pair is built with the logic of k_pair_hist_planes
-// (LOP3 borrow-chain max, 3+3-bit decode, carry-save counting) instead of 2^p_aux shared-memory
-// read-modify-writes, and written once into the thread's shared-memory column for the estimator.
-//   auxP[(plane*nw + w)*npad + g] : word w (32 registers) of a plane of the g-th sorted genome
-//                                   (subset form: the quad layout of k_aux_planes_quad in the same buffer)
-//   agrange[g]                    : min | max<<8 of that genome's auxiliary registers
-// The 32 pairs of a warp step share one 32-value window (their genomes sit within the CB band of each
-// other, so their register ranges coincide); a step whose pairs do not fit one window takes the byte
-// path of k_tile_filter_hll for its pairs.
+// K4'' : hll_a / hll_an on BIT PLANES of the auxiliary sketches (p_aux >= 6), in two passes.
+//
+//   pass A  k_tile_filter_hll_bound   every pair of the CB band (tile walk, thread per pair, lane = column, row word =
+//           broadcast): the union histogram of the pair's 32-value window is counted in registers with the logic of
+//           k_pair_hist_planes (LOP3 borrow-chain max, subset masks on groups of four values, carry-save counting) and
+//           turned, in fp32 and without touching shared memory, into a LOWER BOUND of the union estimate
+//           (selb::hll_surely_fails, estimators.cuh).  Both criteria are non-increasing in the estimate, so a pair that
+//           fails at the bound fails; everything else — about one pair in a few hundred — goes to the candidate list.
+//           The bound is also evaluated after half and after three quarters of the registers, with the unread part
+//           replaced by the smaller of the two genomes' own sums over it (atail, built at load): max(a,b) >= a, so the
+//           union's harmonic sum and zero count over any set of positions are at most either genome's.  A warp step
+//           whose 32 pairs all fail there stops reading; strangers of similar size fail after half of a 1024-register
+//           sketch, so most steps do.
+//   pass B  k_hll_verify              the candidates, thread per candidate: the same counting into the thread's
+//           shared-memory histogram column, then the Ertl MLE and the criterion exactly as the reference evaluates them
+//           (include/criteria_sketch.hpp:52-64, sketch/include/sketch/hll.h:628-688).  Decisions are the reference's:
+//           pass A only ever discards pairs pass B would discard.
+//   k_tile_filter_hll_planes (SELB200_HLLFILTER=onepass) is the single-pass form both replace: exact MLE for every CB pair.
+//
+//   auxQ[(wp*3 + q)*npad + g] (uint4) : the twelve plane words of word pair wp of the g-th sorted genome (k_aux_planes_quad)
+//   agrange[g]                        : min | max<<8 of that genome's auxiliary registers
+//   atail[g]                          : harmonic sum and zero count of its registers behind the two checkpoints
+// The 32 pairs of a warp step share one 32-value window (their genomes sit within the CB band of each other, so their
+// register ranges coincide); a step whose pairs do not fit one window goes to pass B, which takes the byte path
+// (shared-memory counters over auxT) for such a pair.
 // ============================================================================
 #ifndef HLLP_MIN_CTAS
 #define HLLP_MIN_CTAS 8
 #endif
 
-__global__ void __launch_bounds__(256)
-k_aux_planes(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, long long npad,
-             int p_aux, uint32_t* __restrict__ auxP) {
-    const int nw = (1 << p_aux) >> 5;
-    const long long total = n * nw;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int w = (int)(idx / n);
-        const long long g = idx - (long long)w * n;
-        const uint4* src = reinterpret_cast<const uint4*>(aux + ((size_t)order[g] << p_aux) + (size_t)w * 32);
-        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-        const uint32_t wd[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) m |= ((((wd[q] >> b) & 0x01010101u) * 0x10204080u) >> 28) << (4 * q);
-            auxP[((size_t)b * nw + w) * npad + g] = m;
-        }
-    }
-}
-
-// The same planes in QUAD layout, read by the subset form of the filter (k_tile_filter_hll_planes<2>, <3>): the twelve
-// plane words of a word PAIR (planes 0..5 of word 2wp, then of word 2wp+1) of one genome sit in three uint4,
+// The planes in QUAD layout: the twelve plane words of a word PAIR (planes 0..5 of word 2wp, then of word 2wp+1) of one
+// genome sit in three uint4,
 //   auxQ[(wp*3 + q)*npad + g]   q = 0: planes 0..3 of word 2wp   q = 1: planes 4,5 of 2wp and 0,1 of 2wp+1   q = 2: planes 2..5 of 2wp+1
-// so a filter step is three 128-bit loads per genome (coalesced over the 32 columns of a warp step) instead of twelve
-// 32-bit loads with their own index arithmetic.
+// so a filter step is three 128-bit loads per genome (coalesced over the 32 columns of a warp step).
 __global__ void __launch_bounds__(256)
 k_aux_planes_quad(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, long long npad,
                   int p_aux, uint32_t* __restrict__ auxQ) {
@@ -166,58 +157,68 @@ k_aux_planes_quad(const uint8_t* __restrict__ aux, const int32_t* __restrict__ o
     }
 }
 
+// checkpoints of pass A, in word pairs: after half and after three quarters of the sketch (0 = no such checkpoint)
+struct HllCheckpoints { int cp1, cp2, nwp; };
+__host__ __device__ __forceinline__ HllCheckpoints hll_checkpoints(int p_aux) {
+    const int nwp = (1 << p_aux) >> 6;
+    HllCheckpoints c{nwp / 2, (3 * nwp) / 4, nwp};
+    if (c.cp2 <= c.cp1 || c.cp2 >= nwp) c.cp2 = 0;
+    if (c.cp1 <= 0 || c.cp1 >= nwp) c.cp1 = 0;
+    return c;
+}
+struct AuxTail { float z1, c1, z2, c2; };     // sum of 2^-r over the non-empty registers / count of empty ones, behind cp1 and cp2
+
+// one warp per genome: smallest / largest register value, and the tail sums pass A bounds the unread part with
+// (rounded UP: they stand in for an upper bound)
 __global__ void __launch_bounds__(256)
 k_aux_range(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, long long n, int p_aux,
-            uint16_t* __restrict__ agrange) {
-    // one warp per genome: smallest / largest register value
+            uint16_t* __restrict__ agrange, AuxTail* __restrict__ atail) {
     const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= n) return;
     const uint8_t* row = aux + ((size_t)order[g] << p_aux);
+    const HllCheckpoints cp = hll_checkpoints(p_aux);
+    const int j1 = cp.cp1 * 64, j2 = cp.cp2 * 64;
     int vmin = 255, vmax = 0;
-    for (int j = lane; j < (1 << p_aux); j += 32) { const int v = row[j]; vmin = min(vmin, v); vmax = max(vmax, v); }
+    double z1 = 0., z2 = 0.;
+    uint32_t c1 = 0, c2 = 0;
+    for (int j = lane; j < (1 << p_aux); j += 32) {
+        const int v = row[j];
+        vmin = min(vmin, v); vmax = max(vmax, v);
+        const double t = v ? ldexp(1.0, -v) : 0.;
+        if (j >= j1) { z1 += t; c1 += v == 0; }
+        if (j >= j2) { z2 += t; c2 += v == 0; }
+    }
     for (int o = 16; o; o >>= 1) {
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
         vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
     }
-    if (lane == 0) agrange[g] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
+    if (lane == 0) {
+        agrange[g] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
+        if (atail) atail[g] = AuxTail{(float)z1 * 1.000001f, (float)c1, (float)z2 * 1.000001f, (float)c2};
+    }
 }
 
-// all word pairs of one (row, 32 columns) step for window G0: S / C2 end as the per-value carry-save state
-// FORM 0: one-hot masks on groups of eight values (gmask: 4 bits); FORM 1: subset masks on groups of four values
-// (gmask: 8 bits) followed by the in-register Moebius step — the counting step of plane_chunk_subsets in
-// kernels/union_planes.inl, where the scheme is described (SELB200_HLLFILTER=subsets; CPU-checked, not yet measured)
-template <int G0, int FORM>
-__device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
-                                                long long npad, int nw, uint32_t gmask, uint32_t (&x)[32]) {
-    uint32_t S[32], C2[32];
-#pragma unroll
-    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
+// word pairs [wp0, wp1) of one (row, column) pair for window G0 into the per-value carry-save state S / C2:
+// subset masks on groups of four values (the counting step of plane_chunk_subsets in kernels/union_planes.inl, where the
+// scheme is described); gmask: bit t = group t (values 8*G0 + 4t .. +3) can occur
+template <int G0>
+__device__ __forceinline__ void aux_subset_accum(const uint4* __restrict__ rq, const uint4* __restrict__ cq, uint32_t np32,
+                                                 int wp0, int wp1, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
 #pragma unroll 1
-    for (int w = 0; w < nw; w += 2) {
+    for (int wp = wp0; wp < wp1; ++wp) {
         uint32_t M[2][6];
         {
-            uint32_t a[2][6], b[2][6];
-            if (FORM == 1) {
-                // quad layout (k_aux_planes_quad): rowp / colp point at the genome's first uint4; three 128-bit loads
-                // per genome and step, 32-bit uint4 offsets (the launcher checks that the matrix stays below 2^32)
-                const uint4* rq = reinterpret_cast<const uint4*>(rowp);
-                const uint4* cq = reinterpret_cast<const uint4*>(colp);
-                const uint32_t np32 = (uint32_t)npad, o = (uint32_t)(w >> 1) * 3u * np32;
-                const uint4 r0 = __ldg(rq + o), r1 = __ldg(rq + (o + np32)), r2 = __ldg(rq + (o + 2u * np32));
-                const uint4 c0 = __ldg(cq + o), c1 = __ldg(cq + (o + np32)), c2 = __ldg(cq + (o + 2u * np32));
-                a[0][0] = r0.x; a[0][1] = r0.y; a[0][2] = r0.z; a[0][3] = r0.w; a[0][4] = r1.x; a[0][5] = r1.y;
-                a[1][0] = r1.z; a[1][1] = r1.w; a[1][2] = r2.x; a[1][3] = r2.y; a[1][4] = r2.z; a[1][5] = r2.w;
-                b[0][0] = c0.x; b[0][1] = c0.y; b[0][2] = c0.z; b[0][3] = c0.w; b[0][4] = c1.x; b[0][5] = c1.y;
-                b[1][0] = c1.z; b[1][1] = c1.w; b[1][2] = c2.x; b[1][3] = c2.y; b[1][4] = c2.z; b[1][5] = c2.w;
-            } else {
-#pragma unroll
-            for (int pl = 0; pl < 6; ++pl) {
-                const size_t o0 = ((size_t)pl * nw + w) * (size_t)npad, o1 = o0 + (size_t)npad;
-                a[0][pl] = __ldg(rowp + o0); a[1][pl] = __ldg(rowp + o1);
-                b[0][pl] = __ldg(colp + o0); b[1][pl] = __ldg(colp + o1);
-            }
-            }
+            // three 128-bit loads per genome and step, 32-bit uint4 offsets (the launcher checks that the matrix stays below 2^32)
+            const uint32_t o = (uint32_t)wp * 3u * np32;
+            const uint4 r0 = __ldg(rq + o), r1 = __ldg(rq + (o + np32)), r2 = __ldg(rq + (o + 2u * np32));
+            const uint4 c0 = __ldg(cq + o), c1 = __ldg(cq + (o + np32)), c2 = __ldg(cq + (o + 2u * np32));
+            const uint32_t a[2][6] = {{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y}, {r1.z, r1.w, r2.x, r2.y, r2.z, r2.w}};
+            const uint32_t b[2][6] = {{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y}, {c1.z, c1.w, c2.x, c2.y, c2.z, c2.w}};
             uint32_t lt0 = 0u, lt1 = 0u;
 #pragma unroll
             for (int pl = 0; pl < 6; ++pl) {
@@ -230,97 +231,107 @@ __device__ __forceinline__ void aux_plane_pairs(const uint32_t* __restrict__ row
                 M[1][pl] = lop3<0xCA>(lt1, b[1][pl], a[1][pl]);
             }
         }
-        if (FORM == 1) {
 #define SELB_AUX_SUBSET_GROUP(T8, HALF)                                                                   \
-            if (gmask & (1u << (2 * T8 + HALF))) {                                                        \
-                constexpr int c0 = 4 * (2 * T8 + HALF);                                                   \
-                const uint32_t e0 = HALF ? lop3<0xC0>(H0, M[0][2], 0u) : lop3<0x30>(H0, M[0][2], 0u);     \
-                const uint32_t e1 = HALF ? lop3<0xC0>(H1, M[1][2], 0u) : lop3<0x30>(H1, M[1][2], 0u);     \
-                uint32_t m0[4], m1[4], kk[4];                                                             \
-                m0[0] = e0; m0[1] = lop3<0xC0>(e0, M[0][0], 0u); m0[2] = lop3<0xC0>(e0, M[0][1], 0u);     \
-                m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);                                                 \
-                m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);     \
-                m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                 \
-                _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]); \
-                _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
-                _Pragma("unroll") for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);                \
-            }
+        if (gmask & (1u << (2 * T8 + HALF))) {                                                            \
+            constexpr int c0 = 4 * (2 * T8 + HALF);                                                       \
+            const uint32_t e0 = HALF ? lop3<0xC0>(H0, M[0][2], 0u) : lop3<0x30>(H0, M[0][2], 0u);         \
+            const uint32_t e1 = HALF ? lop3<0xC0>(H1, M[1][2], 0u) : lop3<0x30>(H1, M[1][2], 0u);         \
+            uint32_t m0[4], m1[4], kk[4];                                                                 \
+            m0[0] = e0; m0[1] = lop3<0xC0>(e0, M[0][0], 0u); m0[2] = lop3<0xC0>(e0, M[0][1], 0u);         \
+            m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);                                                     \
+            m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);         \
+            m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                     \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);    \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);                    \
+        }
 #define SELB_AUX_SUBSET_GROUP8(T8)                                                                        \
-            if (gmask & (3u << (2 * T8))) {                                                               \
-                const uint32_t H0 = lop3<(1 << (G0 + T8))>(M[0][5], M[0][4], M[0][3]);                    \
-                const uint32_t H1 = lop3<(1 << (G0 + T8))>(M[1][5], M[1][4], M[1][3]);                    \
-                SELB_AUX_SUBSET_GROUP(T8, 0)                                                              \
-                SELB_AUX_SUBSET_GROUP(T8, 1)                                                              \
-            }
-            SELB_AUX_SUBSET_GROUP8(0)
-            SELB_AUX_SUBSET_GROUP8(1)
-            SELB_AUX_SUBSET_GROUP8(2)
-            SELB_AUX_SUBSET_GROUP8(3)
+        if (gmask & (3u << (2 * T8))) {                                                                   \
+            const uint32_t H0 = lop3<(1 << (G0 + T8))>(M[0][5], M[0][4], M[0][3]);                        \
+            const uint32_t H1 = lop3<(1 << (G0 + T8))>(M[1][5], M[1][4], M[1][3]);                        \
+            SELB_AUX_SUBSET_GROUP(T8, 0)                                                                  \
+            SELB_AUX_SUBSET_GROUP(T8, 1)                                                                  \
+        }
+        SELB_AUX_SUBSET_GROUP8(0)
+        SELB_AUX_SUBSET_GROUP8(1)
+        SELB_AUX_SUBSET_GROUP8(2)
+        SELB_AUX_SUBSET_GROUP8(3)
 #undef SELB_AUX_SUBSET_GROUP8
 #undef SELB_AUX_SUBSET_GROUP
-            continue;
-        }
-        uint32_t L[2][8];
-#pragma unroll
-        for (int ws = 0; ws < 2; ++ws) {
-            L[ws][0] = lop3<0x01>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][1] = lop3<0x02>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][2] = lop3<0x04>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][3] = lop3<0x08>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][4] = lop3<0x10>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][5] = lop3<0x20>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][6] = lop3<0x40>(M[ws][2], M[ws][1], M[ws][0]);
-            L[ws][7] = lop3<0x80>(M[ws][2], M[ws][1], M[ws][0]);
-        }
-#define SELB_AUX_GROUP(T)                                                                                 \
-        if (gmask & (1u << T)) {                                                                          \
-            const uint32_t H0 = lop3<(1 << (G0 + T))>(M[0][5], M[0][4], M[0][3]);                         \
-            const uint32_t H1 = lop3<(1 << (G0 + T))>(M[1][5], M[1][4], M[1][3]);                         \
-            uint32_t m0[8], m1[8], kk[8];                                                                 \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);                 \
-        }
-        SELB_AUX_GROUP(0)
-        SELB_AUX_GROUP(1)
-        SELB_AUX_GROUP(2)
-        SELB_AUX_GROUP(3)
-#undef SELB_AUX_GROUP
-    }
-#pragma unroll
-    for (int v = 0; v < 32; ++v) x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]);
-    if (FORM == 1) {
-        // x[4t + s] = #registers of group t whose two low bits contain subset s -> the four bins of the group
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            x[4 * t + 0] -= x[4 * t + 1];
-            x[4 * t + 2] -= x[4 * t + 3];
-            x[4 * t + 0] -= x[4 * t + 2];
-            x[4 * t + 1] -= x[4 * t + 3];
-        }
     }
 }
 
-template <int G0, int FORM>
+// the four bins of group t from the state: totals 2*C2 + popc(S) count the registers of the group whose two low bits
+// CONTAIN subset s; two subtract steps (Moebius inversion, exact in integers) turn them into the four bins
+__device__ __forceinline__ void aux_subset_bins(const uint32_t (&S)[32], const uint32_t (&C2)[32], int t, uint32_t (&x)[4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) x[s] = 2u * C2[4 * t + s] + (uint32_t)__popc(S[4 * t + s]);
+    x[0] -= x[1];
+    x[2] -= x[3];
+    x[0] -= x[2];
+    x[1] -= x[3];
+}
+
+__device__ __forceinline__ uint32_t aux_gmask(int g0, int vlo, int vhi) {
+    uint32_t gmask = 0;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt)
+        if ((2 * g0 + tt) >= (vlo >> 2) && (2 * g0 + tt) <= (vhi >> 2)) gmask |= 1u << tt;
+    return gmask;
+}
+
+template <int G0>
 __device__ __forceinline__ void aux_plane_hist(const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
                                                long long npad, int nw, uint32_t gmask, uint32_t* __restrict__ hcol,
-                                               int nbins) {
-    uint32_t x[32];
-    aux_plane_pairs<G0, FORM>(rowp, colp, npad, nw, gmask, x);
+                                               int nbins, bool write = true) {
+    uint32_t S[32], C2[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
+    aux_subset_accum<G0>(reinterpret_cast<const uint4*>(rowp), reinterpret_cast<const uint4*>(colp), (uint32_t)npad, 0, nw >> 1,
+                         gmask, S, C2);
+    if (!write) return;
     // the thread's histogram column: zeros outside the window, the counts inside
     for (int b = 0; b < 8 * G0; ++b) hcol[b * 64] = 0u;
 #pragma unroll
-    for (int v = 0; v < 32; ++v)
-        if (8 * G0 + v < nbins) hcol[(8 * G0 + v) * 64] = x[v];
+    for (int t = 0; t < 8; ++t) {
+        uint32_t x[4];
+        aux_subset_bins(S, C2, t, x);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            if (8 * G0 + 4 * t + s < nbins) hcol[(8 * G0 + 4 * t + s) * 64] = x[s];
+    }
     for (int b = 8 * G0 + 32; b < nbins; ++b) hcol[b * 64] = 0u;
 }
 
-// AN bit 0: 0 = hll_a, 1 = hll_an; AN bit 1: counting form (0 = one-hot, 1 = subsets).  One integer keeps the names of
-// the two GPU-validated instantiations <0> and <1> (and with them the SASS identity check of tools/sass_diff.py).
+__device__ __forceinline__ void aux_plane_hist_g(int g0, const uint32_t* __restrict__ rowp, const uint32_t* __restrict__ colp,
+                                                 long long npad, int nw, uint32_t gmask, uint32_t* __restrict__ hcol, int nbins,
+                                                 bool write = true) {
+    switch (g0) {
+        case 0: aux_plane_hist<0>(rowp, colp, npad, nw, gmask, hcol, nbins, write); break;
+        case 1: aux_plane_hist<1>(rowp, colp, npad, nw, gmask, hcol, nbins, write); break;
+        case 2: aux_plane_hist<2>(rowp, colp, npad, nw, gmask, hcol, nbins, write); break;
+        case 3: aux_plane_hist<3>(rowp, colp, npad, nw, gmask, hcol, nbins, write); break;
+        default: aux_plane_hist<4>(rowp, colp, npad, nw, gmask, hcol, nbins, write); break;
+    }
+}
+
+// byte path of one pair into the thread's histogram column (register ranges too far apart for one window)
+__device__ __forceinline__ void aux_byte_hist(const uint32_t* __restrict__ auxT, long long npad, int words, int i, int kc,
+                                              uint32_t* __restrict__ hcol, int nbins, uint32_t bias0, uint32_t tb) {
+    for (int b = 0; b < nbins; ++b) hcol[b * 64] = 0u;
+    const uint32_t* colp = auxT + kc;
+    const uint32_t* row0 = auxT + i;
+    for (int j = 0; j < words; ++j) {
+        const uint32_t m0 = max4_lt128(__ldg(row0 + (size_t)j * npad), __ldg(colp + (size_t)j * npad)) + bias0;
+        hist_inc2<0, 1>(m0, tb);
+        hist_inc2<2, 3>(m0, tb);
+    }
+}
+
+// ---- single pass (SELB200_HLLFILTER=onepass): exact MLE + criterion for every pair of the band -------------------
 template <int AN>
 __global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
-k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __restrict__ agrange,
+k_tile_filter_hll_planes(const uint32_t* __restrict__ auxQ, const uint16_t* __restrict__ agrange,
                          const uint32_t* __restrict__ auxT, long long npad, int p_aux, TileWalk tw,
                          const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
                          const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
@@ -362,36 +373,10 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
                 vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
             }
             const int g0 = min(vlo >> 3, 4);
-            if ((vhi >> 3) <= g0 + 3) {
-                constexpr int FORM = (AN >> 1) & 1;
-                uint32_t gmask = 0;
-                if (FORM == 0) {
-                    for (int tt = 0; tt < 4; ++tt)
-                        if ((g0 + tt) >= (vlo >> 3) && (g0 + tt) <= (vhi >> 3)) gmask |= 1u << tt;
-                } else {
-                    for (int tt = 0; tt < 8; ++tt)
-                        if ((2 * g0 + tt) >= (vlo >> 2) && (2 * g0 + tt) <= (vhi >> 2)) gmask |= 1u << tt;
-                }
-                const uint32_t* rowp = FORM ? auxP + 4 * (size_t)i : auxP + i;      // FORM 1: quad layout, uint4 per genome
-                const uint32_t* colp = FORM ? auxP + 4 * (size_t)kc : auxP + kc;
-                switch (g0) {
-                    case 0: aux_plane_hist<0, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 1: aux_plane_hist<1, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 2: aux_plane_hist<2, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    case 3: aux_plane_hist<3, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                    default: aux_plane_hist<4, FORM>(rowp, colp, npad, nw, gmask, hcol, nbins); break;
-                }
-            } else {
-                // register ranges too far apart for one window: byte path (shared-memory counters)
-                for (int b = 0; b < nbins; ++b) hcol[b * 64] = 0u;
-                const uint32_t* colp = auxT + kc;
-                const uint32_t* row0 = auxT + i;
-                for (int j = 0; j < words; ++j) {
-                    const uint32_t m0 = max4_lt128(__ldg(row0 + (size_t)j * npad), __ldg(colp + (size_t)j * npad)) + bias0;
-                    hist_inc2<0, 1>(m0, tb);
-                    hist_inc2<2, 3>(m0, tb);
-                }
-            }
+            if ((vhi >> 3) <= g0 + 3)
+                aux_plane_hist_g(g0, auxQ + 4 * (size_t)i, auxQ + 4 * (size_t)kc, npad, nw, aux_gmask(g0, vlo, vhi), hcol, nbins);
+            else
+                aux_byte_hist(auxT, npad, words, i, kc, hcol, nbins, bias0, tb);
             bool pass = false;
             if (v) {
                 bool stopped = false;
@@ -403,6 +388,165 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxP, const uint16_t* __re
                 const unsigned long long slot = warp_claim(pair_count);
                 if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
             }
+        }
+    }
+}
+
+// ---- pass A: the bound ------------------------------------------------------------------------------------------------
+// harmonic sum over the non-empty values and the empty count of the window's counts so far, in fp32 (Horner from the top
+// value down; every count is an exact small integer, the bound's margins absorb the 32 roundings)
+__device__ __forceinline__ void aux_window_sums(const uint32_t (&S)[32], const uint32_t (&C2)[32], int g0, float& z, float& c0) {
+    float acc = 0.f;
+    c0 = 0.f;
+#pragma unroll
+    for (int t = 7; t >= 0; --t) {
+        uint32_t x[4];
+        aux_subset_bins(S, C2, t, x);
+#pragma unroll
+        for (int s = 3; s >= 0; --s) {
+            if (t == 0 && s == 0) {
+                // value 8*g0: the empty bin when the window starts at 0 (it is not part of the harmonic sum)
+                if (g0 == 0) c0 = (float)x[0];
+                else acc = fmaf(acc, 0.5f, (float)x[0]);
+            } else {
+                acc = fmaf(acc, 0.5f, (float)x[s]);
+            }
+        }
+    }
+    // acc = sum x[j] 2^-(j - j0), j0 = first value in the sum: 1 (window at 0) or 8*g0
+    z = ldexpf(acc, g0 == 0 ? -1 : -8 * g0);
+}
+
+template <int AN>
+__global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
+k_tile_filter_hll_bound(const uint32_t* __restrict__ auxQ, const uint16_t* __restrict__ agrange,
+                        const AuxTail* __restrict__ atail, long long npad, int p_aux, TileWalk tw,
+                        const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
+                        const unsigned long long* __restrict__ e, float tau, float zs, int order_n,
+                        uint2* __restrict__ cand, unsigned long long* __restrict__ cand_count,
+                        unsigned long long cand_cap, unsigned long long* __restrict__ unit_counter) {
+    __shared__ int s_unit;
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5;
+    uint32_t steps = 0;                         // word-pair steps this warp executed (statistics: unit_counter[1] = M_STEPS)
+    const HllCheckpoints cp = hll_checkpoints(p_aux);
+    const float m_f = (float)(1 << p_aux);
+    const int q = 64 - p_aux;
+    const uint32_t np32 = (uint32_t)npad;
+    const int uend = tw.count() * 4;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_unit = tw.j0 * 4 + (int)atomicAdd(unit_counter, 1ull);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= uend) break;
+        const int2 rc = tw.tile(unit >> 2);
+        const int r0 = rc.x * TILE + (unit & 3) * 32, c0 = rc.y * TILE;
+        for (int item = (int)w; item < 128; item += 2) {
+            const int i = r0 + (item >> 2);
+            const int k = c0 + (item & 3) * 32 + (int)lane;
+            if (i >= n) continue;
+            const bool v = k < n && k >= lo[i] && k <= hi[i];
+            if (!__any_sync(0xffffffffu, v)) continue;
+            const int kc = (int)min((long long)k, npad - 1), kn = min(kc, n - 1);
+            const uint32_t ra = agrange[i], rb = agrange[kn];
+            int vlo = v ? max((int)(ra & 0xff), (int)(rb & 0xff)) : 255;
+            int vhi = v ? max((int)(ra >> 8), (int)(rb >> 8)) : 0;
+            for (int o = 16; o; o >>= 1) {
+                vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, o));
+                vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
+            }
+            const int g0 = min(vlo >> 3, 4);
+            // the bound needs one window for the step's pairs and no register at q+1 (then the estimate's starting point
+            // is its first branch, hll.h:657); zs < 0 would make the criteria non-monotone.  Otherwise: all to pass B
+            bool alive = v;
+            if ((vhi >> 3) <= g0 + 3 && vhi <= q && zs >= 0.f) {
+                const uint32_t gmask = aux_gmask(g0, vlo, vhi);
+                const uint4* rq = reinterpret_cast<const uint4*>(auxQ) + i;
+                const uint4* cq = reinterpret_cast<const uint4*>(auxQ) + kc;
+                const float e1 = (float)e[i], e2 = (float)e[kn];
+                const AuxTail ti = atail[i], tk = atail[kn];
+                uint32_t S[32], C2[32];
+#pragma unroll
+                for (int x = 0; x < 32; ++x) { S[x] = 0; C2[x] = 0; }
+                int wp = 0;
+#pragma unroll 1
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int wend = seg == 0 ? cp.cp1 : (seg == 1 ? cp.cp2 : cp.nwp);
+                    if (wend <= wp) continue;
+                    switch (g0) {
+                        case 0: aux_subset_accum<0>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                        case 1: aux_subset_accum<1>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                        case 2: aux_subset_accum<2>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                        case 3: aux_subset_accum<3>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                        default: aux_subset_accum<4>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                    }
+                    steps += (uint32_t)(wend - wp);
+                    wp = wend;
+                    float z, zeros;
+                    aux_window_sums(S, C2, g0, z, zeros);
+                    if (seg == 0) { z += fminf(ti.z1, tk.z1); zeros += fminf(ti.c1, tk.c1); }
+                    else if (seg == 1) { z += fminf(ti.z2, tk.z2); zeros += fminf(ti.c2, tk.c2); }
+                    alive = alive && !selb::hll_surely_fails(AN, tau, zs, order_n, m_f, e1, e2, z, zeros);
+                    if (!__any_sync(0xffffffffu, alive)) break;
+                }
+            }
+            if (alive) {
+                const unsigned long long slot = warp_claim(cand_count);
+                if (slot < cand_cap) cand[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+            }
+        }
+    }
+    if (lane == 0 && steps) atomicAdd(unit_counter + 1, (unsigned long long)steps);
+}
+
+// ---- pass B: exact decision for the candidates -------------------------------------------------------------------
+template <int AN>
+__global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
+k_hll_verify(const uint32_t* __restrict__ auxQ, const uint16_t* __restrict__ agrange, const uint32_t* __restrict__ auxT,
+             long long npad, int p_aux, const uint2* __restrict__ cand, const unsigned long long* __restrict__ cand_count,
+             unsigned long long cand_cap, int n, const unsigned long long* __restrict__ e, double tau, float zs, int order_n,
+             uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap) {
+#ifndef SELB_EMUL
+    extern __shared__ __align__(1024) uint32_t hist_dyn[];   // [nbins][64 threads]
+#endif
+    const int nbins = 64 - p_aux + 2;
+    const uint32_t t = threadIdx.x, lane = t & 31, tb = t * 4;
+    const int nw = (1 << p_aux) >> 5;
+    const int words = (1 << p_aux) >> 2;
+    uint32_t* hcol = hist_dyn + t;
+    const uint32_t bias0 = hist_bias(hist_dyn);
+    const long long ncand = (long long)min(*cand_count, cand_cap);
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + t) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp0 * 32; base < ncand; base += nwarps * 32) {
+        const bool valid = base + lane < ncand;
+        const uint2 pr = valid ? cand[base + lane] : make_uint2(0u, 0u);
+        const int i = (int)pr.x, k = (int)pr.y;
+        const uint32_t ra = agrange[i], rb = agrange[k];
+        const int vlo = max((int)(ra & 0xff), (int)(rb & 0xff)), vhi = max((int)(ra >> 8), (int)(rb >> 8));
+        const int g0 = min(vlo >> 3, 4);
+        const bool fits = (vhi >> 3) <= g0 + 3;
+        // candidates come from anywhere in the band: group the warp's lanes by window, one counting pass per window
+        // (every lane runs it on its own pair; only the group's lanes keep the result)
+        uint32_t todo = __ballot_sync(0xffffffffu, valid && fits);
+        while (todo) {
+            const int g = __shfl_sync(0xffffffffu, g0, __ffs((int)todo) - 1);
+            const bool mine = valid && fits && g0 == g;
+            uint32_t gmask = mine ? aux_gmask(g0, vlo, vhi) : 0u;
+            for (int o = 16; o; o >>= 1) gmask |= __shfl_xor_sync(0xffffffffu, gmask, o);     // a superset counts empty groups: harmless
+            aux_plane_hist_g(g, auxQ + 4 * (size_t)i, auxQ + 4 * (size_t)k, npad, nw, gmask, hcol, nbins, mine);
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
+        if (valid && !fits) aux_byte_hist(auxT, npad, words, i, k, hcol, nbins, bias0, tb);
+        bool pass = false;
+        if (valid) {
+            bool stopped = false;
+            const StopHll stop{tau, e[i], e[k], zs, order_n, AN & 1};
+            const double tu = selb::ertl_mle(hcol, p_aux, 64, stop, &stopped);
+            pass = !stopped && stop.crit(tu);
+        }
+        if (pass) {
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = pr;
         }
     }
 }

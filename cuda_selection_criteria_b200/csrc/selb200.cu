@@ -51,10 +51,14 @@ namespace {
 
 thread_local std::string g_err;
 
-// SELB200_HLLFILTER=subsets (read once per process): subset form of the plane hll filter and its quad plane layout
-bool hll_subsets_enabled() {
-    static const bool on = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "subsets"); }();
-    return on;
+// SELB200_HLLFILTER (read once per process): "onepass" = exact MLE for every pair of the band on bit planes (the form the
+// two-pass filter replaced), "bytes" = shared-memory-counter filter over the transposed registers; both for A/B measurements
+int hll_filter_mode() {
+    static const int mode = [] {
+        const char* e = getenv("SELB200_HLLFILTER");
+        return !e ? 0 : !strcmp(e, "onepass") ? 1 : !strcmp(e, "bytes") ? 2 : 0;
+    }();
+    return mode;
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -208,8 +212,8 @@ struct selb200_ctx {
     } g;
     DevBuf g_push, g_merged;
     DevBuf row_cnt, row_off, sort_tmp;
-    DevBuf auxP, agrange;                // bit planes / register ranges of the auxiliary HLLs (sorted order)
-    bool auxp_quad = false;              // auxP holds the quad layout of k_aux_planes_quad (SELB200_HLLFILTER=subsets)
+    DevBuf auxP, agrange, atail;         // bit planes (quad layout) / register ranges / tail sums of the auxiliary HLLs (sorted order)
+    bool auxp_quad = false;              // auxP holds the planes of the loaded auxiliary HLLs (k_aux_planes_quad)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
     int chunk_regs = 0;
     // counting step of the plane kernel: subset masks on groups of four values (k_pair_hist_planes<EpiSubsets<..>>,
@@ -574,26 +578,25 @@ int load_end(selb200_ctx* c) {
                                              c->npad, row_words, c->auxT.as<uint32_t>());
         CK(cudaGetLastError());
         c->auxp_quad = false;
-        if (aux_len >= 6) {       // bit planes for k_tile_filter_hll_planes (two 32-register words per step)
-            const int nw = (1 << aux_len) >> 5;
+        // bit planes for the plane filter, in the quad layout (a word pair = two 32-register words per step); the filter
+        // addresses it with 32-bit uint4 offsets, a matrix beyond that keeps the byte form over auxT
+        const int nw = (1 << aux_len) >> 5;
+        if (aux_len >= 6 && (uint64_t)6 * nw * (uint64_t)c->npad < (1ull << 32)) {
             CKR(c->auxP.ensure((size_t)6 * nw * c->npad * 4));
             CKR(c->agrange.ensure((size_t)c->npad * sizeof(uint16_t)));
+            CKR(c->atail.ensure((size_t)c->npad * sizeof(AuxTail)));
             CK(cudaMemsetAsync(c->auxP.p, 0, (size_t)6 * nw * c->npad * 4, s));
             CK(cudaMemsetAsync(c->agrange.p, 0, (size_t)c->npad * sizeof(uint16_t), s));
+            CK(cudaMemsetAsync(c->atail.p, 0, (size_t)c->npad * sizeof(AuxTail), s));
             const int g2 = (int)std::min<int64_t>((n * nw + 255) / 256, (int64_t)c->sm_count * 16);
-            // the subset form of the filter reads the quad layout with 32-bit uint4 offsets
-            c->auxp_quad = hll_subsets_enabled() && (uint64_t)6 * nw * (uint64_t)c->npad < (1ull << 32);
-            if (c->auxp_quad)
-                k_aux_planes_quad<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n,
-                                                     c->npad, aux_len, c->auxP.as<uint32_t>());
-            else
-                k_aux_planes<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n, c->npad,
-                                                aux_len, c->auxP.as<uint32_t>());
+            k_aux_planes_quad<<<g2, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux), c->order_dev.as<int32_t>(), n,
+                                                 c->npad, aux_len, c->auxP.as<uint32_t>());
             CK(cudaGetLastError());
             k_aux_range<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_aux),
                                                                          c->order_dev.as<int32_t>(), n, aux_len,
-                                                                         c->agrange.as<uint16_t>());
+                                                                         c->agrange.as<uint16_t>(), c->atail.as<AuxTail>());
             CK(cudaGetLastError());
+            c->auxp_quad = true;
         }
     }
     CK(cudaStreamSynchronize(s));
@@ -675,7 +678,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -903,13 +906,11 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const float zs = prm->z_score * (crit >= SELB200_CRIT_HLL_A ? selb::sigma_p(c->aux_len) : 0.f);
     size_t hll_smem = 0;
     int hll_grid = 0;
-    // SELB200_HLLFILTER=bytes keeps the shared-memory-counter filter (A/B measurements); sketches below 64
-    // registers have no bit planes
-    static const bool hll_bytes_env = [] { const char* e = getenv("SELB200_HLLFILTER"); return e && !strcmp(e, "bytes"); }();
-    // SELB200_HLLFILTER=subsets: the plane filter with subset counting on groups of four values (instantiations <2>, <3>),
-    // decided at load time together with the layout of auxP
-    const bool hll_subsets_env = c->auxp_quad;
-    const bool hll_planes = crit >= SELB200_CRIT_HLL_A && c->aux_len >= 6 && !hll_bytes_env;
+    // hll_a / hll_an: two passes on bit planes (bound over the band, exact decision for the survivors) unless the
+    // auxiliary sketches have no planes (below 64 registers, or a matrix beyond 32-bit offsets) or SELB200_HLLFILTER says so
+    const bool hll_planes = crit >= SELB200_CRIT_HLL_A && c->auxp_quad && hll_filter_mode() != 2;
+    const bool hll_twopass = hll_planes && hll_filter_mode() == 0;
+    int hll_bound_grid = 0;
     if (crit >= SELB200_CRIT_HLL_A) {
         hll_smem = (size_t)(hll_planes ? 1 : 2) * (64 - c->aux_len + 2) * 64 * sizeof(uint32_t);
         static bool carve = false;
@@ -918,20 +919,21 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             cudaFuncSetAttribute(k_tile_filter_hll<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_tile_filter_hll_planes<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             cudaFuncSetAttribute(k_tile_filter_hll_planes<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_tile_filter_hll_planes<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_tile_filter_hll_planes<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_hll_verify<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_hll_verify<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             carve = true;
         }
         int per_sm = 0;
-        const cudaError_t oe = hll_planes
-            ? (hll_subsets_env ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<2>, 64, hll_smem)
-                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<0>, 64, hll_smem))
-            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem);
+        const cudaError_t oe = hll_twopass ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hll_verify<0>, 64, hll_smem)
+                               : hll_planes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll_planes<0>, 64, hll_smem)
+                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_filter_hll<0>, 64, hll_smem);
         if (oe != cudaSuccess || per_sm < 1) {
             cudaGetLastError();
             per_sm = 4;
         }
         hll_grid = c->sm_count * per_sm;
+        static const int bound_per_sm = resident_ctas(k_tile_filter_hll_bound<0>, 64);
+        hll_bound_grid = c->sm_count * bound_per_sm;
     }
     static const int smh_grid_per_sm = [] {
         int per_sm = 0;
@@ -1037,6 +1039,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         if (attempt > 0) {          // the memset at the top of the run covers the first attempt
             CK(cudaMemsetAsync(d_cnt, 0, 32, s));
             CK(cudaMemsetAsync(d_cnt + M_PUSHED, 0, 8, s));
+            CK(cudaMemsetAsync(d_cnt + M_STEPS, 0, 8, s));
         }
         const unsigned long long pair_lim = (unsigned long long)std::min<int64_t>(PAIR_CAP, c->hist_cap_pairs);
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
@@ -1058,18 +1061,18 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * 8);
                 k_tile_enum<<<grid, 256, 0, s>>>(tw, c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->pairs.as<uint2>(),
                                                  d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
-            } else if (hll_planes && hll_subsets_env) {
-                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
+            } else if (hll_twopass) {
+                const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_bound_grid);
                 if (crit == SELB200_CRIT_HLL_A)
-                    k_tile_filter_hll_planes<2><<<grid, 64, hll_smem, s>>>(
-                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
-                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
-                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
+                    k_tile_filter_hll_bound<0><<<grid, 64, 0, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->atail.as<AuxTail>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), (float)tau, zs,
+                        prm->order_n, c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
                 else
-                    k_tile_filter_hll_planes<3><<<grid, 64, hll_smem, s>>>(
-                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len, tw,
-                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), tau, zs,
-                        prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
+                    k_tile_filter_hll_bound<1><<<grid, 64, 0, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->atail.as<AuxTail>(), c->npad, c->aux_len, tw,
+                        c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, c->e_sorted.as<unsigned long long>(), (float)tau, zs,
+                        prm->order_n, c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, d_cnt + M_UNIT);
             } else if (hll_planes) {
                 const int grid = (int)std::min<int64_t>(nt * 4, (int64_t)hll_grid);
                 if (crit == SELB200_CRIT_HLL_A)
@@ -1100,6 +1103,20 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             DBG_SYNC(c, "tile filter");
             cudaEvent_t f1 = c->ev();
             t_filter.push_back({f0, f1});
+            if (hll_twopass) {
+                if (crit == SELB200_CRIT_HLL_A)
+                    k_hll_verify<0><<<hll_grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len,
+                        c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, n, c->e_sorted.as<unsigned long long>(),
+                        tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
+                else
+                    k_hll_verify<1><<<hll_grid, 64, hll_smem, s>>>(
+                        c->auxP.as<uint32_t>(), c->agrange.as<uint16_t>(), c->auxT.as<uint32_t>(), c->npad, c->aux_len,
+                        c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, n, c->e_sorted.as<unsigned long long>(),
+                        tau, zs, prm->order_n, c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP);
+                CK(cudaGetLastError());
+                st.launches++;
+            }
             if (crit == SELB200_CRIT_SMH_A) {
                 k_smh_verify<<<c->sm_count * 8, 256, 0, s>>>(
                     c->aux_sorted.as<uint64_t>(), c->sigT.as<uint32_t>(), c->npad, c->aux_len, n_rows, n_bands,
@@ -1111,7 +1128,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             DBG_SYNC(c, "smh verify");
             // ---- K5 + K6 --------------------------------------------------------------
             cudaEvent_t u0 = c->ev();
-            if (crit == SELB200_CRIT_SMH_A) t_verify.push_back({f1, u0});
+            if (crit == SELB200_CRIT_SMH_A || hll_twopass) t_verify.push_back({f1, u0});
             if (union_bytes) {
                 CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
                                      (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
@@ -1180,7 +1197,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             }
             next.push_back({ra, rb});
             if ((int64_t)sn[1] > c->hist_cap_pairs) { c->hist_cap_pairs = (int64_t)sn[1]; redo = true; }
-            cand_sum += crit == SELB200_CRIT_SMH_A ? (int64_t)sn[0] : (int64_t)sn[1];
+            cand_sum += crit == SELB200_CRIT_SMH_A || hll_twopass ? (int64_t)sn[0] : (int64_t)sn[1];
             pair_sum += (int64_t)sn[1];
         }
         if ((int64_t)h_fin[M_OUT] > c->out_cap) { c->out_cap = (int64_t)h_fin[M_OUT] + (1 << 16); redo = true; }
@@ -1196,6 +1213,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         if (!ranges.empty()) ranges.swap(next);
     }
     st.pairs_cb = (int64_t)h_fin[M_PAIRS_CB];
+    st.filter_steps = (int64_t)h_fin[M_STEPS];
     st.tiles_total = tiles_total;
     st.tiles_shard = shard_tiles(tiles_total);
     c->out_count = (int64_t)h_fin[M_OUT];
@@ -1365,6 +1383,7 @@ struct GatherHandle {            // what selb200_gather_create exports (SELB200_
     int32_t device, pad;
 };
 static_assert(sizeof(GatherHandle) <= SELB200_GATHER_HANDLE_BYTES, "handle blob too small");
+static_assert(sizeof(selb200_stats) == 160, "selb200_stats is part of the C ABI: fields are added inside the reserved words");
 
 size_t gather_zone_bytes(int64_t cap, int64_t near_cap) {
     return sizeof(GatherHdr) + (size_t)cap * 32 + (size_t)near_cap * 32;

@@ -97,7 +97,10 @@ typedef struct selb200_stats {
     float ms_estimate;    /* MLE + Jaccard + emit                                  */
     float ms_sort;
     float ms_total;       /* first launch to last, device time                     */
-    int32_t reserved[8];
+    int32_t reserved0;
+    int64_t filter_steps; /* hll_a / hll_an plane filter, first pass: warp steps executed (one step = 64 auxiliary
+                             registers of 32 pairs); below pairs_cb_shard/32 * 2^p_aux/64 when steps stop early */
+    int32_t reserved[5];
 } selb200_stats;
 
 /* ---- library / device ---------------------------------------------------- */

@@ -98,15 +98,31 @@ static inline void launch(unsigned grid, unsigned block, const std::function<voi
 static inline void launch(unsigned grid, const std::function<void()>& body) { launch(grid, 32, body); }
 }  // namespace emul
 
-template <class T> static inline T __shfl_sync(uint32_t, T v, int src) { return (T)emul::exchange((uint64_t)v, src); }
-template <class T> static inline T __shfl_xor_sync(uint32_t, T v, int m) { return (T)emul::exchange((uint64_t)v, (int)((threadIdx.x & 31) ^ (unsigned)m)); }
+// values travel as bit patterns (floating-point operands keep their bits, as on the device)
+namespace emul {
+template <class T> static inline uint64_t to_bits(T v) {
+    static_assert(sizeof(T) <= 8);
+    uint64_t b = 0;
+    std::memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <class T> static inline T from_bits(uint64_t b) {
+    T v;
+    std::memcpy(&v, &b, sizeof(T));
+    return v;
+}
+}  // namespace emul
+template <class T> static inline T __shfl_sync(uint32_t, T v, int src) { return emul::from_bits<T>(emul::exchange(emul::to_bits(v), src)); }
+template <class T> static inline T __shfl_xor_sync(uint32_t, T v, int m) {
+    return emul::from_bits<T>(emul::exchange(emul::to_bits(v), (int)((threadIdx.x & 31) ^ (unsigned)m)));
+}
 template <class T> static inline T __shfl_up_sync(uint32_t, T v, int d) {
     const int lane = (int)(threadIdx.x & 31);
-    return (T)emul::exchange((uint64_t)v, lane >= d ? lane - d : lane);
+    return emul::from_bits<T>(emul::exchange(emul::to_bits(v), lane >= d ? lane - d : lane));
 }
 template <class T> static inline T __shfl_down_sync(uint32_t, T v, int d) {
     const int lane = (int)(threadIdx.x & 31);
-    return (T)emul::exchange((uint64_t)v, lane + d < 32 ? lane + d : lane);
+    return emul::from_bits<T>(emul::exchange(emul::to_bits(v), lane + d < 32 ? lane + d : lane));
 }
 static inline uint32_t __ballot_sync(uint32_t, bool p) {
     emul::warp->xchg[threadIdx.x & 31] = p ? 1u : 0u;

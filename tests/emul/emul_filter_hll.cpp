@@ -1,8 +1,9 @@
 // emul_filter_hll.cpp — runs the CB + hll_a / hll_an chain of a selection run on the CPU through cuda_emul.h, from the
 // same .inl sources the GPU build compiles:
 //   k_cb_bounds -> k_rowblock_span -> exclusive scan -> k_tile_table                 (kernels/tiles.inl)
-//   k_aux_planes, k_aux_range (load time) -> k_tile_filter_hll_planes<AN>            (kernels/filter_hll.inl;
-//                                            <2>, <3>: the subset counting form, SELB200_HLLFILTER=subsets)
+//   k_aux_planes_quad, k_aux_range (load time) -> k_tile_filter_hll_bound<AN> -> k_hll_verify<AN>   (kernels/filter_hll.inl:
+//                                            the two-pass plane filter), or the single pass k_tile_filter_hll_planes<AN>
+//                                            (SELB200_HLLFILTER=onepass),
 //   or the byte form k_tile_filter_hll<AN> over the transposed registers
 // Input (file): sorted truncated cardinalities, auxiliary HLL registers in sorted order, tau, Z*sigma, criterion.
 // Output (file): P_cb and the surviving pair list — tests/test_emul_filter.py holds them against the oracle's
@@ -28,8 +29,8 @@ constexpr int TILE = 128;          // as in csrc/selb200.cu
 template <class T> static void rd(FILE* f, T* p, size_t n) { if (fread(p, sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 template <class T> static void wr(FILE* f, const T* p, size_t n) { if (fwrite(p, sizeof(T), n, f) != n) { fprintf(stderr, "short write\n"); exit(2); } }
 
-// emul_filter_hll hist-check SEED COUNT: the per-thread histogram step of the plane filter (aux_plane_hist, both
-// counting forms, every window) against the byte-wise definition hist[max(a[j], b[j])]++ on random sketch pairs
+// emul_filter_hll hist-check SEED COUNT: the per-thread histogram step of the plane filter (aux_plane_hist, every
+// window) against the byte-wise definition hist[max(a[j], b[j])]++ on random sketch pairs
 static int hist_check(uint64_t seed, int count) {
     std::mt19937_64 rng(seed);
     int bad = 0, done = 0;
@@ -49,14 +50,13 @@ static int hist_check(uint64_t seed, int count) {
         }
         a[rng() % m] = b[rng() % m] = (uint8_t)vhi;                   // the range is attained
         a[rng() % m] = (uint8_t)vlo; b[rng() % m] = (uint8_t)vlo;
-        const long long npad = 2;                                     // two "genomes": planes[plane][word][genome]
-        std::vector<uint32_t> P((size_t)6 * nw * npad, 0u), Q((size_t)6 * nw * npad, 0u);   // Q: quad layout (k_aux_planes_quad)
+        const long long npad = 2;                                     // two "genomes", quad layout (k_aux_planes_quad)
+        std::vector<uint32_t> Q((size_t)6 * nw * npad, 0u);
         for (int g = 0; g < 2; ++g)
             for (int j = 0; j < m; ++j)
                 for (int pl = 0; pl < 6; ++pl)
                     if (((g ? b[j] : a[j]) >> pl) & 1) {
                         const int w = j >> 5, slot = (w & 1) * 6 + pl;
-                        P[((size_t)pl * nw + w) * npad + g] |= 1u << (j & 31);
                         Q[(((size_t)(w >> 1) * 3 + (slot >> 2)) * npad + g) * 4 + (slot & 3)] |= 1u << (j & 31);
                     }
         uint32_t want[64] = {0};
@@ -66,39 +66,29 @@ static int hist_check(uint64_t seed, int count) {
         const int klo = std::max((int)*std::min_element(a.begin(), a.end()), (int)*std::min_element(b.begin(), b.end()));
         const int khi = std::max((int)*std::max_element(a.begin(), a.end()), (int)*std::max_element(b.begin(), b.end()));
         ++done;
-        for (int form = 0; form < 2; ++form) {
+        {
             uint32_t gmask = 0;
-            if (form == 0) { for (int t = 0; t < 4; ++t) if (g0 + t >= (klo >> 3) && g0 + t <= (khi >> 3)) gmask |= 1u << t; }
-            else { for (int t = 0; t < 8; ++t) if (2 * g0 + t >= (klo >> 2) && 2 * g0 + t <= (khi >> 2)) gmask |= 1u << t; }
+            for (int t = 0; t < 8; ++t) if (2 * g0 + t >= (klo >> 2) && 2 * g0 + t <= (khi >> 2)) gmask |= 1u << t;
             std::vector<uint32_t> hcol((size_t)64 * 64, 0xDEADBEEFu);
-            auto run = [&](auto G0) {
-                if (form) aux_plane_hist<decltype(G0)::value, 1>(Q.data(), Q.data() + 4, npad, nw, gmask, hcol.data(), nbins);
-                else aux_plane_hist<decltype(G0)::value, 0>(P.data(), P.data() + 1, npad, nw, gmask, hcol.data(), nbins);
-            };
-            switch (g0) {
-                case 0: run(std::integral_constant<int, 0>{}); break;
-                case 1: run(std::integral_constant<int, 1>{}); break;
-                case 2: run(std::integral_constant<int, 2>{}); break;
-                case 3: run(std::integral_constant<int, 3>{}); break;
-                default: run(std::integral_constant<int, 4>{}); break;
-            }
+            aux_plane_hist_g(g0, Q.data(), Q.data() + 4, npad, nw, gmask, hcol.data(), nbins);
+            // the fp32 sums pass A bounds the estimate with, from the same state
             for (int v = 0; v < nbins; ++v)
                 if (hcol[(size_t)v * 64] != want[v]) {
-                    if (bad < 10) printf("hist-check %d form %d p_aux=%d g0=%d range %d..%d: bin %d is %u, want %u\n", it, form, p_aux, g0, klo, khi, v, hcol[(size_t)v * 64], want[v]);
+                    if (bad < 10) printf("hist-check %d p_aux=%d g0=%d range %d..%d: bin %d is %u, want %u\n", it, p_aux, g0, klo, khi, v, hcol[(size_t)v * 64], want[v]);
                     ++bad;
                 }
         }
     }
     if (bad) printf("hist-check FAILED (%d bins of %d pairs)\n", bad, done);
-    else printf("hist-check: both forms identical to the definition on %d pairs\n", done);
+    else printf("hist-check: identical to the definition on %d pairs\n", done);
     return bad ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
     if (argc == 4 && std::string(argv[1]) == "hist-check") return hist_check(strtoull(argv[2], nullptr, 10), atoi(argv[3]));
-    if (argc < 5) { fprintf(stderr, "usage: emul_filter_hll in.bin out.bin planes|subsets|bytes n_shards [grid]\n"); return 2; }
-    const bool subsets = std::string(argv[3]) == "subsets";      // plane filter, subset counting (SELB200_HLLFILTER=subsets)
-    const bool planes = std::string(argv[3]) == "planes" || subsets;
+    if (argc < 5) { fprintf(stderr, "usage: emul_filter_hll in.bin out.bin twopass|onepass|bytes n_shards [grid]\n"); return 2; }
+    const bool twopass = std::string(argv[3]) == "twopass";      // the default plane filter: bound, then exact decision
+    const bool planes = std::string(argv[3]) == "onepass" || twopass;
     const int n_shards = atoi(argv[4]);
     const unsigned fgrid = argc > 5 ? (unsigned)atoi(argv[5]) : 3u;
     FILE* f = fopen(argv[1], "rb");
@@ -112,7 +102,7 @@ int main(int argc, char** argv) {
     const int n = hdr[0], p_aux = hdr[1], an = hdr[2], order_n = hdr[3], zeros = hdr[4];
     const size_t m_aux = (size_t)1 << p_aux;
     std::vector<unsigned long long> e((size_t)n);
-    std::vector<uint8_t> aux((size_t)n * m_aux + 32);      // k_aux_planes reads 32 bytes per word
+    std::vector<uint8_t> aux((size_t)n * m_aux + 32);      // k_aux_planes_quad reads 32 bytes per word
     rd(f, e.data(), e.size());
     rd(f, aux.data(), (size_t)n * m_aux);
     fclose(f);
@@ -140,30 +130,40 @@ int main(int argc, char** argv) {
     const int nw = (int)(m_aux >> 5);
     std::vector<uint32_t> auxP(planes ? (size_t)6 * nw * npad : 1, 0u);
     std::vector<uint16_t> agrange((size_t)npad, 0);
+    std::vector<AuxTail> atail((size_t)npad, AuxTail{0.f, 0.f, 0.f, 0.f});
     if (planes) {
-        emul::launch(2, 256, [&] {
-            if (subsets) k_aux_planes_quad(aux.data(), order.data(), n, npad, p_aux, auxP.data());
-            else k_aux_planes(aux.data(), order.data(), n, npad, p_aux, auxP.data());
-        });
-        emul::launch((unsigned)(((long long)n * 32 + 255) / 256), 256, [&] { k_aux_range(aux.data(), order.data(), n, p_aux, agrange.data()); });
+        emul::launch(2, 256, [&] { k_aux_planes_quad(aux.data(), order.data(), n, npad, p_aux, auxP.data()); });
+        emul::launch((unsigned)(((long long)n * 32 + 255) / 256), 256,
+                     [&] { k_aux_range(aux.data(), order.data(), n, p_aux, agrange.data(), atail.data()); });
     }
     const unsigned long long cap = 1ull << 22;
-    std::vector<uint2> pairs((size_t)cap), all_pairs;
+    std::vector<uint2> pairs((size_t)cap), cand(twopass ? (size_t)cap : 1), all_pairs;
+    unsigned long long cand_total = 0;
     for (int shard = 0; shard < n_shards; ++shard) {
-        meta[M_PAIRS] = meta[M_UNIT] = 0;
+        meta[M_PAIRS] = meta[M_UNIT] = meta[M_CAND] = 0;
         const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};
-        emul::launch(fgrid, 64, [&] {
-            if (subsets) {
-                if (an) k_tile_filter_hll_planes<3>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-                else k_tile_filter_hll_planes<2>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-            } else if (planes) {
-                if (an) k_tile_filter_hll_planes<1>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-                else k_tile_filter_hll_planes<0>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-            } else {
-                if (an) k_tile_filter_hll<1>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-                else k_tile_filter_hll<0>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
-            }
-        });
+        if (twopass) {
+            emul::launch(fgrid, 64, [&] {
+                if (an) k_tile_filter_hll_bound<1>(auxP.data(), agrange.data(), atail.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), (float)tau, zs, order_n, cand.data(), meta.data() + M_CAND, cap, meta.data() + M_UNIT);
+                else k_tile_filter_hll_bound<0>(auxP.data(), agrange.data(), atail.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), (float)tau, zs, order_n, cand.data(), meta.data() + M_CAND, cap, meta.data() + M_UNIT);
+            });
+            if (meta[M_CAND] > cap) { fprintf(stderr, "list overflow\n"); return 3; }
+            cand_total += meta[M_CAND];
+            emul::launch(fgrid, 64, [&] {
+                if (an) k_hll_verify<1>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, cand.data(), meta.data() + M_CAND, cap, n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap);
+                else k_hll_verify<0>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, cand.data(), meta.data() + M_CAND, cap, n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap);
+            });
+        } else {
+            emul::launch(fgrid, 64, [&] {
+                if (planes) {
+                    if (an) k_tile_filter_hll_planes<1>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                    else k_tile_filter_hll_planes<0>(auxP.data(), agrange.data(), auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                } else {
+                    if (an) k_tile_filter_hll<1>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                    else k_tile_filter_hll<0>(auxT.data(), npad, p_aux, tw, lo.data(), hi.data(), n, e.data(), tau, zs, order_n, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_UNIT);
+                }
+            });
+        }
         if (meta[M_PAIRS] > cap) { fprintf(stderr, "list overflow\n"); return 3; }
         all_pairs.insert(all_pairs.end(), pairs.begin(), pairs.begin() + (long long)meta[M_PAIRS]);
     }
@@ -174,6 +174,6 @@ int main(int argc, char** argv) {
     wr(f, out_hdr, 2);
     wr(f, all_pairs.data(), all_pairs.size());
     fclose(f);
-    printf("n=%d p_aux=%d %s %s P_cb=%llu pairs=%zu\n", n, p_aux, subsets ? "subsets" : planes ? "planes" : "bytes", an ? "hll_an" : "hll_a", meta[M_PAIRS_CB], all_pairs.size());
+    printf("n=%d p_aux=%d %s %s P_cb=%llu candidates=%llu pairs=%zu\n", n, p_aux, twopass ? "twopass" : planes ? "onepass" : "bytes", an ? "hll_an" : "hll_a", meta[M_PAIRS_CB], cand_total, all_pairs.size());
     return 0;
 }

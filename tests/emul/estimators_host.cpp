@@ -28,4 +28,12 @@ int est_cb(double tau, uint64_t e1, uint64_t e2) { return selb::crit_cb(tau, e1,
 int est_hll_a(double tau, uint64_t e1, uint64_t e2, double t, float zs) { return selb::crit_hll_a(tau, e1, e2, t, zs); }
 int est_hll_an(double tau, uint64_t e1, uint64_t e2, double t, float zs, int n) { return selb::crit_hll_an(tau, e1, e2, t, zs, n); }
 double est_jaccard(uint64_t e1, uint64_t e2, double t) { return selb::jaccard(e1, e2, t); }
+// pass A of the hll plane filter: the fp32 sufficient test, and the exact decision it must never contradict
+int est_hll_surely_fails(int an, float tau, float zs, int order_n, float m, float e1, float e2, float z_ub, float c0_ub) {
+    return selb::hll_surely_fails(an, tau, zs, order_n, m, e1, e2, z_ub, c0_ub);
+}
+int est_hll_exact(int an, const uint32_t* hist, int p_aux, double tau, uint64_t e1, uint64_t e2, float zs, int order_n) {
+    const double t = selb::ertl_mle<uint32_t>(hist, p_aux);
+    return an ? selb::crit_hll_an(tau, e1, e2, t, zs, order_n) : selb::crit_hll_a(tau, e1, e2, t, zs);
+}
 }

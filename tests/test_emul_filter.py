@@ -96,8 +96,9 @@ def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_a
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# hll_a / hll_an: k_aux_planes + k_aux_range + k_tile_filter_hll_planes<AN> (bit-plane form) and k_tile_filter_hll<AN>
-# (byte form; the histogram helpers are the emulator's semantic versions) against the oracle's decision per pair
+# hll_a / hll_an: k_aux_planes_quad + k_aux_range + the two-pass plane filter (k_tile_filter_hll_bound<AN> ->
+# k_hll_verify<AN>), the single-pass plane filter k_tile_filter_hll_planes<AN> and k_tile_filter_hll<AN> (byte form; the
+# histogram helpers are the emulator's semantic versions) against the oracle's decision per pair
 # ----------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def exe_hll(tmp_path_factory):
@@ -128,16 +129,20 @@ def oracle_hll_decisions(e, aux_sorted, p_aux, tau32, an, order_n):
 
 
 @pytest.mark.parametrize("n,seed,tau,p_aux,criterion,form,n_shards,grid,odd", [
-    (400, 51, 0.9, 8, "hll_a", "planes", 1, 3, False),
-    (400, 52, 0.85, 8, "hll_an", "planes", 2, 2, False),
-    (300, 53, 0.9, 10, "hll_a", "planes", 1, 4, False),
-    (300, 54, 0.9, 6, "hll_an", "planes", 1, 2, True),     # outliers: steps whose pairs do not share a 32-value window
+    # the default: pass A's fp32 bound (early exits after half / three quarters of the sketch) + pass B's exact decision
+    (400, 51, 0.9, 8, "hll_a", "twopass", 1, 3, False),
+    (400, 52, 0.85, 8, "hll_an", "twopass", 2, 2, False),
+    (300, 53, 0.9, 10, "hll_a", "twopass", 1, 4, False),
+    (300, 60, 0.9, 10, "hll_an", "twopass", 1, 4, False),
+    (300, 54, 0.9, 6, "hll_an", "twopass", 1, 2, True),     # outliers: steps whose pairs do not share a 32-value window
+    (300, 61, 0.7, 7, "hll_a", "twopass", 1, 2, True),
+    (300, 62, 0.95, 12, "hll_a", "twopass", 2, 3, False),
     (300, 55, 0.9, 5, "hll_a", "bytes", 1, 2, False),       # p_aux < 6 has no bit planes: the byte form
     (300, 56, 0.8, 8, "hll_an", "bytes", 2, 3, True),
-    # the plane filter with subset counting on groups of four values (SELB200_HLLFILTER=subsets)
-    (400, 57, 0.9, 8, "hll_a", "subsets", 1, 3, False),
-    (300, 58, 0.85, 10, "hll_an", "subsets", 2, 2, False),
-    (300, 59, 0.9, 6, "hll_a", "subsets", 1, 2, True),
+    # exact MLE for every pair of the band on the same planes (SELB200_HLLFILTER=onepass)
+    (400, 57, 0.9, 8, "hll_a", "onepass", 1, 3, False),
+    (300, 58, 0.85, 10, "hll_an", "onepass", 2, 2, False),
+    (300, 59, 0.9, 6, "hll_a", "onepass", 1, 2, True),
 ])
 def test_cb_and_hll_decisions_on_the_emulator(exe_hll, tmp_path, n, seed, tau, p_aux, criterion, form, n_shards, grid, odd):
     tau32 = np.float32(tau)
@@ -169,14 +174,19 @@ def test_cb_and_hll_decisions_on_the_emulator(exe_hll, tmp_path, n, seed, tau, p
     assert p_cb == op_cb
     assert pairs == opairs                                 # hll_a / hll_an decisions bit-exact (early-exit MLE included)
     assert 10 < len(opairs) < op_cb
+    if form == "twopass":
+        ncand = int(r.stdout.split("candidates=")[1].split()[0])
+        assert len(opairs) <= ncand
+        if not odd and p_aux >= 8:
+            assert ncand < 2 * len(opairs) + 0.1 * op_cb   # the bound has to discard most failing pairs, or the second pass gains nothing
 
 
-def test_hll_plane_histograms_both_counting_forms(exe_hll):
-    """aux_plane_hist (the per-thread histogram step of k_tile_filter_hll_planes) in its one-hot and its subset form
-    against hist[max(a[j], b[j])]++ on random sketch pairs: p_aux 6..12, every window, ranges of 1..24 values."""
+def test_hll_plane_histograms(exe_hll):
+    """aux_plane_hist (the per-thread histogram step of k_hll_verify / k_tile_filter_hll_planes: subset counting on the
+    quad plane layout) against hist[max(a[j], b[j])]++ on random sketch pairs: p_aux 6..12, every window, ranges of 1..24 values."""
     r = subprocess.run([exe_hll, "hist-check", "20261018", "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "both forms identical to the definition" in r.stdout
+    assert "hist-check: identical to the definition" in r.stdout
 
 
 _SMH_MUTATIONS = [

@@ -32,6 +32,8 @@ def est(tmp_path_factory):
     L.est_cb.argtypes = [C.c_double, C.c_uint64, C.c_uint64]
     L.est_hll_a.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_float]
     L.est_hll_an.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_float, C.c_int]
+    L.est_hll_surely_fails.argtypes = [C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.est_hll_exact.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, C.c_float, C.c_int]
     L.est_jaccard.restype = C.c_double
     L.est_jaccard.argtypes = [C.c_uint64, C.c_uint64, C.c_double]
     return L
@@ -143,3 +145,55 @@ def test_criteria_bit_exact_vs_oracle(est):
                 n_true += a
                 n_false += not a
     assert n_true > 1000 and n_false > 1000
+
+
+@pytest.mark.parametrize("p_aux,tau", [(10, 0.9), (8, 0.9), (6, 0.8), (12, 0.95), (9, 0.7)])
+def test_hll_bound_never_rejects_a_passing_pair(est, p_aux, tau):
+    """Pass A of the hll plane filter (selb::hll_surely_fails on upper bounds of the union's harmonic sum and empty count)
+    against the exact decision (Ertl MLE + hll_a / hll_an): with all registers read, and after half / three quarters of them
+    with the rest replaced by the smaller of the two genomes' own tail sums.  It may only discard pairs the exact decision
+    discards; and it has to discard most strangers, or the two-pass filter gains nothing."""
+    n = 500
+    plan = synth.make_plan(n, 300 + p_aux)
+    regs = synth.hll(plan, 14)
+    aux = synth.hll(plan, p_aux, synth.TAG_AUX_HLL).astype(np.int64)
+    cards = np.array([O.cardinality(regs[g], 14) for g in range(n)])
+    order = np.argsort(cards, kind="stable")
+    e = cards[order].astype(np.uint64)
+    A = aux[order]
+    m = 1 << p_aux
+    tau32 = np.float32(tau)
+    zs = np.float32(1.96) * np.float32(O.lib().oracle_sigma(p_aux))
+    w = np.where(A > 0, np.exp2(-A.astype(np.float64)), 0.0)
+    cuts = sorted({m, m // 2, (3 * m) // 4})
+    tails = {c: (w[:, c:].sum(1), (A[:, c:] == 0).sum(1)) for c in cuts}
+    tested = rejected_full = strangers = strangers_rejected_half = passing = 0
+    cl = plan.cluster[order]
+    for an in (0, 1):
+        for i in range(0, n - 1, 3):
+            for k in range(i + 1, n):
+                if not est.est_cb(float(tau32), int(e[i]), int(e[k])):
+                    break
+                U = np.maximum(A[i], A[k])
+                h = hist64(U.astype(np.uint8))
+                exact = est.est_hll_exact(an, h.ctypes.data, p_aux, float(tau32), int(e[i]), int(e[k]), zs, 1)
+                wu = np.where(U > 0, np.exp2(-U.astype(np.float64)), 0.0)
+                passing += exact
+                for c in cuts:
+                    z = wu[:c].sum() + min(tails[c][0][i], tails[c][0][k])
+                    c0 = (U[:c] == 0).sum() + min(tails[c][1][i], tails[c][1][k])
+                    rej = est.est_hll_surely_fails(an, tau32, zs, 1, float(m), float(e[i]), float(e[k]),
+                                                   float(np.float32(z) * np.float32(1.000001)), float(c0))
+                    assert not (rej and exact), (an, i, k, c)
+                    tested += 1
+                    if c == m:
+                        rejected_full += rej
+                    if c == m // 2 and cl[i] != cl[k]:
+                        strangers += 1
+                        strangers_rejected_half += rej
+    assert tested > 3000 and passing > 10
+    assert rejected_full > 0.9 * (tested / len(cuts) - passing) - 5
+    if p_aux >= 9 and tau >= 0.9:
+        # strangers of equal size e: z_ub = 1.5 z_union after half the registers, so t_lb = 0.62 t = 1.23 e and k_mas = 0.73 —
+        # decided at the first checkpoint for tau = 0.9, only at the second (k_mas = 0.47) for lower thresholds
+        assert strangers_rejected_half > 0.99 * strangers

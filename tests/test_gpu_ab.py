@@ -1,7 +1,8 @@
 """-m gpu: the forms of the union pass (bit planes with subset counting = default, with one-hot counting, bytes) and the
-forms of the hll filter against each other, at sizes the CPU oracle would take minutes for.  All forms compute the
-same integer histograms, so pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=planes|bytes
-is read when a context is created, SELB200_HLLFILTER=bytes at library load)."""
+forms of the hll filter (two passes on bit planes = default, one pass on bit planes, bytes) against each other, at sizes
+the CPU oracle would take minutes for.  All forms compute the same integer histograms and the same fp64 decision, so
+pair lists, Jaccard bits and stage counts must be identical (SELB200_UNION=planes|bytes is read when a context is
+created, SELB200_HLLFILTER=onepass|bytes at library load)."""
 import hashlib
 import json
 import os
@@ -55,4 +56,6 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
     by = _run({"SELB200_UNION": "bytes", "SELB200_HLLFILTER": "bytes"}, tmp_path)
     assert default == by
     assert onehot == by
+    onepass = _run({"SELB200_HLLFILTER": "onepass"}, tmp_path)
+    assert onepass == by
     assert all(v[1] > 1000 for v in default.values())          # thousands of emitted pairs in every case
