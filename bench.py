@@ -458,9 +458,9 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
             # counts the executed steps (stats.filter_steps: 64 registers x 32 pairs each)
             steps = st["filter_steps"]
             full = p_cb / 32.0 * (regs_aux / 64.0)
-            add("filter", "k_tile_filter_hll_bound", mean("ms_filter"), "int_alu", steps * 32.0, hll_essential_lop3(64),
-                f"essential LOP3 per executed step and pair: {hll_essential_lop3(64):.0f} per 64 registers (max 2x12 + 6 selectors + "
-                f"5 four-value groups x 16); {steps} warp steps executed = {steps / max(full, 1):.3f} of the "
+            add("filter", "k_tile_filter_hll_bound", mean("ms_filter"), "int_alu", steps * 32.0, HLL_BOUND_LOP3,
+                f"essential LOP3 per executed step and pair: {HLL_BOUND_LOP3:.0f} per 64 registers (max 2x12 + 4 selectors + "
+                f"3 counted four-value groups x 16); {steps} warp steps executed = {steps / max(full, 1):.3f} of the "
                 f"{full:.0f} a full read of every CB pair's sketches would take (bound decided after 1/2 or 3/4 of the registers)")
             add("verify", "k_hll_verify", mean("ms_verify"), "int_alu", p_cand, hll_essential_lop3(regs_aux),
                 f"essential LOP3 per candidate: {hll_essential_lop3(regs_aux):.0f} (full sketch) ; then the fp64 Ertl MLE per candidate",
@@ -487,6 +487,9 @@ def union_lop3_per_pair():
     # 4 groups x 34) = 1376; subset form 8 x (20 max + 8 selectors + 8 groups of four x 16) = 1248.  With the group masks of
     # the C4 workload the kernels execute about 1200 and 905 (tests/emul/union_lop3_model.py).
     return {"planes": 1376.0, "bytes": 0.0}.get(os.environ.get("SELB200_UNION", ""), 1248.0)
+
+
+HLL_BOUND_LOP3 = 24.0 + 4 + 3 * 16      # pass A of the two-pass hll filter, per step of 64 auxiliary registers
 
 
 def hll_essential_lop3(regs_aux):

@@ -103,8 +103,9 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 // K4'' : hll_a / hll_an on BIT PLANES of the auxiliary sketches (p_aux >= 6), in two passes.
 //
 //   pass A  k_tile_filter_hll_bound   every pair of the CB band (tile walk, thread per pair, lane = column, row word =
-//           broadcast): the union histogram of the pair's 32-value window is counted in registers with the logic of
-//           k_pair_hist_planes (LOP3 borrow-chain max, subset masks on groups of four values, carry-save counting) and
+//           broadcast): the twelve smallest values of the union's registers are counted in registers with the logic of
+//           k_pair_hist_planes (LOP3 borrow-chain max, subset masks on groups of four values, carry-save counting), every
+//           other register is charged the next value, and the sums are
 //           turned, in fp32 and without touching shared memory, into a LOWER BOUND of the union estimate
 //           (selb::hll_surely_fails, estimators.cuh).  Both criteria are non-increasing in the estimate, so a pair that
 //           fails at the bound fails; everything else — about one pair in a few hundred — goes to the candidate list.
@@ -129,6 +130,11 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 #ifndef HLLP_MIN_CTAS
 #define HLLP_MIN_CTAS 8
 #endif
+#ifndef HLLB_MIN_CTAS
+#define HLLB_MIN_CTAS 12      // pass A: 64 threads x 12 CTAs = 24 warps per SM at <= 80 registers (measured: 10 CTAs 8.34 ms,
+                              // 12 CTAs 7.79, 16 CTAs with 32 B spilled 7.67; loading a step ahead: 8.3 — C5, p_aux = 10)
+#endif
+
 
 // The planes in QUAD layout: the twelve plane words of a word PAIR (planes 0..5 of word 2wp, then of word 2wp+1) of one
 // genome sit in three uint4,
@@ -393,32 +399,106 @@ k_tile_filter_hll_planes(const uint32_t* __restrict__ auxQ, const uint16_t* __re
 }
 
 // ---- pass A: the bound ------------------------------------------------------------------------------------------------
-// harmonic sum over the non-empty values and the empty count of the window's counts so far, in fp32 (Horner from the top
-// value down; every count is an exact small integer, the bound's margins absorb the 32 roundings)
-__device__ __forceinline__ void aux_window_sums(const uint32_t (&S)[32], const uint32_t (&C2)[32], int g0, float& z, float& c0) {
-    float acc = 0.f;
-    c0 = 0.f;
+// The bound needs an UPPER bound of the union's harmonic sum, not its histogram: only the twelve smallest values the step's
+// pairs can hold (three groups of four, from the group of vlo up) are counted; every other register read so far is
+// larger than those and enters the sum with 2^-vcap, vcap = the first value not counted.  Register values fall off
+// geometrically above the smallest one (P(value >= k) ~ load 2^-k), so those registers are a few percent of the sketch
+// and each is charged at most 2^-9 of an average term: the sum grows by ~1e-3 of itself, far inside the bound's slack.
+// Three groups instead of the five or six a full window holds: 76 instead of ~130 LOP3 per step, 24 state registers
+// instead of 64.
+constexpr int HLLB_NG = 3, HLLB_NV = 4 * HLLB_NG;
+
+// word pairs [wp0, wp1) of one (row, column) pair: groups T0 .. T0+2 (of four values, counted from value 8*G0) into the
+// carry-save state; gmask as in aux_subset_accum (bit t = group t can occur)
+template <int G0, int T0>
+__device__ __forceinline__ void aux_bound_accum(const uint4* __restrict__ rq, const uint4* __restrict__ cq, uint32_t np32,
+                                                int wp0, int wp1, uint32_t gmask, uint32_t (&S)[HLLB_NV], uint32_t (&C2)[HLLB_NV]) {
+#pragma unroll 1
+    for (int wp = wp0; wp < wp1; ++wp) {
+        uint32_t M[2][6];
+        {
+            const uint32_t o = (uint32_t)wp * 3u * np32;
+            const uint4 r0 = __ldg(rq + o), r1 = __ldg(rq + (o + np32)), r2 = __ldg(rq + (o + 2u * np32));
+            const uint4 c0 = __ldg(cq + o), c1 = __ldg(cq + (o + np32)), c2 = __ldg(cq + (o + 2u * np32));
+            const uint32_t a[2][6] = {{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y}, {r1.z, r1.w, r2.x, r2.y, r2.z, r2.w}};
+            const uint32_t b[2][6] = {{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y}, {c1.z, c1.w, c2.x, c2.y, c2.z, c2.w}};
+            uint32_t lt0 = 0u, lt1 = 0u;
 #pragma unroll
-    for (int t = 7; t >= 0; --t) {
-        uint32_t x[4];
-        aux_subset_bins(S, C2, t, x);
+            for (int pl = 0; pl < 6; ++pl) {
+                lt0 = lop3<0x8E>(a[0][pl], b[0][pl], lt0);
+                lt1 = lop3<0x8E>(a[1][pl], b[1][pl], lt1);
+            }
 #pragma unroll
-        for (int s = 3; s >= 0; --s) {
-            if (t == 0 && s == 0) {
-                // value 8*g0: the empty bin when the window starts at 0 (it is not part of the harmonic sum)
-                if (g0 == 0) c0 = (float)x[0];
-                else acc = fmaf(acc, 0.5f, (float)x[0]);
-            } else {
-                acc = fmaf(acc, 0.5f, (float)x[s]);
+            for (int pl = 0; pl < 6; ++pl) {
+                M[0][pl] = lop3<0xCA>(lt0, b[0][pl], a[0][pl]);
+                M[1][pl] = lop3<0xCA>(lt1, b[1][pl], a[1][pl]);
+            }
+        }
+        // groups T0 .. T0+2 lie in the eight-value blocks 0 and 1 of the window for T0 = 0 and for T0 = 1
+        const uint32_t H[2][2] = {{lop3<(1 << G0)>(M[0][5], M[0][4], M[0][3]), lop3<(1 << G0)>(M[1][5], M[1][4], M[1][3])},
+                                  {lop3<(1 << (G0 + 1))>(M[0][5], M[0][4], M[0][3]), lop3<(1 << (G0 + 1))>(M[1][5], M[1][4], M[1][3])}};
+#pragma unroll
+        for (int u = 0; u < HLLB_NG; ++u) {
+            const int t = T0 + u, t8 = t >> 1, half = t & 1;
+            if (gmask & (1u << t)) {
+                const int c0 = 4 * u;
+                const uint32_t e0 = half ? lop3<0xC0>(H[t8][0], M[0][2], 0u) : lop3<0x30>(H[t8][0], M[0][2], 0u);
+                const uint32_t e1 = half ? lop3<0xC0>(H[t8][1], M[1][2], 0u) : lop3<0x30>(H[t8][1], M[1][2], 0u);
+                uint32_t m0[4], m1[4], kk[4];
+                m0[0] = e0; m0[1] = lop3<0xC0>(e0, M[0][0], 0u); m0[2] = lop3<0xC0>(e0, M[0][1], 0u);
+                m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);
+                m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);
+                m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);
             }
         }
     }
-    // acc = sum x[j] 2^-(j - j0), j0 = first value in the sum: 1 (window at 0) or 8*g0
-    z = ldexpf(acc, g0 == 0 ? -1 : -8 * g0);
+}
+
+// upper bounds of the harmonic sum over the non-empty registers and of the empty count among the nread registers read
+// so far, in fp32 (Horner from the top counted value down; every count is an exact small integer, the bound's margins
+// absorb the roundings)
+template <int G0, int T0>
+__device__ __forceinline__ void aux_bound_sums(const uint32_t (&S)[HLLB_NV], const uint32_t (&C2)[HLLB_NV], uint32_t nread,
+                                               float& z, float& c0) {
+    constexpr int v0 = 8 * G0 + 4 * T0;            // first counted value
+    constexpr int vfirst = v0 == 0 ? 1 : v0;       // first value of the harmonic sum (0 = empty register)
+    constexpr int vcap = v0 + HLLB_NV;             // every register not counted holds at least this
+    float acc = 0.f;
+    uint32_t cnt = 0;
+    c0 = 0.f;
+#pragma unroll
+    for (int u = HLLB_NG - 1; u >= 0; --u) {
+        uint32_t x[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) x[s] = 2u * C2[4 * u + s] + (uint32_t)__popc(S[4 * u + s]);
+        x[0] -= x[1]; x[2] -= x[3]; x[0] -= x[2]; x[1] -= x[3];      // Moebius inversion, as in aux_subset_bins
+#pragma unroll
+        for (int s = 3; s >= 0; --s) {
+            cnt += x[s];
+            if (v0 + 4 * u + s == 0) c0 = (float)x[s];
+            else acc = fmaf(acc, 0.5f, (float)x[s]);
+        }
+    }
+    // acc = sum x[v] 2^-(v - vfirst)
+    z = acc * (1.f / (float)(1ull << vfirst)) + (float)(nread - cnt) * (1.f / (float)(1ull << vcap));
+}
+
+template <int G0, int T0>
+__device__ __forceinline__ void aux_bound_segment(const uint4* __restrict__ rq, const uint4* __restrict__ cq, uint32_t np32,
+                                                  int wp0, int wp1, uint32_t gmask, uint32_t (&S)[HLLB_NV],
+                                                  uint32_t (&C2)[HLLB_NV], float& z, float& c0) {
+    aux_bound_accum<G0, T0>(rq, cq, np32, wp0, wp1, gmask, S, C2);
+    aux_bound_sums<G0, T0>(S, C2, 64u * (uint32_t)wp1, z, c0);
 }
 
 template <int AN>
-__global__ void __launch_bounds__(64, HLLP_MIN_CTAS)
+__global__ void __launch_bounds__(64, HLLB_MIN_CTAS)
 k_tile_filter_hll_bound(const uint32_t* __restrict__ auxQ, const uint16_t* __restrict__ agrange,
                         const AuxTail* __restrict__ atail, long long npad, int p_aux, TileWalk tw,
                         const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,
@@ -455,35 +535,41 @@ k_tile_filter_hll_bound(const uint32_t* __restrict__ auxQ, const uint16_t* __res
                 vlo = min(vlo, __shfl_xor_sync(0xffffffffu, vlo, o));
                 vhi = max(vhi, __shfl_xor_sync(0xffffffffu, vhi, o));
             }
-            const int g0 = min(vlo >> 3, 4);
-            // the bound needs one window for the step's pairs and no register at q+1 (then the estimate's starting point
-            // is its first branch, hll.h:657); zs < 0 would make the criteria non-monotone.  Otherwise: all to pass B
+            // every union register of the step's pairs holds at least vlo: the counted groups start at vlo's.  The bound
+            // needs no register at q+1 (then the estimate's starting point is its first branch, hll.h:657) and vlo below 40
+            // (the templates cover windows 0..4 x the first two groups); zs < 0 would make the criteria non-monotone.
+            // Otherwise the step's pairs all go to pass B
+            const int g0 = min(vlo >> 3, 4), t0 = (vlo >> 2) - 2 * g0;
             bool alive = v;
-            if ((vhi >> 3) <= g0 + 3 && vhi <= q && zs >= 0.f) {
+            if (t0 <= 1 && vhi <= q && zs >= 0.f) {
                 const uint32_t gmask = aux_gmask(g0, vlo, vhi);
                 const uint4* rq = reinterpret_cast<const uint4*>(auxQ) + i;
                 const uint4* cq = reinterpret_cast<const uint4*>(auxQ) + kc;
                 const float e1 = (float)e[i], e2 = (float)e[kn];
                 const AuxTail ti = atail[i], tk = atail[kn];
-                uint32_t S[32], C2[32];
+                uint32_t S[HLLB_NV], C2[HLLB_NV];
 #pragma unroll
-                for (int x = 0; x < 32; ++x) { S[x] = 0; C2[x] = 0; }
+                for (int x = 0; x < HLLB_NV; ++x) { S[x] = 0; C2[x] = 0; }
                 int wp = 0;
 #pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
                     const int wend = seg == 0 ? cp.cp1 : (seg == 1 ? cp.cp2 : cp.nwp);
                     if (wend <= wp) continue;
-                    switch (g0) {
-                        case 0: aux_subset_accum<0>(rq, cq, np32, wp, wend, gmask, S, C2); break;
-                        case 1: aux_subset_accum<1>(rq, cq, np32, wp, wend, gmask, S, C2); break;
-                        case 2: aux_subset_accum<2>(rq, cq, np32, wp, wend, gmask, S, C2); break;
-                        case 3: aux_subset_accum<3>(rq, cq, np32, wp, wend, gmask, S, C2); break;
-                        default: aux_subset_accum<4>(rq, cq, np32, wp, wend, gmask, S, C2); break;
+                    float z, zeros;
+                    switch (2 * g0 + t0) {
+                        case 0: aux_bound_segment<0, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 1: aux_bound_segment<0, 1>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 2: aux_bound_segment<1, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 3: aux_bound_segment<1, 1>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 4: aux_bound_segment<2, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 5: aux_bound_segment<2, 1>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 6: aux_bound_segment<3, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 7: aux_bound_segment<3, 1>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        case 8: aux_bound_segment<4, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
+                        default: aux_bound_segment<4, 1>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
                     }
                     steps += (uint32_t)(wend - wp);
                     wp = wend;
-                    float z, zeros;
-                    aux_window_sums(S, C2, g0, z, zeros);
                     if (seg == 0) { z += fminf(ti.z1, tk.z1); zeros += fminf(ti.c1, tk.c1); }
                     else if (seg == 1) { z += fminf(ti.z2, tk.z2); zeros += fminf(ti.c2, tk.c2); }
                     alive = alive && !selb::hll_surely_fails(AN, tau, zs, order_n, m_f, e1, e2, z, zeros);

@@ -33,7 +33,7 @@ template <class T> static void wr(FILE* f, const T* p, size_t n) { if (fwrite(p,
 // window) against the byte-wise definition hist[max(a[j], b[j])]++ on random sketch pairs
 static int hist_check(uint64_t seed, int count) {
     std::mt19937_64 rng(seed);
-    int bad = 0, done = 0;
+    int bad = 0, done = 0, bound_done = 0;
     for (int it = 0; it < count; ++it) {
         const int p_aux = 6 + (int)(rng() % 7);                       // 6 .. 12
         const int m = 1 << p_aux, nw = m >> 5, nbins = 64 - p_aux + 2;
@@ -71,7 +71,37 @@ static int hist_check(uint64_t seed, int count) {
             for (int t = 0; t < 8; ++t) if (2 * g0 + t >= (klo >> 2) && 2 * g0 + t <= (khi >> 2)) gmask |= 1u << t;
             std::vector<uint32_t> hcol((size_t)64 * 64, 0xDEADBEEFu);
             aux_plane_hist_g(g0, Q.data(), Q.data() + 4, npad, nw, gmask, hcol.data(), nbins);
-            // the fp32 sums pass A bounds the estimate with, from the same state
+            // pass A's sums from its twelve-value state: an upper bound of the union's harmonic sum (every register it does
+            // not count charged the first uncounted value), the empty count exact
+            const int t0 = (klo >> 2) - 2 * g0;
+            if (t0 <= 1) {
+                uint32_t S[HLLB_NV] = {0}, C2[HLLB_NV] = {0};
+                float zb = -1.f, cb = -1.f;
+                const uint4* q4 = reinterpret_cast<const uint4*>(Q.data());
+                switch (2 * g0 + t0) {
+                    case 0: aux_bound_segment<0, 0>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 1: aux_bound_segment<0, 1>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 2: aux_bound_segment<1, 0>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 3: aux_bound_segment<1, 1>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 4: aux_bound_segment<2, 0>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 5: aux_bound_segment<2, 1>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 6: aux_bound_segment<3, 0>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 7: aux_bound_segment<3, 1>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    case 8: aux_bound_segment<4, 0>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                    default: aux_bound_segment<4, 1>(q4, q4 + 1, (uint32_t)npad, 0, nw >> 1, gmask, S, C2, zb, cb); break;
+                }
+                double z_true = 0., z_cap = 0.;
+                const int vcap = 8 * g0 + 4 * t0 + HLLB_NV;
+                for (int v = 1; v < 64; ++v) {
+                    z_true += std::ldexp((double)want[v], -v);
+                    z_cap += std::ldexp((double)want[v], -std::min(v, vcap));
+                }
+                ++bound_done;
+                if (cb != (float)want[0] || !(zb >= z_true * (1 - 1e-6)) || !(zb <= z_cap * (1 + 1e-5))) {
+                    if (bad < 10) printf("bound-check %d p_aux=%d g0=%d t0=%d range %d..%d: z %g (true %g, capped %g) empty %g (true %u)\n", it, p_aux, g0, t0, klo, khi, zb, z_true, z_cap, cb, want[0]);
+                    ++bad;
+                }
+            }
             for (int v = 0; v < nbins; ++v)
                 if (hcol[(size_t)v * 64] != want[v]) {
                     if (bad < 10) printf("hist-check %d p_aux=%d g0=%d range %d..%d: bin %d is %u, want %u\n", it, p_aux, g0, klo, khi, v, hcol[(size_t)v * 64], want[v]);
@@ -80,7 +110,7 @@ static int hist_check(uint64_t seed, int count) {
         }
     }
     if (bad) printf("hist-check FAILED (%d bins of %d pairs)\n", bad, done);
-    else printf("hist-check: identical to the definition on %d pairs\n", done);
+    else printf("hist-check: identical to the definition on %d pairs, bound sums valid on %d\n", done, bound_done);
     return bad ? 1 : 0;
 }
 

@@ -187,6 +187,7 @@ def test_hll_plane_histograms(exe_hll):
     r = subprocess.run([exe_hll, "hist-check", "20261018", "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "hist-check: identical to the definition" in r.stdout
+    assert int(r.stdout.split("bound sums valid on ")[1].split()[0]) > 1000     # pass A's twelve-value sums: valid upper bounds
 
 
 _SMH_MUTATIONS = [
