@@ -722,7 +722,7 @@ def main():
                 # H2D of the slice piece by piece; each piece is all-gathered over NVLink and digested
                 # (validation, histograms, cardinalities, bit planes) while the next one is on the PCIe bus
                 sel2.load_device_begin(sh.regs, sh.aux, aux_kind)
-                sh.assemble(regs_h, aux_h, on_piece=sel2.load_device_rows)
+                sh.assemble(regs_h, aux_h, on_piece=sel2.load_device_rows, on_piece_packed=sel2.load_device_rows_packed)
                 sel2.load_end()
             t_b = time.perf_counter()              # load returns after its last device sync
             sel2.run(tau=tau32, criterion=cfg.criterion, shard=rank, n_shards=world, fetch=False, gather=(world > 1),

@@ -1,0 +1,111 @@
+// hostpack.cpp — see hostpack.h.  Plain g++ translation unit (AVX2 path behind a run-time CPU check).
+#include "hostpack.h"
+
+#include <algorithm>
+#include <cstring>
+#include <omp.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace selb {
+namespace {
+
+// one genome, portable form (also the tail of the vector form's exception handling)
+inline void pack_genome_scalar(const uint8_t* v, size_t m, uint8_t* nib, uint32_t* exc, Nib4Hdr* hdr) {
+    uint8_t base = 255;
+    for (size_t j = 0; j < m; ++j) base = std::min(base, v[j]);
+    uint32_t ne = 0;
+    for (size_t j = 0; j < m; j += 2) {
+        const unsigned d0 = std::min<unsigned>(v[j] - base, 15u), d1 = std::min<unsigned>(v[j + 1] - base, 15u);
+        nib[j >> 1] = (uint8_t)(d0 | (d1 << 4));
+        if (d0 == 15u) { if (ne < (uint32_t)NIB4_EXC_CAP) exc[ne] = ((uint32_t)j << 8) | v[j]; ++ne; }
+        if (d1 == 15u) { if (ne < (uint32_t)NIB4_EXC_CAP) exc[ne] = ((uint32_t)(j + 1) << 8) | v[j + 1]; ++ne; }
+    }
+    hdr->base = base;
+    hdr->raw = ne > (uint32_t)NIB4_EXC_CAP;
+    hdr->n_exc = (uint16_t)std::min<uint32_t>(ne, NIB4_EXC_CAP);
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void pack_genome_avx2(const uint8_t* v, size_t m, uint8_t* nib, uint32_t* exc, Nib4Hdr* hdr) {
+    __m256i mn = _mm256_set1_epi8((char)0xff);
+    for (size_t j = 0; j < m; j += 64) {
+        mn = _mm256_min_epu8(mn, _mm256_loadu_si256((const __m256i*)(v + j)));
+        mn = _mm256_min_epu8(mn, _mm256_loadu_si256((const __m256i*)(v + j + 32)));
+    }
+    alignas(32) uint8_t lanes[32];
+    _mm256_store_si256((__m256i*)lanes, mn);
+    uint8_t base = 255;
+    for (int i = 0; i < 32; ++i) base = std::min(base, lanes[i]);
+    const __m256i vb = _mm256_set1_epi8((char)base), v15 = _mm256_set1_epi8(15), mul = _mm256_set1_epi16(0x1001);
+    uint32_t ne = 0;
+    for (size_t j = 0; j < m; j += 64) {
+        const __m256i a = _mm256_loadu_si256((const __m256i*)(v + j)), b = _mm256_loadu_si256((const __m256i*)(v + j + 32));
+        const __m256i da = _mm256_min_epu8(_mm256_sub_epi8(a, vb), v15), db = _mm256_min_epu8(_mm256_sub_epi8(b, vb), v15);
+        // byte pair (n0, n1) -> n0 + 16 n1 in a 16-bit lane, then the low bytes of the 16 + 16 lanes in register order
+        const __m256i pa = _mm256_maddubs_epi16(da, mul), pb = _mm256_maddubs_epi16(db, mul);
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi16(pa, pb), 0xD8);
+        _mm256_storeu_si256((__m256i*)(nib + (j >> 1)), pk);
+        const uint32_t ea = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(da, v15));
+        const uint32_t eb = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(db, v15));
+        uint64_t e = (uint64_t)ea | ((uint64_t)eb << 32);
+        while (e) {
+            const int t = __builtin_ctzll(e);
+            e &= e - 1;
+            if (ne < (uint32_t)NIB4_EXC_CAP) exc[ne] = ((uint32_t)(j + (size_t)t) << 8) | v[j + (size_t)t];
+            ++ne;
+        }
+    }
+    hdr->base = base;
+    hdr->raw = ne > (uint32_t)NIB4_EXC_CAP;
+    hdr->n_exc = (uint16_t)std::min<uint32_t>(ne, NIB4_EXC_CAP);
+}
+bool have_avx2() {
+    static const bool ok = __builtin_cpu_supports("avx2");
+    return ok;
+}
+#else
+bool have_avx2() { return false; }
+#endif
+
+}  // namespace
+
+const char* nib4_impl() { return have_avx2() ? "avx2" : "scalar"; }
+
+int64_t nib4_pack(const uint8_t* regs, int64_t rows, size_t m, uint8_t* nib, uint32_t* exc, Nib4Hdr* hdr, int threads) {
+    int64_t n_raw = 0;
+    const bool vec = have_avx2();
+    const int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nt) reduction(+ : n_raw)
+    for (int64_t g = 0; g < rows; ++g) {
+        const uint8_t* v = regs + (size_t)g * m;
+#if defined(__x86_64__)
+        if (vec) pack_genome_avx2(v, m, nib + (size_t)g * (m >> 1), exc + (size_t)g * NIB4_EXC_CAP, hdr + g);
+        else
+#endif
+            pack_genome_scalar(v, m, nib + (size_t)g * (m >> 1), exc + (size_t)g * NIB4_EXC_CAP, hdr + g);
+        n_raw += hdr[g].raw;
+    }
+    return n_raw;
+}
+
+int64_t nib4_pack_piece(const uint8_t* regs, int64_t rows, size_t m, uint8_t* piece, int threads) {
+    const Nib4Piece L = nib4_piece(rows, m);
+    Nib4Hdr* hdr = reinterpret_cast<Nib4Hdr*>(piece + L.off_hdr);
+    int32_t* raw_idx = reinterpret_cast<int32_t*>(piece + L.off_rawidx);
+    const int64_t n_raw = nib4_pack(regs, rows, m, piece + L.off_nib, reinterpret_cast<uint32_t*>(piece + L.off_exc), hdr, threads);
+    for (int r = 0; r < 64; ++r) raw_idx[r] = -1;            // the whole 256-byte block
+    if (n_raw) {
+        int slot = 0;
+        for (int64_t g = 0; g < rows && slot < NIB4_RAW_CAP; ++g)
+            if (hdr[g].raw) {
+                raw_idx[slot] = (int32_t)g;
+                std::memcpy(piece + L.off_raw + (size_t)slot * m, regs + (size_t)g * m, m);
+                ++slot;
+            }
+    }
+    return n_raw;
+}
+
+}  // namespace selb

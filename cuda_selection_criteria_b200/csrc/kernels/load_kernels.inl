@@ -12,6 +12,61 @@ __global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data
     for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
     if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
 }
+// ============================================================================
+// packed upload (hostpack.h): nibbles + per-genome base -> register bytes, then the exceptions.
+// A thread turns 8 bytes of nibbles into 16 register bytes (one 128-bit store); raw genomes are skipped, their bytes
+// arrive by a copy of their own.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_unpack_nib4(const uint2* __restrict__ nib, const selb::Nib4Hdr* __restrict__ hdr, long long rows, int log2_m,
+              uint4* __restrict__ regs) {
+    const int per_row = 1 << (log2_m - 4);                         // 16-register groups per genome
+    const long long total = rows << (log2_m - 4);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long g = idx >> (log2_m - 4);
+        const selb::Nib4Hdr h = hdr[g];
+        if (h.raw) continue;
+        const uint2 v = __ldg(nib + idx);
+        const uint32_t b4 = 0x01010101u * h.base;                  // value - base <= 15 and values < 128: no carry between bytes
+        uint4 o;
+        // bytes n0 | n1<<4 -> n0, n1: the even nibbles of a word are its low nibbles, the odd ones its high nibbles
+        const uint32_t lo0 = v.x & 0x0f0f0f0fu, hi0 = (v.x >> 4) & 0x0f0f0f0fu;
+        const uint32_t lo1 = v.y & 0x0f0f0f0fu, hi1 = (v.y >> 4) & 0x0f0f0f0fu;
+        o.x = __byte_perm(lo0, hi0, 0x5140) + b4;                  // n0 n1 n2 n3 of byte 0, 1
+        o.y = __byte_perm(lo0, hi0, 0x7362) + b4;                  // of byte 2, 3
+        o.z = __byte_perm(lo1, hi1, 0x5140) + b4;
+        o.w = __byte_perm(lo1, hi1, 0x7362) + b4;
+        regs[idx] = o;
+        (void)per_row;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_apply_nib4_exc(const uint32_t* __restrict__ exc, const selb::Nib4Hdr* __restrict__ hdr, long long rows, int log2_m,
+                 uint8_t* __restrict__ regs) {
+    const long long total = rows * selb::NIB4_EXC_CAP;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long g = idx / selb::NIB4_EXC_CAP;
+        const int e = (int)(idx - g * selb::NIB4_EXC_CAP);
+        const selb::Nib4Hdr h = hdr[g];
+        if (h.raw || e >= (int)h.n_exc) continue;
+        const uint32_t x = exc[idx];
+        regs[((size_t)g << log2_m) + (x >> 8)] = (uint8_t)(x & 0xffu);
+    }
+}
+
+// raw genomes of a piece: slot r of the raw area -> row raw_idx[r]
+__global__ void __launch_bounds__(256)
+k_apply_nib4_raw(const uint4* __restrict__ raw, const int32_t* __restrict__ raw_idx, int log2_m, uint4* __restrict__ regs) {
+    const int r = blockIdx.y;
+    const int g = raw_idx[r];
+    if (g < 0) return;
+    const int n16 = 1 << (log2_m - 4);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        regs[((size_t)g << (log2_m - 4)) + i] = raw[((size_t)r << (log2_m - 4)) + i];
+}
+
 __global__ void k_iota_i32(int32_t* v, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) v[i] = (int32_t)i;

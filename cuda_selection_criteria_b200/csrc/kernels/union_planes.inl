@@ -95,12 +95,39 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 }
 #endif   // SELB_EMUL
 
+// Experiment switches of the subset form (A/B builds, `make variants`):
+//   PL_PACK_C2   the 32 carry counters of a lane in 16 registers (two 16-bit halves: a lane sees at most m/32 registers
+//                of a pair, so a carry count stays below 2^15 up to p = 20): frees 16 registers
+//   PL_UNROLL    the steps of a full chunk straight-line instead of a loop
+#ifndef PL_PACK_C2
+#define PL_PACK_C2 0
+#endif
+#ifndef PL_UNROLL
+#define PL_UNROLL 0
+#endif
+constexpr int PL_NC2 = PL_PACK_C2 ? 16 : 32;
+__device__ __forceinline__ void c2_add(uint32_t (&C2)[PL_NC2], int v, uint32_t cnt) {
+#if PL_PACK_C2
+    if (v < 16) C2[v] += cnt;
+    else C2[v - 16] = cnt * 65536u + C2[v - 16];
+#else
+    C2[v] += cnt;
+#endif
+}
+__device__ __forceinline__ uint32_t c2_get(const uint32_t (&C2)[PL_NC2], int v) {
+#if PL_PACK_C2
+    return v < 16 ? (C2[v] & 0xffffu) : (C2[v - 16] >> 16);
+#else
+    return C2[v];
+#endif
+}
+
 // One chunk (<= PL_CHUNK_REGS registers) against the running carry-save state.  Per step, lane q holds
 // two consecutive words of every plane (LDS.64).  Written stage by stage over the 8 values of a group so
 // that eight independent dependency chains are in flight (LOP3 latency 4 at one issue per 2 clocks).
 template <int G0, int NQ>   // NQ > 0: uint2 per plane known at compile time (full 2048-register chunks)
 __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
-                                            int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
+                                            int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[PL_NC2]) {
     const int nq = NQ > 0 ? NQ : nq_rt;
     // nq = uint2 (2 x 32 registers) per plane; plane b of genome X at sX + b*nq.
     // Window 0 holds values below 32 only: plane 5 is all zero there and is neither copied nor read.
@@ -148,7 +175,7 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
                 _Pragma("unroll") for (int j = 0; j < 8; ++j) { m0[j] = H0 & L[0][j]; m1[j] = H1 & L[1][j]; } \
                 _Pragma("unroll") for (int j = 0; j < 8; ++j) kk[j] = lop3<0xE8>(S[T * 8 + j], m0[j], m1[j]); \
                 _Pragma("unroll") for (int j = 0; j < 8; ++j) S[T * 8 + j] = lop3<0x96>(S[T * 8 + j], m0[j], m1[j]); \
-                _Pragma("unroll") for (int j = 0; j < 8; ++j) C2[T * 8 + j] += __popc(kk[j]);             \
+                _Pragma("unroll") for (int j = 0; j < 8; ++j) c2_add(C2, T * 8 + j, (uint32_t)__popc(kk[j])); \
             }                                                                                             \
         }
         SELB_PLANE_GROUP(0, false)
@@ -172,10 +199,14 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
 // gmask: bit t = the group of values 8*G0 + 4t .. 8*G0 + 4t + 3 lies inside the pair's range (warp-uniform).
 template <int G0, int NQ>
 __device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
-                                                    int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[32]) {
+                                                    int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[PL_NC2]) {
     const int nq = NQ > 0 ? NQ : nq_rt;
     constexpr int NP = (G0 == 0) ? 5 : 6;
+#if PL_UNROLL
+#pragma unroll (NQ > 0 ? NQ / 32 : 1)
+#else
 #pragma unroll 1
+#endif
     for (int q = lane; q < nq; q += 32) {
         uint32_t M[2][6];
         {
@@ -208,7 +239,7 @@ __device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA
             m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                     \
             _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);    \
             _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) C2[c0 + j] += __popc(kk[j]);                    \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) c2_add(C2, c0 + j, (uint32_t)__popc(kk[j]));    \
         }
 #define SELB_SUBSET_GROUP8(T8)                                                                            \
         if (gmask & (3u << (2 * T8))) {                                                                   \
@@ -390,9 +421,11 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         ++n_issued;
         if (++prod.ch >= nchunks) next_pair(prod, false);
     }
-    uint32_t S[32], C2[32];
+    uint32_t S[32], C2[PL_NC2];
 #pragma unroll
-    for (int v = 0; v < 32; ++v) { S[v] = 0; C2[v] = 0; }
+    for (int v = 0; v < 32; ++v) S[v] = 0;
+#pragma unroll
+    for (int v = 0; v < PL_NC2; ++v) C2[v] = 0;
     while (cons.valid) {
         __syncwarp();                          // every lane has finished reading the stage about to be refilled
         if (!prod.valid && !prod.done) next_pair(prod, false);
@@ -456,7 +489,9 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             // per-lane totals, then a transposing butterfly: lane L ends with the warp total of value 8*g0 + L
             uint32_t x[32];
 #pragma unroll
-            for (int v = 0; v < 32; ++v) { x[v] = 2u * C2[v] + (uint32_t)__popc(S[v]); S[v] = 0; C2[v] = 0; }
+            for (int v = 0; v < 32; ++v) { x[v] = 2u * c2_get(C2, v) + (uint32_t)__popc(S[v]); S[v] = 0; }
+#pragma unroll
+            for (int v = 0; v < PL_NC2; ++v) C2[v] = 0;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
                 const bool upper = (lane & o) != 0;

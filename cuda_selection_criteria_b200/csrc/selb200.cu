@@ -43,6 +43,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "estimators.cuh"
+#include "hostpack.h"
 
 // ============================================================================
 // error plumbing
@@ -154,6 +155,13 @@ struct StageSlot {            // pinned host staging of one chunk
     bool in_flight = false;
 };
 
+struct PackSlot {             // pinned host staging of one packed piece (hostpack.h)
+    uint8_t* buf = nullptr;
+    size_t cap = 0;
+    cudaEvent_t free_ev = nullptr;    // recorded on the copy stream after the slot's H2D copy
+    bool in_flight = false;
+};
+
 struct selb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -188,6 +196,8 @@ struct selb200_ctx {
     int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
     int64_t near_cap = 1 << 16;                   // near-tau list: grown (and the pass redone) when a run overflows it
     LoadState ld;
+    PackSlot pack_slots[4];
+    DevBuf pk_buf;                       // packed pieces as they land on the device, before k_unpack_nib4
     StageSlot slots[3];
     int next_slot = 0;
     bool _order_cache_valid = false;
@@ -604,12 +614,109 @@ int load_end(selb200_ctx* c) {
     return SELB200_OK;
 }
 
+// SELB200_H2D=raw: registers cross PCIe as the bytes they are (A/B measurements); default: packed (hostpack.h)
+bool h2d_packed() {
+    static const bool on = [] { const char* e = getenv("SELB200_H2D"); return !(e && !strcmp(e, "raw")); }();
+    return on;
+}
+// threads of the host packer: SELB200_PACK_THREADS, else the machine's hardware threads shared among the processes of
+// this node (LOCAL_WORLD_SIZE, as torchrun exports it; torchrun also pins OMP_NUM_THREADS to 1, which is why the OpenMP
+// default is not used here)
+int pack_threads() {
+    static const int nt = [] {
+        if (const char* e = getenv("SELB200_PACK_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 256); }
+        long hw = sysconf(_SC_NPROCESSORS_ONLN);
+        if (hw < 1) hw = 1;
+        int local = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
+        return (int)std::max<long>(1, std::min<long>(hw / local, 64));
+    }();
+    return nt;
+}
+
+// a packed piece that sits in device memory -> rows [g0, g0 + rows) of the byte matrix `regs` (run stream)
+int unpack_piece(selb200_ctx* c, const uint8_t* d_piece, int64_t rows, bool maybe_raw, uint8_t* regs_rows) {
+    const selb::Nib4Piece P = selb::nib4_piece(rows, c->m);
+    const selb::Nib4Hdr* hdr = reinterpret_cast<const selb::Nib4Hdr*>(d_piece + P.off_hdr);
+    const long long n16 = (long long)rows * (long long)(c->m >> 4);
+    k_unpack_nib4<<<(int)std::min<long long>((n16 + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+        reinterpret_cast<const uint2*>(d_piece + P.off_nib), hdr, rows, c->p, reinterpret_cast<uint4*>(regs_rows));
+    CK(cudaGetLastError());
+    const long long ne = (long long)rows * selb::NIB4_EXC_CAP;
+    k_apply_nib4_exc<<<(int)std::min<long long>((ne + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
+        reinterpret_cast<const uint32_t*>(d_piece + P.off_exc), hdr, rows, c->p, regs_rows);
+    CK(cudaGetLastError());
+    if (maybe_raw) {
+        k_apply_nib4_raw<<<dim3(4, selb::NIB4_RAW_CAP), 256, 0, c->stream>>>(
+            reinterpret_cast<const uint4*>(d_piece + P.off_raw), reinterpret_cast<const int32_t*>(d_piece + P.off_rawidx), c->p,
+            reinterpret_cast<uint4*>(regs_rows));
+        CK(cudaGetLastError());
+    }
+    return SELB200_OK;
+}
+
+// host registers -> device in packed form: 16 MiB of registers at a time are packed by the host threads into one of four
+// pinned slots and copied (half the bytes) while the next piece is being packed; the run stream unpacks each piece as it
+// lands and, every rows_per_chunk rows, digests what is there like any other chunk
+int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const double* stored, const void* aux) {
+    LoadState& L = c->ld;
+    const size_t m = c->m;
+    const int64_t pk_rows = std::max<int64_t>(1, (int64_t)(16u << 20) / (int64_t)m);
+    const selb::Nib4Piece P = selb::nib4_piece(pk_rows, m);
+    const int64_t n_pieces = (n + pk_rows - 1) / pk_rows;
+    CKR(c->pk_buf.ensure((size_t)n_pieces * P.bytes));
+    for (PackSlot& ps : c->pack_slots) {
+        if (ps.cap < P.bytes) {
+            if (ps.buf) cudaFreeHost(ps.buf);
+            ps.buf = nullptr;
+            ps.cap = 0;
+            CK(cudaMallocHost(&ps.buf, P.bytes));
+            ps.cap = P.bytes;
+        }
+        if (!ps.free_ev) CK(cudaEventCreateWithFlags(&ps.free_ev, cudaEventDisableTiming));
+    }
+    const int nt = pack_threads();
+    int slot_i = 0;
+    int64_t group0 = 0;                       // first row not yet digested
+    for (int64_t g0 = 0; g0 < n; g0 += pk_rows) {
+        const int64_t rows = std::min(pk_rows, n - g0);
+        const selb::Nib4Piece Q = selb::nib4_piece(rows, m);          // the last piece may be shorter
+        PackSlot& ps = c->pack_slots[slot_i];
+        slot_i = (slot_i + 1) & 3;
+        if (ps.in_flight) { CK(cudaEventSynchronize(ps.free_ev)); ps.in_flight = false; }
+        const int64_t n_raw = selb::nib4_pack_piece(regs + (size_t)g0 * m, rows, m, ps.buf, nt);
+        uint8_t* d_piece = c->pk_buf.as<uint8_t>() + (size_t)(g0 / pk_rows) * P.bytes;
+        uint8_t* d_rows = c->regs_own.as<uint8_t>() + (size_t)g0 * m;
+        if (n_raw > selb::NIB4_RAW_CAP) {     // not the registers of HLLs of real sets: the piece travels as it is
+            CK(cudaMemcpyAsync(d_rows, regs + (size_t)g0 * m, (size_t)rows * m, cudaMemcpyHostToDevice, c->copy_stream));
+            CKR(load_join_copies(c));
+        } else {
+            CK(cudaMemcpyAsync(d_piece, ps.buf, Q.off_raw + (size_t)n_raw * m, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(ps.free_ev, c->copy_stream));
+            ps.in_flight = true;
+            CKR(load_join_copies(c));
+            CKR(unpack_piece(c, d_piece, rows, n_raw > 0, d_rows));
+        }
+        const int64_t done = g0 + rows;
+        if (done - group0 >= L.rows_per_chunk || done == n) {
+            CKR(load_chunk(c, group0, done - group0, nullptr, stored ? stored + group0 : nullptr,
+                           aux ? (const uint8_t*)aux + (size_t)group0 * L.aux_row_bytes : nullptr));
+            group0 = done;
+        }
+    }
+    return SELB200_OK;
+}
+
 int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool on_device, const double* stored,
             int aux_kind, int aux_len, const void* aux) {
     if (n > 0 && !regs) return fail(SELB200_EINVAL, "null register matrix");
     if (aux_kind != SELB200_AUX_NONE && n > 0 && !aux) return fail(SELB200_EINVAL, "null aux matrix");
     CKR(load_begin(c, n, p, aux_kind, aux_len, on_device ? regs : nullptr, on_device ? aux : nullptr));
     LoadState& L = c->ld;
+    if (!on_device && h2d_packed() && n > 0) {
+        CKR(load_host_packed(c, n, regs, stored, aux));
+        return load_end(c);
+    }
     const int64_t step = on_device ? std::max<int64_t>(n, 1) : L.rows_per_chunk;
     for (int64_t g0 = 0; g0 < n; g0 += step) {
         const int64_t rows = std::min(step, n - g0);
@@ -678,13 +785,17 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    for (PackSlot& ps : c->pack_slots) {
+        if (ps.buf) cudaFreeHost(ps.buf);
+        if (ps.free_ev) cudaEventDestroy(ps.free_ev);
+    }
     for (StageSlot& sl : c->slots) {
         if (sl.regs) cudaFreeHost(sl.regs);
         if (sl.aux) cudaFreeHost(sl.aux);
@@ -712,6 +823,27 @@ int selb200_load_device_begin(selb200_ctx* ctx, int64_t n, int p, const uint8_t*
     if (n > 0 && !d_regs) return fail(SELB200_EINVAL, "null register matrix");
     if (aux_kind != SELB200_AUX_NONE && n > 0 && !d_aux) return fail(SELB200_EINVAL, "null aux matrix");
     return load_begin(ctx, n, p, aux_kind, aux_len, d_regs, d_aux);
+}
+
+int64_t selb200_nib4_piece_bytes(int64_t rows, int p) {
+    if (rows < 0 || p < 9 || p > 20) { fail(SELB200_EINVAL, "nib4 piece: rows=%lld p=%d", (long long)rows, p); return -1; }
+    return (int64_t)selb::nib4_piece(rows, (size_t)1 << p).bytes;
+}
+
+int64_t selb200_nib4_pack_piece(const uint8_t* regs, int64_t rows, int p, uint8_t* piece, int threads) {
+    if (rows < 0 || p < 9 || p > 20 || (rows && (!regs || !piece))) { fail(SELB200_EINVAL, "nib4 pack: bad arguments"); return -1; }
+    return selb::nib4_pack_piece(regs, rows, (size_t)1 << p, piece, threads > 0 ? threads : pack_threads());
+}
+
+// rows [g0, g0+count) arrive as a packed piece in device memory (selb200_nib4_pack_piece on some host, then any copy or
+// collective): unpacked INTO the matrix given to selb200_load_device_begin, then digested like selb200_load_device_rows
+int selb200_load_device_rows_packed(selb200_ctx* c, int64_t g0, int64_t count, const uint8_t* d_piece) {
+    if (!c || !c->ld.active || !c->ld.regs_borrowed) return fail(SELB200_ESTATE, "selb200_load_device_rows_packed outside load_device_begin/load_end");
+    if (g0 < 0 || count < 0 || g0 + count > c->n) return fail(SELB200_EINVAL, "rows [%lld,+%lld) outside the matrix", (long long)g0, (long long)count);
+    if (count && !d_piece) return fail(SELB200_EINVAL, "null piece");
+    CK(cudaSetDevice(c->device));
+    if (count) CKR(unpack_piece(c, d_piece, count, true, const_cast<uint8_t*>(c->d_regs) + (size_t)g0 * c->m));
+    return load_chunk(c, g0, count, nullptr, nullptr, nullptr);
 }
 
 int selb200_load_device_rows(selb200_ctx* c, int64_t g0, int64_t count) {

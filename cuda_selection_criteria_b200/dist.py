@@ -13,9 +13,13 @@ and "gloo" (CPU tensors; used by the world_size-2 CPU tests of this plumbing).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 class _DevView:
@@ -83,35 +87,78 @@ class ShardedSketches:
         lo = c * self.world * self.rpc
         return t[lo:lo + self.world * self.rpc], t[lo + self.rank * self.rpc:lo + (self.rank + 1) * self.rpc]
 
-    def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None, on_piece=None):
+    def _packed_buffers(self, m: int):
+        """Pinned host staging and device landing zones of the packed pieces (include/selb200.h, "Packed transport"):
+        [piece][rank][piece_bytes] on the device, so that one all-gather per piece moves every rank's rows."""
+        if getattr(self, "_pk_dev", None) is None:
+            L = _lib.lib()
+            self._p = m.bit_length() - 1
+            pb = int(L.selb200_nib4_piece_bytes(self.rpc, self._p))
+            if pb <= 0:
+                raise _lib.SelB200Error(L.selb200_last_error().decode())
+            self._pk_dev = torch.empty((self.chunks, self.world, pb), dtype=torch.uint8, device=self.regs.device)
+            self._pk_host = [torch.empty(pb, dtype=torch.uint8, pin_memory=True) for _ in range(self.chunks)]
+            self._pad = torch.zeros((self.rpc, m), dtype=torch.uint8)
+        return self._pk_dev, self._pk_host
+
+    def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None, on_piece=None, on_piece_packed=None):
         """on_piece(row0, rows): called after the all-gather of each piece has been queued on the current
-        stream (e.g. Selection.load_device_rows, so that the piece is digested while the next one travels)."""
+        stream (e.g. Selection.load_device_rows, so that the piece is digested while the next one travels).
+
+        With on_piece_packed (e.g. Selection.load_device_rows_packed) the register rows travel PACKED — half the
+        bytes over PCIe and over NVLink: every piece is packed by this rank's host threads into pinned memory, copied,
+        all-gathered as bytes, and on_piece_packed(row0, rows, piece) is called for each rank's part, which unpacks
+        it into `self.regs` and digests it.  SELB200_H2D=raw keeps the unpacked route."""
         cuda = self._copy_stream is not None
-        events = []
+        packed = cuda and on_piece_packed is not None and os.environ.get("SELB200_H2D") != "raw"
         if cuda:
             self._copy_stream.wait_stream(torch.cuda.current_stream())   # earlier readers of the matrices are done
+        if packed:
+            pk_dev, pk_host = self._packed_buffers(int(regs_host.shape[1]))
+            L = _lib.lib()
         for c in range(self.chunks):
             h0, h1 = min(self.rows, c * self.rpc), min(self.rows, (c + 1) * self.rpc)
+            if packed:
+                if h1 - h0 == self.rpc:
+                    src = regs_host[h0:h1]
+                else:                       # the slice ends inside this piece: the rest are all-zero sketches
+                    self._pad.zero_()
+                    if h1 > h0:
+                        self._pad[:h1 - h0].copy_(regs_host[h0:h1])
+                    src = self._pad
+                n_raw = int(L.selb200_nib4_pack_piece(src.data_ptr(), self.rpc, self._p, pk_host[c].data_ptr(), 0))
+                if n_raw < 0:
+                    raise _lib.SelB200Error(L.selb200_last_error().decode())
+                if n_raw > 4:
+                    raise _lib.SelB200Error(f"{n_raw} rows of a piece do not look like HLL sketches (more than 32 registers far "
+                                            "above the smallest): set SELB200_H2D=raw to move the registers unpacked")
             ctx = torch.cuda.stream(self._copy_stream) if cuda else _Null()
             with ctx:
-                if h1 > h0:
+                if packed:
+                    pk_dev[c, self.rank].copy_(pk_host[c], non_blocking=True)
+                elif h1 > h0:
                     self._piece(self.regs, c)[1][:h1 - h0].copy_(regs_host[h0:h1], non_blocking=True)
-                    if self.aux is not None:
-                        self._piece(self.aux, c)[1][:h1 - h0].copy_(aux_host[h0:h1], non_blocking=True)
+                if h1 > h0 and self.aux is not None:
+                    self._piece(self.aux, c)[1][:h1 - h0].copy_(aux_host[h0:h1], non_blocking=True)
                 if cuda:
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
-                    events.append(ev)
-        for c in range(self.chunks):
+            # queued behind the copy on the current stream: the host goes on to pack the next piece meanwhile
             if cuda:
-                torch.cuda.current_stream().wait_event(events[c])
+                torch.cuda.current_stream().wait_event(ev)
             if self.world > 1:
-                whole, mine = self._piece(self.regs, c)
-                dist.all_gather_into_tensor(whole, mine)
+                if packed:
+                    dist.all_gather_into_tensor(pk_dev[c].view(-1), pk_dev[c, self.rank])
+                else:
+                    whole, mine = self._piece(self.regs, c)
+                    dist.all_gather_into_tensor(whole, mine)
                 if self.aux is not None:
                     whole, mine = self._piece(self.aux, c)
                     dist.all_gather_into_tensor(whole, mine)
-            if on_piece is not None:
+            if packed:
+                for r in range(self.world):
+                    on_piece_packed((c * self.world + r) * self.rpc, self.rpc, pk_dev[c, r])
+            elif on_piece is not None:
                 on_piece(c * self.world * self.rpc, self.world * self.rpc)
         return self.regs, self.aux
 

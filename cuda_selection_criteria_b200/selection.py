@@ -137,6 +137,11 @@ class Selection:
     def load_device_rows(self, g0: int, count: int):
         _lib.check(self._L.selb200_load_device_rows(self._h, int(g0), int(count)))
 
+    def load_device_rows_packed(self, g0: int, count: int, piece):
+        """Rows [g0, g0+count) arrived as a packed piece (selb200_nib4_pack_piece) in device memory: `piece` is a CUDA
+        uint8 tensor holding it.  They are unpacked into the matrix given to load_device_begin, then digested."""
+        _lib.check(self._L.selb200_load_device_rows_packed(self._h, int(g0), int(count), piece.data_ptr()))
+
     def load_end(self):
         _lib.check(self._L.selb200_load_end(self._h))
         self._order = None

@@ -157,6 +157,23 @@ int selb200_load_device_begin(selb200_ctx* ctx, int64_t n, int p, const uint8_t*
                               const void* d_aux);
 int selb200_load_device_rows(selb200_ctx* ctx, int64_t g0, int64_t count);
 
+/* Packed transport of register rows (csrc/hostpack.h).  HLL registers of one sketch sit in a narrow band above the
+ * smallest one, so a row crosses PCIe / NVLink as one base byte + 4-bit offsets + a short exception list: 0.51 of its
+ * bytes.  selb200_load_host packs, copies and unpacks internally (SELB200_H2D=raw turns that off); these three entry
+ * points expose the same pieces to a caller that moves the bytes itself (cuda_selection_criteria_b200/dist.py: per-rank
+ * slices, H2D + NCCL all-gather of the packed pieces):
+ *   piece_bytes : size of the buffer holding `rows` packed rows
+ *   pack_piece  : host rows -> piece (threads <= 0: hardware threads / LOCAL_WORLD_SIZE, or SELB200_PACK_THREADS).
+ *                 Returns the number of rows that had to be kept as raw bytes (more than 32 registers 15 or more above
+ *                 the row's smallest): up to 4 of them travel inside the piece, a return value > 4 means the piece
+ *                 cannot be used (send those rows raw); negative = error
+ *   load_device_rows_packed : like selb200_load_device_rows, for rows that arrived as a piece in device memory; the
+ *                 rows are unpacked INTO the matrix given to selb200_load_device_begin (which must be writable)
+ * Unpacking reproduces the bytes exactly: nothing downstream can depend on the transport. */
+int64_t selb200_nib4_piece_bytes(int64_t rows, int p);
+int64_t selb200_nib4_pack_piece(const uint8_t* regs, int64_t rows, int p, uint8_t* piece, int threads);
+int selb200_load_device_rows_packed(selb200_ctx* ctx, int64_t g0, int64_t count, const uint8_t* d_piece);
+
 /* After a load: cards_sorted[i] = cardinality (double) of the i-th genome in sorted
  * order; order[i] = its index in file-list order.  Either pointer may be NULL. */
 int selb200_get_order(selb200_ctx* ctx, double* cards_sorted, int32_t* order);
