@@ -74,24 +74,28 @@ def test_sharded_assemble_packed_world_of_one(gpu, chunks):
     dev = torch.device("cuda", gpu)
     regs_h = torch.from_numpy(regs).pin_memory()
     aux_h = torch.from_numpy(aux.view(np.int64)).pin_memory()
-    sh = sdist.ShardedSketches(n, regs.shape[1], aux.shape[1], torch.int64, dev, 0, 1, chunks=chunks)
-    with S.Selection(gpu) as a, S.Selection(gpu) as b:
-        a.load_device_begin(sh.regs, sh.aux, AUX_SMH)
-        calls = []
-        sh.assemble(regs_h, aux_h, on_piece=a.load_device_rows,
-                    on_piece_packed=lambda g0, cnt, piece: (calls.append((g0, cnt)), a.load_device_rows_packed(g0, cnt, piece)))
-        a.load_end()
-        assert len(calls) == chunks and sum(c for _, c in calls) == sh.n_dev
-        # the device matrix holds the host rows again (padding rows: all zero)
-        got = sh.regs.cpu().numpy()
-        keep = sh.row_to_file >= 0
-        assert np.array_equal(got[keep], regs[sh.row_to_file[keep]]) and not got[~keep].any()
-        b.load(regs, aux, AUX_SMH)
-        ra = a.run(tau=np.float32(0.85), criterion="smh_a")
-        rb = b.run(tau=np.float32(0.85), criterion="smh_a")
-        # padding rows shift sorted positions: compare in file indices
-        fa = np.sort(np.stack([sh.row_to_file[a.order()[1][ra.i]], sh.row_to_file[a.order()[1][ra.k]]], 1), axis=1)
-        fb = np.sort(np.stack([b.order()[1][rb.i], b.order()[1][rb.k]], 1), axis=1)
-        ka = np.lexsort((fa[:, 1], fa[:, 0]))
-        kb = np.lexsort((fb[:, 1], fb[:, 0]))
-        assert rb.i.size > 100 and np.array_equal(fa[ka], fb[kb]) and np.array_equal(ra.jaccard[ka], rb.jaccard[kb])
+    # one explicit stream for the torch copies and the library's kernels: load_device_rows(_packed) declares rows complete
+    # in the order of the CONTEXT's stream, so the context must run on the stream the copies are queued behind
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        sh = sdist.ShardedSketches(n, regs.shape[1], aux.shape[1], torch.int64, dev, 0, 1, chunks=chunks)
+        with S.Selection(gpu, stream=st.cuda_stream) as a, S.Selection(gpu) as b:
+            a.load_device_begin(sh.regs, sh.aux, AUX_SMH)
+            calls = []
+            sh.assemble(regs_h, aux_h, on_piece=a.load_device_rows,
+                        on_piece_packed=lambda g0, cnt, piece: (calls.append((g0, cnt)), a.load_device_rows_packed(g0, cnt, piece)))
+            a.load_end()
+            assert len(calls) == chunks and sum(c for _, c in calls) == sh.n_dev
+            # the device matrix holds the host rows again (padding rows: all zero)
+            got = sh.regs.cpu().numpy()
+            keep = sh.row_to_file >= 0
+            assert np.array_equal(got[keep], regs[sh.row_to_file[keep]]) and not got[~keep].any()
+            b.load(regs, aux, AUX_SMH)
+            ra = a.run(tau=np.float32(0.85), criterion="smh_a")
+            rb = b.run(tau=np.float32(0.85), criterion="smh_a")
+            # padding rows shift sorted positions: compare in file indices
+            fa = np.sort(np.stack([sh.row_to_file[a.order()[1][ra.i]], sh.row_to_file[a.order()[1][ra.k]]], 1), axis=1)
+            fb = np.sort(np.stack([b.order()[1][rb.i], b.order()[1][rb.k]], 1), axis=1)
+            ka = np.lexsort((fa[:, 1], fa[:, 0]))
+            kb = np.lexsort((fb[:, 1], fb[:, 0]))
+            assert rb.i.size > 100 and np.array_equal(fa[ka], fb[kb]) and np.array_equal(ra.jaccard[ka], rb.jaccard[kb])
