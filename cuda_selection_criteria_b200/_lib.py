@@ -57,7 +57,7 @@ SYMBOLS = [
     ("selb200_load_device_rows", _I, [_VP, _I64, _I64]),
     ("selb200_nib4_piece_bytes", _I64, [_I64, _I]),
     ("selb200_nib4_pack_piece", _I64, [_VP, _I64, _I, _VP, _I]),
-    ("selb200_load_device_rows_packed", _I, [_VP, _I64, _I64, _VP]),
+    ("selb200_load_device_rows_packed", _I, [_VP, _I64, _I64, _VP, _I64]),
     ("selb200_load_begin", _I, [_VP, _I64, _I, _I, _I, C.POINTER(_I64)]),
     ("selb200_load_acquire", _I, [_VP, _I64, _I64, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     ("selb200_load_commit", _I, [_VP]),

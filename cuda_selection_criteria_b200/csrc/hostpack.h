@@ -32,8 +32,13 @@ constexpr int NIB4_RAW_CAP = 4;
 struct Nib4Piece {
     size_t off_hdr, off_exc, off_rawidx, off_nib, off_raw, bytes;
 };
-inline size_t nib4_up256(size_t x) { return (x + 255) & ~(size_t)255; }
-inline Nib4Piece nib4_piece(int64_t rows, size_t m) {
+#if defined(__CUDACC__)
+#define SELB_PK_HD __host__ __device__ inline
+#else
+#define SELB_PK_HD inline
+#endif
+SELB_PK_HD size_t nib4_up256(size_t x) { return (x + 255) & ~(size_t)255; }
+SELB_PK_HD Nib4Piece nib4_piece(long long rows, size_t m) {
     Nib4Piece L;
     L.off_hdr = 0;
     L.off_exc = nib4_up256((size_t)rows * sizeof(Nib4Hdr));

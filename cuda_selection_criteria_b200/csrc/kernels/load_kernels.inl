@@ -13,37 +13,53 @@ __global__ void __launch_bounds__(256) k_max_byte(const uint4* __restrict__ data
     if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
 }
 // ============================================================================
-// packed upload (hostpack.h): nibbles + per-genome base -> register bytes, then the exceptions.
-// A thread turns 8 bytes of nibbles into 16 register bytes (one 128-bit store); raw genomes are skipped, their bytes
-// arrive by a copy of their own.
+// packed upload (hostpack.h): nibbles + per-genome base -> register bytes, then the exceptions, then raw rows.
+// `pieces` holds consecutive packed pieces of piece_rows rows each (the last one shorter), piece_stride bytes apart;
+// blockIdx.y = piece.  A thread turns 8 bytes of nibbles into 16 register bytes (one 128-bit store); raw rows are skipped
+// by the first two kernels and copied by the third.
 // ============================================================================
-__global__ void __launch_bounds__(256)
-k_unpack_nib4(const uint2* __restrict__ nib, const selb::Nib4Hdr* __restrict__ hdr, long long rows, int log2_m,
-              uint4* __restrict__ regs) {
-    const int per_row = 1 << (log2_m - 4);                         // 16-register groups per genome
-    const long long total = rows << (log2_m - 4);
+struct Nib4Pieces {
+    const uint8_t* pieces;
+    size_t piece_stride;
+    long long piece_rows, count;      // rows per piece, rows in all
+    int log2_m;
+    __device__ __forceinline__ long long rows_of(int pi) const { return min(piece_rows, count - (long long)pi * piece_rows); }
+};
+
+__global__ void __launch_bounds__(256) k_unpack_nib4(Nib4Pieces a, uint8_t* __restrict__ regs) {
+    const int pi = blockIdx.y;
+    const long long rows = a.rows_of(pi);
+    const selb::Nib4Piece P = selb::nib4_piece(rows, (size_t)1 << a.log2_m);
+    const uint8_t* piece = a.pieces + (size_t)pi * a.piece_stride;
+    const selb::Nib4Hdr* hdr = reinterpret_cast<const selb::Nib4Hdr*>(piece + P.off_hdr);
+    const uint2* nib = reinterpret_cast<const uint2*>(piece + P.off_nib);
+    uint4* out = reinterpret_cast<uint4*>(regs + (((size_t)pi * (size_t)a.piece_rows) << a.log2_m));
+    const long long total = rows << (a.log2_m - 4);               // 16-register groups
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const long long g = idx >> (log2_m - 4);
-        const selb::Nib4Hdr h = hdr[g];
+        const selb::Nib4Hdr h = hdr[idx >> (a.log2_m - 4)];
         if (h.raw) continue;
         const uint2 v = __ldg(nib + idx);
         const uint32_t b4 = 0x01010101u * h.base;                  // value - base <= 15 and values < 128: no carry between bytes
-        uint4 o;
-        // bytes n0 | n1<<4 -> n0, n1: the even nibbles of a word are its low nibbles, the odd ones its high nibbles
+        // bytes n0 | n1<<4 -> n0, n1: the even registers of a word are its low nibbles, the odd ones its high nibbles
         const uint32_t lo0 = v.x & 0x0f0f0f0fu, hi0 = (v.x >> 4) & 0x0f0f0f0fu;
         const uint32_t lo1 = v.y & 0x0f0f0f0fu, hi1 = (v.y >> 4) & 0x0f0f0f0fu;
-        o.x = __byte_perm(lo0, hi0, 0x5140) + b4;                  // n0 n1 n2 n3 of byte 0, 1
-        o.y = __byte_perm(lo0, hi0, 0x7362) + b4;                  // of byte 2, 3
+        uint4 o;
+        o.x = __byte_perm(lo0, hi0, 0x5140) + b4;                  // registers 0..3 (nibble bytes 0, 1)
+        o.y = __byte_perm(lo0, hi0, 0x7362) + b4;                  // registers 4..7 (nibble bytes 2, 3)
         o.z = __byte_perm(lo1, hi1, 0x5140) + b4;
         o.w = __byte_perm(lo1, hi1, 0x7362) + b4;
-        regs[idx] = o;
-        (void)per_row;
+        out[idx] = o;
     }
 }
-__global__ void __launch_bounds__(256)
-k_apply_nib4_exc(const uint32_t* __restrict__ exc, const selb::Nib4Hdr* __restrict__ hdr, long long rows, int log2_m,
-                 uint8_t* __restrict__ regs) {
+__global__ void __launch_bounds__(256) k_apply_nib4_exc(Nib4Pieces a, uint8_t* __restrict__ regs) {
+    const int pi = blockIdx.y;
+    const long long rows = a.rows_of(pi);
+    const selb::Nib4Piece P = selb::nib4_piece(rows, (size_t)1 << a.log2_m);
+    const uint8_t* piece = a.pieces + (size_t)pi * a.piece_stride;
+    const selb::Nib4Hdr* hdr = reinterpret_cast<const selb::Nib4Hdr*>(piece + P.off_hdr);
+    const uint32_t* exc = reinterpret_cast<const uint32_t*>(piece + P.off_exc);
+    uint8_t* out = regs + (((size_t)pi * (size_t)a.piece_rows) << a.log2_m);
     const long long total = rows * selb::NIB4_EXC_CAP;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -52,19 +68,20 @@ k_apply_nib4_exc(const uint32_t* __restrict__ exc, const selb::Nib4Hdr* __restri
         const selb::Nib4Hdr h = hdr[g];
         if (h.raw || e >= (int)h.n_exc) continue;
         const uint32_t x = exc[idx];
-        regs[((size_t)g << log2_m) + (x >> 8)] = (uint8_t)(x & 0xffu);
+        out[((size_t)g << a.log2_m) + (x >> 8)] = (uint8_t)(x & 0xffu);
     }
 }
-
-// raw genomes of a piece: slot r of the raw area -> row raw_idx[r]
-__global__ void __launch_bounds__(256)
-k_apply_nib4_raw(const uint4* __restrict__ raw, const int32_t* __restrict__ raw_idx, int log2_m, uint4* __restrict__ regs) {
-    const int r = blockIdx.y;
-    const int g = raw_idx[r];
-    if (g < 0) return;
-    const int n16 = 1 << (log2_m - 4);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
-        regs[((size_t)g << (log2_m - 4)) + i] = raw[((size_t)r << (log2_m - 4)) + i];
+// raw rows of a piece: slot r = blockIdx.x of the raw area -> row raw_idx[r]
+__global__ void __launch_bounds__(256) k_apply_nib4_raw(Nib4Pieces a, uint8_t* __restrict__ regs) {
+    const int pi = blockIdx.y, r = blockIdx.x;
+    const long long rows = a.rows_of(pi);
+    const selb::Nib4Piece P = selb::nib4_piece(rows, (size_t)1 << a.log2_m);
+    const uint8_t* piece = a.pieces + (size_t)pi * a.piece_stride;
+    const int g = reinterpret_cast<const int32_t*>(piece + P.off_rawidx)[r];
+    if (g < 0 || g >= rows) return;
+    const uint4* raw = reinterpret_cast<const uint4*>(piece + P.off_raw + ((size_t)r << a.log2_m));
+    uint4* out = reinterpret_cast<uint4*>(regs + (((size_t)pi * (size_t)a.piece_rows + (size_t)g) << a.log2_m));
+    for (int i = threadIdx.x; i < (1 << (a.log2_m - 4)); i += blockDim.x) out[i] = raw[i];
 }
 
 __global__ void k_iota_i32(int32_t* v, long long n) {

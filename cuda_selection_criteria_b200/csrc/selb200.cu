@@ -30,6 +30,7 @@
 
 #include <cuda_runtime.h>
 #include <unistd.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -634,22 +635,23 @@ int pack_threads() {
     return nt;
 }
 
-// a packed piece that sits in device memory -> rows [g0, g0 + rows) of the byte matrix `regs` (run stream)
-int unpack_piece(selb200_ctx* c, const uint8_t* d_piece, int64_t rows, bool maybe_raw, uint8_t* regs_rows) {
-    const selb::Nib4Piece P = selb::nib4_piece(rows, c->m);
-    const selb::Nib4Hdr* hdr = reinterpret_cast<const selb::Nib4Hdr*>(d_piece + P.off_hdr);
-    const long long n16 = (long long)rows * (long long)(c->m >> 4);
-    k_unpack_nib4<<<(int)std::min<long long>((n16 + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
-        reinterpret_cast<const uint2*>(d_piece + P.off_nib), hdr, rows, c->p, reinterpret_cast<uint4*>(regs_rows));
+// packed pieces that sit in device memory (piece_rows rows each, the last one shorter, piece_stride bytes apart) -> `count`
+// rows of the byte matrix starting at regs_rows (run stream)
+int unpack_pieces(selb200_ctx* c, const uint8_t* d_pieces, size_t piece_stride, int64_t piece_rows, int64_t count,
+                  bool maybe_raw, uint8_t* regs_rows) {
+    if (count <= 0) return SELB200_OK;
+    const unsigned n_pieces = (unsigned)((count + piece_rows - 1) / piece_rows);
+    const Nib4Pieces a{d_pieces, piece_stride, (long long)piece_rows, (long long)count, c->p};
+    const long long n16 = (long long)std::min(piece_rows, count) * (long long)(c->m >> 4);
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((n16 + 255) / 256, (long long)c->sm_count * 16 / n_pieces + 1));
+    k_unpack_nib4<<<dim3(gx, n_pieces), 256, 0, c->stream>>>(a, regs_rows);
     CK(cudaGetLastError());
-    const long long ne = (long long)rows * selb::NIB4_EXC_CAP;
-    k_apply_nib4_exc<<<(int)std::min<long long>((ne + 255) / 256, (long long)c->sm_count * 8), 256, 0, c->stream>>>(
-        reinterpret_cast<const uint32_t*>(d_piece + P.off_exc), hdr, rows, c->p, regs_rows);
+    const long long ne = (long long)std::min(piece_rows, count) * selb::NIB4_EXC_CAP;
+    const unsigned ex = (unsigned)std::max<long long>(1, std::min<long long>((ne + 255) / 256, (long long)c->sm_count * 8 / n_pieces + 1));
+    k_apply_nib4_exc<<<dim3(ex, n_pieces), 256, 0, c->stream>>>(a, regs_rows);
     CK(cudaGetLastError());
     if (maybe_raw) {
-        k_apply_nib4_raw<<<dim3(4, selb::NIB4_RAW_CAP), 256, 0, c->stream>>>(
-            reinterpret_cast<const uint4*>(d_piece + P.off_raw), reinterpret_cast<const int32_t*>(d_piece + P.off_rawidx), c->p,
-            reinterpret_cast<uint4*>(regs_rows));
+        k_apply_nib4_raw<<<dim3(selb::NIB4_RAW_CAP, n_pieces), 256, 0, c->stream>>>(a, regs_rows);
         CK(cudaGetLastError());
     }
     return SELB200_OK;
@@ -678,13 +680,22 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
     const int nt = pack_threads();
     int slot_i = 0;
     int64_t group0 = 0;                       // first row not yet digested
+    static const bool trace = getenv("SELB200_PACK_TRACE") != nullptr;
+    double t_pack = 0., t_wait = 0., t_queue = 0.;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t_begin = now();
     for (int64_t g0 = 0; g0 < n; g0 += pk_rows) {
         const int64_t rows = std::min(pk_rows, n - g0);
         const selb::Nib4Piece Q = selb::nib4_piece(rows, m);          // the last piece may be shorter
         PackSlot& ps = c->pack_slots[slot_i];
         slot_i = (slot_i + 1) & 3;
+        const double t0 = now();
         if (ps.in_flight) { CK(cudaEventSynchronize(ps.free_ev)); ps.in_flight = false; }
+        const double t1 = now();
         const int64_t n_raw = selb::nib4_pack_piece(regs + (size_t)g0 * m, rows, m, ps.buf, nt);
+        const double t2 = now();
+        t_wait += t1 - t0;
+        t_pack += t2 - t1;
         uint8_t* d_piece = c->pk_buf.as<uint8_t>() + (size_t)(g0 / pk_rows) * P.bytes;
         uint8_t* d_rows = c->regs_own.as<uint8_t>() + (size_t)g0 * m;
         if (n_raw > selb::NIB4_RAW_CAP) {     // not the registers of HLLs of real sets: the piece travels as it is
@@ -695,7 +706,7 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
             CK(cudaEventRecord(ps.free_ev, c->copy_stream));
             ps.in_flight = true;
             CKR(load_join_copies(c));
-            CKR(unpack_piece(c, d_piece, rows, n_raw > 0, d_rows));
+            CKR(unpack_pieces(c, d_piece, P.bytes, rows, rows, n_raw > 0, d_rows));
         }
         const int64_t done = g0 + rows;
         if (done - group0 >= L.rows_per_chunk || done == n) {
@@ -703,7 +714,11 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
                            aux ? (const uint8_t*)aux + (size_t)group0 * L.aux_row_bytes : nullptr));
             group0 = done;
         }
+        t_queue += now() - t2;
     }
+    if (trace)
+        fprintf(stderr, "selb200 packed load: %lld rows, %d threads: pack %.2f ms, waiting for a slot %.2f ms, queueing %.2f ms, loop %.2f ms\n",
+                (long long)n, nt, t_pack * 1e3, t_wait * 1e3, t_queue * 1e3, (now() - t_begin) * 1e3);
     return SELB200_OK;
 }
 
@@ -835,14 +850,16 @@ int64_t selb200_nib4_pack_piece(const uint8_t* regs, int64_t rows, int p, uint8_
     return selb::nib4_pack_piece(regs, rows, (size_t)1 << p, piece, threads > 0 ? threads : pack_threads());
 }
 
-// rows [g0, g0+count) arrive as a packed piece in device memory (selb200_nib4_pack_piece on some host, then any copy or
+// rows [g0, g0+count) arrive as packed pieces in device memory (selb200_nib4_pack_piece on some host, then any copy or
 // collective): unpacked INTO the matrix given to selb200_load_device_begin, then digested like selb200_load_device_rows
-int selb200_load_device_rows_packed(selb200_ctx* c, int64_t g0, int64_t count, const uint8_t* d_piece) {
+int selb200_load_device_rows_packed(selb200_ctx* c, int64_t g0, int64_t count, const uint8_t* d_pieces, int64_t piece_rows) {
     if (!c || !c->ld.active || !c->ld.regs_borrowed) return fail(SELB200_ESTATE, "selb200_load_device_rows_packed outside load_device_begin/load_end");
     if (g0 < 0 || count < 0 || g0 + count > c->n) return fail(SELB200_EINVAL, "rows [%lld,+%lld) outside the matrix", (long long)g0, (long long)count);
-    if (count && !d_piece) return fail(SELB200_EINVAL, "null piece");
+    if (count && (!d_pieces || piece_rows < 1)) return fail(SELB200_EINVAL, "null pieces / piece_rows < 1");
     CK(cudaSetDevice(c->device));
-    if (count) CKR(unpack_piece(c, d_piece, count, true, const_cast<uint8_t*>(c->d_regs) + (size_t)g0 * c->m));
+    if (count)
+        CKR(unpack_pieces(c, d_pieces, selb::nib4_piece(piece_rows, c->m).bytes, piece_rows, count, true,
+                          const_cast<uint8_t*>(c->d_regs) + (size_t)g0 * c->m));
     return load_chunk(c, g0, count, nullptr, nullptr, nullptr);
 }
 

@@ -87,19 +87,67 @@ class ShardedSketches:
         lo = c * self.world * self.rpc
         return t[lo:lo + self.world * self.rpc], t[lo + self.rank * self.rpc:lo + (self.rank + 1) * self.rpc]
 
+    SUB_ROWS_BYTES = 16 << 20      # registers packed at a time: four pinned staging slots of this size stay in the host's
+                                   # last-level cache, so the copy engine reads the packed bytes from there, not from DRAM
+
     def _packed_buffers(self, m: int):
-        """Pinned host staging and device landing zones of the packed pieces (include/selb200.h, "Packed transport"):
-        [piece][rank][piece_bytes] on the device, so that one all-gather per piece moves every rank's rows."""
+        """Pinned host staging and device landing zones of the packed rows (include/selb200.h, "Packed transport"): a
+        piece (the unit of the all-gather) is packed as ceil(rpc / sub_rows) small pieces back to back, [piece][rank][...]
+        on the device, so that one all-gather per piece moves every rank's rows."""
         if getattr(self, "_pk_dev", None) is None:
             L = _lib.lib()
             self._p = m.bit_length() - 1
-            pb = int(L.selb200_nib4_piece_bytes(self.rpc, self._p))
-            if pb <= 0:
+            self._sub_rows = max(1, min(self.rpc, self.SUB_ROWS_BYTES // m))
+            self._n_sub = (self.rpc + self._sub_rows - 1) // self._sub_rows
+            self._sub_bytes = int(L.selb200_nib4_piece_bytes(self._sub_rows, self._p))
+            if self._sub_bytes <= 0:
                 raise _lib.SelB200Error(L.selb200_last_error().decode())
-            self._pk_dev = torch.empty((self.chunks, self.world, pb), dtype=torch.uint8, device=self.regs.device)
-            self._pk_host = [torch.empty(pb, dtype=torch.uint8, pin_memory=True) for _ in range(self.chunks)]
-            self._pad = torch.zeros((self.rpc, m), dtype=torch.uint8)
+            self._pk_dev = torch.empty((self.chunks, self.world, self._n_sub * self._sub_bytes), dtype=torch.uint8,
+                                       device=self.regs.device)
+            self._pk_host = [torch.empty(self._sub_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+            self._pk_free = [None] * 4
+            self._pad = torch.zeros((self._sub_rows, m), dtype=torch.uint8)
         return self._pk_dev, self._pk_host
+
+    def _pack_and_copy(self, L, regs_host, c: int, h0: int, h1: int):
+        """rows [h0, h1) of this rank's slice (piece c, rpc rows with the zero padding) -> packed, into pk_dev[c, rank];
+        the copies are queued on the copy stream, the host only waits for a staging slot to come back"""
+        slot = getattr(self, "_slot", 0)
+        import time as _t
+        tr = self._trace
+        for s in range(self._n_sub):
+            r0 = s * self._sub_rows
+            rows = min(self._sub_rows, self.rpc - r0)
+            a, b = min(h1, h0 + r0), min(h1, h0 + r0 + rows)
+            if b - a == rows:
+                src = regs_host[a:b]
+            else:                       # the slice ends inside this piece: the rest are all-zero sketches
+                self._pad.zero_()
+                if b > a:
+                    self._pad[:b - a].copy_(regs_host[a:b])
+                src = self._pad
+            t0 = _t.perf_counter()
+            if self._pk_free[slot] is not None:
+                self._pk_free[slot].synchronize()
+            t1 = _t.perf_counter()
+            n_raw = int(L.selb200_nib4_pack_piece(src.data_ptr(), rows, self._p, self._pk_host[slot].data_ptr(), 0))
+            t2 = _t.perf_counter()
+            tr[0] += t1 - t0
+            tr[1] += t2 - t1
+            if n_raw < 0:
+                raise _lib.SelB200Error(L.selb200_last_error().decode())
+            if n_raw > 4:
+                raise _lib.SelB200Error(f"{n_raw} rows of a piece do not look like HLL sketches (more than 32 registers far "
+                                        "above the smallest): set SELB200_H2D=raw to move the registers unpacked")
+            nbytes = int(L.selb200_nib4_piece_bytes(rows, self._p))
+            with torch.cuda.stream(self._copy_stream):
+                dst = self._pk_dev[c, self.rank, s * self._sub_bytes:s * self._sub_bytes + nbytes]
+                dst.copy_(self._pk_host[slot][:nbytes], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._pk_free[slot] = ev
+            slot = (slot + 1) & 3
+        self._slot = slot
 
     def assemble(self, regs_host: torch.Tensor, aux_host: torch.Tensor | None, on_piece=None, on_piece_packed=None):
         """on_piece(row0, rows): called after the all-gather of each piece has been queued on the current
@@ -107,43 +155,38 @@ class ShardedSketches:
 
         With on_piece_packed (e.g. Selection.load_device_rows_packed) the register rows travel PACKED — half the
         bytes over PCIe and over NVLink: every piece is packed by this rank's host threads into pinned memory, copied,
-        all-gathered as bytes, and on_piece_packed(row0, rows, piece) is called for each rank's part, which unpacks
-        it into `self.regs` and digests it.  SELB200_H2D=raw keeps the unpacked route."""
+        all-gathered as bytes, and on_piece_packed(row0, rows, pieces, piece_rows) is called for each rank's part, which
+        unpacks it into `self.regs` and digests it.  Default for a world of one; SELB200_H2D=packed selects it for any world."""
+        import time as _t
+        t_begin = _t.perf_counter()
+        t_cb = 0.0
         cuda = self._copy_stream is not None
-        packed = cuda and on_piece_packed is not None and os.environ.get("SELB200_H2D") != "raw"
+        # packing costs host memory bandwidth (about 110 GB/s of registers on a 24-thread box, all ranks together), a raw
+        # copy costs PCIe time (54 GB/s per link): packed wins on one link (18 ms against 32 for 1.64 GB), loses from
+        # two links on (22 ms against 18.5 at two ranks), so it is the default for a world of one only;
+        # SELB200_H2D=packed / raw force either route
+        mode = os.environ.get("SELB200_H2D", "")
+        packed = cuda and on_piece_packed is not None and (mode == "packed" or (mode != "raw" and self.world == 1))
         if cuda:
             self._copy_stream.wait_stream(torch.cuda.current_stream())   # earlier readers of the matrices are done
         if packed:
-            pk_dev, pk_host = self._packed_buffers(int(regs_host.shape[1]))
+            pk_dev, _ = self._packed_buffers(int(regs_host.shape[1]))
             L = _lib.lib()
+            self._trace = [0.0, 0.0]
         for c in range(self.chunks):
             h0, h1 = min(self.rows, c * self.rpc), min(self.rows, (c + 1) * self.rpc)
             if packed:
-                if h1 - h0 == self.rpc:
-                    src = regs_host[h0:h1]
-                else:                       # the slice ends inside this piece: the rest are all-zero sketches
-                    self._pad.zero_()
-                    if h1 > h0:
-                        self._pad[:h1 - h0].copy_(regs_host[h0:h1])
-                    src = self._pad
-                n_raw = int(L.selb200_nib4_pack_piece(src.data_ptr(), self.rpc, self._p, pk_host[c].data_ptr(), 0))
-                if n_raw < 0:
-                    raise _lib.SelB200Error(L.selb200_last_error().decode())
-                if n_raw > 4:
-                    raise _lib.SelB200Error(f"{n_raw} rows of a piece do not look like HLL sketches (more than 32 registers far "
-                                            "above the smallest): set SELB200_H2D=raw to move the registers unpacked")
+                self._pack_and_copy(L, regs_host, c, h0, h1)
             ctx = torch.cuda.stream(self._copy_stream) if cuda else _Null()
             with ctx:
-                if packed:
-                    pk_dev[c, self.rank].copy_(pk_host[c], non_blocking=True)
-                elif h1 > h0:
+                if not packed and h1 > h0:
                     self._piece(self.regs, c)[1][:h1 - h0].copy_(regs_host[h0:h1], non_blocking=True)
                 if h1 > h0 and self.aux is not None:
                     self._piece(self.aux, c)[1][:h1 - h0].copy_(aux_host[h0:h1], non_blocking=True)
                 if cuda:
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
-            # queued behind the copy on the current stream: the host goes on to pack the next piece meanwhile
+            # queued behind the copies on the current stream: the host goes on to pack the next piece meanwhile
             if cuda:
                 torch.cuda.current_stream().wait_event(ev)
             if self.world > 1:
@@ -156,10 +199,16 @@ class ShardedSketches:
                     whole, mine = self._piece(self.aux, c)
                     dist.all_gather_into_tensor(whole, mine)
             if packed:
+                t0 = _t.perf_counter()
                 for r in range(self.world):
-                    on_piece_packed((c * self.world + r) * self.rpc, self.rpc, pk_dev[c, r])
+                    on_piece_packed((c * self.world + r) * self.rpc, self.rpc, pk_dev[c, r], self._sub_rows)
+                t_cb += _t.perf_counter() - t0
             elif on_piece is not None:
                 on_piece(c * self.world * self.rpc, self.world * self.rpc)
+        if packed and os.environ.get("SELB200_PACK_TRACE"):
+            import sys
+            print(f"rank {self.rank} packed assemble: waiting for a slot {self._trace[0] * 1e3:.2f} ms, pack {self._trace[1] * 1e3:.2f} ms, "
+                  f"callbacks {t_cb * 1e3:.2f} ms, whole call {(_t.perf_counter() - t_begin) * 1e3:.2f} ms", file=sys.stderr)
         return self.regs, self.aux
 
 

@@ -137,10 +137,12 @@ class Selection:
     def load_device_rows(self, g0: int, count: int):
         _lib.check(self._L.selb200_load_device_rows(self._h, int(g0), int(count)))
 
-    def load_device_rows_packed(self, g0: int, count: int, piece):
-        """Rows [g0, g0+count) arrived as a packed piece (selb200_nib4_pack_piece) in device memory: `piece` is a CUDA
-        uint8 tensor holding it.  They are unpacked into the matrix given to load_device_begin, then digested."""
-        _lib.check(self._L.selb200_load_device_rows_packed(self._h, int(g0), int(count), piece.data_ptr()))
+    def load_device_rows_packed(self, g0: int, count: int, pieces, piece_rows: int | None = None):
+        """Rows [g0, g0+count) arrived as packed pieces (selb200_nib4_pack_piece) in device memory: `pieces` is a CUDA
+        uint8 tensor holding ceil(count / piece_rows) of them back to back (piece_rows = count: one piece).  They are
+        unpacked into the matrix given to load_device_begin, then digested."""
+        _lib.check(self._L.selb200_load_device_rows_packed(self._h, int(g0), int(count), pieces.data_ptr(),
+                                                           int(piece_rows or count)))
 
     def load_end(self):
         _lib.check(self._L.selb200_load_end(self._h))

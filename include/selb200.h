@@ -167,12 +167,14 @@ int selb200_load_device_rows(selb200_ctx* ctx, int64_t g0, int64_t count);
  *                 Returns the number of rows that had to be kept as raw bytes (more than 32 registers 15 or more above
  *                 the row's smallest): up to 4 of them travel inside the piece, a return value > 4 means the piece
  *                 cannot be used (send those rows raw); negative = error
- *   load_device_rows_packed : like selb200_load_device_rows, for rows that arrived as a piece in device memory; the
- *                 rows are unpacked INTO the matrix given to selb200_load_device_begin (which must be writable)
+ *   load_device_rows_packed : like selb200_load_device_rows, for rows that arrived as pieces in device memory:
+ *                 ceil(count / piece_rows) pieces of piece_rows rows each (the last one shorter, packed as such),
+ *                 selb200_nib4_piece_bytes(piece_rows, p) bytes apart; the rows are unpacked INTO the matrix given to
+ *                 selb200_load_device_begin (which must be writable)
  * Unpacking reproduces the bytes exactly: nothing downstream can depend on the transport. */
 int64_t selb200_nib4_piece_bytes(int64_t rows, int p);
 int64_t selb200_nib4_pack_piece(const uint8_t* regs, int64_t rows, int p, uint8_t* piece, int threads);
-int selb200_load_device_rows_packed(selb200_ctx* ctx, int64_t g0, int64_t count, const uint8_t* d_piece);
+int selb200_load_device_rows_packed(selb200_ctx* ctx, int64_t g0, int64_t count, const uint8_t* d_pieces, int64_t piece_rows);
 
 /* After a load: cards_sorted[i] = cardinality (double) of the i-th genome in sorted
  * order; order[i] = its index in file-list order.  Either pointer may be NULL. */

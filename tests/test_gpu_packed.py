@@ -65,7 +65,8 @@ def test_packed_load_still_validates_registers(gpu):
 
 
 @pytest.mark.parametrize("chunks", [1, 3])
-def test_sharded_assemble_packed_world_of_one(gpu, chunks):
+def test_sharded_assemble_packed_world_of_one(gpu, chunks, monkeypatch):
+    monkeypatch.setattr(sdist.ShardedSketches, "SUB_ROWS_BYTES", 300 << 14)       # several small pieces per piece, a short last one
     n = 2100
     plan = synth.make_plan(n, 12)
     regs = _odd_rows(synth.hll(plan, 14), 2)
@@ -83,7 +84,7 @@ def test_sharded_assemble_packed_world_of_one(gpu, chunks):
             a.load_device_begin(sh.regs, sh.aux, AUX_SMH)
             calls = []
             sh.assemble(regs_h, aux_h, on_piece=a.load_device_rows,
-                        on_piece_packed=lambda g0, cnt, piece: (calls.append((g0, cnt)), a.load_device_rows_packed(g0, cnt, piece)))
+                        on_piece_packed=lambda g0, cnt, pieces, pr: (calls.append((g0, cnt)), a.load_device_rows_packed(g0, cnt, pieces, pr)))
             a.load_end()
             assert len(calls) == chunks and sum(c for _, c in calls) == sh.n_dev
             # the device matrix holds the host rows again (padding rows: all zero)

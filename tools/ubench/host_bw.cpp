@@ -7,12 +7,21 @@
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
+#ifdef USE_PINNED
+#include <cuda_runtime.h>
+#endif
 #include <vector>
 #include "../../cuda_selection_criteria_b200/csrc/hostpack.h"
 int main(int argc, char** argv) {
     const size_t bytes = (argc > 1 ? atoll(argv[1]) : 1638400000ll);
+#ifdef USE_PINNED      // nvcc -DUSE_PINNED: source and staging in cudaMallocHost memory, as the loader sees them
+    uint8_t *src = nullptr, *dst = nullptr;
+    if (cudaMallocHost(&src, bytes) != cudaSuccess || cudaMallocHost(&dst, bytes) != cudaSuccess) { printf("cudaMallocHost failed\n"); return 1; }
+    printf("pinned source and staging\n");
+#else
     uint8_t* src = (uint8_t*)aligned_alloc(4096, bytes);
     uint8_t* dst = (uint8_t*)aligned_alloc(4096, bytes);
+#endif
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)bytes; i += 4096) { memset(src + i, (int)(i >> 12) & 15, 4096); memset(dst + i, 0, 4096); }
     const int max_threads = omp_get_max_threads();
