@@ -79,7 +79,9 @@ int64_t nib4_pack(const uint8_t* regs, int64_t rows, size_t m, uint8_t* nib, uin
     int64_t n_raw = 0;
     const bool vec = have_avx2();
     const int nt = threads > 0 ? threads : omp_get_max_threads();
-#pragma omp parallel for schedule(static) num_threads(nt) reduction(+ : n_raw)
+    // dynamic, in grains of 16 rows: inside a process that also runs driver and sampler threads one delayed thread would
+    // otherwise hold the whole team at the barrier of every piece
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt) reduction(+ : n_raw)
     for (int64_t g = 0; g < rows; ++g) {
         const uint8_t* v = regs + (size_t)g * m;
 #if defined(__x86_64__)
