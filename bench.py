@@ -438,13 +438,16 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
     p_cb, p_cand, p_aux, p_out = st["pairs_cb_shard"], st["pairs_cand"], st["pairs_aux"], st["pairs_out"]
     add("bounds", "k_cb_bounds + k_rowblock_span + scan + k_tile_table", mean("ms_bounds"), "hbm", cfg.n, 16.0 * 20,
         "16 B per tested pair x ~20 binary-search probes per row", "latency-bound: four small launches")
-    if cfg.criterion == "smh_a":
+    if cfg.criterion == "smh_a" and os.environ.get("SELB200_SMHFILTER", "") != "tiles":
         nb = st["n_bands"]
-        add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, float((nb + 1) // 2),
-            f"one packed min/add lane-operation (VIADDMNMX.U16x2) per two LSH bands and pair: {(nb + 1) // 2} per CB pair of the shard "
-            "(a thread owns an 8x8 block of pairs, so one lane-operation serves one pair)")
-        add("verify", "k_smh_verify", mean("ms_verify"), "hbm", p_cand, 2.0 * 8 * st["n_rows"] + 16,
-            "2 x 8 x n_rows bucket bytes + 16 B per candidate", "latency-bound: thread per candidate, dependent loads")
+        # equality join: n x bands keys of 8 B (key + position) generated, sorted (three 8-bit radix passes, each reading and
+        # writing them) and walked once, plus the exact bucket compare of the candidates
+        add("filter", "k_smh_sigkeys + cub radix sort + k_smh_join", mean("ms_filter"), "hbm", cfg.n * nb, 8.0 * 9,
+            f"{cfg.n} x {nb} (band | signature, position) keys of 8 B: written once, 3 radix passes read + write, the walk reads them "
+            "(9 x 8 B per key); work is O(n x bands + matches), not O(P_cb x bands)",
+            "latency-bound: seven small launches (keys, five of the sort, walk) over 13 MB")
+    elif cfg.criterion == "smh_a":
+        nb = st["n_bands"]
     elif cfg.criterion in ("hll_a", "hll_an"):
         regs_aux = cfg.aux_bytes
         mode = os.environ.get("SELB200_HLLFILTER", "")

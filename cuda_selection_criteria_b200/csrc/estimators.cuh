@@ -43,6 +43,10 @@ struct NeverStop {
 // therefore stop as soon as the decision already fails at the bound: the outcome is identical
 // to running the reference iteration to its end.  When stop() fires, *stopped is set and the
 // bound is returned; otherwise the result is bit-for-bit the reference's sequence of operations.
+// The estimator proper, for a histogram whose smallest and largest non-empty bins are already known (kMin <= kMax <= q+1).
+template <typename CountT, typename Stop = NeverStop>
+SELB_HD double ertl_mle_range(const CountT* c, int p, int stride, int kMin, int kMax, Stop stop = Stop(), bool* stopped = nullptr);
+
 template <typename CountT, typename Stop = NeverStop>
 SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1, Stop stop = Stop(), bool* stopped = nullptr) {
     const int q = 64 - p;
@@ -51,8 +55,16 @@ SELB_HD double ertl_mle(const CountT* c, int p, int stride = 1, Stop stop = Stop
     int kMin, kMax;
     for (kMin = 0; kMin <= q + 1 && c[kMin * stride] == 0; ++kMin) {}
     if (kMin > q + 1) return 0.;   // empty histogram: cannot happen for a sketch (counts sum to m); guards the scan
-    const int kMinP = imax(1, kMin);
     for (kMax = q + 1; kMax && c[kMax * stride] == 0; --kMax) {}
+    return ertl_mle_range(c, p, stride, kMin, kMax, stop, stopped);
+}
+
+template <typename CountT, typename Stop>
+SELB_HD double ertl_mle_range(const CountT* c, int p, int stride, int kMin, int kMax, Stop stop, bool* stopped) {
+    const int q = 64 - p;
+    const unsigned long long m = 1ull << p;
+    if ((unsigned long long)c[(q + 1) * stride] == m) return __builtin_huge_val();
+    const int kMinP = imax(1, kMin);
     const int kMaxP = imin(q, kMax);
     double z = 0.;
     for (int k = kMaxP; k >= kMinP; --k) z = 0.5 * z + (double)c[k * stride];

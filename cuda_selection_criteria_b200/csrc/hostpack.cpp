@@ -3,7 +3,9 @@
 
 #include <algorithm>
 #include <cstring>
+#ifdef _OPENMP
 #include <omp.h>
+#endif
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -78,7 +80,11 @@ const char* nib4_impl() { return have_avx2() ? "avx2" : "scalar"; }
 int64_t nib4_pack(const uint8_t* regs, int64_t rows, size_t m, uint8_t* nib, uint32_t* exc, Nib4Hdr* hdr, int threads) {
     int64_t n_raw = 0;
     const bool vec = have_avx2();
+#ifdef _OPENMP
     const int nt = threads > 0 ? threads : omp_get_max_threads();
+#else
+    (void)threads;
+#endif
     // dynamic, in grains of 16 rows: inside a process that also runs driver and sampler threads one delayed thread would
     // otherwise hold the whole team at the barrier of every piece
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt) reduction(+ : n_raw)

@@ -24,9 +24,21 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
     for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
          pi += (long long)gridDim.x * blockDim.x) {
         const uint2 pr = pairs[pi];
+        // the row's non-empty bins from sixteen independent 128-bit loads (the estimator's own scans for the first and
+        // the last one are a chain of dependent loads: ~35 round trips before the arithmetic starts); the row is in L1 after
+        const uint4* row = reinterpret_cast<const uint4*>(hist + pi * 64);
+        unsigned long long nz = 0ull;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint4 v = __ldg(row + j);
+            const unsigned long long b = (v.x ? 1ull : 0ull) | (v.y ? 2ull : 0ull) | (v.z ? 4ull : 0ull) | (v.w ? 8ull : 0ull);
+            nz |= b << (4 * j);
+        }
         const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+        if (nz == 0ull) continue;                                  // no histogram (cannot happen for a counted pair)
         bool stopped = false;
-        const double t = selb::ertl_mle(hist + pi * 64, p, 1, StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
+        const double t = selb::ertl_mle_range(hist + pi * 64, p, 1, __ffsll((long long)nz) - 1, 63 - __clzll((long long)nz),
+                                              StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
         if (stopped) continue;
         const double jac = selb::jaccard(e1, e2, t);
         const uint64_t key = ((uint64_t)pr.x << 32) | pr.y;

@@ -235,6 +235,95 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
     }
 }
 
+// ============================================================================
+// K3'/K4': smh_a as an EQUALITY JOIN (default; the tile filter above stays as SELB200_SMHFILTER=tiles).
+// "Some band equal" (criteria_sketch.hpp:71-79) is a join on (band, band contents): instead of testing all P_cb pairs
+// of the band against all bands (O(P_cb * bands): 3.7e9 half-word operations at n = 100k), the n * bands keys
+// (band << 16 | 16-bit signature of the band's buckets) are sorted once (cub radix sort, stable: equal keys keep ascending
+// sorted position) and every run of equal keys is walked: work O(n * bands + matches).
+//   k_smh_sigkeys : keys, values (= sorted position) in genome-major order, and the signatures genome-major (sigG: two
+//                   bands per word, nbw words per genome = 32 B at 16 bands) for the step below
+//   k_smh_join    : thread per sorted key (band b, genome i): its followers k in the run with k <= hi(i) are the pairs of
+//                   the CB band whose band-b signatures agree.  A pair is handled ONCE, by the first band whose signatures
+//                   agree (the thread reads the earlier bands' signatures of both genomes: 32 B each): that handler
+//                   compares the buckets of every signature-equal band from b on, exactly, and emits the pair at the first
+//                   band that really is equal — the decision of k_smh_verify, so P_aux is the reference's.
+// Shards: the walk is replicated, the handler of a pair is the shard (i + k) mod n_shards (disjoint, balanced).
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, int n_rows, int n_bands, int nbw,
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ sigG) {
+    const int nb2 = nbw * 2;
+    const long long total = n * nb2;
+    const long long stride = (long long)gridDim.x * blockDim.x;          // even: lane pairs stay together
+    for (long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx0 - (threadIdx.x & 31) < total;
+         idx0 += stride) {
+        const bool live = idx0 < total;
+        const long long g = live ? idx0 / nb2 : 0;
+        const int b = live ? (int)(idx0 - g * nb2) : 0;
+        const bool real = live && b < n_bands;
+        uint32_t sig = 0;
+        if (real) {
+            sig = band_sig16(aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows, n_rows);
+            keys[g * n_bands + b] = ((uint32_t)b << 16) | sig;
+            vals[g * n_bands + b] = (uint32_t)g;
+        }
+        const uint32_t other = __shfl_down_sync(0xffffffffu, sig, 1);
+        if (live && !(b & 1)) sigG[g * nbw + (b >> 1)] = sig | (other << 16);
+    }
+}
+
+// buckets of band b of the two genomes equal?
+__device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, const uint64_t* __restrict__ v2, int b, int n_rows) {
+    for (int r = 0; r < n_rows; ++r)
+        if (__ldg(v1 + (size_t)b * n_rows + r) != __ldg(v2 + (size_t)b * n_rows + r)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_smh_join(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
+           const uint32_t* __restrict__ sigG, int nbw, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
+           const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int shard, int n_shards,
+           uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap,
+           unsigned long long* __restrict__ cand_count) {
+    uint32_t n_cand = 0;
+    for (long long s = s0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; s < s1; s += (long long)gridDim.x * blockDim.x) {
+        const uint32_t key = keys[s];
+        const int i = (int)vals[s], b = (int)(key >> 16);
+        const int lo_i = lo[i], hi_i = hi[i];
+        if (hi_i < lo_i) continue;
+        const uint32_t* si = sigG + (size_t)i * nbw;
+        for (long long t = s + 1; t < n_keys && keys[t] == key; ++t) {
+            const int k = (int)vals[t];                    // > i: equal keys keep ascending position
+            if (k > hi_i) break;
+            if (k < lo_i) continue;
+            if (n_shards > 1 && (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) != shard) continue;
+            const uint32_t* sk = sigG + (size_t)k * nbw;
+            // an earlier band with equal signatures handles the pair
+            bool earlier = false;
+            for (int w = 0; w <= (b >> 1) && !earlier; ++w) {
+                const uint32_t x = __ldg(si + w) ^ __ldg(sk + w);
+                if (2 * w < b && (x & 0xffffu) == 0u) earlier = true;
+                if (2 * w + 1 < b && (x >> 16) == 0u) earlier = true;
+            }
+            if (earlier) continue;
+            ++n_cand;
+            const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
+            const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
+            bool hit = smh_band_equal(v1, v2, b, n_rows);
+            for (int b2 = b + 1; b2 < n_bands && !hit; ++b2) {
+                const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
+                if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);
+            }
+            if (hit) {
+                const unsigned long long slot = warp_claim(pair_count);
+                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
+            }
+        }
+    }
+    if (n_cand) atomicAdd(cand_count, (unsigned long long)n_cand);
+}
+
 // CB only: every pair of the band inside this tile
 __global__ void __launch_bounds__(256)
 k_tile_enum(TileWalk tw, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n,

@@ -63,6 +63,12 @@ int hll_filter_mode() {
     return mode;
 }
 
+// SELB200_SMHFILTER=tiles (read once per process): the all-pairs tile filter + verify instead of the equality join
+bool smh_join_enabled() {
+    static const bool on = [] { const char* e = getenv("SELB200_SMHFILTER"); return !(e && !strcmp(e, "tiles")); }();
+    return on;
+}
+
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -199,6 +205,7 @@ struct selb200_ctx {
     LoadState ld;
     PackSlot pack_slots[4];
     DevBuf pk_buf;                       // packed pieces as they land on the device, before k_unpack_nib4
+    DevBuf join_buf;                     // smh_a equality join: keys / values, unsorted and sorted, and the genome-major signatures
     StageSlot slots[3];
     int next_slot = 0;
     bool _order_cache_valid = false;
@@ -800,7 +807,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1049,6 +1056,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_filter, t_verify, t_union, t_est;
     const int n_words = (n_bands + 1) / 2;
     const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
+    const bool smh_join = use_smh && smh_join_enabled() && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
+    const long long jn_keys = (long long)n * n_bands;
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
@@ -1126,7 +1135,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         CKR(c->g_merged.ensure(32));
     }
     auto launch_push = [&](int check, unsigned long long pair_lim) -> int {
-        k_gather_claim<<<1, 32, 0, s>>>(gz, c->g.epoch, d_cnt, check, (unsigned long long)PAIR_CAP, pair_lim,
+        k_gather_claim<<<1, 32, 0, s>>>(gz, c->g.epoch, d_cnt, check, smh_join ? ~0ull : (unsigned long long)PAIR_CAP, pair_lim,
                                         (unsigned long long)c->out_cap, (unsigned long long)c->tile_cap,
                                         (unsigned long long)c->near_cap, c->g_push.as<GatherPush>());
         CK(cudaGetLastError());
@@ -1173,7 +1182,27 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         }
         if ((int)ranges.size() > SNAP_MAX) return fail(SELB200_ENOMEM, "too many tile ranges (%zu)", ranges.size());
         t_filter.clear(); t_verify.clear(); t_union.clear(); t_est.clear();
-        if (use_smh) {
+        if (use_smh && smh_join) {
+            // keys + values (unsorted, sorted) and genome-major signatures; one stable radix sort over band | signature
+            cudaEvent_t a0 = c->ev();
+            CKR(c->join_buf.ensure(((size_t)4 * jn_keys + (size_t)n * n_words) * 4));
+            uint32_t* jk = c->join_buf.as<uint32_t>();
+            int key_bits = 16;
+            while ((1 << (key_bits - 16)) < n_bands) ++key_bits;
+            const int grid = (int)std::min<int64_t>(((int64_t)n * n_words * 2 + 255) / 256, (int64_t)c->sm_count * 16);
+            k_smh_sigkeys<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->aux_len, n_rows, n_bands, n_words, jk,
+                                               jk + jn_keys, jk + 4 * jn_keys);
+            CK(cudaGetLastError());
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, jk, jk + 2 * jn_keys, jk + jn_keys, jk + 3 * jn_keys,
+                                               (int)jn_keys, 0, key_bits, s));
+            CKR(c->cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, jk, jk + 2 * jn_keys, jk + jn_keys, jk + 3 * jn_keys,
+                                               (int)jn_keys, 0, key_bits, s));
+            st.launches += 2;
+            DBG_SYNC(c, "smh signature keys + sort");
+            t_filter.push_back({a0, c->ev()});
+        } else if (use_smh) {
             cudaEvent_t a0 = c->ev();
             const size_t sig_bytes = (size_t)n_words * c->npad * 4;
             CKR(c->sigT.ensure(2 * sig_bytes));
@@ -1200,7 +1229,22 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 if (crit >= SELB200_CRIT_HLL_A) CK(cudaMemsetAsync(d_cnt + M_UNIT, 0, 8, s));
             }
             cudaEvent_t f0 = c->ev();
-            if (crit == SELB200_CRIT_SMH_A) {
+            if (crit == SELB200_CRIT_SMH_A && smh_join) {
+                // a tile range [j0, j1) of the shard's t_end tiles stands for the same fraction of the sorted keys (ranges
+                // other than "everything" only exist after a pass whose lists overflowed, when t_end is known)
+                long long s0 = 0, s1 = jn_keys;
+                if (rg.second != INT32_MAX) {
+                    const long long t_end = std::max<long long>(1, shard_tiles(tiles_total));
+                    s0 = jn_keys * std::min<long long>(rg.first, t_end) / t_end;
+                    s1 = jn_keys * std::min<long long>(rg.second, t_end) / t_end;
+                }
+                const uint32_t* jk = c->join_buf.as<uint32_t>();
+                const int grid = (int)std::max<long long>(1, std::min<long long>((s1 - s0 + 255) / 256, (long long)c->sm_count * 16));
+                k_smh_join<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, jk + 4 * jn_keys, n_words,
+                                                c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, c->lo.as<int32_t>(),
+                                                c->hi.as<int32_t>(), prm->shard, n_shards, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
+                                                (unsigned long long)PAIR_CAP, d_cnt + M_CAND);
+            } else if (crit == SELB200_CRIT_SMH_A) {
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
                 k_tile_filter_smh<<<grid, 256, 0, s>>>(
                     c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad, c->npad, n_words, tw,
@@ -1266,7 +1310,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 CK(cudaGetLastError());
                 st.launches++;
             }
-            if (crit == SELB200_CRIT_SMH_A) {
+            if (crit == SELB200_CRIT_SMH_A && !smh_join) {
                 k_smh_verify<<<c->sm_count * 8, 256, 0, s>>>(
                     c->aux_sorted.as<uint64_t>(), c->sigT.as<uint32_t>(), c->npad, c->aux_len, n_rows, n_bands,
                     c->cand.as<uint2>(), d_cnt + M_CAND, (unsigned long long)PAIR_CAP, c->pairs.as<uint2>(),
@@ -1277,7 +1321,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             DBG_SYNC(c, "smh verify");
             // ---- K5 + K6 --------------------------------------------------------------
             cudaEvent_t u0 = c->ev();
-            if (crit == SELB200_CRIT_SMH_A || hll_twopass) t_verify.push_back({f1, u0});
+            if ((crit == SELB200_CRIT_SMH_A && !smh_join) || hll_twopass) t_verify.push_back({f1, u0});
             if (union_bytes) {
                 CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
                                      (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
@@ -1334,7 +1378,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
             const unsigned long long* sn = c->h_snap + ri * 4;
             const int ra = ranges[ri].first, rb = std::min(ranges[ri].second, t_end);
-            const bool too_many = sn[0] > (unsigned long long)PAIR_CAP || sn[1] > (unsigned long long)PAIR_CAP;
+            // the join only counts its candidates: no list to overflow
+            const bool too_many = (!smh_join && sn[0] > (unsigned long long)PAIR_CAP) || sn[1] > (unsigned long long)PAIR_CAP;
             if (too_many) {
                 const int nt = rb - ra;
                 if (nt <= 1) return fail(SELB200_ENOMEM, "a single tile produced %llu pairs", std::max(sn[0], sn[1]));

@@ -96,6 +96,16 @@ static inline void launch(unsigned grid, unsigned block, const std::function<voi
     cta_bar = nullptr;
 }
 static inline void launch(unsigned grid, const std::function<void()>& body) { launch(grid, 32, body); }
+// two-dimensional grid: blockIdx.y runs over [0, grid_y), one x-sweep after the other
+static thread_local unsigned block_y = 0;
+static unsigned grid_y_now = 0;
+static inline void launch2(unsigned grid_x, unsigned grid_y, unsigned block, const std::function<void()>& body) {
+    for (unsigned y = 0; y < grid_y; ++y) {
+        grid_y_now = y;
+        launch(grid_x, block, [&] { blockIdx.y = grid_y_now; body(); });
+    }
+    gridDim.y = grid_y;
+}
 }  // namespace emul
 
 // values travel as bit patterns (floating-point operands keep their bits, as on the device)
@@ -140,6 +150,13 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+// PRMT, default mode: result byte i = byte (selector nibble i) of the eight bytes {y, x}
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 // SIMD-in-word integer intrinsics of the smh filter (per unsigned 16-bit half)
 static inline uint32_t emul_half_op(uint32_t a, uint32_t b, uint32_t (*f)(uint32_t, uint32_t)) {

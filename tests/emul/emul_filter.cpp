@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "usage: emul_filter in.bin out.bin n_shards [filter_grid]\n"); return 2; }
     const int n_shards = atoi(argv[3]);
     const unsigned fgrid = argc > 4 ? (unsigned)atoi(argv[4]) : 3u;
+    const bool join = argc > 5 && std::string(argv[5]) == "join";      // equality join instead of tile filter + verify
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     int32_t hdr[5];
@@ -65,8 +66,26 @@ int main(int argc, char** argv) {
     std::vector<uint2> cand((size_t)cap), pairs((size_t)cap);
     std::vector<uint2> all_pairs;
     unsigned long long cand_total = 0;
-    for (int shard = 0; shard < n_shards; ++shard) {       // every shard of the round-robin tile deal, one after the other
+    // equality join (the default of the library): keys, stable sort (cub radix sort on the device), one walk per shard
+    const long long nk = (long long)n * n_bands;
+    std::vector<uint32_t> skeys, svals, sigG;
+    if (join) {
+        std::vector<uint32_t> keys((size_t)nk, 0xDEADBEEFu), vals((size_t)nk, 0xDEADBEEFu), idx((size_t)nk);
+        sigG.assign((size_t)n * n_words, 0xDEADBEEFu);
+        emul::launch(2, 256, [&] { k_smh_sigkeys(aux.data(), n, m_aux, n_rows, n_bands, n_words, keys.data(), vals.data(), sigG.data()); });
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+        skeys.resize((size_t)nk); svals.resize((size_t)nk);
+        for (long long t = 0; t < nk; ++t) { skeys[(size_t)t] = keys[idx[(size_t)t]]; svals[(size_t)t] = vals[idx[(size_t)t]]; }
+    }
+    for (int shard = 0; shard < n_shards; ++shard) {       // every shard, one after the other
         meta[M_CAND] = meta[M_PAIRS] = 0;
+        if (join) {
+            emul::launch(fgrid, 256, [&] {
+                k_smh_join(skeys.data(), svals.data(), nk, 0, nk, sigG.data(), n_words, aux.data(), m_aux, n_rows, n_bands, lo.data(),
+                           hi.data(), shard, n_shards, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND);
+            });
+        } else {
         const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};
         emul::launch(fgrid, 256, [&] {
             k_tile_filter_smh(sigR.data(), sigC.data(), npad, n_words, tw, lo.data(), hi.data(), n, cand.data(),
@@ -76,10 +95,12 @@ int main(int argc, char** argv) {
             k_smh_verify(aux.data(), sigR.data(), npad, m_aux, n_rows, n_bands, cand.data(), meta.data() + M_CAND, cap,
                          pairs.data(), meta.data() + M_PAIRS, cap);
         });
+        }
         if (meta[M_CAND] > cap || meta[M_PAIRS] > cap) { fprintf(stderr, "list overflow\n"); return 3; }
         cand_total += meta[M_CAND];
         all_pairs.insert(all_pairs.end(), pairs.begin(), pairs.begin() + (long long)meta[M_PAIRS]);
     }
+    // shards must not overlap: a pair emitted twice would show up as a duplicate below
     std::sort(all_pairs.begin(), all_pairs.end(), [](uint2 a, uint2 b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
 
     f = fopen(argv[2], "wb");

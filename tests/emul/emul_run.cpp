@@ -2,7 +2,8 @@
 // them (csrc/selb200.cu: load_chunk, load_end, selb200_run), from the same .inl sources the GPU build compiles:
 //   load : k_max_byte, k_pair_hist<SrcSelf> (per-genome histograms), k_genome_cards (Ertl MLE + value range),
 //          k_planes_from_bytes, [host: sort by cardinality], k_sorted_prep, k_gather_rows
-//   run  : k_cb_bounds, k_rowblock_span, scan, k_tile_table, k_smh_signatures, k_tile_filter_smh, k_smh_verify,
+//   run  : k_cb_bounds, k_rowblock_span, scan, k_tile_table, k_smh_sigkeys, sort, k_smh_join (or, with a fourth argument
+//          "tiles": k_smh_signatures, k_tile_filter_smh, k_smh_verify),
 //          k_pair_hist_planes (+ k_pair_hist<SrcWide> for wide pairs), k_estimate_emit,
 //          k_rowsort_count, scan, k_rowsort_scatter, k_rowsort_rank
 // Input (file): registers and SuperMinHash sketches in FILE-LIST order, tau, band shape.
@@ -19,6 +20,7 @@
 #define SELB_EMUL 1
 #include "cuda_emul.h"
 #include "../../cuda_selection_criteria_b200/csrc/estimators.cuh"
+#include "../../cuda_selection_criteria_b200/csrc/hostpack.cpp"     // host packer of the packed upload (plain C++)
 
 constexpr int TILE = 128;          // as in csrc/selb200.cu
 constexpr int SIG_CHUNK = 8;
@@ -43,7 +45,7 @@ static void lap(const char* what) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: emul_run in.bin out.bin [subsets]\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: emul_run in.bin out.bin [subsets|planes [tiles]]\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     int32_t hdr[5];
@@ -58,6 +60,26 @@ int main(int argc, char** argv) {
     rd(f, smh.data(), smh.size());
     fclose(f);
 
+    // ------------------------------------------------------------------ packed upload (load_host_packed / unpack_pieces):
+    // the registers go through the host packer and the three unpack kernels, pieces of 50 rows (a short last one), and
+    // everything below works on what came out
+    {
+        const long long piece_rows = 50;
+        const selb::Nib4Piece P = selb::nib4_piece(piece_rows, m);
+        const unsigned n_pieces = (unsigned)((n + piece_rows - 1) / piece_rows);
+        std::vector<uint8_t> pieces((size_t)n_pieces * P.bytes, 0xCD), back((size_t)n * m, 0xEE);
+        for (unsigned pi = 0; pi < n_pieces; ++pi) {
+            const long long rows = std::min<long long>(piece_rows, n - (long long)pi * piece_rows);
+            selb::nib4_pack_piece(regs.data() + (size_t)pi * piece_rows * m, rows, m, pieces.data() + (size_t)pi * P.bytes, 1);
+        }
+        const Nib4Pieces a{pieces.data(), P.bytes, piece_rows, (long long)n, p};
+        emul::launch2(2, n_pieces, 256, [&] { k_unpack_nib4(a, back.data()); });
+        emul::launch2(1, n_pieces, 256, [&] { k_apply_nib4_exc(a, back.data()); });
+        emul::launch2(selb::NIB4_RAW_CAP, n_pieces, 256, [&] { k_apply_nib4_raw(a, back.data()); });
+        if (back != regs) { fprintf(stderr, "packed upload does not reproduce the register bytes\n"); return 5; }
+        regs.swap(back);
+    }
+    lap("packed upload");
     // ------------------------------------------------------------------ load (load_chunk / load_end)
     uint32_t flags[4] = {0, 0, 0, 0};          // max primary register, max aux register, tie flag
     emul::launch(2, 256, [&] { k_max_byte(reinterpret_cast<const uint4*>(regs.data()), (size_t)n * m / 16, flags); });
@@ -111,10 +133,32 @@ int main(int argc, char** argv) {
         k_tile_table(tile_prefix.data(), tile_cb0.data(), nrb, tile_cap, tile_rc.data(), meta.data());
     });
     lap("bounds + tiles");
-    std::vector<uint32_t> sigR((size_t)n_words * npad), sigC((size_t)n_words * npad);
-    emul::launch(2, 256, [&] { k_smh_signatures(aux_sorted.data(), n, npad, m_aux, n_rows, n_bands, sigR.data(), sigC.data()); });
     const unsigned long long cap = 1ull << 20;
     std::vector<uint2> cand((size_t)cap), pairs((size_t)cap);
+    const bool tiles_filter = argc > 4 && std::string(argv[4]) == "tiles";       // SELB200_SMHFILTER=tiles
+    if (!tiles_filter) {
+        // the default: equality join (k_smh_sigkeys -> stable sort by band | signature -> k_smh_join); the device build
+        // sorts with cub's radix sort, std::stable_sort stands in for it here
+        const long long nk = (long long)n * n_bands;
+        std::vector<uint32_t> keys((size_t)nk), vals((size_t)nk), sigG((size_t)n * n_words, 0xDEADBEEFu);
+        emul::launch(2, 256, [&] { k_smh_sigkeys(aux_sorted.data(), n, m_aux, n_rows, n_bands, n_words, keys.data(), vals.data(), sigG.data()); });
+        std::vector<uint32_t> idx((size_t)nk), skeys((size_t)nk), svals((size_t)nk);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+        for (long long t = 0; t < nk; ++t) { skeys[(size_t)t] = keys[idx[(size_t)t]]; svals[(size_t)t] = vals[idx[(size_t)t]]; }
+        // two launches over two halves of the keys, as after a split pass
+        const long long mid = nk / 3;
+        emul::launch(2, 256, [&] {
+            k_smh_join(skeys.data(), svals.data(), nk, 0, mid, sigG.data(), n_words, aux_sorted.data(), m_aux, n_rows, n_bands, lo.data(),
+                       hi.data(), 0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND);
+        });
+        emul::launch(3, 256, [&] {
+            k_smh_join(skeys.data(), svals.data(), nk, mid, nk, sigG.data(), n_words, aux_sorted.data(), m_aux, n_rows, n_bands, lo.data(),
+                       hi.data(), 0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND);
+        });
+    } else {
+    std::vector<uint32_t> sigR((size_t)n_words * npad), sigC((size_t)n_words * npad);
+    emul::launch(2, 256, [&] { k_smh_signatures(aux_sorted.data(), n, npad, m_aux, n_rows, n_bands, sigR.data(), sigC.data()); });
     const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, 0, 1, 0, INT32_MAX};
     emul::launch(3, 256, [&] {
         k_tile_filter_smh(sigR.data(), sigC.data(), npad, n_words, tw, lo.data(), hi.data(), n, cand.data(), meta.data() + M_CAND, cap);
@@ -123,6 +167,7 @@ int main(int argc, char** argv) {
         k_smh_verify(aux_sorted.data(), sigR.data(), npad, m_aux, n_rows, n_bands, cand.data(), meta.data() + M_CAND, cap,
                      pairs.data(), meta.data() + M_PAIRS, cap);
     });
+    }
     if (meta[M_CAND] > cap || meta[M_PAIRS] > cap) { fprintf(stderr, "list overflow\n"); return 3; }
     lap("signatures + filter + verify");
     const long long np = (long long)meta[M_PAIRS];

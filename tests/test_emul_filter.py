@@ -47,7 +47,7 @@ def oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands):
     return lo, hi, p_cb, pairs
 
 
-def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid):
+def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid, form="tiles"):
     n, m = aux_sorted.shape
     inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
@@ -55,7 +55,7 @@ def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards,
         f.write(struct.pack("<d", float(tau32)))          # tau = (double)(float) threshold, selection.cpp:81
         f.write(np.ascontiguousarray(e, np.uint64).tobytes())
         f.write(np.ascontiguousarray(aux_sorted, np.uint64).tobytes())
-    r = subprocess.run([exe, str(inp), str(outp), str(n_shards), str(grid)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([exe, str(inp), str(outp), str(n_shards), str(grid), form], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(outp, "rb").read()
     p_cb, tiles, cand, npairs = struct.unpack_from("<4q", raw, 0)
@@ -66,6 +66,7 @@ def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards,
     return lo, hi, p_cb, tiles, cand, [tuple(x) for x in pr.tolist()]
 
 
+@pytest.mark.parametrize("form", ["join", "tiles"])
 @pytest.mark.parametrize("n,seed,tau,m_aux,n_shards,grid", [
     (700, 41, 0.9, 128, 1, 3),        # the benchmark's shape: 16 bands x 8 rows, 8 signature words
     (600, 42, 0.75, 128, 2, 2),       # 32 bands x 4 rows: two chunks of signature words per tile; two shards
@@ -73,7 +74,7 @@ def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards,
     (300, 44, 0.9, 4, 3, 1),          # 2 bands x 2 rows: one signature word; three shards, one CTA
     (250, 45, 0.9, 1, 1, 2),          # 1 band x 1 row: the odd band count leaves a pad half that must never match
 ])
-def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, n_shards, grid):
+def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, n_shards, grid, form):
     tau32 = np.float32(tau)
     plan = synth.make_plan(n, seed)
     regs = synth.hll(plan, 14)
@@ -85,7 +86,7 @@ def test_cb_and_smh_a_decisions_on_the_emulator(exe, tmp_path, n, seed, tau, m_a
     aux_sorted = np.ascontiguousarray(smh[order])
     n_bands, n_rows = O.band_params(m_aux, tau32)
     assert n_bands * n_rows == m_aux
-    lo, hi, p_cb, tiles, cand, pairs = run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid)
+    lo, hi, p_cb, tiles, cand, pairs = run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards, grid, form)
     olo, ohi, op_cb, opairs = oracle_decisions(e, aux_sorted, tau32, n_rows, n_bands)
     rows_with_band = ohi >= olo
     assert np.array_equal(lo[rows_with_band], olo[rows_with_band]) and np.array_equal(hi[rows_with_band], ohi[rows_with_band])

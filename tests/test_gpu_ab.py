@@ -43,6 +43,7 @@ def _run(env_extra, tmp_path):
     env = dict(os.environ)
     env.pop("SELB200_UNION", None)
     env.pop("SELB200_HLLFILTER", None)
+    env.pop("SELB200_SMHFILTER", None)
     env.update(env_extra)
     r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -58,4 +59,6 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
     assert onehot == by
     onepass = _run({"SELB200_HLLFILTER": "onepass"}, tmp_path)
     assert onepass == by
+    tiles = _run({"SELB200_SMHFILTER": "tiles"}, tmp_path)        # all-pairs tile filter + verify instead of the equality join
+    assert tiles == by
     assert all(v[1] > 1000 for v in default.values())          # thousands of emitted pairs in every case
