@@ -448,6 +448,11 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
             "latency-bound: seven small launches (keys, five of the sort, walk) over 13 MB")
     elif cfg.criterion == "smh_a":
         nb = st["n_bands"]
+        add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, float((nb + 1) // 2),
+            f"one packed min/add lane-operation (VIADDMNMX.U16x2) per two LSH bands and pair: {(nb + 1) // 2} per CB pair of the shard "
+            "(a thread owns an 8x8 block of pairs, so one lane-operation serves one pair)")
+        add("verify", "k_smh_verify", mean("ms_verify"), "hbm", p_cand, 2.0 * 8 * st["n_rows"] + 16,
+            "2 x 8 x n_rows bucket bytes + 16 B per candidate", "latency-bound: thread per candidate, dependent loads")
     elif cfg.criterion in ("hll_a", "hll_an"):
         regs_aux = cfg.aux_bytes
         mode = os.environ.get("SELB200_HLLFILTER", "")

@@ -243,8 +243,10 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 // sorted position) and every run of equal keys is walked: work O(n * bands + matches).
 //   k_smh_sigkeys : keys, values (= sorted position) in genome-major order, and the signatures genome-major (sigG: two
 //                   bands per word, nbw words per genome = 32 B at 16 bands) for the step below
-//   k_smh_join    : thread per sorted key (band b, genome i): its followers k in the run with k <= hi(i) are the pairs of
-//                   the CB band whose band-b signatures agree.  A pair is handled ONCE, by the first band whose signatures
+//   k_smh_join_count + scan + k_smh_join : the followers k of a sorted key (band b, genome i) in its run with k <= hi(i) are
+//                   the pairs of the CB band whose band-b signatures agree; they are counted per key, prefix-summed, and
+//                   handled one per thread (a run of a thousand identical bands is 5e5 items for as many threads, not a
+//                   serial walk of one).  A pair is handled ONCE, by the first band whose signatures
 //                   agree (the thread reads the earlier bands' signatures of both genomes: 32 B each): that handler
 //                   compares the buckets of every signature-equal band from b on, exactly, and emits the pair at the first
 //                   band that really is equal — the decision of k_smh_verify, so P_aux is the reference's.
@@ -280,45 +282,73 @@ __device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, 
     return true;
 }
 
+// followers of key s: the keys t > s of its run whose genome lies inside the CB band of genome vals[s].  Inside a run
+// the positions ascend, so "same key and position <= hi(i)" holds for a prefix of what follows s: galloping search
+// (most runs are one or two keys long: one or two loads).  cnt[s] = that number for s in [s0, s1), 0 elsewhere; cnt[n_keys] = 0.
 __global__ void __launch_bounds__(256)
-k_smh_join(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
-           const uint32_t* __restrict__ sigG, int nbw, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
-           const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int shard, int n_shards,
+k_smh_join_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
+                 const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, unsigned long long* __restrict__ cnt) {
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s <= n_keys; s += (long long)gridDim.x * blockDim.x) {
+        unsigned long long c = 0;
+        if (s >= s0 && s < s1) {
+            const uint32_t key = keys[s];
+            const int i = (int)vals[s];
+            const int hi_i = hi[i];
+            if (hi_i >= lo[i]) {
+                auto ok = [&](long long t) { return t < n_keys && keys[t] == key && (int)vals[t] <= hi_i; };
+                // largest d with ok(s + d) (ok(s + d) true for d = 1 .. c, false afterwards)
+                long long step = 1, good = 0;
+                while (ok(s + good + step)) { good += step; step <<= 1; }
+                for (step >>= 1; step >= 1; step >>= 1)
+                    if (ok(s + good + step)) good += step;
+                c = (unsigned long long)good;
+            }
+        }
+        cnt[s] = c;
+    }
+}
+
+// work item w = the (w - off[s])-th follower of key s, off = exclusive prefix sums of cnt (off[n_keys] = items in all):
+// a thread finds its key by binary search and handles the pair (see the header above)
+__global__ void __launch_bounds__(256)
+k_smh_join(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys,
+           const unsigned long long* __restrict__ off, const uint32_t* __restrict__ sigG, int nbw,
+           const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands, int shard, int n_shards,
            uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap,
            unsigned long long* __restrict__ cand_count) {
+    const unsigned long long n_items = off[n_keys];
     uint32_t n_cand = 0;
-    for (long long s = s0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; s < s1; s += (long long)gridDim.x * blockDim.x) {
-        const uint32_t key = keys[s];
-        const int i = (int)vals[s], b = (int)(key >> 16);
-        const int lo_i = lo[i], hi_i = hi[i];
-        if (hi_i < lo_i) continue;
+    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        long long a = 0, b = n_keys;                      // last s with off[s] <= w
+        while (b - a > 1) {
+            const long long mid = (a + b) >> 1;
+            if (__ldg(off + mid) <= w) a = mid; else b = mid;
+        }
+        const long long s = a, t = s + 1 + (long long)(w - __ldg(off + s));
+        const int i = (int)vals[s], k = (int)vals[t], bnd = (int)(keys[s] >> 16);
+        if (n_shards > 1 && (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) != shard) continue;
         const uint32_t* si = sigG + (size_t)i * nbw;
-        for (long long t = s + 1; t < n_keys && keys[t] == key; ++t) {
-            const int k = (int)vals[t];                    // > i: equal keys keep ascending position
-            if (k > hi_i) break;
-            if (k < lo_i) continue;
-            if (n_shards > 1 && (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) != shard) continue;
-            const uint32_t* sk = sigG + (size_t)k * nbw;
-            // an earlier band with equal signatures handles the pair
-            bool earlier = false;
-            for (int w = 0; w <= (b >> 1) && !earlier; ++w) {
-                const uint32_t x = __ldg(si + w) ^ __ldg(sk + w);
-                if (2 * w < b && (x & 0xffffu) == 0u) earlier = true;
-                if (2 * w + 1 < b && (x >> 16) == 0u) earlier = true;
-            }
-            if (earlier) continue;
-            ++n_cand;
-            const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
-            const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
-            bool hit = smh_band_equal(v1, v2, b, n_rows);
-            for (int b2 = b + 1; b2 < n_bands && !hit; ++b2) {
-                const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
-                if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);
-            }
-            if (hit) {
-                const unsigned long long slot = warp_claim(pair_count);
-                if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
-            }
+        const uint32_t* sk = sigG + (size_t)k * nbw;
+        // an earlier band with equal signatures handles the pair
+        bool earlier = false;
+        for (int wd = 0; wd <= (bnd >> 1) && !earlier; ++wd) {
+            const uint32_t x = __ldg(si + wd) ^ __ldg(sk + wd);
+            if (2 * wd < bnd && (x & 0xffffu) == 0u) earlier = true;
+            if (2 * wd + 1 < bnd && (x >> 16) == 0u) earlier = true;
+        }
+        if (earlier) continue;
+        ++n_cand;
+        const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
+        const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
+        bool hit = smh_band_equal(v1, v2, bnd, n_rows);
+        for (int b2 = bnd + 1; b2 < n_bands && !hit; ++b2) {
+            const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
+            if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);
+        }
+        if (hit) {
+            const unsigned long long slot = warp_claim(pair_count);
+            if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
         }
     }
     if (n_cand) atomicAdd(cand_count, (unsigned long long)n_cand);

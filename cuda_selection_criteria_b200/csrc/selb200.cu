@@ -1058,6 +1058,9 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
     const bool smh_join = use_smh && smh_join_enabled() && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
     const long long jn_keys = (long long)n * n_bands;
+    // join_buf: keys, values, sorted keys, sorted values (u32 each), genome-major signatures, then (8-byte aligned) the
+    // follower counts and their prefix sums (u64 each, jn_keys + 1)
+    const long long jn_words = ((4 * jn_keys + (long long)n * ((n_bands + 1) / 2)) + 1) & ~1ll;
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
@@ -1185,7 +1188,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         if (use_smh && smh_join) {
             // keys + values (unsorted, sorted) and genome-major signatures; one stable radix sort over band | signature
             cudaEvent_t a0 = c->ev();
-            CKR(c->join_buf.ensure(((size_t)4 * jn_keys + (size_t)n * n_words) * 4));
+            CKR(c->join_buf.ensure((size_t)jn_words * 4 + (size_t)2 * (jn_keys + 1) * 8));
             uint32_t* jk = c->join_buf.as<uint32_t>();
             int key_bits = 16;
             while ((1 << (key_bits - 16)) < n_bands) ++key_bits;
@@ -1239,11 +1242,21 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                     s1 = jn_keys * std::min<long long>(rg.second, t_end) / t_end;
                 }
                 const uint32_t* jk = c->join_buf.as<uint32_t>();
-                const int grid = (int)std::max<long long>(1, std::min<long long>((s1 - s0 + 255) / 256, (long long)c->sm_count * 16));
-                k_smh_join<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, jk + 4 * jn_keys, n_words,
-                                                c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, c->lo.as<int32_t>(),
-                                                c->hi.as<int32_t>(), prm->shard, n_shards, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
-                                                (unsigned long long)PAIR_CAP, d_cnt + M_CAND);
+                unsigned long long* jcnt = reinterpret_cast<unsigned long long*>(c->join_buf.as<uint32_t>() + jn_words);
+                unsigned long long* joff = jcnt + (jn_keys + 1);
+                const int grid = (int)std::max<long long>(1, std::min<long long>((jn_keys + 256) / 256, (long long)c->sm_count * 16));
+                k_smh_join_count<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, c->lo.as<int32_t>(),
+                                                      c->hi.as<int32_t>(), jcnt);
+                CK(cudaGetLastError());
+                size_t tmp_bytes = 0;
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, jcnt, joff, (int)(jn_keys + 1), s));
+                CKR(c->cub_tmp.ensure(tmp_bytes));
+                CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, jcnt, joff, (int)(jn_keys + 1), s));
+                k_smh_join<<<c->sm_count * 16, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, joff, jk + 4 * jn_keys, n_words,
+                                                            c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, prm->shard, n_shards,
+                                                            c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP,
+                                                            d_cnt + M_CAND);
+                st.launches += 2;
             } else if (crit == SELB200_CRIT_SMH_A) {
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
                 k_tile_filter_smh<<<grid, 256, 0, s>>>(
