@@ -243,10 +243,10 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 // sorted position) and every run of equal keys is walked: work O(n * bands + matches).
 //   k_smh_sigkeys : keys, values (= sorted position) in genome-major order, and the signatures genome-major (sigG: two
 //                   bands per word, nbw words per genome = 32 B at 16 bands) for the step below
-//   k_smh_join_count + scan + k_smh_join : the followers k of a sorted key (band b, genome i) in its run with k <= hi(i) are
-//                   the pairs of the CB band whose band-b signatures agree; they are counted per key, prefix-summed, and
-//                   handled one per thread (a run of a thousand identical bands is 5e5 items for as many threads, not a
-//                   serial walk of one).  A pair is handled ONCE, by the first band whose signatures
+//   k_smh_join_expand + k_smh_join : the followers k of a sorted key (band b, genome i) in its run with k <= hi(i) are
+//                   the pairs of the CB band whose band-b signatures agree; every (key, follower) is written out as an
+//                   item and handled by a thread of its own (a run of a thousand identical bands is 5e5 items for as
+//                   many threads, not a serial walk).  A pair is handled ONCE, by the first band whose signatures
 //                   agree (the thread reads the earlier bands' signatures of both genomes: 32 B each): that handler
 //                   compares the buckets of every signature-equal band from b on, exactly, and emits the pair at the first
 //                   band that really is equal — the decision of k_smh_verify, so P_aux is the reference's.
@@ -275,67 +275,103 @@ k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, i
     }
 }
 
-// buckets of band b of the two genomes equal?
+// buckets of band b of the two genomes equal?  All loads are issued before the first compare (a chain of load, compare,
+// branch per bucket costs a DRAM round trip each: the sketches are not cache-resident)
 __device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, const uint64_t* __restrict__ v2, int b, int n_rows) {
+    const uint64_t* p1 = v1 + (size_t)b * n_rows;
+    const uint64_t* p2 = v2 + (size_t)b * n_rows;
+    if (!(n_rows & 1) && !(((size_t)b * n_rows) & 1)) {            // 16-byte aligned rows of pairs (sketch rows are 8m bytes, m even here)
+        const ulonglong2* q1 = reinterpret_cast<const ulonglong2*>(p1);
+        const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(p2);
+        unsigned long long diff = 0ull;
+        int r = 0;
+        for (; r + 4 <= (n_rows >> 1); r += 4) {
+            const ulonglong2 a0 = __ldg(q1 + r), a1 = __ldg(q1 + r + 1), a2 = __ldg(q1 + r + 2), a3 = __ldg(q1 + r + 3);
+            const ulonglong2 c0 = __ldg(q2 + r), c1 = __ldg(q2 + r + 1), c2 = __ldg(q2 + r + 2), c3 = __ldg(q2 + r + 3);
+            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y) | (a1.x ^ c1.x) | (a1.y ^ c1.y) | (a2.x ^ c2.x) | (a2.y ^ c2.y) | (a3.x ^ c3.x) | (a3.y ^ c3.y);
+            if (diff) return false;
+        }
+        for (; r < (n_rows >> 1); ++r) {
+            const ulonglong2 a0 = __ldg(q1 + r), c0 = __ldg(q2 + r);
+            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y);
+        }
+        return diff == 0ull;
+    }
     for (int r = 0; r < n_rows; ++r)
-        if (__ldg(v1 + (size_t)b * n_rows + r) != __ldg(v2 + (size_t)b * n_rows + r)) return false;
+        if (__ldg(p1 + r) != __ldg(p2 + r)) return false;
     return true;
 }
 
 // followers of key s: the keys t > s of its run whose genome lies inside the CB band of genome vals[s].  Inside a run
 // the positions ascend, so "same key and position <= hi(i)" holds for a prefix of what follows s: galloping search
-// (most runs are one or two keys long: one or two loads).  cnt[s] = that number for s in [s0, s1), 0 elsewhere; cnt[n_keys] = 0.
+// (most runs are one or two keys long: one or two loads).  Every (key, follower) becomes one ITEM {i, k, band}: a warp
+// claims the room for its lanes' items with one atomic and the lanes write them — the walk itself is then one thread per
+// item (k_smh_join), whatever the length of the runs.
 __global__ void __launch_bounds__(256)
-k_smh_join_count(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
-                 const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, unsigned long long* __restrict__ cnt) {
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s <= n_keys; s += (long long)gridDim.x * blockDim.x) {
+k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
+                  const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, uint4* __restrict__ items,
+                  unsigned long long* __restrict__ item_count, unsigned long long item_cap) {
+    const int lane = threadIdx.x & 31;
+    for (long long sb = s0 + (blockIdx.x * (long long)blockDim.x + threadIdx.x - lane); sb < s1; sb += (long long)gridDim.x * blockDim.x) {
+        const long long s = sb + lane;
         unsigned long long c = 0;
-        if (s >= s0 && s < s1) {
-            const uint32_t key = keys[s];
-            const int i = (int)vals[s];
+        uint32_t key = 0;
+        int i = 0;
+        if (s < s1) {
+            key = keys[s];
+            i = (int)vals[s];
             const int hi_i = hi[i];
             if (hi_i >= lo[i]) {
                 auto ok = [&](long long t) { return t < n_keys && keys[t] == key && (int)vals[t] <= hi_i; };
-                // largest d with ok(s + d) (ok(s + d) true for d = 1 .. c, false afterwards)
-                long long step = 1, good = 0;
+                long long step = 1, good = 0;          // largest d with ok(s + d): true for d = 1 .. c, false afterwards
                 while (ok(s + good + step)) { good += step; step <<= 1; }
                 for (step >>= 1; step >= 1; step >>= 1)
                     if (ok(s + good + step)) good += step;
                 c = (unsigned long long)good;
             }
         }
-        cnt[s] = c;
+        unsigned long long pre = c;                    // inclusive scan over the lanes
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += v;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, pre, 31);
+        if (total == 0ull) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(item_count, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + (pre - c);
+        for (unsigned long long d = 0; d < c; ++d)
+            if (base + d < item_cap) items[base + d] = make_uint4((uint32_t)i, vals[s + 1 + (long long)d], key >> 16, 0u);
     }
 }
 
-// work item w = the (w - off[s])-th follower of key s, off = exclusive prefix sums of cnt (off[n_keys] = items in all):
-// a thread finds its key by binary search and handles the pair (see the header above)
+// one thread per item {i, k, band}: see the header above
 __global__ void __launch_bounds__(256)
-k_smh_join(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys,
-           const unsigned long long* __restrict__ off, const uint32_t* __restrict__ sigG, int nbw,
-           const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands, int shard, int n_shards,
-           uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count, unsigned long long pair_cap,
-           unsigned long long* __restrict__ cand_count) {
-    const unsigned long long n_items = off[n_keys];
+k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict__ item_count, unsigned long long item_cap,
+           const uint32_t* __restrict__ sigG, int nbw, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
+           int shard, int n_shards, uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
+           unsigned long long pair_cap, unsigned long long* __restrict__ cand_count, unsigned long long* __restrict__ item_max) {
+    const unsigned long long n_items = min(*item_count, item_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(item_max, *item_count);     // the host grows the list and redoes the pass if it overflowed
     uint32_t n_cand = 0;
     for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
          w += (unsigned long long)gridDim.x * blockDim.x) {
-        long long a = 0, b = n_keys;                      // last s with off[s] <= w
-        while (b - a > 1) {
-            const long long mid = (a + b) >> 1;
-            if (__ldg(off + mid) <= w) a = mid; else b = mid;
-        }
-        const long long s = a, t = s + 1 + (long long)(w - __ldg(off + s));
-        const int i = (int)vals[s], k = (int)vals[t], bnd = (int)(keys[s] >> 16);
+        const uint4 it = __ldg(items + w);
+        const int i = (int)it.x, k = (int)it.y, bnd = (int)it.z;
         if (n_shards > 1 && (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) != shard) continue;
         const uint32_t* si = sigG + (size_t)i * nbw;
         const uint32_t* sk = sigG + (size_t)k * nbw;
-        // an earlier band with equal signatures handles the pair
+        // an earlier band with equal signatures handles the pair (words of four at a time: independent loads)
         bool earlier = false;
-        for (int wd = 0; wd <= (bnd >> 1) && !earlier; ++wd) {
-            const uint32_t x = __ldg(si + wd) ^ __ldg(sk + wd);
-            if (2 * wd < bnd && (x & 0xffffu) == 0u) earlier = true;
-            if (2 * wd + 1 < bnd && (x >> 16) == 0u) earlier = true;
+        for (int wd = 0; wd <= (bnd >> 1) && !earlier; wd += 4) {
+            uint32_t x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = wd + u <= (bnd >> 1) ? (__ldg(si + wd + u) ^ __ldg(sk + wd + u)) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (2 * (wd + u) < bnd && (x[u] & 0xffffu) == 0u) earlier = true;
+                if (2 * (wd + u) + 1 < bnd && (x[u] >> 16) == 0u) earlier = true;
+            }
         }
         if (earlier) continue;
         ++n_cand;

@@ -205,7 +205,8 @@ struct selb200_ctx {
     LoadState ld;
     PackSlot pack_slots[4];
     DevBuf pk_buf;                       // packed pieces as they land on the device, before k_unpack_nib4
-    DevBuf join_buf;                     // smh_a equality join: keys / values, unsorted and sorted, and the genome-major signatures
+    DevBuf join_buf, join_items;         // smh_a equality join: keys / values, unsorted and sorted, genome-major signatures; items
+    int64_t join_item_cap = 0;           // grow-only, like every other list of the run
     StageSlot slots[3];
     int next_slot = 0;
     bool _order_cache_valid = false;
@@ -807,7 +808,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1058,9 +1059,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
     const bool smh_join = use_smh && smh_join_enabled() && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
     const long long jn_keys = (long long)n * n_bands;
-    // join_buf: keys, values, sorted keys, sorted values (u32 each), genome-major signatures, then (8-byte aligned) the
-    // follower counts and their prefix sums (u64 each, jn_keys + 1)
-    const long long jn_words = ((4 * jn_keys + (long long)n * ((n_bands + 1) / 2)) + 1) & ~1ll;
+    // join_buf: keys, values, sorted keys, sorted values (u32 each), genome-major signatures
+    const long long jn_words = 4 * jn_keys + (long long)n * ((n_bands + 1) / 2);
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
@@ -1188,7 +1188,9 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         if (use_smh && smh_join) {
             // keys + values (unsorted, sorted) and genome-major signatures; one stable radix sort over band | signature
             cudaEvent_t a0 = c->ev();
-            CKR(c->join_buf.ensure((size_t)jn_words * 4 + (size_t)2 * (jn_keys + 1) * 8));
+            CKR(c->join_buf.ensure((size_t)jn_words * 4));
+            if (c->join_item_cap < (4ll << 20)) c->join_item_cap = 4ll << 20;
+            CKR(c->join_items.ensure((size_t)c->join_item_cap * sizeof(uint4)));
             uint32_t* jk = c->join_buf.as<uint32_t>();
             int key_bits = 16;
             while ((1 << (key_bits - 16)) < n_bands) ++key_bits;
@@ -1221,6 +1223,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             CK(cudaMemsetAsync(d_cnt, 0, 32, s));
             CK(cudaMemsetAsync(d_cnt + M_PUSHED, 0, 8, s));
             CK(cudaMemsetAsync(d_cnt + M_STEPS, 0, 8, s));
+            CK(cudaMemsetAsync(d_cnt + M_ITEMS_MAX, 0, 8, s));
         }
         const unsigned long long pair_lim = (unsigned long long)std::min<int64_t>(PAIR_CAP, c->hist_cap_pairs);
         for (size_t ri = 0; ri < ranges.size(); ++ri) {
@@ -1242,21 +1245,17 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                     s1 = jn_keys * std::min<long long>(rg.second, t_end) / t_end;
                 }
                 const uint32_t* jk = c->join_buf.as<uint32_t>();
-                unsigned long long* jcnt = reinterpret_cast<unsigned long long*>(c->join_buf.as<uint32_t>() + jn_words);
-                unsigned long long* joff = jcnt + (jn_keys + 1);
-                const int grid = (int)std::max<long long>(1, std::min<long long>((jn_keys + 256) / 256, (long long)c->sm_count * 16));
-                k_smh_join_count<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, c->lo.as<int32_t>(),
-                                                      c->hi.as<int32_t>(), jcnt);
+                CK(cudaMemsetAsync(d_cnt + M_ITEMS, 0, 8, s));
+                const int grid = (int)std::max<long long>(1, std::min<long long>((s1 - s0 + 255) / 256, (long long)c->sm_count * 16));
+                k_smh_join_expand<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, c->lo.as<int32_t>(),
+                                                       c->hi.as<int32_t>(), c->join_items.as<uint4>(), d_cnt + M_ITEMS,
+                                                       (unsigned long long)c->join_item_cap);
                 CK(cudaGetLastError());
-                size_t tmp_bytes = 0;
-                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, jcnt, joff, (int)(jn_keys + 1), s));
-                CKR(c->cub_tmp.ensure(tmp_bytes));
-                CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, jcnt, joff, (int)(jn_keys + 1), s));
-                k_smh_join<<<c->sm_count * 16, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, joff, jk + 4 * jn_keys, n_words,
-                                                            c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows, n_bands, prm->shard, n_shards,
-                                                            c->pairs.as<uint2>(), d_cnt + M_PAIRS, (unsigned long long)PAIR_CAP,
-                                                            d_cnt + M_CAND);
-                st.launches += 2;
+                k_smh_join<<<c->sm_count * 16, 256, 0, s>>>(c->join_items.as<uint4>(), d_cnt + M_ITEMS, (unsigned long long)c->join_item_cap,
+                                                            jk + 4 * jn_keys, n_words, c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows,
+                                                            n_bands, prm->shard, n_shards, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
+                                                            (unsigned long long)PAIR_CAP, d_cnt + M_CAND, d_cnt + M_ITEMS_MAX);
+                st.launches += 1;
             } else if (crit == SELB200_CRIT_SMH_A) {
                 const int grid = (int)std::min<int64_t>(nt, (int64_t)c->sm_count * smh_grid_per_sm);
                 k_tile_filter_smh<<<grid, 256, 0, s>>>(
@@ -1408,6 +1407,11 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             pair_sum += (int64_t)sn[1];
         }
         if ((int64_t)h_fin[M_OUT] > c->out_cap) { c->out_cap = (int64_t)h_fin[M_OUT] + (1 << 16); redo = true; }
+        // the join's item list: the largest count of any range of the pass
+        if (smh_join && (int64_t)h_fin[M_ITEMS_MAX] > c->join_item_cap) {
+            c->join_item_cap = (int64_t)h_fin[M_ITEMS_MAX] + (int64_t)h_fin[M_ITEMS_MAX] / 4;
+            redo = true;
+        }
         // the near-tau list is part of the result (north_star: "listed separately"): never truncated, grown like the others
         if ((int64_t)h_fin[M_NEAR] > c->near_cap) { c->near_cap = (int64_t)h_fin[M_NEAR] + (1 << 12); redo = true; }
         if (!redo) {

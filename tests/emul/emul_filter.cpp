@@ -81,12 +81,16 @@ int main(int argc, char** argv) {
     for (int shard = 0; shard < n_shards; ++shard) {       // every shard, one after the other
         meta[M_CAND] = meta[M_PAIRS] = 0;
         if (join) {
-            std::vector<unsigned long long> cnt((size_t)nk + 1, 0xDEADBEEFull), off((size_t)nk + 1);
-            emul::launch(2, 256, [&] { k_smh_join_count(skeys.data(), svals.data(), nk, 0, nk, lo.data(), hi.data(), cnt.data()); });
-            std::exclusive_scan(cnt.begin(), cnt.end(), off.begin(), 0ull);          // cub::DeviceScan::ExclusiveSum
+            const unsigned long long item_cap = 1ull << 22;
+            std::vector<uint4> items((size_t)item_cap);
+            meta[M_ITEMS] = 0;
+            emul::launch(2, 256, [&] {
+                k_smh_join_expand(skeys.data(), svals.data(), nk, 0, nk, lo.data(), hi.data(), items.data(), meta.data() + M_ITEMS, item_cap);
+            });
+            if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(fgrid, 256, [&] {
-                k_smh_join(skeys.data(), svals.data(), nk, off.data(), sigG.data(), n_words, aux.data(), m_aux, n_rows, n_bands,
-                           shard, n_shards, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND);
+                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, aux.data(), m_aux, n_rows, n_bands,
+                           shard, n_shards, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         } else {
         const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};

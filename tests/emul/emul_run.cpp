@@ -146,16 +146,20 @@ int main(int argc, char** argv) {
         std::iota(idx.begin(), idx.end(), 0u);
         std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
         for (long long t = 0; t < nk; ++t) { skeys[(size_t)t] = keys[idx[(size_t)t]]; svals[(size_t)t] = vals[idx[(size_t)t]]; }
-        // two passes over two parts of the keys, as after a split pass: count the followers, prefix sums, one thread per item
+        // two passes over two parts of the keys, as after a split pass: expand the followers into items, one thread per item
         const long long mid = nk / 3;
-        std::vector<unsigned long long> cnt((size_t)nk + 1), off((size_t)nk + 1);
+        const unsigned long long item_cap = 1ull << 22;
+        std::vector<uint4> items((size_t)item_cap);
         for (int part = 0; part < 2; ++part) {
             const long long s0 = part ? mid : 0, s1 = part ? nk : mid;
-            emul::launch(2, 256, [&] { k_smh_join_count(skeys.data(), svals.data(), nk, s0, s1, lo.data(), hi.data(), cnt.data()); });
-            std::exclusive_scan(cnt.begin(), cnt.end(), off.begin(), 0ull);          // cub::DeviceScan::ExclusiveSum
+            meta[M_ITEMS] = 0;
+            emul::launch(2, 256, [&] {
+                k_smh_join_expand(skeys.data(), svals.data(), nk, s0, s1, lo.data(), hi.data(), items.data(), meta.data() + M_ITEMS, item_cap);
+            });
+            if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(part ? 3 : 2, 256, [&] {
-                k_smh_join(skeys.data(), svals.data(), nk, off.data(), sigG.data(), n_words, aux_sorted.data(), m_aux, n_rows, n_bands,
-                           0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND);
+                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, aux_sorted.data(), m_aux, n_rows, n_bands,
+                           0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         }
     } else {
