@@ -320,8 +320,10 @@ k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
         if (s < s1) {
             key = keys[s];
             i = (int)vals[s];
-            const int hi_i = hi[i];
-            if (hi_i >= lo[i]) {
+            // most keys have no follower at all: settled by the neighbouring key, before the loads that depend on vals[s]
+            const bool alone = s + 1 >= n_keys || keys[s + 1] != key;
+            const int hi_i = alone ? -1 : hi[i];
+            if (!alone && hi_i >= lo[i]) {
                 auto ok = [&](long long t) { return t < n_keys && keys[t] == key && (int)vals[t] <= hi_i; };
                 long long step = 1, good = 0;          // largest d with ok(s + d): true for d = 1 .. c, false afterwards
                 while (ok(s + good + step)) { good += step; step <<= 1; }
@@ -353,41 +355,66 @@ k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict
            unsigned long long pair_cap, unsigned long long* __restrict__ cand_count, unsigned long long* __restrict__ item_max) {
     const unsigned long long n_items = min(*item_count, item_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(item_max, *item_count);     // the host grows the list and redoes the pass if it overflowed
+    __shared__ uint32_t s_warp_hits[8];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t n_cand = 0;
-    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
-         w += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint4 it = __ldg(items + w);
-        const int i = (int)it.x, k = (int)it.y, bnd = (int)it.z;
-        if (n_shards > 1 && (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) != shard) continue;
-        const uint32_t* si = sigG + (size_t)i * nbw;
-        const uint32_t* sk = sigG + (size_t)k * nbw;
-        // an earlier band with equal signatures handles the pair (words of four at a time: independent loads)
-        bool earlier = false;
-        for (int wd = 0; wd <= (bnd >> 1) && !earlier; wd += 4) {
-            uint32_t x[4];
+    // the loop is uniform over the CTA (block barriers inside): every thread runs the same number of rounds
+    for (unsigned long long w0 = blockIdx.x * (unsigned long long)blockDim.x; w0 < n_items; w0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long w = w0 + threadIdx.x;
+        bool hit = false;
+        int i = 0, k = 0;
+        if (w < n_items) {
+            const uint4 it = __ldg(items + w);
+            i = (int)it.x; k = (int)it.y;
+            const int bnd = (int)it.z;
+            if (n_shards <= 1 || (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) == shard) {
+                const uint32_t* si = sigG + (size_t)i * nbw;
+                const uint32_t* sk = sigG + (size_t)k * nbw;
+                // an earlier band with equal signatures handles the pair (words of four at a time: independent loads)
+                bool earlier = false;
+                for (int wd = 0; wd <= (bnd >> 1) && !earlier; wd += 4) {
+                    uint32_t x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = wd + u <= (bnd >> 1) ? (__ldg(si + wd + u) ^ __ldg(sk + wd + u)) : 0xffffffffu;
+                    for (int u = 0; u < 4; ++u) x[u] = wd + u <= (bnd >> 1) ? (__ldg(si + wd + u) ^ __ldg(sk + wd + u)) : 0xffffffffu;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (2 * (wd + u) < bnd && (x[u] & 0xffffu) == 0u) earlier = true;
-                if (2 * (wd + u) + 1 < bnd && (x[u] >> 16) == 0u) earlier = true;
+                    for (int u = 0; u < 4; ++u) {
+                        if (2 * (wd + u) < bnd && (x[u] & 0xffffu) == 0u) earlier = true;
+                        if (2 * (wd + u) + 1 < bnd && (x[u] >> 16) == 0u) earlier = true;
+                    }
+                }
+                if (!earlier) {
+                    ++n_cand;
+                    const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
+                    const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
+                    hit = smh_band_equal(v1, v2, bnd, n_rows);
+                    for (int b2 = bnd + 1; b2 < n_bands && !hit; ++b2) {
+                        const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
+                        if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);
+                    }
+                }
             }
         }
-        if (earlier) continue;
-        ++n_cand;
-        const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
-        const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
-        bool hit = smh_band_equal(v1, v2, bnd, n_rows);
-        for (int b2 = bnd + 1; b2 < n_bands && !hit; ++b2) {
-            const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
-            if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);
+        // one claim per CTA and round: hits are common here (half a million on the bench), and claims of one word
+        // from every warp serialise in the L2
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp_hits[wid] = (uint32_t)__popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int q = 0; q < 8; ++q) { const uint32_t c = s_warp_hits[q]; s_warp_hits[q] = tot; tot += c; }
+            s_base = tot ? atomicAdd(pair_count, (unsigned long long)tot) : 0ull;
         }
+        __syncthreads();
         if (hit) {
-            const unsigned long long slot = warp_claim(pair_count);
+            const unsigned long long slot = s_base + s_warp_hits[wid] + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
             if (slot < pair_cap) pairs[slot] = make_uint2((uint32_t)i, (uint32_t)k);
         }
+        __syncthreads();                               // s_warp_hits / s_base are rewritten in the next round
     }
-    if (n_cand) atomicAdd(cand_count, (unsigned long long)n_cand);
+    // one atomic per warp: 600 k threads adding to one word is what the kernel's time was (same-address atomics serialise)
+    for (int o = 16; o; o >>= 1) n_cand += __shfl_xor_sync(0xffffffffu, n_cand, o);
+    if ((threadIdx.x & 31) == 0 && n_cand) atomicAdd(cand_count, (unsigned long long)n_cand);
 }
 
 // CB only: every pair of the band inside this tile

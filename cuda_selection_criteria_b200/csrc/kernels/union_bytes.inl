@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(64)
 k_pair_hist(const uint8_t* __restrict__ regs, size_t row_stride, size_t m, Src src, Epi epi) {
     __shared__ __align__(1024) uint32_t hist[NB * 64];
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, tb = t * 4;
+    if ((long long)blockIdx.x * 2 >= src.count()) return;      // nothing for this CTA (the wide list is usually empty)
     const uint32_t bias = hist_bias(hist);
 #pragma unroll 4
     for (int b = 0; b < NB; ++b) hist[b * 64 + t] = 0;
