@@ -412,7 +412,7 @@ def _protect_stdout():
     return os.fdopen(saved, "w")
 
 
-def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
+def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm, n_shards=1):
     """One entry per stage of the run (this rank's launches, CUDA events inside the library): time, share of the run,
     the roof that binds it and the achieved fraction.  Integer-pipe entries count ESSENTIAL lane-operations (the
     instructions the algorithm needs, not the ones issued) against the alu-pipe rate of the SM; byte entries count
@@ -438,7 +438,8 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm):
     p_cb, p_cand, p_aux, p_out = st["pairs_cb_shard"], st["pairs_cand"], st["pairs_aux"], st["pairs_out"]
     add("bounds", "k_cb_bounds + k_rowblock_span + scan + k_tile_table", mean("ms_bounds"), "hbm", cfg.n, 16.0 * 20,
         "16 B per tested pair x ~20 binary-search probes per row", "latency-bound: four small launches")
-    if cfg.criterion == "smh_a" and os.environ.get("SELB200_SMHFILTER", "") != "tiles":
+    smh_mode = os.environ.get("SELB200_SMHFILTER", "")
+    if cfg.criterion == "smh_a" and (smh_mode == "join" or (smh_mode != "tiles" and n_shards < 4)):
         nb = st["n_bands"]
         # equality join: n x bands keys of 8 B (key + position) generated, sorted (three 8-bit radix passes, each reading and
         # writing them) and walked once, plus the exact bucket compare of the candidates
@@ -632,7 +633,7 @@ def main():
     peak, peak_src = measured_peak()
     sm_clk = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-    kernels = kernel_table(cfg, st0, mean_of(stats_acc), sm_clk, n_sm, peak)
+    kernels = kernel_table(cfg, st0, mean_of(stats_acc), sm_clk, n_sm, peak, world)
     dom = max(kernels, key=lambda e: e["ms"])
     dom_alg_bytes = {"union": ALG_BYTES["union"] * st0["pairs_aux"],
                      "filter": {"smh_a": ALG_BYTES["smh_a"], "cb": ALG_BYTES["cb"], "hll_a": 2 * cfg.aux_bytes,

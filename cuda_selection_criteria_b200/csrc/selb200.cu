@@ -63,10 +63,15 @@ int hll_filter_mode() {
     return mode;
 }
 
-// SELB200_SMHFILTER=tiles (read once per process): the all-pairs tile filter + verify instead of the equality join
-bool smh_join_enabled() {
-    static const bool on = [] { const char* e = getenv("SELB200_SMHFILTER"); return !(e && !strcmp(e, "tiles")); }();
-    return on;
+// SELB200_SMHFILTER=tiles | join (read once per process) forces the all-pairs tile filter + verify, or the equality join.
+// Default: by shard count.  Keys, sort and expansion of the join are the same 0.17 ms on every shard (only the walk
+// divides), the tile filter divides as a whole (0.59 ms / shards + 0.03): the join wins below four shards.
+bool smh_join_enabled(int n_shards) {
+    static const int mode = [] {
+        const char* e = getenv("SELB200_SMHFILTER");
+        return !e ? 0 : !strcmp(e, "tiles") ? 1 : !strcmp(e, "join") ? 2 : 0;
+    }();
+    return mode == 2 || (mode == 0 && n_shards < 4);
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -1057,7 +1062,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_filter, t_verify, t_union, t_est;
     const int n_words = (n_bands + 1) / 2;
     const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
-    const bool smh_join = use_smh && smh_join_enabled() && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
+    const bool smh_join = use_smh && smh_join_enabled(n_shards) && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
     const long long jn_keys = (long long)n * n_bands;
     // join_buf: keys, values, sorted keys, sorted values (u32 each), genome-major signatures
     const long long jn_words = 4 * jn_keys + (long long)n * ((n_bands + 1) / 2);
