@@ -91,3 +91,71 @@ k_rowsort_rank(const uint64_t* __restrict__ tkeys, const double* __restrict__ tj
     out_keys[a + r] = key;
     out_j[a + r] = tj[e];
 }
+
+#ifndef SELB_EMUL
+// The print-order sort as ONE cooperative launch: zero the row counters, count, exclusive prefix sums over the n + 1 rows
+// (every CTA sums and scans a contiguous segment; the CTAs' totals meet in `blocksum`), scatter, rank.  Same steps as the
+// four kernels + memset + library scan above (which stay for the emulator and for devices without cooperative launch):
+// seven stream operations of 2 - 6 us each become one.
+__global__ void __launch_bounds__(256)
+k_rowsort_fused(const uint64_t* __restrict__ keys, const double* __restrict__ jac, long long cnt, int n,
+                int32_t* __restrict__ rowcnt, int32_t* __restrict__ rowoff, int32_t* __restrict__ blocksum,
+                uint64_t* __restrict__ tkeys, double* __restrict__ tj, uint64_t* __restrict__ out_keys, double* __restrict__ out_j) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    typedef cub::BlockScan<int, 256> Scan;
+    typedef cub::BlockReduce<int, 256> Reduce;
+    __shared__ union { typename Scan::TempStorage scan; typename Reduce::TempStorage red; } tmp;
+    __shared__ int carry;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i <= n; i += nth) rowcnt[i] = 0;
+    grid.sync();
+    for (long long e = tid; e < cnt; e += nth) atomicAdd(rowcnt + (keys[e] >> 32), 1);
+    grid.sync();
+    // segment of this CTA in rowcnt[0 .. n]
+    const int seg = (n + 1 + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int a = min(n + 1, (int)blockIdx.x * seg), b = min(n + 1, a + seg);
+    {
+        int part = 0;
+        for (int i = a + (int)threadIdx.x; i < b; i += 256) part += rowcnt[i];
+        const int tot = Reduce(tmp.red).Sum(part);
+        if (threadIdx.x == 0) blocksum[blockIdx.x] = tot;
+    }
+    grid.sync();
+    {
+        int part = 0;
+        for (int q = (int)threadIdx.x; q < (int)blockIdx.x; q += 256) part += blocksum[q];
+        const int before = Reduce(tmp.red).Sum(part);
+        if (threadIdx.x == 0) carry = before;
+        __syncthreads();
+        for (int base = a; base < b; base += 256) {
+            const int idx = base + (int)threadIdx.x;
+            const int v = idx < b ? rowcnt[idx] : 0;
+            int ex, tot;
+            Scan(tmp.scan).ExclusiveSum(v, ex, tot);
+            const int c0 = carry;
+            if (idx < b) rowoff[idx] = c0 + ex;
+            __syncthreads();
+            if (threadIdx.x == 0) carry = c0 + tot;
+            __syncthreads();
+        }
+    }
+    grid.sync();
+    for (long long e = tid; e < cnt; e += nth) {
+        const uint64_t key = keys[e];
+        const uint32_t i = (uint32_t)(key >> 32);
+        const int pos = rowoff[i] + atomicSub(rowcnt + i, 1) - 1;    // counts back down to zero
+        tkeys[pos] = key;
+        tj[pos] = jac[e];
+    }
+    grid.sync();
+    for (long long e = tid; e < cnt; e += nth) {
+        const uint64_t key = tkeys[e];
+        const uint32_t i = (uint32_t)(key >> 32);
+        const int ra = rowoff[i], rb = rowoff[i + 1];
+        int r = 0;
+        for (int t = ra; t < rb; ++t) r += tkeys[t] < key;      // keys are unique
+        out_keys[ra + r] = key;
+        out_j[ra + r] = tj[e];
+    }
+}
+#endif

@@ -5,10 +5,8 @@
 //   Sorted ascending + correctly-rounded fp64 division => the passing set of row i is the
 //   contiguous range [lo(i), hi(i)], lo = max(i+1, first index with e>0).
 // ============================================================================
-__global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int zeros, double tau,
-                            int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void cb_bounds_row(int i, const unsigned long long* __restrict__ e, int n, int zeros, double tau,
+                                              int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
     const unsigned long long e1 = e[i];
     const int l = max(i + 1, zeros);
     int a = l, b = n;   // first k in [l,n) failing CB
@@ -18,6 +16,11 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
     }
     lo[i] = l;
     hi[i] = a - 1;
+}
+__global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int zeros, double tau,
+                            int32_t* __restrict__ lo, int32_t* __restrict__ hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cb_bounds_row(i, e, n, zeros, tau, lo, hi);
 }
 
 // ============================================================================
@@ -31,12 +34,10 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 // ============================================================================
 enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_UNIT = 10, M_STEPS = 11, M_ITEMS = 12, M_ITEMS_MAX = 13, M_WORDS = 16 };
 
-__global__ void __launch_bounds__(128)
-k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
-                int32_t* __restrict__ nt, int32_t* __restrict__ cb0, unsigned long long* __restrict__ rb_pairs,
-                unsigned long long* __restrict__ meta) {
-    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (rb > nrb) return;
+// one warp per row block (rb in [0, nrb]; rb == nrb writes the scan sentinel)
+__device__ __forceinline__ void rowblock_span_warp(int rb, int lane, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
+                                                   int n, int nrb, int32_t* __restrict__ nt, int32_t* __restrict__ cb0,
+                                                   unsigned long long* __restrict__ rb_pairs, unsigned long long* __restrict__ meta) {
     if (rb == nrb) { if (lane == 0) nt[nrb] = 0; return; }   // scan sentinel: prefix[nrb] = total
     int cmin = INT32_MAX, cmax = -1;
     unsigned long long cnt = 0;
@@ -59,17 +60,68 @@ k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, 
         if (cnt) atomicAdd(meta + M_PAIRS_CB, cnt);
     }
 }
-
 __global__ void __launch_bounds__(128)
-k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ cb0, int nrb, long long tile_cap,
-             int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
+k_rowblock_span(const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, int n, int nrb,
+                int32_t* __restrict__ nt, int32_t* __restrict__ cb0, unsigned long long* __restrict__ rb_pairs,
+                unsigned long long* __restrict__ meta) {
     const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (rb >= nrb) return;
+    if (rb > nrb) return;
+    rowblock_span_warp(rb, lane, lo, hi, n, nrb, nt, cb0, rb_pairs, meta);
+}
+
+__device__ __forceinline__ void tile_table_warp(int rb, int lane, const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ cb0,
+                                                int nrb, long long tile_cap, int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
     const int a = tile_prefix[rb], cnt = tile_prefix[rb + 1] - a, c0 = cb0[rb];
     for (int t = lane; t < cnt; t += 32)
         if (a + t < tile_cap) tile_rc[a + t] = make_int2(rb, c0 + t);
     if (rb == 0 && lane == 0) meta[M_TILES] = (unsigned long long)tile_prefix[nrb];
 }
+__global__ void __launch_bounds__(128)
+k_tile_table(const int32_t* __restrict__ tile_prefix, const int32_t* __restrict__ cb0, int nrb, long long tile_cap,
+             int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
+    const int rb = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (rb >= nrb) return;
+    tile_table_warp(rb, lane, tile_prefix, cb0, nrb, tile_cap, tile_rc, meta);
+}
+
+#ifndef SELB_EMUL
+// The four steps above as ONE cooperative launch (grid-wide barriers between them): at n = 100k each of them runs for
+// 3 - 7 us, so four launches and their gaps are most of the 27 us they took.  The emulator (and a device without
+// cooperative launch) runs the separate kernels; both call the same device functions.
+__global__ void __launch_bounds__(256)
+k_bounds_fused(const unsigned long long* __restrict__ e, int n, int zeros, double tau, int32_t* __restrict__ lo,
+               int32_t* __restrict__ hi, int nrb, int32_t* __restrict__ nt, int32_t* __restrict__ tile_prefix,
+               int32_t* __restrict__ cb0, unsigned long long* __restrict__ rb_pairs, long long tile_cap,
+               int2* __restrict__ tile_rc, unsigned long long* __restrict__ meta) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = tid >> 5, nwarps = nth >> 5;
+    for (int i = tid; i < n; i += nth) cb_bounds_row(i, e, n, zeros, tau, lo, hi);
+    grid.sync();
+    for (int rb = warp; rb <= nrb; rb += nwarps) rowblock_span_warp(rb, lane, lo, hi, n, nrb, nt, cb0, rb_pairs, meta);
+    grid.sync();
+    if (blockIdx.x == 0) {              // exclusive prefix sums of nt[0 .. nrb] (a few hundred to a few thousand values): one CTA
+        typedef cub::BlockScan<int, 256> Scan;
+        __shared__ typename Scan::TempStorage tmp;
+        __shared__ int carry;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base <= nrb; base += 256) {
+            const int idx = base + (int)threadIdx.x;
+            const int v = idx <= nrb ? nt[idx] : 0;
+            int ex, tot;
+            Scan(tmp).ExclusiveSum(v, ex, tot);
+            const int c0 = carry;
+            if (idx <= nrb) tile_prefix[idx] = c0 + ex;
+            __syncthreads();
+            if (threadIdx.x == 0) carry = c0 + tot;
+            __syncthreads();
+        }
+    }
+    grid.sync();
+    for (int rb = warp; rb < nrb; rb += nwarps) tile_table_warp(rb, lane, tile_prefix, cb0, nrb, tile_cap, tile_rc, meta);
+}
+#endif
 
 // tiles owned by one shard: tile = shard + j * n_shards for j in [0, count)
 struct TileWalk {

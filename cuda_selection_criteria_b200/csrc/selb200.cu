@@ -40,6 +40,9 @@
 #include <utility>
 #include <vector>
 
+#include <cooperative_groups.h>
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -235,7 +238,7 @@ struct selb200_ctx {
         unsigned long long* h_merged = nullptr;   // pinned [4]
     } g;
     DevBuf g_push, g_merged;
-    DevBuf row_cnt, row_off, sort_tmp;
+    DevBuf row_cnt, row_off, sort_tmp, sort_blocksum;
     DevBuf auxP, agrange, atail;         // bit planes (quad layout) / register ranges / tail sums of the auxiliary HLLs (sorted order)
     bool auxp_quad = false;              // auxP holds the planes of the loaded auxiliary HLLs (k_aux_planes_quad)
     DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
@@ -294,6 +297,25 @@ int resident_ctas(K kernel, int threads) {
         per_sm = 8;
     }
     return per_sm;
+}
+
+// cooperative launch (grid-wide barriers inside the kernel): the grid must be co-resident.  SELB200_FUSED=0 keeps the
+// separate kernels (A/B measurements); a device without cooperative launch gets them too
+bool fused_launches_enabled(int device) {
+    static const bool env_on = [] { const char* e = getenv("SELB200_FUSED"); return !(e && !strcmp(e, "0")); }();
+    if (!env_on) return false;
+    int ok = 0;
+    if (cudaDeviceGetAttribute(&ok, cudaDevAttrCooperativeLaunch, device) != cudaSuccess) { cudaGetLastError(); return false; }
+    return ok != 0;
+}
+template <typename K>
+int coop_grid(K kernel, int threads, int sm_count, long long wanted) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return (int)std::max<long long>(1, std::min<long long>(wanted, (long long)sm_count * std::min(per_sm, 4)));
 }
 
 template <class Src, class Epi>
@@ -813,7 +835,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1039,22 +1061,43 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     if (c->tile_cap < std::min<int64_t>(tri, 16ll << 20)) c->tile_cap = std::min<int64_t>(tri, 16ll << 20);
     // no_cb: every ratio passes a bound of -inf, so each row's range is (i, n-1] minus the e==0 columns
     const double tau_cb = prm->no_cb ? -__builtin_huge_val() : tau;
-    k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau_cb,
-                                                c->lo.as<int32_t>(), c->hi.as<int32_t>());
-    CK(cudaGetLastError());
-    k_rowblock_span<<<(nrb + 1 + 3) / 4, 128, 0, s>>>(c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, nrb,
-                                                      c->tile_nt.as<int32_t>(), c->tile_cb0.as<int32_t>(),
-                                                      c->rb_pairs.as<unsigned long long>(), d_cnt);
-    CK(cudaGetLastError());
-    {
-        size_t tmp_bytes = 0;
-        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->tile_nt.as<int32_t>(), c->tile_prefix.as<int32_t>(),
-                                         nrb + 1, s));
-        CKR(c->cub_tmp.ensure(tmp_bytes));
-        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->tile_nt.as<int32_t>(),
-                                         c->tile_prefix.as<int32_t>(), nrb + 1, s));
+    // tile capacity is known before the first pass (it only grows after an overflow), so the table can be part of the
+    // fused launch; a redone pass rebuilds the table alone
+    CKR(c->tile_rc.ensure((size_t)std::max<int64_t>(c->tile_cap, 1) * sizeof(int2)));
+    const bool fused = fused_launches_enabled(c->device) && nrb <= 65536;
+    if (fused) {
+        static const int fgrid_cap = coop_grid(k_bounds_fused, 256, c->sm_count, 1 << 30);
+        const int grid = std::max(1, std::min(fgrid_cap, (n + 255) / 256));
+        const unsigned long long* a_e = c->e_sorted.as<unsigned long long>();
+        int a_n = n, a_zeros = zeros, a_nrb = nrb;
+        double a_tau = tau_cb;
+        int32_t *a_lo = c->lo.as<int32_t>(), *a_hi = c->hi.as<int32_t>(), *a_nt = c->tile_nt.as<int32_t>(),
+                *a_pre = c->tile_prefix.as<int32_t>(), *a_cb0 = c->tile_cb0.as<int32_t>();
+        unsigned long long* a_rbp = c->rb_pairs.as<unsigned long long>();
+        long long a_cap = (long long)c->tile_cap;
+        int2* a_rc = c->tile_rc.as<int2>();
+        unsigned long long* a_meta = d_cnt;
+        void* args[] = {&a_e, &a_n, &a_zeros, &a_tau, &a_lo, &a_hi, &a_nrb, &a_nt, &a_pre, &a_cb0, &a_rbp, &a_cap, &a_rc, &a_meta};
+        CK(cudaLaunchCooperativeKernel((void*)k_bounds_fused, dim3(grid), dim3(256), args, 0, s));
+        st.launches += 1;
+    } else {
+        k_cb_bounds<<<(n + 255) / 256, 256, 0, s>>>(c->e_sorted.as<unsigned long long>(), n, zeros, tau_cb,
+                                                    c->lo.as<int32_t>(), c->hi.as<int32_t>());
+        CK(cudaGetLastError());
+        k_rowblock_span<<<(nrb + 1 + 3) / 4, 128, 0, s>>>(c->lo.as<int32_t>(), c->hi.as<int32_t>(), n, nrb,
+                                                          c->tile_nt.as<int32_t>(), c->tile_cb0.as<int32_t>(),
+                                                          c->rb_pairs.as<unsigned long long>(), d_cnt);
+        CK(cudaGetLastError());
+        {
+            size_t tmp_bytes = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->tile_nt.as<int32_t>(), c->tile_prefix.as<int32_t>(),
+                                             nrb + 1, s));
+            CKR(c->cub_tmp.ensure(tmp_bytes));
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->tile_nt.as<int32_t>(),
+                                             c->tile_prefix.as<int32_t>(), nrb + 1, s));
+        }
+        st.launches += 3;
     }
-    st.launches += 3;
     DBG_SYNC(c, "cb bounds + row-block spans + scan");
     cudaEvent_t ev_bounds = nullptr;
 
@@ -1169,10 +1212,12 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         CKR(c->near_j.ensure((size_t)c->near_cap * 8));
         const unsigned long long near_cap = (unsigned long long)c->near_cap;
         st.launches = launches_fixed;
-        k_tile_table<<<(nrb + 3) / 4, 128, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
-                                                   (long long)c->tile_cap, c->tile_rc.as<int2>(), d_cnt);
-        CK(cudaGetLastError());
-        st.launches++;
+        if (!fused || attempt > 0) {
+            k_tile_table<<<(nrb + 3) / 4, 128, 0, s>>>(c->tile_prefix.as<int32_t>(), c->tile_cb0.as<int32_t>(), nrb,
+                                                       (long long)c->tile_cap, c->tile_rc.as<int2>(), d_cnt);
+            CK(cudaGetLastError());
+            st.launches++;
+        }
         DBG_SYNC(c, "tile table");
         if (!ev_bounds) ev_bounds = c->ev();
         if (ranges.empty()) {
@@ -1496,22 +1541,38 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             CKR(c->sort_tmp.ensure((size_t)cnt * 16));
             uint64_t* tkeys = c->sort_tmp.as<uint64_t>();
             double* tj = reinterpret_cast<double*>(tkeys + cnt);
-            CK(cudaMemsetAsync(c->row_cnt.p, 0, ((size_t)n + 1) * 4, s));
-            const unsigned grid = (unsigned)((cnt + 255) / 256);
-            k_rowsort_count<<<grid, 256, 0, s>>>(src_keys, cnt, c->row_cnt.as<int32_t>());
-            CK(cudaGetLastError());
-            size_t tmp_bytes = 0;
-            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(), n + 1, s));
-            CKR(c->cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
-                                             n + 1, s));
-            k_rowsort_scatter<<<grid, 256, 0, s>>>(src_keys, src_j, cnt, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
-                                                   tkeys, tj);
-            CK(cudaGetLastError());
-            k_rowsort_rank<<<grid, 256, 0, s>>>(tkeys, tj, cnt, c->row_off.as<int32_t>(), c->out_keys2.as<uint64_t>(),
-                                                c->out_j2.as<double>());
-            CK(cudaGetLastError());
-            st.launches += 4;
+            if (fused) {
+                static const int sgrid_cap = coop_grid(k_rowsort_fused, 256, c->sm_count, 1 << 30);
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sgrid_cap, (std::max<int64_t>(cnt, n + 1) + 255) / 256));
+                CKR(c->sort_blocksum.ensure((size_t)grid * 4));
+                const uint64_t* a_keys = src_keys;
+                const double* a_j = src_j;
+                long long a_cnt = cnt;
+                int a_n = n;
+                int32_t *a_rc = c->row_cnt.as<int32_t>(), *a_ro = c->row_off.as<int32_t>(), *a_bs = c->sort_blocksum.as<int32_t>();
+                uint64_t* a_ok = c->out_keys2.as<uint64_t>();
+                double* a_oj = c->out_j2.as<double>();
+                void* args[] = {&a_keys, &a_j, &a_cnt, &a_n, &a_rc, &a_ro, &a_bs, &tkeys, &tj, &a_ok, &a_oj};
+                CK(cudaLaunchCooperativeKernel((void*)k_rowsort_fused, dim3(grid), dim3(256), args, 0, s));
+                st.launches += 1;
+            } else {
+                CK(cudaMemsetAsync(c->row_cnt.p, 0, ((size_t)n + 1) * 4, s));
+                const unsigned grid = (unsigned)((cnt + 255) / 256);
+                k_rowsort_count<<<grid, 256, 0, s>>>(src_keys, cnt, c->row_cnt.as<int32_t>());
+                CK(cudaGetLastError());
+                size_t tmp_bytes = 0;
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(), n + 1, s));
+                CKR(c->cub_tmp.ensure(tmp_bytes));
+                CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
+                                                 n + 1, s));
+                k_rowsort_scatter<<<grid, 256, 0, s>>>(src_keys, src_j, cnt, c->row_cnt.as<int32_t>(), c->row_off.as<int32_t>(),
+                                                       tkeys, tj);
+                CK(cudaGetLastError());
+                k_rowsort_rank<<<grid, 256, 0, s>>>(tkeys, tj, cnt, c->row_off.as<int32_t>(), c->out_keys2.as<uint64_t>(),
+                                                    c->out_j2.as<double>());
+                CK(cudaGetLastError());
+                st.launches += 4;
+            }
         } else if (prm->sort_output && cnt > 1) {
             size_t tmp_bytes = 0;
             int nbits = 1;
