@@ -103,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 #define PL_PACK_C2 0
 #endif
 #ifndef PL_UNROLL
-#define PL_UNROLL 0
+#define PL_UNROLL 1      // measured 1.546 against 1.566 ms (n = 100k, 511 521 pairs); packing the carry counters: no change
 #endif
 constexpr int PL_NC2 = PL_PACK_C2 ? 16 : 32;
 __device__ __forceinline__ void c2_add(uint32_t (&C2)[PL_NC2], int v, uint32_t cnt) {
