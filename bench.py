@@ -763,22 +763,19 @@ def main():
         h2d = host_bytes
         h2d_mode = os.environ.get("SELB200_H2D", "")
         packed_h2d = (h2d_mode == "packed") or (h2d_mode != "raw" and world == 1)
-        if packed_h2d:
-            # what crosses the bus: the packed pieces (csrc/hostpack.h: header + exception slots + nibbles per 1024 rows;
-            # the raw area of a piece is only copied when it holds rows) + the auxiliary sketches as they are
-            Lb = S._lib.lib()
-            m_regs = int(regs_d.shape[1])
-            pr = max(1, (16 << 20) // m_regs)
-            full, rest = divmod(cfg.n, pr)
-            def piece(rows):
-                return int(Lb.selb200_nib4_piece_bytes(rows, m_regs.bit_length() - 1)) - 4 * m_regs if rows else 0
-            h2d = full * piece(pr) + piece(rest) + (aux_d.numel() * aux_d.element_size() if aux_d is not None else 0)
+        load_info = None
+        if world == 1:
+            # what crossed the bus in the last step, as the library counted it: register pieces packed (csrc/hostpack.h) or
+            # raw (whenever the link had run out of work), + the auxiliary sketches as they are
+            load_info = sel2.load_info()
+            h2d = int(load_info["h2d_register_bytes"]) + (aux_d.numel() * aux_d.element_size() if aux_d is not None else 0)
         link_total = float(link_gbs.item())
         e2e = {"value": cfg.pairs / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "host_input_bytes_per_step": host_bytes,
-               "h2d_transport": ("packed: per row one base byte + 4-bit offsets + <= 32 exceptions (csrc/hostpack.h), packed by the "
-                                 "host threads inside the timed region, unpacked on the device; auxiliary sketches unpacked"
-                                 if packed_h2d else "raw register bytes"),
+               "h2d_transport": ("register rows packed by the host threads inside the timed region (per row one base byte + 4-bit offsets "
+                                 "+ <= 32 exceptions, csrc/hostpack.h) and unpacked on the device; a piece goes raw whenever the copy "
+                                 "engine has run out of work; auxiliary sketches as they are" if packed_h2d else "raw register bytes"),
+               "h2d_rows": load_info,
                "d2h_bytes_per_step": int(out_n * 16 + cfg.n * 8), "ms_per_step": e2e_ms, "steps": e2e_steps,
                "timer": "max(host wall clock, CUDA events) per step, max over ranks",
                "rank0_phases_ms": {k: v * 1e3 / e2e_steps for k, v in phase.items()},

@@ -55,6 +55,7 @@ SYMBOLS = [
     ("selb200_load_device", _I, [_VP, _I64, _I, _VP, _VP, _I, _I, _VP]),
     ("selb200_load_device_begin", _I, [_VP, _I64, _I, _VP, _I, _I, _VP]),
     ("selb200_load_device_rows", _I, [_VP, _I64, _I64]),
+    ("selb200_load_info", _I, [_VP, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     ("selb200_nib4_piece_bytes", _I64, [_I64, _I]),
     ("selb200_nib4_pack_piece", _I64, [_VP, _I64, _I, _VP, _I]),
     ("selb200_load_device_rows_packed", _I, [_VP, _I64, _I64, _VP, _I64]),

@@ -212,6 +212,8 @@ struct selb200_ctx {
     int64_t near_cap = 1 << 16;                   // near-tau list: grown (and the pass redone) when a run overflows it
     LoadState ld;
     PackSlot pack_slots[4];
+    cudaEvent_t h2d_tail_ev = nullptr;   // re-recorded behind every register copy of a packed load: "the link has nothing left to do"
+    int64_t ld_h2d_bytes = 0, ld_rows_packed = 0, ld_rows_raw = 0;     // register bytes the last host load moved, and how
     DevBuf pk_buf;                       // packed pieces as they land on the device, before k_unpack_nib4
     DevBuf join_buf, join_items;         // smh_a equality join: keys / values, unsorted and sorted, genome-major signatures; items
     int64_t join_item_cap = 0;           // grow-only, like every other list of the run
@@ -716,33 +718,68 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
     int slot_i = 0;
     int64_t group0 = 0;                       // first row not yet digested
     static const bool trace = getenv("SELB200_PACK_TRACE") != nullptr;
+    // SELB200_H2D=packed: every piece packed (A/B measurements); default: a piece goes RAW whenever the copy engine has
+    // nothing left to do — packing is bounded by the host's memory system (47 - 146 GB/s of registers measured on this
+    // pool's hosts, depending on the machine and its neighbours), the raw copy by PCIe (54 GB/s), and the two resources
+    // work side by side: a fast host packs everything (copy-bound, half the bytes), a slow one lets the link carry
+    // raw pieces while it packs
+    static const bool always_pack = [] { const char* e = getenv("SELB200_H2D"); return e && !strcmp(e, "packed"); }();
+    bool src_pinned = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, regs) == cudaSuccess) src_pinned = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    if (!c->h2d_tail_ev) CK(cudaEventCreateWithFlags(&c->h2d_tail_ev, cudaEventDisableTiming));
+    bool any_copy = false;
+    c->ld_h2d_bytes = 0; c->ld_rows_packed = 0; c->ld_rows_raw = 0;
     double t_pack = 0., t_wait = 0., t_queue = 0.;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     const double t_begin = now();
     for (int64_t g0 = 0; g0 < n; g0 += pk_rows) {
         const int64_t rows = std::min(pk_rows, n - g0);
         const selb::Nib4Piece Q = selb::nib4_piece(rows, m);          // the last piece may be shorter
-        PackSlot& ps = c->pack_slots[slot_i];
-        slot_i = (slot_i + 1) & 3;
-        const double t0 = now();
-        if (ps.in_flight) { CK(cudaEventSynchronize(ps.free_ev)); ps.in_flight = false; }
-        const double t1 = now();
-        const int64_t n_raw = selb::nib4_pack_piece(regs + (size_t)g0 * m, rows, m, ps.buf, nt);
-        const double t2 = now();
-        t_wait += t1 - t0;
-        t_pack += t2 - t1;
         uint8_t* d_piece = c->pk_buf.as<uint8_t>() + (size_t)(g0 / pk_rows) * P.bytes;
         uint8_t* d_rows = c->regs_own.as<uint8_t>() + (size_t)g0 * m;
-        if (n_raw > selb::NIB4_RAW_CAP) {     // not the registers of HLLs of real sets: the piece travels as it is
-            CK(cudaMemcpyAsync(d_rows, regs + (size_t)g0 * m, (size_t)rows * m, cudaMemcpyHostToDevice, c->copy_stream));
-            CKR(load_join_copies(c));
-        } else {
-            CK(cudaMemcpyAsync(d_piece, ps.buf, Q.off_raw + (size_t)n_raw * m, cudaMemcpyHostToDevice, c->copy_stream));
-            CK(cudaEventRecord(ps.free_ev, c->copy_stream));
-            ps.in_flight = true;
-            CKR(load_join_copies(c));
-            CKR(unpack_pieces(c, d_piece, P.bytes, rows, rows, n_raw > 0, d_rows));
+        const double t0 = now();
+        bool raw_piece = false;
+        if (src_pinned && !always_pack) {
+            // everything queued so far has been copied: the link is idle, this piece keeps it busy at no cost to the host
+            raw_piece = !any_copy || cudaEventQuery(c->h2d_tail_ev) == cudaSuccess;
+            cudaGetLastError();
         }
+        double t2 = t0;
+        if (!raw_piece) {
+            PackSlot& ps = c->pack_slots[slot_i];
+            slot_i = (slot_i + 1) & 3;
+            if (ps.in_flight) { CK(cudaEventSynchronize(ps.free_ev)); ps.in_flight = false; }
+            const double t1 = now();
+            const int64_t n_raw = selb::nib4_pack_piece(regs + (size_t)g0 * m, rows, m, ps.buf, nt);
+            t2 = now();
+            t_wait += t1 - t0;
+            t_pack += t2 - t1;
+            if (n_raw > selb::NIB4_RAW_CAP) {     // not the registers of HLLs of real sets: the piece travels as it is
+                raw_piece = true;
+            } else {
+                const size_t nbytes = Q.off_raw + (size_t)n_raw * m;
+                CK(cudaMemcpyAsync(d_piece, ps.buf, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
+                CK(cudaEventRecord(ps.free_ev, c->copy_stream));
+                ps.in_flight = true;
+                CK(cudaEventRecord(c->h2d_tail_ev, c->copy_stream));
+                CKR(load_join_copies(c));
+                CKR(unpack_pieces(c, d_piece, P.bytes, rows, rows, n_raw > 0, d_rows));
+                c->ld_h2d_bytes += (int64_t)nbytes;
+                c->ld_rows_packed += rows;
+            }
+        }
+        if (raw_piece) {
+            CK(cudaMemcpyAsync(d_rows, regs + (size_t)g0 * m, (size_t)rows * m, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(c->h2d_tail_ev, c->copy_stream));
+            CKR(load_join_copies(c));
+            c->ld_h2d_bytes += (int64_t)rows * (int64_t)m;
+            c->ld_rows_raw += rows;
+        }
+        any_copy = true;
         const int64_t done = g0 + rows;
         if (done - group0 >= L.rows_per_chunk || done == n) {
             CKR(load_chunk(c, group0, done - group0, nullptr, stored ? stored + group0 : nullptr,
@@ -752,8 +789,9 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
         t_queue += now() - t2;
     }
     if (trace)
-        fprintf(stderr, "selb200 packed load: %lld rows, %d threads: pack %.2f ms, waiting for a slot %.2f ms, queueing %.2f ms, loop %.2f ms\n",
-                (long long)n, nt, t_pack * 1e3, t_wait * 1e3, t_queue * 1e3, (now() - t_begin) * 1e3);
+        fprintf(stderr, "selb200 packed load: %lld rows (%lld packed, %lld raw), %d threads: pack %.2f ms, waiting for a slot %.2f ms, "
+                "queueing %.2f ms, loop %.2f ms\n", (long long)n, (long long)c->ld_rows_packed, (long long)c->ld_rows_raw, nt,
+                t_pack * 1e3, t_wait * 1e3, t_queue * 1e3, (now() - t_begin) * 1e3);
     return SELB200_OK;
 }
 
@@ -767,6 +805,9 @@ int do_load(selb200_ctx* c, int64_t n, int p, const uint8_t* regs, bool on_devic
         CKR(load_host_packed(c, n, regs, stored, aux));
         return load_end(c);
     }
+    c->ld_h2d_bytes = on_device ? 0 : (int64_t)n * (int64_t)c->m;
+    c->ld_rows_packed = 0;
+    c->ld_rows_raw = on_device ? 0 : n;
     const int64_t step = on_device ? std::max<int64_t>(n, 1) : L.rows_per_chunk;
     for (int64_t g0 = 0; g0 < n; g0 += step) {
         const int64_t rows = std::min(step, n - g0);
@@ -842,6 +883,7 @@ void selb200_destroy(selb200_ctx* c) {
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    if (c->h2d_tail_ev) cudaEventDestroy(c->h2d_tail_ev);
     for (PackSlot& ps : c->pack_slots) {
         if (ps.buf) cudaFreeHost(ps.buf);
         if (ps.free_ev) cudaEventDestroy(ps.free_ev);
@@ -873,6 +915,14 @@ int selb200_load_device_begin(selb200_ctx* ctx, int64_t n, int p, const uint8_t*
     if (n > 0 && !d_regs) return fail(SELB200_EINVAL, "null register matrix");
     if (aux_kind != SELB200_AUX_NONE && n > 0 && !d_aux) return fail(SELB200_EINVAL, "null aux matrix");
     return load_begin(ctx, n, p, aux_kind, aux_len, d_regs, d_aux);
+}
+
+int selb200_load_info(selb200_ctx* c, int64_t* h2d_register_bytes, int64_t* rows_packed, int64_t* rows_raw) {
+    if (!c) return fail(SELB200_EINVAL, "null context");
+    if (h2d_register_bytes) *h2d_register_bytes = c->ld_h2d_bytes;
+    if (rows_packed) *rows_packed = c->ld_rows_packed;
+    if (rows_raw) *rows_raw = c->ld_rows_raw;
+    return SELB200_OK;
 }
 
 int64_t selb200_nib4_piece_bytes(int64_t rows, int p) {

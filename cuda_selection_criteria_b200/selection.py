@@ -137,6 +137,12 @@ class Selection:
     def load_device_rows(self, g0: int, count: int):
         _lib.check(self._L.selb200_load_device_rows(self._h, int(g0), int(count)))
 
+    def load_info(self) -> dict:
+        """Register bytes the last host load moved over PCIe, and how many rows went packed / raw."""
+        b, rp, rr = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._L.selb200_load_info(self._h, C.byref(b), C.byref(rp), C.byref(rr)))
+        return {"h2d_register_bytes": b.value, "rows_packed": rp.value, "rows_raw": rr.value}
+
     def load_device_rows_packed(self, g0: int, count: int, pieces, piece_rows: int | None = None):
         """Rows [g0, g0+count) arrived as packed pieces (selb200_nib4_pack_piece) in device memory: `pieces` is a CUDA
         uint8 tensor holding ceil(count / piece_rows) of them back to back (piece_rows = count: one piece).  They are

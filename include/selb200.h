@@ -159,7 +159,8 @@ int selb200_load_device_rows(selb200_ctx* ctx, int64_t g0, int64_t count);
 
 /* Packed transport of register rows (csrc/hostpack.h).  HLL registers of one sketch sit in a narrow band above the
  * smallest one, so a row crosses PCIe / NVLink as one base byte + 4-bit offsets + a short exception list: 0.51 of its
- * bytes.  selb200_load_host packs, copies and unpacks internally (SELB200_H2D=raw turns that off); these three entry
+ * bytes.  selb200_load_host packs, copies and unpacks internally (SELB200_H2D=raw turns that off, =packed packs every
+ * piece even when the link idles); these three entry
  * points expose the same pieces to a caller that moves the bytes itself (cuda_selection_criteria_b200/dist.py: per-rank
  * slices, H2D + NCCL all-gather of the packed pieces):
  *   piece_bytes : size of the buffer holding `rows` packed rows
@@ -172,6 +173,10 @@ int selb200_load_device_rows(selb200_ctx* ctx, int64_t g0, int64_t count);
  *                 selb200_nib4_piece_bytes(piece_rows, p) bytes apart; the rows are unpacked INTO the matrix given to
  *                 selb200_load_device_begin (which must be writable)
  * Unpacking reproduces the bytes exactly: nothing downstream can depend on the transport. */
+/* What the last selb200_load_host moved over PCIe for the REGISTER matrix (auxiliary sketches always travel as they are):
+ * bytes copied, rows that went packed, rows that went raw.  The loader packs a piece unless the copy engine has run out
+ * of work, in which case the piece goes raw (pinned source memory only) — host packing and PCIe run side by side. */
+int selb200_load_info(selb200_ctx* ctx, int64_t* h2d_register_bytes, int64_t* rows_packed, int64_t* rows_raw);
 int64_t selb200_nib4_piece_bytes(int64_t rows, int p);
 int64_t selb200_nib4_pack_piece(const uint8_t* regs, int64_t rows, int p, uint8_t* piece, int threads);
 int selb200_load_device_rows_packed(selb200_ctx* ctx, int64_t g0, int64_t count, const uint8_t* d_pieces, int64_t piece_rows);
