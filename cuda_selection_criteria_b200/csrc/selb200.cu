@@ -212,7 +212,7 @@ struct selb200_ctx {
     int64_t near_cap = 1 << 16;                   // near-tau list: grown (and the pass redone) when a run overflows it
     LoadState ld;
     PackSlot pack_slots[4];
-    cudaEvent_t h2d_tail_ev = nullptr;   // re-recorded behind every register copy of a packed load: "the link has nothing left to do"
+    cudaEvent_t h2d_evs[16] = {};        // one per register copy in flight during a packed load: how much work the link still holds
     int64_t ld_h2d_bytes = 0, ld_rows_packed = 0, ld_rows_raw = 0;     // register bytes the last host load moved, and how
     DevBuf pk_buf;                       // packed pieces as they land on the device, before k_unpack_nib4
     DevBuf join_buf, join_items;         // smh_a equality join: keys / values, unsorted and sorted, genome-major signatures; items
@@ -730,8 +730,26 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
         if (cudaPointerGetAttributes(&at, regs) == cudaSuccess) src_pinned = at.type == cudaMemoryTypeHost;
         else cudaGetLastError();
     }
-    if (!c->h2d_tail_ev) CK(cudaEventCreateWithFlags(&c->h2d_tail_ev, cudaEventDisableTiming));
-    bool any_copy = false;
+    for (cudaEvent_t& e : c->h2d_evs)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // copies in flight (they complete in order): ring of (event, estimated link time); the link is assumed to move 50 GB/s
+    double q_cost[16];
+    int q_head = 0, q_tail = 0;             // [q_tail, q_head) in flight, indices mod 16
+    auto link_pending = [&]() -> double {
+        while (q_tail != q_head && cudaEventQuery(c->h2d_evs[q_tail & 15]) == cudaSuccess) ++q_tail;
+        cudaGetLastError();
+        double t = 0.;
+        for (int q = q_tail; q != q_head; ++q) t += q_cost[q & 15];
+        return t;
+    };
+    auto link_push = [&](size_t bytes) -> int {
+        if (q_head - q_tail == 16) { CK(cudaEventSynchronize(c->h2d_evs[q_tail & 15])); ++q_tail; }
+        CK(cudaEventRecord(c->h2d_evs[q_head & 15], c->copy_stream));
+        q_cost[q_head & 15] = (double)bytes / 50e9;
+        ++q_head;
+        return SELB200_OK;
+    };
+    double pack_est = (double)pk_rows * (double)m / 100e9;     // seconds to pack a piece: 100 GB/s to start with, then measured
     c->ld_h2d_bytes = 0; c->ld_rows_packed = 0; c->ld_rows_raw = 0;
     double t_pack = 0., t_wait = 0., t_queue = 0.;
     auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
@@ -744,9 +762,9 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
         const double t0 = now();
         bool raw_piece = false;
         if (src_pinned && !always_pack) {
-            // everything queued so far has been copied: the link is idle, this piece keeps it busy at no cost to the host
-            raw_piece = !any_copy || cudaEventQuery(c->h2d_tail_ev) == cudaSuccess;
-            cudaGetLastError();
+            // the copies queued so far will be done before this piece is packed: the link would idle — the piece goes raw
+            // and keeps it busy at no cost to the host
+            raw_piece = link_pending() < pack_est;
         }
         double t2 = t0;
         if (!raw_piece) {
@@ -758,6 +776,7 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
             t2 = now();
             t_wait += t1 - t0;
             t_pack += t2 - t1;
+            pack_est = 0.75 * pack_est + 0.25 * (t2 - t1) * ((double)pk_rows / (double)rows);
             if (n_raw > selb::NIB4_RAW_CAP) {     // not the registers of HLLs of real sets: the piece travels as it is
                 raw_piece = true;
             } else {
@@ -765,7 +784,7 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
                 CK(cudaMemcpyAsync(d_piece, ps.buf, nbytes, cudaMemcpyHostToDevice, c->copy_stream));
                 CK(cudaEventRecord(ps.free_ev, c->copy_stream));
                 ps.in_flight = true;
-                CK(cudaEventRecord(c->h2d_tail_ev, c->copy_stream));
+                CKR(link_push(nbytes));
                 CKR(load_join_copies(c));
                 CKR(unpack_pieces(c, d_piece, P.bytes, rows, rows, n_raw > 0, d_rows));
                 c->ld_h2d_bytes += (int64_t)nbytes;
@@ -774,12 +793,11 @@ int load_host_packed(selb200_ctx* c, int64_t n, const uint8_t* regs, const doubl
         }
         if (raw_piece) {
             CK(cudaMemcpyAsync(d_rows, regs + (size_t)g0 * m, (size_t)rows * m, cudaMemcpyHostToDevice, c->copy_stream));
-            CK(cudaEventRecord(c->h2d_tail_ev, c->copy_stream));
+            CKR(link_push((size_t)rows * m));
             CKR(load_join_copies(c));
             c->ld_h2d_bytes += (int64_t)rows * (int64_t)m;
             c->ld_rows_raw += rows;
         }
-        any_copy = true;
         const int64_t done = g0 + rows;
         if (done - group0 >= L.rows_per_chunk || done == n) {
             CKR(load_chunk(c, group0, done - group0, nullptr, stored ? stored + group0 : nullptr,
@@ -883,7 +901,7 @@ void selb200_destroy(selb200_ctx* c) {
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
-    if (c->h2d_tail_ev) cudaEventDestroy(c->h2d_tail_ev);
+    for (cudaEvent_t e : c->h2d_evs) if (e) cudaEventDestroy(e);
     for (PackSlot& ps : c->pack_slots) {
         if (ps.buf) cudaFreeHost(ps.buf);
         if (ps.free_ev) cudaEventDestroy(ps.free_ev);
