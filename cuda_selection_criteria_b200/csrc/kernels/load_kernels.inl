@@ -96,7 +96,10 @@ __global__ void k_sorted_prep(const double* __restrict__ cards_sorted, long long
     if (i >= n) return;
     const double cd = cards_sorted[i];
     e[i] = (unsigned long long)cd;
-    if (i + 1 < n && !(cd < cards_sorted[i + 1])) *tie_flag = 1;
+    // a tie sends the load to the reference's own (unstable) std::sort on the host.  Ties at cardinality 0 do not count:
+    // empty sketches (and the all-zero padding rows of a sharded load) pair with nothing (e == 0 columns are skipped, an
+    // e == 0 row fails CB for every tau > 0), so their order among themselves never reaches the output
+    if (i + 1 < n && !(cd < cards_sorted[i + 1]) && cd > 0.) *tie_flag = 1;
 }
 
 // per-genome cardinality: hll.h:834-837 (sum) / :1138-1141 (trusted stored value)
