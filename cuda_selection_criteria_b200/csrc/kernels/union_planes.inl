@@ -280,13 +280,9 @@ template <class E> struct EpiSubsets : E {};
 template <class E> struct union_form { static constexpr int value = 0; };
 template <class E> struct union_form<EpiSubsets<E>> { static constexpr int value = 1; };
 
-// NCH > 0: the geometry is a compile-time constant — NCH full chunks of PL_CHUNK_REGS registers per genome (NCH = 4 is
-// p = 14, the precision the path runs at); byte counts, item counts and the chunk step's trip count then cost nothing,
-// where the generic kernel (NCH = 0: m and chunk_regs as passed) rematerialises them under its 128-register cap
-// (about 100 of its 2270 instructions per pair).
-template <class Epi, int NCH = 0>
+template <class Epi>
 __global__ void __launch_bounds__(32, PL_MIN_CTAS)
-k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m_rt, int chunk_regs_rt, const uint16_t* __restrict__ grange,
+k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
                    SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
                    unsigned long long* __restrict__ batch_counter) {
     constexpr int FORM = union_form<Epi>::value;
@@ -295,9 +291,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m_rt, int chunk_r
 #endif
     constexpr uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x;
-    const size_t m = NCH > 0 ? (size_t)NCH * PL_CHUNK_REGS : m_rt;
-    const int chunk_regs = NCH > 0 ? PL_CHUNK_REGS : chunk_regs_rt;
-    const int nchunks = NCH > 0 ? NCH : (int)(m / (size_t)chunk_regs);
+    const int nchunks = (int)(m / (size_t)chunk_regs);
     const uint32_t chunk_bytes = (uint32_t)(6 * (chunk_regs >> 3));
     const int nq = chunk_regs >> 6;
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(pl_smem);
@@ -457,7 +451,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m_rt, int chunk_r
         const int g0 = (int)(cons.gm & 0xffu);
         const uint32_t gmask = cons.gm >> 8;
         if (FORM == 1) {
-            if (NCH > 0 || nq == PL_NQ) {
+            if (nq == PL_NQ) {
                 switch (g0) {
                     case 0: plane_chunk_subsets<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
                     case 1: plane_chunk_subsets<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
@@ -474,7 +468,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m_rt, int chunk_r
                     default: plane_chunk_subsets<4, 0>(pa, pb, nq, lane, gmask, S, C2); break;
                 }
             }
-        } else if (NCH > 0 || nq == PL_NQ) {
+        } else if (nq == PL_NQ) {
             switch (g0) {
                 case 0: plane_chunk<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
                 case 1: plane_chunk<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;

@@ -380,8 +380,6 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         if (!u_per_sm || u_per_sm_smem != smem) {
             cudaFuncSetAttribute(k_pair_hist_planes<EpiSubsets<EpiWriteHist>>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_pair_hist_planes<EpiSubsets<EpiWriteHist>, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&u_per_sm, k_pair_hist_planes<EpiSubsets<EpiWriteHist>>, 32, smem) != cudaSuccess ||
                 u_per_sm < 1) {
                 cudaGetLastError();
@@ -390,17 +388,9 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
             u_per_sm_smem = smem;
         }
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * u_per_sm);
-        // p = 14 (four full chunks per genome): the kernel with its geometry compiled in; SELB200_UNION_GENERIC=1 keeps the
-        // generic one (A/B measurements)
-        static const bool generic_only = getenv("SELB200_UNION_GENERIC") != nullptr;
-        if (c->m == (size_t)4 * PL_CHUNK_REGS && c->chunk_regs == PL_CHUNK_REGS && !generic_only)
-            k_pair_hist_planes<EpiSubsets<EpiWriteHist>, 4><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
-                                                                              c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                                              c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
-        else
-            k_pair_hist_planes<EpiSubsets<EpiWriteHist>><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
-                                                                           c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                                           c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+        k_pair_hist_planes<EpiSubsets<EpiWriteHist>><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
+                                                                       c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
+                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
     } else {
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
         k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,

@@ -185,7 +185,7 @@ int main(int argc, char** argv) {
         const bool subsets = argc > 3 && std::string(argv[3]) == "subsets";     // SELB200_UNION=subsets
         emul::launch(3, 32, [&] {
             if (subsets)
-                k_pair_hist_planes<EpiSubsets<EpiWriteHist>, 4>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi},
+                k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi},
                                                              wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH);
             else
                 k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide.data(), meta.data() + M_WIDE,

@@ -157,18 +157,6 @@ int run_case(const Case& cs, uint64_t seed) {
               const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
               return (hi >> 3) > std::min(lo >> 3, 4) + 3;
           });
-    // ---- the same kernel with the p = 14 geometry compiled in (what the library launches for 16384-register sketches) ----
-    if (m == (size_t)4 * PL_CHUNK_REGS && chunk_regs == PL_CHUNK_REGS)
-        check("subsets4",
-              [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
-                  emul::launch(cs.grid, [&] {
-                      k_pair_hist_planes<EpiSubsets<EpiWriteHist>, 4>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi}, wide, counters, counters + 1);
-                  });
-              },
-              [&](uint32_t a, uint32_t b) {
-                  const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
-                  return (hi >> 3) > std::min(lo >> 3, 4) + 3;
-              });
     return bad;
 }
 

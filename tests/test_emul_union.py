@@ -24,7 +24,6 @@ def test_union_kernels_on_the_warp_emulator(tmp_path):
     assert "all identical" in r.stdout
     assert r.stdout.count(" ok") >= 28 and "FAIL" not in r.stdout          # 14 cases x (planes, subsets)
     assert r.stdout.count(" subsets ") == 14
-    assert r.stdout.count(" subsets4 ") >= 3 and r.stdout.count(" subsets4 ") == r.stdout.count(" p=14 ") // 3    # geometry compiled in
 
 
 _MUTATIONS = [
