@@ -21,43 +21,23 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
         }
     };
     const long long npairs = (long long)min(*npairs_dev, npairs_cap);
-    // A thread estimates one pair, but a thread reading its own 256-byte row touches a different cache line than every
-    // other lane of its warp on every load (32 tag look-ups per instruction: that, not the arithmetic, was the kernel's
-    // time).  Each warp therefore stages the rows of its 32 pairs through shared memory: row r is read by the whole warp
-    // (one coalesced 256-byte load) and stored bin-major with a stride of 33 words, so that lane r later finds bin k of
-    // ITS row at [k * 33 + r] — conflict-free whenever the lanes ask for the same bin.  The non-empty bins of a row come
-    // from two ballots of the loading step.
-    __shared__ uint32_t s_rows[4][64 * 33];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* rows = s_rows[wid];
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long base = warp0 * 32; base < npairs; base += nwarps * 32) {
-        const int nrow = (int)min(32ll, npairs - base);
-        unsigned long long nz = 0ull;
-        __syncwarp();                                  // the previous round's rows have been read
-        for (int r = 0; r < nrow; ++r) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(hist + (base + r) * 64) + lane);     // bins 2 lane, 2 lane + 1
-            rows[(2 * lane) * 33 + r] = v.x;
-            rows[(2 * lane + 1) * 33 + r] = v.y;
-            const uint32_t even = __ballot_sync(0xffffffffu, v.x != 0u), odd = __ballot_sync(0xffffffffu, v.y != 0u);
-            if (lane == r) {
-                // bit 2l = bin 2l non-empty, bit 2l+1 = bin 2l+1: interleave the two ballots
-                unsigned long long e = even, o = odd;
-                e = (e | (e << 16)) & 0x0000ffff0000ffffull; o = (o | (o << 16)) & 0x0000ffff0000ffffull;
-                e = (e | (e << 8)) & 0x00ff00ff00ff00ffull;  o = (o | (o << 8)) & 0x00ff00ff00ff00ffull;
-                e = (e | (e << 4)) & 0x0f0f0f0f0f0f0f0full;  o = (o | (o << 4)) & 0x0f0f0f0f0f0f0f0full;
-                e = (e | (e << 2)) & 0x3333333333333333ull;  o = (o | (o << 2)) & 0x3333333333333333ull;
-                e = (e | (e << 1)) & 0x5555555555555555ull;  o = (o | (o << 1)) & 0x5555555555555555ull;
-                nz = e | (o << 1);
-            }
-        }
-        __syncwarp();
-        if (lane >= nrow || nz == 0ull) continue;      // nz == 0: no histogram (cannot happen for a counted pair)
-        const long long pi = base + lane;
+    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
+         pi += (long long)gridDim.x * blockDim.x) {
         const uint2 pr = pairs[pi];
+        // the row's non-empty bins from sixteen independent 128-bit loads (the estimator's own scans for the first and
+        // the last one are a chain of dependent loads: ~35 round trips before the arithmetic starts); the row is in L1 after
+        const uint4* row = reinterpret_cast<const uint4*>(hist + pi * 64);
+        unsigned long long nz = 0ull;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint4 v = __ldg(row + j);
+            const unsigned long long b = (v.x ? 1ull : 0ull) | (v.y ? 2ull : 0ull) | (v.z ? 4ull : 0ull) | (v.w ? 8ull : 0ull);
+            nz |= b << (4 * j);
+        }
         const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+        if (nz == 0ull) continue;                                  // no histogram (cannot happen for a counted pair)
         bool stopped = false;
-        const double t = selb::ertl_mle_range(rows + lane, p, 33, __ffsll((long long)nz) - 1, 63 - __clzll((long long)nz),
+        const double t = selb::ertl_mle_range(hist + pi * 64, p, 1, __ffsll((long long)nz) - 1, 63 - __clzll((long long)nz),
                                               StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);
         if (stopped) continue;
         const double jac = selb::jaccard(e1, e2, t);

@@ -1462,7 +1462,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             }
             DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
-            k_estimate_emit<<<c->sm_count * 6, 128, 0, s>>>(
+            k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
                 c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
                 c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
                 d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
