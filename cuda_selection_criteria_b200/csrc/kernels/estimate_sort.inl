@@ -3,39 +3,76 @@
 // K6: union estimate -> Jaccard -> tau test -> emit
 //   reference: hll.h:1206 (calculate_estimate(counts, ERTL_MLE...)), selection.cpp:286-288
 // ============================================================================
+// J is non-increasing in t: once it is below tau (and outside the near-tau window) at the MLE's lower bound the pair can
+// neither be emitted nor listed as near
+struct StopJ {
+    double tau, slack;
+    unsigned long long e1, e2;
+    __device__ __forceinline__ bool operator()(double t_lb) const { return selb::jaccard(e1, e2, t_lb) < tau - slack; }
+};
+// the same test at the estimator's starting point only: stops there either way and says which way
+struct StopJFirst {
+    StopJ j;
+    bool* fails;
+    __device__ __forceinline__ bool operator()(double t_lb) const { *fails = j(t_lb); return true; }
+};
+
+// the row's non-empty bins from sixteen independent 128-bit loads (the estimator's own scans for the first and the last
+// one are a chain of dependent loads: ~35 round trips before the arithmetic starts); the row is in L1 afterwards
+__device__ __forceinline__ unsigned long long hist_row_nonzero(const uint32_t* __restrict__ row64) {
+    const uint4* row = reinterpret_cast<const uint4*>(row64);
+    unsigned long long nz = 0ull;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint4 v = __ldg(row + j);
+        const unsigned long long b = (v.x ? 1ull : 0ull) | (v.y ? 2ull : 0ull) | (v.z ? 4ull : 0ull) | (v.w ? 8ull : 0ull);
+        nz |= b << (4 * j);
+    }
+    return nz;
+}
+
+// K6 in two steps.  Nine pairs in ten fail J >= tau already at the estimator's starting point, but one passing lane makes
+// its whole warp walk the fp64 secant iterations (the single-kernel form was bound by issue slots for that reason: 122
+// warp instructions per pair).  k_estimate_screen settles the pairs that fail at the starting point and lists the rest;
+// k_estimate_emit runs the full estimator on the list, all lanes busy.
+__global__ void __launch_bounds__(128)
+k_estimate_screen(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
+                  const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
+                  const unsigned long long* __restrict__ e, int p, double tau,
+                  uint32_t* __restrict__ surv, unsigned long long* __restrict__ surv_count) {
+    const long long npairs = (long long)min(*npairs_dev, npairs_cap);
+    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
+         pi += (long long)gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[pi];
+        const unsigned long long nz = hist_row_nonzero(hist + pi * 64);
+        const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
+        if (nz == 0ull) continue;                                  // no histogram (cannot happen for a counted pair)
+        bool fails = false, stopped = false;
+        selb::ertl_mle_range(hist + pi * 64, p, 1, __ffsll((long long)nz) - 1, 63 - __clzll((long long)nz),
+                             StopJFirst{StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &fails}, &stopped);
+        // stopped && fails: settled.  Anything else (not settled at the starting point, or the estimator returned without
+        // iterating: saturated or converged at once) goes through the full estimator
+        if (stopped && fails) continue;
+        const unsigned long long slot = warp_claim(surv_count);
+        surv[slot] = (uint32_t)pi;                                 // the list is as long as the pair list: cannot overflow
+    }
+}
+
 __global__ void __launch_bounds__(128)
 k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
-                const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
+                const uint32_t* __restrict__ surv, const unsigned long long* __restrict__ surv_count,
                 const unsigned long long* __restrict__ e, int p, double tau,
                 uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
                 unsigned long long* __restrict__ out_count, unsigned long long out_cap,
                 uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
                 unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
-    // J is non-increasing in t: once it is below tau (and outside the near-tau window) at the
-    // MLE's lower bound the pair can neither be emitted nor listed as near
-    struct StopJ {
-        double tau, slack;
-        unsigned long long e1, e2;
-        __device__ __forceinline__ bool operator()(double t_lb) const {
-            return selb::jaccard(e1, e2, t_lb) < tau - slack;
-        }
-    };
-    const long long npairs = (long long)min(*npairs_dev, npairs_cap);
-    for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
-         pi += (long long)gridDim.x * blockDim.x) {
+    const long long nsurv = (long long)*surv_count;
+    for (long long si = blockIdx.x * (long long)blockDim.x + threadIdx.x; si < nsurv;
+         si += (long long)gridDim.x * blockDim.x) {
+        const long long pi = (long long)surv[si];
         const uint2 pr = pairs[pi];
-        // the row's non-empty bins from sixteen independent 128-bit loads (the estimator's own scans for the first and
-        // the last one are a chain of dependent loads: ~35 round trips before the arithmetic starts); the row is in L1 after
-        const uint4* row = reinterpret_cast<const uint4*>(hist + pi * 64);
-        unsigned long long nz = 0ull;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint4 v = __ldg(row + j);
-            const unsigned long long b = (v.x ? 1ull : 0ull) | (v.y ? 2ull : 0ull) | (v.z ? 4ull : 0ull) | (v.w ? 8ull : 0ull);
-            nz |= b << (4 * j);
-        }
+        const unsigned long long nz = hist_row_nonzero(hist + pi * 64);
         const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
-        if (nz == 0ull) continue;                                  // no histogram (cannot happen for a counted pair)
         bool stopped = false;
         const double t = selb::ertl_mle_range(hist + pi * 64, p, 1, __ffsll((long long)nz) - 1, 63 - __clzll((long long)nz),
                                               StopJ{tau, 1e-6 * fabs(tau), e1, e2}, &stopped);

@@ -32,7 +32,7 @@ __global__ void k_cb_bounds(const unsigned long long* __restrict__ e, int n, int
 // meta[] (unsigned long long, device): [0] candidates [1] pairs [2] out [3] near of the current
 // range, [4] pairs inside the CB band, [5] tiles of the band, [6] gather: pushed flag
 // ============================================================================
-enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_UNIT = 10, M_STEPS = 11, M_ITEMS = 12, M_ITEMS_MAX = 13, M_WORDS = 16 };
+enum { M_CAND = 0, M_PAIRS = 1, M_OUT = 2, M_NEAR = 3, M_PAIRS_CB = 4, M_TILES = 5, M_PUSHED = 6, M_WIDE = 7, M_BATCH = 8, M_KERR = 9, M_UNIT = 10, M_STEPS = 11, M_ITEMS = 12, M_ITEMS_MAX = 13, M_SURV = 14, M_WORDS = 16 };
 
 // one warp per row block (rb in [0, nrb]; rb == nrb writes the scan sentinel)
 __device__ __forceinline__ void rowblock_span_warp(int rb, int lane, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,

@@ -4,7 +4,7 @@
 //          k_planes_from_bytes, [host: sort by cardinality], k_sorted_prep, k_gather_rows
 //   run  : k_cb_bounds, k_rowblock_span, scan, k_tile_table, k_smh_sigkeys, sort, k_smh_join (or, with a fourth argument
 //          "tiles": k_smh_signatures, k_tile_filter_smh, k_smh_verify),
-//          k_pair_hist_planes (+ k_pair_hist<SrcWide> for wide pairs), k_estimate_emit,
+//          k_pair_hist_planes (+ k_pair_hist<SrcWide> for wide pairs), k_estimate_screen, k_estimate_emit,
 //          k_rowsort_count, scan, k_rowsort_scatter, k_rowsort_rank
 // Input (file): registers and SuperMinHash sketches in FILE-LIST order, tau, band shape.
 // Output (file): cardinalities, sorted order, stage counts, the final (i, k, J) list in print order, near-tau count.
@@ -200,10 +200,18 @@ int main(int argc, char** argv) {
     const unsigned long long out_cap = 1ull << 20, near_cap = 1ull << 16;
     std::vector<uint64_t> out_keys((size_t)out_cap), near_keys((size_t)near_cap);
     std::vector<double> out_j((size_t)out_cap), near_j((size_t)near_cap);
+    std::vector<uint32_t> surv((size_t)cap, 0xDEADBEEFu);
     emul::launch(3, 128, [&] {
-        k_estimate_emit(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
+        k_estimate_screen(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, surv.data(), meta.data() + M_SURV);
+    });
+    emul::launch(2, 128, [&] {
+        k_estimate_emit(hist.data(), pairs.data(), surv.data(), meta.data() + M_SURV, e.data(), p, tau, out_keys.data(), out_j.data(),
                         meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
     });
+    if (meta[M_SURV] > meta[M_PAIRS] || (np > 100 && meta[M_SURV] == meta[M_PAIRS])) {
+        fprintf(stderr, "estimate screen kept %llu of %llu pairs\n", meta[M_SURV], meta[M_PAIRS]);
+        return 6;
+    }
     lap("estimate");
     const long long cnt = (long long)meta[M_OUT];
     // K7: sparse-output print order
