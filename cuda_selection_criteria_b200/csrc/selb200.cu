@@ -1462,19 +1462,29 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             }
             DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
-            // the survivor list borrows the candidate list's buffer (its readers — verify kernels — are done by now)
-            if (attempt > 0 || ri > 0) CK(cudaMemsetAsync(d_cnt + M_SURV, 0, 8, s));
-            k_estimate_screen<<<c->sm_count * 8, 128, 0, s>>>(
-                c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
-                c->e_sorted.as<unsigned long long>(), c->p, tau, c->cand.as<uint32_t>(), d_cnt + M_SURV);
-            CK(cudaGetLastError());
-            k_estimate_emit<<<c->sm_count * 4, 128, 0, s>>>(
-                c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->cand.as<uint32_t>(), d_cnt + M_SURV,
-                c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
-                d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
-                d_cnt + M_NEAR, near_cap);
-            CK(cudaGetLastError());
-            st.launches += 2;
+            if (crit == SELB200_CRIT_CB) {
+                // unfiltered list: screen first (the survivor list borrows the candidate list's buffer, unused in this mode)
+                if (attempt > 0 || ri > 0) CK(cudaMemsetAsync(d_cnt + M_SURV, 0, 8, s));
+                k_estimate_screen<<<c->sm_count * 8, 128, 0, s>>>(
+                    c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
+                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->cand.as<uint32_t>(), d_cnt + M_SURV);
+                CK(cudaGetLastError());
+                k_estimate_emit<<<c->sm_count * 4, 128, 0, s>>>(
+                    c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->cand.as<uint32_t>(), d_cnt + M_SURV, pair_lim,
+                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
+                    d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                    d_cnt + M_NEAR, near_cap);
+                CK(cudaGetLastError());
+                st.launches += 2;
+            } else {
+                k_estimate_emit<<<c->sm_count * 8, 128, 0, s>>>(
+                    c->hist.as<uint32_t>(), c->pairs.as<uint2>(), nullptr, d_cnt + M_PAIRS, pair_lim,
+                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
+                    d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                    d_cnt + M_NEAR, near_cap);
+                CK(cudaGetLastError());
+                st.launches++;
+            }
             DBG_SYNC(c, "estimate + emit");
             cudaEvent_t u2 = c->ev();
             t_union.push_back({u0, u1});

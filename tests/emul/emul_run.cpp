@@ -200,17 +200,26 @@ int main(int argc, char** argv) {
     const unsigned long long out_cap = 1ull << 20, near_cap = 1ull << 16;
     std::vector<uint64_t> out_keys((size_t)out_cap), near_keys((size_t)near_cap);
     std::vector<double> out_j((size_t)out_cap), near_j((size_t)near_cap);
-    std::vector<uint32_t> surv((size_t)cap, 0xDEADBEEFu);
-    emul::launch(3, 128, [&] {
-        k_estimate_screen(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, surv.data(), meta.data() + M_SURV);
-    });
-    emul::launch(2, 128, [&] {
-        k_estimate_emit(hist.data(), pairs.data(), surv.data(), meta.data() + M_SURV, e.data(), p, tau, out_keys.data(), out_j.data(),
-                        meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
-    });
-    if (meta[M_SURV] > meta[M_PAIRS] || (np > 100 && meta[M_SURV] == meta[M_PAIRS])) {
-        fprintf(stderr, "estimate screen kept %llu of %llu pairs\n", meta[M_SURV], meta[M_PAIRS]);
-        return 6;
+    // the filtered list goes through k_estimate_emit directly; with "screen" as fifth argument through the two-step form the
+    // library uses for unfiltered (criterion cb) lists
+    if (argc > 5 && std::string(argv[5]) == "screen") {
+        std::vector<uint32_t> surv((size_t)cap, 0xDEADBEEFu);
+        emul::launch(3, 128, [&] {
+            k_estimate_screen(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, surv.data(), meta.data() + M_SURV);
+        });
+        emul::launch(2, 128, [&] {
+            k_estimate_emit(hist.data(), pairs.data(), surv.data(), meta.data() + M_SURV, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
+                            meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
+        });
+        if (meta[M_SURV] > meta[M_PAIRS] || (np > 100 && meta[M_SURV] == meta[M_PAIRS])) {
+            fprintf(stderr, "estimate screen kept %llu of %llu pairs\n", meta[M_SURV], meta[M_PAIRS]);
+            return 6;
+        }
+    } else {
+        emul::launch(3, 128, [&] {
+            k_estimate_emit(hist.data(), pairs.data(), nullptr, meta.data() + M_PAIRS, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
+                            meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
+        });
     }
     lap("estimate");
     const long long cnt = (long long)meta[M_OUT];

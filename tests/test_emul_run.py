@@ -31,6 +31,7 @@ def exe(tmp_path_factory):
     (120, 63, 0.9, 128, True, "subsets", "join"),        # the default forms: subset counting, equality join
     (150, 64, 0.7, 128, False, "subsets", "join"),       # 32 bands of 4 rows
     (130, 61, 0.9, 128, False, "subsets", "tiles"),      # the all-pairs tile filter + verify (SELB200_SMHFILTER=tiles)
+    (130, 61, 0.9, 128, False, "subsets", "join screen"),  # estimate in two steps (screen, then the survivors): the cb route
 ])
 def test_whole_smh_a_run_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, outliers, union_form, smh_form):
     tau32 = np.float32(tau)
@@ -52,7 +53,7 @@ def test_whole_smh_a_run_on_the_emulator(exe, tmp_path, n, seed, tau, m_aux, out
         f.write(struct.pack("<d", float(tau32)))
         f.write(np.ascontiguousarray(regs, np.uint8).tobytes())
         f.write(np.ascontiguousarray(smh, np.uint64).tobytes())
-    r = subprocess.run([exe, str(inp), str(outp), union_form, smh_form], capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([exe, str(inp), str(outp), union_form] + smh_form.split(), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(outp, "rb").read()
     p_cb, cand, p_aux, p_out, near, wide, tie, _ = struct.unpack_from("<8q", raw, 0)
