@@ -236,25 +236,34 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 }
 
 // ============================================================================
-// K3'/K4': smh_a as an EQUALITY JOIN (default; the tile filter above stays as SELB200_SMHFILTER=tiles).
+// K3'/K4': smh_a as an EQUALITY JOIN (default below four shards; the tile filter above stays for more shards and as
+// SELB200_SMHFILTER=tiles).
 // "Some band equal" (criteria_sketch.hpp:71-79) is a join on (band, band contents): instead of testing all P_cb pairs
 // of the band against all bands (O(P_cb * bands): 3.7e9 half-word operations at n = 100k), the n * bands keys
-// (band << 16 | 16-bit signature of the band's buckets) are sorted once (cub radix sort, stable: equal keys keep ascending
-// sorted position) and every run of equal keys is walked: work O(n * bands + matches).
-//   k_smh_sigkeys : keys, values (= sorted position) in genome-major order, and the signatures genome-major (sigG: two
-//                   bands per word, nbw words per genome = 32 B at 16 bands) for the step below
-//   k_smh_join_expand + k_smh_join : the followers k of a sorted key (band b, genome i) in its run with k <= hi(i) are
-//                   the pairs of the CB band whose band-b signatures agree; every (key, follower) is written out as an
-//                   item and handled by a thread of its own (a run of a thousand identical bands is 5e5 items for as
-//                   many threads, not a serial walk).  A pair is handled ONCE, by the first band whose signatures
-//                   agree (the thread reads the earlier bands' signatures of both genomes: 32 B each): that handler
-//                   compares the buckets of every signature-equal band from b on, exactly, and emits the pair at the first
-//                   band that really is equal — the decision of k_smh_verify, so P_aux is the reference's.
-// Shards: the walk is replicated, the handler of a pair is the shard (i + k) mod n_shards (disjoint, balanced).
+// (band << sbits | top sbits of the 16-bit signature of the band's buckets; sbits = 16 up to 256 bands, fewer beyond so
+// that the bucket table stays below 2^24 entries) are bucketed by a counting sort and every bucket is walked:
+// work O(n * bands + matches).
+//   k_smh_sigkeys   : key of every (genome, band), its rank inside its bucket (the atomicAdd that counts the bucket),
+//                     and the full signatures genome-major (sigG: two bands per word, nbw words per genome = 32 B at 16 bands)
+//   exclusive scan  : bucket offsets (cub)
+//   k_smh_scatter   : positions into their buckets (order inside a bucket: arbitrary)
+//   k_smh_join_expand + k_smh_join : for the element (band b, genome i) the members k of its bucket with i < k <= hi(i) are
+//                     the pairs of the CB band whose band-b keys agree (every unordered pair exactly once, from its smaller
+//                     position); every one is written out as an item and handled by a thread of its own (a bucket of a
+//                     thousand identical bands is 5e5 items for as many threads, not a serial walk).  A pair is handled
+//                     ONCE, by the first band whose KEYS agree (the thread reads the earlier bands' signatures of both
+//                     genomes: 32 B each): that handler compares the buckets of every band from b on whose 16-bit signatures
+//                     agree, exactly, and emits the pair at the first band that really is equal — an equal band has equal
+//                     signatures, hence equal keys, hence lies at or behind the handler's band: the decision is that of
+//                     k_smh_verify, so P_aux is the reference's.
+// (First version: stable radix sort of (key, position) + galloping search for the followers: 86 + 56 us at n = 100k
+// against 8 + 5 + 40 for scan, scatter and this expansion.)
+// Shards: buckets and items are replicated, the handler of a pair is the shard (i + k) mod n_shards (disjoint, balanced).
 // ============================================================================
 __global__ void __launch_bounds__(256)
-k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, int n_rows, int n_bands, int nbw,
-              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ sigG) {
+k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, int n_rows, int n_bands, int nbw, int sbits,
+              uint32_t* __restrict__ keys, uint32_t* __restrict__ rank, uint32_t* __restrict__ bucket_cnt,
+              uint32_t* __restrict__ sigG) {
     const int nb2 = nbw * 2;
     const long long total = n * nb2;
     const long long stride = (long long)gridDim.x * blockDim.x;          // even: lane pairs stay together
@@ -267,12 +276,21 @@ k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, i
         uint32_t sig = 0;
         if (real) {
             sig = band_sig16(aux_sorted + (size_t)g * m_aux + (size_t)b * n_rows, n_rows);
-            keys[g * n_bands + b] = ((uint32_t)b << 16) | sig;
-            vals[g * n_bands + b] = (uint32_t)g;
+            const uint32_t key = ((uint32_t)b << sbits) | (sig >> (16 - sbits));
+            keys[g * n_bands + b] = key;
+            rank[g * n_bands + b] = atomicAdd(bucket_cnt + key, 1u);
         }
         const uint32_t other = __shfl_down_sync(0xffffffffu, sig, 1);
         if (live && !(b & 1)) sigG[g * nbw + (b >> 1)] = sig | (other << 16);
     }
+}
+
+// element e = (genome, band) -> its slot of its bucket
+__global__ void __launch_bounds__(256)
+k_smh_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ bucket_off,
+              long long n_keys, int n_bands, uint32_t* __restrict__ members) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_keys; e += (long long)gridDim.x * blockDim.x)
+        members[bucket_off[keys[e]] + rank[e]] = (uint32_t)(e / n_bands);
 }
 
 // buckets of band b of the two genomes equal?  All loads are issued before the first compare (a chain of load, compare,
@@ -302,34 +320,30 @@ __device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, 
     return true;
 }
 
-// followers of key s: the keys t > s of its run whose genome lies inside the CB band of genome vals[s].  Inside a run
-// the positions ascend, so "same key and position <= hi(i)" holds for a prefix of what follows s: galloping search
-// (most runs are one or two keys long: one or two loads).  Every (key, follower) becomes one ITEM {i, k, band}: a warp
+// element e = (genome i, band b) in [e0, e1): the members k of its bucket with i < k <= hi(i) become ITEMS {i, k, band}.  A warp
 // claims the room for its lanes' items with one atomic and the lanes write them — the walk itself is then one thread per
-// item (k_smh_join), whatever the length of the runs.
+// item (k_smh_join), whatever the size of the buckets.  Most buckets hold one element: settled by two loads.
 __global__ void __launch_bounds__(256)
-k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_keys, long long s0, long long s1,
-                  const int32_t* __restrict__ lo, const int32_t* __restrict__ hi, uint4* __restrict__ items,
-                  unsigned long long* __restrict__ item_count, unsigned long long item_cap) {
+k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bucket_off, const uint32_t* __restrict__ members,
+                  long long e0, long long e1, int n_bands, int sbits, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
+                  uint4* __restrict__ items, unsigned long long* __restrict__ item_count, unsigned long long item_cap) {
     const int lane = threadIdx.x & 31;
-    for (long long sb = s0 + (blockIdx.x * (long long)blockDim.x + threadIdx.x - lane); sb < s1; sb += (long long)gridDim.x * blockDim.x) {
-        const long long s = sb + lane;
+    for (long long eb = e0 + (blockIdx.x * (long long)blockDim.x + threadIdx.x - lane); eb < e1; eb += (long long)gridDim.x * blockDim.x) {
+        const long long e = eb + lane;
         unsigned long long c = 0;
-        uint32_t key = 0;
-        int i = 0;
-        if (s < s1) {
-            key = keys[s];
-            i = (int)vals[s];
-            // most keys have no follower at all: settled by the neighbouring key, before the loads that depend on vals[s]
-            const bool alone = s + 1 >= n_keys || keys[s + 1] != key;
-            const int hi_i = alone ? -1 : hi[i];
-            if (!alone && hi_i >= lo[i]) {
-                auto ok = [&](long long t) { return t < n_keys && keys[t] == key && (int)vals[t] <= hi_i; };
-                long long step = 1, good = 0;          // largest d with ok(s + d): true for d = 1 .. c, false afterwards
-                while (ok(s + good + step)) { good += step; step <<= 1; }
-                for (step >>= 1; step >= 1; step >>= 1)
-                    if (ok(s + good + step)) good += step;
-                c = (unsigned long long)good;
+        uint32_t key = 0, a = 0, b = 0;
+        int i = 0, hi_i = -1;
+        if (e < e1) {
+            key = keys[e];
+            a = bucket_off[key]; b = bucket_off[key + 1];
+            if (b - a > 1u) {
+                i = (int)(e / n_bands);
+                hi_i = hi[i];
+                if (hi_i >= lo[i])                      // lo(i) = max(i + 1, first genome with e > 0): implied by k > i for such rows
+                    for (uint32_t t = a; t < b; ++t) {
+                        const int k = (int)members[t];
+                        c += (k > i && k <= hi_i) ? 1u : 0u;
+                    }
             }
         }
         unsigned long long pre = c;                    // inclusive scan over the lanes
@@ -342,15 +356,23 @@ k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(item_count, total);
         base = __shfl_sync(0xffffffffu, base, 0) + (pre - c);
-        for (unsigned long long d = 0; d < c; ++d)
-            if (base + d < item_cap) items[base + d] = make_uint4((uint32_t)i, vals[s + 1 + (long long)d], key >> 16, 0u);
+        if (c) {
+            unsigned long long d = 0;
+            for (uint32_t t = a; t < b; ++t) {
+                const int k = (int)members[t];
+                if (k > i && k <= hi_i) {
+                    if (base + d < item_cap) items[base + d] = make_uint4((uint32_t)i, (uint32_t)k, key >> sbits, 0u);
+                    ++d;
+                }
+            }
+        }
     }
 }
 
 // one thread per item {i, k, band}: see the header above
 __global__ void __launch_bounds__(256)
 k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict__ item_count, unsigned long long item_cap,
-           const uint32_t* __restrict__ sigG, int nbw, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
+           const uint32_t* __restrict__ sigG, int nbw, int sbits, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
            int shard, int n_shards, uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
            unsigned long long pair_cap, unsigned long long* __restrict__ cand_count, unsigned long long* __restrict__ item_max) {
     const unsigned long long n_items = min(*item_count, item_cap);
@@ -371,23 +393,28 @@ k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict
             if (n_shards <= 1 || (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) == shard) {
                 const uint32_t* si = sigG + (size_t)i * nbw;
                 const uint32_t* sk = sigG + (size_t)k * nbw;
-                // an earlier band with equal signatures handles the pair (words of four at a time: independent loads)
+                // an earlier band with equal KEYS (the top sbits of the signatures: what the buckets are made of, so an item
+                // exists for it) handles the pair (words of four at a time: independent loads)
+                const uint32_t kmask = (0xffffu << (16 - sbits)) & 0xffffu;
                 bool earlier = false;
+                uint32_t x_own = 0u;
                 for (int wd = 0; wd <= (bnd >> 1) && !earlier; wd += 4) {
                     uint32_t x[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) x[u] = wd + u <= (bnd >> 1) ? (__ldg(si + wd + u) ^ __ldg(sk + wd + u)) : 0xffffffffu;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (2 * (wd + u) < bnd && (x[u] & 0xffffu) == 0u) earlier = true;
-                        if (2 * (wd + u) + 1 < bnd && (x[u] >> 16) == 0u) earlier = true;
+                        if (2 * (wd + u) < bnd && (x[u] & kmask) == 0u) earlier = true;
+                        if (2 * (wd + u) + 1 < bnd && ((x[u] >> 16) & kmask) == 0u) earlier = true;
+                        if (wd + u == (bnd >> 1)) x_own = x[u];
                     }
                 }
                 if (!earlier) {
                     ++n_cand;
                     const uint64_t* v1 = aux_sorted + (size_t)i * m_aux;
                     const uint64_t* v2 = aux_sorted + (size_t)k * m_aux;
-                    hit = smh_band_equal(v1, v2, bnd, n_rows);
+                    // equal buckets need equal 16-bit signatures: with coarse keys (sbits < 16) this band may already be out
+                    hit = ((x_own >> (16 * (bnd & 1))) & 0xffffu) == 0u && smh_band_equal(v1, v2, bnd, n_rows);
                     for (int b2 = bnd + 1; b2 < n_bands && !hit; ++b2) {
                         const uint32_t x = __ldg(si + (b2 >> 1)) ^ __ldg(sk + (b2 >> 1));
                         if (((x >> (16 * (b2 & 1))) & 0xffffu) == 0u) hit = smh_band_equal(v1, v2, b2, n_rows);

@@ -1175,8 +1175,12 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     const bool use_smh = crit == SELB200_CRIT_SMH_A && smh_shape_ok;
     const bool smh_join = use_smh && smh_join_enabled(n_shards) && (int64_t)n * n_bands < (1ll << 31) && n_bands <= 65536;
     const long long jn_keys = (long long)n * n_bands;
-    // join_buf: keys, values, sorted keys, sorted values (u32 each), genome-major signatures
-    const long long jn_words = 4 * jn_keys + (long long)n * ((n_bands + 1) / 2);
+    // join_buf: keys, ranks, bucket members (u32 per (genome, band)), genome-major signatures, bucket counters and offsets.
+    // Key = band << sbits | top sbits of the signature: 16 bits up to 256 bands, fewer beyond (the table stays <= 2^24)
+    int j_sbits = 16;
+    while (j_sbits > 1 && ((long long)n_bands << j_sbits) > (1ll << 24)) --j_sbits;
+    const long long j_buckets = (long long)std::max(n_bands, 1) << j_sbits;
+    const long long jn_words = 3 * jn_keys + (long long)n * ((n_bands + 1) / 2) + 2 * (j_buckets + 1);
 
     CKR(c->cand.ensure((size_t)PAIR_CAP * sizeof(uint2)));
     CKR(c->pairs.ensure((size_t)PAIR_CAP * sizeof(uint2)));
@@ -1304,26 +1308,28 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         if ((int)ranges.size() > SNAP_MAX) return fail(SELB200_ENOMEM, "too many tile ranges (%zu)", ranges.size());
         t_filter.clear(); t_verify.clear(); t_union.clear(); t_est.clear();
         if (use_smh && smh_join) {
-            // keys + values (unsorted, sorted) and genome-major signatures; one stable radix sort over band | signature
+            // keys, ranks, members (u32 per (genome, band)), genome-major signatures, bucket counters and offsets
             cudaEvent_t a0 = c->ev();
             CKR(c->join_buf.ensure((size_t)jn_words * 4));
             if (c->join_item_cap < (4ll << 20)) c->join_item_cap = 4ll << 20;
             CKR(c->join_items.ensure((size_t)c->join_item_cap * sizeof(uint4)));
             uint32_t* jk = c->join_buf.as<uint32_t>();
-            int key_bits = 16;
-            while ((1 << (key_bits - 16)) < n_bands) ++key_bits;
+            uint32_t *j_keys = jk, *j_rank = jk + jn_keys, *j_memb = jk + 2 * jn_keys, *j_sig = jk + 3 * jn_keys;
+            uint32_t *j_cnt = j_sig + (size_t)n * n_words, *j_off = j_cnt + (j_buckets + 1);
+            CK(cudaMemsetAsync(j_cnt, 0, (size_t)(j_buckets + 1) * 4, s));
             const int grid = (int)std::min<int64_t>(((int64_t)n * n_words * 2 + 255) / 256, (int64_t)c->sm_count * 16);
-            k_smh_sigkeys<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->aux_len, n_rows, n_bands, n_words, jk,
-                                               jk + jn_keys, jk + 4 * jn_keys);
+            k_smh_sigkeys<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->aux_len, n_rows, n_bands, n_words, j_sbits, j_keys,
+                                               j_rank, j_cnt, j_sig);
             CK(cudaGetLastError());
             size_t tmp_bytes = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, jk, jk + 2 * jn_keys, jk + jn_keys, jk + 3 * jn_keys,
-                                               (int)jn_keys, 0, key_bits, s));
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), s));
             CKR(c->cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, jk, jk + 2 * jn_keys, jk + jn_keys, jk + 3 * jn_keys,
-                                               (int)jn_keys, 0, key_bits, s));
-            st.launches += 2;
-            DBG_SYNC(c, "smh signature keys + sort");
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), s));
+            k_smh_scatter<<<(int)std::min<int64_t>((jn_keys + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, s>>>(
+                j_keys, j_rank, j_off, jn_keys, n_bands, j_memb);
+            CK(cudaGetLastError());
+            st.launches += 3;
+            DBG_SYNC(c, "smh signature keys + buckets");
             t_filter.push_back({a0, c->ev()});
         } else if (use_smh) {
             cudaEvent_t a0 = c->ev();
@@ -1363,14 +1369,16 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                     s1 = jn_keys * std::min<long long>(rg.second, t_end) / t_end;
                 }
                 const uint32_t* jk = c->join_buf.as<uint32_t>();
+                const uint32_t *j_keys = jk, *j_memb = jk + 2 * jn_keys, *j_sig = jk + 3 * jn_keys;
+                const uint32_t* j_off = j_sig + (size_t)n * n_words + (j_buckets + 1);
                 CK(cudaMemsetAsync(d_cnt + M_ITEMS, 0, 8, s));
                 const int grid = (int)std::max<long long>(1, std::min<long long>((s1 - s0 + 255) / 256, (long long)c->sm_count * 16));
-                k_smh_join_expand<<<grid, 256, 0, s>>>(jk + 2 * jn_keys, jk + 3 * jn_keys, jn_keys, s0, s1, c->lo.as<int32_t>(),
+                k_smh_join_expand<<<grid, 256, 0, s>>>(j_keys, j_off, j_memb, s0, s1, n_bands, j_sbits, c->lo.as<int32_t>(),
                                                        c->hi.as<int32_t>(), c->join_items.as<uint4>(), d_cnt + M_ITEMS,
                                                        (unsigned long long)c->join_item_cap);
                 CK(cudaGetLastError());
                 k_smh_join<<<c->sm_count * 16, 256, 0, s>>>(c->join_items.as<uint4>(), d_cnt + M_ITEMS, (unsigned long long)c->join_item_cap,
-                                                            jk + 4 * jn_keys, n_words, c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows,
+                                                            j_sig, n_words, j_sbits, c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows,
                                                             n_bands, prm->shard, n_shards, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
                                                             (unsigned long long)PAIR_CAP, d_cnt + M_CAND, d_cnt + M_ITEMS_MAX);
                 st.launches += 1;

@@ -66,17 +66,24 @@ int main(int argc, char** argv) {
     std::vector<uint2> cand((size_t)cap), pairs((size_t)cap);
     std::vector<uint2> all_pairs;
     unsigned long long cand_total = 0;
-    // equality join (the default of the library): keys, stable sort (cub radix sort on the device), one walk per shard
+    // equality join (the default of the library below four shards): keys + bucket counts, exclusive scan (cub on the
+    // device), scatter; then one expansion + walk per shard.  sbits < 16 (coarser buckets, as for more than 256 bands) when
+    // the sixth argument says so
     const long long nk = (long long)n * n_bands;
-    std::vector<uint32_t> skeys, svals, sigG;
+    const int sbits = argc > 6 ? atoi(argv[6]) : 16;
+    const long long nbk = (long long)n_bands << sbits;
+    std::vector<uint32_t> jkeys, members, sigG, boff;
     if (join) {
-        std::vector<uint32_t> keys((size_t)nk, 0xDEADBEEFu), vals((size_t)nk, 0xDEADBEEFu), idx((size_t)nk);
+        std::vector<uint32_t> rank((size_t)nk, 0xDEADBEEFu), bcnt((size_t)nbk + 1, 0u);
+        jkeys.assign((size_t)nk, 0xDEADBEEFu);
+        members.assign((size_t)nk, 0xDEADBEEFu);
         sigG.assign((size_t)n * n_words, 0xDEADBEEFu);
-        emul::launch(2, 256, [&] { k_smh_sigkeys(aux.data(), n, m_aux, n_rows, n_bands, n_words, keys.data(), vals.data(), sigG.data()); });
-        std::iota(idx.begin(), idx.end(), 0u);
-        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-        skeys.resize((size_t)nk); svals.resize((size_t)nk);
-        for (long long t = 0; t < nk; ++t) { skeys[(size_t)t] = keys[idx[(size_t)t]]; svals[(size_t)t] = vals[idx[(size_t)t]]; }
+        boff.resize((size_t)nbk + 1);
+        emul::launch(2, 256, [&] {
+            k_smh_sigkeys(aux.data(), n, m_aux, n_rows, n_bands, n_words, sbits, jkeys.data(), rank.data(), bcnt.data(), sigG.data());
+        });
+        std::exclusive_scan(bcnt.begin(), bcnt.end(), boff.begin(), 0u);
+        emul::launch(2, 256, [&] { k_smh_scatter(jkeys.data(), rank.data(), boff.data(), nk, n_bands, members.data()); });
     }
     for (int shard = 0; shard < n_shards; ++shard) {       // every shard, one after the other
         meta[M_CAND] = meta[M_PAIRS] = 0;
@@ -85,11 +92,12 @@ int main(int argc, char** argv) {
             std::vector<uint4> items((size_t)item_cap);
             meta[M_ITEMS] = 0;
             emul::launch(2, 256, [&] {
-                k_smh_join_expand(skeys.data(), svals.data(), nk, 0, nk, lo.data(), hi.data(), items.data(), meta.data() + M_ITEMS, item_cap);
+                k_smh_join_expand(jkeys.data(), boff.data(), members.data(), 0, nk, n_bands, sbits, lo.data(), hi.data(), items.data(),
+                                  meta.data() + M_ITEMS, item_cap);
             });
             if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(fgrid, 256, [&] {
-                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, aux.data(), m_aux, n_rows, n_bands,
+                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, sbits, aux.data(), m_aux, n_rows, n_bands,
                            shard, n_shards, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         } else {

@@ -2,7 +2,8 @@
 // them (csrc/selb200.cu: load_chunk, load_end, selb200_run), from the same .inl sources the GPU build compiles:
 //   load : k_max_byte, k_pair_hist<SrcSelf> (per-genome histograms), k_genome_cards (Ertl MLE + value range),
 //          k_planes_from_bytes, [host: sort by cardinality], k_sorted_prep, k_gather_rows
-//   run  : k_cb_bounds, k_rowblock_span, scan, k_tile_table, k_smh_sigkeys, sort, k_smh_join (or, with a fourth argument
+//   run  : k_cb_bounds, k_rowblock_span, scan, k_tile_table, k_smh_sigkeys, scan, k_smh_scatter, k_smh_join_expand, k_smh_join
+//          (or, with a fourth argument
 //          "tiles": k_smh_signatures, k_tile_filter_smh, k_smh_verify),
 //          k_pair_hist_planes (+ k_pair_hist<SrcWide> for wide pairs), k_estimate_screen, k_estimate_emit,
 //          k_rowsort_count, scan, k_rowsort_scatter, k_rowsort_rank
@@ -137,16 +138,19 @@ int main(int argc, char** argv) {
     std::vector<uint2> cand((size_t)cap), pairs((size_t)cap);
     const bool tiles_filter = argc > 4 && std::string(argv[4]) == "tiles";       // SELB200_SMHFILTER=tiles
     if (!tiles_filter) {
-        // the default: equality join (k_smh_sigkeys -> stable sort by band | signature -> k_smh_join); the device build
-        // sorts with cub's radix sort, std::stable_sort stands in for it here
+        // the default: equality join — k_smh_sigkeys (keys, ranks, bucket counts) -> exclusive scan (cub on the device) ->
+        // k_smh_scatter -> k_smh_join_expand -> k_smh_join
         const long long nk = (long long)n * n_bands;
-        std::vector<uint32_t> keys((size_t)nk), vals((size_t)nk), sigG((size_t)n * n_words, 0xDEADBEEFu);
-        emul::launch(2, 256, [&] { k_smh_sigkeys(aux_sorted.data(), n, m_aux, n_rows, n_bands, n_words, keys.data(), vals.data(), sigG.data()); });
-        std::vector<uint32_t> idx((size_t)nk), skeys((size_t)nk), svals((size_t)nk);
-        std::iota(idx.begin(), idx.end(), 0u);
-        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-        for (long long t = 0; t < nk; ++t) { skeys[(size_t)t] = keys[idx[(size_t)t]]; svals[(size_t)t] = vals[idx[(size_t)t]]; }
-        // two passes over two parts of the keys, as after a split pass: expand the followers into items, one thread per item
+        const int sbits = 16;
+        const long long nbk = (long long)n_bands << sbits;
+        std::vector<uint32_t> keys((size_t)nk, 0xDEADBEEFu), rank((size_t)nk, 0xDEADBEEFu), members((size_t)nk, 0xDEADBEEFu),
+            sigG((size_t)n * n_words, 0xDEADBEEFu), bcnt((size_t)nbk + 1, 0u), boff((size_t)nbk + 1);
+        emul::launch(2, 256, [&] {
+            k_smh_sigkeys(aux_sorted.data(), n, m_aux, n_rows, n_bands, n_words, sbits, keys.data(), rank.data(), bcnt.data(), sigG.data());
+        });
+        std::exclusive_scan(bcnt.begin(), bcnt.end(), boff.begin(), 0u);
+        emul::launch(2, 256, [&] { k_smh_scatter(keys.data(), rank.data(), boff.data(), nk, n_bands, members.data()); });
+        // two passes over two parts of the elements, as after a split pass: expand the bucket members into items, one thread per item
         const long long mid = nk / 3;
         const unsigned long long item_cap = 1ull << 22;
         std::vector<uint4> items((size_t)item_cap);
@@ -154,11 +158,12 @@ int main(int argc, char** argv) {
             const long long s0 = part ? mid : 0, s1 = part ? nk : mid;
             meta[M_ITEMS] = 0;
             emul::launch(2, 256, [&] {
-                k_smh_join_expand(skeys.data(), svals.data(), nk, s0, s1, lo.data(), hi.data(), items.data(), meta.data() + M_ITEMS, item_cap);
+                k_smh_join_expand(keys.data(), boff.data(), members.data(), s0, s1, n_bands, sbits, lo.data(), hi.data(), items.data(),
+                                  meta.data() + M_ITEMS, item_cap);
             });
             if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(part ? 3 : 2, 256, [&] {
-                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, aux_sorted.data(), m_aux, n_rows, n_bands,
+                k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, sbits, aux_sorted.data(), m_aux, n_rows, n_bands,
                            0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         }

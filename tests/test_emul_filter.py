@@ -55,7 +55,7 @@ def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards,
         f.write(struct.pack("<d", float(tau32)))          # tau = (double)(float) threshold, selection.cpp:81
         f.write(np.ascontiguousarray(e, np.uint64).tobytes())
         f.write(np.ascontiguousarray(aux_sorted, np.uint64).tobytes())
-    r = subprocess.run([exe, str(inp), str(outp), str(n_shards), str(grid), form], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([exe, str(inp), str(outp), str(n_shards), str(grid)] + form.split(), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(outp, "rb").read()
     p_cb, tiles, cand, npairs = struct.unpack_from("<4q", raw, 0)
@@ -66,7 +66,7 @@ def run_emulated(exe, tmp_path, e, aux_sorted, tau32, n_rows, n_bands, n_shards,
     return lo, hi, p_cb, tiles, cand, [tuple(x) for x in pr.tolist()]
 
 
-@pytest.mark.parametrize("form", ["join", "tiles"])
+@pytest.mark.parametrize("form", ["join", "join 9", "tiles"])     # "join 9": 9 signature bits in the bucket key (coarser buckets)
 @pytest.mark.parametrize("n,seed,tau,m_aux,n_shards,grid", [
     (700, 41, 0.9, 128, 1, 3),        # the benchmark's shape: 16 bands x 8 rows, 8 signature words
     (600, 42, 0.75, 128, 2, 2),       # 32 bands x 4 rows: two chunks of signature words per tile; two shards
