@@ -441,12 +441,13 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm, n_shards=1):
     smh_mode = os.environ.get("SELB200_SMHFILTER", "")
     if cfg.criterion == "smh_a" and (smh_mode == "join" or (smh_mode != "tiles" and n_shards < 4)):
         nb = st["n_bands"]
-        # equality join: n x bands keys of 8 B (key + position) generated, sorted (three 8-bit radix passes, each reading and
-        # writing them) and walked once, plus the exact bucket compare of the candidates
-        add("filter", "k_smh_sigkeys + cub radix sort + k_smh_join", mean("ms_filter"), "hbm", cfg.n * nb, 8.0 * 9,
-            f"{cfg.n} x {nb} (band | signature, position) keys of 8 B: written once, 3 radix passes read + write, the walk reads them "
-            "(9 x 8 B per key); work is O(n x bands + matches), not O(P_cb x bands)",
-            "latency-bound: seven small launches (keys, five of the sort, walk) over 13 MB")
+        # equality join: n x bands elements bucketed by a counting sort and walked once, plus the exact bucket compare of
+        # the candidates
+        add("filter", "k_smh_sigkeys + scan + k_smh_scatter + k_smh_join_expand + k_smh_join", mean("ms_filter"), "hbm", cfg.n * nb,
+            8.0 * st["n_rows"] + 24.0,
+            f"{cfg.n} x {nb} (genome, band) elements: the band's {st['n_rows']} buckets read once (8 B each) + key, rank and bucket slot "
+            "written and read (24 B); work is O(n x bands + matches), not O(P_cb x bands)",
+            "latency-bound: six small launches (keys, two of the scan, scatter, expansion, walk), dependent loads per item")
     elif cfg.criterion == "smh_a":
         nb = st["n_bands"]
         add("filter", "k_smh_signatures + k_tile_filter_smh", mean("ms_filter"), "int_alu", p_cb, float((nb + 1) // 2),

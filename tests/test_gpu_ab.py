@@ -33,6 +33,17 @@ for crit, aux, kind, tau in (("smh_a", synth.smh(plan, 128, device=0), AUX_SMH, 
         r = sel.run(tau=np.float32(tau), criterion=crit)
     h = hashlib.sha256(r.i.tobytes() + r.k.tobytes() + r.jaccard.tobytes()).hexdigest()
     out[f"{crit}@{tau}"] = [h, int(r.i.size), int(r.stats["pairs_cb"]), int(r.stats["pairs_aux"]), int(r.stats["pairs_near"])]
+# 1500 copies of one genome: every band of theirs is one bucket of 1500 (1.1 M items per band, 18 M in all: the join's item
+# list overflows its first capacity and the pass is redone), 1.1 M pairs with J = 1 (the output list grows too)
+plan = synth.make_plan(4000, 7)
+regs_h, aux_h = synth.hll(plan, 14).copy(), synth.smh(plan, 128).copy()
+regs_h[2000:3500] = regs_h[1999]
+aux_h[2000:3500] = aux_h[1999]
+with S.Selection(0) as sel:
+    sel.load(regs_h, aux_h, AUX_SMH)
+    r = sel.run(tau=np.float32(0.9), criterion="smh_a")
+h = hashlib.sha256(r.i.tobytes() + r.k.tobytes() + r.jaccard.tobytes()).hexdigest()
+out["duplicates"] = [h, int(r.i.size), int(r.stats["pairs_cb"]), int(r.stats["pairs_aux"]), int(r.stats["pairs_near"])]
 print("RESULT " + json.dumps(out))
 """
 
@@ -62,3 +73,4 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
     tiles = _run({"SELB200_SMHFILTER": "tiles"}, tmp_path)        # all-pairs tile filter + verify instead of the equality join
     assert tiles == by
     assert all(v[1] > 1000 for v in default.values())          # thousands of emitted pairs in every case
+    assert default["duplicates"][1] > 1500 * 1499 // 2         # every pair of the 1501 identical genomes, and the rest
