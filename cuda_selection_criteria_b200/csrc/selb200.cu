@@ -205,7 +205,7 @@ struct selb200_ctx {
     std::vector<uint64_t> h_e;
 
     // run scratch (grow-only)
-    DevBuf lo, hi, tile_prefix, tile_cb0, tile_rc, sigT, cand, pairs, hist, counters, cub_tmp;
+    DevBuf lo, hi, tile_prefix, tile_cb0, tile_rc, sigT, cand, pairs, hist, counters, cub_tmp, cub_tmp2;
     DevBuf out_keys, out_j, out_keys2, out_j2, near_keys, near_j;
     int64_t out_count = 0, near_count = 0;
     int64_t hist_cap_pairs = 0, out_cap = 0;      // grow-only capacities of the sync-free run pipeline
@@ -252,16 +252,18 @@ struct selb200_ctx {
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
 
-    cudaEvent_t ev() {
+    cudaEvent_t ev() { return ev_on(stream); }
+    cudaEvent_t ev_on(cudaStream_t where) {
         if (ev_used == ev_pool.size()) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             ev_pool.push_back(e);
         }
         cudaEvent_t e = ev_pool[ev_used++];
-        cudaEventRecord(e, stream);
+        cudaEventRecord(e, where);
         return e;
     }
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;     // side-stream work of a run (signatures next to the bounds)
 };
 
 // ============================================================================
@@ -893,7 +895,7 @@ void selb200_destroy(selb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
-                      &c->counters, &c->cub_tmp, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
+                      &c->counters, &c->cub_tmp, &c->cub_tmp2, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
                       &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -902,6 +904,8 @@ void selb200_destroy(selb200_ctx* c) {
     if (c->h_snap) cudaFreeHost(c->h_snap);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->h2d_evs) if (e) cudaEventDestroy(e);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    if (c->join_ev) cudaEventDestroy(c->join_ev);
     for (PackSlot& ps : c->pack_slots) {
         if (ps.buf) cudaFreeHost(ps.buf);
         if (ps.free_ev) cudaEventDestroy(ps.free_ev);
@@ -1113,6 +1117,14 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     unsigned long long* d_cnt = c->counters.as<unsigned long long>();
 
     cudaEvent_t ev_begin = c->ev();
+    // smh_a: the signatures / bucket keys do not depend on the CB band, so they run on the side stream next to the bounds
+    // kernel (fork here, join before the filter): 20 us of a run that is 0.6 ms at eight shards
+    cudaStream_t side = c->copy_stream;
+    if (!c->fork_ev) {
+        CK(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->fork_ev, s));
     // ---- K2: CB band + tile list, all on the device ------------------------------------------
     int zeros = 0;
     while (zeros < n && c->h_e[(size_t)zeros] == 0) ++zeros;
@@ -1309,39 +1321,45 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
         t_filter.clear(); t_verify.clear(); t_union.clear(); t_est.clear();
         if (use_smh && smh_join) {
             // keys, ranks, members (u32 per (genome, band)), genome-major signatures, bucket counters and offsets
-            cudaEvent_t a0 = c->ev();
+            CK(cudaStreamWaitEvent(side, c->fork_ev, 0));
+            cudaEvent_t a0 = c->ev_on(side);
             CKR(c->join_buf.ensure((size_t)jn_words * 4));
             if (c->join_item_cap < (4ll << 20)) c->join_item_cap = 4ll << 20;
             CKR(c->join_items.ensure((size_t)c->join_item_cap * sizeof(uint4)));
             uint32_t* jk = c->join_buf.as<uint32_t>();
             uint32_t *j_keys = jk, *j_rank = jk + jn_keys, *j_memb = jk + 2 * jn_keys, *j_sig = jk + 3 * jn_keys;
             uint32_t *j_cnt = j_sig + (size_t)n * n_words, *j_off = j_cnt + (j_buckets + 1);
-            CK(cudaMemsetAsync(j_cnt, 0, (size_t)(j_buckets + 1) * 4, s));
+            CK(cudaMemsetAsync(j_cnt, 0, (size_t)(j_buckets + 1) * 4, side));
             const int grid = (int)std::min<int64_t>(((int64_t)n * n_words * 2 + 255) / 256, (int64_t)c->sm_count * 16);
-            k_smh_sigkeys<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->aux_len, n_rows, n_bands, n_words, j_sbits, j_keys,
+            k_smh_sigkeys<<<grid, 256, 0, side>>>(c->aux_sorted.as<uint64_t>(), n, c->aux_len, n_rows, n_bands, n_words, j_sbits, j_keys,
                                                j_rank, j_cnt, j_sig);
             CK(cudaGetLastError());
             size_t tmp_bytes = 0;
-            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), s));
-            CKR(c->cub_tmp.ensure(tmp_bytes));
-            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), s));
-            k_smh_scatter<<<(int)std::min<int64_t>((jn_keys + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, s>>>(
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), side));
+            CKR(c->cub_tmp2.ensure(tmp_bytes));      // its own scratch: the main stream may be scanning too
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp2.p, tmp_bytes, j_cnt, j_off, (int)(j_buckets + 1), side));
+            k_smh_scatter<<<(int)std::min<int64_t>((jn_keys + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, side>>>(
                 j_keys, j_rank, j_off, jn_keys, n_bands, j_memb);
             CK(cudaGetLastError());
             st.launches += 3;
+            t_filter.push_back({a0, c->ev_on(side)});
+            CK(cudaEventRecord(c->join_ev, side));
+            CK(cudaStreamWaitEvent(s, c->join_ev, 0));
             DBG_SYNC(c, "smh signature keys + buckets");
-            t_filter.push_back({a0, c->ev()});
         } else if (use_smh) {
-            cudaEvent_t a0 = c->ev();
+            CK(cudaStreamWaitEvent(side, c->fork_ev, 0));
+            cudaEvent_t a0 = c->ev_on(side);
             const size_t sig_bytes = (size_t)n_words * c->npad * 4;
             CKR(c->sigT.ensure(2 * sig_bytes));
             const int grid = (int)std::min<int64_t>(((int64_t)c->npad * n_words * 2 + 255) / 256, (int64_t)c->sm_count * 16);
-            k_smh_signatures<<<grid, 256, 0, s>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
+            k_smh_signatures<<<grid, 256, 0, side>>>(c->aux_sorted.as<uint64_t>(), n, c->npad, c->aux_len, n_rows, n_bands,
                                                   c->sigT.as<uint32_t>(), c->sigT.as<uint32_t>() + (size_t)n_words * c->npad);
             CK(cudaGetLastError());
             st.launches++;
+            t_filter.push_back({a0, c->ev_on(side)});
+            CK(cudaEventRecord(c->join_ev, side));
+            CK(cudaStreamWaitEvent(s, c->join_ev, 0));
             DBG_SYNC(c, "smh signatures");
-            t_filter.push_back({a0, c->ev()});
         }
         if (attempt > 0) {          // the memset at the top of the run covers the first attempt
             CK(cudaMemsetAsync(d_cnt, 0, 32, s));
