@@ -109,11 +109,11 @@ k_tile_filter_hll(const uint32_t* __restrict__ auxT, long long npad, int p_aux, 
 //           turned, in fp32 and without touching shared memory, into a LOWER BOUND of the union estimate
 //           (selb::hll_surely_fails, estimators.cuh).  Both criteria are non-increasing in the estimate, so a pair that
 //           fails at the bound fails; everything else — about one pair in a few hundred — goes to the candidate list.
-//           The bound is also evaluated after half and after three quarters of the registers, with the unread part
+//           The bound is also evaluated after 3/8, 1/2 and 3/4 of the registers, with the unread part
 //           replaced by the smaller of the two genomes' own sums over it (atail, built at load): max(a,b) >= a, so the
 //           union's harmonic sum and zero count over any set of positions are at most either genome's.  A warp step
-//           whose 32 pairs all fail there stops reading; strangers of similar size fail after half of a 1024-register
-//           sketch, so most steps do.
+//           whose 32 pairs all fail there stops reading; strangers of similar size fail at the first checkpoint of a
+//           1024-register sketch, so most steps do.
 //   pass B  k_hll_verify              the candidates, thread per candidate: the same counting into the thread's
 //           shared-memory histogram column, then the Ertl MLE and the criterion exactly as the reference evaluates them
 //           (include/criteria_sketch.hpp:52-64, sketch/include/sketch/hll.h:628-688).  Decisions are the reference's:
@@ -163,16 +163,26 @@ k_aux_planes_quad(const uint8_t* __restrict__ aux, const int32_t* __restrict__ o
     }
 }
 
-// checkpoints of pass A, in word pairs: after half and after three quarters of the sketch (0 = no such checkpoint)
-struct HllCheckpoints { int cp1, cp2, nwp; };
+// checkpoints of pass A, in word pairs (steps of 64 registers): after 1/2 and 3/4 of the sketch, and for sketches of 2048
+// registers and more also after 3/8 (ascending; a checkpoint that does not fall strictly between its neighbours is
+// dropped).  Strangers of similar size are decided at the first one for tau = 0.9, pairs with some overlap at the later
+// ones.  Measured on C5 (filter ms, executed fraction of a full read): p_aux = 12: 3/8 first 21.2 (0.425), 1/2 first 25.7
+// (0.541), 1/4 first 26.9 (0.539); p_aux = 10: 8.07 (0.504) against 8.00 (0.545) — a step stops only when all its 32
+// pairs are decided, and the bound of a short sketch is too loose for that after 3/8; p_aux = 8 (4 steps): a checkpoint
+// after the first step costs more than it stops (5.0 against 4.1).
+constexpr int HLLB_NCP = 3;
+struct HllCheckpoints { int cp[HLLB_NCP]; int n, nwp; };
 __host__ __device__ __forceinline__ HllCheckpoints hll_checkpoints(int p_aux) {
     const int nwp = (1 << p_aux) >> 6;
-    HllCheckpoints c{nwp / 2, (3 * nwp) / 4, nwp};
-    if (c.cp2 <= c.cp1 || c.cp2 >= nwp) c.cp2 = 0;
-    if (c.cp1 <= 0 || c.cp1 >= nwp) c.cp1 = 0;
+    const int want[HLLB_NCP] = {nwp >= 32 ? (3 * nwp) / 8 : 0, nwp / 2, (3 * nwp) / 4};
+    HllCheckpoints c{{0, 0, 0}, 0, nwp};
+    int last = 0;
+    for (int q = 0; q < HLLB_NCP; ++q)
+        if (want[q] > last && want[q] < nwp) { c.cp[c.n++] = want[q]; last = want[q]; }
     return c;
 }
-struct AuxTail { float z1, c1, z2, c2; };     // sum of 2^-r over the non-empty registers / count of empty ones, behind cp1 and cp2
+// per genome: sum of 2^-r over the non-empty registers / count of empty ones, behind each checkpoint
+struct AuxTail { float z[HLLB_NCP], c[HLLB_NCP]; };
 
 // one warp per genome: smallest / largest register value, and the tail sums pass A bounds the unread part with
 // (rounded UP: they stand in for an upper bound)
@@ -184,28 +194,34 @@ k_aux_range(const uint8_t* __restrict__ aux, const int32_t* __restrict__ order, 
     if (g >= n) return;
     const uint8_t* row = aux + ((size_t)order[g] << p_aux);
     const HllCheckpoints cp = hll_checkpoints(p_aux);
-    const int j1 = cp.cp1 * 64, j2 = cp.cp2 * 64;
     int vmin = 255, vmax = 0;
-    double z1 = 0., z2 = 0.;
-    uint32_t c1 = 0, c2 = 0;
+    double z[HLLB_NCP] = {0., 0., 0.};
+    uint32_t cz[HLLB_NCP] = {0, 0, 0};
     for (int j = lane; j < (1 << p_aux); j += 32) {
         const int v = row[j];
         vmin = min(vmin, v); vmax = max(vmax, v);
         const double t = v ? ldexp(1.0, -v) : 0.;
-        if (j >= j1) { z1 += t; c1 += v == 0; }
-        if (j >= j2) { z2 += t; c2 += v == 0; }
+#pragma unroll
+        for (int q = 0; q < HLLB_NCP; ++q)
+            if (q < cp.n && j >= cp.cp[q] * 64) { z[q] += t; cz[q] += v == 0; }
     }
     for (int o = 16; o; o >>= 1) {
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
         vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
-        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+#pragma unroll
+        for (int q = 0; q < HLLB_NCP; ++q) {
+            z[q] += __shfl_xor_sync(0xffffffffu, z[q], o);
+            cz[q] += __shfl_xor_sync(0xffffffffu, cz[q], o);
+        }
     }
     if (lane == 0) {
         agrange[g] = (uint16_t)(min(vmin, vmax) | (vmax << 8));
-        if (atail) atail[g] = AuxTail{(float)z1 * 1.000001f, (float)c1, (float)z2 * 1.000001f, (float)c2};
+        if (atail) {
+            AuxTail t;
+#pragma unroll
+            for (int q = 0; q < HLLB_NCP; ++q) { t.z[q] = (float)z[q] * 1.000001f; t.c[q] = (float)cz[q]; }   // rounded UP: they stand in for an upper bound
+            atail[g] = t;
+        }
     }
 }
 
@@ -552,9 +568,8 @@ k_tile_filter_hll_bound(const uint32_t* __restrict__ auxQ, const uint16_t* __res
                 for (int x = 0; x < HLLB_NV; ++x) { S[x] = 0; C2[x] = 0; }
                 int wp = 0;
 #pragma unroll 1
-                for (int seg = 0; seg < 3; ++seg) {
-                    const int wend = seg == 0 ? cp.cp1 : (seg == 1 ? cp.cp2 : cp.nwp);
-                    if (wend <= wp) continue;
+                for (int seg = 0; seg <= cp.n; ++seg) {
+                    const int wend = seg >= cp.n ? cp.nwp : (seg == 0 ? cp.cp[0] : seg == 1 ? cp.cp[1] : cp.cp[2]);
                     float z, zeros;
                     switch (2 * g0 + t0) {
                         case 0: aux_bound_segment<0, 0>(rq, cq, np32, wp, wend, gmask, S, C2, z, zeros); break;
@@ -570,8 +585,10 @@ k_tile_filter_hll_bound(const uint32_t* __restrict__ auxQ, const uint16_t* __res
                     }
                     steps += (uint32_t)(wend - wp);
                     wp = wend;
-                    if (seg == 0) { z += fminf(ti.z1, tk.z1); zeros += fminf(ti.c1, tk.c1); }
-                    else if (seg == 1) { z += fminf(ti.z2, tk.z2); zeros += fminf(ti.c2, tk.c2); }
+                    if (seg < cp.n) {              // the unread part: at most the smaller of the two genomes' own sums over it
+                        z += seg == 0 ? fminf(ti.z[0], tk.z[0]) : seg == 1 ? fminf(ti.z[1], tk.z[1]) : fminf(ti.z[2], tk.z[2]);
+                        zeros += seg == 0 ? fminf(ti.c[0], tk.c[0]) : seg == 1 ? fminf(ti.c[1], tk.c[1]) : fminf(ti.c[2], tk.c[2]);
+                    }
                     alive = alive && !selb::hll_surely_fails(AN, tau, zs, order_n, m_f, e1, e2, z, zeros);
                     if (!__any_sync(0xffffffffu, alive)) break;
                 }

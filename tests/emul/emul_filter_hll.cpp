@@ -160,7 +160,7 @@ int main(int argc, char** argv) {
     const int nw = (int)(m_aux >> 5);
     std::vector<uint32_t> auxP(planes ? (size_t)6 * nw * npad : 1, 0u);
     std::vector<uint16_t> agrange((size_t)npad, 0);
-    std::vector<AuxTail> atail((size_t)npad, AuxTail{0.f, 0.f, 0.f, 0.f});
+    std::vector<AuxTail> atail((size_t)npad, AuxTail{});
     if (planes) {
         emul::launch(2, 256, [&] { k_aux_planes_quad(aux.data(), order.data(), n, npad, p_aux, auxP.data()); });
         emul::launch((unsigned)(((long long)n * 32 + 255) / 256), 256,

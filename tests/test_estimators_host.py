@@ -165,7 +165,7 @@ def test_hll_bound_never_rejects_a_passing_pair(est, p_aux, tau):
     tau32 = np.float32(tau)
     zs = np.float32(1.96) * np.float32(O.lib().oracle_sigma(p_aux))
     w = np.where(A > 0, np.exp2(-A.astype(np.float64)), 0.0)
-    cuts = sorted({m, m // 2, (3 * m) // 4})
+    cuts = sorted({m, (3 * m) // 8, m // 2, (3 * m) // 4})      # all registers, and the three checkpoints of pass A
     tails = {c: (w[:, c:].sum(1), (A[:, c:] == 0).sum(1)) for c in cuts}
     tested = rejected_full = strangers = strangers_rejected_half = passing = 0
     cl = plan.cluster[order]
