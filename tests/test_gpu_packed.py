@@ -42,9 +42,16 @@ def test_packed_host_load_equals_device_load(gpu, n, odd):
         regs = _odd_rows(regs, 1)
     with S.Selection(gpu) as a, S.Selection(gpu) as b:
         a.load(regs, aux, AUX_SMH)                                       # host rows: packed transport
+        info = a.load_info()
+        assert info["rows_packed"] + info["rows_raw"] == n
+        if odd:                                                          # the piece with seven raw rows went raw as a whole
+            assert info["rows_raw"] >= 1024 and info["rows_packed"] >= 1024
+        else:                                                            # pageable source: no piece goes raw to feed the link
+            assert info["rows_raw"] == 0 and info["h2d_register_bytes"] < 0.53 * regs.size
         regs_d = torch.from_numpy(regs).to(f"cuda:{gpu}")
         aux_d = synth.smh(plan, 128, device=gpu)
         b.load(regs_d, aux_d, AUX_SMH)                                   # device matrix: no transport at all
+        assert b.load_info() == {"h2d_register_bytes": 0, "rows_packed": 0, "rows_raw": 0}
         ca, oa = a.order()
         cb, ob = b.order()
         assert np.array_equal(ca, cb) and np.array_equal(oa, ob)
