@@ -41,10 +41,12 @@ __global__ void __launch_bounds__(128)
 k_estimate_screen(const uint32_t* __restrict__ hist, const uint2* __restrict__ pairs,
                   const unsigned long long* __restrict__ npairs_dev, unsigned long long npairs_cap,
                   const unsigned long long* __restrict__ e, int p, double tau,
-                  uint32_t* __restrict__ surv, unsigned long long* __restrict__ surv_count) {
+                  uint32_t* __restrict__ surv, unsigned long long* __restrict__ surv_count,
+                  const uint32_t* __restrict__ wide_flag = nullptr, uint32_t epoch = 0u) {
     const long long npairs = (long long)min(*npairs_dev, npairs_cap);
     for (long long pi = blockIdx.x * (long long)blockDim.x + threadIdx.x; pi < npairs;
          pi += (long long)gridDim.x * blockDim.x) {
+        if (wide_flag && wide_flag[pi] == epoch) continue;         // a wide pair: its row is being written on the other stream
         const uint2 pr = pairs[pi];
         const unsigned long long nz = hist_row_nonzero(hist + pi * 64);
         const unsigned long long e1 = e[pr.x], e2 = e[pr.y];
@@ -67,12 +69,15 @@ k_estimate_emit(const uint32_t* __restrict__ hist, const uint2* __restrict__ pai
                 uint64_t* __restrict__ out_keys, double* __restrict__ out_j,
                 unsigned long long* __restrict__ out_count, unsigned long long out_cap,
                 uint64_t* __restrict__ near_keys, double* __restrict__ near_j,
-                unsigned long long* __restrict__ near_count, unsigned long long near_cap) {
-    // surv == nullptr: every pair of the list (count_dev = its length); else the pairs k_estimate_screen kept
+                unsigned long long* __restrict__ near_count, unsigned long long near_cap,
+                const uint32_t* __restrict__ wide_flag = nullptr, uint32_t epoch = 0u) {
+    // surv == nullptr: every pair of the list (count_dev = its length); else the listed pairs (what k_estimate_screen
+    // kept, or the wide list).  wide_flag: pairs to leave out (they are estimated from the wide list)
     const long long nsurv = (long long)min(*count_dev, count_cap);
     for (long long si = blockIdx.x * (long long)blockDim.x + threadIdx.x; si < nsurv;
          si += (long long)gridDim.x * blockDim.x) {
         const long long pi = surv ? (long long)surv[si] : si;
+        if (wide_flag && wide_flag[pi] == epoch) continue;
         const uint2 pr = pairs[pi];
         const unsigned long long nz = hist_row_nonzero(hist + pi * 64);
         const unsigned long long e1 = e[pr.x], e2 = e[pr.y];

@@ -198,6 +198,33 @@ k_tile_filter_smh(const uint32_t* __restrict__ sigR, const uint32_t* __restrict_
     }
 }
 
+// buckets of band b of the two genomes equal?  All loads are issued before the first compare (a chain of load, compare,
+// branch per bucket costs a DRAM round trip each: the sketches are not cache-resident)
+__device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, const uint64_t* __restrict__ v2, int b, int n_rows) {
+    const uint64_t* p1 = v1 + (size_t)b * n_rows;
+    const uint64_t* p2 = v2 + (size_t)b * n_rows;
+    if (!(n_rows & 1) && !(((size_t)b * n_rows) & 1)) {            // 16-byte aligned rows of pairs (sketch rows are 8m bytes, m even here)
+        const ulonglong2* q1 = reinterpret_cast<const ulonglong2*>(p1);
+        const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(p2);
+        unsigned long long diff = 0ull;
+        int r = 0;
+        for (; r + 4 <= (n_rows >> 1); r += 4) {
+            const ulonglong2 a0 = __ldg(q1 + r), a1 = __ldg(q1 + r + 1), a2 = __ldg(q1 + r + 2), a3 = __ldg(q1 + r + 3);
+            const ulonglong2 c0 = __ldg(q2 + r), c1 = __ldg(q2 + r + 1), c2 = __ldg(q2 + r + 2), c3 = __ldg(q2 + r + 3);
+            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y) | (a1.x ^ c1.x) | (a1.y ^ c1.y) | (a2.x ^ c2.x) | (a2.y ^ c2.y) | (a3.x ^ c3.x) | (a3.y ^ c3.y);
+            if (diff) return false;
+        }
+        for (; r < (n_rows >> 1); ++r) {
+            const ulonglong2 a0 = __ldg(q1 + r), c0 = __ldg(q2 + r);
+            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y);
+        }
+        return diff == 0ull;
+    }
+    for (int r = 0; r < n_rows; ++r)
+        if (__ldg(p1 + r) != __ldg(p2 + r)) return false;
+    return true;
+}
+
 // exact smh_a on the candidates: include/criteria_sketch.hpp:66-81.  Thread per candidate.
 // A band can only be equal if its 16-bit signatures are, so the thread re-reads the (L2-resident)
 // signature words of both genomes, and compares bucket by bucket only the bands whose signatures
@@ -216,17 +243,20 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
         const uint64_t* v1 = aux_sorted + (size_t)pr.x * m_aux;
         const uint64_t* v2 = aux_sorted + (size_t)pr.y * m_aux;
         bool hit = false;
-        for (int w = 0; w < n_words && !hit; ++w) {
-            const uint32_t x = __ldg(sigR + (size_t)w * npad + pr.x) ^ __ldg(sigR + (size_t)w * npad + pr.y);
+        // signature words four at a time (independent loads), then the bands whose halves agree, exactly
+        for (int w0 = 0; w0 < n_words && !hit; w0 += 4) {
+            uint32_t x[4];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int b = 2 * w + half;
-                if (hit || b >= n_bands || ((x >> (16 * half)) & 0xffffu) != 0) continue;
-                bool eq = true;
-                for (int r = 0; r < n_rows; ++r)
-                    if (__ldg(v1 + (size_t)b * n_rows + r) != __ldg(v2 + (size_t)b * n_rows + r)) { eq = false; break; }
-                hit = eq;
-            }
+            for (int u = 0; u < 4; ++u)
+                x[u] = w0 + u < n_words ? (__ldg(sigR + (size_t)(w0 + u) * npad + pr.x) ^ __ldg(sigR + (size_t)(w0 + u) * npad + pr.y)) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int b = 2 * (w0 + u) + half;
+                    if (hit || b >= n_bands || ((x[u] >> (16 * half)) & 0xffffu) != 0) continue;
+                    hit = smh_band_equal(v1, v2, b, n_rows);
+                }
         }
         if (hit) {
             const unsigned long long slot = warp_claim(pair_count);
@@ -291,33 +321,6 @@ k_smh_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ra
               long long n_keys, int n_bands, uint32_t* __restrict__ members) {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_keys; e += (long long)gridDim.x * blockDim.x)
         members[bucket_off[keys[e]] + rank[e]] = (uint32_t)(e / n_bands);
-}
-
-// buckets of band b of the two genomes equal?  All loads are issued before the first compare (a chain of load, compare,
-// branch per bucket costs a DRAM round trip each: the sketches are not cache-resident)
-__device__ __forceinline__ bool smh_band_equal(const uint64_t* __restrict__ v1, const uint64_t* __restrict__ v2, int b, int n_rows) {
-    const uint64_t* p1 = v1 + (size_t)b * n_rows;
-    const uint64_t* p2 = v2 + (size_t)b * n_rows;
-    if (!(n_rows & 1) && !(((size_t)b * n_rows) & 1)) {            // 16-byte aligned rows of pairs (sketch rows are 8m bytes, m even here)
-        const ulonglong2* q1 = reinterpret_cast<const ulonglong2*>(p1);
-        const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(p2);
-        unsigned long long diff = 0ull;
-        int r = 0;
-        for (; r + 4 <= (n_rows >> 1); r += 4) {
-            const ulonglong2 a0 = __ldg(q1 + r), a1 = __ldg(q1 + r + 1), a2 = __ldg(q1 + r + 2), a3 = __ldg(q1 + r + 3);
-            const ulonglong2 c0 = __ldg(q2 + r), c1 = __ldg(q2 + r + 1), c2 = __ldg(q2 + r + 2), c3 = __ldg(q2 + r + 3);
-            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y) | (a1.x ^ c1.x) | (a1.y ^ c1.y) | (a2.x ^ c2.x) | (a2.y ^ c2.y) | (a3.x ^ c3.x) | (a3.y ^ c3.y);
-            if (diff) return false;
-        }
-        for (; r < (n_rows >> 1); ++r) {
-            const ulonglong2 a0 = __ldg(q1 + r), c0 = __ldg(q2 + r);
-            diff |= (a0.x ^ c0.x) | (a0.y ^ c0.y);
-        }
-        return diff == 0ull;
-    }
-    for (int r = 0; r < n_rows; ++r)
-        if (__ldg(p1 + r) != __ldg(p2 + r)) return false;
-    return true;
 }
 
 // element e = (genome i, band b) in [e0, e1): the members k of its bucket with i < k <= hi(i) become ITEMS {i, k, band}.  A warp

@@ -284,7 +284,9 @@ template <class Epi>
 __global__ void __launch_bounds__(32, PL_MIN_CTAS)
 k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
                    SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
-                   unsigned long long* __restrict__ batch_counter) {
+                   unsigned long long* __restrict__ batch_counter, uint32_t* __restrict__ wide_flag = nullptr, uint32_t epoch = 0u) {
+    // wide_flag (optional): wide_flag[pair] = epoch for every pair handed to the wide list, so that the estimate kernel of
+    // the plane pairs can leave those rows to the byte kernel + estimate that run beside it on another stream
     constexpr int FORM = union_form<Epi>::value;
 #ifndef SELB_EMUL   // the emulator's dynamic shared memory is a global array of this name
     extern __shared__ __align__(128) uint8_t pl_smem[];
@@ -328,6 +330,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             const int g0 = min(lo >> 3, 4);
             if ((hi >> 3) > g0 + 3) {        // value range wider than the window: the byte kernel does this pair
                 wide_list[atomicAdd(wide_count, 1ull)] = (uint32_t)pi;
+                if (wide_flag) wide_flag[pi] = epoch;
                 ok = false;
             } else {
                 uint32_t gmask = 0;

@@ -243,7 +243,8 @@ struct selb200_ctx {
     DevBuf row_cnt, row_off, sort_tmp, sort_blocksum;
     DevBuf auxP, agrange, atail;         // bit planes (quad layout) / register ranges / tail sums of the auxiliary HLLs (sorted order)
     bool auxp_quad = false;              // auxP holds the planes of the loaded auxiliary HLLs (k_aux_planes_quad)
-    DevBuf planes, grange, wide_list;    // bit-plane copy of the primary registers (file-list order)
+    DevBuf planes, grange, wide_list, wide_flag;    // bit-plane copy of the primary registers (file-list order)
+    uint32_t wide_epoch = 0;             // stamp of the current union pass in wide_flag
     int chunk_regs = 0;
     // counting step of the plane kernel: subset masks on groups of four values (k_pair_hist_planes<EpiSubsets<..>>,
     // default) or one-hot masks on groups of eight (SELB200_UNION=planes)
@@ -352,12 +353,28 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
 }
 
 // bit-plane union pass over the run's pair list (+ the byte kernel on whatever landed in the wide list)
+// The plane kernel on the run stream; the byte kernel for the pairs it hands to the wide list on `wide_stream` (behind an
+// event of the plane kernel).  With another stream than the run stream the caller estimates the wide pairs there too and
+// joins afterwards: a wide pair costs the byte kernel 20 us whatever their number, which then overlaps the estimate of
+// everything else; the plane kernel stamps wide_flag[pair] = c->wide_epoch so that the main estimate leaves those rows alone.
 int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pairs, uint32_t* hist_out,
                             const unsigned long long* npairs_dev, unsigned long long* wide_count, int* launches,
-                            bool counters_are_zero) {
+                            bool counters_are_zero, cudaStream_t wide_stream = nullptr) {
     if (max_pairs <= 0) return SELB200_OK;
     cudaStream_t s = c->stream;
+    if (!wide_stream) wide_stream = s;
     CKR(c->wide_list.ensure((size_t)max_pairs * 4));
+    {
+        const void* had = c->wide_flag.p;
+        CKR(c->wide_flag.ensure((size_t)max_pairs * 4));
+        if (c->wide_flag.p != had) {              // fresh memory: no stamp of an epoch to come
+            CK(cudaMemsetAsync(c->wide_flag.p, 0, c->wide_flag.cap, s));
+            c->wide_epoch = 0;
+        }
+        ++c->wide_epoch;
+    }
+    uint32_t* wflag = c->wide_flag.as<uint32_t>();
+    const uint32_t wepoch = c->wide_epoch;
     SrcPairs src{pairs, c->order_dev.as<int32_t>(), (long long)max_pairs, npairs_dev};
     EpiWriteHist epi{hist_out};
     const size_t smem = (size_t)PL_STAGES * 2 * 6 * (c->chunk_regs >> 3) + 8 * PL_STAGES;
@@ -397,16 +414,20 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
         k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
                                                                c->grange.as<uint16_t>(), src, epi,
-                                                               c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+                                                               c->wide_list.as<uint32_t>(), wide_count, wide_count + 1, wflag, wepoch);
     }
     CK(cudaGetLastError());
+    if (wide_stream != s) {
+        CK(cudaEventRecord(c->fork_ev, s));
+        CK(cudaStreamWaitEvent(wide_stream, c->fork_ev, 0));
+    }
     // pairs whose value range exceeds the 32-value window: byte kernel, small persistent grid
     SrcWide wsrc{pairs, c->order_dev.as<int32_t>(), c->wide_list.as<uint32_t>(), wide_count};
     if (c->m >= 512) {
         const int nbins = 64 - c->p + 2;
         const int wgrid = (int)std::min<int64_t>((max_pairs + 1) / 2, (int64_t)c->sm_count * 2);
-        if (nbins <= 52) k_pair_hist<52, SrcWide, EpiWriteHist><<<wgrid, 64, 0, s>>>(c->d_regs, c->m, c->m, wsrc, epi);
-        else k_pair_hist<64, SrcWide, EpiWriteHist><<<wgrid, 64, 0, s>>>(c->d_regs, c->m, c->m, wsrc, epi);
+        if (nbins <= 52) k_pair_hist<52, SrcWide, EpiWriteHist><<<wgrid, 64, 0, wide_stream>>>(c->d_regs, c->m, c->m, wsrc, epi);
+        else k_pair_hist<64, SrcWide, EpiWriteHist><<<wgrid, 64, 0, wide_stream>>>(c->d_regs, c->m, c->m, wsrc, epi);
         CK(cudaGetLastError());
     }
     if (launches) *launches += 2;
@@ -896,7 +917,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->cub_tmp2, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->wide_list, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->wide_list, &c->wide_flag, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);
@@ -1477,6 +1498,7 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             DBG_SYNC(c, "smh verify");
             // ---- K5 + K6 --------------------------------------------------------------
             cudaEvent_t u0 = c->ev();
+            bool wide_on_side = false;
             if ((crit == SELB200_CRIT_SMH_A && !smh_join) || hll_twopass) t_verify.push_back({f1, u0});
             if (union_bytes) {
                 CKR(launch_pair_hist(c, c->d_regs, c->m, c->p, c->order_dev.as<int32_t>(), c->pairs.as<uint2>(),
@@ -1484,7 +1506,17 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 st.launches++;
             } else {
                 CKR(launch_pair_hist_planes(c, c->pairs.as<uint2>(), (int64_t)pair_lim, c->hist.as<uint32_t>(),
-                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches, attempt == 0 && ri == 0));
+                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches, attempt == 0 && ri == 0, side));
+                // the wide pairs' estimate follows their histograms on the side stream
+                k_estimate_emit<<<c->sm_count, 128, 0, side>>>(
+                    c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->wide_list.as<uint32_t>(), d_cnt + M_WIDE, pair_lim,
+                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
+                    d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                    d_cnt + M_NEAR, near_cap);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(c->join_ev, side));
+                st.launches++;
+                wide_on_side = true;
             }
             DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
@@ -1493,7 +1525,8 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 if (attempt > 0 || ri > 0) CK(cudaMemsetAsync(d_cnt + M_SURV, 0, 8, s));
                 k_estimate_screen<<<c->sm_count * 8, 128, 0, s>>>(
                     c->hist.as<uint32_t>(), c->pairs.as<uint2>(), d_cnt + M_PAIRS, pair_lim,
-                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->cand.as<uint32_t>(), d_cnt + M_SURV);
+                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->cand.as<uint32_t>(), d_cnt + M_SURV,
+                    wide_on_side ? c->wide_flag.as<uint32_t>() : nullptr, c->wide_epoch);
                 CK(cudaGetLastError());
                 k_estimate_emit<<<c->sm_count * 4, 128, 0, s>>>(
                     c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->cand.as<uint32_t>(), d_cnt + M_SURV, pair_lim,
@@ -1507,10 +1540,11 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                     c->hist.as<uint32_t>(), c->pairs.as<uint2>(), nullptr, d_cnt + M_PAIRS, pair_lim,
                     c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
                     d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
-                    d_cnt + M_NEAR, near_cap);
+                    d_cnt + M_NEAR, near_cap, wide_on_side ? c->wide_flag.as<uint32_t>() : nullptr, c->wide_epoch);
                 CK(cudaGetLastError());
                 st.launches++;
             }
+            if (wide_on_side) CK(cudaStreamWaitEvent(s, c->join_ev, 0));     // the wide pairs' results are in the lists too
             DBG_SYNC(c, "estimate + emit");
             cudaEvent_t u2 = c->ev();
             t_union.push_back({u0, u1});

@@ -184,6 +184,13 @@ int main(int argc, char** argv) {
     const long long np = (long long)meta[M_PAIRS];
     // K5: plane union over the pair list (rows through `order`), wide pairs through the byte kernel
     std::vector<uint32_t> hist((size_t)std::max<long long>(np, 1) * 64, 0xDEADBEEFu), wide((size_t)std::max<long long>(np, 1));
+    // the plane kernel stamps the pairs it hands to the wide list; the library runs the byte kernel and the estimate of
+    // those pairs on a second stream, next to the estimate of everything else, which skips stamped pairs.  Here: the main
+    // estimate FIRST, while the wide pairs' rows still hold poison, then the byte kernel, then the wide pairs' estimate
+    std::vector<uint32_t> wflag((size_t)std::max<long long>(np, 1), 6u);      // stamps of an older pass
+    const uint32_t wepoch = 7u;
+    SrcWide wsrc{pairs.data(), order.data(), wide.data(), meta.data() + M_WIDE};
+    EpiWriteHist epi_w{hist.data()};
     {
         SrcPairs src{pairs.data(), order.data(), (long long)cap, meta.data() + M_PAIRS};
         EpiWriteHist epi{hist.data()};
@@ -191,13 +198,11 @@ int main(int argc, char** argv) {
         emul::launch(3, 32, [&] {
             if (subsets)
                 k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                             wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH);
+                                                             wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH, wflag.data(), wepoch);
             else
                 k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide.data(), meta.data() + M_WIDE,
-                                                 meta.data() + M_BATCH);
+                                                 meta.data() + M_BATCH, wflag.data(), wepoch);
         });
-        SrcWide wsrc{pairs.data(), order.data(), wide.data(), meta.data() + M_WIDE};
-        emul::launch(2, 64, [&] { k_pair_hist<52, SrcWide, EpiWriteHist>(regs.data(), m, m, wsrc, epi); });
     }
     if (meta[M_KERR]) { fprintf(stderr, "union kernel error word %llx\n", meta[M_KERR]); return 5; }
     lap("union");
@@ -210,7 +215,8 @@ int main(int argc, char** argv) {
     if (argc > 5 && std::string(argv[5]) == "screen") {
         std::vector<uint32_t> surv((size_t)cap, 0xDEADBEEFu);
         emul::launch(3, 128, [&] {
-            k_estimate_screen(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, surv.data(), meta.data() + M_SURV);
+            k_estimate_screen(hist.data(), pairs.data(), meta.data() + M_PAIRS, cap, e.data(), p, tau, surv.data(), meta.data() + M_SURV,
+                              wflag.data(), wepoch);
         });
         emul::launch(2, 128, [&] {
             k_estimate_emit(hist.data(), pairs.data(), surv.data(), meta.data() + M_SURV, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
@@ -223,9 +229,15 @@ int main(int argc, char** argv) {
     } else {
         emul::launch(3, 128, [&] {
             k_estimate_emit(hist.data(), pairs.data(), nullptr, meta.data() + M_PAIRS, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
-                            meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
+                            meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap, wflag.data(), wepoch);
         });
     }
+    // the wide pairs: byte kernel, then their estimate from the wide list
+    emul::launch(2, 64, [&] { k_pair_hist<52, SrcWide, EpiWriteHist>(regs.data(), m, m, wsrc, epi_w); });
+    emul::launch(1, 128, [&] {
+        k_estimate_emit(hist.data(), pairs.data(), wide.data(), meta.data() + M_WIDE, cap, e.data(), p, tau, out_keys.data(), out_j.data(),
+                        meta.data() + M_OUT, out_cap, near_keys.data(), near_j.data(), meta.data() + M_NEAR, near_cap);
+    });
     lap("estimate");
     const long long cnt = (long long)meta[M_OUT];
     // K7: sparse-output print order
