@@ -409,7 +409,7 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * u_per_sm);
         k_pair_hist_planes<EpiSubsets<EpiWriteHist>><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
                                                                        c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1);
+                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1, wflag, wepoch);
     } else {
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
         k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
