@@ -288,6 +288,29 @@ class ReferenceLeg:
             self.lines = O.format_lines(file_names(self.cfg.n), res)
         return wall, wall
 
+    def cli_pass(self, runs=2):
+        """The process-level drop-in: this repo's own `selection` binary on the SAME gz files and flags
+        as the reference binary, whole process timed (CUDA start-up, gunzip, upload, compare, print), stdout held
+        against the reference's byte for byte.  Outside every timed region of the metric; reported as `cli`."""
+        exe = os.path.join(ROOT, "cuda_selection_criteria_b200", "bin", "selection")
+        if not (self.have_ref and os.path.exists(exe) and self.lines is not None):
+            return None
+        cmd = [exe] + ref_cmd(self.cfg, self.cores, self.cfg.tau)[1:]
+        walls, out, err = [], b"", None
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, cwd=self.td, capture_output=True)
+            walls.append(round(time.perf_counter() - t0, 3))
+            if r.returncode != 0:
+                err = f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-200:]
+                break
+            out = r.stdout
+        got = out.decode().splitlines()
+        return {"cmd": "cuda_selection_criteria_b200/bin/selection " + " ".join(cmd[1:]), "wall_s": walls,
+                "reference_cmd": "oracle/_ref/selection " + " ".join(cmd[1:]), "lines": len(got),
+                "stdout_identical_to_reference": err is None and got == self.lines, "stdout_sha256_16": lines_sha(got)[:16],
+                "error": err}
+
     def drop_files(self):
         shutil.rmtree(self.td, ignore_errors=True)
 
@@ -520,6 +543,7 @@ def main():
     # ---- reference leg first (rank 0 at N=1 only), before this process touches CUDA: the file writers fork -------
     cb = None
     ref_lines = None
+    cli = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         leg = ReferenceLeg(cfg)
         try:
@@ -527,6 +551,9 @@ def main():
             c, w = leg.one_pass()
             cb = leg.baseline([c], [w])
             ref_lines = leg.lines
+            cli = leg.cli_pass()
+            if cli is not None:
+                cli["reference_wall_s"] = round(w, 3)
         finally:
             leg.drop_files()
         del leg
@@ -839,7 +866,7 @@ def main():
                            "bands_x_rows": [st0["n_bands"], st0["n_rows"]]},
                 "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(sum(s["launches"] for s in stats_acc)),
-                "roofline": roofline, "kernels": kernels, "parity": parity, "cpu_baseline": cb, "configs": configs}
+                "roofline": roofline, "kernels": kernels, "parity": parity, "cpu_baseline": cb, "cli": cli, "configs": configs}
         print(json.dumps(line), file=real_stdout, flush=True)
     if configs is None:
         sel.close()
