@@ -33,7 +33,9 @@ constexpr int PL_NQ = PL_CHUNK_REGS / 64;   // uint2 per plane of a full chunk
 
 __global__ void __launch_bounds__(256)
 k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, int chunk_regs,
-                    uint32_t* __restrict__ planes) {
+                    uint32_t* __restrict__ planes, uint32_t* __restrict__ gtop = nullptr) {
+    // gtop (optional, zeroed by the caller, m >= 4096): gtop[8 g + j] = largest register of the j-th eighth of genome g —
+    // the union kernel stops counting a 2048-register step at the group its eighths reach (see k_pair_hist_planes)
     const int lane = threadIdx.x & 31;
     const long long nblk = rows * (long long)(m >> 9);          // 512-register blocks
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -44,6 +46,15 @@ k_planes_from_bytes(const uint8_t* __restrict__ regs, long long rows, size_t m, 
         const long long g = blk / blk_per_genome;
         const int bg = (int)(blk - g * blk_per_genome);
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(regs + (size_t)g * m + (size_t)bg * 512) + lane);
+        if (gtop) {
+            uint32_t mx = 0;
+#pragma unroll
+            for (int sh = 0; sh < 32; sh += 8)
+                mx = max(max(mx, (v.x >> sh) & 0xffu), max(max((v.y >> sh) & 0xffu, (v.z >> sh) & 0xffu), (v.w >> sh) & 0xffu));
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) atomicMax(gtop + g * 8 + (long long)bg * 8 / blk_per_genome, mx);
+        }
         const int chunk = bg / blk_per_chunk, bc = bg - chunk * blk_per_chunk;
         uint32_t* dst = planes + (size_t)g * 6 * (m >> 5) + (size_t)chunk * chunk_words + (size_t)bc * 16;
 #pragma unroll
@@ -104,6 +115,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 #endif
 #ifndef PL_UNROLL
 #define PL_UNROLL 1      // measured 1.546 against 1.566 ms (n = 100k, 511 521 pairs); packing the carry counters: no change
+#endif
+//   PL_DIRECT    (subset form) 4-bit mask over the four subset masks of a group: a mask with its bit set is counted with two
+//                POPC and one three-input add instead of a carry-save step (2 LOP3 + POPC + add).  The carry-save form
+//                loads the ALU pipe (LOP3, 16 lanes / clk / scheduler), POPC the XU pipe (4 lanes): with one mask of four
+//                counted directly the two pipes carry about the same time per step, and the mask's state register goes
+//   PL_BFLY16    epilogue butterfly on 16 words holding two 16-bit totals each (16 shuffles instead of 31); totals of
+//                sixteen lanes stay below 2^16 while m <= 2^16, larger sketches take the 32-word butterfly
+// measured (n = 100k, 511 521 pairs, same box): neither 1.533 ms, PL_DIRECT=1 1.490, PL_BFLY16 1.531, both 1.475 (kept);
+// PL_DIRECT=9 (two masks of four counted directly) 1.570: the XU pipe becomes the limit
+#ifndef PL_DIRECT
+#define PL_DIRECT 1
+#endif
+#ifndef PL_BFLY16
+#define PL_BFLY16 1
 #endif
 constexpr int PL_NC2 = PL_PACK_C2 ? 16 : 32;
 __device__ __forceinline__ void c2_add(uint32_t (&C2)[PL_NC2], int v, uint32_t cnt) {
@@ -197,9 +222,12 @@ __device__ __forceinline__ void plane_chunk(const uint2* __restrict__ sA, const 
 // closely (a range 6..25 counts 24 bins instead of 32): per 32 registers and a range of 20 values
 // 12 (max) + 4 + 6*4 (form) + 24 (absorb) = 64 LOP3 and 12 POPC instead of 88 and 16.
 // gmask: bit t = the group of values 8*G0 + 4t .. 8*G0 + 4t + 3 lies inside the pair's range (warp-uniform).
+// tops: three bits per eighth of the sketch, the last group of four (relative to the window) that the eighth's registers of
+// either genome reach; step s of this chunk lies in eighth (step0 + s) >> tsh and counts the groups of gmask_all up to there
 template <int G0, int NQ>
 __device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA, const uint2* __restrict__ sB, int nq_rt,
-                                                    int lane, uint32_t gmask, uint32_t (&S)[32], uint32_t (&C2)[PL_NC2]) {
+                                                    int lane, uint32_t gmask_all, uint32_t (&S)[32], uint32_t (&C2)[PL_NC2],
+                                                    uint32_t tops = 0x00ffffffu, int step0 = 0, int tsh = 0) {
     const int nq = NQ > 0 ? NQ : nq_rt;
     constexpr int NP = (G0 == 0) ? 5 : 6;
 #if PL_UNROLL
@@ -208,6 +236,7 @@ __device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA
 #pragma unroll 1
 #endif
     for (int q = lane; q < nq; q += 32) {
+        const uint32_t gmask = gmask_all & ((2u << ((tops >> (3 * ((step0 + (q >> 5)) >> tsh))) & 7u)) - 1u);
         uint32_t M[2][6];
         {
             uint2 a[NP], b[NP];
@@ -237,9 +266,13 @@ __device__ __forceinline__ void plane_chunk_subsets(const uint2* __restrict__ sA
             m0[3] = lop3<0x80>(e0, M[0][0], M[0][1]);                                                     \
             m1[0] = e1; m1[1] = lop3<0xC0>(e1, M[1][0], 0u); m1[2] = lop3<0xC0>(e1, M[1][1], 0u);         \
             m1[3] = lop3<0x80>(e1, M[1][0], M[1][1]);                                                     \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);    \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]); \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) c2_add(C2, c0 + j, (uint32_t)__popc(kk[j]));    \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j)                                                 \
+                if (!((PL_DIRECT >> j) & 1)) kk[j] = lop3<0xE8>(S[c0 + j], m0[j], m1[j]);                 \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j)                                                 \
+                if (!((PL_DIRECT >> j) & 1)) S[c0 + j] = lop3<0x96>(S[c0 + j], m0[j], m1[j]);             \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j)                                                 \
+                c2_add(C2, c0 + j, ((PL_DIRECT >> j) & 1) ? (uint32_t)(__popc(m0[j]) + __popc(m1[j]))     \
+                                                          : (uint32_t)__popc(kk[j]));                     \
         }
 #define SELB_SUBSET_GROUP8(T8)                                                                            \
         if (gmask & (3u << (2 * T8))) {                                                                   \
@@ -284,7 +317,12 @@ template <class Epi>
 __global__ void __launch_bounds__(32, PL_MIN_CTAS)
 k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs, const uint16_t* __restrict__ grange,
                    SrcPairs src, Epi epi, uint32_t* __restrict__ wide_list, unsigned long long* __restrict__ wide_count,
-                   unsigned long long* __restrict__ batch_counter, uint32_t* __restrict__ wide_flag = nullptr, uint32_t epoch = 0u) {
+                   unsigned long long* __restrict__ batch_counter, uint32_t* __restrict__ wide_flag = nullptr, uint32_t epoch = 0u,
+                   const uint32_t* __restrict__ gtop = nullptr) {
+    // gtop (optional, subset form, m >= 16384 so that an eighth is one or more whole 2048-register steps): the per-eighth
+    // maxima written by k_planes_from_bytes.  High values are rare — 2048 registers seldom reach the top of the range of all
+    // 2^p — so a step counts the groups up to the larger of the two genomes' maxima over its eighth instead of up to the
+    // pair's maximum (C4: 5.4 -> 4.8 groups of four per step); every register of the step lies at or below that group
     // wide_flag (optional): wide_flag[pair] = epoch for every pair handed to the wide list, so that the estimate kernel of
     // the plane pairs can leave those rows to the byte kernel + estimate that run beside it on another stream
     constexpr int FORM = union_form<Epi>::value;
@@ -310,6 +348,9 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
 
     // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
     uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
+    uint32_t d_tp0 = 0x00ffffffu, d_tp1 = 0x00ffffffu;      // per-eighth top groups of the lane's pair (gtop)
+    int tsh = 0;                                            // 2048-register steps per eighth = 1 << tsh
+    while (((size_t)16384 << tsh) < m) ++tsh;
     uint32_t mask0 = 0, mask1 = 0;          // lanes of the set holding a pair to do (warp-uniform)
     long long base0 = 0, base1 = 0;         // first pair index of the batch
     bool end0 = false, end1 = false;        // the batch starts past the end of the list: nothing follows
@@ -322,7 +363,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         const long long pi = bidx * bsz + lane;
         bool ok = lane < bsz && pi < npairs;
         uint2 id = make_uint2(0u, 0u), rw = id;
-        uint32_t gm = 0;
+        uint32_t gm = 0, tp = 0x00ffffffu;
         if (ok) {
             rw = src.rows(pi, id);
             const uint32_t ra = grange[rw.x], rb = grange[rw.y];
@@ -342,11 +383,22 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
                         if ((2 * g0 + t) >= (lo >> 2) && (2 * g0 + t) <= (hi >> 2)) gmask |= 1u << t;
                 }
                 gm = (uint32_t)g0 | (gmask << 8);
+                if (FORM == 1 && gtop) {
+                    const uint4* ta = reinterpret_cast<const uint4*>(gtop + (size_t)rw.x * 8);
+                    const uint4* tb = reinterpret_cast<const uint4*>(gtop + (size_t)rw.y * 8);
+                    const uint4 a0 = ta[0], a1 = ta[1], b0 = tb[0], b1 = tb[1];
+                    const uint32_t top[8] = {max(a0.x, b0.x), max(a0.y, b0.y), max(a0.z, b0.z), max(a0.w, b0.w),
+                                             max(a1.x, b1.x), max(a1.y, b1.y), max(a1.z, b1.z), max(a1.w, b1.w)};
+                    tp = 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)      // lo <= top[j] <= hi: the group index lies in 0 .. 7
+                        tp |= (uint32_t)min(max((int)(top[j] >> 2) - 2 * g0, 0), 7) << (3 * j);
+                }
             }
         }
         const uint32_t msk = __ballot_sync(FULL, ok);
-        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; mask1 = msk; base1 = bidx * bsz; end1 = bidx * bsz >= npairs; }
-        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; mask0 = msk; base0 = bidx * bsz; end0 = bidx * bsz >= npairs; }
+        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; d_tp1 = tp; mask1 = msk; base1 = bidx * bsz; end1 = bidx * bsz >= npairs; }
+        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; d_tp0 = tp; mask0 = msk; base0 = bidx * bsz; end0 = bidx * bsz >= npairs; }
         filled = k;
     };
 
@@ -355,7 +407,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         uint32_t mask;         // pairs of the batch not started yet
         bool valid, done;
         int ch;
-        uint32_t rx, ry, ix, iy, gm;
+        uint32_t rx, ry, ix, iy, gm, tp;
         long long pi;
         const uint8_t* ga;     // planes of the two genomes (producer side)
         const uint8_t* gb;
@@ -381,6 +433,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
                 c.ix = __shfl_sync(FULL, odd ? d_ix1 : d_ix0, j);
                 c.iy = __shfl_sync(FULL, odd ? d_iy1 : d_iy0, j);
                 c.gm = __shfl_sync(FULL, odd ? d_gm1 : d_gm0, j);
+                if (FORM == 1 && is_cons) c.tp = __shfl_sync(FULL, odd ? d_tp1 : d_tp0, j);
                 c.pi = (odd ? base1 : base0) + j;
                 if (!is_cons) {
                     c.ga = reinterpret_cast<const uint8_t*>(planes) + (size_t)c.rx * genome_bytes;
@@ -413,7 +466,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     fill(0);
     if (!end0) fill(1);
     cons.k = 0; cons.mask = mask0; cons.valid = false; cons.done = false; cons.ch = 0;
-    cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.pi = 0;
+    cons.rx = cons.ry = cons.ix = cons.iy = cons.gm = 0; cons.tp = 0x00ffffffu; cons.pi = 0;
     cons.ga = cons.gb = nullptr;
     prod = cons;
     next_pair(cons, true);
@@ -456,11 +509,11 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         if (FORM == 1) {
             if (nq == PL_NQ) {
                 switch (g0) {
-                    case 0: plane_chunk_subsets<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                    case 1: plane_chunk_subsets<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                    case 2: plane_chunk_subsets<2, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                    case 3: plane_chunk_subsets<3, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
-                    default: plane_chunk_subsets<4, PL_NQ>(pa, pb, nq, lane, gmask, S, C2); break;
+                    case 0: plane_chunk_subsets<0, PL_NQ>(pa, pb, nq, lane, gmask, S, C2, cons.tp, cons.ch * (PL_NQ / 32), tsh); break;
+                    case 1: plane_chunk_subsets<1, PL_NQ>(pa, pb, nq, lane, gmask, S, C2, cons.tp, cons.ch * (PL_NQ / 32), tsh); break;
+                    case 2: plane_chunk_subsets<2, PL_NQ>(pa, pb, nq, lane, gmask, S, C2, cons.tp, cons.ch * (PL_NQ / 32), tsh); break;
+                    case 3: plane_chunk_subsets<3, PL_NQ>(pa, pb, nq, lane, gmask, S, C2, cons.tp, cons.ch * (PL_NQ / 32), tsh); break;
+                    default: plane_chunk_subsets<4, PL_NQ>(pa, pb, nq, lane, gmask, S, C2, cons.tp, cons.ch * (PL_NQ / 32), tsh); break;
                 }
             } else {
                 switch (g0) {
@@ -492,17 +545,41 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             // per-lane totals, then a transposing butterfly: lane L ends with the warp total of value 8*g0 + L
             uint32_t x[32];
 #pragma unroll
-            for (int v = 0; v < 32; ++v) { x[v] = 2u * c2_get(C2, v) + (uint32_t)__popc(S[v]); S[v] = 0; }
+            for (int v = 0; v < 32; ++v) {
+                // a directly counted subset mask (PL_DIRECT, subset form) has no carry-save state: C2 holds its count
+                if (FORM == 1 && ((PL_DIRECT >> (v & 3)) & 1)) x[v] = c2_get(C2, v);
+                else x[v] = 2u * c2_get(C2, v) + (uint32_t)__popc(S[v]);
+                S[v] = 0;
+            }
 #pragma unroll
             for (int v = 0; v < PL_NC2; ++v) C2[v] = 0;
+            if (PL_BFLY16 && m <= 65536) {
+                // two totals per word (value v in the low half, v + 16 in the high half: a lane sees m/32 registers, sixteen
+                // lanes m/2 <= 2^15), four butterfly stages over the lane's low bits, then the halves part over bit 4
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-                const bool upper = (lane & o) != 0;
+                for (int i = 0; i < 16; ++i) x[i] += x[i + 16] << 16;
 #pragma unroll
-                for (int i = 0; i < o; ++i) {
-                    const uint32_t send = upper ? x[i] : x[i + o];
-                    const uint32_t keep = upper ? x[i + o] : x[i];
-                    x[i] = keep + __shfl_xor_sync(FULL, send, o);
+                for (int o = 8; o >= 1; o >>= 1) {
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < o; ++i) {
+                        const uint32_t send = upper ? x[i] : x[i + o];
+                        const uint32_t keep = upper ? x[i + o] : x[i];
+                        x[i] = keep + __shfl_xor_sync(FULL, send, o);
+                    }
+                }
+                const uint32_t other = __shfl_xor_sync(FULL, x[0], 16);
+                x[0] = (lane & 16) ? (x[0] >> 16) + (other >> 16) : (x[0] & 0xffffu) + (other & 0xffffu);
+            } else {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < o; ++i) {
+                        const uint32_t send = upper ? x[i] : x[i + o];
+                        const uint32_t keep = upper ? x[i + o] : x[i];
+                        x[i] = keep + __shfl_xor_sync(FULL, send, o);
+                    }
                 }
             }
             if (FORM == 1) {

@@ -243,12 +243,13 @@ struct selb200_ctx {
     DevBuf row_cnt, row_off, sort_tmp, sort_blocksum;
     DevBuf auxP, agrange, atail;         // bit planes (quad layout) / register ranges / tail sums of the auxiliary HLLs (sorted order)
     bool auxp_quad = false;              // auxP holds the planes of the loaded auxiliary HLLs (k_aux_planes_quad)
-    DevBuf planes, grange, wide_list, wide_flag;    // bit-plane copy of the primary registers (file-list order)
+    DevBuf planes, grange, gtop, wide_list, wide_flag;    // bit-plane copy of the primary registers (file-list order)
     uint32_t wide_epoch = 0;             // stamp of the current union pass in wide_flag
     int chunk_regs = 0;
     // counting step of the plane kernel: subset masks on groups of four values (k_pair_hist_planes<EpiSubsets<..>>,
     // default) or one-hot masks on groups of eight (SELB200_UNION=planes)
     bool union_subsets = true;
+    bool union_tops = true;              // per-step group limit from the per-eighth maxima (SELB200_UNION_TOPS=0: the pair's range)
     void* h_res = nullptr;               // pinned host copy of the result lists (params.host_results)
     size_t h_res_cap = 0;                // in pairs: keys at [0, cap), Jaccards at [cap, 2 cap)
     int64_t host_count = -1;
@@ -409,7 +410,8 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * u_per_sm);
         k_pair_hist_planes<EpiSubsets<EpiWriteHist>><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
                                                                        c->grange.as<uint16_t>(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1, wflag, wepoch);
+                                                                       c->wide_list.as<uint32_t>(), wide_count, wide_count + 1, wflag, wepoch,
+                                                                       c->union_tops && c->m >= 16384 ? c->gtop.as<uint32_t>() : nullptr);
     } else {
         const int grid = (int)std::min<int64_t>((max_pairs + 3) / 4, (int64_t)c->sm_count * per_sm);
         k_pair_hist_planes<EpiWriteHist><<<grid, 32, smem, s>>>(c->planes.as<uint32_t>(), c->m, c->chunk_regs,
@@ -490,6 +492,7 @@ int load_begin(selb200_ctx* c, int64_t n, int p, int aux_kind, int aux_len, cons
     c->chunk_regs = (int)std::min<size_t>(c->m, (size_t)PL_CHUNK_REGS);
     CKR(c->planes.ensure((size_t)n * 6 * (c->m >> 3)));
     CKR(c->grange.ensure((size_t)n * sizeof(uint16_t)));
+    CKR(c->gtop.ensure((size_t)n * 8 * sizeof(uint32_t)));
     CKR(c->hist.ensure((size_t)n * 64 * sizeof(uint32_t)));
     CKR(c->cards_in.ensure((size_t)n * sizeof(double)));
     CKR(c->out_j.ensure((size_t)n * sizeof(double)));        // stored value_ of each header (-1 = recompute)
@@ -563,8 +566,11 @@ int load_chunk(selb200_ctx* c, int64_t g0, int64_t rows, const uint8_t* h_regs, 
     {   // bit-plane copy of the chunk for the union kernel
         const long long nblk = rows * (long long)(c->m >> 9);
         const int grid = (int)std::min<long long>((nblk + 7) / 8, (long long)c->sm_count * 16);
+        // per-eighth maxima next to the planes (the subset union kernel's per-step group limit)
+        CK(cudaMemsetAsync(c->gtop.as<uint32_t>() + (size_t)g0 * 8, 0, (size_t)rows * 8 * sizeof(uint32_t), s));
         k_planes_from_bytes<<<grid, 256, 0, s>>>(c->d_regs + (size_t)g0 * c->m, rows, c->m, c->chunk_regs,
-                                                 c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5));
+                                                 c->planes.as<uint32_t>() + (size_t)g0 * 6 * (c->m >> 5),
+                                                 c->m >= 4096 ? c->gtop.as<uint32_t>() + (size_t)g0 * 8 : nullptr);
         CK(cudaGetLastError());
     }
     L.rows_done += rows;
@@ -901,6 +907,8 @@ int selb200_create(int device, void* stream, selb200_ctx** out) {
     {   // SELB200_UNION: subsets (default) | planes (one-hot counting) | bytes — form of the union pass, read per context
         const char* e = getenv("SELB200_UNION");
         c->union_subsets = !(e && !strcmp(e, "planes"));
+        const char* t = getenv("SELB200_UNION_TOPS");
+        c->union_tops = !(t && !strcmp(t, "0"));
     }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
@@ -917,7 +925,7 @@ void selb200_destroy(selb200_ctx* c) {
     DevBuf* bufs[] = {&c->regs_own, &c->aux_sorted, &c->auxT, &c->cards_in, &c->e_sorted, &c->order_dev,
                       &c->lo, &c->hi, &c->tile_prefix, &c->tile_cb0, &c->tile_rc, &c->sigT, &c->cand, &c->pairs, &c->hist,
                       &c->counters, &c->cub_tmp, &c->cub_tmp2, &c->out_keys, &c->out_j, &c->out_keys2, &c->out_j2,
-                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->wide_list, &c->wide_flag, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
+                      &c->near_keys, &c->near_j, &c->tile_nt, &c->rb_pairs, &c->g_push, &c->g_merged, &c->row_cnt, &c->row_off, &c->sort_tmp, &c->sort_blocksum, &c->planes, &c->grange, &c->gtop, &c->wide_list, &c->wide_flag, &c->auxP, &c->agrange, &c->atail, &c->pk_buf, &c->join_buf, &c->join_items};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     selb200_gather_close(c);

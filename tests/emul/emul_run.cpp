@@ -99,7 +99,8 @@ int main(int argc, char** argv) {
     });
     const int chunk_regs = (int)std::min<size_t>(m, PL_CHUNK_REGS);
     std::vector<uint32_t> planes((size_t)n * 6 * (m >> 5), 0xA5A5A5A5u);
-    emul::launch(2, 256, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes.data()); });
+    std::vector<uint32_t> gtop((size_t)n * 8, 0u);          // per-eighth maxima, as the library's load step writes them
+    emul::launch(2, 256, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes.data(), m >= 4096 ? gtop.data() : nullptr); });
     lap("cards + planes");
     // device radix sort of (cardinality, index): distinct keys have one order; ties take the host path in the library
     std::vector<int32_t> order(n);
@@ -198,7 +199,8 @@ int main(int argc, char** argv) {
         emul::launch(3, 32, [&] {
             if (subsets)
                 k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi},
-                                                             wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH, wflag.data(), wepoch);
+                                                             wide.data(), meta.data() + M_WIDE, meta.data() + M_BATCH, wflag.data(), wepoch,
+                                                             m >= 16384 ? gtop.data() : nullptr);
             else
                 k_pair_hist_planes<EpiWriteHist>(planes.data(), m, chunk_regs, grange.data(), src, epi, wide.data(), meta.data() + M_WIDE,
                                                  meta.data() + M_BATCH, wflag.data(), wepoch);

@@ -157,6 +157,29 @@ int run_case(const Case& cs, uint64_t seed) {
               const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
               return (hi >> 3) > std::min(lo >> 3, 4) + 3;
           });
+    // ---- subset counting with the per-step group limit from the per-eighth maxima (m >= 16384: the library's default) ----
+    if (m >= 16384) {
+        std::vector<uint32_t> gtop((size_t)n * 8, 0u), planes2((size_t)n * 6 * (m >> 5), 0x5A5A5A5Au);
+        emul::launch(2, [&] { k_planes_from_bytes(regs.data(), n, m, chunk_regs, planes2.data(), gtop.data()); });
+        if (planes2 != planes) { printf("  %s: planes differ when the tops are written too\n", cs.name); ++bad; }
+        for (int g = 0; g < n; ++g)
+            for (int j = 0; j < 8; ++j) {
+                uint32_t mx = 0;
+                for (size_t r = (size_t)j * (m / 8); r < (size_t)(j + 1) * (m / 8); ++r) mx = std::max<uint32_t>(mx, regs[(size_t)g * m + r]);
+                if (gtop[(size_t)g * 8 + j] != mx) { printf("  %s: gtop[%d][%d] = %u, want %u\n", cs.name, g, j, gtop[(size_t)g * 8 + j], mx); ++bad; }
+            }
+        check("subtops",
+              [&](EpiWriteHist epi, uint32_t* wide, unsigned long long* counters) {
+                  emul::launch(cs.grid, [&] {
+                      k_pair_hist_planes<EpiSubsets<EpiWriteHist>>(planes.data(), m, chunk_regs, grange.data(), src, EpiSubsets<EpiWriteHist>{epi}, wide, counters, counters + 1,
+                                                                   nullptr, 0u, gtop.data());
+                  });
+              },
+              [&](uint32_t a, uint32_t b) {
+                  const int lo = std::max(grange[a] & 0xff, grange[b] & 0xff), hi = std::max(grange[a] >> 8, grange[b] >> 8);
+                  return (hi >> 3) > std::min(lo >> 3, 4) + 3;
+              });
+    }
     return bad;
 }
 
@@ -198,6 +221,7 @@ int main(int argc, char** argv) {
         {"tiny sketches p9", 9, {100, 120, 140, 90, 300}, 0.7, 56, 2},
         {"p12 one chunk", 12, {200, 220, 180}, 0.8, 53, 1},
         {"p16 sixteen chunks", 16, {250, 260}, 0.9, 49, 1},
+        {"p15 eight chunks", 15, {120, 260, 700}, 0.6, 50, 2},      // an eighth of the sketch is one chunk, two steps
         {"empty and sparse p14", 14, {0, 0.01, 0.5, 3}, 0.0, 51, 2},
         {"saturated values p14", 14, {1e12, 2e12, 200}, 0.5, 51, 1},
         // genome 0 has another base: its 25 pairs come first in the list, so with batches of 16 a whole batch is wide

@@ -22,8 +22,10 @@ def test_union_kernels_on_the_warp_emulator(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "all identical" in r.stdout
-    assert r.stdout.count(" ok") >= 28 and "FAIL" not in r.stdout          # 14 cases x (planes, subsets)
-    assert r.stdout.count(" subsets ") == 14
+    assert r.stdout.count(" ok") >= 30 and "FAIL" not in r.stdout          # 15 cases x (planes, subsets)
+    assert r.stdout.count(" subsets ") == 15
+    # subset counting with the per-step group limit (per-eighth maxima), every case with 2^14 registers or more
+    assert r.stdout.count(" subtops ") == 10
 
 
 _MUTATIONS = [
