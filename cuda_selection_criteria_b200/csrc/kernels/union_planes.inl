@@ -343,8 +343,13 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     const long long npairs = src.count();
     // batch size: 32 pairs when there is plenty of work, fewer (down to 4) when the list is short, so that
     // every warp still gets several batches and the dynamic claiming can balance the tail
-    int bsz = 32;
-    while (bsz > 4 && npairs < (long long)bsz * gridDim.x * 4) bsz >>= 1;
+    // Guided claims: a batch is 1/(PL_GUIDE x warps) of the pairs still unclaimed, between 4 and 32 — whole batches of 32
+    // while there is plenty of work (the descriptor loads are paid once per batch), small ones towards the end, so that
+    // the warps finish within a few pairs of one another (a pair is 6 us of a warp's time, a batch of 32 a seventh of the
+    // whole kernel at n = 100k: with fixed batches the last ones left most warps idle for half a batch on average).
+#ifndef PL_GUIDE
+#define PL_GUIDE 2
+#endif
 
     // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
     uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
@@ -357,10 +362,16 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
     int filled = -1;
 
     auto fill = [&](int k) {
-        long long bidx = 0;
-        if (lane == 0) bidx = (long long)atomicAdd(batch_counter, 1ull);
-        bidx = __shfl_sync(FULL, bidx, 0);
-        const long long pi = bidx * bsz + lane;
+        long long start = 0;
+        int bsz = 0;
+        if (lane == 0) {
+            const long long left = npairs - (long long)*reinterpret_cast<volatile unsigned long long*>(batch_counter);
+            bsz = (int)max(4ll, min(32ll, left / ((long long)PL_GUIDE * gridDim.x)));
+            start = (long long)atomicAdd(batch_counter, (unsigned long long)bsz);
+        }
+        start = __shfl_sync(FULL, start, 0);
+        bsz = __shfl_sync(FULL, bsz, 0);
+        const long long pi = start + lane;
         bool ok = lane < bsz && pi < npairs;
         uint2 id = make_uint2(0u, 0u), rw = id;
         uint32_t gm = 0, tp = 0x00ffffffu;
@@ -397,8 +408,8 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
             }
         }
         const uint32_t msk = __ballot_sync(FULL, ok);
-        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; d_tp1 = tp; mask1 = msk; base1 = bidx * bsz; end1 = bidx * bsz >= npairs; }
-        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; d_tp0 = tp; mask0 = msk; base0 = bidx * bsz; end0 = bidx * bsz >= npairs; }
+        if (k & 1) { d_rx1 = rw.x; d_ry1 = rw.y; d_ix1 = id.x; d_iy1 = id.y; d_gm1 = gm; d_tp1 = tp; mask1 = msk; base1 = start; end1 = start >= npairs; }
+        else       { d_rx0 = rw.x; d_ry0 = rw.y; d_ix0 = id.x; d_iy0 = id.y; d_gm0 = gm; d_tp0 = tp; mask0 = msk; base0 = start; end0 = start >= npairs; }
         filled = k;
     };
 
