@@ -503,6 +503,30 @@ def kernel_table(cfg: Cfg, st, mean, sm_clk_hz, n_sm, peak_hbm, n_shards=1):
     lop3 = union_lop3_per_pair()
     add("union", union_kernel_name(), mean("ms_union"), "int_alu", p_aux, lop3 * 32.0,
         f"{lop3:.0f} essential LOP3 per pair and lane (all value groups of the 32-value window active: upper bound) x 32 lanes")
+    if rows and rows[-1]["stage"] == "union" and union_kernel_name().endswith("<EpiSubsets>"):
+        # The subset kernel counts one mask of four with POPC (XU pipe, 16 lanes / clk / SM) and three with carry-save LOP3
+        # (ALU pipe, 64): both pipes carry about the same time, so both are stated — with every group of the window active
+        # (upper bound, the figure above) and with the groups the C4 workload executes (per-eighth limits, value range of
+        # the pairs: tests/emul/union_lop3_model.py on the same generator).  frac = the busier pipe on the EXECUTED counts.
+        e = rows[-1]
+        clk_per_pair = mean("ms_union") * 1e-3 * sm_clk_hz * n_sm / max(p_aux, 1)
+        pipes = {}
+        for name, rate, all_groups, executed in (("alu", INT_PEAK, lop3, UNION_EXECUTED["lop3"]), ("xu", XU_PEAK, UNION_ALL["popc"], UNION_EXECUTED["popc"])):
+            pipes[name] = {"rate_lane_ops_per_clk_sm": rate,
+                           "all_groups": {"ops_per_pair_lane": all_groups, "frac": all_groups * 32.0 / rate / clk_per_pair},
+                           "executed_c4": {"ops_per_pair_lane": executed, "frac": executed * 32.0 / rate / clk_per_pair}}
+        busier = max(pipes, key=lambda k: pipes[k]["executed_c4"]["frac"])
+        e["pipes"] = pipes
+        e["clk_per_pair_per_sm"] = clk_per_pair
+        if cfg.n == 100_000 and cfg.criterion == "smh_a":
+            e["frac_all_groups_alu"] = e["frac"]
+            e["frac"] = pipes[busier]["executed_c4"]["frac"]
+            e["achieved"] = e["frac"] * pipes[busier]["rate_lane_ops_per_clk_sm"]
+            e["peak"] = pipes[busier]["rate_lane_ops_per_clk_sm"]
+            e["unit"] = f"executed {busier}-pipe lane-ops/clk/SM"
+            e["def"] = (f"{pipes[busier]['executed_c4']['ops_per_pair_lane']:.0f} {'POPC' if busier == 'xu' else 'LOP3'} per pair and lane that the "
+                        f"C4 workload executes (tests/emul/union_lop3_model.py) x 32 lanes on the {busier} pipe "
+                        f"({pipes[busier]['rate_lane_ops_per_clk_sm']:.0f} lanes/clk/SM); `pipes` has both pipes, also with all groups active")
     add("estimate", "k_estimate_emit", mean("ms_estimate"), "hbm", p_aux, 256.0 + 16,
         "256 B histogram row + 16 B descriptor per aux-passing pair", "fp64-latency-bound: thread per histogram, Ertl MLE secant loop")
     add("sort", "k_rowsort_* + D2H", mean("ms_sort"), "hbm", max(p_out, 1), 16.0 * 4, "16 B per emitted pair, four passes",
@@ -517,9 +541,15 @@ def union_kernel_name():
 
 def union_lop3_per_pair():
     # essential LOP3 per pair and lane at p=14 (8 steps of 64 registers per lane): one-hot form 8 x (20 max + 16 decode +
-    # 4 groups x 34) = 1376; subset form 8 x (20 max + 8 selectors + 8 groups of four x 16) = 1248.  With the group masks of
-    # the C4 workload the kernels execute about 1200 and 905 (tests/emul/union_lop3_model.py).
-    return {"planes": 1376.0, "bytes": 0.0}.get(os.environ.get("SELB200_UNION", ""), 1248.0)
+    # 4 groups x 34) = 1376; subset form 8 x (20 max + 8 selectors + 8 groups of four x 14) = 1120 (one mask of four is
+    # counted with POPC, kernels/union_planes.inl PL_DIRECT).  With the group masks of the C4 workload the kernels execute
+    # about 1200 and 738 (tests/emul/union_lop3_model.py).
+    return {"planes": 1376.0, "bytes": 0.0}.get(os.environ.get("SELB200_UNION", ""), 1120.0)
+
+
+XU_PEAK = 16.0          # POPC lanes per clock per SM (tools/ubench/int_pipes.cu: 16)
+UNION_ALL = {"popc": 8 * 8 * 5 + 24.0}                 # all eight groups: 5 POPC per group and step, 24 in the epilogue
+UNION_EXECUTED = {"lop3": 738.0, "popc": 189.0 + 24.0}   # C4 pairs, tests/emul/union_lop3_model.py (4.73 groups per step)
 
 
 HLL_BOUND_LOP3 = 24.0 + 4 + 3 * 16      # pass A of the two-pass hll filter, per step of 64 auxiliary registers
@@ -674,8 +704,11 @@ def main():
     roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"],
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": ncu_traffic(dom["kernel"]), "launch_ms": dom["ms"],
                 "def": dom["def"],
-                "peak_source": ("alu pipe: 4 SMSPs x 16 lanes per clock (B300_MICROARCH.md 'alu-pipe rt_SMSP=2'; "
-                                "tools/ubench/int_pipes.cu measured 63 on this pool)" if dom["bound"] == "int_alu" else peak_src),
+                "peak_source": (("xu pipe (POPC): 4 SMSPs x 4 lanes per clock (tools/ubench/int_pipes.cu measured 16 on this pool)"
+                                 if "xu-pipe" in dom["unit"] else
+                                 "alu pipe: 4 SMSPs x 16 lanes per clock (B300_MICROARCH.md 'alu-pipe rt_SMSP=2'; "
+                                 "tools/ubench/int_pipes.cu measured 63 on this pool)") if dom["bound"] == "int_alu" else peak_src),
+                "pipes": dom.get("pipes"), "frac_all_groups_alu": dom.get("frac_all_groups_alu"),
                 "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": dom_alg_bytes,
                         "note": "SURVEY.md 8d algorithmic bytes / launch time; not the binding roof when frac > 1"},

@@ -44,10 +44,20 @@ def main():
     npl = np.where(np.minimum(lo >> 3, 4) == 0, 5, 6)
     steps = (1 << p) // 64 / 32                            # 64-register steps per lane and pair
     onehot, subsets = steps * (4 * npl + 16 + 34 * g8), steps * (4 * npl + 2 * g8 + 16 * g4)
+    # the kernel as shipped: one mask of four counted directly (PL_DIRECT=1: 14 LOP3 and 5 POPC per group of four and step)
+    # and, per 2048-register step, only the groups up to the larger of the two genomes' maxima over that eighth (gtop)
+    blk = R.reshape(n, 8, -1).max(2).astype(int)                                   # per-eighth maxima
+    top = np.maximum(blk[pa[:, 0]], blk[pa[:, 1]])                                 # [pairs][8]
+    g4b = (top >> 2) - (lo >> 2)[:, None] + 1
+    g8b = (top >> 3) - (lo >> 3)[:, None] + 1
+    shipped = (4 * npl[:, None] + 2 * g8b + 14 * g4b).sum(1) * steps / 8
+    shipped_popc = (5 * g4b).sum(1) * steps / 8
     print(f"n={n}: {len(pa)} pairs reach the union pass; value range lo {lo.mean():.2f} .. hi {hi.mean():.2f}, "
           f"8-groups {g8.mean():.2f}, 4-groups {g4.mean():.2f}")
     print(f"LOP3 per pair and lane: one-hot {onehot.mean():.0f}, subsets {subsets.mean():.0f} "
           f"(x{subsets.mean() / onehot.mean():.3f}); all four 8-groups: {steps * 172:.0f}")
+    print(f"shipped subset kernel (direct mask + per-eighth tops): LOP3 {shipped.mean():.0f}, POPC {shipped_popc.mean():.0f}, "
+          f"4-groups per step {g4b.mean():.2f}")
     print(f"POPC per pair and lane (loop): one-hot {(steps * 8 * g8).mean():.0f}, subsets {(steps * 4 * g4).mean():.0f}")
 
 
