@@ -16,8 +16,9 @@
 // POPC issues at 16 lanes/clk/SM on B200 (LOP3: 63), hence the carry-save adders.
 // The planes are staged into shared memory by cp.async.bulk (TMA) copies completing on mbarriers;
 // one warp per CTA, 16 CTAs per SM.
-// Pairs whose value range does not fit a 32-value window (never seen on real sketches) go to a
-// "wide" list and through the byte kernel.
+// Pairs whose value range does not fit a 32-value window (a register of 32 or more next to a smallest register below 8:
+// one genome in 1 700 of the bench workload has such a register, about 0.1 % of the pairs) go to a "wide" list and
+// through the byte kernel.
 // layout: genome g at planes + g * 6 * m/8 bytes; chunk c (PL_CHUNK_REGS registers, or m if smaller) holds its
 //         6 planes back to back: [chunk][plane][chunk_regs/32 words], bit r of word w = register 32w+r
 // ============================================================================

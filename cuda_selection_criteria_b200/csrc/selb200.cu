@@ -354,10 +354,10 @@ int launch_pair_hist(selb200_ctx* c, const uint8_t* regs, size_t m, int p, const
 }
 
 // bit-plane union pass over the run's pair list (+ the byte kernel on whatever landed in the wide list)
-// The plane kernel on the run stream; the byte kernel for the pairs it hands to the wide list on `wide_stream` (behind an
-// event of the plane kernel).  With another stream than the run stream the caller estimates the wide pairs there too and
-// joins afterwards: a wide pair costs the byte kernel 20 us whatever their number, which then overlaps the estimate of
-// everything else; the plane kernel stamps wide_flag[pair] = c->wide_epoch so that the main estimate leaves those rows alone.
+// The plane kernel on the run stream; the byte kernel for the pairs it hands to the wide list on `wide_stream` — by default
+// the run stream itself, so that one estimate launch behind it sees every row.  With another stream (SELB200_WIDE=side) the
+// caller estimates the wide pairs there too and joins afterwards; the plane kernel stamps wide_flag[pair] = c->wide_epoch so
+// that the main estimate leaves those rows alone (measured slower: the side chain runs behind the main estimate, not beside it).
 int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pairs, uint32_t* hist_out,
                             const unsigned long long* npairs_dev, unsigned long long* wide_count, int* launches,
                             bool counters_are_zero, cudaStream_t wide_stream = nullptr) {
@@ -427,6 +427,7 @@ int launch_pair_hist_planes(selb200_ctx* c, const uint2* pairs, int64_t max_pair
     SrcWide wsrc{pairs, c->order_dev.as<int32_t>(), c->wide_list.as<uint32_t>(), wide_count};
     if (c->m >= 512) {
         const int nbins = 64 - c->p + 2;
+        // (two, four or eight CTAs per SM: 22 us either way for the ~800 wide pairs of n = 100k — latency, not throughput)
         const int wgrid = (int)std::min<int64_t>((max_pairs + 1) / 2, (int64_t)c->sm_count * 2);
         if (nbins <= 52) k_pair_hist<52, SrcWide, EpiWriteHist><<<wgrid, 64, 0, wide_stream>>>(c->d_regs, c->m, c->m, wsrc, epi);
         else k_pair_hist<64, SrcWide, EpiWriteHist><<<wgrid, 64, 0, wide_stream>>>(c->d_regs, c->m, c->m, wsrc, epi);
@@ -1513,18 +1514,25 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                                      (int64_t)pair_lim, c->hist.as<uint32_t>(), d_cnt + M_PAIRS));
                 st.launches++;
             } else {
+                // SELB200_WIDE=side: the wide pairs' byte kernel and an estimate of their own on the side stream, the main
+                // estimate skipping the rows the plane kernel stamped.  Measured: the side chain (22 + 17 us) does not run
+                // beside the main estimate but behind it (0.138 against 0.099 ms for the estimate phase), so the default
+                // is the byte kernel on the run stream, behind the plane kernel, and one estimate over every pair.
+                static const bool wide_side = [] { const char* e = getenv("SELB200_WIDE"); return e && !strcmp(e, "side"); }();
                 CKR(launch_pair_hist_planes(c, c->pairs.as<uint2>(), (int64_t)pair_lim, c->hist.as<uint32_t>(),
-                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches, attempt == 0 && ri == 0, side));
-                // the wide pairs' estimate follows their histograms on the side stream
-                k_estimate_emit<<<c->sm_count, 128, 0, side>>>(
-                    c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->wide_list.as<uint32_t>(), d_cnt + M_WIDE, pair_lim,
-                    c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
-                    d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
-                    d_cnt + M_NEAR, near_cap);
-                CK(cudaGetLastError());
-                CK(cudaEventRecord(c->join_ev, side));
-                st.launches++;
-                wide_on_side = true;
+                                            d_cnt + M_PAIRS, d_cnt + M_WIDE, &st.launches, attempt == 0 && ri == 0,
+                                            wide_side ? side : nullptr));
+                if (wide_side) {
+                    k_estimate_emit<<<c->sm_count, 128, 0, side>>>(
+                        c->hist.as<uint32_t>(), c->pairs.as<uint2>(), c->wide_list.as<uint32_t>(), d_cnt + M_WIDE, pair_lim,
+                        c->e_sorted.as<unsigned long long>(), c->p, tau, c->out_keys.as<uint64_t>(), c->out_j.as<double>(),
+                        d_cnt + M_OUT, (unsigned long long)c->out_cap, c->near_keys.as<uint64_t>(), c->near_j.as<double>(),
+                        d_cnt + M_NEAR, near_cap);
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(c->join_ev, side));
+                    st.launches++;
+                    wide_on_side = true;
+                }
             }
             DBG_SYNC(c, "union histogram (planes + wide)");
             cudaEvent_t u1 = c->ev();
