@@ -72,5 +72,10 @@ def test_plane_kernels_equal_byte_kernels(gpu, tmp_path):
     assert onepass == by
     tiles = _run({"SELB200_SMHFILTER": "tiles"}, tmp_path)        # all-pairs tile filter + verify instead of the equality join
     assert tiles == by
+    # the subset union kernel without its per-step group limit (per-eighth maxima), and the wide pairs on the side stream
+    notops = _run({"SELB200_UNION_TOPS": "0"}, tmp_path)
+    assert notops == by
+    side = _run({"SELB200_WIDE": "side"}, tmp_path)
+    assert side == by
     assert all(v[1] > 1000 for v in default.values())          # thousands of emitted pairs in every case
     assert default["duplicates"][1] > 1500 * 1499 // 2         # every pair of the 1501 identical genomes, and the rest

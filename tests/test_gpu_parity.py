@@ -205,7 +205,7 @@ def test_errors_are_loud(gpu):
 
 def test_other_primary_precisions(gpu):
     plan = synth.make_plan(300, 17)
-    for p in (10, 12, 16):
+    for p in (10, 12, 15, 16):      # 15, 16: an eighth of the sketch (the union kernel's per-step group limit) spans 2 / 4 steps
         regs = synth.hll(plan, p)
         r = run_gpu(regs, None, "cb", 0.9, gpu)
         o = O.select(regs, p, "cb", np.float32(0.9))
