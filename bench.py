@@ -296,19 +296,21 @@ class ReferenceLeg:
         if not (self.have_ref and os.path.exists(exe) and self.lines is not None):
             return None
         cmd = [exe] + ref_cmd(self.cfg, self.cores, self.cfg.tau)[1:]
-        walls, out, err = [], b"", None
+        walls, out, err, phases = [], b"", None, []
         for _ in range(runs):
             t0 = time.perf_counter()
-            r = subprocess.run(cmd, cwd=self.td, capture_output=True)
+            r = subprocess.run(cmd + ["-g"], cwd=self.td, capture_output=True)     # -g: phase times on stderr, stdout unchanged
             walls.append(round(time.perf_counter() - t0, 3))
             if r.returncode != 0:
                 err = f"exit {r.returncode}: " + r.stderr.decode(errors="replace")[-200:]
                 break
             out = r.stdout
+            phases += [ln[len("selb200: "):] for ln in r.stderr.decode(errors="replace").splitlines() if ln.startswith("selb200: host ms")]
         got = out.decode().splitlines()
         return {"cmd": "cuda_selection_criteria_b200/bin/selection " + " ".join(cmd[1:]), "wall_s": walls,
                 "reference_cmd": "oracle/_ref/selection " + " ".join(cmd[1:]), "lines": len(got),
                 "stdout_identical_to_reference": err is None and got == self.lines, "stdout_sha256_16": lines_sha(got)[:16],
+                "phases": phases,
                 "error": err}
 
     def drop_files(self):

@@ -14,6 +14,7 @@
 // The device work is entirely behind selb200_load_host / selb200_run; this file only parses
 // flags, gunzips sketches (zlib, OpenMP over files) and formats lines.
 #include <getopt.h>
+#include <chrono>
 #include <omp.h>
 #include <zlib.h>
 
@@ -162,8 +163,15 @@ int main(int argc, char* argv[]) {
                                  : aux_kind == SELB200_AUX_HLL ? ".hll_" + std::to_string(p_aux) : "";
 
     // ---- device context first: the sketches are decoded straight into its pinned staging slots ----
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     selb200_ctx* ctx = nullptr;
     if (selb200_create(0, nullptr, &ctx) != SELB200_OK) die("create");
+    const double ms_create = since(t_start);
+    const auto t_load = std::chrono::steady_clock::now();
+    double ms_gunzip = 0.;
 
     // ---- load (OpenMP over the files of a chunk, like selection.cpp:241-249); the device copy,
     // validation, histogram and cardinality of chunk c run while chunk c+1 is being gunzipped ----
@@ -182,6 +190,7 @@ int main(int argc, char* argv[]) {
         void* A = nullptr;
         if (selb200_load_acquire(ctx, g0, count, &R, &S, &A) != SELB200_OK) die("load");
         std::string load_error;
+        const auto t_gz = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic)
         for (int64_t i = 0; i < count; ++i) {
             try {
@@ -198,10 +207,13 @@ int main(int argc, char* argv[]) {
                 if (load_error.empty()) load_error = e.what();
             }
         }
+        ms_gunzip += since(t_gz);
         if (!load_error.empty()) throw std::runtime_error(load_error);   // uncaught, like the reference
         if (selb200_load_commit(ctx) != SELB200_OK) die("load");
     }
     if (selb200_load_end(ctx) != SELB200_OK) die("load");
+    const double ms_load = since(t_load);
+    const auto t_run = std::chrono::steady_clock::now();
     selb200_params prm;
     selb200_default_params(&prm);
     prm.tau = threshold;
@@ -222,6 +234,8 @@ int main(int argc, char* argv[]) {
     std::vector<double> rj((size_t)cnt);
     if (selb200_copy_results(ctx, cnt, ri.data(), rk.data(), rj.data()) != SELB200_OK) die("results");
     if (selb200_get_order(ctx, nullptr, order.data()) != SELB200_OK) die("order");
+    const double ms_run = since(t_run);
+    const auto t_print = std::chrono::steady_clock::now();
 
     std::string out;
     out.reserve((size_t)cnt * 96);
@@ -237,6 +251,10 @@ int main(int argc, char* argv[]) {
 #endif
     }
     std::cout << out;
+    std::cout.flush();
+    if (verbose)
+        fprintf(stderr, "selb200: host ms: create %.0f load %.0f (gunzip into pinned slots %.0f, %u threads) run+fetch %.1f print %.1f "
+                        "total %.0f\n", ms_create, ms_load, ms_gunzip, threads, ms_run, since(t_print), since(t_start));
     if (verbose)
         fprintf(stderr, "selb200: n=%lld pairs=%lld P_cb=%lld P_aux=%lld P_out=%lld near=%lld | bands x rows %dx%d | "
                         "device ms: bounds %.3f filter %.3f verify %.3f union %.3f estimate %.3f sort %.3f total %.3f\n",
