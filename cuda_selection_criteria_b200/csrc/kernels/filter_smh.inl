@@ -288,7 +288,8 @@ k_smh_verify(const uint64_t* __restrict__ aux_sorted, const uint32_t* __restrict
 //                     k_smh_verify, so P_aux is the reference's.
 // (First version: stable radix sort of (key, position) + galloping search for the followers: 86 + 56 us at n = 100k
 // against 8 + 5 + 40 for scan, scatter and this expansion.)
-// Shards: buckets and items are replicated, the handler of a pair is the shard (i + k) mod n_shards (disjoint, balanced).
+// Shards: keys and buckets are replicated (0.06 ms at n = 100k), expansion and item walk cover the shard's own rows
+// (i mod n_shards == shard): they divide by the shard count.
 // ============================================================================
 __global__ void __launch_bounds__(256)
 k_smh_sigkeys(const uint64_t* __restrict__ aux_sorted, long long n, int m_aux, int n_rows, int n_bands, int nbw, int sbits,
@@ -329,14 +330,25 @@ k_smh_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ra
 __global__ void __launch_bounds__(256)
 k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ bucket_off, const uint32_t* __restrict__ members,
                   long long e0, long long e1, int n_bands, int sbits, const int32_t* __restrict__ lo, const int32_t* __restrict__ hi,
-                  uint4* __restrict__ items, unsigned long long* __restrict__ item_count, unsigned long long item_cap) {
+                  uint4* __restrict__ items, unsigned long long* __restrict__ item_count, unsigned long long item_cap,
+                  int shard = 0, int n_shards = 1, long long n = 0) {
+    // Shards: a pair belongs to the shard of its ROW, i mod n_shards — this shard expands the elements of its own rows only
+    // (rows shard, shard + n_shards, ...: the walk below runs over that compact sequence, 16 bands of two rows to a warp),
+    // so expansion, items and item walk all divide by the shard count; rows are in cardinality order, cluster mates sit next
+    // to one another, and dealing them round-robin balances the pairs.  n: number of genomes (only read when n_shards > 1).
     const int lane = threadIdx.x & 31;
-    for (long long eb = e0 + (blockIdx.x * (long long)blockDim.x + threadIdx.x - lane); eb < e1; eb += (long long)gridDim.x * blockDim.x) {
-        const long long e = eb + lane;
+    const long long t_end = n_shards > 1 ? ((n - shard + n_shards - 1) / n_shards) * n_bands : e1 - e0;
+    for (long long tb = blockIdx.x * (long long)blockDim.x + threadIdx.x - lane; tb < t_end; tb += (long long)gridDim.x * blockDim.x) {
+        const long long t = tb + lane;
+        long long e = e0 + t;                            // one shard: the elements of [e0, e1) in order
+        if (n_shards > 1) {
+            const long long li = t / n_bands;
+            e = ((long long)shard + li * n_shards) * n_bands + (t - li * n_bands);
+        }
         unsigned long long c = 0;
         uint32_t key = 0, a = 0, b = 0;
         int i = 0, hi_i = -1;
-        if (e < e1) {
+        if (t < t_end && e >= e0 && e < e1) {
             key = keys[e];
             a = bucket_off[key]; b = bucket_off[key + 1];
             if (b - a > 1u) {
@@ -376,7 +388,7 @@ k_smh_join_expand(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
 __global__ void __launch_bounds__(256)
 k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict__ item_count, unsigned long long item_cap,
            const uint32_t* __restrict__ sigG, int nbw, int sbits, const uint64_t* __restrict__ aux_sorted, int m_aux, int n_rows, int n_bands,
-           int shard, int n_shards, uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
+           uint2* __restrict__ pairs, unsigned long long* __restrict__ pair_count,
            unsigned long long pair_cap, unsigned long long* __restrict__ cand_count, unsigned long long* __restrict__ item_max) {
     const unsigned long long n_items = min(*item_count, item_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(item_max, *item_count);     // the host grows the list and redoes the pass if it overflowed
@@ -393,7 +405,7 @@ k_smh_join(const uint4* __restrict__ items, const unsigned long long* __restrict
             const uint4 it = __ldg(items + w);
             i = (int)it.x; k = (int)it.y;
             const int bnd = (int)it.z;
-            if (n_shards <= 1 || (int)(((unsigned)i + (unsigned)k) % (unsigned)n_shards) == shard) {
+            {   // (every item of the list is this shard's: the expansion only wrote the items of its own rows)
                 const uint32_t* si = sigG + (size_t)i * nbw;
                 const uint32_t* sk = sigG + (size_t)k * nbw;
                 // an earlier band with equal KEYS (the top sbits of the signatures: what the buckets are made of, so an item

@@ -67,14 +67,16 @@ int hll_filter_mode() {
 }
 
 // SELB200_SMHFILTER=tiles | join (read once per process) forces the all-pairs tile filter + verify, or the equality join.
-// Default: by shard count.  Keys, sort and expansion of the join are the same 0.17 ms on every shard (only the walk
-// divides), the tile filter divides as a whole (0.59 ms / shards + 0.03): the join wins below four shards.
+// Default: the join at every shard count.  Its keys and buckets are the same 0.06 ms on every shard, expansion and item walk
+// divide (a shard expands its own rows); the tile filter divides as a whole (0.59 ms / shards + 0.05 for signatures and
+// verify).  (While the expansion was replicated too — 0.15 ms on every shard — the tile filter won from four shards on.)
 bool smh_join_enabled(int n_shards) {
     static const int mode = [] {
         const char* e = getenv("SELB200_SMHFILTER");
         return !e ? 0 : !strcmp(e, "tiles") ? 1 : !strcmp(e, "join") ? 2 : 0;
     }();
-    return mode == 2 || (mode == 0 && n_shards < 4);
+    (void)n_shards;
+    return mode != 1;
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -1420,14 +1422,15 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
                 const uint32_t *j_keys = jk, *j_memb = jk + 2 * jn_keys, *j_sig = jk + 3 * jn_keys;
                 const uint32_t* j_off = j_sig + (size_t)n * n_words + (j_buckets + 1);
                 CK(cudaMemsetAsync(d_cnt + M_ITEMS, 0, 8, s));
-                const int grid = (int)std::max<long long>(1, std::min<long long>((s1 - s0 + 255) / 256, (long long)c->sm_count * 16));
+                const long long j_elems = n_shards > 1 ? (jn_keys + n_shards - 1) / n_shards + n_bands : s1 - s0;
+                const int grid = (int)std::max<long long>(1, std::min<long long>((j_elems + 255) / 256, (long long)c->sm_count * 16));
                 k_smh_join_expand<<<grid, 256, 0, s>>>(j_keys, j_off, j_memb, s0, s1, n_bands, j_sbits, c->lo.as<int32_t>(),
                                                        c->hi.as<int32_t>(), c->join_items.as<uint4>(), d_cnt + M_ITEMS,
-                                                       (unsigned long long)c->join_item_cap);
+                                                       (unsigned long long)c->join_item_cap, prm->shard, n_shards, (long long)n);
                 CK(cudaGetLastError());
                 k_smh_join<<<c->sm_count * 16, 256, 0, s>>>(c->join_items.as<uint4>(), d_cnt + M_ITEMS, (unsigned long long)c->join_item_cap,
                                                             j_sig, n_words, j_sbits, c->aux_sorted.as<uint64_t>(), c->aux_len, n_rows,
-                                                            n_bands, prm->shard, n_shards, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
+                                                            n_bands, c->pairs.as<uint2>(), d_cnt + M_PAIRS,
                                                             (unsigned long long)PAIR_CAP, d_cnt + M_CAND, d_cnt + M_ITEMS_MAX);
                 st.launches += 1;
             } else if (crit == SELB200_CRIT_SMH_A) {

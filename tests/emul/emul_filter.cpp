@@ -93,12 +93,12 @@ int main(int argc, char** argv) {
             meta[M_ITEMS] = 0;
             emul::launch(2, 256, [&] {
                 k_smh_join_expand(jkeys.data(), boff.data(), members.data(), 0, nk, n_bands, sbits, lo.data(), hi.data(), items.data(),
-                                  meta.data() + M_ITEMS, item_cap);
+                                  meta.data() + M_ITEMS, item_cap, shard, n_shards, (long long)n);
             });
             if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(fgrid, 256, [&] {
                 k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, sbits, aux.data(), m_aux, n_rows, n_bands,
-                           shard, n_shards, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
+                           pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         } else {
         const TileWalk tw{tile_rc.data(), meta.data(), tile_cap, shard, n_shards, 0, INT32_MAX};

@@ -165,7 +165,7 @@ int main(int argc, char** argv) {
             if (meta[M_ITEMS] > item_cap) { fprintf(stderr, "item list overflow\n"); return 3; }
             emul::launch(part ? 3 : 2, 256, [&] {
                 k_smh_join(items.data(), meta.data() + M_ITEMS, item_cap, sigG.data(), n_words, sbits, aux_sorted.data(), m_aux, n_rows, n_bands,
-                           0, 1, pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
+                           pairs.data(), meta.data() + M_PAIRS, cap, meta.data() + M_CAND, meta.data() + M_ITEMS_MAX);
             });
         }
     } else {
