@@ -351,6 +351,9 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
 #ifndef PL_GUIDE
 #define PL_GUIDE 2
 #endif
+#ifndef PL_BATCH_MAX
+#define PL_BATCH_MAX 32      // measured: cap 16 1.365 ms, cap 8 1.383 against 1.356 (plane + byte kernel); PL_GUIDE 3: 1.358
+#endif
 
     // two descriptor sets (batch k lives in set k&1); per lane: one pair of the batch
     uint32_t d_rx0 = 0, d_ry0 = 0, d_ix0 = 0, d_iy0 = 0, d_gm0 = 0, d_rx1 = 0, d_ry1 = 0, d_ix1 = 0, d_iy1 = 0, d_gm1 = 0;
@@ -367,7 +370,7 @@ k_pair_hist_planes(const uint32_t* __restrict__ planes, size_t m, int chunk_regs
         int bsz = 0;
         if (lane == 0) {
             const long long left = npairs - (long long)*reinterpret_cast<volatile unsigned long long*>(batch_counter);
-            bsz = (int)max(4ll, min(32ll, left / ((long long)PL_GUIDE * gridDim.x)));
+            bsz = (int)max(4ll, min((long long)PL_BATCH_MAX, left / ((long long)PL_GUIDE * gridDim.x)));
             start = (long long)atomicAdd(batch_counter, (unsigned long long)bsz);
         }
         start = __shfl_sync(FULL, start, 0);
