@@ -230,8 +230,9 @@ struct selb200_ctx {
     // device-built tile list
     DevBuf tile_nt, rb_pairs;
     int64_t tile_cap = 0;
-    std::vector<int32_t> h_tprefix;
-    std::vector<unsigned long long> h_rb_pairs;
+    // pinned: tile prefix (nrb + 1 x i32) and pairs per row block (nrb x u64) of a sharded run (the shard's share of the band)
+    void* h_band = nullptr;
+    size_t h_band_cap = 0;
     // peer-memory gather (selb200_gather_*)
     struct Gather {
         bool attached = false, is_root = false, mapped = false;
@@ -934,6 +935,7 @@ void selb200_destroy(selb200_ctx* c) {
     selb200_gather_close(c);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_snap) cudaFreeHost(c->h_snap);
+    if (c->h_band) cudaFreeHost(c->h_band);
     for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->h2d_evs) if (e) cudaEventDestroy(e);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -1285,8 +1287,13 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     if (!c->h_snap) CK(cudaMallocHost(&c->h_snap, (SNAP_MAX * 4 + M_WORDS) * sizeof(unsigned long long)));
     unsigned long long* h_fin = c->h_snap + SNAP_MAX * 4;     // the final meta[] block
     std::memset(h_fin, 0, M_WORDS * sizeof(unsigned long long));
-    c->h_tprefix.resize((size_t)nrb + 1);
-    c->h_rb_pairs.resize((size_t)nrb);
+    // a sharded run reports its share of the CB band (stats.pairs_cb_shard) from two small tables of the bounds step; one
+    // shard owns the whole band and copies nothing (the two copies went to pageable memory before: staged by the driver,
+    // 15 us on the critical path of every run)
+    const size_t band_off = (((size_t)nrb + 1) * 4 + 7) & ~(size_t)7;
+    if (n_shards > 1) CKR(pinned_ensure(&c->h_band, &c->h_band_cap, band_off + (size_t)nrb * 8));
+    int32_t* const h_tprefix = static_cast<int32_t*>(c->h_band);
+    unsigned long long* const h_rb_pairs = n_shards > 1 ? reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(c->h_band) + band_off) : nullptr;
     const int launches_fixed = st.launches;
     GatherZone gz{};
     if (gather) {
@@ -1583,8 +1590,10 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
             }
         }
         CK(cudaMemcpyAsync(h_fin, d_cnt, M_WORDS * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(c->h_tprefix.data(), c->tile_prefix.p, ((size_t)nrb + 1) * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(c->h_rb_pairs.data(), c->rb_pairs.p, (size_t)nrb * 8, cudaMemcpyDeviceToHost, s));
+        if (n_shards > 1) {
+            CK(cudaMemcpyAsync(h_tprefix, c->tile_prefix.p, ((size_t)nrb + 1) * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_rb_pairs, c->rb_pairs.p, (size_t)nrb * 8, cudaMemcpyDeviceToHost, s));
+        }
         CK(cudaStreamSynchronize(s));
         // ---- overflow check ------------------------------------------------------------------
         tiles_total = (int64_t)h_fin[M_TILES];
@@ -1797,15 +1806,17 @@ int selb200_run(selb200_ctx* c, const selb200_params* prm, selb200_stats* st_out
     cudaEventElapsedTime(&st.ms_total, ev_begin, ev_end);
     // shard share of the CB band: a row block's pairs are apportioned by how many of its tiles
     // the shard owns
-    {
+    if (n_shards <= 1) {
+        st.pairs_cb_shard = st.pairs_cb;
+    } else {
         double acc = 0.;
         for (int rb = 0; rb < nrb; ++rb) {
-            const int a = c->h_tprefix[(size_t)rb], b = c->h_tprefix[(size_t)rb + 1];
+            const int a = h_tprefix[(size_t)rb], b = h_tprefix[(size_t)rb + 1];
             if (b <= a) continue;
             // tiles t in [a,b) with t % n_shards == shard
             const int first = a + ((prm->shard - a % n_shards) % n_shards + n_shards) % n_shards;
             const int mine = first < b ? (b - 1 - first) / n_shards + 1 : 0;
-            acc += (double)c->h_rb_pairs[(size_t)rb] * (double)mine / (double)(b - a);
+            acc += (double)h_rb_pairs[(size_t)rb] * (double)mine / (double)(b - a);
         }
         st.pairs_cb_shard = (int64_t)(acc + 0.5);
     }
